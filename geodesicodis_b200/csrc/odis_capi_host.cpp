@@ -1,0 +1,233 @@
+// C ABI, host-only groups (config, grid, mesh) of include/odis_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/odis_b200.h"
+#include "odis_config.h"
+#include "odis_error.h"
+#include "odis_gridgen.h"
+#include "odis_mesh.h"
+
+struct odis_config {
+    odis::Config cfg;
+    bool finalized = false;
+};
+struct odis_mesh {
+    odis::MeshTables t;
+};
+
+namespace odis {
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+}  // namespace odis
+
+using odis::fail;
+
+extern "C" {
+
+const char* odis_last_error(void) { return odis::g_last_error.c_str(); }
+const char* odis_version(void) { return "odis_b200 0.1 sm_100a"; }
+
+// ------------------------------------------------------------------ config ----
+int odis_config_create(odis_config** out) {
+    if (!out) return fail(ODIS_ERR_ARG, "out is NULL");
+    *out = new (std::nothrow) odis_config();
+    return *out ? ODIS_OK : fail(ODIS_ERR_ARG, "out of memory");
+}
+
+int odis_config_load(const char* run_dir, odis_config** out) {
+    if (!run_dir || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    odis_config* c = new (std::nothrow) odis_config();
+    if (!c) return fail(ODIS_ERR_ARG, "out of memory");
+    std::string err;
+    if (c->cfg.load(run_dir, err) != 0) {
+        delete c;
+        return fail(ODIS_ERR_IO, err);
+    }
+    if (c->cfg.finalize(err) != 0) {
+        delete c;
+        return fail(ODIS_ERR_CONFIG, err);
+    }
+    c->finalized = true;
+    *out = c;
+    return ODIS_OK;
+}
+
+int odis_config_set(odis_config* cfg, const char* key, const char* value_text) {
+    if (!cfg || !key || !value_text) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (cfg->cfg.set(key, value_text) != 0) return fail(ODIS_ERR_ARG, std::string("unknown input.in key: ") + key);
+    return ODIS_OK;
+}
+
+int odis_config_finalize(odis_config* cfg) {
+    if (!cfg) return fail(ODIS_ERR_ARG, "NULL argument");
+    std::string err;
+    if (cfg->cfg.finalize(err) != 0) return fail(ODIS_ERR_CONFIG, err);
+    cfg->finalized = true;
+    return ODIS_OK;
+}
+
+static const odis::ConfigEntry* lookup(const odis_config* cfg, const char* key, odis::ConfigEntry::Type t, int* rc) {
+    if (!cfg || !key) { *rc = fail(ODIS_ERR_ARG, "NULL argument"); return nullptr; }
+    const odis::ConfigEntry* e = cfg->cfg.find(key);
+    if (!e) { *rc = fail(ODIS_ERR_ARG, std::string("unknown input.in key: ") + key); return nullptr; }
+    if (e->type != t) { *rc = fail(ODIS_ERR_ARG, std::string("wrong type requested for key: ") + key); return nullptr; }
+    *rc = ODIS_OK;
+    return e;
+}
+
+int odis_config_get_double(const odis_config* cfg, const char* key, double* out) {
+    int rc;
+    const odis::ConfigEntry* e = lookup(cfg, key, odis::ConfigEntry::DOUBLE, &rc);
+    if (e && out) *out = e->d;
+    return rc;
+}
+int odis_config_get_int(const odis_config* cfg, const char* key, int32_t* out) {
+    int rc;
+    const odis::ConfigEntry* e = lookup(cfg, key, odis::ConfigEntry::INT, &rc);
+    if (e && out) *out = e->i;
+    return rc;
+}
+int odis_config_get_bool(const odis_config* cfg, const char* key, int32_t* out) {
+    int rc;
+    const odis::ConfigEntry* e = lookup(cfg, key, odis::ConfigEntry::BOOL, &rc);
+    if (e && out) *out = e->b ? 1 : 0;
+    return rc;
+}
+int odis_config_get_string(const odis_config* cfg, const char* key, char* buf, int32_t buflen) {
+    int rc;
+    const odis::ConfigEntry* e = lookup(cfg, key, odis::ConfigEntry::STRING, &rc);
+    if (e && buf && buflen > 0) {
+        std::strncpy(buf, e->s.c_str(), (size_t)buflen - 1);
+        buf[buflen - 1] = 0;
+    }
+    return rc;
+}
+int odis_config_get_enum(const odis_config* cfg, int32_t which, int32_t* out) {
+    if (!cfg || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (!cfg->finalized) return fail(ODIS_ERR_STATE, "odis_config_finalize has not been called");
+    switch (which) {
+        case 0: *out = cfg->cfg.fric_type; break;
+        case 1: *out = cfg->cfg.surface_type; break;
+        case 2: *out = cfg->cfg.solver_type; break;
+        case 3: *out = cfg->cfg.tide_type; break;
+        case 4: *out = cfg->cfg.initial_condition; break;
+        default: return fail(ODIS_ERR_ARG, "which must be 0..4");
+    }
+    return ODIS_OK;
+}
+void odis_config_free(odis_config* cfg) { delete cfg; }
+
+int odis_quantise_time_step(double period, double target_dt, double* dt_out, int32_t* steps_out) {
+    if (!dt_out || !steps_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    int n = 0;
+    odis::quantise_time_step(period, target_dt, dt_out, &n);
+    *steps_out = n;
+    return ODIS_OK;
+}
+
+// ------------------------------------------------------------------ mesh ----
+static int build_from(const odis::GridFile& g, double radius, int threads, odis_mesh** out) {
+    odis_mesh* m = new (std::nothrow) odis_mesh();
+    if (!m) return fail(ODIS_ERR_ARG, "out of memory");
+    std::string err;
+    if (odis::build_mesh_tables(g, radius, m->t, err, threads) != 0) {
+        delete m;
+        return fail(ODIS_ERR_GRID, err);
+    }
+    *out = m;
+    return ODIS_OK;
+}
+
+int odis_mesh_from_file(const char* grid_path, double radius, int32_t threads, odis_mesh** out) {
+    if (!grid_path || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    odis::GridFile g;
+    std::string err;
+    if (odis::read_grid_file(grid_path, g, err) != 0) return fail(ODIS_ERR_IO, err);
+    return build_from(g, radius, threads, out);
+}
+
+int odis_mesh_from_arrays(int32_t n_cells, const double* node_pos_sph, const int32_t* node_friends,
+                          const double* centroid_pos_sph, double radius, int32_t threads, odis_mesh** out) {
+    if (!node_pos_sph || !node_friends || !centroid_pos_sph || !out || n_cells < 12) return fail(ODIS_ERR_ARG, "bad argument");
+    odis::GridFile g;
+    g.n_cells = n_cells;
+    g.node_pos_sph.assign(node_pos_sph, node_pos_sph + (size_t)n_cells * 2);
+    g.node_friends.assign(node_friends, node_friends + (size_t)n_cells * 6);
+    g.centroid_pos_sph.assign(centroid_pos_sph, centroid_pos_sph + (size_t)n_cells * 12);
+    return build_from(g, radius, threads, out);
+}
+
+int odis_mesh_get_view(const odis_mesh* mesh, odis_mesh_view* v) {
+    if (!mesh || !v) return fail(ODIS_ERR_ARG, "NULL argument");
+    const odis::MeshTables& t = mesh->t;
+    v->n_cells = t.n_cells; v->n_edges = t.n_edges; v->n_vertices = t.n_vertices; v->radius = t.radius;
+    v->node_pos_sph = t.node_pos_sph.data();
+    v->node_friends = t.node_friends.data();
+    v->centroid_pos_sph = t.centroid_pos_sph.data();
+    v->control_volume_surf_area_map = t.control_volume_surf_area_map.data();
+    v->faces = t.faces.data();
+    v->node_face_dir = t.node_face_dir.data();
+    v->vertexes = t.vertexes.data();
+    v->face_nodes = t.face_nodes.data();
+    v->face_vertexes = t.face_vertexes.data();
+    v->face_interp_friends = t.face_interp_friends.data();
+    v->face_interp_weights = t.face_interp_weights.data();
+    v->face_len = t.face_len.data();
+    v->face_node_dist = t.face_node_dist.data();
+    v->face_centre_m = t.face_centre_m.data();
+    v->face_centre_pos_sph = t.face_centre_pos_sph.data();
+    v->face_intercept_pos_sph = t.face_intercept_pos_sph.data();
+    v->face_area = t.face_area.data();
+    v->face_normal_vec_map = t.face_normal_vec_map.data();
+    v->vertex_pos_sph = t.vertex_pos_sph.data();
+    v->vertex_nodes = t.vertex_nodes.data();
+    v->vertex_R = t.vertex_R.data();
+    return ODIS_OK;
+}
+void odis_mesh_free(odis_mesh* mesh) { delete mesh; }
+
+// ------------------------------------------------------------------ grid ----
+int odis_grid_generate(int32_t level, int32_t* n_cells_out, double** node_pos_sph_out, int32_t** node_friends_out,
+                       double** centroid_pos_sph_out) {
+    if (!n_cells_out || !node_pos_sph_out || !node_friends_out || !centroid_pos_sph_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    odis::GridFile g;
+    std::string err;
+    if (odis::generate_icosahedral_grid(level, g, err) != 0) return fail(ODIS_ERR_ARG, err);
+    const size_t n = (size_t)g.n_cells;
+    double* pos = (double*)std::malloc(n * 2 * sizeof(double));
+    int32_t* fr = (int32_t*)std::malloc(n * 6 * sizeof(int32_t));
+    double* cen = (double*)std::malloc(n * 12 * sizeof(double));
+    if (!pos || !fr || !cen) {
+        std::free(pos); std::free(fr); std::free(cen);
+        return fail(ODIS_ERR_ARG, "out of memory");
+    }
+    std::memcpy(pos, g.node_pos_sph.data(), n * 2 * sizeof(double));
+    std::memcpy(fr, g.node_friends.data(), n * 6 * sizeof(int32_t));
+    std::memcpy(cen, g.centroid_pos_sph.data(), n * 12 * sizeof(double));
+    *n_cells_out = g.n_cells;
+    *node_pos_sph_out = pos; *node_friends_out = fr; *centroid_pos_sph_out = cen;
+    return ODIS_OK;
+}
+
+int odis_grid_write_file(const char* path, int32_t n_cells, const double* node_pos_sph, const int32_t* node_friends,
+                         const double* centroid_pos_sph) {
+    if (!path || !node_pos_sph || !node_friends || !centroid_pos_sph || n_cells < 12) return fail(ODIS_ERR_ARG, "bad argument");
+    odis::GridFile g;
+    g.n_cells = n_cells;
+    g.node_pos_sph.assign(node_pos_sph, node_pos_sph + (size_t)n_cells * 2);
+    g.node_friends.assign(node_friends, node_friends + (size_t)n_cells * 6);
+    g.centroid_pos_sph.assign(centroid_pos_sph, centroid_pos_sph + (size_t)n_cells * 12);
+    std::string err;
+    if (odis::write_grid_file(path, g, err) != 0) return fail(ODIS_ERR_IO, err);
+    return ODIS_OK;
+}
+
+void odis_free(void* p) { std::free(p); }
+
+}  // extern "C"

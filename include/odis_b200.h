@@ -1,0 +1,187 @@
+/* odis_b200.h — C ABI of the B200-native LTE time-step engine (drop-in for the GeodesicODIS hot path).
+ *
+ * The reference (hamishHay/GeodesicODIS) has no FFI or plugin interface; its boundary is the
+ * C++ call surface of one process: main() -> Globals -> Mesh -> solveODIS -> ab3Explicit and the
+ * free functions that loop calls. Every entry point below names the reference interface it
+ * replaces (paths are relative to the reference tree). All arguments are plain pointers, sizes and
+ * scalars; arrays are in the reference's own row-major layouts and numbering. The library owns
+ * all device memory and any internal renumbering. Functions return ODIS_OK (0) or a negative
+ * odis_status; odis_last_error() gives the message for the calling thread.
+ *
+ * There is no CPU fallback: entry points in the "solver" group fail with ODIS_ERR_CUDA when no
+ * CUDA device is usable. The "config", "grid" and "mesh" groups are host-only.
+ */
+#ifndef ODIS_B200_H
+#define ODIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum odis_status {
+    ODIS_OK = 0,
+    ODIS_ERR_ARG = -1,        /* bad argument / unknown key / size mismatch */
+    ODIS_ERR_IO = -2,         /* file missing or malformed */
+    ODIS_ERR_GRID = -3,       /* grid is not a usable closed icosahedral Voronoi grid */
+    ODIS_ERR_CONFIG = -4,     /* input.in value rejected (the reference would TerminateODIS) */
+    ODIS_ERR_CUDA = -5,       /* no device, launch or allocation failure */
+    ODIS_ERR_UNSUPPORTED = -6,/* configuration outside the LTE hot path */
+    ODIS_ERR_STATE = -7       /* call order violated (e.g. step before set_state) */
+} odis_status;
+
+const char* odis_last_error(void);
+/* library / build identification, e.g. "odis_b200 0.1 sm_100a" */
+const char* odis_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * config — replaces `new Globals(0)`: src/globals.cpp:35-323 (ctor), :325-477 (ReadGlobals),
+ * :479-571 (SetDefault) and applySurfaceBCs, src/boundaryConditions.cpp:7-399.
+ * Keys are the input.in key strings (src/globals.cpp:58-203), lower case.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct odis_config odis_config;
+
+/* Titan defaults only (Globals(1)). */
+int odis_config_create(odis_config** out);
+/* Defaults, then <run_dir>/input.in, then the derived values (period rounding, enums, surface BCs). */
+int odis_config_load(const char* run_dir, odis_config** out);
+/* Set one key from its input.in text form; call odis_config_finalize afterwards. */
+int odis_config_set(odis_config* cfg, const char* key, const char* value_text);
+int odis_config_finalize(odis_config* cfg);
+int odis_config_get_double(const odis_config* cfg, const char* key, double* out);
+int odis_config_get_int(const odis_config* cfg, const char* key, int32_t* out);
+int odis_config_get_bool(const odis_config* cfg, const char* key, int32_t* out);
+/* Copies at most buflen-1 bytes + NUL. */
+int odis_config_get_string(const odis_config* cfg, const char* key, char* buf, int32_t buflen);
+/* Enumerations after finalize, numbered as include/globals.h:45-80:
+ * which = 0 friction, 1 surface, 2 solver, 3 potential, 4 initial condition. */
+int odis_config_get_enum(const odis_config* cfg, int32_t which, int32_t* out);
+void odis_config_free(odis_config* cfg);
+
+/* Time-step quantisation of Mesh::CalcMaxTimeStep, src/mesh.cpp:1601-1618. */
+int odis_quantise_time_step(double period, double target_dt, double* dt_out, int32_t* steps_per_period_out);
+
+/* ------------------------------------------------------------------------------------------
+ * grid + mesh — replaces `new Mesh(...)`: src/mesh.cpp:32-197 (ctor), :4016-4101 (ReadMeshFile)
+ * and the table builders it calls (:436-506, :508-1154, :1384-1484, :1828-1867, :2122-2152).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct odis_mesh odis_mesh;
+
+/* Borrowed views of the mesh tables, reference names and layouts (include/mesh.h:77-187).
+ * Valid until odis_mesh_free. Integer tables are int32; pads are -1 (0 in face_interp_friends). */
+typedef struct odis_mesh_view {
+    int32_t n_cells, n_edges, n_vertices;
+    double radius;
+    const double* node_pos_sph;                 /* [N][2] lat, lon (rad) */
+    const int32_t* node_friends;                /* [N][6] */
+    const double* centroid_pos_sph;             /* [N][6][2] */
+    const double* control_volume_surf_area_map; /* [N] */
+    const int32_t* faces;                       /* [N][6] */
+    const int32_t* node_face_dir;               /* [N][6] */
+    const int32_t* vertexes;                    /* [N][6] */
+    const int32_t* face_nodes;                  /* [F][2] */
+    const int32_t* face_vertexes;               /* [F][2] */
+    const int32_t* face_interp_friends;         /* [F][10] */
+    const double* face_interp_weights;          /* [F][10] */
+    const double* face_len;                     /* [F] */
+    const double* face_node_dist;               /* [F] */
+    const double* face_centre_m;                /* [F][2] */
+    const double* face_centre_pos_sph;          /* [F][2] */
+    const double* face_intercept_pos_sph;       /* [F][2] */
+    const double* face_area;                    /* [F] */
+    const double* face_normal_vec_map;          /* [F][2] */
+    const double* vertex_pos_sph;               /* [V][2] */
+    const int32_t* vertex_nodes;                /* [V][3] */
+    const double* vertex_R;                     /* [V][3] */
+} odis_mesh_view;
+
+/* Read input_files/grid_l<L>.txt style file and build all tables for a sphere of `radius`.
+ * threads <= 0: OpenMP default. */
+int odis_mesh_from_file(const char* grid_path, double radius, int32_t threads, odis_mesh** out);
+/* Same, from already-parsed arrays (radians). */
+int odis_mesh_from_arrays(int32_t n_cells, const double* node_pos_sph, const int32_t* node_friends,
+                          const double* centroid_pos_sph, double radius, int32_t threads, odis_mesh** out);
+int odis_mesh_get_view(const odis_mesh* mesh, odis_mesh_view* view);
+void odis_mesh_free(odis_mesh* mesh);
+
+/* Synthetic icosahedral-bisection grid in the grid_l<L>.txt conventions (the reference ships only
+ * levels 3-6; input_files/grid_l7.txt, grid_l8.txt are listed in .MISSING_LARGE_BLOBS). `level`
+ * follows the reference's file-name convention: 10*4^(level-1)+2 cells
+ * (constants/gridConstants.h:19-32). Outputs are malloc'ed; release with odis_free. */
+int odis_grid_generate(int32_t level, int32_t* n_cells_out, double** node_pos_sph_out,
+                       int32_t** node_friends_out, double** centroid_pos_sph_out);
+int odis_grid_write_file(const char* path, int32_t n_cells, const double* node_pos_sph,
+                         const int32_t* node_friends, const double* centroid_pos_sph);
+void odis_free(void* p);
+
+/* ------------------------------------------------------------------------------------------
+ * solver — replaces the body of ab3Explicit, src/timeIntegrator.cpp:57-322, whose loop (:205-313)
+ * calls updateMomentum (src/updateMomentum.cpp:16-47), forcing (src/tidalPotentials.cpp:29-328),
+ * the drag/forcing-gradient SpMV (src/timeIntegrator.cpp:219), integrateAB3scalar
+ * (src/temporalOperators.cpp:17-68), updateEta (src/updateEta.cpp:7-44), interpolateVelocity
+ * (src/interpolation.cpp:26-62) and updateEnergy (src/energy.cpp:13-62).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct odis_solver odis_solver;
+
+typedef struct odis_params {
+    double g;               /* surface gravity                       globals->g            */
+    double h;               /* ocean thickness                       globals->h            */
+    double alpha;           /* linear drag coefficient               globals->alpha        */
+    double dt;              /* quantised time step                   globals->timeStep     */
+    double radius;          /* radius after applySurfaceBCs          globals->radius       */
+    double omega;           /* spin rate after period rounding       globals->angVel       */
+    double love_reduct;     /* tidal potential prefactor             globals->loveReduct   */
+    double ecc;             /* eccentricity                          globals->e            */
+    double obl;             /* obliquity (rad)                       globals->theta        */
+    double shell_thickness; /* added back to r in forcing for LID_*  tidalPotentials.cpp:50-53 */
+    double semimajor_axis;  /* PLANET forcing only                   globals->a            */
+    int32_t potential;      /* enum Potential, include/globals.h:60-76 */
+    int32_t friction;       /* enum Friction (only the diagnostic differs, energy.cpp:46-55) */
+    int32_t surface;        /* enum Surface */
+    int32_t init_load;      /* 1: AB3 uses the 3-level formula from step 0 (temporalOperators.cpp:36) */
+    int32_t reorder;        /* 1: locality (space-filling-curve) renumbering on device; 0: reference order */
+    int32_t block_threads;  /* 0 = default */
+    int32_t reserved[4];
+} odis_params;
+
+typedef enum odis_field {
+    ODIS_FIELD_VELOCITY = 0,      /* v_t0          [F]    normal velocity on edges               */
+    ODIS_FIELD_ETA = 1,           /* p_t0          [N]    surface displacement                   */
+    ODIS_FIELD_DVDT = 2,          /* dv_dt         [F][3] AB3 history, level 0 newest            */
+    ODIS_FIELD_DETADT = 3,        /* dp_dt         [N][3]                                        */
+    ODIS_FIELD_VELOCITY_EN = 4,   /* v_avg         [F][2] east, north components at edges        */
+    ODIS_FIELD_DISSIPATION = 5,   /* energy_diss   [F]    per-edge dissipated energy flux        */
+    ODIS_FIELD_POTENTIAL = 6      /* forcing_potential [N] at the time used by the last step     */
+} odis_field;
+
+/* Copies the mesh tables to device `device` (cudaSetDevice ordinal), builds the stencil tables and
+ * zero state. */
+int odis_create(const odis_mesh_view* mesh, const odis_params* params, int32_t device, odis_solver** out);
+/* Host -> device state in reference numbering. NULL pointers mean zeros. `iter` is the number of
+ * steps already taken (current_time = dt*iter, src/timeIntegrator.cpp:187,277). */
+int odis_set_state(odis_solver* s, const double* v, const double* eta, const double* dvdt /*[F][3]*/,
+                   const double* detadt /*[N][3]*/, int64_t iter);
+/* Advance nsteps time steps (asynchronous on the solver's stream; odis_get_* synchronise). */
+int odis_step(odis_solver* s, int32_t nsteps);
+/* As odis_step, bracketed by CUDA events on the solver's stream; returns elapsed device ms. */
+int odis_step_timed(odis_solver* s, int32_t nsteps, float* elapsed_ms_out);
+/* Device -> host, reference numbering and layout. */
+int odis_get_field(odis_solver* s, int32_t field, double* out);
+/* Area-mean dissipated energy flux after the last step (e_diss of updateEnergy, energy.cpp:60). */
+int odis_get_dissipation_avg(odis_solver* s, double* out);
+/* Per-step series of the same quantity for steps [first, first+count) counted from the last
+ * odis_set_state; entry k is the value after step k+1. */
+int odis_get_dissipation_series(odis_solver* s, int64_t first, int64_t count, double* out);
+int odis_get_iter(odis_solver* s, int64_t* iter_out);
+/* Bytes of device memory held, and the algorithmic HBM bytes one step moves. */
+int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* algorithmic_bytes_per_step_out);
+/* Number of kernel launches issued by this solver since creation. */
+int odis_get_launch_count(odis_solver* s, int64_t* launches_out);
+int odis_synchronize(odis_solver* s);
+void odis_destroy(odis_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODIS_B200_H */
