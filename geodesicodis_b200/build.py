@@ -1,0 +1,82 @@
+"""Builds geodesicodis_b200/libodis_b200.so in-tree: C++ host code (g++) + sm_100a CUDA kernels (nvcc).
+
+Flags that matter for parity:
+  * host:   -ffp-contract=off  — the mesh-table expressions must evaluate as written (the reference
+            oracle is built the same way, oracle/ref_build/Makefile), otherwise GCC's FMA fusion makes
+            table values depend on instruction scheduling;
+  * device: -fmad=false        — same reason for the time-step kernels (bit-for-bit agreement with the
+            CPU solver's operation order). The kernels are HBM-bound; FMA fusion buys nothing.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libodis_b200.so")
+
+HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp"]
+CUDA_SOURCES = ["odis_kernels.cu", "odis_engine.cu"]
+
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "--expt-relaxed-constexpr"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(CSRC)) + ["../build.py", "../../include/odis_b200.h"]:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode())
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if sources changed) and return the path of the shared library."""
+    os.makedirs(BUILD, exist_ok=True)
+    stamp = os.path.join(BUILD, "stamp.txt")
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    jobs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(BUILD, src + ".o")
+        jobs.append((["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj], obj))
+    for src in CUDA_SOURCES:
+        obj = os.path.join(BUILD, src + ".o")
+        extra = ["-Xptxas", "-v"] if verbose else []
+        jobs.append(([nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj], obj))
+    procs = [(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), cmd, obj) for cmd, obj in jobs]
+    for p, cmd, obj in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), out))
+        if verbose and out.strip():
+            print(out)
+        objs.append(obj)
+    link = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(link), r.stdout))
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

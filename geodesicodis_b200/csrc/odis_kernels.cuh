@@ -1,0 +1,96 @@
+// Device kernels of the LTE time step (sm_100a, FP64, built with -fmad=false).
+//
+// One reference time step (/root/reference/src/timeIntegrator.cpp:205-313) is two launches:
+//
+//   edge_step   for every edge e: tangential-velocity reconstruction of v^n over the 10-point
+//               TRiSK stencil — used both for the Coriolis term of dv/dt and for the dissipated
+//               energy of v^n —, pressure gradient from eta^n, linear drag, gradient of the tidal
+//               potential U(t_n + dt), Adams-Bashforth update, forward-Euler drag/forcing add.
+//               Replaces updateMomentum (updateMomentum.cpp:42), the drag/forcing SpMV
+//               (timeIntegrator.cpp:219), integrateAB3scalar (temporalOperators.cpp:36-65),
+//               timeIntegrator.cpp:242 and, for the previous step, interpolateVelocity
+//               (interpolation.cpp:31-59) + updateEnergy (energy.cpp:32-60).
+//   cell_step   for every cell i: divergence of v^{n+1} over its 5/6 edges, Adams-Bashforth update
+//               of eta, and the tidal potential for the next step. Replaces updateEta
+//               (updateEta.cpp:39), integrateAB3scalar and forcing (tidalPotentials.cpp:80-172).
+//
+// Floating point follows the reference's operation order so that v and eta can agree with the
+// CPU solver to the last bit: sums run in the reference's CSR column order (ascending reference
+// id — baked into the slot order of the stencil tables on the host), scalar*coefficient products
+// are formed before the multiply with the field, and FMA contraction is off.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace odis {
+
+constexpr int kStencil = 10;   // TRiSK tangential stencil width (9 beside pentagons)
+constexpr int kCellEdges = 6;  // edges per cell (5 for the 12 pentagons)
+
+// potential types handled on device; values follow enum Potential (include/globals.h:60-76)
+enum DevPotential : int { P_OBLIQ = 0, P_OBLIQ_WEST = 1, P_ECC = 5, P_FULL = 8, P_FULL2 = 9, P_NONE = 16 };
+
+// AB3 start-up modes (temporalOperators.cpp:36-65)
+enum Ab3Mode : int { AB3_FIRST = 0, AB3_SECOND = 1, AB3_FULL = 2 };
+
+struct StepScalars {          // per-step host-evaluated trigonometry (tidalPotentials.cpp:55-61)
+    double cosM, sinM, cos2M, sin2M, cos3M, cos4M;
+};
+
+struct EdgeTables {
+    int n_edges;
+    const int2* cells;        // [F] inner, outer cell (device numbering)
+    const double2* grad;      // [F] G_e,inner = -m_e0/d_e ; G_e,outer = +m_e1/d_e   (mesh.cpp:3076-3080)
+    const double* fcor;       // [F] (-2.0*Omega)*sin(lat_e)                          (mesh.cpp:2881)
+    const double* dist;       // [F] d_e = face_node_dist
+    const int* sid;           // [10][F] stencil edge ids, slot order = ascending reference id, -1 pad
+    const double* sw;         // [10][F] TRiSK weights w_ee' in the same slot order
+};
+
+struct CellTables {
+    int n_cells;
+    const int* eid;           // [6][N] edge ids, bit 31 set when the cell is the edge's outer cell; -1 pad
+    const double* area;       // [N] control_volume_surf_area_map
+    const double* trig;       // [8][N] cosLat sinLat cosLon sinLon cos2Lat sin2Lat cos2Lon sin2Lon   (mesh.cpp:2132-2142)
+    const double* trig_sq;    // [2][N] cos^2 lat, sin^2 lat                                           (mesh.cpp:2144-2145)
+};
+
+struct Physics {
+    double g, h, alpha, dt;
+    double area_sphere_inv;   // unused by kernels; 1/(4 pi r^2) applied on the host like energy.cpp:60
+    double factor, factor2;   // potential prefactors (tidalPotentials.cpp:84,106,120,135,160-162)
+    double ecc, obl;
+    int potential;
+    int friction;             // 0 linear, 1 quadratic (energy.cpp:30-56)
+};
+
+struct EdgeState {
+    const double2* vl_in;     // [F] {v^n, l_e}
+    double2* vl_out;          // [F] {v^{n+1}, l_e}
+    const double2* eu;        // [N] {eta^n, U(t_n+dt)}
+    double* h1;               // [F] dv/dt of step n-1
+    double* h2;               // [F] dv/dt of step n-2
+    double* block_partial;    // [gridDim.x] per-block sum of eps_e * A_e for v^n
+    unsigned int* ticket;     // last-block-done counter
+    double* energy_out;       // where the finished sum goes (series[iter])
+};
+
+struct CellState {
+    const double2* vl;        // [F] {v^{n+1}, l_e}
+    double2* eu;              // [N] in: {eta^n, .}  out: {eta^{n+1}, U(t_{n+1}+dt)}
+    double* h1;               // [N]
+    double* h2;               // [N]
+};
+
+void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, int block_threads,
+                      cudaStream_t stream);
+void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
+                      int update_eta, int block_threads, cudaStream_t stream);
+// Diagnostics / output fields of the current velocity (interpolation.cpp:31-59, energy.cpp:32-56):
+// v_avg [F][2] and energy_diss [F]; either pointer may be null. Also leaves sum(eps_e*A_e) in energy_out.
+void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double2* vl, const double2* normal,
+                             double2* v_avg, double* energy_diss, double* block_partial, unsigned int* ticket,
+                             double* energy_out, int block_threads, cudaStream_t stream);
+int edge_grid_blocks(int n_edges, int block_threads);
+
+}  // namespace odis
