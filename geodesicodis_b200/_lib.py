@@ -1,0 +1,100 @@
+"""ctypes binding of the C ABI declared in include/odis_b200.h (libodis_b200.so, built in-tree by
+geodesicodis_b200/build.py). There is no fallback: if the library is missing, loading raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libodis_b200.so")
+
+c_i32, c_i64, c_f64 = C.c_int32, C.c_int64, C.c_double
+P = C.POINTER
+
+MESH_VIEW_ARRAYS = [  # name, dtype code, (dim symbol, columns)
+    ("node_pos_sph", "d", ("N", 2)), ("node_friends", "i", ("N", 6)), ("centroid_pos_sph", "d", ("N", 12)),
+    ("control_volume_surf_area_map", "d", ("N", 1)), ("faces", "i", ("N", 6)), ("node_face_dir", "i", ("N", 6)),
+    ("vertexes", "i", ("N", 6)), ("face_nodes", "i", ("F", 2)), ("face_vertexes", "i", ("F", 2)),
+    ("face_interp_friends", "i", ("F", 10)), ("face_interp_weights", "d", ("F", 10)), ("face_len", "d", ("F", 1)),
+    ("face_node_dist", "d", ("F", 1)), ("face_centre_m", "d", ("F", 2)), ("face_centre_pos_sph", "d", ("F", 2)),
+    ("face_intercept_pos_sph", "d", ("F", 2)), ("face_area", "d", ("F", 1)), ("face_normal_vec_map", "d", ("F", 2)),
+    ("vertex_pos_sph", "d", ("V", 2)), ("vertex_nodes", "i", ("V", 3)), ("vertex_R", "d", ("V", 3)),
+]
+
+
+class MeshView(C.Structure):
+    _fields_ = [("n_cells", c_i32), ("n_edges", c_i32), ("n_vertices", c_i32), ("radius", c_f64)] + \
+               [(name, C.c_void_p) for name, _, _ in MESH_VIEW_ARRAYS]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, c_f64) for n in ("g", "h", "alpha", "dt", "radius", "omega", "love_reduct", "ecc", "obl",
+                                     "shell_thickness", "semimajor_axis")] + \
+               [(n, c_i32) for n in ("potential", "friction", "surface", "init_load", "reorder", "block_threads")] + \
+               [("reserved", c_i32 * 4)]
+
+
+# every symbol include/odis_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "odis_last_error": (C.c_char_p, []),
+    "odis_version": (C.c_char_p, []),
+    "odis_config_create": (C.c_int, [P(C.c_void_p)]),
+    "odis_config_load": (C.c_int, [C.c_char_p, P(C.c_void_p)]),
+    "odis_config_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "odis_config_finalize": (C.c_int, [C.c_void_p]),
+    "odis_config_get_double": (C.c_int, [C.c_void_p, C.c_char_p, P(c_f64)]),
+    "odis_config_get_int": (C.c_int, [C.c_void_p, C.c_char_p, P(c_i32)]),
+    "odis_config_get_bool": (C.c_int, [C.c_void_p, C.c_char_p, P(c_i32)]),
+    "odis_config_get_string": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, c_i32]),
+    "odis_config_get_enum": (C.c_int, [C.c_void_p, c_i32, P(c_i32)]),
+    "odis_config_free": (None, [C.c_void_p]),
+    "odis_quantise_time_step": (C.c_int, [c_f64, c_f64, P(c_f64), P(c_i32)]),
+    "odis_mesh_from_file": (C.c_int, [C.c_char_p, c_f64, c_i32, P(C.c_void_p)]),
+    "odis_mesh_from_arrays": (C.c_int, [c_i32, C.c_void_p, C.c_void_p, C.c_void_p, c_f64, c_i32, P(C.c_void_p)]),
+    "odis_mesh_get_view": (C.c_int, [C.c_void_p, P(MeshView)]),
+    "odis_mesh_free": (None, [C.c_void_p]),
+    "odis_grid_generate": (C.c_int, [c_i32, P(c_i32), P(P(c_f64)), P(P(c_i32)), P(P(c_f64))]),
+    "odis_grid_write_file": (C.c_int, [C.c_char_p, c_i32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "odis_free": (None, [C.c_void_p]),
+    "odis_create": (C.c_int, [P(MeshView), P(Params), c_i32, P(C.c_void_p)]),
+    "odis_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64]),
+    "odis_step": (C.c_int, [C.c_void_p, c_i32]),
+    "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
+    "odis_get_field": (C.c_int, [C.c_void_p, c_i32, C.c_void_p]),
+    "odis_get_dissipation_avg": (C.c_int, [C.c_void_p, P(c_f64)]),
+    "odis_get_dissipation_series": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p]),
+    "odis_get_iter": (C.c_int, [C.c_void_p, P(c_i64)]),
+    "odis_get_footprint": (C.c_int, [C.c_void_p, P(c_i64), P(c_i64)]),
+    "odis_get_launch_count": (C.c_int, [C.c_void_p, P(c_i64)]),
+    "odis_synchronize": (C.c_int, [C.c_void_p]),
+    "odis_destroy": (None, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class OdisError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"odis_b200 error {code}: {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -m geodesicodis_b200.build "
+                "or __graft_entry__.build()). geodesicodis_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here means the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise OdisError(rc, load().odis_last_error().decode(errors="replace"))

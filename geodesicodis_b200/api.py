@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's interface for the LTE path, over the C ABI.
+
+  reference (C++)                                   here
+  ------------------------------------------------  ---------------------------------------------
+  new Globals(0)            src/globals.cpp:35      Globals.load(run_dir)
+  globals->g.Value() ...    include/globalVar.h:91  Globals["surface gravity"] (input.in key strings)
+  new Mesh(globals, ...)    src/mesh.cpp:32         Mesh.from_file(path, radius) / Mesh.from_globals(g)
+  grid->face_nodes(i,k) ... include/mesh.h:154      Mesh.tables["face_nodes"][i, k]
+  ab3Explicit(globals,grid) src/timeIntegrator.cpp:57   Solver(mesh, params).step(n)  (device resident)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import MESH_VIEW_ARRAYS, MeshView, Params, check
+
+FIELD_VELOCITY, FIELD_ETA, FIELD_DVDT, FIELD_DETADT, FIELD_VELOCITY_EN, FIELD_DISSIPATION, FIELD_POTENTIAL = range(7)
+_FIELD_SHAPES = {0: ("F",), 1: ("N",), 2: ("F", 3), 3: ("N", 3), 4: ("F", 2), 5: ("F",), 6: ("N",)}
+
+# enum Potential / Surface / Friction names, include/globals.h:45-76
+POTENTIALS = ["OBLIQ", "OBLIQ_WEST", "OBLIQ_EAST", "ECC_RAD", "ECC_LIB", "ECC", "ECC_WEST", "ECC_EAST", "FULL", "FULL2",
+              "TOTAL", "ECC_W3", "OBLIQ_W3", "PLANET", "PLANET_OBL", "GENERAL", "NONE"]
+SURFACES = ["FREE", "FREE_LOADING", "LID_LOVE", "LID_MEMBR", "LID_NUM", "LID_INF"]
+FRICTIONS = ["LINEAR", "QUADRATIC"]
+
+
+class Globals:
+    """Parsed input.in (same keys as the reference, src/globals.cpp:58-203)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def load(cls, run_dir: str) -> "Globals":
+        h = C.c_void_p()
+        check(_lib.load().odis_config_load(os.fsencode(run_dir), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def defaults(cls, **overrides) -> "Globals":
+        """Titan defaults (Globals(1)) plus input.in-style overrides given as {key: text}; finalised."""
+        h = C.c_void_p()
+        check(_lib.load().odis_config_create(C.byref(h)))
+        g = cls(h)
+        for k, v in overrides.items():
+            g.set(k, v)
+        g.finalize()
+        return g
+
+    def set(self, key: str, value) -> None:
+        text = ("true" if value else "false") if isinstance(value, bool) else repr(value) if isinstance(value, float) else str(value)
+        check(_lib.load().odis_config_set(self._h, key.encode(), text.encode()))
+
+    def finalize(self) -> None:
+        check(_lib.load().odis_config_finalize(self._h))
+
+    def __getitem__(self, key: str):
+        lib = _lib.load()
+        d = C.c_double()
+        if lib.odis_config_get_double(self._h, key.encode(), C.byref(d)) == 0:
+            return d.value
+        i = C.c_int32()
+        if lib.odis_config_get_int(self._h, key.encode(), C.byref(i)) == 0:
+            return i.value
+        if lib.odis_config_get_bool(self._h, key.encode(), C.byref(i)) == 0:
+            return bool(i.value)
+        buf = C.create_string_buffer(1024)
+        check(lib.odis_config_get_string(self._h, key.encode(), buf, 1024))
+        return buf.value.decode()
+
+    def enum(self, which: int) -> int:
+        i = C.c_int32()
+        check(_lib.load().odis_config_get_enum(self._h, which, C.byref(i)))
+        return i.value
+
+    fric_type = property(lambda self: self.enum(0))
+    surface_type = property(lambda self: self.enum(1))
+    solver_type = property(lambda self: self.enum(2))
+    tide_type = property(lambda self: self.enum(3))
+    initial_condition = property(lambda self: self.enum(4))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.load().odis_config_free(self._h)
+            self._h = None
+
+
+def quantise_time_step(period: float, target_dt: float) -> tuple[float, int]:
+    """dt and steps per period as Mesh::CalcMaxTimeStep sets them (src/mesh.cpp:1601-1618)."""
+    dt, n = C.c_double(), C.c_int32()
+    check(_lib.load().odis_quantise_time_step(period, target_dt, C.byref(dt), C.byref(n)))
+    return dt.value, n.value
+
+
+class Mesh:
+    """C-grid tables (reference names, include/mesh.h:77-187) as numpy views into library memory."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.view = MeshView()
+        check(_lib.load().odis_mesh_get_view(self._h, C.byref(self.view)))
+        self.n_cells, self.n_edges, self.n_vertices = self.view.n_cells, self.view.n_edges, self.view.n_vertices
+        self.radius = self.view.radius
+        dims = {"N": self.n_cells, "F": self.n_edges, "V": self.n_vertices}
+        self.tables = {}
+        for name, code, (dim, cols) in MESH_VIEW_ARRAYS:
+            n = dims[dim]
+            ctype = C.c_double if code == "d" else C.c_int32
+            arr = np.ctypeslib.as_array(C.cast(getattr(self.view, name), C.POINTER(ctype)), shape=(n * cols,))
+            self.tables[name] = arr.reshape((n, cols)) if cols > 1 else arr
+            self.tables[name].flags.writeable = False
+
+    @classmethod
+    def from_file(cls, grid_path: str, radius: float, threads: int = 0) -> "Mesh":
+        h = C.c_void_p()
+        check(_lib.load().odis_mesh_from_file(os.fsencode(grid_path), radius, threads, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, node_pos_sph, node_friends, centroid_pos_sph, radius: float, threads: int = 0) -> "Mesh":
+        pos = np.ascontiguousarray(node_pos_sph, dtype=np.float64)
+        fr = np.ascontiguousarray(node_friends, dtype=np.int32)
+        cen = np.ascontiguousarray(centroid_pos_sph, dtype=np.float64)
+        h = C.c_void_p()
+        check(_lib.load().odis_mesh_from_arrays(pos.shape[0], pos.ctypes.data, fr.ctypes.data, cen.ctypes.data, radius, threads, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_globals(cls, g: Globals, run_dir: str, threads: int = 0) -> "Mesh":
+        """input_files/grid_l<L>.txt under run_dir, radius after the surface BCs (src/mesh.cpp:4023)."""
+        path = os.path.join(run_dir, "input_files", "grid_l%d.txt" % g["geodesic grid level"])
+        return cls.from_file(path, g["radius"], threads)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.tables = {}
+            _lib.load().odis_mesh_free(self._h)
+            self._h = None
+
+
+def generate_grid(level: int):
+    """Synthetic icosahedral-bisection grid, reference file-name level (10*4^(level-1)+2 cells).
+    Returns (node_pos_sph [N,2], node_friends [N,6], centroid_pos_sph [N,6,2]) in radians."""
+    lib = _lib.load()
+    n = C.c_int32()
+    pos, fr, cen = C.POINTER(C.c_double)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
+    check(lib.odis_grid_generate(level, C.byref(n), C.byref(pos), C.byref(fr), C.byref(cen)))
+    try:
+        N = n.value
+        a = np.ctypeslib.as_array(pos, shape=(N, 2)).copy()
+        b = np.ctypeslib.as_array(fr, shape=(N, 6)).copy()
+        c = np.ctypeslib.as_array(cen, shape=(N, 6, 2)).copy()
+    finally:
+        lib.odis_free(pos); lib.odis_free(fr); lib.odis_free(cen)
+    return a, b, c
+
+
+def write_grid_file(path: str, node_pos_sph, node_friends, centroid_pos_sph) -> None:
+    pos = np.ascontiguousarray(node_pos_sph, dtype=np.float64)
+    fr = np.ascontiguousarray(node_friends, dtype=np.int32)
+    cen = np.ascontiguousarray(centroid_pos_sph, dtype=np.float64)
+    check(_lib.load().odis_grid_write_file(os.fsencode(path), pos.shape[0], pos.ctypes.data, fr.ctypes.data, cen.ctypes.data))
+
+
+def params_from_globals(g: Globals, dt: float, reorder: bool = True) -> dict:
+    """The scalars ab3Explicit reads from Globals (src/timeIntegrator.cpp:116-128,198-201)."""
+    return dict(g=g["surface gravity"], h=g["ocean thickness"], alpha=g["friction coefficient"], dt=dt, radius=g["radius"],
+                omega=g["angular velocity"], love_reduct=g["love reduction factor"], ecc=g["eccentricity"], obl=g["obliquity"],
+                shell_thickness=g["shell thickness"], semimajor_axis=g["semimajor axis"], potential=g.tide_type,
+                friction=g.fric_type, surface=g.surface_type, init_load=int(g.initial_condition == 1), reorder=int(reorder))
+
+
+class Solver:
+    """Device-resident AB3 time stepper (replaces the body of ab3Explicit). Fields cross in reference numbering."""
+
+    def __init__(self, mesh: Mesh, params: dict, device: int = 0):
+        self.mesh = mesh
+        p = Params()
+        for k, v in params.items():
+            setattr(p, k, v)
+        self.params = p
+        self._h = C.c_void_p()
+        check(_lib.load().odis_create(C.byref(mesh.view), C.byref(p), device, C.byref(self._h)))
+        self.N, self.F = mesh.n_cells, mesh.n_edges
+        self._iter0 = 0
+
+    @property
+    def steps_since_state(self) -> int:
+        return self.iter - self._iter0
+
+    @staticmethod
+    def _ptr(a, n):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.size != n:
+            raise ValueError(f"array has {a.size} elements, expected {n}")
+        return a, a.ctypes.data
+
+    def set_state(self, v=None, eta=None, dvdt=None, detadt=None, iter: int = 0) -> None:
+        k = [self._ptr(v, self.F), self._ptr(eta, self.N), self._ptr(dvdt, self.F * 3), self._ptr(detadt, self.N * 3)]
+        check(_lib.load().odis_set_state(self._h, k[0][1], k[1][1], k[2][1], k[3][1], iter))
+        self._iter0 = iter
+
+    def step(self, nsteps: int = 1) -> None:
+        check(_lib.load().odis_step(self._h, nsteps))
+
+    def step_timed(self, nsteps: int) -> float:
+        ms = C.c_float()
+        check(_lib.load().odis_step_timed(self._h, nsteps, C.byref(ms)))
+        return ms.value
+
+    def field(self, fid: int) -> np.ndarray:
+        shape = tuple(self.F if d == "F" else self.N if d == "N" else d for d in _FIELD_SHAPES[fid])
+        out = np.empty(shape, dtype=np.float64)
+        check(_lib.load().odis_get_field(self._h, fid, out.ctypes.data))
+        return out
+
+    def dissipation_avg(self) -> float:
+        d = C.c_double()
+        check(_lib.load().odis_get_dissipation_avg(self._h, C.byref(d)))
+        return d.value
+
+    def dissipation_series(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        if count is None:
+            count = self.steps_since_state + 1 - first
+        out = np.empty(count, dtype=np.float64)
+        check(_lib.load().odis_get_dissipation_series(self._h, first, count, out.ctypes.data))
+        return out
+
+    @property
+    def iter(self) -> int:
+        i = C.c_int64()
+        check(_lib.load().odis_get_iter(self._h, C.byref(i)))
+        return i.value
+
+    def footprint(self) -> tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        check(_lib.load().odis_get_footprint(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @property
+    def launches(self) -> int:
+        i = C.c_int64()
+        check(_lib.load().odis_get_launch_count(self._h, C.byref(i)))
+        return i.value
+
+    def synchronize(self) -> None:
+        check(_lib.load().odis_synchronize(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.load().odis_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

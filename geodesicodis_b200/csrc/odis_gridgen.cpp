@@ -144,7 +144,9 @@ int generate_icosahedral_grid(int level, GridFile& out, std::string& err) {
         if (lon < 0) lon += 360.0;
         double lat = std::atan2(pts[i].z, std::sqrt(pts[i].x * pts[i].x + pts[i].y * pts[i].y)) / kRadPerDeg;
         out.node_pos_sph[(size_t)i * 2] = canon_degrees(lat) * kRadPerDeg;
-        out.node_pos_sph[(size_t)i * 2 + 1] = canon_degrees(lon) * kRadPerDeg;
+        double lon_c = canon_degrees(lon);
+        if (lon_c >= 360.0) lon_c = 0.0;
+        out.node_pos_sph[(size_t)i * 2 + 1] = lon_c * kRadPerDeg;
         int cur = from[(size_t)i * 6];
         for (int k = 1; k < n; k++) cur = std::min(cur, from[(size_t)i * 6 + k]);   // start at the lowest id
         for (int j = 0; j < n; j++) {

@@ -86,6 +86,9 @@ inline herr_t H5Dwrite(hid_t set, hid_t, hid_t, hid_t filespace, hid_t, const vo
     const float* src = (const float*)buf;
     const size_t rank = d.dims.size();
     if (!s.selected) { std::memcpy(d.data.data(), src, d.data.size() * sizeof(float)); return 0; }
+    // a selection outside the dataset extent is an error in HDF5 (nothing is written)
+    for (size_t k = 0; k < rank; k++)
+        if (s.start[k] + s.count[k] > d.dims[k]) return -1;
     if (rank == 1) {
         for (hsize_t i = 0; i < s.count[0]; i++) d.data[s.start[0] + i] = src[i];
     } else if (rank == 2) {

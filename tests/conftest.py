@@ -1,0 +1,68 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The in-tree shared library must exist before anything imports geodesicodis_b200."""
+    from geodesicodis_b200.build import build
+    return build()
+
+
+@pytest.fixture(scope="session")
+def odis(built_library):
+    import geodesicodis_b200
+    return geodesicodis_b200
+
+
+def load_case(name: str) -> dict:
+    with np.load(os.path.join(GOLDEN, f"case_{name}.npz"), allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def write_grid_text(path: str, lat_deg, lon_deg, friends, centroid_deg) -> None:
+    """grid_l<L>.txt text with 16 decimals: re-parses to exactly the doubles the reference read
+    (the fixtures store the parsed degree values, not the reference's files)."""
+    with open(path, "w") as f:
+        f.write("ID    NODE LAT     NODE LON     FRIENDS LIST                           CENTROID COORD LIST \n")
+        for i in range(len(lat_deg)):
+            fr = ",".join("%5d" % v for v in friends[i])
+            cen = ", ".join("( %.16f, %.16f)" % (c[0], c[1]) for c in centroid_deg[i])
+            f.write("%-5d %.16f %.16f {%s}, {%s} \n" % (i, lat_deg[i], lon_deg[i], fr, cen))
+
+
+def make_run_dir(tmp_path, case: dict) -> str:
+    """A run directory (input.in + input_files/grid_l<L>.txt + DATA/) reproducing a golden case."""
+    d = str(tmp_path)
+    os.makedirs(os.path.join(d, "input_files"), exist_ok=True)
+    os.makedirs(os.path.join(d, "DATA"), exist_ok=True)
+    with open(os.path.join(d, "input.in"), "w") as f:
+        f.write(str(case["input_in"]))
+    write_grid_text(os.path.join(d, "input_files", "grid_l%d.txt" % int(case["level"])), case["grid_lat_deg"],
+                    case["grid_lon_deg"], case["grid_friends"], case["grid_centroid_deg"])
+    return d
+
+
+def case_params(case: dict, init_load: int = 0) -> dict:
+    """Solver scalars as the reference derived them (dumped by oracle/ref_build/ref_driver.cpp)."""
+    s = lambda k: float(case["scalar_" + k][0])
+    return dict(g=s("g"), h=s("h"), alpha=s("alpha"), dt=s("timeStep"), radius=s("radius"), omega=s("angVel"),
+                love_reduct=s("loveReduct"), ecc=s("e"), obl=s("theta"), shell_thickness=s("shell_thickness"),
+                potential=int(s("tide_type")), friction=int(s("fric_type")), surface=int(s("surface_type")), init_load=init_load)
+
+
+ALL_CASES = ["l3_obliqwest_earth", "l4_ecc_enceladus", "l6_obliqwest_earth", "l3_full_loaded", "l3_obliq_quadratic",
+             "l4_full2_lidlove", "l5_none_loaded"]
