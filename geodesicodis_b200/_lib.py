@@ -60,6 +60,7 @@ SIGNATURES = {
     "odis_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64]),
     "odis_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
+    "odis_step_profiled": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float)]),
     "odis_get_field": (C.c_int, [C.c_void_p, c_i32, C.c_void_p]),
     "odis_get_dissipation_avg": (C.c_int, [C.c_void_p, P(c_f64)]),
     "odis_get_dissipation_series": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p]),

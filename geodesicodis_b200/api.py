@@ -214,6 +214,12 @@ class Solver:
         check(_lib.load().odis_step_timed(self._h, nsteps, C.byref(ms)))
         return ms.value
 
+    def step_profiled(self, nsteps: int) -> tuple[float, float]:
+        """(edge-kernel ms, cell-kernel ms) summed over nsteps, each launch timed with its own CUDA events."""
+        a, b = C.c_float(), C.c_float()
+        check(_lib.load().odis_step_profiled(self._h, nsteps, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def field(self, fid: int) -> np.ndarray:
         shape = tuple(self.F if d == "F" else self.N if d == "N" else d for d in _FIELD_SHAPES[fid])
         out = np.empty(shape, dtype=np.float64)

@@ -346,7 +346,33 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     return ODIS_OK;
 }
 
-int odis_step(odis_solver* s, int32_t nsteps) {
+static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* marks);
+
+int odis_step(odis_solver* s, int32_t nsteps) { return step_impl(s, nsteps, nullptr); }
+
+int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out) {
+    if (!s || !edge_ms_out || !cell_ms_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (nsteps < 0 || nsteps > 100000) return fail(ODIS_ERR_ARG, "nsteps out of range");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    std::vector<cudaEvent_t> marks((size_t)nsteps * 3);
+    for (auto& e : marks) ODIS_CUDA(cudaEventCreate(&e));
+    int rc = step_impl(s, nsteps, &marks);
+    if (!rc && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(ODIS_ERR_CUDA, "synchronize failed");
+    double edge = 0.0, cell = 0.0;
+    if (!rc) {
+        for (int k = 0; k < nsteps; k++) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, marks[(size_t)k * 3], marks[(size_t)k * 3 + 1]);
+            cudaEventElapsedTime(&b, marks[(size_t)k * 3 + 1], marks[(size_t)k * 3 + 2]);
+            edge += a; cell += b;
+        }
+    }
+    for (auto& e : marks) cudaEventDestroy(e);
+    *edge_ms_out = (float)edge; *cell_ms_out = (float)cell;
+    return rc;
+}
+
+static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* marks) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (!s->have_state) return fail(ODIS_ERR_STATE, "odis_set_state has not been called");
     if (nsteps < 0) return fail(ODIS_ERR_ARG, "nsteps must be >= 0");
@@ -362,12 +388,15 @@ int odis_step(odis_solver* s, int32_t nsteps) {
         es.h1 = s->d_hv[s->hv1]; es.h2 = s->d_hv[1 - s->hv1];
         es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
         es.energy_out = s->d_series + (s->iter - s->iter0);
+        if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
         odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
+        if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
         if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
         odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu, s->d_he[s->he1], s->d_he[1 - s->he1]};
         // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
         const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
         odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), 1, s->prm.block_threads, s->stream);
+        if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream);
         if (mode == odis::AB3_FULL) s->he1 = 1 - s->he1;
         s->cur = 1 - s->cur;
         s->iter++;

@@ -116,6 +116,24 @@ int read_grid_file(const std::string& path, GridFile& out, std::string& err) {
     return 0;
 }
 
+namespace {
+// Degrees whose "%.16f" text parses back (x pi/180) to exactly `rad`, when such a value exists within a
+// few ulps of rad*180/pi (true for every grid that was itself read from / generated for this format).
+double degrees_for_text(double rad) {
+    const double d0 = rad * (180.0 / kPi);
+    char buf[64];
+    for (int k = 0; k < 9; k++) {
+        double cand = d0;
+        const int steps = (k + 1) / 2;
+        for (int s = 0; s < steps; s++) cand = std::nextafter(cand, (k % 2) ? INFINITY : -INFINITY);
+        std::snprintf(buf, sizeof buf, "%.16f", cand);
+        const double back = std::strtod(buf, nullptr);
+        if (back * kRadPerDeg == rad) return back;
+    }
+    return d0;
+}
+}  // namespace
+
 int write_grid_file(const std::string& path, const GridFile& g, std::string& err) {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) {
@@ -123,14 +141,13 @@ int write_grid_file(const std::string& path, const GridFile& g, std::string& err
         return -1;
     }
     std::fprintf(f, "ID    NODE LAT     NODE LON     FRIENDS LIST                           CENTROID COORD LIST \n");
-    const double deg = 180.0 / kPi;
     for (int i = 0; i < g.n_cells; i++) {
-        std::fprintf(f, "%-5d %.16f %.16f {", i, g.node_pos_sph[(size_t)i * 2] * deg, g.node_pos_sph[(size_t)i * 2 + 1] * deg);
+        std::fprintf(f, "%-5d %.16f %.16f {", i, degrees_for_text(g.node_pos_sph[(size_t)i * 2]), degrees_for_text(g.node_pos_sph[(size_t)i * 2 + 1]));
         for (int j = 0; j < 6; j++) std::fprintf(f, "%5d%s", g.node_friends[(size_t)i * 6 + j], j < 5 ? "," : "}, {");
         for (int j = 0; j < 6; j++) {
             const bool pad = g.node_friends[(size_t)i * 6 + j] < 0;
-            const double la = pad ? -1.0 : g.centroid_pos_sph[(size_t)i * 12 + 2 * j] * deg;
-            const double lo = pad ? -1.0 : g.centroid_pos_sph[(size_t)i * 12 + 2 * j + 1] * deg;
+            const double la = pad ? -1.0 : degrees_for_text(g.centroid_pos_sph[(size_t)i * 12 + 2 * j]);
+            const double lo = pad ? -1.0 : degrees_for_text(g.centroid_pos_sph[(size_t)i * 12 + 2 * j + 1]);
             std::fprintf(f, "( %.16f, %.16f)%s", la, lo, j < 5 ? ", " : "} \n");
         }
     }

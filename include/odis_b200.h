@@ -166,12 +166,15 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
 int odis_step(odis_solver* s, int32_t nsteps);
 /* As odis_step, bracketed by CUDA events on the solver's stream; returns elapsed device ms. */
 int odis_step_timed(odis_solver* s, int32_t nsteps, float* elapsed_ms_out);
+/* As odis_step, with every kernel launch bracketed by its own CUDA event pair; returns the summed device
+ * time (ms) of the edge-update and of the cell-update launches separately (roofline instrumentation). */
+int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out);
 /* Device -> host, reference numbering and layout. */
 int odis_get_field(odis_solver* s, int32_t field, double* out);
 /* Area-mean dissipated energy flux after the last step (e_diss of updateEnergy, energy.cpp:60). */
 int odis_get_dissipation_avg(odis_solver* s, double* out);
-/* Per-step series of the same quantity for steps [first, first+count) counted from the last
- * odis_set_state; entry k is the value after step k+1. */
+/* Per-step series of the same quantity counted from the last odis_set_state: entry j (first <= j <
+ * first+count) is the value for the state after j steps, j = 0 being the state as set. */
 int odis_get_dissipation_series(odis_solver* s, int64_t first, int64_t count, double* out);
 int odis_get_iter(odis_solver* s, int64_t* iter_out);
 /* Bytes of device memory held, and the algorithmic HBM bytes one step moves. */
