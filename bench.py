@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the LTE time-step hot path (BASELINE.json metric: LTE timesteps/s at 655,362 cells, FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One bench "step" = one output interval of the reference's loop: --substeps (default 100) consecutive LTE
+time steps (ab3Explicit dumps every totalIter/outputTime steps; the shipped input.in gives 290). `value`
+counts LTE time steps per second with everything resident in HBM; `e2e` is the same interval driven
+through the C ABI with HOST buffers: state H2D (odis_set_state), the interval's steps, and the D2H reads a
+dump needs (eta, edge velocities, dissipation). Under torchrun every rank advances its own member of a
+parameter sweep on its own GPU (weak scaling, no data-path collective); grid partitioning with halo
+exchange is not part of this round.
+
+`--impl reference` times the reference's own CPU solver (oracle/_ref/odis_ref_l<L>: the unmodified
+reference sources) on the same workload, on rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "LTE timesteps/sec at grid L8 (FP64), 1-8 B200; achieved HBM GB/s vs peak"
+UNIT = "timesteps/s"
+
+# Enceladus subsurface ocean (literature values, not in the reference)
+ENCELADUS = dict(radius=252.1e3, shell=23e3, h=38e3, g=0.113, omega=5.307e-5, ecc=0.0047, alpha=1e-7, love_reduct=0.9)
+
+
+def workload_params(mesh, member: int = 0, n_members: int = 1) -> dict:
+    """Solver scalars for sweep member `member` (ocean thickness x drag, log-spaced as in SURVEY §8d item 5)."""
+    h, alpha = ENCELADUS["h"], ENCELADUS["alpha"]
+    if n_members > 1:
+        h = float(np.logspace(np.log10(10e3), np.log10(38e3), n_members)[member])
+        alpha = float(np.logspace(-8, -6, n_members)[member])
+    dmin = float(mesh.tables["face_node_dist"].min())
+    # dt from the wave CFL rule in the reference's (commented) code, src/mesh.cpp:1593-1594, on the thickest ocean
+    dt = 0.2 * dmin / math.sqrt(ENCELADUS["g"] * ENCELADUS["h"])
+    return dict(g=ENCELADUS["g"], h=h, alpha=alpha, dt=dt, radius=mesh.radius, omega=ENCELADUS["omega"],
+                love_reduct=ENCELADUS["love_reduct"], ecc=ENCELADUS["ecc"], obl=0.0, shell_thickness=ENCELADUS["shell"],
+                semimajor_axis=238.02e6, potential=5, friction=0, surface=2, init_load=0, reorder=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        if shutil.which("nvidia-smi"):
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                              "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.t = threading.Thread(target=self._read, daemon=True)
+                self.t.start()
+            except OSError:
+                self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch() -> float | None:
+    """dram bytes per edge_step launch from the committed ncu summary, if one exists."""
+    p = os.path.join(ROOT, "profiles", "edge_step_summary.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def cpu_baseline_port(mesh, prm: dict, budget_s: float = 15.0) -> dict:
+    """The oracle's plain-C restatement of the reference loop (bit-identical to the reference solver, see
+    tests/test_oracle_pinned.py) timed on one host core on a bounded sample of the same workload."""
+    from oracle.lte_oracle import LteOracle
+    keys = ("g", "h", "alpha", "dt", "radius", "omega", "love_reduct", "ecc", "obl", "shell_thickness", "potential", "friction", "surface", "init_load")
+    o = LteOracle(mesh.tables, {k: prm[k] for k in keys})
+    o.set_state()
+    t0 = time.perf_counter(); o.step(3); probe = (time.perf_counter() - t0) / 3
+    n = int(max(5, min(2000, budget_s / max(probe, 1e-9))))
+    t0 = time.perf_counter(); o.step(n); el = time.perf_counter() - t0
+    return {"value": n / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} LTE steps of the same {mesh.n_cells}-cell workload, oracle/lte_oracle.c (gcc -O2), single thread"}
+
+
+def run_ours(args) -> None:
+    import torch
+    import geodesicodis_b200 as odis
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: geodesicodis_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pos, fr, cen = odis.generate_grid(args.level)
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])      # LID_LOVE: boundaryConditions.cpp:126
+    prm = workload_params(mesh, rank, world)
+    solver = odis.Solver(mesh, prm, device=local_rank)
+    N, F = mesh.n_cells, mesh.n_edges
+    S, K, W = args.substeps, args.steps, max(args.warmup, 3)
+    dev_bytes, alg_bytes = solver.footprint()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(W):
+        solver.step(S)
+    barrier()
+    launches0 = solver.launches
+    sampler = ClockSampler(local_rank)
+    t_wall0 = time.time()
+    ms = solver.step_timed(K * S)               # CUDA events on the solver's own stream
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    launches = solver.launches - launches0
+    barrier()
+    ms = max_over_ranks(ms)
+    value = world * K * S / (ms * 1e-3)
+
+    # ---- per-kernel timing for the roofline (live, CUDA events around every launch) --------------
+    edge_ms, cell_ms = solver.step_profiled(min(K * S, 400))
+    nprof = min(K * S, 400)
+    edge_us, cell_us = edge_ms / nprof * 1e3, cell_ms / nprof * 1e3
+    peak, peak_src = measured_peak()
+    edge_alg = 200 * F                          # per-edge algorithmic bytes x edges per launch
+    achieved = edge_alg / (edge_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "edge_step_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": edge_alg, "avg_launch_us": round(edge_us, 2),
+                "cell_step_kernel": {"algorithmic_bytes_per_launch": 128 * N, "avg_launch_us": round(cell_us, 2),
+                                     "achieved": round(128 * N / (cell_us * 1e-6) / 1e9, 1)},
+                "whole_step": {"algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes * value / world / 1e9, 1),
+                               "frac": round(alg_bytes * value / world / 1e9 / peak, 4), "frac_of_8TBs_nominal": round(alg_bytes * value / world / 8e12, 4)}}
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------
+    pin = lambda n: torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+    h_v, h_eta, h_dv, h_de = pin(F), pin(N), pin(3 * F), pin(3 * N)
+    h_v[:] = solver.field(odis.FIELD_VELOCITY); h_eta[:] = solver.field(odis.FIELD_ETA)
+    h_dv[:] = solver.field(odis.FIELD_DVDT).ravel(); h_de[:] = solver.field(odis.FIELD_DETADT).ravel()
+    it0 = solver.iter
+    Ke = max(1, min(K, 20))
+
+    def e2e_interval(k: int):
+        solver.set_state(h_v, h_eta, h_dv, h_de, iter=it0 + k * S)          # H2D of the interval's inputs
+        solver.step(S)
+        h_eta[:] = solver.field(odis.FIELD_ETA)                              # D2H of what a dump reads
+        h_v[:] = solver.field(odis.FIELD_VELOCITY)
+        return solver.dissipation_avg()
+
+    e2e_interval(0)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        e2e_interval(k + 1)
+    torch.cuda.synchronize()
+    el = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": round(world * Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * (4 * F + 4 * N),
+           "d2h_bytes_per_step": 8 * (F + N + 1), "intervals_timed": Ke}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (icosahedral-bisection grid generated in the reference's grid_lN.txt conventions; zero initial state, tidal forcing)",
+                "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE, 23 km shell), ECC tide, linear drag, {N} cells / {F} edges "
+                                       f"(reference file level {args.level} = BASELINE 'L{args.level - 1}'); SH self-gravity term is dead code at reference HEAD and not run",
+                           "cells": N, "edges": F, "lte_steps_per_bench_step": S, "dt_s": prm["dt"],
+                           "cache": f"working set {dev_bytes / 1e6:.0f} MB device, {alg_bytes / 1e6:.0f} MB streamed per LTE step > 126 MB L2 (no flush needed)",
+                           "parallelism": "1 GPU" if world == 1 else f"{world} sweep members, one per GPU, no data-path collective"},
+                "cell_updates_per_s": round(value * N, 1), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_port(mesh, prm)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_reference(args) -> None:
+    """The reference's own CPU implementation of the path on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import geodesicodis_b200 as odis
+    from oracle.build_oracle import reference_binary
+    level = args.level
+    S = args.ref_substeps
+    K, W = args.steps, max(args.warmup, 0)
+    nsteps = (K + W) * S
+    pos, fr, cen = odis.generate_grid(level)
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
+    prm = workload_params(mesh)
+    N, F = mesh.n_cells, mesh.n_edges
+    binary = reference_binary(level)
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE), ECC tide, linear drag, {N} cells / {F} edges", "cells": N, "edges": F,
+                       "lte_steps_per_bench_step": S}}
+    if binary is not None:
+        d = tempfile.mkdtemp(prefix="odis_ref_bench_")
+        try:
+            os.makedirs(d + "/input_files"); os.makedirs(d + "/DATA")
+            odis.write_grid_file(f"{d}/input_files/grid_l{level}.txt", pos, fr, cen)
+            # the reference quantises dt to period/(100k): ask for our dt, then bound the loop to nsteps
+            period = 2 * round(math.pi / ENCELADUS["omega"])
+            dt, total = odis.quantise_time_step(float(period), prm["dt"])
+            keys = {"radius": ENCELADUS["radius"], "k2": 0.0, "h2": 0.0, "love reduction factor": ENCELADUS["love_reduct"],
+                    "angular velocity": ENCELADUS["omega"], "surface gravity": ENCELADUS["g"], "semimajor axis": 238.02e6,
+                    "eccentricity": ENCELADUS["ecc"], "obliquity": 0.0, "ocean thickness": ENCELADUS["h"], "shell thickness": ENCELADUS["shell"],
+                    "friction coefficient": ENCELADUS["alpha"], "friction type": "LINEAR", "potential": "ECC", "surface type": "LID_LOVE",
+                    "advection": "false", "solver type": "AB3", "sh degree": 2, "geodesic grid level": level, "output time": 1,
+                    "dissipation output": "false", "dissipation avg output": "true", "kinetic avg output": "false",
+                    "displacement output": "false", "velocity output": "false", "velocity cartesian output": "false",
+                    "sh coefficient output": "false", "initial conditions": "NONE", "dummy1 output": "false",
+                    "simulation end time": repr((nsteps - 0.5) / total), "time step": repr(prm["dt"]), "core number": 1, "rbf epsilon": 0.5}
+            with open(d + "/input.in", "w") as f:
+                f.write("".join(f"{k}; {v}; bench;\n" for k, v in keys.items()))
+            t0 = time.perf_counter()
+            subprocess.run([binary, "--quiet-restart"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            wall = time.perf_counter() - t0
+            timing = dict(l.split() for l in open(d + "/DATA/ref_timing.txt") if l.strip())
+            loop_s = float(timing["loop_seconds"]) - float(timing["dump_seconds_inside_loop"])
+            value = nsteps / loop_s
+            kind, cores = "reference", 1
+            sample = (f"{nsteps} LTE steps in the reference's own ab3Explicit loop (unmodified sources, g++ -O3 -march=native, serial as in its "
+                      f"Makefile) at {N} cells; loop {loop_s:.1f} s of {wall:.0f} s wall (the rest is the reference's mesh construction)")
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    else:
+        base = cpu_baseline_port(mesh, prm, budget_s=20.0)
+        value, kind, cores, sample = base["value"], "port", 1, base["sample"] + " (oracle/_ref binary for this level not present)"
+    line.update({"value": round(value, 3), "ms_per_step": round(1e3 * S / value, 2),
+                 "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--level", type=int, default=9, help="reference grid-file level; 9 = 655,362 cells (BASELINE 'L8')")
+    ap.add_argument("--substeps", type=int, default=100, help="LTE time steps per bench step (one output interval)")
+    ap.add_argument("--ref-substeps", type=int, default=2, help="LTE time steps per bench step for --impl reference")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

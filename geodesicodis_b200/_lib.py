@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libodis_b200.so")
+# ODIS_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("ODIS_B200_LIB") or os.path.join(HERE, "libodis_b200.so")
 
 c_i32, c_i64, c_f64 = C.c_int32, C.c_int64, C.c_double
 P = C.POINTER

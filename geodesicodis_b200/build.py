@@ -44,6 +44,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Tuning aid: build geodesicodis_b200/_build/libodis_b200_<name>.so with extra -D flags (load it via
+    the ODIS_B200_LIB environment variable)."""
+    nvcc = _nvcc()
+    vdir = os.path.join(BUILD, "variant_" + name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(vdir, src + ".o")
+        subprocess.run(["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        objs.append(obj)
+    for src in CUDA_SOURCES:
+        obj = os.path.join(vdir, src + ".o")
+        subprocess.run([nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        objs.append(obj)
+    lib = os.path.join(HERE, f"libodis_b200_{name}.so")
+    subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-Xcompiler", "-fopenmp", "-lgomp"], check=True)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile (if sources changed) and return the path of the shared library."""
     os.makedirs(BUILD, exist_ok=True)

@@ -286,7 +286,7 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
     // ---- state ----
-    const int blocks = odis::edge_grid_blocks(F, prm->block_threads);
+    const int blocks = (F + 31) / 32;      // one energy partial per warp of edges (>= blocks of edge_diagnostics)
     if ((rc = dev_alloc(s, &s->d_eu, (size_t)N)) || (rc = dev_alloc(s, &s->d_hv[0], (size_t)F)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)F)) ||
         (rc = dev_alloc(s, &s->d_he[0], (size_t)N)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)N)) ||
         (rc = dev_alloc(s, &s->d_block_partial, (size_t)blocks)) || (rc = dev_alloc(s, &s->d_ticket, (size_t)1)) ||
@@ -338,7 +338,7 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     s->have_state = true;
     // potential for the first step: forcing(current_time + dt), timeIntegrator.cpp:187,218
     const double t = s->prm.dt * (double)iter + s->prm.dt;
-    odis::CellState cs{s->d_vl[s->cur], s->d_eu, s->d_he[0], s->d_he[1]};
+    odis::CellState cs{s->d_vl[s->cur], s->d_eu, s->d_he[0], s->d_he[1], nullptr, 0, nullptr};
     odis::launch_cell_step(s->cell_tables(), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), 0, s->prm.block_threads, s->stream);
     s->launches++;
     ODIS_CUDA(cudaGetLastError());
@@ -392,7 +392,8 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
         if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
-        odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu, s->d_he[s->he1], s->d_he[1 - s->he1]};
+        odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu, s->d_he[s->he1], s->d_he[1 - s->he1],
+                           s->d_block_partial, (s->F + 31) / 32, es.energy_out};
         // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
         const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
         odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), 1, s->prm.block_threads, s->stream);

@@ -70,9 +70,9 @@ struct EdgeState {
     const double2* eu;        // [N] {eta^n, U(t_n+dt)}
     double* h1;               // [F] dv/dt of step n-1
     double* h2;               // [F] dv/dt of step n-2
-    double* block_partial;    // [gridDim.x] per-block sum of eps_e * A_e for v^n
-    unsigned int* ticket;     // last-block-done counter
-    double* energy_out;       // where the finished sum goes (series[iter])
+    double* block_partial;    // [ceil(F/32)] per-warp sums of eps_e * A_e for v^n (finished by the next cell_step)
+    unsigned int* ticket;     // unused by edge_step (edge_diagnostics' last-block counter)
+    double* energy_out;       // where the finished sum goes (series[iter]); consumed by cell_step
 };
 
 struct CellState {
@@ -80,6 +80,9 @@ struct CellState {
     double2* eu;              // [N] in: {eta^n, .}  out: {eta^{n+1}, U(t_{n+1}+dt)}
     double* h1;               // [N]
     double* h2;               // [N]
+    const double* energy_partial;   // per-warp partials left by edge_step (block 0 sums them), or unused
+    int n_energy_partials;
+    double* energy_out;             // nullptr: no energy sum to finish
 };
 
 void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, int block_threads,
