@@ -35,6 +35,15 @@ class Params(C.Structure):
                [("reserved", c_i32 * 4)]
 
 
+class RunOptions(C.Structure):
+    _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("reserved", c_i32), ("max_steps", c_i64)]
+
+
+class RunResult(C.Structure):
+    _fields_ = [("steps", c_i64), ("kernel_launches", c_i64), ("dumps", c_i32), ("interrupted", c_i32), ("n_cells", c_i32),
+                ("n_edges", c_i32), ("steps_per_period", c_i32), ("reserved", c_i32), ("dt", c_f64), ("last_dissipation_avg", c_f64)]
+
+
 # every symbol include/odis_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "odis_last_error": (C.c_char_p, []),
@@ -70,6 +79,11 @@ SIGNATURES = {
     "odis_get_launch_count": (C.c_int, [C.c_void_p, P(c_i64)]),
     "odis_synchronize": (C.c_int, [C.c_void_p]),
     "odis_destroy": (None, [C.c_void_p]),
+    "odis_h5_create": (C.c_int, [C.c_char_p, P(C.c_void_p)]),
+    "odis_h5_add_dataset": (C.c_int, [C.c_void_p, C.c_char_p, c_i32, P(C.c_uint64), P(c_i32)]),
+    "odis_h5_write_rows": (C.c_int, [C.c_void_p, c_i32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "odis_h5_close": (C.c_int, [C.c_void_p]),
+    "odis_run": (C.c_int, [C.c_char_p, P(RunOptions), P(RunResult)]),
 }
 
 _lib = None

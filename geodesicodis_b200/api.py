@@ -174,6 +174,45 @@ def params_from_globals(g: Globals, dt: float, reorder: bool = True) -> dict:
                 friction=g.fric_type, surface=g.surface_type, init_load=int(g.initial_condition == 1), reorder=int(reorder))
 
 
+class H5Writer:
+    """DATA/data.h5 writer (float32, contiguous, fixed-shape datasets; src/outFiles.cpp:138-684)."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        check(_lib.load().odis_h5_create(os.fsencode(path), C.byref(self._h)))
+
+    def add_dataset(self, name: str, shape) -> int:
+        dims = (C.c_uint64 * len(shape))(*shape)
+        i = C.c_int32()
+        check(_lib.load().odis_h5_add_dataset(self._h, name.encode(), len(shape), dims, C.byref(i)))
+        return i.value
+
+    def write_rows(self, dataset: int, first_row: int, data) -> None:
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        nrows = a.shape[0] if a.ndim >= 1 else 1
+        check(_lib.load().odis_h5_write_rows(self._h, dataset, first_row, nrows, a.ctypes.data))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            h, self._h = self._h, None
+            check(_lib.load().odis_h5_close(h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False, max_steps: int = 0) -> dict:
+    """`./ODIS` in run_dir: main -> solveODIS -> ab3Explicit (src/main.cpp:46-68), writing DATA/ and
+    InitialConditions/ like the reference. Returns the run summary."""
+    opt = _lib.RunOptions(device, int(reorder), int(echo), 0, max_steps)
+    res = _lib.RunResult()
+    check(_lib.load().odis_run(os.fsencode(run_dir), C.byref(opt), C.byref(res)))
+    return {n: getattr(res, n) for n, _ in _lib.RunResult._fields_ if n != "reserved"}
+
+
 class Solver:
     """Device-resident AB3 time stepper (replaces the body of ab3Explicit). Fields cross in reference numbering."""
 

@@ -20,7 +20,8 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libodis_b200.so")
 
-HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp"]
+HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp", "odis_h5lite.cpp",
+                "odis_run.cpp"]
 CUDA_SOURCES = ["odis_kernels.cu", "odis_engine.cu"]
 
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]
@@ -89,10 +90,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out.strip():
             print(out)
         objs.append(obj)
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(link), r.stdout))
+    # the drop-in executable: `ODIS` run from a directory holding input.in (src/main.cpp)
+    exe = os.path.join(HERE, "bin", "ODIS")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", os.path.join(CSRC, "odis_main.cpp"), "-o", exe, "-L" + HERE, "-lodis_b200", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout))
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB

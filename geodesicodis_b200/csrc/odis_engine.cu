@@ -59,11 +59,13 @@ struct odis_solver {
     size_t series_cap = 0;
     double2* d_vavg = nullptr;
     double* d_ediss = nullptr;
+    int *d_edge_perm = nullptr, *d_cell_perm = nullptr;   // perm[new] = old, for renumbering on the device
+    double* d_stage = nullptr;                             // 3F doubles: reference-ordered staging for H2D / D2H
+    double *d_lvl0_v = nullptr, *d_lvl0_e = nullptr;       // AB3 history level 0 as loaded (device order)
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
     int last_mode = -1;
-    std::vector<double> h_dv0, h_de0;   // history level 0 as loaded (reference numbering)
     int64_t launches = 0;
     size_t device_bytes = 0;
 
@@ -292,6 +294,10 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         (rc = dev_alloc(s, &s->d_block_partial, (size_t)blocks)) || (rc = dev_alloc(s, &s->d_ticket, (size_t)1)) ||
         (rc = dev_alloc(s, &s->d_vavg, (size_t)F)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)F)))
         return bail(rc);
+    if ((rc = upload(s, &s->d_edge_perm, s->edge_perm)) || (rc = upload(s, &s->d_cell_perm, s->cell_perm)) ||
+        (rc = dev_alloc(s, &s->d_stage, (size_t)F * 3)) || (rc = dev_alloc(s, &s->d_lvl0_v, (size_t)F)) ||
+        (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)N)))
+        return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
     *out = s;
     rc = odis_set_state(s, nullptr, nullptr, nullptr, nullptr, 0);
@@ -304,33 +310,25 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
     ODIS_CUDA(cudaSetDevice(s->device));
     const int N = s->N, F = s->F;
-    // velocities keep the static edge length beside them
-    std::vector<double2> vl((size_t)F);
-    ODIS_CUDA(cudaMemcpyAsync(vl.data(), s->d_vl[s->cur], (size_t)F * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
-    ODIS_CUDA(cudaStreamSynchronize(s->stream));
-    std::vector<double> h1((size_t)F, 0.0), h2((size_t)F, 0.0);
-    s->h_dv0.assign((size_t)F, 0.0);
-    for (int en = 0; en < F; en++) {
-        const int eo = s->edge_perm[en];
-        vl[en].x = v ? v[eo] : 0.0;
-        if (dvdt) { s->h_dv0[eo] = dvdt[(size_t)eo * 3]; h1[en] = dvdt[(size_t)eo * 3 + 1]; h2[en] = dvdt[(size_t)eo * 3 + 2]; }
-    }
-    ODIS_CUDA(cudaMemcpyAsync(s->d_vl[s->cur], vl.data(), (size_t)F * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
+    // Reference-ordered host arrays go through one device staging buffer and are renumbered by small
+    // kernels; velocities keep the static edge length beside them (only .x is rewritten).
+    auto stage = [&](const double* host, size_t n) -> int {
+        if (!host) return ODIS_OK;
+        ODIS_CUDA(cudaMemcpyAsync(s->d_stage, host, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        return ODIS_OK;
+    };
+    int rc;
+    if ((rc = stage(v, (size_t)F))) return rc;
+    odis::launch_scatter_x(F, s->d_edge_perm, v ? s->d_stage : nullptr, s->d_vl[s->cur], 0, s->stream);
+    if ((rc = stage(dvdt, (size_t)F * 3))) return rc;
     s->hv1 = 0;
-    ODIS_CUDA(cudaMemcpyAsync(s->d_hv[0], h1.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    ODIS_CUDA(cudaMemcpyAsync(s->d_hv[1], h2.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    std::vector<double2> eu((size_t)N);
-    std::vector<double> g1((size_t)N, 0.0), g2((size_t)N, 0.0);
-    s->h_de0.assign((size_t)N, 0.0);
-    for (int cn = 0; cn < N; cn++) {
-        const int co = s->cell_perm[cn];
-        eu[cn] = make_double2(eta ? eta[co] : 0.0, 0.0);
-        if (detadt) { s->h_de0[co] = detadt[(size_t)co * 3]; g1[cn] = detadt[(size_t)co * 3 + 1]; g2[cn] = detadt[(size_t)co * 3 + 2]; }
-    }
-    ODIS_CUDA(cudaMemcpyAsync(s->d_eu, eu.data(), (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
+    odis::launch_scatter_history(F, s->d_edge_perm, dvdt ? s->d_stage : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
+    if ((rc = stage(eta, (size_t)N))) return rc;
+    odis::launch_scatter_x(N, s->d_cell_perm, eta ? s->d_stage : nullptr, s->d_eu, 1, s->stream);
+    if ((rc = stage(detadt, (size_t)N * 3))) return rc;
     s->he1 = 0;
-    ODIS_CUDA(cudaMemcpyAsync(s->d_he[0], g1.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    ODIS_CUDA(cudaMemcpyAsync(s->d_he[1], g2.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    odis::launch_scatter_history(N, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    s->launches += 4;
     s->iter = iter;
     s->iter0 = iter;
     s->last_mode = -1;
@@ -429,66 +427,52 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     if (!s->have_state) return fail(ODIS_ERR_STATE, "no state");
     ODIS_CUDA(cudaSetDevice(s->device));
     const int N = s->N, F = s->F;
+    size_t count = 0;
     switch (field) {
-        case ODIS_FIELD_VELOCITY: {
-            std::vector<double2> h((size_t)F);
-            ODIS_CUDA(cudaMemcpyAsync(h.data(), s->d_vl[s->cur], (size_t)F * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
-            ODIS_CUDA(cudaStreamSynchronize(s->stream));
-            for (int en = 0; en < F; en++) out[s->edge_perm[en]] = h[en].x;
-            return ODIS_OK;
-        }
+        case ODIS_FIELD_VELOCITY:
+            odis::launch_gather_component(F, s->d_edge_perm, s->d_vl[s->cur], 0, s->d_stage, s->stream);
+            count = (size_t)F;
+            break;
         case ODIS_FIELD_ETA:
-        case ODIS_FIELD_POTENTIAL: {
-            std::vector<double2> h((size_t)N);
-            ODIS_CUDA(cudaMemcpyAsync(h.data(), s->d_eu, (size_t)N * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
-            ODIS_CUDA(cudaStreamSynchronize(s->stream));
-            for (int cn = 0; cn < N; cn++) out[s->cell_perm[cn]] = (field == ODIS_FIELD_ETA) ? h[cn].x : h[cn].y;
-            return ODIS_OK;
-        }
+        case ODIS_FIELD_POTENTIAL:
+            odis::launch_gather_component(N, s->d_cell_perm, s->d_eu, field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
+            count = (size_t)N;
+            break;
         case ODIS_FIELD_DVDT:
         case ODIS_FIELD_DETADT: {
-            const bool edge = (field == ODIS_FIELD_DVDT);
-            const int n = edge ? F : N;
-            const std::vector<int>& perm = edge ? s->edge_perm : s->cell_perm;
-            const int l1 = edge ? s->hv1 : s->he1;
-            double* const* arr = edge ? s->d_hv : s->d_he;
-            std::vector<double> a1((size_t)n), a2((size_t)n);
-            ODIS_CUDA(cudaMemcpyAsync(a1.data(), arr[l1], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-            ODIS_CUDA(cudaMemcpyAsync(a2.data(), arr[1 - l1], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-            ODIS_CUDA(cudaStreamSynchronize(s->stream));
-            const std::vector<double>& lvl0 = edge ? s->h_dv0 : s->h_de0;
-            for (int i = 0; i < n; i++) {
-                const int o = perm[i];
-                double f0;
-                if (s->last_mode < 0) f0 = lvl0[o];                       // nothing stepped yet: as loaded
-                else if (s->last_mode == odis::AB3_FIRST) f0 = a2[i];     // temporalOperators.cpp:56
-                else f0 = a1[i];                                          // :47 / :65
-                out[(size_t)o * 3] = f0;
-                out[(size_t)o * 3 + 1] = a1[i];
-                out[(size_t)o * 3 + 2] = a2[i];
+            // level 0 = newest tendency: as loaded before any step, else where the last step stored it
+            // (temporalOperators.cpp:47,56,65)
+            const int which0 = s->last_mode < 0 ? 0 : (s->last_mode == odis::AB3_FIRST ? 2 : 1);
+            if (field == ODIS_FIELD_DVDT) {
+                odis::launch_gather_history(F, s->d_edge_perm, s->d_lvl0_v, s->d_hv[s->hv1], s->d_hv[1 - s->hv1], which0, s->d_stage, s->stream);
+                count = (size_t)F * 3;
+            } else {
+                odis::launch_gather_history(N, s->d_cell_perm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[1 - s->he1], which0, s->d_stage, s->stream);
+                count = (size_t)N * 3;
             }
-            return ODIS_OK;
+            break;
         }
         case ODIS_FIELD_VELOCITY_EN:
         case ODIS_FIELD_DISSIPATION: {
             int rc = run_diagnostics(s, true);
             if (rc) return rc;
             if (field == ODIS_FIELD_VELOCITY_EN) {
-                std::vector<double2> h((size_t)F);
-                ODIS_CUDA(cudaMemcpyAsync(h.data(), s->d_vavg, (size_t)F * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
-                ODIS_CUDA(cudaStreamSynchronize(s->stream));
-                for (int en = 0; en < F; en++) { out[(size_t)s->edge_perm[en] * 2] = h[en].x; out[(size_t)s->edge_perm[en] * 2 + 1] = h[en].y; }
+                odis::launch_gather_pair(F, s->d_edge_perm, s->d_vavg, s->d_stage, s->stream);
+                count = (size_t)F * 2;
             } else {
-                std::vector<double> h((size_t)F);
-                ODIS_CUDA(cudaMemcpyAsync(h.data(), s->d_ediss, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-                ODIS_CUDA(cudaStreamSynchronize(s->stream));
-                for (int en = 0; en < F; en++) out[s->edge_perm[en]] = h[en];
+                odis::launch_gather_scalar(F, s->d_edge_perm, s->d_ediss, s->d_stage, s->stream);
+                count = (size_t)F;
             }
-            return ODIS_OK;
+            break;
         }
         default:
             return fail(ODIS_ERR_ARG, "unknown field id");
     }
+    s->launches++;
+    ODIS_CUDA(cudaGetLastError());
+    ODIS_CUDA(cudaMemcpyAsync(out, s->d_stage, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    return ODIS_OK;
 }
 
 static double sphere_area(const odis_solver* s) { return 4 * odis::kPi * (s->prm.radius * s->prm.radius); }   // energy.cpp:60
@@ -553,7 +537,8 @@ void odis_destroy(odis_solver* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_normal, s->d_eid, s->d_area, s->d_trig,
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu, s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1],
-                    s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss};
+                    s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
+                    s->d_lvl0_v, s->d_lvl0_e};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -312,6 +312,53 @@ __global__ void __launch_bounds__(kThreads) edge_diag_kernel(EdgeTables t, Physi
     block_sum_and_publish<kThreads>(e_area, block_partial, ticket, energy_out);
 }
 
+// ---- renumbering kernels (set_state / get_field; not on the per-step path) ----
+__global__ void scatter_x_kernel(int n, const int* __restrict__ perm, const double* __restrict__ src, double2* dst, int zero_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 v = dst[i];
+    v.x = src ? src[perm[i]] : 0.0;
+    if (zero_y) v.y = 0.0;
+    dst[i] = v;
+}
+__global__ void scatter_history_kernel(int n, const int* __restrict__ perm, const double* __restrict__ src3, double* lvl0, double* h1,
+                                       double* h2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t o = (size_t)perm[i] * 3;
+    lvl0[i] = src3 ? src3[o] : 0.0;
+    h1[i] = src3 ? src3[o + 1] : 0.0;
+    h2[i] = src3 ? src3[o + 2] : 0.0;
+}
+__global__ void gather_component_kernel(int n, const int* __restrict__ perm, const double2* __restrict__ src, int component, double* dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 v = src[i];
+    dst[perm[i]] = component ? v.y : v.x;
+}
+__global__ void gather_pair_kernel(int n, const int* __restrict__ perm, const double2* __restrict__ src, double* dst2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 v = src[i];
+    const size_t o = (size_t)perm[i] * 2;
+    dst2[o] = v.x;
+    dst2[o + 1] = v.y;
+}
+__global__ void gather_scalar_kernel(int n, const int* __restrict__ perm, const double* __restrict__ src, double* dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+__global__ void gather_history_kernel(int n, const int* __restrict__ perm, const double* __restrict__ lvl0, const double* __restrict__ h1,
+                                      const double* __restrict__ h2, int which0, double* dst3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a1 = h1[i], a2 = h2[i];
+    const size_t o = (size_t)perm[i] * 3;
+    dst3[o] = which0 == 0 ? lvl0[i] : (which0 == 1 ? a1 : a2);
+    dst3[o + 1] = a1;
+    dst3[o + 2] = a2;
+}
+
 template <typename F>
 void dispatch_threads(int block_threads, F&& f) {
     switch (block_threads) {
@@ -352,6 +399,27 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
         edge_diag_kernel<kT><<<(t.n_edges + kT - 1) / kT, kT, 0, stream>>>(t, p, vl, normal, v_avg, energy_diss, block_partial,
                                                                            ticket, energy_out);
     });
+}
+
+void launch_scatter_x(int n, const int* perm, const double* src_ref, double2* dst_new, int zero_y, cudaStream_t stream) {
+    scatter_x_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, src_ref, dst_new, zero_y);
+}
+void launch_scatter_history(int n, const int* perm, const double* src_ref3, double* lvl0_new, double* h1_new, double* h2_new,
+                            cudaStream_t stream) {
+    scatter_history_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, src_ref3, lvl0_new, h1_new, h2_new);
+}
+void launch_gather_component(int n, const int* perm, const double2* src_new, int component, double* dst_ref, cudaStream_t stream) {
+    gather_component_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, src_new, component, dst_ref);
+}
+void launch_gather_pair(int n, const int* perm, const double2* src_new, double* dst_ref2, cudaStream_t stream) {
+    gather_pair_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, src_new, dst_ref2);
+}
+void launch_gather_scalar(int n, const int* perm, const double* src_new, double* dst_ref, cudaStream_t stream) {
+    gather_scalar_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, src_new, dst_ref);
+}
+void launch_gather_history(int n, const int* perm, const double* lvl0_new, const double* h1_new, const double* h2_new, int which0,
+                           double* dst_ref3, cudaStream_t stream) {
+    gather_history_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, lvl0_new, h1_new, h2_new, which0, dst_ref3);
 }
 
 }  // namespace odis

@@ -96,4 +96,20 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
                              double* energy_out, int block_threads, cudaStream_t stream);
 int edge_grid_blocks(int n_edges, int block_threads);
 
+// ---- renumbering on the device: fields cross the C ABI in reference numbering, perm[new] = old ----
+// x component of a double2 array from a reference-ordered source (src == nullptr: zeros); y untouched/kept.
+void launch_scatter_x(int n, const int* perm, const double* src_ref, double2* dst_new, int zero_y, cudaStream_t stream);
+// AB3 history [n][3] in reference order -> level-0 copy, level 1, level 2 in device order (src == nullptr: zeros)
+void launch_scatter_history(int n, const int* perm, const double* src_ref3, double* lvl0_new, double* h1_new, double* h2_new,
+                            cudaStream_t stream);
+// component (0 = x, 1 = y) of a device-ordered double2 array -> reference order
+void launch_gather_component(int n, const int* perm, const double2* src_new, int component, double* dst_ref, cudaStream_t stream);
+// device-ordered double2 array -> reference-ordered [n][2]
+void launch_gather_pair(int n, const int* perm, const double2* src_new, double* dst_ref2, cudaStream_t stream);
+// device-ordered scalar array -> reference order
+void launch_gather_scalar(int n, const int* perm, const double* src_new, double* dst_ref, cudaStream_t stream);
+// history levels in device order -> reference-ordered [n][3]; level 0 is lvl0_new, h1_new or h2_new depending on `which0` (0,1,2)
+void launch_gather_history(int n, const int* perm, const double* lvl0_new, const double* h1_new, const double* h2_new, int which0,
+                           double* dst_ref3, cudaStream_t stream);
+
 }  // namespace odis

@@ -1,0 +1,355 @@
+// Whole-run driver: what `./ODIS` does from a run directory, on the GPU engine.
+//
+// Replaces main() (/root/reference/src/main.cpp:46-68), solveODIS (src/solver.cpp:15-61), the
+// non-loop parts of ab3Explicit (src/timeIntegrator.cpp:57-204,276-322: output cadence, the
+// "DUMPING DATA" log line, SIGINT handling, restart files) and OutFiles (src/outFiles.cpp: OUTPUT.txt /
+// ERROR.txt, data.h5 creation :138-462, grid dump :464-520, DumpData :522-684). The loop body itself
+// is odis_step(). Same files in, same files out:
+//   <run_dir>/input.in, <run_dir>/input_files/grid_l<L>.txt [, InitialConditions/*.txt]
+//   <run_dir>/DATA/OUTPUT.txt, ERROR.txt, data.h5 ; <run_dir>/InitialConditions/{vel,pres}_init.txt
+#include <cmath>
+#include <csignal>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../../include/odis_b200.h"
+#include "odis_config.h"
+#include "odis_error.h"
+#include "odis_h5lite.h"
+#include "odis_mesh.h"
+#include "odis_sphere.h"
+
+using odis::fail;
+
+struct odis_h5 {
+    odis::H5LiteWriter w;
+};
+
+namespace {
+
+volatile std::sig_atomic_t g_sigint = 0;
+void on_sigint(int) { g_sigint = 1; }     // CatchExit, timeIntegrator.cpp:34-37
+
+struct Logs {
+    std::string out_path, err_path;
+    bool echo = false;
+    void out(const std::string& s) const {
+        std::ofstream f(out_path, std::ofstream::out | std::ofstream::app);
+        f << s << std::endl;              // OutFiles::WriteMessage appends a newline (outFiles.cpp:72)
+        if (echo) std::printf("%s\n", s.c_str());
+    }
+    void err(const std::string& s) const {
+        std::ofstream f(err_path, std::ofstream::out | std::ofstream::app);
+        f << s << std::endl;
+    }
+};
+
+std::string fmt(const char* f, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    std::vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+// Globals::OutputConsts, globals.cpp:573-597 (default ostream formatting = %g with 6 digits)
+void write_model_parameters(const odis::Config& cfg, const Logs& log) {
+    log.out("Model parameters: ");
+    for (const std::string& key : cfg.keys()) {
+        const odis::ConfigEntry* e = cfg.find(key);
+        std::ostringstream o;
+        o << "\t\t " << std::left;
+        o.width(30);
+        o << key;
+        switch (e->type) {
+            case odis::ConfigEntry::DOUBLE: o << e->d; break;
+            case odis::ConfigEntry::INT: o << e->i; break;
+            case odis::ConfigEntry::BOOL: o << e->b; break;
+            case odis::ConfigEntry::STRING: o << e->s; break;
+        }
+        log.out(o.str());
+    }
+}
+
+// loadInitialConditions, initialConditions.cpp:19-144: "<a>, <b>, <c>, <d>" per line, std::stod on each token
+int load_restart(const std::string& path, size_t n, std::vector<double>& s, std::vector<double>& hist) {
+    std::ifstream f(path);
+    if (!f.is_open()) return -1;
+    std::string line;
+    size_t i = 0;
+    while (i < n && std::getline(f, line)) {
+        std::istringstream ls(line);
+        std::string tok;
+        double vals[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; k++) {
+            if (!std::getline(ls >> std::ws, tok, ' ')) break;
+            try { vals[k] = std::stod(tok); } catch (...) { return -2; }
+        }
+        s[i] = vals[0];
+        hist[i * 3] = vals[1]; hist[i * 3 + 1] = vals[2]; hist[i * 3 + 2] = vals[3];
+        i++;
+    }
+    return 0;
+}
+
+// writeInitialConditions, initialConditions.cpp:209-276 ("%1.6E, %1.6E, %1.6E, %1.6E\n")
+void write_restart(const std::string& path, size_t n, const std::vector<double>& s, const std::vector<double>& hist) {
+    std::remove(path.c_str());
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return;
+    for (size_t i = 0; i < n; i++) std::fprintf(f, "%1.6E, %1.6E, %1.6E, %1.6E\n", s[i], hist[i * 3], hist[i * 3 + 1], hist[i * 3 + 2]);
+    std::fclose(f);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ HDF5 output ----
+int odis_h5_create(const char* path, odis_h5** out) {
+    if (!path || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    odis_h5* h = new odis_h5();
+    std::string err;
+    if (h->w.create(path, err) != 0) { delete h; return fail(ODIS_ERR_IO, err); }
+    *out = h;
+    return ODIS_OK;
+}
+int odis_h5_add_dataset(odis_h5* h, const char* name, int32_t rank, const uint64_t* dims, int32_t* id_out) {
+    if (!h || !name || !dims || !id_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    std::string err;
+    const int id = h->w.add_dataset(name, rank, dims, err);
+    if (id < 0) return fail(ODIS_ERR_ARG, err);
+    *id_out = id;
+    return ODIS_OK;
+}
+int odis_h5_write_rows(odis_h5* h, int32_t dataset, uint64_t first_row, uint64_t nrows, const float* data) {
+    if (!h || !data) return fail(ODIS_ERR_ARG, "NULL argument");
+    std::string err;
+    if (h->w.write_rows(dataset, first_row, nrows, data, err) != 0) return fail(ODIS_ERR_IO, err);
+    return ODIS_OK;
+}
+int odis_h5_close(odis_h5* h) {
+    if (!h) return ODIS_OK;
+    std::string err;
+    const int rc = h->w.close(err);
+    delete h;
+    return rc ? fail(ODIS_ERR_IO, err) : ODIS_OK;
+}
+
+// ------------------------------------------------------------------ whole run ----
+int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_result* res) {
+    if (!run_dir_c) return fail(ODIS_ERR_ARG, "NULL run_dir");
+    odis_run_options opt{};
+    opt.reorder = 1;
+    if (opt_in) opt = *opt_in;
+    odis_run_result local{};
+    if (!res) res = &local;
+    *res = odis_run_result{};
+    const std::string dir(run_dir_c);
+    const std::string data = dir + "/DATA";
+    ::mkdir(data.c_str(), 0770);                                              // outFiles.cpp:160
+    Logs log{data + "/OUTPUT.txt", data + "/ERROR.txt", opt.echo != 0};
+    std::remove(log.out_path.c_str());
+    std::remove(log.err_path.c_str());
+    log.out("\n\n        | ODIS time-step engine for NVIDIA B200 (GeodesicODIS-compatible run directory) |\n\n");
+    log.err("ODIS error file. Warnings and model termination errors will be written here.\n");   // outFiles.cpp:64
+    auto terminate = [&](int code, const std::string& msg) {                  // OutFiles::TerminateODIS, outFiles.cpp:123-130
+        log.err(msg);
+        log.err("TERMINATING ODIS.");
+        return fail(code, msg);
+    };
+
+    // ---- Globals(0) ----
+    odis::Config cfg;
+    std::string err;
+    if (cfg.load(dir, err) != 0) return terminate(ODIS_ERR_IO, err);
+    log.out("Found input file.");                                             // globals.cpp:351
+    for (const std::string& k : cfg.unassigned())                             // globals.cpp:445-466
+        log.err("WARNING: Unassigned global constant: " + k + ". \nAssigning default value could be risky...\nUsing Titan value\n");
+    if (cfg.finalize(err) != 0) return terminate(ODIS_ERR_CONFIG, err);
+    if (cfg.get_bool("advection"))
+        return terminate(ODIS_ERR_UNSUPPORTED, "advection; true selects the nonlinear branch (momAdvection.cpp), which is outside the LTE hot path");
+    if (cfg.get_bool("velocity cartesian output"))
+        return terminate(ODIS_ERR_UNSUPPORTED, "velocity cartesian output needs the RBF interpolation operator (interpolation.cpp:64-174), outside the LTE hot path");
+    if (cfg.solver_type != odis::AB3) return terminate(ODIS_ERR_UNSUPPORTED, "only solver type AB3 has a live implementation (solver.cpp:25-50)");
+    if (cfg.initial_condition == odis::INIT_ANALYTICAL) return terminate(ODIS_ERR_UNSUPPORTED, "initial conditions; ANALYTICAL is not provided");
+    for (const char* k : {"pressure output", "kinetic output", "dummy2 output"})
+        if (cfg.get_bool(k)) log.err(std::string("WARNING: '") + k + "' would create a second dataset named 'displacement' (outFiles.cpp:286,308,338); ignored.");
+
+    // ---- Mesh ----
+    const std::string grid_path = dir + "/input_files/grid_l" + std::to_string(cfg.get_int("geodesic grid level")) + ".txt";   // mesh.cpp:4023
+    odis::GridFile grid;
+    if (odis::read_grid_file(grid_path, grid, err) != 0) return terminate(ODIS_ERR_IO, err);
+    log.out("\nFound mesh file: " + grid_path);                               // mesh.cpp:4030
+    odis::MeshTables mesh;
+    if (odis::build_mesh_tables(grid, cfg.get_double("radius"), mesh, err, 0) != 0) return terminate(ODIS_ERR_GRID, err);
+    double dt = 0.0;
+    int total_iter = 0;
+    odis::quantise_time_step(cfg.get_double("orbital period"), cfg.get_double("time step"), &dt, &total_iter);   // mesh.cpp:1601-1618
+    cfg.set_double("time step", dt);
+    cfg.set_int("total iterations", total_iter);
+    const int N = mesh.n_cells, F = mesh.n_edges;
+    const double end_time = cfg.get_double("simulation end time");
+    const int output_time = cfg.get_int("output time");
+    if (total_iter <= 0 || output_time <= 0 || total_iter / output_time <= 0)
+        return terminate(ODIS_ERR_CONFIG, "time step / output time give no usable output cadence");
+    const int out_freq = total_iter / output_time;                            // timeIntegrator.cpp:188
+
+    // ---- data.h5 (CreateHDF5Framework, outFiles.cpp:138-462) ----
+    odis::H5LiteWriter h5;
+    if (h5.create(data + "/data.h5", err) != 0) return terminate(ODIS_ERR_IO, err);
+    const uint64_t T = (uint64_t)((int)end_time * output_time + 1);            // outFiles.cpp:149-150,179
+    const uint64_t dims_f[2] = {T, (uint64_t)F}, dims_n[2] = {T, (uint64_t)N}, dims_t[1] = {T}, dims_fp[1] = {(uint64_t)F};
+    int ds_u = -1, ds_v = -1, ds_eta = -1, ds_diss = -1, ds_avg = -1, ds_kin = -1, ds_d1 = -1;
+    if (cfg.get_bool("velocity output")) { ds_u = h5.add_dataset("east velocity", 2, dims_f, err); ds_v = h5.add_dataset("north velocity", 2, dims_f, err); }
+    if (cfg.get_bool("displacement output")) ds_eta = h5.add_dataset("displacement", 2, dims_n, err);
+    if (cfg.get_bool("dissipation output")) ds_diss = h5.add_dataset("dissipated energy", 2, dims_f, err);
+    if (cfg.get_bool("dissipation avg output")) ds_avg = h5.add_dataset("dissipation avg output", 1, dims_t, err);
+    if (cfg.get_bool("kinetic avg output")) ds_kin = h5.add_dataset("kinetic avg output", 1, dims_t, err);
+    if (cfg.get_bool("dummy1 output")) ds_d1 = h5.add_dataset("dummy1 output", 2, dims_n, err);
+    const int ds_lon = h5.add_dataset("face longitude", 1, dims_fp, err), ds_lat = h5.add_dataset("face latitude", 1, dims_fp, err);
+    if (h5.finalize(err) != 0) return terminate(ODIS_ERR_IO, err);
+    {   // DumpGridData, outFiles.cpp:492-515
+        std::vector<float> lons((size_t)F), lats((size_t)F);
+        for (int i = 0; i < F; i++) {
+            lats[i] = (float)((float)mesh.face_centre_pos_sph[(size_t)i * 2] * 180. / odis::kPi);
+            lons[i] = (float)((float)mesh.face_centre_pos_sph[(size_t)i * 2 + 1] * 180. / odis::kPi);
+        }
+        h5.write_rows(ds_lon, 0, (uint64_t)F, lons.data(), err);
+        h5.write_rows(ds_lat, 0, (uint64_t)F, lats.data(), err);
+    }
+    write_model_parameters(cfg, log);                                         // main.cpp:59
+
+    // ---- solveODIS -> ab3Explicit ----
+    log.out("Identifying using selected solver method... " + cfg.get_string("solver type") + "\n");
+    log.out("Entering time solver " + cfg.get_string("solver type") + "...\n");
+    odis_mesh_view mv{};
+    mv.n_cells = N; mv.n_edges = F; mv.n_vertices = mesh.n_vertices; mv.radius = mesh.radius;
+    mv.node_pos_sph = mesh.node_pos_sph.data(); mv.node_friends = mesh.node_friends.data();
+    mv.centroid_pos_sph = mesh.centroid_pos_sph.data();
+    mv.control_volume_surf_area_map = mesh.control_volume_surf_area_map.data();
+    mv.faces = mesh.faces.data(); mv.node_face_dir = mesh.node_face_dir.data(); mv.vertexes = mesh.vertexes.data();
+    mv.face_nodes = mesh.face_nodes.data(); mv.face_vertexes = mesh.face_vertexes.data();
+    mv.face_interp_friends = mesh.face_interp_friends.data(); mv.face_interp_weights = mesh.face_interp_weights.data();
+    mv.face_len = mesh.face_len.data(); mv.face_node_dist = mesh.face_node_dist.data(); mv.face_centre_m = mesh.face_centre_m.data();
+    mv.face_centre_pos_sph = mesh.face_centre_pos_sph.data(); mv.face_intercept_pos_sph = mesh.face_intercept_pos_sph.data();
+    mv.face_area = mesh.face_area.data(); mv.face_normal_vec_map = mesh.face_normal_vec_map.data();
+    mv.vertex_pos_sph = mesh.vertex_pos_sph.data(); mv.vertex_nodes = mesh.vertex_nodes.data(); mv.vertex_R = mesh.vertex_R.data();
+    odis_params p{};
+    p.g = cfg.get_double("surface gravity"); p.h = cfg.get_double("ocean thickness"); p.alpha = cfg.get_double("friction coefficient");
+    p.dt = dt; p.radius = cfg.get_double("radius"); p.omega = cfg.get_double("angular velocity");
+    p.love_reduct = cfg.get_double("love reduction factor"); p.ecc = cfg.get_double("eccentricity"); p.obl = cfg.get_double("obliquity");
+    p.shell_thickness = cfg.get_double("shell thickness"); p.semimajor_axis = cfg.get_double("semimajor axis");
+    p.potential = cfg.tide_type; p.friction = cfg.fric_type; p.surface = cfg.surface_type;
+    p.init_load = cfg.initial_condition == odis::INIT_LOAD; p.reorder = opt.reorder;
+    odis_solver* s = nullptr;
+    int rc = odis_create(&mv, &p, opt.device, &s);
+    if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+
+    std::vector<double> v((size_t)F, 0.0), eta((size_t)N, 0.0), dv((size_t)F * 3, 0.0), de((size_t)N * 3, 0.0);
+    if (cfg.initial_condition == odis::INIT_LOAD) {                           // initialConditions.cpp:19-144
+        const std::string fv = dir + "/InitialConditions/vel_init.txt", fp = dir + "/InitialConditions/pres_init.txt";
+        if (load_restart(fv, (size_t)F, v, dv) == 0) log.out("\nFound initial conditions file: " + fv);
+        else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fv);
+        if (load_restart(fp, (size_t)N, eta, de) == 0) log.out("\nFound initial conditions file: " + fp);
+        else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fp);
+        rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
+        if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
+    }
+    log.out("Defining arrays for Adams-Bashforth time integration...");       // timeIntegrator.cpp:140
+
+    const bool stepping = cfg.surface_type == odis::FREE || cfg.surface_type == odis::FREE_LOADING ||
+                          cfg.surface_type == odis::LID_LOVE || cfg.surface_type == odis::LID_MEMBR;      // timeIntegrator.cpp:207-210
+    const double r = cfg.get_double("radius"), period = cfg.get_double("orbital period");
+    std::vector<double> ven((size_t)F * 2), ediss((size_t)F);
+    std::vector<float> fa((size_t)std::max(F, N)), fb((size_t)F);
+    int out_count = 1;
+    int64_t iter = 0;
+    double e_diss = 0.0;
+    auto dump = [&](double current_time) -> int {                             // timeIntegrator.cpp:190-196,296-302 + DumpData
+        int rc2 = odis_get_dissipation_avg(s, &e_diss);
+        if (rc2) return rc2;
+        log.out(fmt("DUMPING DATA AT %f AVG DISS: %e GW%d", current_time / period, e_diss * 4 * odis::kPi * r * r / 1e9, out_count));
+        const uint64_t row = (uint64_t)(out_count - 1);
+        if (row < T) {                                                         // beyond the extent HDF5 refuses the selection
+            if (ds_u >= 0) {
+                if ((rc2 = odis_get_field(s, ODIS_FIELD_VELOCITY_EN, ven.data()))) return rc2;
+                for (int i = 0; i < F; i++) { fa[i] = (float)ven[(size_t)i * 2]; fb[i] = (float)ven[(size_t)i * 2 + 1]; }   // outFiles.cpp:546-553
+                h5.write_rows(ds_u, row, 1, fa.data(), err);
+                h5.write_rows(ds_v, row, 1, fb.data(), err);
+            }
+            if (ds_eta >= 0) {
+                if ((rc2 = odis_get_field(s, ODIS_FIELD_ETA, eta.data()))) return rc2;
+                for (int i = 0; i < N; i++) fa[i] = (float)eta[i];
+                h5.write_rows(ds_eta, row, 1, fa.data(), err);
+            }
+            if (ds_diss >= 0) {
+                if ((rc2 = odis_get_field(s, ODIS_FIELD_DISSIPATION, ediss.data()))) return rc2;
+                for (int i = 0; i < F; i++) fa[i] = (float)ediss[i];
+                h5.write_rows(ds_diss, row, 1, fa.data(), err);
+            }
+            if (ds_avg >= 0) { const float x = (float)e_diss; h5.write_rows(ds_avg, row, 1, &x, err); }
+            if (ds_kin >= 0) { const float x = (float)current_time; h5.write_rows(ds_kin, row, 1, &x, err); }   // pp[] points at current_time, timeIntegrator.cpp:150
+            if (ds_d1 >= 0) { std::fill(fa.begin(), fa.begin() + N, 0.0f); h5.write_rows(ds_d1, row, 1, fa.data(), err); }
+        }
+        out_count++;
+        res->dumps++;
+        return ODIS_OK;
+    };
+
+    g_sigint = 0;
+    struct sigaction sa_new {}, sa_old {};
+    sa_new.sa_handler = on_sigint;
+    sigaction(SIGINT, &sa_new, &sa_old);                                       // timeIntegrator.cpp:120
+    rc = dump(dt * (double)iter);
+    const double bound = (double)total_iter * end_time;                        // timeIntegrator.cpp:205
+    while (rc == ODIS_OK && (double)iter < bound) {
+        // advance to the next output step, the loop bound or the caller's step budget, whichever is first
+        int64_t n = out_freq - iter % out_freq;
+        const int64_t left = (int64_t)std::ceil(bound - (double)iter);
+        if (n > left) n = left;
+        if (opt.max_steps > 0 && iter + n > opt.max_steps) n = opt.max_steps - iter;
+        if (n <= 0) break;
+        if (stepping) rc = odis_step(s, (int32_t)n);
+        if (rc != ODIS_OK) break;
+        iter += n;
+        if (iter % out_freq == 0) rc = dump(dt * (double)iter);                // timeIntegrator.cpp:280-304
+        else rc = odis_synchronize(s);
+        if (g_sigint) {                                                        // :307-312
+            log.out("Terminate signal caught...");
+            break;
+        }
+    }
+    sigaction(SIGINT, &sa_old, nullptr);
+    if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
+
+    // restart files (writeInitialConditions, initialConditions.cpp:209-276)
+    ::mkdir((dir + "/InitialConditions").c_str(), 0770);
+    if (odis_get_field(s, ODIS_FIELD_VELOCITY, v.data()) == ODIS_OK && odis_get_field(s, ODIS_FIELD_DVDT, dv.data()) == ODIS_OK &&
+        odis_get_field(s, ODIS_FIELD_ETA, eta.data()) == ODIS_OK && odis_get_field(s, ODIS_FIELD_DETADT, de.data()) == ODIS_OK) {
+        write_restart(dir + "/InitialConditions/vel_init.txt", (size_t)F, v, dv);
+        write_restart(dir + "/InitialConditions/pres_init.txt", (size_t)N, eta, de);
+    }
+    int64_t launches = 0;
+    odis_get_launch_count(s, &launches);
+    odis_destroy(s);
+    h5.close(err);
+    res->steps = iter;
+    res->n_cells = N; res->n_edges = F;
+    res->dt = dt; res->steps_per_period = total_iter;
+    res->last_dissipation_avg = e_diss;
+    res->interrupted = g_sigint ? 1 : 0;
+    res->kernel_launches = launches;
+    if (g_sigint) log.out("SOLVER RETURNED WITH AN ERROR...\n");                // solver.cpp:52-55
+    else log.out("Calculations appear to have finished!");                     // solver.cpp:57-58
+    return ODIS_OK;
+}
+
+}  // extern "C"

@@ -184,6 +184,51 @@ int odis_get_launch_count(odis_solver* s, int64_t* launches_out);
 int odis_synchronize(odis_solver* s);
 void odis_destroy(odis_solver* s);
 
+/* ------------------------------------------------------------------------------------------
+ * output — replaces the HDF5 side of OutFiles: CreateHDF5Framework (src/outFiles.cpp:138-462: H5Fcreate +
+ * one H5Dcreate(H5T_NATIVE_FLOAT, contiguous, fixed shape) per enabled field), DumpGridData (:464-520) and
+ * DumpData's H5Sselect_hyperslab/H5Dwrite of one row per dump (:522-684). Writes the HDF5 file format
+ * directly (superblock v0, v1 object headers, contiguous f32 datasets); declare all datasets, then write.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct odis_h5 odis_h5;
+int odis_h5_create(const char* path, odis_h5** out);
+/* float32 dataset of rank 1 or 2 with fixed dims; fails on a duplicate name (as H5Dcreate does). */
+int odis_h5_add_dataset(odis_h5* h, const char* name, int32_t rank, const uint64_t* dims, int32_t* id_out);
+/* rows [first_row, first_row+nrows) of a rank-2 dataset (row = dims[1] floats) or elements of a rank-1
+ * dataset; fails when the selection leaves the dataset extent (as H5Sselect_hyperslab does). */
+int odis_h5_write_rows(odis_h5* h, int32_t dataset, uint64_t first_row, uint64_t nrows, const float* data);
+/* Flushes the metadata, closes the file and frees the handle. */
+int odis_h5_close(odis_h5* h);
+
+/* ------------------------------------------------------------------------------------------
+ * whole run — replaces `./ODIS` started in a run directory: main() (src/main.cpp:46-68) -> solveODIS
+ * (src/solver.cpp:15-61) -> ab3Explicit (src/timeIntegrator.cpp:57-322) with its output cadence
+ * (:188,280), log line (:296-299), SIGINT handling (:32-37,120,307-312) and restart files (:316).
+ * Reads <run_dir>/input.in, input_files/grid_l<L>.txt [, InitialConditions/]; writes DATA/OUTPUT.txt,
+ * DATA/ERROR.txt, DATA/data.h5, InitialConditions/{vel,pres}_init.txt.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct odis_run_options {
+    int32_t device;       /* CUDA device ordinal */
+    int32_t reorder;      /* as odis_params.reorder (default 1 when options == NULL) */
+    int32_t echo;         /* 1: copy OUTPUT.txt lines to stdout */
+    int32_t reserved;
+    int64_t max_steps;    /* > 0: stop after this many steps even if the loop bound is larger */
+} odis_run_options;
+
+typedef struct odis_run_result {
+    int64_t steps;              /* time steps taken */
+    int64_t kernel_launches;
+    int32_t dumps;              /* rows written to data.h5 (including the initial state) */
+    int32_t interrupted;        /* 1 if SIGINT ended the run (ab3Explicit's return value) */
+    int32_t n_cells, n_edges;
+    int32_t steps_per_period;   /* totalIter */
+    int32_t reserved;
+    double dt;
+    double last_dissipation_avg;
+} odis_run_result;
+
+int odis_run(const char* run_dir, const odis_run_options* options, odis_run_result* result_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,4 +65,4 @@ def case_params(case: dict, init_load: int = 0) -> dict:
 
 
 ALL_CASES = ["l3_obliqwest_earth", "l4_ecc_enceladus", "l6_obliqwest_earth", "l3_full_loaded", "l3_obliq_quadratic",
-             "l4_full2_lidlove", "l5_none_loaded"]
+             "l4_full2_lidlove", "l5_none_loaded", "l3_ecc_full_orbit"]

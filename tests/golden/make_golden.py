@@ -85,7 +85,10 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
         open(d + "/input.in", "w").write(input_text(dict(over, **{"simulation end time": "0"})))
         subprocess.run([binary, "--no-run"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         total = int(read_records(d + "/DATA/ref_tables.bin")["totalIter"][0])
-        over["simulation end time"] = repr((nsteps - 0.5) / total)
+        if nsteps > 0:
+            over["simulation end time"] = repr((nsteps - 0.5) / total)
+        else:                                   # whole orbits as configured: HDF5 gets int(endTime)*outputTime+1 rows
+            nsteps = int(np.ceil(total * float(over["simulation end time"])))
         if every_step_dumps:
             over["output time"] = str(total)
         if init_state is not None:
@@ -128,9 +131,9 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
         sl, tag = k.split(":")
         if tag == "dissipation avg output":
             diss.append(v[0]); slices.append(int(sl))
-        elif tag == "displacement output" and (not every_step_dumps or int(sl) in (1, nsteps + 1)):
+        elif tag == "displacement output" and (not every_step_dumps or int(sl) in (1, nsteps + 1)) and len(eta_d) < 16:
             eta_d.append(v)
-        elif tag == "velocity output" and (not every_step_dumps or int(sl) in (1, nsteps + 1)):
+        elif tag == "velocity output" and (not every_step_dumps or int(sl) in (1, nsteps + 1)) and len(vel_d) < 16:
             vel_d.append(v.reshape(-1, 2))
     out["dump_slices"] = np.array(slices)
     out["dump_dissipation_avg"] = np.array(diss)
@@ -175,6 +178,9 @@ if __name__ == "__main__":
     # (6) FULL2 under an ice shell (LID_LOVE: radius reduced by the shell, forcing at the outer radius)
     run_case("l4_full2_lidlove", 4, {"potential": "FULL2", "surface type": "LID_LOVE", "shell thickness": "23e3",
                                      "love reduction factor": "0.9", "time step": "50"}, 40, every_step_dumps=True, full_tables=False)
+    # (8) one whole orbit on L3 with the HDF5 rows the reference wrote (11 slices) and dissipation output on
+    run_case("l3_ecc_full_orbit", 3, {"time step": "100", "output time": "10", "simulation end time": "1", "dissipation output": "true"},
+             0, every_step_dumps=False, full_tables=False)
     # (7) no forcing, decaying loaded state on L5
     run_case("l5_none_loaded", 5, {"potential": "NONE", "time step": "20"}, 30, every_step_dumps=False, full_tables=False,
              init_state=random_state(5, 5))
