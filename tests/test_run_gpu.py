@@ -34,7 +34,8 @@ def test_full_orbit_run_matches_reference_outputs(odis, tmp_path):
         assert np.array_equal(h5[name], ref[name]), name
     # v_avg / dissipation use a different 10-point summation order and a parallel sum: float32 round-off at most
     for name in ("east velocity", "north velocity", "dissipated energy", "dissipation avg output"):
-        assert np.allclose(h5[name], ref[name], rtol=2e-7, atol=1e-30), name
+        # components are sums with cancellation, so the bound is relative to the field's magnitude (float32 eps = 6e-8)
+        assert np.abs(h5[name] - ref[name]).max() <= 2e-7 * np.abs(ref[name]).max(), name
     # the progress lines are the de-facto status API (parsed by python_scripts/dissipation_progress.py)
     out = open(os.path.join(d, "DATA", "OUTPUT.txt")).read()
     assert dumping_lines(out) == dumping_lines(str(case["output_txt"]))
