@@ -35,6 +35,12 @@ class Params(C.Structure):
                [("reserved", c_i32 * 4)]
 
 
+class PartitionPlan(C.Structure):
+    _fields_ = [(n, c_i32) for n in ("rank", "world", "own_cells", "own_edges", "local_cells", "local_edges", "n_peers", "reserved")] + \
+               [(n, P(c_i32)) for n in ("local_cell_ref", "local_edge_ref", "peer_rank", "peer_counts", "send_edge_ref", "send_edge_slot",
+                                        "send_cell_ref", "send_cell_slot")]
+
+
 class RunOptions(C.Structure):
     _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("reserved", c_i32), ("max_steps", c_i64)]
 
@@ -67,6 +73,13 @@ SIGNATURES = {
     "odis_grid_write_file": (C.c_int, [C.c_char_p, c_i32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_free": (None, [C.c_void_p]),
     "odis_create": (C.c_int, [P(MeshView), P(Params), c_i32, P(C.c_void_p)]),
+    "odis_create_partitioned": (C.c_int, [P(MeshView), P(Params), c_i32, c_i32, c_i32, P(C.c_void_p)]),
+    "odis_halo_blob_size": (C.c_int, []),
+    "odis_halo_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "odis_halo_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "odis_get_partition": (C.c_int, [C.c_void_p] + [P(c_i32)] * 7),
+    "odis_partition_plan": (C.c_int, [P(MeshView), c_i32, c_i32, c_i32, P(PartitionPlan)]),
+    "odis_partition_plan_free": (None, [P(PartitionPlan)]),
     "odis_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64]),
     "odis_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),

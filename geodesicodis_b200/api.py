@@ -174,6 +174,24 @@ def params_from_globals(g: Globals, dt: float, reorder: bool = True) -> dict:
                 friction=g.fric_type, surface=g.surface_type, init_load=int(g.initial_condition == 1), reorder=int(reorder))
 
 
+def partition_plan(mesh: Mesh, rank: int, world: int, reorder: bool = True) -> dict:
+    """Host-only view of the domain decomposition rank `rank` of `world` would use (numpy copies)."""
+    lib = _lib.load()
+    plan = _lib.PartitionPlan()
+    check(lib.odis_partition_plan(C.byref(mesh.view), int(reorder), rank, world, C.byref(plan)))
+    try:
+        arr = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, dtype=np.int32)
+        counts = arr(plan.peer_counts, plan.n_peers * 4).reshape(-1, 4)
+        se, sc = int(counts[:, 0].sum()), int(counts[:, 1].sum())
+        return dict(rank=plan.rank, world=plan.world, own_cells=plan.own_cells, own_edges=plan.own_edges,
+                    local_cell_ref=arr(plan.local_cell_ref, plan.local_cells), local_edge_ref=arr(plan.local_edge_ref, plan.local_edges),
+                    peer_rank=arr(plan.peer_rank, plan.n_peers), peer_counts=counts,
+                    send_edge_ref=arr(plan.send_edge_ref, se), send_edge_slot=arr(plan.send_edge_slot, se),
+                    send_cell_ref=arr(plan.send_cell_ref, sc), send_cell_slot=arr(plan.send_cell_slot, sc))
+    finally:
+        lib.odis_partition_plan_free(C.byref(plan))
+
+
 class H5Writer:
     """DATA/data.h5 writer (float32, contiguous, fixed-shape datasets; src/outFiles.cpp:138-684)."""
 
@@ -216,16 +234,38 @@ def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False,
 class Solver:
     """Device-resident AB3 time stepper (replaces the body of ab3Explicit). Fields cross in reference numbering."""
 
-    def __init__(self, mesh: Mesh, params: dict, device: int = 0):
+    def __init__(self, mesh: Mesh, params: dict, device: int = 0, rank: int = 0, world: int = 1):
+        """world > 1: this rank's part of a domain-decomposed run (one Solver per GPU). After creating all
+        ranks' solvers, exchange halo_blob() among the ranks and call halo_connect() before stepping."""
         self.mesh = mesh
         p = Params()
         for k, v in params.items():
             setattr(p, k, v)
         self.params = p
         self._h = C.c_void_p()
-        check(_lib.load().odis_create(C.byref(mesh.view), C.byref(p), device, C.byref(self._h)))
+        self.rank, self.world = rank, world
+        if world == 1:
+            check(_lib.load().odis_create(C.byref(mesh.view), C.byref(p), device, C.byref(self._h)))
+        else:
+            check(_lib.load().odis_create_partitioned(C.byref(mesh.view), C.byref(p), device, rank, world, C.byref(self._h)))
         self.N, self.F = mesh.n_cells, mesh.n_edges
         self._iter0 = 0
+
+    def halo_blob(self) -> bytes:
+        n = _lib.load().odis_halo_blob_size()
+        buf = C.create_string_buffer(n)
+        check(_lib.load().odis_halo_export(self._h, buf))
+        return buf.raw
+
+    def halo_connect(self, blobs) -> None:
+        """blobs: the halo_blob() of every rank, ordered by rank (list of bytes or one concatenated bytes)."""
+        data = blobs if isinstance(blobs, (bytes, bytearray)) else b"".join(blobs)
+        check(_lib.load().odis_halo_connect(self._h, C.c_char_p(bytes(data))))
+
+    def partition(self) -> dict:
+        v = [C.c_int32() for _ in range(7)]
+        check(_lib.load().odis_get_partition(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("rank", "world", "own_cells", "own_edges", "ghost_cells", "ghost_edges", "n_peers"), (x.value for x in v)))
 
     @property
     def steps_since_state(self) -> int:

@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libodis_b200.so")
 
-HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp", "odis_h5lite.cpp",
+HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp", "odis_partition.cpp", "odis_h5lite.cpp",
                 "odis_run.cpp"]
 CUDA_SOURCES = ["odis_kernels.cu", "odis_engine.cu"]
 

@@ -9,6 +9,7 @@
 #include "odis_error.h"
 #include "odis_gridgen.h"
 #include "odis_mesh.h"
+#include "odis_partition.h"
 
 struct odis_config {
     odis::Config cfg;
@@ -229,5 +230,46 @@ int odis_grid_write_file(const char* path, int32_t n_cells, const double* node_p
 }
 
 void odis_free(void* p) { std::free(p); }
+
+// ------------------------------------------------------------------ partition plan (host only) ----
+static int32_t* dup_ints(const std::vector<int>& v) {
+    int32_t* p = (int32_t*)std::malloc((v.size() + 1) * sizeof(int32_t));
+    if (p && !v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(int32_t));
+    return p;
+}
+
+int odis_partition_plan(const odis_mesh_view* mv, int32_t reorder, int32_t rank, int32_t world, odis_partition_plan_t* plan) {
+    if (!mv || !plan) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ODIS_ERR_ARG, "rank/world out of range");
+    odis::LocalNumbering L;
+    odis::build_local_numbering(mv->n_cells, mv->n_edges, mv->node_pos_sph, mv->face_nodes, mv->faces, reorder != 0, rank, world, L);
+    std::memset(plan, 0, sizeof *plan);
+    plan->rank = rank; plan->world = world;
+    plan->own_cells = L.part.n_own_cells; plan->own_edges = L.part.n_own_edges;
+    plan->local_cells = (int32_t)L.cell_perm.size(); plan->local_edges = (int32_t)L.edge_perm.size();
+    plan->local_cell_ref = dup_ints(L.cell_perm);
+    plan->local_edge_ref = dup_ints(L.edge_perm);
+    plan->n_peers = (int32_t)L.part.peers.size();
+    std::vector<int> ranks, counts, se_ref, se_slot, sc_ref, sc_slot;
+    for (const odis::HaloPeer& p : L.part.peers) {
+        ranks.push_back(p.rank);
+        counts.push_back((int)p.send_edge_local.size()); counts.push_back((int)p.send_cell_local.size());
+        counts.push_back(p.recv_edges); counts.push_back(p.recv_cells);
+        for (size_t i = 0; i < p.send_edge_local.size(); i++) { se_ref.push_back(L.edge_perm[(size_t)p.send_edge_local[i]]); se_slot.push_back(p.send_edge_remote[i]); }
+        for (size_t i = 0; i < p.send_cell_local.size(); i++) { sc_ref.push_back(L.cell_perm[(size_t)p.send_cell_local[i]]); sc_slot.push_back(p.send_cell_remote[i]); }
+    }
+    plan->peer_rank = dup_ints(ranks);
+    plan->peer_counts = dup_ints(counts);
+    plan->send_edge_ref = dup_ints(se_ref); plan->send_edge_slot = dup_ints(se_slot);
+    plan->send_cell_ref = dup_ints(sc_ref); plan->send_cell_slot = dup_ints(sc_slot);
+    return ODIS_OK;
+}
+
+void odis_partition_plan_free(odis_partition_plan_t* plan) {
+    if (!plan) return;
+    std::free(plan->local_cell_ref); std::free(plan->local_edge_ref); std::free(plan->peer_rank); std::free(plan->peer_counts);
+    std::free(plan->send_edge_ref); std::free(plan->send_edge_slot); std::free(plan->send_cell_ref); std::free(plan->send_cell_slot);
+    std::memset(plan, 0, sizeof *plan);
+}
 
 }  // extern "C"

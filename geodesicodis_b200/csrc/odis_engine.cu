@@ -15,7 +15,10 @@
 
 #include "../../include/odis_b200.h"
 #include "odis_error.h"
+#include <unistd.h>
+
 #include "odis_kernels.cuh"
+#include "odis_partition.h"
 #include "odis_reorder.h"
 #include "odis_sphere.h"
 
@@ -28,15 +31,21 @@ using odis::fail;
             return fail(ODIS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));       \
     } while (0)
 
+constexpr int kMaxPeers = 8;
+
 struct odis_solver {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int N = 0, F = 0;
+    int Ng = 0, Fg = 0;              // global sizes (what crosses the C ABI)
+    int N = 0, F = 0;                // local sizes including the halo
+    int No = 0, Fo = 0;              // owned cells / edges (the kernels' iteration spaces)
+    int rank = 0, world = 1;
     odis_params prm{};
     odis::Physics phys{};
     double forcing_radius = 0.0;
-    std::vector<int> cell_perm, cell_inv, edge_perm, edge_inv;   // perm[new] = old, inv[old] = new
+    std::vector<int> cell_perm, edge_perm;   // local id -> reference id
+    odis::Partition part;
 
     // device tables
     int2* d_cells = nullptr;
@@ -59,9 +68,22 @@ struct odis_solver {
     size_t series_cap = 0;
     double2* d_vavg = nullptr;
     double* d_ediss = nullptr;
-    int *d_edge_perm = nullptr, *d_cell_perm = nullptr;   // perm[new] = old, for renumbering on the device
-    double* d_stage = nullptr;                             // 3F doubles: reference-ordered staging for H2D / D2H
+    int *d_edge_perm = nullptr, *d_cell_perm = nullptr;   // local id -> reference id, for renumbering on the device
+    double* d_stage = nullptr;                             // 3*Fg doubles: reference-ordered staging for H2D / D2H
     double *d_lvl0_v = nullptr, *d_lvl0_e = nullptr;       // AB3 history level 0 as loaded (device order)
+
+    // halo exchange (world > 1)
+    int n_peers = 0;
+    int peer_rank[kMaxPeers] = {0};
+    bool connected = false;
+    int n_send_e = 0, n_send_c = 0;
+    int *d_send_e_local = nullptr, *d_send_e_remote = nullptr, *d_send_e_peer = nullptr;
+    int *d_send_c_local = nullptr, *d_send_c_remote = nullptr, *d_send_c_peer = nullptr;
+    unsigned long long* d_flags = nullptr;                 // [2][world] epochs written by the peers
+    unsigned int* d_halo_ticket = nullptr;
+    odis::HaloRemote remote_v[2], remote_c;                // peers' vl[0], vl[1], eu + their flag arrays
+    void* ipc_opened[kMaxPeers][4] = {{nullptr}};
+    unsigned long long epoch = 0;
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
@@ -71,20 +93,30 @@ struct odis_solver {
 
     odis::EdgeTables edge_tables() const {
         odis::EdgeTables t;
-        t.n_edges = F; t.cells = d_cells; t.grad = d_grad; t.fcor = d_fcor; t.dist = d_dist; t.sid = d_sid; t.sw = d_sw;
+        t.n_edges = Fo; t.cells = d_cells; t.grad = d_grad; t.fcor = d_fcor; t.dist = d_dist; t.sid = d_sid; t.sw = d_sw;
         return t;
     }
-    odis::CellTables cell_tables() const {
+    odis::CellTables cell_tables(int n_active) const {
         odis::CellTables t;
-        t.n_cells = N; t.eid = d_eid; t.area = d_area; t.trig = d_trig; t.trig_sq = d_trig_sq;
+        t.n_cells = N; t.n_active = n_active; t.eid = d_eid; t.area = d_area; t.trig = d_trig; t.trig_sq = d_trig_sq;
         return t;
     }
+};
+
+struct HaloBlob {                     // what one rank publishes to the others (odis_halo_export)
+    int32_t rank, world;
+    int64_t pid;
+    void* raw[4];                     // vl[0], vl[1], eu, flags — usable directly inside one process
+    cudaIpcMemHandle_t ipc[4];
+    int32_t device;
+    int32_t pad;
 };
 
 namespace {
 
 template <typename T>
 int dev_alloc(odis_solver* s, T** p, size_t count) {
+    if (count == 0) count = 1;
     ODIS_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
     s->device_bytes += count * sizeof(T);
     return ODIS_OK;
@@ -93,7 +125,7 @@ template <typename T>
 int upload(odis_solver* s, T** p, const std::vector<T>& h) {
     int rc = dev_alloc(s, p, h.size());
     if (rc) return rc;
-    ODIS_CUDA(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    if (!h.empty()) ODIS_CUDA(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
     return ODIS_OK;
 }
 
@@ -146,14 +178,12 @@ int run_diagnostics(odis_solver* s, bool want_fields) {
     return ODIS_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device, odis_solver** out) {
+int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device, int32_t rank, int32_t world, odis_solver** out) {
     if (!mv || !prm || !out) return fail(ODIS_ERR_ARG, "NULL argument");
     if (mv->n_cells < 12 || mv->n_edges != 3 * mv->n_cells - 6) return fail(ODIS_ERR_ARG, "mesh sizes are inconsistent (F != 3N-6)");
     if (!(prm->dt > 0.0) || !(prm->radius > 0.0)) return fail(ODIS_ERR_ARG, "dt and radius must be positive");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ODIS_ERR_ARG, "rank/world out of range");
+    if (world > mv->n_cells / 16) return fail(ODIS_ERR_ARG, "too many ranks for this grid");
     switch (prm->potential) {
         case odis::P_OBLIQ: case odis::P_OBLIQ_WEST: case odis::P_ECC: case odis::P_FULL: case odis::P_FULL2: case odis::P_NONE: break;
         default:
@@ -167,10 +197,11 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
 
     odis_solver* s = new odis_solver();
     s->device = device;
-    s->N = mv->n_cells;
-    s->F = mv->n_edges;
+    s->rank = rank; s->world = world;
+    s->Ng = mv->n_cells;
+    s->Fg = mv->n_edges;
     s->prm = *prm;
-    const int N = s->N, F = s->F;
+    const int Ng = s->Ng, Fg = s->Fg;
     int rc = ODIS_OK;
     auto bail = [&](int code) { odis_destroy(s); return code; };
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "cudaStreamCreate failed"));
@@ -199,30 +230,39 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         default: break;
     }
 
-    // ---- renumbering ----
-    s->cell_perm = odis::cell_locality_order(N, mv->node_pos_sph, prm->reorder == 0);
-    s->cell_inv = odis::invert_permutation(s->cell_perm);
-    s->edge_perm = odis::edge_locality_order(F, mv->face_nodes, s->cell_inv, prm->reorder == 0);
-    s->edge_inv = odis::invert_permutation(s->edge_perm);
+    // ---- global renumbering and, for world > 1, the partition with its halo ----
+    odis::LocalNumbering num;
+    odis::build_local_numbering(Ng, Fg, mv->node_pos_sph, mv->face_nodes, mv->faces, prm->reorder != 0, rank, world, num);
+    if ((int)num.part.peers.size() > kMaxPeers) return bail(fail(ODIS_ERR_UNSUPPORTED, "more than 8 neighbouring ranks"));
+    s->part = num.part;
+    s->cell_perm = num.cell_perm;
+    s->edge_perm = num.edge_perm;
+    s->N = (int)s->cell_perm.size(); s->F = (int)s->edge_perm.size();
+    s->No = s->part.n_own_cells; s->Fo = s->part.n_own_edges;
+    const int N = s->N, F = s->F, No = s->No, Fo = s->Fo;
+    auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
+    auto local_edge = [&](int old_id) { return num.local_edge_of_ref(old_id); };
 
-    // ---- edge tables ----
+    // ---- edge tables (owned edges; SoA stride Fo) and the {v,l} arrays (all local edges) ----
     {
-        std::vector<int2> cells((size_t)F);
-        std::vector<double2> grad((size_t)F), normal((size_t)F), vl((size_t)F);
-        std::vector<double> fcor((size_t)F), dist((size_t)F), sw((size_t)F * odis::kStencil, 0.0);
-        std::vector<int> sid((size_t)F * odis::kStencil, -1);
+        std::vector<int2> cells((size_t)Fo);
+        std::vector<double2> grad((size_t)Fo), normal((size_t)Fo), vl((size_t)F);
+        std::vector<double> fcor((size_t)Fo), dist((size_t)Fo), sw((size_t)Fo * odis::kStencil, 0.0);
+        std::vector<int> sid((size_t)Fo * odis::kStencil, -1);
         int bad = 0;
+#pragma omp parallel for schedule(static)
+        for (int en = 0; en < F; en++) vl[en] = make_double2(0.0, mv->face_len[s->edge_perm[en]]);
 #pragma omp parallel for schedule(static) reduction(+ : bad)
-        for (int en = 0; en < F; en++) {
+        for (int en = 0; en < Fo; en++) {
             const int eo = s->edge_perm[en];
             const int c0 = mv->face_nodes[(size_t)eo * 2], c1 = mv->face_nodes[(size_t)eo * 2 + 1];
-            cells[en] = make_int2(s->cell_inv[c0], s->cell_inv[c1]);
+            cells[en] = make_int2(local_cell(c0), local_cell(c1));
+            if (cells[en].x < 0 || cells[en].y < 0) bad++;
             const double d = mv->face_node_dist[eo];
             grad[en] = make_double2((-mv->face_centre_m[(size_t)eo * 2]) / d, (mv->face_centre_m[(size_t)eo * 2 + 1]) / d);   // mesh.cpp:3076-3080
             fcor[en] = -2.0 * prm->omega * std::sin(mv->face_centre_pos_sph[(size_t)eo * 2]);                                   // mesh.cpp:2881
             dist[en] = d;
             normal[en] = make_double2(mv->face_normal_vec_map[(size_t)eo * 2], mv->face_normal_vec_map[(size_t)eo * 2 + 1]);
-            vl[en] = make_double2(0.0, mv->face_len[eo]);
             int cnt = 10;                                                                                                       // mesh.cpp:2866-2872
             if (mv->node_friends[(size_t)c0 * 6 + 5] < 0) cnt--;
             if (mv->node_friends[(size_t)c1 * 6 + 5] < 0) cnt--;
@@ -235,19 +275,21 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
                 ids[b + 1] = id; ws[b + 1] = w;
             }
             for (int j = 0; j < cnt; j++) {
-                if (ids[j] < 0 || ids[j] >= F) { bad++; continue; }
-                sid[(size_t)j * F + en] = s->edge_inv[ids[j]];
-                sw[(size_t)j * F + en] = ws[j];
+                if (ids[j] < 0 || ids[j] >= Fg) { bad++; continue; }
+                const int le = local_edge(ids[j]);
+                if (le < 0) { bad++; continue; }
+                sid[(size_t)j * Fo + en] = le;
+                sw[(size_t)j * Fo + en] = ws[j];
             }
         }
-        if (bad) return bail(fail(ODIS_ERR_ARG, "face_interp_friends holds out-of-range edge ids"));
+        if (bad) return bail(fail(ODIS_ERR_ARG, "face_interp_friends / face_nodes hold out-of-range ids (or the halo is incomplete)"));
         if ((rc = upload(s, &s->d_cells, cells)) || (rc = upload(s, &s->d_grad, grad)) || (rc = upload(s, &s->d_fcor, fcor)) ||
             (rc = upload(s, &s->d_dist, dist)) || (rc = upload(s, &s->d_sid, sid)) || (rc = upload(s, &s->d_sw, sw)) ||
             (rc = upload(s, &s->d_normal, normal)) || (rc = upload(s, &s->d_vl[0], vl)) || (rc = upload(s, &s->d_vl[1], vl)))
             return bail(rc);
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
-    // ---- cell tables ----
+    // ---- cell tables (SoA stride N = all local cells: ghosts need their potential at set_state) ----
     {
         std::vector<int> eid((size_t)N * odis::kCellEdges, -1);
         std::vector<double> area((size_t)N), trig((size_t)N * 8), trig_sq((size_t)N * 2);
@@ -255,18 +297,22 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
 #pragma omp parallel for schedule(static) reduction(+ : bad)
         for (int cn = 0; cn < N; cn++) {
             const int co = s->cell_perm[cn];
-            const int n = (mv->node_friends[(size_t)co * 6 + 5] < 0) ? 5 : 6;
-            int ids[6], dirs[6];
-            for (int j = 0; j < n; j++) { ids[j] = mv->faces[(size_t)co * 6 + j]; dirs[j] = mv->node_face_dir[(size_t)co * 6 + j]; }
-            for (int a = 1; a < n; a++) {                    // CSR column order of operatorDivergence
-                const int id = ids[a], dr = dirs[a];
-                int b = a - 1;
-                while (b >= 0 && ids[b] > id) { ids[b + 1] = ids[b]; dirs[b + 1] = dirs[b]; b--; }
-                ids[b + 1] = id; dirs[b + 1] = dr;
-            }
-            for (int j = 0; j < n; j++) {
-                if (ids[j] < 0 || ids[j] >= F) { bad++; continue; }
-                eid[(size_t)j * N + cn] = s->edge_inv[ids[j]] | (dirs[j] < 0 ? (int)0x80000000 : 0);
+            if (cn < No) {
+                const int n = (mv->node_friends[(size_t)co * 6 + 5] < 0) ? 5 : 6;
+                int ids[6], dirs[6];
+                for (int j = 0; j < n; j++) { ids[j] = mv->faces[(size_t)co * 6 + j]; dirs[j] = mv->node_face_dir[(size_t)co * 6 + j]; }
+                for (int a = 1; a < n; a++) {                    // CSR column order of operatorDivergence
+                    const int id = ids[a], dr = dirs[a];
+                    int b = a - 1;
+                    while (b >= 0 && ids[b] > id) { ids[b + 1] = ids[b]; dirs[b + 1] = dirs[b]; b--; }
+                    ids[b + 1] = id; dirs[b + 1] = dr;
+                }
+                for (int j = 0; j < n; j++) {
+                    if (ids[j] < 0 || ids[j] >= Fg) { bad++; continue; }
+                    const int le = local_edge(ids[j]);
+                    if (le < 0) { bad++; continue; }
+                    eid[(size_t)j * N + cn] = le | (dirs[j] < 0 ? (int)0x80000000 : 0);
+                }
             }
             area[cn] = mv->control_volume_surf_area_map[co];
             const double lat = mv->node_pos_sph[(size_t)co * 2], lon = mv->node_pos_sph[(size_t)co * 2 + 1];
@@ -281,27 +327,131 @@ int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device
             trig_sq[cn] = std::cos(lat) * std::cos(lat);
             trig_sq[(size_t)N + cn] = std::sin(lat) * std::sin(lat);
         }
-        if (bad) return bail(fail(ODIS_ERR_ARG, "faces table holds out-of-range edge ids"));
+        if (bad) return bail(fail(ODIS_ERR_ARG, "faces table holds out-of-range edge ids (or the halo is incomplete)"));
         if ((rc = upload(s, &s->d_eid, eid)) || (rc = upload(s, &s->d_area, area)) || (rc = upload(s, &s->d_trig, trig)) ||
             (rc = upload(s, &s->d_trig_sq, trig_sq)))
             return bail(rc);
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
     // ---- state ----
-    const int blocks = (F + 31) / 32;      // one energy partial per warp of edges (>= blocks of edge_diagnostics)
-    if ((rc = dev_alloc(s, &s->d_eu, (size_t)N)) || (rc = dev_alloc(s, &s->d_hv[0], (size_t)F)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)F)) ||
-        (rc = dev_alloc(s, &s->d_he[0], (size_t)N)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)N)) ||
+    const int blocks = (Fo + 31) / 32;      // one energy partial per warp of edges (>= blocks of edge_diagnostics)
+    if ((rc = dev_alloc(s, &s->d_eu, (size_t)N)) || (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fo)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fo)) ||
+        (rc = dev_alloc(s, &s->d_he[0], (size_t)No)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)No)) ||
         (rc = dev_alloc(s, &s->d_block_partial, (size_t)blocks)) || (rc = dev_alloc(s, &s->d_ticket, (size_t)1)) ||
-        (rc = dev_alloc(s, &s->d_vavg, (size_t)F)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)F)))
+        (rc = dev_alloc(s, &s->d_vavg, (size_t)Fo)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)Fo)))
         return bail(rc);
     if ((rc = upload(s, &s->d_edge_perm, s->edge_perm)) || (rc = upload(s, &s->d_cell_perm, s->cell_perm)) ||
-        (rc = dev_alloc(s, &s->d_stage, (size_t)F * 3)) || (rc = dev_alloc(s, &s->d_lvl0_v, (size_t)F)) ||
-        (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)N)))
+        (rc = dev_alloc(s, &s->d_stage, (size_t)Fg * 3)) || (rc = dev_alloc(s, &s->d_lvl0_v, (size_t)Fo)) ||
+        (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)No)))
         return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
+    cudaMemsetAsync(s->d_eu, 0, (size_t)N * sizeof(double2), s->stream);
+    // ---- halo send lists ----
+    if (world > 1) {
+        std::vector<int> el, er, ep, cl, cr, cp;
+        s->n_peers = (int)s->part.peers.size();
+        for (int k = 0; k < s->n_peers; k++) {
+            const odis::HaloPeer& peer = s->part.peers[(size_t)k];
+            s->peer_rank[k] = peer.rank;
+            for (size_t i = 0; i < peer.send_edge_local.size(); i++) { el.push_back(peer.send_edge_local[i]); er.push_back(peer.send_edge_remote[i]); ep.push_back(k); }
+            for (size_t i = 0; i < peer.send_cell_local.size(); i++) { cl.push_back(peer.send_cell_local[i]); cr.push_back(peer.send_cell_remote[i]); cp.push_back(k); }
+        }
+        s->n_send_e = (int)el.size(); s->n_send_c = (int)cl.size();
+        if ((rc = upload(s, &s->d_send_e_local, el)) || (rc = upload(s, &s->d_send_e_remote, er)) || (rc = upload(s, &s->d_send_e_peer, ep)) ||
+            (rc = upload(s, &s->d_send_c_local, cl)) || (rc = upload(s, &s->d_send_c_remote, cr)) || (rc = upload(s, &s->d_send_c_peer, cp)) ||
+            (rc = dev_alloc(s, &s->d_flags, (size_t)2 * world)) || (rc = dev_alloc(s, &s->d_halo_ticket, (size_t)1)))
+            return bail(rc);
+        cudaMemsetAsync(s->d_flags, 0, (size_t)2 * world * sizeof(unsigned long long), s->stream);
+        cudaMemsetAsync(s->d_halo_ticket, 0, sizeof(unsigned int), s->stream);
+    }
     *out = s;
     rc = odis_set_state(s, nullptr, nullptr, nullptr, nullptr, 0);
     if (rc) { *out = nullptr; return bail(rc); }
+    return ODIS_OK;
+}
+
+// one halo exchange: push my boundary values into the peers' ghost slots, publish the epoch, wait for theirs
+int halo_exchange(odis_solver* s, int kind /*0: edges {v,l}, 1: cells {eta,U}*/, const double2* src, int dst_buffer) {
+    const odis::HaloRemote& rem = kind == 0 ? s->remote_v[dst_buffer] : s->remote_c;
+    odis::launch_halo_push(kind == 0 ? s->n_send_e : s->n_send_c, kind == 0 ? s->d_send_e_local : s->d_send_c_local,
+                           kind == 0 ? s->d_send_e_remote : s->d_send_c_remote, kind == 0 ? s->d_send_e_peer : s->d_send_c_peer, src, rem,
+                           s->n_peers, kind * s->world + s->rank, s->epoch, s->d_halo_ticket, s->stream);
+    odis::HaloWait w;
+    w.n_peers = s->n_peers;
+    for (int k = 0; k < s->n_peers; k++) w.flag[k] = s->d_flags + (size_t)kind * s->world + s->peer_rank[k];
+    odis::launch_halo_wait(w, s->epoch, s->stream);
+    s->launches += 2;
+    ODIS_CUDA(cudaGetLastError());
+    return ODIS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int odis_create(const odis_mesh_view* mv, const odis_params* prm, int32_t device, odis_solver** out) {
+    return create_impl(mv, prm, device, 0, 1, out);
+}
+
+int odis_create_partitioned(const odis_mesh_view* mv, const odis_params* prm, int32_t device, int32_t rank, int32_t world,
+                            odis_solver** out) {
+    return create_impl(mv, prm, device, rank, world, out);
+}
+
+int odis_halo_blob_size(void) { return (int)sizeof(HaloBlob); }
+
+int odis_halo_export(odis_solver* s, void* blob_out) {
+    if (!s || !blob_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    HaloBlob b;
+    std::memset(&b, 0, sizeof b);
+    b.rank = s->rank; b.world = s->world; b.pid = (int64_t)getpid(); b.device = s->device;
+    b.raw[0] = s->d_vl[0]; b.raw[1] = s->d_vl[1]; b.raw[2] = s->d_eu; b.raw[3] = s->d_flags;
+    if (s->world > 1)
+        for (int k = 0; k < 4; k++) ODIS_CUDA(cudaIpcGetMemHandle(&b.ipc[k], b.raw[k]));
+    std::memcpy(blob_out, &b, sizeof b);
+    return ODIS_OK;
+}
+
+int odis_halo_connect(odis_solver* s, const void* all_blobs) {
+    if (!s || !all_blobs) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (s->world == 1) { s->connected = true; return ODIS_OK; }
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const HaloBlob* blobs = (const HaloBlob*)all_blobs;
+    for (int k = 0; k < s->n_peers; k++) {
+        const HaloBlob& b = blobs[s->peer_rank[k]];
+        if (b.rank != s->peer_rank[k] || b.world != s->world) return fail(ODIS_ERR_ARG, "halo blobs are not ordered by rank");
+        void* p[4];
+        if (b.pid == (int64_t)getpid()) {                       // same process: the raw pointers are usable after enabling peer access
+            if (b.device != s->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ODIS_ERR_CUDA, "cudaDeviceEnablePeerAccess failed");
+                cudaGetLastError();
+            }
+            for (int j = 0; j < 4; j++) p[j] = b.raw[j];
+        } else {
+            for (int j = 0; j < 4; j++) {
+                ODIS_CUDA(cudaIpcOpenMemHandle(&p[j], b.ipc[j], cudaIpcMemLazyEnablePeerAccess));
+                s->ipc_opened[k][j] = p[j];
+            }
+        }
+        s->remote_v[0].data[k] = (double2*)p[0]; s->remote_v[1].data[k] = (double2*)p[1]; s->remote_c.data[k] = (double2*)p[2];
+        s->remote_v[0].flags[k] = s->remote_v[1].flags[k] = s->remote_c.flags[k] = (unsigned long long*)p[3];
+    }
+    s->connected = true;
+    return ODIS_OK;
+}
+
+int odis_get_partition(odis_solver* s, int32_t* rank, int32_t* world, int32_t* own_cells, int32_t* own_edges, int32_t* ghost_cells,
+                       int32_t* ghost_edges, int32_t* n_peers) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (rank) *rank = s->rank;
+    if (world) *world = s->world;
+    if (own_cells) *own_cells = s->No;
+    if (own_edges) *own_edges = s->Fo;
+    if (ghost_cells) *ghost_cells = s->N - s->No;
+    if (ghost_edges) *ghost_edges = s->F - s->Fo;
+    if (n_peers) *n_peers = s->n_peers;
     return ODIS_OK;
 }
 
@@ -309,35 +459,37 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
     ODIS_CUDA(cudaSetDevice(s->device));
-    const int N = s->N, F = s->F;
-    // Reference-ordered host arrays go through one device staging buffer and are renumbered by small
-    // kernels; velocities keep the static edge length beside them (only .x is rewritten).
+    const int N = s->N, F = s->F, No = s->No, Fo = s->Fo;
+    // Reference-ordered (global) host arrays go through one device staging buffer and are renumbered by
+    // small kernels; velocities keep the static edge length beside them (only .x is rewritten). A
+    // partitioned solver takes the same global arrays and keeps its own cells/edges plus its halo.
     auto stage = [&](const double* host, size_t n) -> int {
         if (!host) return ODIS_OK;
         ODIS_CUDA(cudaMemcpyAsync(s->d_stage, host, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         return ODIS_OK;
     };
     int rc;
-    if ((rc = stage(v, (size_t)F))) return rc;
+    if ((rc = stage(v, (size_t)s->Fg))) return rc;
     odis::launch_scatter_x(F, s->d_edge_perm, v ? s->d_stage : nullptr, s->d_vl[s->cur], 0, s->stream);
-    if ((rc = stage(dvdt, (size_t)F * 3))) return rc;
+    if ((rc = stage(dvdt, (size_t)s->Fg * 3))) return rc;
     s->hv1 = 0;
-    odis::launch_scatter_history(F, s->d_edge_perm, dvdt ? s->d_stage : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
-    if ((rc = stage(eta, (size_t)N))) return rc;
+    odis::launch_scatter_history(Fo, s->d_edge_perm, dvdt ? s->d_stage : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
+    if ((rc = stage(eta, (size_t)s->Ng))) return rc;
     odis::launch_scatter_x(N, s->d_cell_perm, eta ? s->d_stage : nullptr, s->d_eu, 1, s->stream);
-    if ((rc = stage(detadt, (size_t)N * 3))) return rc;
+    if ((rc = stage(detadt, (size_t)s->Ng * 3))) return rc;
     s->he1 = 0;
-    odis::launch_scatter_history(N, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    odis::launch_scatter_history(No, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
     s->launches += 4;
     s->iter = iter;
     s->iter0 = iter;
     s->last_mode = -1;
     s->diag_current = false;
     s->have_state = true;
-    // potential for the first step: forcing(current_time + dt), timeIntegrator.cpp:187,218
+    // potential for the first step: forcing(current_time + dt), timeIntegrator.cpp:187,218 — for every
+    // local cell, ghosts included (later steps receive the ghosts' potential from their owners)
     const double t = s->prm.dt * (double)iter + s->prm.dt;
     odis::CellState cs{s->d_vl[s->cur], s->d_eu, s->d_he[0], s->d_he[1], nullptr, 0, nullptr};
-    odis::launch_cell_step(s->cell_tables(), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), 0, s->prm.block_threads, s->stream);
+    odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), 0, s->prm.block_threads, s->stream);
     s->launches++;
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
@@ -377,8 +529,9 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
     ODIS_CUDA(cudaSetDevice(s->device));
     int rc = ensure_series(s, (size_t)(s->iter - s->iter0) + (size_t)nsteps + 1);
     if (rc) return rc;
+    if (s->world > 1 && !s->connected) return fail(ODIS_ERR_STATE, "odis_halo_connect has not been called on this partitioned solver");
     const odis::EdgeTables et = s->edge_tables();
-    const odis::CellTables ct = s->cell_tables();
+    const odis::CellTables ct = s->cell_tables(s->No);
     for (int k = 0; k < nsteps; k++) {
         const int mode = ab3_mode(s, s->iter);
         odis::EdgeState es;
@@ -388,13 +541,22 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         es.energy_out = s->d_series + (s->iter - s->iter0);
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
         odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
+        if (s->world > 1) {                       // v^{n+1} of my boundary edges -> the neighbours' halos
+            s->epoch++;
+            int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
+            if (rc2) return rc2;
+        }
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
         if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
         odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu, s->d_he[s->he1], s->d_he[1 - s->he1],
-                           s->d_block_partial, (s->F + 31) / 32, es.energy_out};
+                           s->d_block_partial, (s->Fo + 31) / 32, es.energy_out};
         // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
         const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
         odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), 1, s->prm.block_threads, s->stream);
+        if (s->world > 1) {                       // {eta^{n+1}, U} of my boundary cells -> the neighbours' halos
+            int rc2 = halo_exchange(s, 1, s->d_eu, 0);
+            if (rc2) return rc2;
+        }
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream);
         if (mode == odis::AB3_FULL) s->he1 = 1 - s->he1;
         s->cur = 1 - s->cur;
@@ -426,17 +588,20 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     if (!s || !out) return fail(ODIS_ERR_ARG, "NULL argument");
     if (!s->have_state) return fail(ODIS_ERR_STATE, "no state");
     ODIS_CUDA(cudaSetDevice(s->device));
-    const int N = s->N, F = s->F;
+    const int No = s->No, Fo = s->Fo;
     size_t count = 0;
+    // a partitioned solver fills its own cells/edges of the global array and leaves zeros elsewhere
+    // (the caller sums the ranks' arrays)
+    auto clear = [&](size_t n) { if (s->world > 1) cudaMemsetAsync(s->d_stage, 0, n * sizeof(double), s->stream); };
     switch (field) {
         case ODIS_FIELD_VELOCITY:
-            odis::launch_gather_component(F, s->d_edge_perm, s->d_vl[s->cur], 0, s->d_stage, s->stream);
-            count = (size_t)F;
+            count = (size_t)s->Fg; clear(count);
+            odis::launch_gather_component(Fo, s->d_edge_perm, s->d_vl[s->cur], 0, s->d_stage, s->stream);
             break;
         case ODIS_FIELD_ETA:
         case ODIS_FIELD_POTENTIAL:
-            odis::launch_gather_component(N, s->d_cell_perm, s->d_eu, field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
-            count = (size_t)N;
+            count = (size_t)s->Ng; clear(count);
+            odis::launch_gather_component(No, s->d_cell_perm, s->d_eu, field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
             break;
         case ODIS_FIELD_DVDT:
         case ODIS_FIELD_DETADT: {
@@ -444,11 +609,11 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
             // (temporalOperators.cpp:47,56,65)
             const int which0 = s->last_mode < 0 ? 0 : (s->last_mode == odis::AB3_FIRST ? 2 : 1);
             if (field == ODIS_FIELD_DVDT) {
-                odis::launch_gather_history(F, s->d_edge_perm, s->d_lvl0_v, s->d_hv[s->hv1], s->d_hv[1 - s->hv1], which0, s->d_stage, s->stream);
-                count = (size_t)F * 3;
+                count = (size_t)s->Fg * 3; clear(count);
+                odis::launch_gather_history(Fo, s->d_edge_perm, s->d_lvl0_v, s->d_hv[s->hv1], s->d_hv[1 - s->hv1], which0, s->d_stage, s->stream);
             } else {
-                odis::launch_gather_history(N, s->d_cell_perm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[1 - s->he1], which0, s->d_stage, s->stream);
-                count = (size_t)N * 3;
+                count = (size_t)s->Ng * 3; clear(count);
+                odis::launch_gather_history(No, s->d_cell_perm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[1 - s->he1], which0, s->d_stage, s->stream);
             }
             break;
         }
@@ -457,11 +622,11 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
             int rc = run_diagnostics(s, true);
             if (rc) return rc;
             if (field == ODIS_FIELD_VELOCITY_EN) {
-                odis::launch_gather_pair(F, s->d_edge_perm, s->d_vavg, s->d_stage, s->stream);
-                count = (size_t)F * 2;
+                count = (size_t)s->Fg * 2; clear(count);
+                odis::launch_gather_pair(Fo, s->d_edge_perm, s->d_vavg, s->d_stage, s->stream);
             } else {
-                odis::launch_gather_scalar(F, s->d_edge_perm, s->d_ediss, s->d_stage, s->stream);
-                count = (size_t)F;
+                count = (size_t)s->Fg; clear(count);
+                odis::launch_gather_scalar(Fo, s->d_edge_perm, s->d_ediss, s->d_stage, s->stream);
             }
             break;
         }
@@ -514,7 +679,7 @@ int odis_get_iter(odis_solver* s, int64_t* iter_out) {
 int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* alg_bytes_out) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL argument");
     if (device_bytes_out) *device_bytes_out = (int64_t)s->device_bytes;
-    if (alg_bytes_out) *alg_bytes_out = 200LL * s->F + 128LL * s->N;
+    if (alg_bytes_out) *alg_bytes_out = 200LL * s->Fo + 128LL * s->No;    // SURVEY.md §8(d), this rank's share
     return ODIS_OK;
 }
 
@@ -538,7 +703,11 @@ void odis_destroy(odis_solver* s) {
     void* ptrs[] = {s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_normal, s->d_eid, s->d_area, s->d_trig,
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu, s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1],
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
-                    s->d_lvl0_v, s->d_lvl0_e};
+                    s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,
+                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket};
+    for (int k = 0; k < kMaxPeers; k++)
+        for (int j = 0; j < 4; j++)
+            if (s->ipc_opened[k][j]) cudaIpcCloseMemHandle(s->ipc_opened[k][j]);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physi
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= t.n_cells) return;
+    if (i >= t.n_active) return;
     const int N = t.n_cells;
     // ---- phase A: independent loads ----
     int packed[kCellEdges];
@@ -310,6 +310,35 @@ __global__ void __launch_bounds__(kThreads) edge_diag_kernel(EdgeTables t, Physi
         e_area = eps * (d * own.y);
     }
     block_sum_and_publish<kThreads>(e_area, block_partial, ticket, energy_out);
+}
+
+// ---- halo exchange ----
+__global__ void halo_push_kernel(int n, const int* __restrict__ local_idx, const int* __restrict__ remote_idx, const int* __restrict__ peer,
+                                 const double2* __restrict__ src, HaloRemote remote, int n_peers, int flag_slot, unsigned long long epoch,
+                                 unsigned int* ticket) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) remote.data[peer[k]][remote_idx[k]] = src[local_idx[k]];      // direct store into the neighbour GPU over NVLink
+    __threadfence_system();                                                  // my stores are performed before the ticket
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {                                                           // every block's data is out: publish the epoch
+        __threadfence_system();
+        if ((int)threadIdx.x < n_peers) {
+            unsigned long long* f = remote.flags[threadIdx.x] + flag_slot;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+__global__ void halo_wait_kernel(HaloWait w, unsigned long long epoch) {
+    if ((int)threadIdx.x < w.n_peers) {
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(w.flag[threadIdx.x]) : "memory");
+        } while (seen < epoch);
+    }
 }
 
 // ---- renumbering kernels (set_state / get_field; not on the per-step path) ----
@@ -387,7 +416,7 @@ void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s,
                       int update_eta, int block_threads, cudaStream_t stream) {
     dispatch_threads(block_threads, [&](auto bt) {
         constexpr int kT = decltype(bt)::value;
-        cell_step_kernel<kT><<<(t.n_cells + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, update_eta);
+        cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, update_eta);
     });
 }
 
@@ -399,6 +428,15 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
         edge_diag_kernel<kT><<<(t.n_edges + kT - 1) / kT, kT, 0, stream>>>(t, p, vl, normal, v_avg, energy_diss, block_partial,
                                                                            ticket, energy_out);
     });
+}
+
+void launch_halo_push(int n, const int* local_idx, const int* remote_idx, const int* peer, const double2* src, const HaloRemote& remote,
+                      int n_peers, int flag_slot, unsigned long long epoch, unsigned int* ticket, cudaStream_t stream) {
+    const int blocks = n > 0 ? (n + 255) / 256 : 1;
+    halo_push_kernel<<<blocks, 256, 0, stream>>>(n, local_idx, remote_idx, peer, src, remote, n_peers, flag_slot, epoch, ticket);
+}
+void launch_halo_wait(const HaloWait& w, unsigned long long epoch, cudaStream_t stream) {
+    halo_wait_kernel<<<1, 32, 0, stream>>>(w, epoch);
 }
 
 void launch_scatter_x(int n, const int* perm, const double* src_ref, double2* dst_new, int zero_y, cudaStream_t stream) {

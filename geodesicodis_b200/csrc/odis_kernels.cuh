@@ -48,7 +48,8 @@ struct EdgeTables {
 };
 
 struct CellTables {
-    int n_cells;
+    int n_cells;              // SoA stride = cells held (own + halo)
+    int n_active;             // cells this launch updates (own cells; all held cells for the potential-only pass)
     const int* eid;           // [6][N] edge ids, bit 31 set when the cell is the edge's outer cell; -1 pad
     const double* area;       // [N] control_volume_surf_area_map
     const double* trig;       // [8][N] cosLat sinLat cosLon sinLon cos2Lat sin2Lat cos2Lon sin2Lon   (mesh.cpp:2132-2142)
@@ -95,6 +96,23 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
                              double2* v_avg, double* energy_diss, double* block_partial, unsigned int* ticket,
                              double* energy_out, int block_threads, cudaStream_t stream);
 int edge_grid_blocks(int n_edges, int block_threads);
+
+// ---- halo exchange between ranks (one GPU each): peers' arrays are mapped into this process ----
+constexpr int kHaloMaxPeers = 8;
+struct HaloRemote {
+    double2* data[kHaloMaxPeers];                 // the peer's {v,l} (or {eta,U}) array, its local numbering
+    unsigned long long* flags[kHaloMaxPeers];     // the peer's epoch flags [2][world]
+};
+struct HaloWait {
+    int n_peers;
+    const unsigned long long* flag[kHaloMaxPeers];   // my flags that the peers raise
+};
+// remote.data[peer[k]][remote_idx[k]] = src[local_idx[k]] for every k, then (system-scope fence, last
+// block) remote.flags[p][flag_slot] = epoch for every peer p.
+void launch_halo_push(int n, const int* local_idx, const int* remote_idx, const int* peer, const double2* src, const HaloRemote& remote,
+                      int n_peers, int flag_slot, unsigned long long epoch, unsigned int* ticket, cudaStream_t stream);
+// spins (one thread per peer, acquire loads at system scope) until every flag >= epoch
+void launch_halo_wait(const HaloWait& w, unsigned long long epoch, cudaStream_t stream);
 
 // ---- renumbering on the device: fields cross the C ABI in reference numbering, perm[new] = old ----
 // x component of a double2 array from a reference-ordered source (src == nullptr: zeros); y untouched/kept.

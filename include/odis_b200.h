@@ -158,6 +158,41 @@ typedef enum odis_field {
 /* Copies the mesh tables to device `device` (cudaSetDevice ordinal), builds the stencil tables and
  * zero state. */
 int odis_create(const odis_mesh_view* mesh, const odis_params* params, int32_t device, odis_solver** out);
+/* Multi-GPU: one solver per rank (process or device), each holding a contiguous part of the
+ * space-filling-curve cell order plus a one-ring halo. All ranks pass the same global mesh and params.
+ * After creation every rank publishes odis_halo_blob_size() bytes with odis_halo_export; the world*size
+ * bytes of all ranks, ordered by rank (e.g. an all-gather), go to odis_halo_connect, which maps the
+ * neighbours' halo buffers (CUDA IPC across processes, peer access inside one). From then on odis_step
+ * exchanges boundary values by direct stores into the neighbours' memory. odis_set_state takes the GLOBAL
+ * arrays on every rank; odis_get_field fills this rank's own entries of the global array and zeros
+ * elsewhere; the dissipation getters return this rank's partial sum. All calls are collective. */
+int odis_create_partitioned(const odis_mesh_view* mesh, const odis_params* params, int32_t device, int32_t rank,
+                            int32_t world, odis_solver** out);
+int odis_halo_blob_size(void);
+int odis_halo_export(odis_solver* s, void* blob_out);
+int odis_halo_connect(odis_solver* s, const void* all_blobs);
+int odis_get_partition(odis_solver* s, int32_t* rank, int32_t* world, int32_t* own_cells, int32_t* own_edges,
+                       int32_t* ghost_cells, int32_t* ghost_edges, int32_t* n_peers);
+/* The decomposition odis_create_partitioned would use, computed on the host only (no GPU needed): which
+ * cells/edges (reference ids) rank `rank` holds — own first, then halo —, its neighbours, and for every
+ * neighbour what it sends (reference id + the slot in the neighbour's local numbering). Arrays are
+ * malloc'ed; release with odis_partition_plan_free. */
+typedef struct odis_partition_plan_t {
+    int32_t rank, world;
+    int32_t own_cells, own_edges, local_cells, local_edges;
+    int32_t n_peers, reserved;
+    int32_t* local_cell_ref;    /* [local_cells] */
+    int32_t* local_edge_ref;    /* [local_edges] */
+    int32_t* peer_rank;         /* [n_peers] ascending */
+    int32_t* peer_counts;       /* [n_peers][4]: edges sent, cells sent, edges received, cells received */
+    int32_t* send_edge_ref;     /* concatenated over peers in peer order */
+    int32_t* send_edge_slot;
+    int32_t* send_cell_ref;
+    int32_t* send_cell_slot;
+} odis_partition_plan_t;
+int odis_partition_plan(const odis_mesh_view* mesh, int32_t reorder, int32_t rank, int32_t world, odis_partition_plan_t* plan_out);
+void odis_partition_plan_free(odis_partition_plan_t* plan);
+
 /* Host -> device state in reference numbering. NULL pointers mean zeros. `iter` is the number of
  * steps already taken (current_time = dt*iter, src/timeIntegrator.cpp:187,277). */
 int odis_set_state(odis_solver* s, const double* v, const double* eta, const double* dvdt /*[F][3]*/,
