@@ -7,9 +7,11 @@ One bench "step" = one output interval of the reference's loop: --substeps (defa
 time steps (ab3Explicit dumps every totalIter/outputTime steps; the shipped input.in gives 290). `value`
 counts LTE time steps per second with everything resident in HBM; `e2e` is the same interval driven
 through the C ABI with HOST buffers: state H2D (odis_set_state), the interval's steps, and the D2H reads a
-dump needs (eta, edge velocities, dissipation). Under torchrun every rank advances its own member of a
-parameter sweep on its own GPU (weak scaling, no data-path collective); grid partitioning with halo
-exchange is not part of this round.
+dump needs (eta, edge velocities, dissipation). Under torchrun (N > 1) the SAME grid is cut into N
+contiguous space-filling-curve parts, one per GPU, with a one-ring halo exchanged twice per step by direct
+stores into the neighbours' memory over NVLink (BASELINE config 3: "1/2/4/8 B200 face-partitioned"): total
+work is fixed, so "scaling" is "strong". NCCL is used only for the barrier / max-over-ranks timing and to
+pass the IPC handles around.
 
 `--impl reference` times the reference's own CPU solver (oracle/_ref/odis_ref_l<L>: the unmodified
 reference sources) on the same workload, on rank 0 only.
@@ -158,8 +160,13 @@ def run_ours(args) -> None:
 
     pos, fr, cen = odis.generate_grid(args.level)
     mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])      # LID_LOVE: boundaryConditions.cpp:126
-    prm = workload_params(mesh, rank, world)
-    solver = odis.Solver(mesh, prm, device=local_rank)
+    prm = workload_params(mesh)
+    solver = odis.Solver(mesh, prm, device=local_rank, rank=rank, world=world)
+    if world > 1:                                   # every rank publishes its halo buffers; neighbours map them
+        blobs = [None] * world
+        dist.all_gather_object(blobs, solver.halo_blob())
+        solver.halo_connect(blobs)
+        dist.barrier()
     N, F = mesh.n_cells, mesh.n_edges
     S, K, W = args.substeps, args.steps, max(args.warmup, 3)
     dev_bytes, alg_bytes = solver.footprint()
@@ -178,28 +185,38 @@ def run_ours(args) -> None:
     launches = solver.launches - launches0
     barrier()
     ms = max_over_ranks(ms)
-    value = world * K * S / (ms * 1e-3)
+    value = K * S / (ms * 1e-3)                  # all ranks advance the same K*S steps of the one global grid
 
     # ---- per-kernel timing for the roofline (live, CUDA events around every launch) --------------
     edge_ms, cell_ms = solver.step_profiled(min(K * S, 400))
     nprof = min(K * S, 400)
     edge_us, cell_us = edge_ms / nprof * 1e3, cell_ms / nprof * 1e3
     peak, peak_src = measured_peak()
-    edge_alg = 200 * F                          # per-edge algorithmic bytes x edges per launch
+    part = solver.partition()
+    edge_alg = 200 * part["own_edges"]          # per-edge algorithmic bytes x edges per launch (this rank's)
     achieved = edge_alg / (edge_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "edge_step_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": edge_alg, "avg_launch_us": round(edge_us, 2),
-                "cell_step_kernel": {"algorithmic_bytes_per_launch": 128 * N, "avg_launch_us": round(cell_us, 2),
-                                     "achieved": round(128 * N / (cell_us * 1e-6) / 1e9, 1)},
-                "whole_step": {"algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes * value / world / 1e9, 1),
-                               "frac": round(alg_bytes * value / world / 1e9 / peak, 4), "frac_of_8TBs_nominal": round(alg_bytes * value / world / 8e12, 4)}}
+                "cell_step_kernel": {"algorithmic_bytes_per_launch": 128 * part["own_cells"], "avg_launch_us": round(cell_us, 2),
+                                     "achieved": round(128 * part["own_cells"] / (cell_us * 1e-6) / 1e9, 1)},
+                "whole_step": {"algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes * value / 1e9, 1),
+                               "frac": round(alg_bytes * value / 1e9 / peak, 4), "frac_of_8TBs_nominal": round(alg_bytes * value / 8e12, 4),
+                               "note": "per GPU: this rank's share of the grid; for N>1 the kernel timings include the halo push/wait"}}
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     pin = lambda n: torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
     h_v, h_eta, h_dv, h_de = pin(F), pin(N), pin(3 * F), pin(3 * N)
-    h_v[:] = solver.field(odis.FIELD_VELOCITY); h_eta[:] = solver.field(odis.FIELD_ETA)
-    h_dv[:] = solver.field(odis.FIELD_DVDT).ravel(); h_de[:] = solver.field(odis.FIELD_DETADT).ravel()
+    def whole(field):                            # a partitioned solver returns its own entries, zeros elsewhere
+        a = solver.field(field)
+        if dist is not None:
+            t = torch.from_numpy(a).cuda()
+            dist.all_reduce(t)
+            a = t.cpu().numpy()
+        return a
+
+    h_v[:] = whole(odis.FIELD_VELOCITY); h_eta[:] = whole(odis.FIELD_ETA)
+    h_dv[:] = whole(odis.FIELD_DVDT).ravel(); h_de[:] = whole(odis.FIELD_DETADT).ravel()
     it0 = solver.iter
     Ke = max(1, min(K, 20))
 
@@ -218,18 +235,20 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     el = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e = {"value": round(world * Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * (4 * F + 4 * N),
+    e2e = {"value": round(Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * (4 * F + 4 * N),
            "d2h_bytes_per_step": 8 * (F + N + 1), "intervals_timed": Ke}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (icosahedral-bisection grid generated in the reference's grid_lN.txt conventions; zero initial state, tidal forcing)",
                 "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE, 23 km shell), ECC tide, linear drag, {N} cells / {F} edges "
                                        f"(reference file level {args.level} = BASELINE 'L{args.level - 1}'); SH self-gravity term is dead code at reference HEAD and not run",
                            "cells": N, "edges": F, "lte_steps_per_bench_step": S, "dt_s": prm["dt"],
                            "cache": f"working set {dev_bytes / 1e6:.0f} MB device, {alg_bytes / 1e6:.0f} MB streamed per LTE step > 126 MB L2 (no flush needed)",
-                           "parallelism": "1 GPU" if world == 1 else f"{world} sweep members, one per GPU, no data-path collective"},
+                           "parallelism": "1 GPU" if world == 1 else
+                           f"{world} GPUs, grid cut into {world} space-filling-curve parts, one-ring halo, 2 peer-store exchanges per step "
+                           f"(rank 0: {part['own_cells']} own + {part['ghost_cells']} ghost cells, {part['n_peers']} neighbours)"},
                 "cell_updates_per_s": round(value * N, 1), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}
         if world == 1 and not args.no_cpu:

@@ -84,8 +84,8 @@ class Globals:
     initial_condition = property(lambda self: self.enum(4))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib.load().odis_config_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
+            _lib._lib.odis_config_free(self._h)
             self._h = None
 
 
@@ -136,9 +136,9 @@ class Mesh:
         return cls.from_file(path, g["radius"], threads)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
             self.tables = {}
-            _lib.load().odis_mesh_free(self._h)
+            _lib._lib.odis_mesh_free(self._h)
             self._h = None
 
 
@@ -338,8 +338,8 @@ class Solver:
         check(_lib.load().odis_synchronize(self._h))
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
-            _lib.load().odis_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
+            _lib._lib.odis_destroy(self._h)
             self._h = None
 
     def __del__(self):
