@@ -240,7 +240,10 @@ class Solver:
         self.mesh = mesh
         p = Params()
         for k, v in params.items():
-            setattr(p, k, v)
+            if k == "kernel_select":             # odis_params.reserved[0]: bit 0 direct-load edge kernel, bit 1 staged cell kernel
+                p.reserved[0] = int(v)
+            else:
+                setattr(p, k, v)
         self.params = p
         self._h = C.c_void_p()
         self.rank, self.world = rank, world

@@ -40,6 +40,8 @@ struct odis_solver {
     int Ng = 0, Fg = 0;              // global sizes (what crosses the C ABI)
     int N = 0, F = 0;                // local sizes including the halo
     int No = 0, Fo = 0;              // owned cells / edges (the kernels' iteration spaces)
+    int Np = 0, Fp = 0;              // SoA strides: N and Fo rounded up to the pipelined kernels' tile
+    bool pipe_edge = true, pipe_cell = false;  // params.reserved[0]: bit 0 = direct-load edge kernel, bit 1 = staged cell kernel
     int rank = 0, world = 1;
     odis_params prm{};
     odis::Physics phys{};
@@ -93,12 +95,12 @@ struct odis_solver {
 
     odis::EdgeTables edge_tables() const {
         odis::EdgeTables t;
-        t.n_edges = Fo; t.cells = d_cells; t.grad = d_grad; t.fcor = d_fcor; t.dist = d_dist; t.sid = d_sid; t.sw = d_sw;
+        t.n_edges = Fo; t.stride = Fp; t.cells = d_cells; t.grad = d_grad; t.fcor = d_fcor; t.dist = d_dist; t.sid = d_sid; t.sw = d_sw;
         return t;
     }
     odis::CellTables cell_tables(int n_active) const {
         odis::CellTables t;
-        t.n_cells = N; t.n_active = n_active; t.eid = d_eid; t.area = d_area; t.trig = d_trig; t.trig_sq = d_trig_sq;
+        t.n_cells = Np; t.n_active = n_active; t.eid = d_eid; t.area = d_area; t.trig = d_trig; t.trig_sq = d_trig_sq;
         return t;
     }
 };
@@ -239,16 +241,22 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->edge_perm = num.edge_perm;
     s->N = (int)s->cell_perm.size(); s->F = (int)s->edge_perm.size();
     s->No = s->part.n_own_cells; s->Fo = s->part.n_own_edges;
-    const int N = s->N, F = s->F, No = s->No, Fo = s->Fo;
+    const int tile = odis::pipe_tile();
+    s->Np = (s->N + tile - 1) / tile * tile;
+    s->Fp = (s->Fo + tile - 1) / tile * tile;
+    s->pipe_edge = (prm->reserved[0] & 1) == 0;
+    s->pipe_cell = (prm->reserved[0] & 2) != 0;
+    const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
+    const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
     auto local_edge = [&](int old_id) { return num.local_edge_of_ref(old_id); };
 
     // ---- edge tables (owned edges; SoA stride Fo) and the {v,l} arrays (all local edges) ----
     {
-        std::vector<int2> cells((size_t)Fo);
-        std::vector<double2> grad((size_t)Fo), normal((size_t)Fo), vl((size_t)F);
-        std::vector<double> fcor((size_t)Fo), dist((size_t)Fo), sw((size_t)Fo * odis::kStencil, 0.0);
-        std::vector<int> sid((size_t)Fo * odis::kStencil, -1);
+        std::vector<int2> cells((size_t)Fp, make_int2(0, 0));
+        std::vector<double2> grad((size_t)Fp, make_double2(0.0, 0.0)), normal((size_t)Fo), vl((size_t)Fvl, make_double2(0.0, 0.0));
+        std::vector<double> fcor((size_t)Fp, 0.0), dist((size_t)Fp, 1.0), sw((size_t)Fp * odis::kStencil, 0.0);
+        std::vector<int> sid((size_t)Fp * odis::kStencil, -1);
         int bad = 0;
 #pragma omp parallel for schedule(static)
         for (int en = 0; en < F; en++) vl[en] = make_double2(0.0, mv->face_len[s->edge_perm[en]]);
@@ -278,8 +286,8 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
                 if (ids[j] < 0 || ids[j] >= Fg) { bad++; continue; }
                 const int le = local_edge(ids[j]);
                 if (le < 0) { bad++; continue; }
-                sid[(size_t)j * Fo + en] = le;
-                sw[(size_t)j * Fo + en] = ws[j];
+                sid[(size_t)j * Fp + en] = le;
+                sw[(size_t)j * Fp + en] = ws[j];
             }
         }
         if (bad) return bail(fail(ODIS_ERR_ARG, "face_interp_friends / face_nodes hold out-of-range ids (or the halo is incomplete)"));
@@ -291,8 +299,8 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     }
     // ---- cell tables (SoA stride N = all local cells: ghosts need their potential at set_state) ----
     {
-        std::vector<int> eid((size_t)N * odis::kCellEdges, -1);
-        std::vector<double> area((size_t)N), trig((size_t)N * 8), trig_sq((size_t)N * 2);
+        std::vector<int> eid((size_t)Np * odis::kCellEdges, -1);
+        std::vector<double> area((size_t)Np, 1.0), trig((size_t)Np * 8, 0.0), trig_sq((size_t)Np * 2, 0.0);
         int bad = 0;
 #pragma omp parallel for schedule(static) reduction(+ : bad)
         for (int cn = 0; cn < N; cn++) {
@@ -311,21 +319,21 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
                     if (ids[j] < 0 || ids[j] >= Fg) { bad++; continue; }
                     const int le = local_edge(ids[j]);
                     if (le < 0) { bad++; continue; }
-                    eid[(size_t)j * N + cn] = le | (dirs[j] < 0 ? (int)0x80000000 : 0);
+                    eid[(size_t)j * Np + cn] = le | (dirs[j] < 0 ? (int)0x80000000 : 0);
                 }
             }
             area[cn] = mv->control_volume_surf_area_map[co];
             const double lat = mv->node_pos_sph[(size_t)co * 2], lon = mv->node_pos_sph[(size_t)co * 2 + 1];
-            trig[0 * (size_t)N + cn] = std::cos(lat);            // mesh.cpp:2132-2145
-            trig[1 * (size_t)N + cn] = std::sin(lat);
-            trig[2 * (size_t)N + cn] = std::cos(lon);
-            trig[3 * (size_t)N + cn] = std::sin(lon);
-            trig[4 * (size_t)N + cn] = std::cos(2.0 * lat);
-            trig[5 * (size_t)N + cn] = std::sin(2.0 * lat);
-            trig[6 * (size_t)N + cn] = std::cos(2.0 * lon);
-            trig[7 * (size_t)N + cn] = std::sin(2.0 * lon);
+            trig[0 * (size_t)Np + cn] = std::cos(lat);            // mesh.cpp:2132-2145
+            trig[1 * (size_t)Np + cn] = std::sin(lat);
+            trig[2 * (size_t)Np + cn] = std::cos(lon);
+            trig[3 * (size_t)Np + cn] = std::sin(lon);
+            trig[4 * (size_t)Np + cn] = std::cos(2.0 * lat);
+            trig[5 * (size_t)Np + cn] = std::sin(2.0 * lat);
+            trig[6 * (size_t)Np + cn] = std::cos(2.0 * lon);
+            trig[7 * (size_t)Np + cn] = std::sin(2.0 * lon);
             trig_sq[cn] = std::cos(lat) * std::cos(lat);
-            trig_sq[(size_t)N + cn] = std::sin(lat) * std::sin(lat);
+            trig_sq[(size_t)Np + cn] = std::sin(lat) * std::sin(lat);
         }
         if (bad) return bail(fail(ODIS_ERR_ARG, "faces table holds out-of-range edge ids (or the halo is incomplete)"));
         if ((rc = upload(s, &s->d_eid, eid)) || (rc = upload(s, &s->d_area, area)) || (rc = upload(s, &s->d_trig, trig)) ||
@@ -334,9 +342,9 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
     // ---- state ----
-    const int blocks = (Fo + 31) / 32;      // one energy partial per warp of edges (>= blocks of edge_diagnostics)
-    if ((rc = dev_alloc(s, &s->d_eu, (size_t)N)) || (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fo)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fo)) ||
-        (rc = dev_alloc(s, &s->d_he[0], (size_t)No)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)No)) ||
+    const int blocks = Fp / 32;             // one energy partial per warp of edges (>= blocks of edge_diagnostics)
+    if ((rc = dev_alloc(s, &s->d_eu, (size_t)Np)) || (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fp)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fp)) ||
+        (rc = dev_alloc(s, &s->d_he[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)Np)) ||
         (rc = dev_alloc(s, &s->d_block_partial, (size_t)blocks)) || (rc = dev_alloc(s, &s->d_ticket, (size_t)1)) ||
         (rc = dev_alloc(s, &s->d_vavg, (size_t)Fo)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)Fo)))
         return bail(rc);
@@ -345,7 +353,11 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)No)))
         return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
-    cudaMemsetAsync(s->d_eu, 0, (size_t)N * sizeof(double2), s->stream);
+    cudaMemsetAsync(s->d_eu, 0, (size_t)Np * sizeof(double2), s->stream);
+    cudaMemsetAsync(s->d_hv[0], 0, (size_t)Fp * sizeof(double), s->stream);
+    cudaMemsetAsync(s->d_hv[1], 0, (size_t)Fp * sizeof(double), s->stream);
+    cudaMemsetAsync(s->d_he[0], 0, (size_t)Np * sizeof(double), s->stream);
+    cudaMemsetAsync(s->d_he[1], 0, (size_t)Np * sizeof(double), s->stream);
     // ---- halo send lists ----
     if (world > 1) {
         std::vector<int> el, er, ep, cl, cr, cp;
@@ -540,7 +552,8 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
         es.energy_out = s->d_series + (s->iter - s->iter0);
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
-        odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
+        if (s->pipe_edge) ODIS_CUDA(odis::launch_edge_step_pipe(et, s->phys, es, mode, s->stream));
+        else odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
         if (s->world > 1) {                       // v^{n+1} of my boundary edges -> the neighbours' halos
             s->epoch++;
             int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
@@ -552,7 +565,8 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
                            s->d_block_partial, (s->Fo + 31) / 32, es.energy_out};
         // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
         const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
-        odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), 1, s->prm.block_threads, s->stream);
+        if (s->pipe_cell) ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), s->stream));
+        else odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), 1, s->prm.block_threads, s->stream);
         if (s->world > 1) {                       // {eta^{n+1}, U} of my boundary cells -> the neighbours' halos
             int rc2 = halo_exchange(s, 1, s->d_eu, 0);
             if (rc2) return rc2;

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, ODIS_EDGE_MIN_BLOCKS * 256 / kThread
     const int e = blockIdx.x * kThreads + threadIdx.x;
     double e_area = 0.0;
     if (e < t.n_edges) {
-        const int F = t.n_edges;
+        const int F = t.stride;
         // ---- phase A: every load that does not depend on another load, issued back to back ----
         int id[kStencil];
         double w[kStencil];
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kThreads) edge_diag_kernel(EdgeTables t, Physi
     const int e = blockIdx.x * kThreads + threadIdx.x;
     double e_area = 0.0;
     if (e < t.n_edges) {
-        const int F = t.n_edges;
+        const int F = t.stride;
         const double2 own = vl[e];
         const double d = t.dist[e];
         double vt = 0.0;

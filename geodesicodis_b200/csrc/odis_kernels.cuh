@@ -38,13 +38,14 @@ struct StepScalars {          // per-step host-evaluated trigonometry (tidalPote
 };
 
 struct EdgeTables {
-    int n_edges;
+    int n_edges;              // edges this rank updates
+    int stride;               // SoA row stride of sid / sw (n_edges rounded up to the 128-edge tile)
     const int2* cells;        // [F] inner, outer cell (device numbering)
     const double2* grad;      // [F] G_e,inner = -m_e0/d_e ; G_e,outer = +m_e1/d_e   (mesh.cpp:3076-3080)
     const double* fcor;       // [F] (-2.0*Omega)*sin(lat_e)                          (mesh.cpp:2881)
     const double* dist;       // [F] d_e = face_node_dist
-    const int* sid;           // [10][F] stencil edge ids, slot order = ascending reference id, -1 pad
-    const double* sw;         // [10][F] TRiSK weights w_ee' in the same slot order
+    const int* sid;           // [10][stride] stencil edge ids, slot order = ascending reference id, -1 pad
+    const double* sw;         // [10][stride] TRiSK weights w_ee' in the same slot order
 };
 
 struct CellTables {
@@ -96,6 +97,14 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
                              double2* v_avg, double* energy_diss, double* block_partial, unsigned int* ticket,
                              double* energy_out, int block_threads, cudaStream_t stream);
 int edge_grid_blocks(int n_edges, int block_threads);
+
+// Pipelined variants (odis_kernels_pipe.cu): persistent CTAs, tables staged through shared memory by
+// cp.async.bulk + mbarrier, 128-entity tiles. Same results bit for bit. All arrays a tile touches must
+// be allocated up to the next multiple of pipe_tile().
+int pipe_tile();
+cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, cudaStream_t stream);
+cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
+                                  cudaStream_t stream);
 
 // ---- halo exchange between ranks (one GPU each): peers' arrays are mapped into this process ----
 constexpr int kHaloMaxPeers = 8;
