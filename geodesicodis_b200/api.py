@@ -240,7 +240,7 @@ class Solver:
         self.mesh = mesh
         p = Params()
         for k, v in params.items():
-            if k == "kernel_select":             # odis_params.reserved[0]: bit 0 direct-load edge kernel, bit 1 staged cell kernel
+            if k == "kernel_select":             # odis_params.reserved[0], see include/odis_b200.h (0 = fused one-launch step)
                 p.reserved[0] = int(v)
             else:
                 setattr(p, k, v)

@@ -60,10 +60,16 @@ struct odis_solver {
     // device state
     double2* d_vl[2] = {nullptr, nullptr};
     int cur = 0;
-    double2* d_eu = nullptr;
+    double2* d_eu[2] = {nullptr, nullptr};   // {eta,U}: cell updates read one and write the other
+    int ecur = 0;                    // which holds the newest values
     double* d_hv[2] = {nullptr, nullptr};
-    double* d_he[2] = {nullptr, nullptr};
-    int hv1 = 0, he1 = 0;            // which of the two arrays holds history level 1
+    double* d_he[3] = {nullptr, nullptr, nullptr};   // cell tendency history: levels 1, 2 and the slot the next update writes
+    int hv1 = 0;                     // which of the two edge arrays holds history level 1
+    int he1 = 0, he2 = 1, hefree = 2;
+    unsigned long long* d_cmap = nullptr;   // fused kernel: per-edge slot map of its two cells
+    bool fused = false;              // one fused kernel per step (params.reserved[0] bit 2) instead of the two-launch kernels
+    bool eta_lag = false;            // fused stepping: eta is one step behind v until finalize_eta()
+    int mode_lag = 0;                // AB3 mode of the pending cell update
     double* d_block_partial = nullptr;
     unsigned int* d_ticket = nullptr;
     double* d_series = nullptr;
@@ -83,8 +89,8 @@ struct odis_solver {
     int *d_send_c_local = nullptr, *d_send_c_remote = nullptr, *d_send_c_peer = nullptr;
     unsigned long long* d_flags = nullptr;                 // [2][world] epochs written by the peers
     unsigned int* d_halo_ticket = nullptr;
-    odis::HaloRemote remote_v[2], remote_c;                // peers' vl[0], vl[1], eu + their flag arrays
-    void* ipc_opened[kMaxPeers][4] = {{nullptr}};
+    odis::HaloRemote remote_v[2], remote_c[2];             // peers' vl[0], vl[1], eu[0], eu[1] + their flag arrays
+    void* ipc_opened[kMaxPeers][5] = {{nullptr}};
     unsigned long long epoch = 0;
 
     int64_t iter = 0, iter0 = 0;
@@ -108,8 +114,8 @@ struct odis_solver {
 struct HaloBlob {                     // what one rank publishes to the others (odis_halo_export)
     int32_t rank, world;
     int64_t pid;
-    void* raw[4];                     // vl[0], vl[1], eu, flags — usable directly inside one process
-    cudaIpcMemHandle_t ipc[4];
+    void* raw[5];                     // vl[0], vl[1], eu[0], eu[1], flags — usable directly inside one process
+    cudaIpcMemHandle_t ipc[5];
     int32_t device;
     int32_t pad;
 };
@@ -246,6 +252,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->Fp = (s->Fo + tile - 1) / tile * tile;
     s->pipe_edge = (prm->reserved[0] & 1) == 0;
     s->pipe_cell = (prm->reserved[0] & 2) != 0;
+    s->fused = (prm->reserved[0] & 4) != 0;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -257,6 +264,18 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         std::vector<double2> grad((size_t)Fp, make_double2(0.0, 0.0)), normal((size_t)Fo), vl((size_t)Fvl, make_double2(0.0, 0.0));
         std::vector<double> fcor((size_t)Fp, 0.0), dist((size_t)Fp, 1.0), sw((size_t)Fp * odis::kStencil, 0.0);
         std::vector<int> sid((size_t)Fp * odis::kStencil, -1);
+        std::vector<unsigned long long> cmap((size_t)Fp, ~0ull >> 4);       // all slots "none", no store flags
+        // the edge of each local cell that stores it in the fused kernel: the lowest local edge this rank updates
+        std::vector<int> keeper((size_t)N, -1);
+        for (int en = Fo - 1; en >= 0; en--) {
+            const int eo = s->edge_perm[en];
+            for (int k = 0; k < 2; k++) {
+                const int lc = local_cell(mv->face_nodes[(size_t)eo * 2 + k]);
+                if (lc >= 0) keeper[(size_t)lc] = en;
+            }
+        }
+        for (int cn = 0; cn < N; cn++)
+            if (keeper[(size_t)cn] < 0) s->fused = false;    // a held cell without an updated edge: the two-launch kernels handle it
         int bad = 0;
 #pragma omp parallel for schedule(static)
         for (int en = 0; en < F; en++) vl[en] = make_double2(0.0, mv->face_len[s->edge_perm[en]]);
@@ -289,11 +308,44 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
                 sid[(size_t)j * Fp + en] = le;
                 sw[(size_t)j * Fp + en] = ws[j];
             }
+            // slot map of the two cells (fused kernel): the cell's edges in ascending reference id, each as
+            // "0 = this edge, j+1 = stencil slot j" + a sign bit (set when the cell is that edge's outer cell)
+            unsigned long long cm = 0;
+            const int cref[2] = {c0, c1};
+            for (int k = 0; k < 2; k++) {
+                const int co = cref[k];
+                const int n = (mv->node_friends[(size_t)co * 6 + 5] < 0) ? 5 : 6;
+                int cid[6], cdir[6];
+                for (int j = 0; j < n; j++) { cid[j] = mv->faces[(size_t)co * 6 + j]; cdir[j] = mv->node_face_dir[(size_t)co * 6 + j]; }
+                for (int a = 1; a < n; a++) {
+                    const int id = cid[a], dr = cdir[a];
+                    int b = a - 1;
+                    while (b >= 0 && cid[b] > id) { cid[b + 1] = cid[b]; cdir[b + 1] = cdir[b]; b--; }
+                    cid[b + 1] = id; cdir[b + 1] = dr;
+                }
+                for (int m = 0; m < 6; m++) {
+                    unsigned long long field = 15;
+                    if (m < n) {
+                        int slot = -1;
+                        if (cid[m] == eo) slot = 0;
+                        else
+                            for (int j = 0; j < cnt; j++)
+                                if (ids[j] == cid[m]) slot = j + 1;
+                        if (slot < 0) { bad++; continue; }
+                        field = (unsigned long long)slot | (cdir[m] < 0 ? 16ull : 0ull);
+                    }
+                    cm |= field << ((k * 6 + m) * 5);
+                }
+                const int lc = k == 0 ? cells[en].x : cells[en].y;
+                if (lc >= 0 && keeper[(size_t)lc] == en) cm |= 1ull << (60 + k);
+            }
+            cmap[en] = cm;
         }
         if (bad) return bail(fail(ODIS_ERR_ARG, "face_interp_friends / face_nodes hold out-of-range ids (or the halo is incomplete)"));
         if ((rc = upload(s, &s->d_cells, cells)) || (rc = upload(s, &s->d_grad, grad)) || (rc = upload(s, &s->d_fcor, fcor)) ||
             (rc = upload(s, &s->d_dist, dist)) || (rc = upload(s, &s->d_sid, sid)) || (rc = upload(s, &s->d_sw, sw)) ||
-            (rc = upload(s, &s->d_normal, normal)) || (rc = upload(s, &s->d_vl[0], vl)) || (rc = upload(s, &s->d_vl[1], vl)))
+            (rc = upload(s, &s->d_normal, normal)) || (rc = upload(s, &s->d_vl[0], vl)) || (rc = upload(s, &s->d_vl[1], vl)) ||
+            (rc = upload(s, &s->d_cmap, cmap)))
             return bail(rc);
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
@@ -305,7 +357,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
 #pragma omp parallel for schedule(static) reduction(+ : bad)
         for (int cn = 0; cn < N; cn++) {
             const int co = s->cell_perm[cn];
-            if (cn < No) {
+            {
                 const int n = (mv->node_friends[(size_t)co * 6 + 5] < 0) ? 5 : 6;
                 int ids[6], dirs[6];
                 for (int j = 0; j < n; j++) { ids[j] = mv->faces[(size_t)co * 6 + j]; dirs[j] = mv->node_face_dir[(size_t)co * 6 + j]; }
@@ -343,17 +395,20 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     }
     // ---- state ----
     const int blocks = Fp / 32;             // one energy partial per warp of edges (>= blocks of edge_diagnostics)
-    if ((rc = dev_alloc(s, &s->d_eu, (size_t)Np)) || (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fp)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fp)) ||
-        (rc = dev_alloc(s, &s->d_he[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)Np)) ||
+    if ((rc = dev_alloc(s, &s->d_eu[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_eu[1], (size_t)Np)) ||
+        (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fp)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fp)) ||
+        (rc = dev_alloc(s, &s->d_he[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[2], (size_t)Np)) ||
         (rc = dev_alloc(s, &s->d_block_partial, (size_t)blocks)) || (rc = dev_alloc(s, &s->d_ticket, (size_t)1)) ||
         (rc = dev_alloc(s, &s->d_vavg, (size_t)Fo)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)Fo)))
         return bail(rc);
     if ((rc = upload(s, &s->d_edge_perm, s->edge_perm)) || (rc = upload(s, &s->d_cell_perm, s->cell_perm)) ||
         (rc = dev_alloc(s, &s->d_stage, (size_t)Fg * 3)) || (rc = dev_alloc(s, &s->d_lvl0_v, (size_t)Fo)) ||
-        (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)No)))
+        (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)Np)))
         return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
-    cudaMemsetAsync(s->d_eu, 0, (size_t)Np * sizeof(double2), s->stream);
+    cudaMemsetAsync(s->d_eu[0], 0, (size_t)Np * sizeof(double2), s->stream);
+    cudaMemsetAsync(s->d_eu[1], 0, (size_t)Np * sizeof(double2), s->stream);
+    cudaMemsetAsync(s->d_he[2], 0, (size_t)Np * sizeof(double), s->stream);
     cudaMemsetAsync(s->d_hv[0], 0, (size_t)Fp * sizeof(double), s->stream);
     cudaMemsetAsync(s->d_hv[1], 0, (size_t)Fp * sizeof(double), s->stream);
     cudaMemsetAsync(s->d_he[0], 0, (size_t)Np * sizeof(double), s->stream);
@@ -384,7 +439,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
 
 // one halo exchange: push my boundary values into the peers' ghost slots, publish the epoch, wait for theirs
 int halo_exchange(odis_solver* s, int kind /*0: edges {v,l}, 1: cells {eta,U}*/, const double2* src, int dst_buffer) {
-    const odis::HaloRemote& rem = kind == 0 ? s->remote_v[dst_buffer] : s->remote_c;
+    const odis::HaloRemote& rem = kind == 0 ? s->remote_v[dst_buffer] : s->remote_c[dst_buffer];
     odis::launch_halo_push(kind == 0 ? s->n_send_e : s->n_send_c, kind == 0 ? s->d_send_e_local : s->d_send_c_local,
                            kind == 0 ? s->d_send_e_remote : s->d_send_c_remote, kind == 0 ? s->d_send_e_peer : s->d_send_c_peer, src, rem,
                            s->n_peers, kind * s->world + s->rank, s->epoch, s->d_halo_ticket, s->stream);
@@ -418,9 +473,9 @@ int odis_halo_export(odis_solver* s, void* blob_out) {
     HaloBlob b;
     std::memset(&b, 0, sizeof b);
     b.rank = s->rank; b.world = s->world; b.pid = (int64_t)getpid(); b.device = s->device;
-    b.raw[0] = s->d_vl[0]; b.raw[1] = s->d_vl[1]; b.raw[2] = s->d_eu; b.raw[3] = s->d_flags;
+    b.raw[0] = s->d_vl[0]; b.raw[1] = s->d_vl[1]; b.raw[2] = s->d_eu[0]; b.raw[3] = s->d_eu[1]; b.raw[4] = s->d_flags;
     if (s->world > 1)
-        for (int k = 0; k < 4; k++) ODIS_CUDA(cudaIpcGetMemHandle(&b.ipc[k], b.raw[k]));
+        for (int k = 0; k < 5; k++) ODIS_CUDA(cudaIpcGetMemHandle(&b.ipc[k], b.raw[k]));
     std::memcpy(blob_out, &b, sizeof b);
     return ODIS_OK;
 }
@@ -433,22 +488,23 @@ int odis_halo_connect(odis_solver* s, const void* all_blobs) {
     for (int k = 0; k < s->n_peers; k++) {
         const HaloBlob& b = blobs[s->peer_rank[k]];
         if (b.rank != s->peer_rank[k] || b.world != s->world) return fail(ODIS_ERR_ARG, "halo blobs are not ordered by rank");
-        void* p[4];
+        void* p[5];
         if (b.pid == (int64_t)getpid()) {                       // same process: the raw pointers are usable after enabling peer access
             if (b.device != s->device) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ODIS_ERR_CUDA, "cudaDeviceEnablePeerAccess failed");
                 cudaGetLastError();
             }
-            for (int j = 0; j < 4; j++) p[j] = b.raw[j];
+            for (int j = 0; j < 5; j++) p[j] = b.raw[j];
         } else {
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 5; j++) {
                 ODIS_CUDA(cudaIpcOpenMemHandle(&p[j], b.ipc[j], cudaIpcMemLazyEnablePeerAccess));
                 s->ipc_opened[k][j] = p[j];
             }
         }
-        s->remote_v[0].data[k] = (double2*)p[0]; s->remote_v[1].data[k] = (double2*)p[1]; s->remote_c.data[k] = (double2*)p[2];
-        s->remote_v[0].flags[k] = s->remote_v[1].flags[k] = s->remote_c.flags[k] = (unsigned long long*)p[3];
+        s->remote_v[0].data[k] = (double2*)p[0]; s->remote_v[1].data[k] = (double2*)p[1];
+        s->remote_c[0].data[k] = (double2*)p[2]; s->remote_c[1].data[k] = (double2*)p[3];
+        s->remote_v[0].flags[k] = s->remote_v[1].flags[k] = s->remote_c[0].flags[k] = s->remote_c[1].flags[k] = (unsigned long long*)p[4];
     }
     s->connected = true;
     return ODIS_OK;
@@ -487,21 +543,24 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     s->hv1 = 0;
     odis::launch_scatter_history(Fo, s->d_edge_perm, dvdt ? s->d_stage : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
     if ((rc = stage(eta, (size_t)s->Ng))) return rc;
-    odis::launch_scatter_x(N, s->d_cell_perm, eta ? s->d_stage : nullptr, s->d_eu, 1, s->stream);
+    odis::launch_scatter_x(N, s->d_cell_perm, eta ? s->d_stage : nullptr, s->d_eu[s->ecur], 1, s->stream);
     if ((rc = stage(detadt, (size_t)s->Ng * 3))) return rc;
-    s->he1 = 0;
-    odis::launch_scatter_history(No, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    s->he1 = 0; s->he2 = 1; s->hefree = 2;
+    // the history of every held cell is kept (halo cells are updated locally by the fused kernel)
+    odis::launch_scatter_history(N, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
     s->launches += 4;
     s->iter = iter;
     s->iter0 = iter;
     s->last_mode = -1;
     s->diag_current = false;
     s->have_state = true;
+    s->eta_lag = false;
     // potential for the first step: forcing(current_time + dt), timeIntegrator.cpp:187,218 — for every
-    // local cell, ghosts included (later steps receive the ghosts' potential from their owners)
+    // held cell, halo included
     const double t = s->prm.dt * (double)iter + s->prm.dt;
-    odis::CellState cs{s->d_vl[s->cur], s->d_eu, s->d_he[0], s->d_he[1], nullptr, 0, nullptr};
-    odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), 0, s->prm.block_threads, s->stream);
+    odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr};
+    odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), odis::CELL_UPDATE_U, s->prm.block_threads,
+                           s->stream);
     s->launches++;
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
@@ -534,6 +593,30 @@ int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float
     return rc;
 }
 
+// the cell tendency history is three arrays whose roles rotate (temporalOperators.cpp:44-65 shifts in place)
+static void rotate_cell_history(odis_solver* s, int mode) {
+    const int l1 = s->he1, l2 = s->he2, fr = s->hefree;
+    if (mode == odis::AB3_FIRST) { s->he2 = fr; s->hefree = l2; }                       // level 2 := f0
+    else if (mode == odis::AB3_SECOND) { s->he1 = fr; s->hefree = l1; }                 // level 1 := f0
+    else { s->he1 = fr; s->he2 = l1; s->hefree = l2; }                                  // shift
+}
+
+// fused stepping leaves eta one step behind v; this runs the pending cell update (all held cells, so the
+// halo stays consistent) and keeps the potential the next edge update needs
+static int finalize_eta(odis_solver* s) {
+    if (!s->eta_lag) return ODIS_OK;
+    odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
+                       nullptr, 0, nullptr};
+    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, s->mode_lag, odis::StepScalars{}, odis::CELL_UPDATE_ETA, s->prm.block_threads,
+                           s->stream);
+    s->launches++;
+    ODIS_CUDA(cudaGetLastError());
+    rotate_cell_history(s, s->mode_lag);
+    s->ecur = 1 - s->ecur;
+    s->eta_lag = false;
+    return ODIS_OK;
+}
+
 static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* marks) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (!s->have_state) return fail(ODIS_ERR_STATE, "odis_set_state has not been called");
@@ -543,11 +626,46 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
     if (rc) return rc;
     if (s->world > 1 && !s->connected) return fail(ODIS_ERR_STATE, "odis_halo_connect has not been called on this partitioned solver");
     const odis::EdgeTables et = s->edge_tables();
+    if (s->fused) {
+        odis::FusedTables ft;
+        ft.e = et; ft.cmap = s->d_cmap; ft.area = s->d_area; ft.trig = s->d_trig; ft.trig_sq = s->d_trig_sq; ft.cell_stride = s->Np;
+        for (int k = 0; k < nsteps; k++) {
+            const int mode = ab3_mode(s, s->iter);
+            odis::FusedState fs;
+            fs.vl_in = s->d_vl[s->cur]; fs.vl_out = s->d_vl[1 - s->cur];
+            fs.eu_in = s->d_eu[s->ecur]; fs.eu_out = s->d_eu[1 - s->ecur];
+            fs.h1 = s->d_hv[s->hv1]; fs.h2 = s->d_hv[1 - s->hv1];
+            fs.ch1 = s->d_he[s->he1]; fs.ch2 = s->d_he[s->he2]; fs.chw = s->d_he[s->hefree];
+            fs.block_partial = s->d_block_partial; fs.ticket = s->d_ticket;
+            fs.energy_out = s->d_series + (s->iter - s->iter0);
+            const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
+            if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
+            ODIS_CUDA(odis::launch_step_fused(ft, s->phys, fs, mode, s->mode_lag, s->eta_lag ? 1 : 0, step_scalars(s->prm.omega, tnext), s->stream));
+            if (s->eta_lag) rotate_cell_history(s, s->mode_lag);
+            s->ecur = 1 - s->ecur;
+            if (s->world > 1) {                   // one exchange per step: v^{n+1} of my boundary edges
+                s->epoch++;
+                int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
+                if (rc2) return rc2;
+            }
+            if (marks) { cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream); cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream); }
+            if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
+            s->cur = 1 - s->cur;
+            s->iter++;
+            s->last_mode = mode;
+            s->eta_lag = true;
+            s->mode_lag = mode;
+            s->launches += 1;
+        }
+        if (nsteps > 0) s->diag_current = false;
+        ODIS_CUDA(cudaGetLastError());
+        return ODIS_OK;
+    }
     const odis::CellTables ct = s->cell_tables(s->No);
     for (int k = 0; k < nsteps; k++) {
         const int mode = ab3_mode(s, s->iter);
         odis::EdgeState es;
-        es.vl_in = s->d_vl[s->cur]; es.vl_out = s->d_vl[1 - s->cur]; es.eu = s->d_eu;
+        es.vl_in = s->d_vl[s->cur]; es.vl_out = s->d_vl[1 - s->cur]; es.eu = s->d_eu[s->ecur];
         es.h1 = s->d_hv[s->hv1]; es.h2 = s->d_hv[1 - s->hv1];
         es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
         es.energy_out = s->d_series + (s->iter - s->iter0);
@@ -561,18 +679,20 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         }
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
         if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
-        odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu, s->d_he[s->he1], s->d_he[1 - s->he1],
+        odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
                            s->d_block_partial, (s->Fo + 31) / 32, es.energy_out};
         // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
         const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
         if (s->pipe_cell) ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), s->stream));
-        else odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), 1, s->prm.block_threads, s->stream);
+        else odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U,
+                                    s->prm.block_threads, s->stream);
+        rotate_cell_history(s, mode);
+        s->ecur = 1 - s->ecur;
         if (s->world > 1) {                       // {eta^{n+1}, U} of my boundary cells -> the neighbours' halos
-            int rc2 = halo_exchange(s, 1, s->d_eu, 0);
+            int rc2 = halo_exchange(s, 1, s->d_eu[s->ecur], s->ecur);
             if (rc2) return rc2;
         }
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream);
-        if (mode == odis::AB3_FULL) s->he1 = 1 - s->he1;
         s->cur = 1 - s->cur;
         s->iter++;
         s->last_mode = mode;
@@ -604,6 +724,10 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     ODIS_CUDA(cudaSetDevice(s->device));
     const int No = s->No, Fo = s->Fo;
     size_t count = 0;
+    {
+        int rcf = finalize_eta(s);
+        if (rcf) return rcf;
+    }
     // a partitioned solver fills its own cells/edges of the global array and leaves zeros elsewhere
     // (the caller sums the ranks' arrays)
     auto clear = [&](size_t n) { if (s->world > 1) cudaMemsetAsync(s->d_stage, 0, n * sizeof(double), s->stream); };
@@ -615,7 +739,7 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
         case ODIS_FIELD_ETA:
         case ODIS_FIELD_POTENTIAL:
             count = (size_t)s->Ng; clear(count);
-            odis::launch_gather_component(No, s->d_cell_perm, s->d_eu, field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
+            odis::launch_gather_component(No, s->d_cell_perm, s->d_eu[s->ecur], field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
             break;
         case ODIS_FIELD_DVDT:
         case ODIS_FIELD_DETADT: {
@@ -627,7 +751,7 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
                 odis::launch_gather_history(Fo, s->d_edge_perm, s->d_lvl0_v, s->d_hv[s->hv1], s->d_hv[1 - s->hv1], which0, s->d_stage, s->stream);
             } else {
                 count = (size_t)s->Ng * 3; clear(count);
-                odis::launch_gather_history(No, s->d_cell_perm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[1 - s->he1], which0, s->d_stage, s->stream);
+                odis::launch_gather_history(No, s->d_cell_perm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[s->he2], which0, s->d_stage, s->stream);
             }
             break;
         }
@@ -715,12 +839,12 @@ void odis_destroy(odis_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_normal, s->d_eid, s->d_area, s->d_trig,
-                    s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu, s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1],
+                    s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,
                     s->d_send_c_peer, s->d_flags, s->d_halo_ticket};
     for (int k = 0; k < kMaxPeers; k++)
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < 5; j++)
             if (s->ipc_opened[k][j]) cudaIpcCloseMemHandle(s->ipc_opened[k][j]);
     for (void* p : ptrs)
         if (p) cudaFree(p);

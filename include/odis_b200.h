@@ -142,8 +142,10 @@ typedef struct odis_params {
     int32_t init_load;      /* 1: AB3 uses the 3-level formula from step 0 (temporalOperators.cpp:36) */
     int32_t reorder;        /* 1: locality (space-filling-curve) renumbering on device; 0: reference order */
     int32_t block_threads;  /* 0 = default */
-    int32_t reserved[4];    /* [0] kernel selection, 0 = default (bulk-async staged edge kernel + direct-load cell kernel);
-                             *     bit 0: direct-load edge kernel, bit 1: bulk-async staged cell kernel. Rest must be 0. */
+    int32_t reserved[4];    /* [0] kernel selection, 0 = default: two launches per step, bulk-async staged edge kernel +
+                             *     direct-load cell kernel. bit 0: direct-load edge kernel; bit 1: staged cell kernel; bit 2: ONE fused
+                             *     kernel per step (cell update of the previous step + edge update; one halo exchange per step).
+                             *     Every selection gives bit-identical fields. Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {

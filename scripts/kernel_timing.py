@@ -16,8 +16,9 @@ prm = dict(g=0.113, h=38e3, alpha=1e-7, dt=0.2 * dmin / np.sqrt(0.113 * 38e3), r
 if level <= 6:   # correctness guard on small grids
     o = LteOracle(mesh.tables, {k: v for k, v in prm.items() if k not in ("semimajor_axis", "reorder")}); o.set_state(); o.step(20)
 for bt in blocks:
-    # block size 0: default (staged edge + direct cell); -2: both staged; > 0: both direct with that block size
-    sel = 1 if bt > 0 else (2 if bt == -2 else 0)
+    # block size 0: fused one-launch step; -1: default (two-launch staged edge + direct cell); -2: two-launch both staged;
+    # > 0: two-launch both direct with that block size
+    sel = 1 if bt > 0 else (2 if bt == -2 else (0 if bt == -1 else 4))
     s = odis.Solver(mesh, dict(prm, block_threads=max(bt, 0), kernel_select=sel))
     if level <= 6:
         s.step(20)

@@ -23,7 +23,7 @@ def test_full_orbit_run_matches_reference_outputs(odis, tmp_path):
     res = odis.run(d)
     assert res["steps"] == int(case["nsteps"]) == 1200 and res["dumps"] == 11 and res["interrupted"] == 0
     assert res["steps_per_period"] == int(case["scalar_totalIter"][0]) and res["dt"] == float(case["scalar_timeStep"][0])
-    assert res["kernel_launches"] >= 2 * 1200
+    assert res["kernel_launches"] >= 1200
     h5 = read_h5(os.path.join(d, "DATA", "data.h5"))
     ref = {k[3:]: case[k] for k in case if k.startswith("h5_")}
     assert sorted(h5) == sorted(ref)                                   # same dataset names (src/outFiles.cpp:250-338,500,509)

@@ -106,7 +106,8 @@ def test_cuda_matches_oracle_random_state(odis, potential, friction):
 
 @pytest.mark.parametrize("level", [3, 6])
 def test_direct_and_pipelined_kernels_agree(odis, level):
-    """The two kernel generations (direct loads / bulk-async staged) are the same arithmetic."""
+    """Every kernel variant (fused one-launch step; two-launch with direct-load or staged kernels) is the same
+    arithmetic: bit-identical fields."""
     pos, fr, cen = odis.generate_grid(level)
     mesh = odis.Mesh.from_arrays(pos, fr, cen, 1.0e6)
     prm = dict(g=1.3, h=1.0e3, alpha=1e-6, dt=20.0, radius=1.0e6, omega=2e-5, love_reduct=1.0, ecc=0.01, obl=0.01,
@@ -114,7 +115,7 @@ def test_direct_and_pipelined_kernels_agree(odis, level):
     rng = np.random.default_rng(5)
     v0, e0 = rng.uniform(-1, 1, mesh.n_edges) * 1e-2, rng.uniform(-1, 1, mesh.n_cells)
     out = []
-    for sel in (0, 1, 2, 3):                 # every combination of direct-load / staged edge and cell kernels
+    for sel in (0, 1, 2, 3, 4):              # every two-launch combination (0 = default) and the fused one-launch step
         s = odis.Solver(mesh, dict(prm, kernel_select=sel))
         s.set_state(v0, e0)
         s.step(33)
