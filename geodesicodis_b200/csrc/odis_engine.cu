@@ -679,8 +679,9 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         }
         if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
         if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
+        // the staged edge kernel finishes its own energy sum; the direct one leaves per-warp partials to the cell kernel
         odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
-                           s->d_block_partial, (s->Fo + 31) / 32, es.energy_out};
+                           s->d_block_partial, (s->Fo + 31) / 32, s->pipe_edge ? nullptr : es.energy_out};
         // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
         const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
         if (s->pipe_cell) ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), s->stream));

@@ -5,26 +5,32 @@ namespace odis {
 
 namespace {
 
-// Streaming (read-once) table loads: keep them out of L1 so that L1 holds the gathered
-// velocity / displacement neighbourhoods instead.
+// Streaming (read-once) table loads: keep them out of L1 so that L1 holds the gathered velocity / displacement
+// neighbourhoods instead, and tag them evict-first in L2 so that they do not push the state arrays the next kernel
+// gathers from ({v,l}, {eta,U}) out of the 126 MB L2.
+__device__ __forceinline__ unsigned long long stream_policy() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ int ld_stream(const int* p) {
     int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(stream_policy()));
     return v;
 }
 __device__ __forceinline__ double ld_stream(const double* p) {
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(stream_policy()));
     return v;
 }
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
     double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(stream_policy()));
     return v;
 }
 __device__ __forceinline__ int2 ld_stream(const int2* p) {
     int2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(stream_policy()));
     return v;
 }
 // Gathered loads of field values that other kernels write (plain coherent loads, cached). volatile asm:

@@ -72,9 +72,10 @@ struct EdgeState {
     const double2* eu;        // [N] {eta^n, U(t_n+dt)}
     double* h1;               // [F] dv/dt of step n-1
     double* h2;               // [F] dv/dt of step n-2
-    double* block_partial;    // [ceil(F/32)] per-warp sums of eps_e * A_e for v^n (finished by the next cell_step)
-    unsigned int* ticket;     // unused by edge_step (edge_diagnostics' last-block counter)
-    double* energy_out;       // where the finished sum goes (series[iter]); consumed by cell_step
+    double* block_partial;    // direct kernel: [ceil(F/32)] per-warp sums of eps_e * A_e for v^n, finished by the next cell_step;
+                              // staged kernel: [grid] per-CTA sums, finished by its own last CTA
+    unsigned int* ticket;     // last-CTA-done counter (staged kernel, edge_diagnostics)
+    double* energy_out;       // where the finished sum goes (series[iter])
 };
 
 struct CellState {

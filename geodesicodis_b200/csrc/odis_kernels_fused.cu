@@ -53,9 +53,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
+// read-once table rows are tagged evict-first in L2 so that they do not push the gathered state ({v,l}, {eta,U}),
+// which the next kernel re-reads, out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ double2 ld_gather(const double2* p) {
@@ -194,6 +201,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kStages;
                 if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
@@ -201,17 +209,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
                 const size_t e0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile;
                 mbar_expect_tx(full + st, kFusedStageBytes);
 #pragma unroll
-                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sid[j], t.e.sid + j * S + e0, kTile * 4, full + st);
+                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sid[j], t.e.sid + j * S + e0, kTile * 4, full + st, pol);
 #pragma unroll
-                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sw[j], t.e.sw + j * S + e0, kTile * 8, full + st);
-                bulk_g2s(d->cells, t.e.cells + e0, kTile * 8, full + st);
-                bulk_g2s(d->grad, t.e.grad + e0, kTile * 16, full + st);
-                bulk_g2s(d->dist, t.e.dist + e0, kTile * 8, full + st);
-                bulk_g2s(d->fcor, t.e.fcor + e0, kTile * 8, full + st);
-                bulk_g2s(d->own, s.vl_in + e0, kTile * 16, full + st);
-                bulk_g2s(d->h1, s.h1 + e0, kTile * 8, full + st);
-                bulk_g2s(d->h2, s.h2 + e0, kTile * 8, full + st);
-                bulk_g2s(d->cmap, t.cmap + e0, kTile * 8, full + st);
+                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sw[j], t.e.sw + j * S + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->cells, t.e.cells + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->grad, t.e.grad + e0, kTile * 16, full + st, pol);
+                bulk_g2s(d->dist, t.e.dist + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->fcor, t.e.fcor + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->own, s.vl_in + e0, kTile * 16, full + st, pol);
+                bulk_g2s(d->h1, s.h1 + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->h2, s.h2 + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->cmap, t.cmap + e0, kTile * 8, full + st, pol);
             }
         }
         return;

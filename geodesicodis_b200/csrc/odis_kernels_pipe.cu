@@ -50,9 +50,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 // global -> shared bulk copy (TMA, 1-D), completion bytes counted on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
+// read-once table rows are tagged evict-first in L2 so that they do not push the gathered state ({v,l}, {eta,U}),
+// which the next kernel re-reads, out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ double2 ld_gather(const double2* p) {
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kStages;
                 if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
@@ -124,16 +132,16 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
                 const size_t e0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile;
                 mbar_expect_tx(full + st, kEdgeStageBytes);
 #pragma unroll
-                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sid[j], t.sid + j * S + e0, kTile * 4, full + st);
+                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sid[j], t.sid + j * S + e0, kTile * 4, full + st, pol);
 #pragma unroll
-                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sw[j], t.sw + j * S + e0, kTile * 8, full + st);
-                bulk_g2s(d->cells, t.cells + e0, kTile * 8, full + st);
-                bulk_g2s(d->grad, t.grad + e0, kTile * 16, full + st);
-                bulk_g2s(d->dist, t.dist + e0, kTile * 8, full + st);
-                bulk_g2s(d->fcor, t.fcor + e0, kTile * 8, full + st);
-                bulk_g2s(d->own, s.vl_in + e0, kTile * 16, full + st);
-                bulk_g2s(d->h1, s.h1 + e0, kTile * 8, full + st);
-                bulk_g2s(d->h2, s.h2 + e0, kTile * 8, full + st);
+                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sw[j], t.sw + j * S + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->cells, t.cells + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->grad, t.grad + e0, kTile * 16, full + st, pol);
+                bulk_g2s(d->dist, t.dist + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->fcor, t.fcor + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->own, s.vl_in + e0, kTile * 16, full + st, pol);
+                bulk_g2s(d->h1, s.h1 + e0, kTile * 8, full + st, pol);
+                bulk_g2s(d->h2, s.h2 + e0, kTile * 8, full + st, pol);
             }
         }
         return;
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
     // ---- consumers: group g takes this CTA's tiles g, g+kGroups, ... ----
     const int g = (warp - 1) / (kTile / 32);
     const int tl = (int)threadIdx.x - 32 - g * kTile;       // 0..127 within the tile
+    double warp_energy = 0.0;                               // lane 0: this warp's tiles, in tile order
     for (int i = g; i < my_tiles; i += kGroups) {
         const int st = i % kStages;
         const EdgeStage* d = stages + st;
@@ -184,7 +193,32 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);          // this warp no longer reads the stage
         for (int o = 16; o > 0; o >>= 1) e_area += __shfl_down_sync(0xffffffffu, e_area, o);
-        if (lane == 0) s.block_partial[e >> 5] = e_area;
+        warp_energy += e_area;
+    }
+    // energy diagnostic (energy.cpp:36-40 sums serially): warp sums -> CTA sum -> the last CTA to finish adds the
+    // CTA sums in index order. Every level has a fixed order, so the result is reproducible.
+    constexpr int kConsumerWarps = kGroups * kTile / 32;
+    __shared__ double warp_sums[kConsumerWarps];
+    __shared__ bool is_last;
+    if (lane == 0) warp_sums[warp - 1] = warp_energy;
+    asm volatile("bar.sync 1, %0;" ::"n"(kGroups * kTile) : "memory");      // consumers only (the producer warp has left)
+    if (threadIdx.x == 32) {
+        double tot = 0.0;
+        for (int w = 0; w < kConsumerWarps; w++) tot += warp_sums[w];
+        s.block_partial[blockIdx.x] = tot;
+        __threadfence();
+        is_last = (atomicAdd(s.ticket, 1u) == gridDim.x - 1);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kGroups * kTile) : "memory");
+    if (is_last && warp == 1) {
+        __threadfence();
+        double acc = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) acc += ((volatile double*)s.block_partial)[b];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            *s.energy_out = acc;
+            *s.ticket = 0u;
+        }
     }
 }
 
@@ -292,6 +326,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTab
     const int my_tiles = (n_tiles - (int)blockIdx.x + n_workers - 1) / n_workers;
     if (warp == 0) {
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kStages;
                 if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
@@ -299,15 +334,15 @@ __global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTab
                 const size_t c0 = ((size_t)blockIdx.x + (size_t)i * n_workers) * kTile;
                 mbar_expect_tx(full + st, stage_bytes);
 #pragma unroll
-                for (int j = 0; j < kCellEdges; j++) bulk_g2s(d->eid[j], t.eid + j * S + c0, kTile * 4, full + st);
-                bulk_g2s(d->area, t.area + c0, kTile * 8, full + st);
-                bulk_g2s(d->eu, s.eu_in + c0, kTile * 16, full + st);
-                bulk_g2s(d->h1, s.h1 + c0, kTile * 8, full + st);
-                bulk_g2s(d->h2, s.h2 + c0, kTile * 8, full + st);
+                for (int j = 0; j < kCellEdges; j++) bulk_g2s(d->eid[j], t.eid + j * S + c0, kTile * 4, full + st, pol);
+                bulk_g2s(d->area, t.area + c0, kTile * 8, full + st, pol);
+                bulk_g2s(d->eu, s.eu_in + c0, kTile * 16, full + st, pol);
+                bulk_g2s(d->h1, s.h1 + c0, kTile * 8, full + st, pol);
+                bulk_g2s(d->h2, s.h2 + c0, kTile * 8, full + st, pol);
                 for (int k = 0; k < rows.n; k++) {
                     const int r = rows.row[k];
                     const double* src = r < 8 ? t.trig + (size_t)r * S + c0 : t.trig_sq + (size_t)(r - 8) * S + c0;
-                    bulk_g2s(d->trig[k], src, kTile * 8, full + st);
+                    bulk_g2s(d->trig[k], src, kTile * 8, full + st, pol);
                 }
             }
         }
