@@ -21,21 +21,25 @@ def build_oracle(force: bool = False) -> str:
     return LIB
 
 
-def build_reference(levels=(3, 4, 5, 6), reference_root: str = "/root/reference") -> list[str]:
-    """Build oracle/_ref/odis_ref_l<L> from the unmodified reference sources. No-op (returns what is
-    already there) when the reference tree is absent, e.g. on the GPU box."""
-    have = [os.path.join(REF_DIR, f"odis_ref_l{L}") for L in levels]
+def build_reference(levels=(3, 4, 5, 6), reference_root: str = "/root/reference", openmp_levels=()) -> list[str]:
+    """Build oracle/_ref/odis_ref_l<L> from the unmodified reference sources (and, for `openmp_levels`, the
+    -fopenmp variant odis_ref_l<L>_omp that bench.py's reference arm runs on all host cores). No-op (returns
+    what is already there) when the reference tree is absent, e.g. on the GPU box."""
+    have = [os.path.join(REF_DIR, f"odis_ref_l{L}") for L in levels] + [os.path.join(REF_DIR, f"odis_ref_l{L}_omp") for L in openmp_levels]
     if not os.path.isdir(os.path.join(reference_root, "src")):
         return [p for p in have if os.path.exists(p)]
-    cmd = ["make", "-C", os.path.join(HERE, "ref_build"), f"REF={reference_root}", "LEVELS=" + " ".join(str(L) for L in levels), "-j8"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("reference build failed:\n" + r.stdout[-4000:])
+    for lv, extra in ((levels, []), (openmp_levels, ["OPENMP=1"])):
+        if not lv:
+            continue
+        cmd = ["make", "-C", os.path.join(HERE, "ref_build"), f"REF={reference_root}", "LEVELS=" + " ".join(str(L) for L in lv), *extra, "-j8"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference build failed:\n" + r.stdout[-4000:])
     return [p for p in have if os.path.exists(p)]
 
 
-def reference_binary(level: int) -> str | None:
-    p = os.path.join(REF_DIR, f"odis_ref_l{level}")
+def reference_binary(level: int, openmp: bool = False) -> str | None:
+    p = os.path.join(REF_DIR, f"odis_ref_l{level}" + ("_omp" if openmp else ""))
     return p if os.path.exists(p) else None
 
 

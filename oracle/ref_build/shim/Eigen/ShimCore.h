@@ -297,6 +297,11 @@ template <typename S, int Opt>
 inline VecResult spmv(const SparseMatrix<S, Opt>& A, const double* x) {
     A.flush();
     VecResult r; r.v.assign((size_t)A.nr, 0.0);
+    // Eigen runs row-major sparse * dense products row-parallel when built with OpenMP (rows are independent,
+    // so results do not depend on the thread count); only the OPENMP=1 variant of the Makefile enables it
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
     for (int i = 0; i < A.nr; i++) {
         double tmp = 0;
         for (int k = A.ptr[i]; k < A.ptr[(size_t)i + 1]; k++) tmp += A.val[k] * x[A.idx[k]];
@@ -308,6 +313,9 @@ template <typename S, int Opt>
 inline VecResult spmv_scaled(S s, const SparseMatrix<S, Opt>& A, const double* x) {
     A.flush();
     VecResult r; r.v.assign((size_t)A.nr, 0.0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
     for (int i = 0; i < A.nr; i++) {
         double tmp = 0;
         for (int k = A.ptr[i]; k < A.ptr[(size_t)i + 1]; k++) tmp += (s * A.val[k]) * x[A.idx[k]];
