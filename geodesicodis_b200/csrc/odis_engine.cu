@@ -5,9 +5,11 @@
 // allocation, :205-313 loop). Memory kept per edge: {v,l_e} x2 (ping-pong), two AB3 history levels;
 // per cell: {eta,U}, two history levels — the reference keeps 11 F-sized and 13 N-sized arrays and
 // physically shifts its [.,3] histories every step.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -74,6 +76,11 @@ struct odis_solver {
     unsigned int* d_ticket = nullptr;
     double* d_series = nullptr;
     size_t series_cap = 0;
+    odis::StepCtl* d_ctl = nullptr;          // device-side step counter / halo epochs / current time factors
+    odis::StepScalars* d_scal = nullptr;     // [series_cap] host-evaluated time factors of step k since set_state
+    bool use_graph = true;                   // params.reserved[0] bit 3 clear: steady-state steps replay captured CUDA graphs
+    std::map<unsigned, cudaGraphExec_t> graphs;   // one per phase of the buffer rotation (period 6 steps)
+    int64_t graph_launches = 0;
     double2* d_vavg = nullptr;
     double* d_ediss = nullptr;
     int *d_edge_perm = nullptr, *d_cell_perm = nullptr;   // local id -> reference id, for renumbering on the device
@@ -87,11 +94,15 @@ struct odis_solver {
     int n_send_e = 0, n_send_c = 0;
     int *d_send_e_local = nullptr, *d_send_e_remote = nullptr, *d_send_e_peer = nullptr;
     int *d_send_c_local = nullptr, *d_send_c_remote = nullptr, *d_send_c_peer = nullptr;
+    // the edge send list as CSR over the boundary-first own numbering, for the exchange fused into the edge kernel
+    int Fb = 0;                                            // boundary edges: local ids [0, Fb)
+    int wait_from = 0;                                     // cells [wait_from, N) read ghost edges (own boundary cells, ghost cells)
+    int *d_csr_e_first = nullptr, *d_csr_e_peer = nullptr, *d_csr_e_remote = nullptr;
+    unsigned int* d_halo_done = nullptr;                   // boundary tiles finished
     unsigned long long* d_flags = nullptr;                 // [2][world] epochs written by the peers
     unsigned int* d_halo_ticket = nullptr;
     odis::HaloRemote remote_v[2], remote_c[2];             // peers' vl[0], vl[1], eu[0], eu[1] + their flag arrays
     void* ipc_opened[kMaxPeers][5] = {{nullptr}};
-    unsigned long long epoch = 0;
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
@@ -159,24 +170,36 @@ int ensure_series(odis_solver* s, size_t need) {
     size_t cap = s->series_cap ? s->series_cap : 4096;
     while (cap < need) cap *= 2;
     double* nd = nullptr;
+    odis::StepScalars* ns = nullptr;
     ODIS_CUDA(cudaMalloc((void**)&nd, cap * sizeof(double)));
+    ODIS_CUDA(cudaMalloc((void**)&ns, cap * sizeof(odis::StepScalars)));
     ODIS_CUDA(cudaMemsetAsync(nd, 0, cap * sizeof(double), s->stream));
+    ODIS_CUDA(cudaMemsetAsync(ns, 0, cap * sizeof(odis::StepScalars), s->stream));
     if (s->d_series) {
         ODIS_CUDA(cudaMemcpyAsync(nd, s->d_series, s->series_cap * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        ODIS_CUDA(cudaMemcpyAsync(ns, s->d_scal, s->series_cap * sizeof(odis::StepScalars), cudaMemcpyDeviceToDevice, s->stream));
         ODIS_CUDA(cudaStreamSynchronize(s->stream));
         cudaFree(s->d_series);
-        s->device_bytes -= s->series_cap * sizeof(double);
+        cudaFree(s->d_scal);
+        s->device_bytes -= s->series_cap * (sizeof(double) + sizeof(odis::StepScalars));
+        // captured graphs hold the old table addresses
+        for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);
+        s->graphs.clear();
     }
-    s->device_bytes += cap * sizeof(double);
+    s->device_bytes += cap * (sizeof(double) + sizeof(odis::StepScalars));
     s->d_series = nd;
+    s->d_scal = ns;
     s->series_cap = cap;
     return ODIS_OK;
 }
+
+int halo_drain(odis_solver* s);
 
 int run_diagnostics(odis_solver* s, bool want_fields) {
     if (s->diag_current && !want_fields) return ODIS_OK;
     int rc = ensure_series(s, (size_t)(s->iter - s->iter0) + 1);
     if (rc) return rc;
+    if ((rc = halo_drain(s))) return rc;
     odis::launch_edge_diagnostics(s->edge_tables(), s->phys, s->d_vl[s->cur], s->d_normal, want_fields ? s->d_vavg : nullptr,
                                   want_fields ? s->d_ediss : nullptr, s->d_block_partial, s->d_ticket,
                                   s->d_series + (s->iter - s->iter0), s->prm.block_threads, s->stream);
@@ -253,6 +276,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->pipe_edge = (prm->reserved[0] & 1) == 0;
     s->pipe_cell = (prm->reserved[0] & 2) != 0;
     s->fused = (prm->reserved[0] & 4) != 0;
+    s->use_graph = (prm->reserved[0] & 8) == 0;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -399,6 +423,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fp)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fp)) ||
         (rc = dev_alloc(s, &s->d_he[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[2], (size_t)Np)) ||
         (rc = dev_alloc(s, &s->d_block_partial, (size_t)blocks)) || (rc = dev_alloc(s, &s->d_ticket, (size_t)1)) ||
+        (rc = dev_alloc(s, &s->d_ctl, (size_t)1)) ||
         (rc = dev_alloc(s, &s->d_vavg, (size_t)Fo)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)Fo)))
         return bail(rc);
     if ((rc = upload(s, &s->d_edge_perm, s->edge_perm)) || (rc = upload(s, &s->d_cell_perm, s->cell_perm)) ||
@@ -406,6 +431,8 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)Np)))
         return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
+    cudaMemsetAsync(s->d_ctl, 0, sizeof(odis::StepCtl), s->stream);
+    if (cudaSuccess != odis::pipe_configure()) return bail(fail(ODIS_ERR_CUDA, "cudaFuncSetAttribute(shared memory size) failed"));
     cudaMemsetAsync(s->d_eu[0], 0, (size_t)Np * sizeof(double2), s->stream);
     cudaMemsetAsync(s->d_eu[1], 0, (size_t)Np * sizeof(double2), s->stream);
     cudaMemsetAsync(s->d_he[2], 0, (size_t)Np * sizeof(double), s->stream);
@@ -430,6 +457,33 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
             return bail(rc);
         cudaMemsetAsync(s->d_flags, 0, (size_t)2 * world * sizeof(unsigned long long), s->stream);
         cudaMemsetAsync(s->d_halo_ticket, 0, sizeof(unsigned int), s->stream);
+        // CSR form of the edge send list over the boundary edges (first in the own numbering, odis_partition.h). At
+        // least one boundary tile, so that a rank with nothing to send still publishes its epoch.
+        s->Fb = std::max(1, s->part.n_bnd_edges);
+        s->wait_from = std::min(No - s->part.n_bnd_cells, N - 1);     // at least the last CTA waits
+        std::vector<int> first((size_t)s->Fb + 1, 0), pk, rm;
+        for (int k = 0; k < s->n_peers; k++)
+            for (int l : s->part.peers[(size_t)k].send_edge_local) {
+                if (l < 0 || l >= s->part.n_bnd_edges) return bail(fail(ODIS_ERR_STATE, "send list outside the boundary range"));
+                first[(size_t)l + 1]++;
+            }
+        for (int i = 0; i < s->Fb; i++) first[(size_t)i + 1] += first[(size_t)i];
+        pk.assign((size_t)first[(size_t)s->Fb], 0); rm.assign((size_t)first[(size_t)s->Fb], 0);
+        {
+            std::vector<int> fill(first.begin(), first.end() - 1);
+            for (int k = 0; k < s->n_peers; k++) {
+                const odis::HaloPeer& peer = s->part.peers[(size_t)k];
+                for (size_t i = 0; i < peer.send_edge_local.size(); i++) {
+                    const int at = fill[(size_t)peer.send_edge_local[i]]++;
+                    pk[(size_t)at] = k; rm[(size_t)at] = peer.send_edge_remote[i];
+                }
+            }
+        }
+        if ((rc = upload(s, &s->d_csr_e_first, first)) || (rc = upload(s, &s->d_csr_e_peer, pk)) || (rc = upload(s, &s->d_csr_e_remote, rm)) ||
+            (rc = dev_alloc(s, &s->d_halo_done, (size_t)1)))
+            return bail(rc);
+        cudaMemsetAsync(s->d_halo_done, 0, sizeof(unsigned int), s->stream);
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "halo table upload failed"));
     }
     *out = s;
     rc = odis_set_state(s, nullptr, nullptr, nullptr, nullptr, 0);
@@ -437,17 +491,60 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     return ODIS_OK;
 }
 
-// one halo exchange: push my boundary values into the peers' ghost slots, publish the epoch, wait for theirs
+// one halo exchange (one launch): push my boundary values into the peers' ghost slots, publish the epoch, wait for theirs
 int halo_exchange(odis_solver* s, int kind /*0: edges {v,l}, 1: cells {eta,U}*/, const double2* src, int dst_buffer) {
     const odis::HaloRemote& rem = kind == 0 ? s->remote_v[dst_buffer] : s->remote_c[dst_buffer];
-    odis::launch_halo_push(kind == 0 ? s->n_send_e : s->n_send_c, kind == 0 ? s->d_send_e_local : s->d_send_c_local,
-                           kind == 0 ? s->d_send_e_remote : s->d_send_c_remote, kind == 0 ? s->d_send_e_peer : s->d_send_c_peer, src, rem,
-                           s->n_peers, kind * s->world + s->rank, s->epoch, s->d_halo_ticket, s->stream);
     odis::HaloWait w;
     w.n_peers = s->n_peers;
     for (int k = 0; k < s->n_peers; k++) w.flag[k] = s->d_flags + (size_t)kind * s->world + s->peer_rank[k];
-    odis::launch_halo_wait(w, s->epoch, s->stream);
-    s->launches += 2;
+    odis::launch_halo_exchange(kind == 0 ? s->n_send_e : s->n_send_c, kind == 0 ? s->d_send_e_local : s->d_send_c_local,
+                               kind == 0 ? s->d_send_e_remote : s->d_send_c_remote, kind == 0 ? s->d_send_e_peer : s->d_send_c_peer, src, rem, w,
+                               kind * s->world + s->rank, kind, s->d_ctl, s->d_halo_ticket, s->stream);
+    s->launches += 1;
+    ODIS_CUDA(cudaGetLastError());
+    return ODIS_OK;
+}
+
+odis::HaloWait halo_wait_of(const odis_solver* s, int kind) {
+    odis::HaloWait w;
+    w.n_peers = s->n_peers;
+    for (int k = 0; k < s->n_peers; k++) w.flag[k] = s->d_flags + (size_t)kind * s->world + s->peer_rank[k];
+    return w;
+}
+
+// descriptors of the exchange fused into the step kernels (HaloInline): the edge kernel pushes, the cell kernel waits
+odis::HaloInline halo_inline_edge(const odis_solver* s, int dst_buffer) {
+    odis::HaloInline h;
+    h.n_bnd = s->Fb;
+    h.wait_from = 0x7fffffff;
+    h.n_peers = s->n_peers;
+    h.flag_slot = s->rank;
+    h.send_first = s->d_csr_e_first; h.send_peer = s->d_csr_e_peer; h.send_remote = s->d_csr_e_remote;
+    h.remote = s->remote_v[dst_buffer];
+    h.wait_v = halo_wait_of(s, 0);
+    h.done = s->d_halo_done;
+    h.ctl = s->d_ctl;
+    return h;
+}
+odis::HaloInline halo_inline_cell(const odis_solver* s) {
+    odis::HaloInline h;
+    h.n_bnd = 0;
+    h.wait_from = s->wait_from;
+    h.n_peers = s->n_peers;
+    h.flag_slot = s->rank;
+    h.send_first = h.send_peer = h.send_remote = nullptr;
+    h.wait_v = halo_wait_of(s, 0);
+    h.done = nullptr;
+    h.ctl = s->d_ctl;
+    return h;
+}
+
+// wait (bounded) until every push of the exchanges this rank took part in has landed: before the state is overwritten or
+// read back, and in front of a cell kernel variant that does not wait itself
+int halo_drain(odis_solver* s) {
+    if (s->world <= 1 || !s->connected) return ODIS_OK;
+    odis::launch_halo_drain(halo_wait_of(s, 0), s->d_ctl, s->stream);
+    s->launches++;
     ODIS_CUDA(cudaGetLastError());
     return ODIS_OK;
 }
@@ -537,6 +634,7 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
         return ODIS_OK;
     };
     int rc;
+    if ((rc = halo_drain(s))) return rc;
     if ((rc = stage(v, (size_t)s->Fg))) return rc;
     odis::launch_scatter_x(F, s->d_edge_perm, v ? s->d_stage : nullptr, s->d_vl[s->cur], 0, s->stream);
     if ((rc = stage(dvdt, (size_t)s->Fg * 3))) return rc;
@@ -549,6 +647,7 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     // the history of every held cell is kept (halo cells are updated locally by the fused kernel)
     odis::launch_scatter_history(N, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
     s->launches += 4;
+    ODIS_CUDA(cudaMemsetAsync(&s->d_ctl->count, 0, sizeof(unsigned long long), s->stream));
     s->iter = iter;
     s->iter0 = iter;
     s->last_mode = -1;
@@ -558,9 +657,9 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     // potential for the first step: forcing(current_time + dt), timeIntegrator.cpp:187,218 — for every
     // held cell, halo included
     const double t = s->prm.dt * (double)iter + s->prm.dt;
-    odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr};
+    odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
     odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), odis::CELL_UPDATE_U, s->prm.block_threads,
-                           s->stream);
+                           nullptr, s->stream);
     s->launches++;
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
@@ -568,6 +667,7 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
 }
 
 static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* marks);
+static int check_halo_timeout(odis_solver* s);
 
 int odis_step(odis_solver* s, int32_t nsteps) { return step_impl(s, nsteps, nullptr); }
 
@@ -606,14 +706,66 @@ static void rotate_cell_history(odis_solver* s, int mode) {
 static int finalize_eta(odis_solver* s) {
     if (!s->eta_lag) return ODIS_OK;
     odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
-                       nullptr, 0, nullptr};
+                       nullptr, 0, nullptr, nullptr};
     odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, s->mode_lag, odis::StepScalars{}, odis::CELL_UPDATE_ETA, s->prm.block_threads,
-                           s->stream);
+                           nullptr, s->stream);
     s->launches++;
     ODIS_CUDA(cudaGetLastError());
     rotate_cell_history(s, s->mode_lag);
     s->ecur = 1 - s->ecur;
     s->eta_lag = false;
+    return ODIS_OK;
+}
+
+constexpr int kGraphSteps = 12;      // steps per captured graph: a multiple of the rotation period (2 x 2 x 3 -> 6)
+
+// Launches of one time step on the solver's stream (also under stream capture) and the rotation of the buffers.
+static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cudaEvent_t>* marks, int k) {
+    const odis::EdgeTables et = s->edge_tables();
+    const odis::CellTables ct = s->cell_tables(s->world > 1 ? s->N : s->No);     // partitioned: ghost cells are updated locally
+    odis::EdgeState es;
+    es.vl_in = s->d_vl[s->cur]; es.vl_out = s->d_vl[1 - s->cur]; es.eu = s->d_eu[s->ecur];
+    es.h1 = s->d_hv[s->hv1]; es.h2 = s->d_hv[1 - s->hv1];
+    es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
+    es.energy_out = dev_ctl ? nullptr : s->d_series + (s->iter - s->iter0);
+    es.ctl = dev_ctl ? s->d_ctl : nullptr; es.series = s->d_series; es.scal = s->d_scal;
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
+    // partitioned: ONE exchange per step, of v^{n+1} on the boundary edges. The staged edge kernel pushes it itself
+    // (HaloInline) and the direct cell kernel waits for the neighbours' in its last CTAs; the other variants get a separate
+    // exchange launch (which also waits). Ghost cells are updated locally, so {eta,U} is never exchanged.
+    const bool part = s->world > 1, inline_e = part && s->pipe_edge;
+    if (s->pipe_edge) {
+        odis::HaloInline hv;
+        if (inline_e) hv = halo_inline_edge(s, 1 - s->cur);
+        ODIS_CUDA(odis::launch_edge_step_pipe(et, s->phys, es, mode, inline_e ? &hv : nullptr, s->stream));
+    } else odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
+    if (part && !inline_e) {
+        int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
+        if (rc2) return rc2;
+    }
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
+    if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
+    // the staged edge kernel finishes its own energy sum; the direct one leaves per-warp partials to the cell kernel
+    odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
+                       s->d_block_partial, (s->Fo + 31) / 32, s->pipe_edge ? nullptr : es.energy_out, dev_ctl ? &s->d_ctl->cur : nullptr};
+    // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
+    const odis::StepScalars next = dev_ctl ? odis::StepScalars{} : step_scalars(s->prm.omega, s->prm.dt * (double)(s->iter + 1) + s->prm.dt);
+    if (s->pipe_cell) {
+        if (inline_e) { int rc2 = halo_drain(s); if (rc2) return rc2; }
+        ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, s->stream));
+    } else {
+        odis::HaloInline hc;
+        if (inline_e) hc = halo_inline_cell(s);
+        odis::launch_cell_step(ct, s->phys, cs, mode, next, odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U, s->prm.block_threads,
+                               inline_e ? &hc : nullptr, s->stream);
+    }
+    rotate_cell_history(s, mode);
+    s->ecur = 1 - s->ecur;
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream);
+    s->cur = 1 - s->cur;
+    s->iter++;
+    s->last_mode = mode;
+    s->launches += 2;
     return ODIS_OK;
 }
 
@@ -644,7 +796,6 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             if (s->eta_lag) rotate_cell_history(s, s->mode_lag);
             s->ecur = 1 - s->ecur;
             if (s->world > 1) {                   // one exchange per step: v^{n+1} of my boundary edges
-                s->epoch++;
                 int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
                 if (rc2) return rc2;
             }
@@ -661,43 +812,51 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         ODIS_CUDA(cudaGetLastError());
         return ODIS_OK;
     }
-    const odis::CellTables ct = s->cell_tables(s->No);
-    for (int k = 0; k < nsteps; k++) {
+    // ---- two launches per step (+ one halo exchange launch after each when partitioned) ----
+    const bool dev_ctl = s->pipe_edge;       // the staged edge kernel keeps the step counter / time factors on the device
+    if (dev_ctl && nsteps > 0) {             // time factors of every step of this call, uploaded ahead (tidalPotentials.cpp:55-61)
+        std::vector<odis::StepScalars> sc((size_t)nsteps);
+        // forcing for the NEXT step: current_time = dt*(iter+1), evaluated at current_time + dt
+        for (int k = 0; k < nsteps; k++) sc[(size_t)k] = step_scalars(s->prm.omega, s->prm.dt * (double)(s->iter + k + 1) + s->prm.dt);
+        ODIS_CUDA(cudaMemcpyAsync(s->d_scal + (s->iter - s->iter0), sc.data(), sc.size() * sizeof(odis::StepScalars), cudaMemcpyHostToDevice, s->stream));
+    }
+    int done = 0;
+    while (done < nsteps) {
         const int mode = ab3_mode(s, s->iter);
-        odis::EdgeState es;
-        es.vl_in = s->d_vl[s->cur]; es.vl_out = s->d_vl[1 - s->cur]; es.eu = s->d_eu[s->ecur];
-        es.h1 = s->d_hv[s->hv1]; es.h2 = s->d_hv[1 - s->hv1];
-        es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
-        es.energy_out = s->d_series + (s->iter - s->iter0);
-        if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
-        if (s->pipe_edge) ODIS_CUDA(odis::launch_edge_step_pipe(et, s->phys, es, mode, s->stream));
-        else odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
-        if (s->world > 1) {                       // v^{n+1} of my boundary edges -> the neighbours' halos
-            s->epoch++;
-            int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
-            if (rc2) return rc2;
+        // steady state: replay a captured graph of kGraphSteps steps (the buffer rotation has period 6)
+        if (dev_ctl && s->use_graph && !marks && mode == odis::AB3_FULL && nsteps - done >= kGraphSteps) {
+            const unsigned key = (unsigned)s->cur | (unsigned)s->ecur << 1 | (unsigned)s->hv1 << 2 | (unsigned)s->he1 << 3 | (unsigned)s->he2 << 5 |
+                                 (unsigned)s->hefree << 7;
+            auto it = s->graphs.find(key);
+            if (it == s->graphs.end()) {
+                const int64_t iter_save = s->iter, launches_save = s->launches;
+                cudaGraph_t graph = nullptr;
+                ODIS_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+                int rcc = ODIS_OK;
+                for (int k = 0; k < kGraphSteps && !rcc; k++) rcc = enqueue_step(s, odis::AB3_FULL, true, nullptr, 0);
+                cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+                s->iter = iter_save; s->launches = launches_save;      // nothing ran; the rotation is back where it started
+                if (rcc) { if (graph) cudaGraphDestroy(graph); return rcc; }
+                if (ce != cudaSuccess) return fail(ODIS_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+                cudaGraphExec_t exec = nullptr;
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return fail(ODIS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+                it = s->graphs.emplace(key, exec).first;
+            }
+            const int reps = (nsteps - done) / kGraphSteps;
+            for (int r = 0; r < reps; r++) ODIS_CUDA(cudaGraphLaunch(it->second, s->stream));
+            const int adv = reps * kGraphSteps;
+            s->graph_launches += reps;
+            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0));
+            s->iter += adv;
+            s->last_mode = odis::AB3_FULL;
+            done += adv;
+            continue;
         }
-        if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
-        if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
-        // the staged edge kernel finishes its own energy sum; the direct one leaves per-warp partials to the cell kernel
-        odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
-                           s->d_block_partial, (s->Fo + 31) / 32, s->pipe_edge ? nullptr : es.energy_out};
-        // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
-        const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
-        if (s->pipe_cell) ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), s->stream));
-        else odis::launch_cell_step(ct, s->phys, cs, mode, step_scalars(s->prm.omega, tnext), odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U,
-                                    s->prm.block_threads, s->stream);
-        rotate_cell_history(s, mode);
-        s->ecur = 1 - s->ecur;
-        if (s->world > 1) {                       // {eta^{n+1}, U} of my boundary cells -> the neighbours' halos
-            int rc2 = halo_exchange(s, 1, s->d_eu[s->ecur], s->ecur);
-            if (rc2) return rc2;
-        }
-        if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream);
-        s->cur = 1 - s->cur;
-        s->iter++;
-        s->last_mode = mode;
-        s->launches += 2;
+        int rc2 = enqueue_step(s, mode, dev_ctl, marks, done);
+        if (rc2) return rc2;
+        done++;
     }
     if (nsteps > 0) s->diag_current = false;
     ODIS_CUDA(cudaGetLastError());
@@ -716,7 +875,7 @@ int odis_step_timed(odis_solver* s, int32_t nsteps, float* elapsed_ms_out) {
     ODIS_CUDA(cudaEventRecord(s->ev1, s->stream));
     ODIS_CUDA(cudaEventSynchronize(s->ev1));
     ODIS_CUDA(cudaEventElapsedTime(elapsed_ms_out, s->ev0, s->ev1));
-    return ODIS_OK;
+    return check_halo_timeout(s);
 }
 
 int odis_get_field(odis_solver* s, int32_t field, double* out) {
@@ -776,7 +935,7 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaMemcpyAsync(out, s->d_stage, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
-    return ODIS_OK;
+    return check_halo_timeout(s);
 }
 
 static double sphere_area(const odis_solver* s) { return 4 * odis::kPi * (s->prm.radius * s->prm.radius); }   // energy.cpp:60
@@ -828,18 +987,30 @@ int odis_get_launch_count(odis_solver* s, int64_t* launches_out) {
     return ODIS_OK;
 }
 
+// partitioned runs: did any in-kernel wait for a neighbour give up? (the stream must be idle)
+static int check_halo_timeout(odis_solver* s) {
+    if (s->world <= 1) return ODIS_OK;
+    unsigned long long flag = 0;
+    ODIS_CUDA(cudaMemcpy(&flag, &s->d_ctl->pad, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) return fail(ODIS_ERR_STATE, "halo exchange timed out: a neighbouring rank did not take the same steps (results are invalid)");
+    return ODIS_OK;
+}
+
 int odis_synchronize(odis_solver* s) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL argument");
     ODIS_CUDA(cudaSetDevice(s->device));
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
-    return ODIS_OK;
+    return check_halo_timeout(s);
 }
 
 void odis_destroy(odis_solver* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->stream && s->have_state) halo_drain(s);        // neighbours may still be pushing into this rank's halo
     if (s->stream) cudaStreamSynchronize(s->stream);
-    void* ptrs[] = {s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_normal, s->d_eid, s->d_area, s->d_trig,
+    for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);
+    void* ptrs[] = {s->d_csr_e_first, s->d_csr_e_peer, s->d_csr_e_remote, s->d_halo_done,
+                    s->d_ctl, s->d_scal, s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_normal, s->d_eid, s->d_area, s->d_trig,
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,

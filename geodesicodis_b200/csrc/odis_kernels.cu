@@ -46,6 +46,28 @@ __device__ __forceinline__ double ld_plain(const double* p) {
     return v;
 }
 
+// boundary CTAs of a partitioned run: ghost slots are written by other GPUs while the kernel runs, so bypass L1
+__device__ __forceinline__ double2 ld_gather_cg(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+// spin (bounded) until all neighbours have published the exchange ctl->epoch[0] (see HaloInline)
+__device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
+    const unsigned long long ev = ((volatile unsigned long long*)ctl->epoch)[0];
+    const long long t0 = clock64();
+    bool late = false;
+    for (int k = 0; k < w.n_peers; k++) {
+        unsigned long long seen;
+        const unsigned long long* fv = w.flag[k];
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fv) : "memory");
+        } while (seen < ev && clock64() - t0 < kHaloSpinCycles);
+        late |= seen < ev;
+    }
+    if (late) ctl->pad = 1ull;      // a neighbour never arrived: reported by the host (ODIS_ERR_STATE), no hang
+}
+
 // x / d with IEEE round-to-nearest result, given y = RN(1/d) (Markstein: one reciprocal shared by all the
 // quotients of an edge / cell instead of a ~35-instruction division each). q0 = RN(x*y) is refined twice
 // through exactly computed residuals; the final fused multiply-add rounds to the correctly rounded quotient
@@ -254,48 +276,68 @@ __device__ __forceinline__ double tidal_potential(const Physics& p, const StepSc
 
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                             int flags) {
+                                                             int flags, HaloInline halo) {
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= t.n_active) return;
-    const int N = t.n_cells;
-    // ---- phase A: independent loads ----
-    const int update_eta = flags & CELL_UPDATE_ETA;
-    int packed[kCellEdges];
-#pragma unroll
-    for (int j = 0; j < kCellEdges; j++) packed[j] = update_eta ? ld_stream(t.eid + (size_t)j * N + i) : -1;
-    double2 st = ld_gather(s.eu_in + i);
-    double area = 1.0, f1 = 0.0, f2 = 0.0;
-    if (update_eta) {
-        area = ld_stream(t.area + i);
-        f1 = ld_plain(s.h1 + i);
-        f2 = ld_plain(s.h2 + i);
+    // partitioned runs: the last CTAs hold the cells that read ghost edges (own boundary cells, then the ghost cells)
+    const bool bnd_cta = (int)((blockIdx.x + 1) * kThreads) > halo.wait_from;
+    if (bnd_cta) {
+        if (threadIdx.x == 0) halo_wait_all(halo.wait_v, halo.ctl);
+        __syncthreads();
     }
-    TrigValues tv = load_trig(t, (flags & CELL_UPDATE_U) ? p.potential : (int)P_NONE, i);
-    // ---- phase B: gathers ----
-    double2 ed[kCellEdges];
+    if (i < t.n_active) {
+        const int N = t.n_cells;
+        // ---- phase A: independent loads ----
+        const int update_eta = flags & CELL_UPDATE_ETA;
+        int packed[kCellEdges];
 #pragma unroll
-    for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
-    // ---- phase C ----
-    if (update_eta) {
-        // d eta/dt = h Div v   (updateEta.cpp:39; D_ie = -dir l_e / A_i, mesh.cpp:3246)
-        double div = 0.0;
-        const double ra = __drcp_rn(area);
-#pragma unroll
-        for (int j = 0; j < kCellEdges; j++) {
-            if (packed[j] != -1) {                                    // the 12 pentagons have 5 edges
-                const double ndir = (packed[j] < 0) ? 1.0 : -1.0;     // -dir: dir = -1 for the outer cell
-                const double coeff = exact_div(ndir * ed[j].y, area, ra);
-                div += (p.h * coeff) * ed[j].x;
+        for (int j = 0; j < kCellEdges; j++) packed[j] = update_eta ? ld_stream(t.eid + (size_t)j * N + i) : -1;
+        double2 st = ld_gather(s.eu_in + i);
+        double area = 1.0, f1 = 0.0, f2 = 0.0;
+        if (update_eta) {
+            area = ld_stream(t.area + i);
+            f1 = ld_plain(s.h1 + i);
+            f2 = ld_plain(s.h2 + i);
+        }
+        TrigValues tv = load_trig(t, (flags & CELL_UPDATE_U) ? p.potential : (int)P_NONE, i);
+        if (s.next_dev != nullptr) {                         // graph replay: this step's time factors were left by the edge kernel
+            next.cosM = ld_plain(&s.next_dev->cosM);
+            next.sinM = ld_plain(&s.next_dev->sinM);
+            if (p.potential == P_FULL2) {
+                next.cos2M = ld_plain(&s.next_dev->cos2M); next.sin2M = ld_plain(&s.next_dev->sin2M);
+                next.cos3M = ld_plain(&s.next_dev->cos3M); next.cos4M = ld_plain(&s.next_dev->cos4M);
             }
         }
-        const double f0 = div;
-        st.x += ab3_increment(f0, f1, f2, p.dt, mode);
-        s.hw[i] = f0;
+        // ---- phase B: gathers ----
+        double2 ed[kCellEdges];
+        if (!bnd_cta) {
+#pragma unroll
+            for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+        } else {
+#pragma unroll
+            for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather_cg(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+        }
+        // ---- phase C ----
+        if (update_eta) {
+            // d eta/dt = h Div v   (updateEta.cpp:39; D_ie = -dir l_e / A_i, mesh.cpp:3246)
+            double div = 0.0;
+            const double ra = __drcp_rn(area);
+#pragma unroll
+            for (int j = 0; j < kCellEdges; j++) {
+                if (packed[j] != -1) {                                    // the 12 pentagons have 5 edges
+                    const double ndir = (packed[j] < 0) ? 1.0 : -1.0;     // -dir: dir = -1 for the outer cell
+                    const double coeff = exact_div(ndir * ed[j].y, area, ra);
+                    div += (p.h * coeff) * ed[j].x;
+                }
+            }
+            const double f0 = div;
+            st.x += ab3_increment(f0, f1, f2, p.dt, mode);
+            s.hw[i] = f0;
+        }
+        if ((flags & CELL_UPDATE_U) && p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
+        s.eu_out[i] = st;
     }
-    if ((flags & CELL_UPDATE_U) && p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
-    s.eu_out[i] = st;
 }
 
 template <int kThreads>
@@ -333,9 +375,9 @@ __global__ void __launch_bounds__(kThreads) edge_diag_kernel(EdgeTables t, Physi
 }
 
 // ---- halo exchange ----
-__global__ void halo_push_kernel(int n, const int* __restrict__ local_idx, const int* __restrict__ remote_idx, const int* __restrict__ peer,
-                                 const double2* __restrict__ src, HaloRemote remote, int n_peers, int flag_slot, unsigned long long epoch,
-                                 unsigned int* ticket) {
+__global__ void halo_exchange_kernel(int n, const int* __restrict__ local_idx, const int* __restrict__ remote_idx, const int* __restrict__ peer,
+                                     const double2* __restrict__ src, HaloRemote remote, HaloWait w, int flag_slot, int kind, StepCtl* ctl,
+                                     unsigned int* ticket) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) remote.data[peer[k]][remote_idx[k]] = src[local_idx[k]];      // direct store into the neighbour GPU over NVLink
     __threadfence_system();                                                  // my stores are performed before the ticket
@@ -343,22 +385,31 @@ __global__ void halo_push_kernel(int n, const int* __restrict__ local_idx, const
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last) {                                                           // every block's data is out: publish the epoch
-        __threadfence_system();
-        if ((int)threadIdx.x < n_peers) {
-            unsigned long long* f = remote.flags[threadIdx.x] + flag_slot;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
-        }
-        if (threadIdx.x == 0) *ticket = 0u;
-    }
-}
-__global__ void halo_wait_kernel(HaloWait w, unsigned long long epoch) {
+    if (!is_last) return;
+    // every block's data is out: publish the epoch to the peers, then wait for theirs
+    __threadfence_system();
+    const unsigned long long epoch = ((volatile unsigned long long*)ctl->epoch)[kind] + 1ull;
     if ((int)threadIdx.x < w.n_peers) {
+        unsigned long long* f = remote.flags[threadIdx.x] + flag_slot;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
         unsigned long long seen;
+        const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(w.flag[threadIdx.x]) : "memory");
-        } while (seen < epoch);
+        } while (seen < epoch && clock64() - t0 < kHaloSpinCycles);
+        if (seen < epoch) ctl->pad = 1ull;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctl->epoch[kind] = epoch;
+        *ticket = 0u;
+    }
+}
+
+// bounded wait for the neighbours' last pushes (before state is overwritten / read back, and before a cell kernel
+// variant that does not wait itself)
+__global__ void halo_drain_kernel(HaloWait wv, StepCtl* ctl) {
+    if (threadIdx.x == 0) halo_wait_all(wv, ctl);
 }
 
 // ---- renumbering kernels (set_state / get_field; not on the per-step path) ----
@@ -433,11 +484,17 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
 }
 
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
-                      int flags, int block_threads, cudaStream_t stream) {
+                      int flags, int block_threads, const HaloInline* halo, cudaStream_t stream) {
+    HaloInline none;
+    none.n_bnd = 0;
+    none.wait_from = 0x7fffffff;
     dispatch_threads(block_threads, [&](auto bt) {
         constexpr int kT = decltype(bt)::value;
-        cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags);
+        cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
     });
+}
+void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream) {
+    halo_drain_kernel<<<1, 32, 0, stream>>>(wait_v, ctl);
 }
 
 void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double2* vl, const double2* normal, double2* v_avg,
@@ -450,13 +507,10 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
     });
 }
 
-void launch_halo_push(int n, const int* local_idx, const int* remote_idx, const int* peer, const double2* src, const HaloRemote& remote,
-                      int n_peers, int flag_slot, unsigned long long epoch, unsigned int* ticket, cudaStream_t stream) {
+void launch_halo_exchange(int n, const int* local_idx, const int* remote_idx, const int* peer, const double2* src, const HaloRemote& remote,
+                          const HaloWait& w, int flag_slot, int kind, StepCtl* ctl, unsigned int* ticket, cudaStream_t stream) {
     const int blocks = n > 0 ? (n + 255) / 256 : 1;
-    halo_push_kernel<<<blocks, 256, 0, stream>>>(n, local_idx, remote_idx, peer, src, remote, n_peers, flag_slot, epoch, ticket);
-}
-void launch_halo_wait(const HaloWait& w, unsigned long long epoch, cudaStream_t stream) {
-    halo_wait_kernel<<<1, 32, 0, stream>>>(w, epoch);
+    halo_exchange_kernel<<<blocks, 256, 0, stream>>>(n, local_idx, remote_idx, peer, src, remote, w, flag_slot, kind, ctl, ticket);
 }
 
 void launch_scatter_x(int n, const int* perm, const double* src_ref, double2* dst_new, int zero_y, cudaStream_t stream) {

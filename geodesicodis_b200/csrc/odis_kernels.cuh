@@ -37,6 +37,20 @@ struct StepScalars {          // per-step host-evaluated trigonometry (tidalPote
     double cosM, sinM, cos2M, sin2M, cos3M, cos4M;
 };
 
+// Device-resident step bookkeeping, so that a captured CUDA graph can be replayed without per-step host arguments:
+// the edge kernel's last CTA files the energy sum under series[count], copies the host-evaluated time factors of
+// this step (scal[count], uploaded ahead for the whole odis_step call) to `cur` for the cell kernel that follows,
+// and advances `count`; the halo exchange kernels keep their epochs here.
+struct StepCtl {
+    unsigned long long count;       // steps taken since odis_set_state
+    unsigned long long epoch[2];    // [0] halo exchanges ({v,l} of the boundary edges) published so far; [1] unused
+    unsigned long long pad;         // set to 1 when a halo wait gave up (kHaloSpinCycles)
+    StepScalars cur;
+};
+
+struct HaloInline;   // halo exchange fused into the step kernels, defined below
+struct HaloWait;
+
 struct EdgeTables {
     int n_edges;              // edges this rank updates
     int stride;               // SoA row stride of sid / sw (n_edges rounded up to the 128-edge tile)
@@ -75,7 +89,10 @@ struct EdgeState {
     double* block_partial;    // direct kernel: [ceil(F/32)] per-warp sums of eps_e * A_e for v^n, finished by the next cell_step;
                               // staged kernel: [grid] per-CTA sums, finished by its own last CTA
     unsigned int* ticket;     // last-CTA-done counter (staged kernel, edge_diagnostics)
-    double* energy_out;       // where the finished sum goes (series[iter])
+    double* energy_out;       // where the finished sum goes (series[iter]) when ctl == nullptr
+    StepCtl* ctl;             // staged kernel: device-side step counter (see StepCtl); series / scal are indexed by it
+    double* series;
+    const StepScalars* scal;
 };
 
 struct CellState {
@@ -88,6 +105,7 @@ struct CellState {
     const double* energy_partial;   // per-warp partials left by edge_step (block 0 sums them), or unused
     int n_energy_partials;
     double* energy_out;             // nullptr: no energy sum to finish
+    const StepScalars* next_dev;    // non-null: the time factors are read from device memory (StepCtl::cur) instead of the argument
 };
 
 // cell update flags
@@ -125,7 +143,10 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
                       cudaStream_t stream);
 // flags: CellFlags (update eta and/or the potential)
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
-                      int flags, int block_threads, cudaStream_t stream);
+                      int flags, int block_threads, const HaloInline* halo, cudaStream_t stream);
+// spins (bounded by kHaloSpinCycles) until every neighbour's flag has reached ctl->epoch[0]: all pushes of the
+// exchanges this rank took part in have landed
+void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream);
 // Diagnostics / output fields of the current velocity (interpolation.cpp:31-59, energy.cpp:32-56):
 // v_avg [F][2] and energy_diss [F]; either pointer may be null. Also leaves sum(eps_e*A_e) in energy_out.
 void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double2* vl, const double2* normal,
@@ -137,12 +158,16 @@ int edge_grid_blocks(int n_edges, int block_threads);
 // cp.async.bulk + mbarrier, 128-entity tiles. Same results bit for bit. All arrays a tile touches must
 // be allocated up to the next multiple of pipe_tile().
 int pipe_tile();
-cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, cudaStream_t stream);
+// opts the staged kernels into their dynamic shared-memory size on the current device (before any stream capture)
+cudaError_t pipe_configure();
+cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, const HaloInline* halo,
+                                  cudaStream_t stream);
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                                   cudaStream_t stream);
 
 // ---- halo exchange between ranks (one GPU each): peers' arrays are mapped into this process ----
 constexpr int kHaloMaxPeers = 8;
+constexpr long long kHaloSpinCycles = 20000000000ll;   // ~10 s: upper bound of any in-kernel wait for a neighbour
 struct HaloRemote {
     double2* data[kHaloMaxPeers];                 // the peer's {v,l} (or {eta,U}) array, its local numbering
     unsigned long long* flags[kHaloMaxPeers];     // the peer's epoch flags [2][world]
@@ -151,12 +176,38 @@ struct HaloWait {
     int n_peers;
     const unsigned long long* flag[kHaloMaxPeers];   // my flags that the peers raise
 };
-// remote.data[peer[k]][remote_idx[k]] = src[local_idx[k]] for every k, then (system-scope fence, last
-// block) remote.flags[p][flag_slot] = epoch for every peer p.
-void launch_halo_push(int n, const int* local_idx, const int* remote_idx, const int* peer, const double2* src, const HaloRemote& remote,
-                      int n_peers, int flag_slot, unsigned long long epoch, unsigned int* ticket, cudaStream_t stream);
-// spins (one thread per peer, acquire loads at system scope) until every flag >= epoch
-void launch_halo_wait(const HaloWait& w, unsigned long long epoch, cudaStream_t stream);
+// Halo exchange fused into the step kernels (partitioned runs): one exchange per step, of the new edge velocities.
+//   edge kernel: the own edges [0, n_bnd) are the boundary and are updated first; each stores its new {v,l} straight
+//                into the ghost slots of the neighbours that hold it (NVLink peer stores) and, when the last boundary
+//                tile is done, the epoch ctl->epoch[0]+1 is published to every neighbour (system-scope release). The
+//                interior is updated while stores and flag are in flight. It never waits: the ghost values it reads
+//                were awaited by the previous cell kernel.
+//   cell kernel: the cells [wait_from, n) - own cells with a non-own edge, then the ghost cells, whose eta every rank
+//                updates itself instead of receiving it - come last; their CTAs wait until every neighbour's flag has
+//                reached ctl->epoch[0] and gather with ld.global.cg (ghost slots are written by other GPUs while the
+//                kernel runs). Nothing is sent.
+struct HaloInline {
+    int n_bnd;                        // edge kernel: boundary edges; 0: not partitioned (nothing below is read)
+    int wait_from;                    // cell kernel: first cell that reads ghost edges; INT_MAX: not partitioned
+    int n_peers;
+    int flag_slot;                    // my slot in the neighbours' flag arrays
+    const int* send_first;            // [n_bnd + 1] CSR over the boundary edges
+    const int* send_peer;             // [n_send] neighbour index
+    const int* send_remote;           // [n_send] ghost slot in that neighbour's numbering
+    HaloRemote remote;                // the neighbours' {v,l} arrays (this step's output buffer) and flag arrays
+    HaloWait wait_v;                  // my flags the neighbours raise
+    unsigned int* done;               // boundary tiles finished (reset by the publisher)
+    StepCtl* ctl;
+};
+
+// One launch per exchange: remote.data[peer[k]][remote_idx[k]] = src[local_idx[k]] for every k (direct stores into
+// the neighbours' memory over NVLink); the last block to finish then publishes epoch E = ctl->epoch[kind] + 1 to
+// every peer (system-scope release store to remote.flags[p][flag_slot]), spins (one thread per peer, system-scope
+// acquire loads, bounded) until all of its own flags in `w` reach E, and records ctl->epoch[kind] = E. Used by the
+// kernel variants that do not carry the exchange themselves (direct-load edge kernel, fused one-launch step). The epoch lives on
+// the device so that the launch has no per-step argument (CUDA graph replay).
+void launch_halo_exchange(int n, const int* local_idx, const int* remote_idx, const int* peer, const double2* src, const HaloRemote& remote,
+                          const HaloWait& w, int flag_slot, int kind, StepCtl* ctl, unsigned int* ticket, cudaStream_t stream);
 
 // ---- renumbering on the device: fields cross the C ABI in reference numbering, perm[new] = old ----
 // x component of a double2 array from a reference-ordered source (src == nullptr: zeros); y untouched/kept.

@@ -67,7 +67,21 @@ __device__ __forceinline__ double2 ld_gather(const double2* p) {
     asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
-
+// after the boundary tile's threads have issued their peer stores and met at a barrier: one thread counts the tile
+// done (its system-scope fence is cumulative over the stores the barrier ordered before it); the last one publishes
+// the new epoch to the neighbours
+__device__ __forceinline__ void halo_tile_done(const HaloInline& h, unsigned int n_units) {
+    __threadfence_system();
+    if (atomicAdd(h.done, 1u) == n_units - 1u) {
+        __threadfence_system();
+        const unsigned long long epoch = ((volatile unsigned long long*)h.ctl->epoch)[0] + 1ull;
+        for (int k = 0; k < h.n_peers; k++) {
+            unsigned long long* f = h.remote.flags[k] + h.flag_slot;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        }
+        *h.done = 0u;
+    }
+}
 // x / d with IEEE round-to-nearest result, given y = RN(1/d) (Markstein: one reciprocal shared by all the
 // quotients of an edge / cell instead of a ~35-instruction division each). q0 = RN(x*y) is refined twice
 // through exactly computed residuals; the final fused multiply-add rounds to the correctly rounded quotient
@@ -105,7 +119,8 @@ struct __align__(16) EdgeStage {
 constexpr uint32_t kEdgeStageBytes = sizeof(EdgeStage);
 static_assert(kEdgeStageBytes == 24576, "edge stage layout");
 
-__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles) {
+__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
+                                                                          HaloInline halo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     EdgeStage* stages = reinterpret_cast<EdgeStage*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(EdgeStage));
@@ -154,6 +169,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
         const int st = i % kStages;
         const EdgeStage* d = stages + st;
         const int e = (int)(((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile) + tl;
+        // partitioned runs: the first tiles hold the boundary edges (they feed the neighbours)
+        const bool bnd_tile = (e - tl) < halo.n_bnd;
         mbar_wait(full + st, (i / kStages) & 1);
         double e_area = 0.0;
         if (e < t.n_edges) {
@@ -189,9 +206,17 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
             s.vl_out[e] = make_double2(v, own.y);
             if (mode == AB3_SECOND) s.h1[e] = f0;
             else s.h2[e] = f0;
+            if (e < halo.n_bnd) {                          // into the neighbours' ghost slots (direct stores over NVLink)
+                const int k1 = halo.send_first[e + 1];
+                for (int k = halo.send_first[e]; k < k1; k++) halo.remote.data[halo.send_peer[k]][halo.send_remote[k]] = make_double2(v, own.y);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);          // this warp no longer reads the stage
+        if (bnd_tile) {
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kTile) : "memory");   // the group's peer stores are issued
+            if (tl == 0) halo_tile_done(halo, (unsigned int)((halo.n_bnd + kTile - 1) / kTile));
+        }
         for (int o = 16; o > 0; o >>= 1) e_area += __shfl_down_sync(0xffffffffu, e_area, o);
         warp_energy += e_area;
     }
@@ -216,7 +241,15 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
         for (unsigned int b = lane; b < gridDim.x; b += 32) acc += ((volatile double*)s.block_partial)[b];
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
         if (lane == 0) {
-            *s.energy_out = acc;
+            if (s.ctl != nullptr) {                      // device-side step bookkeeping (StepCtl)
+                const unsigned long long k = s.ctl->count;
+                s.series[k] = acc;
+                s.ctl->cur = s.scal[k];
+                s.ctl->count = k + 1ull;
+                if (halo.n_bnd > 0) s.ctl->epoch[0] += 1ull;    // every CTA is past its boundary tiles: the v exchange is published
+            } else {
+                *s.energy_out = acc;
+            }
             *s.ticket = 0u;
         }
     }
@@ -350,6 +383,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTab
     }
     const int g = (warp - 1) / (kTile / 32);
     const int tl = (int)threadIdx.x - 32 - g * kTile;
+    if (s.next_dev != nullptr) next = *s.next_dev;       // graph replay: time factors left by the edge kernel
     for (int i = g; i < my_tiles; i += kGroups) {
         const int st = i % kStages;
         const CellStage* d = stages + st;
@@ -401,7 +435,16 @@ static int num_sms() {
     return g_num_sms;
 }
 
-cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, cudaStream_t stream) {
+cudaError_t pipe_configure() {
+    cudaError_t e = cudaFuncSetAttribute(edge_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(cell_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kStages * sizeof(CellStage) + 2 * kStages * sizeof(uint64_t)));
+}
+
+cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, const HaloInline* halo,
+                                  cudaStream_t stream) {
     static bool configured_dev[64] = {false};      // the opt-in shared-memory size is a per-device attribute
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -414,7 +457,9 @@ cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const E
     }
     const int n_tiles = (t.n_edges + kTile - 1) / kTile;
     const int grid = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
-    edge_step_pipe_kernel<<<grid, kPipeThreads, smem, stream>>>(t, p, s, mode, n_tiles);
+    HaloInline none;
+    none.n_bnd = 0;
+    edge_step_pipe_kernel<<<grid, kPipeThreads, smem, stream>>>(t, p, s, mode, n_tiles, halo ? *halo : none);
     return cudaGetLastError();
 }
 

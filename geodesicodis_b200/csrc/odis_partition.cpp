@@ -95,6 +95,47 @@ Partition build_partition(int n_cells, int n_edges, const int* edge_cells, const
         peer.recv_edges = recv_e[q];
         if (!peer.send_cell_local.empty() || !peer.send_edge_local.empty() || peer.recv_cells || peer.recv_edges) P.peers.push_back(std::move(peer));
     }
+
+    // ---- boundary placement inside the own ranges (purely local: ghost slots keep their positions) ----
+    // edges: boundary FIRST (sent to a neighbour, or touching a ghost) - the edge kernel updates and pushes them before
+    // the interior; cells: boundary LAST (a non-own edge in their divergence), next to the ghost cells, so that every cell
+    // whose update has to wait for the neighbours' velocities sits at the end of the cell kernel's iteration space
+    const int c0 = P.cell_begin[rank], c1 = P.cell_begin[rank + 1], e0 = P.edge_begin[rank], e1 = P.edge_begin[rank + 1];
+    std::vector<char> bnd_c((size_t)P.n_own_cells, 0), bnd_e((size_t)P.n_own_edges, 0);
+    for (const HaloPeer& peer : P.peers)
+        for (int l : peer.send_edge_local) bnd_e[(size_t)l] = 1;
+    auto cell_has_foreign_edge = [&](int c) {
+        for (int j = 0; j < 6; j++) {
+            const int e = cell_edges[(size_t)c * 6 + j];
+            if (e >= 0 && (e < e0 || e >= e1)) return true;
+        }
+        return false;
+    };
+    for (int c = c0; c < c1; c++)
+        if (cell_has_foreign_edge(c)) bnd_c[(size_t)(c - c0)] = 1;
+    for (int e = e0; e < e1; e++)
+        for (int k = 0; k < 2; k++) {
+            const int c = edge_cells[(size_t)e * 2 + k];
+            if (c < c0 || c >= c1 || cell_has_foreign_edge(c)) bnd_e[(size_t)(e - e0)] = 1;
+        }
+    auto place = [](const std::vector<char>& bnd, bool boundary_first, std::vector<int>& new_of_old) {
+        const int n = (int)bnd.size();
+        new_of_old.resize((size_t)n);
+        int nb = 0;
+        for (int i = 0; i < n; i++) nb += bnd[(size_t)i] ? 1 : 0;
+        int kb = boundary_first ? 0 : n - nb, ki = boundary_first ? nb : 0;
+        for (int i = 0; i < n; i++) new_of_old[(size_t)i] = bnd[(size_t)i] ? kb++ : ki++;
+        return nb;
+    };
+    std::vector<int> cnew, enew;
+    P.n_bnd_cells = place(bnd_c, false, cnew);
+    P.n_bnd_edges = place(bnd_e, true, enew);
+    for (int i = 0; i < P.n_own_cells; i++) P.local_cells[(size_t)cnew[(size_t)i]] = c0 + i;
+    for (int i = 0; i < P.n_own_edges; i++) P.local_edges[(size_t)enew[(size_t)i]] = e0 + i;
+    for (HaloPeer& peer : P.peers) {
+        for (int& l : peer.send_cell_local) l = cnew[(size_t)l];
+        for (int& l : peer.send_edge_local) l = enew[(size_t)l];
+    }
     return P;
 }
 

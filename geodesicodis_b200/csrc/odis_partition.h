@@ -7,8 +7,10 @@
 //   ghost cells  = the other-rank cells of its own edges                     (eta, U for the pressure gradient)
 //   ghost edges  = the other-rank edges of all cells it touches              (v, l for the TRiSK stencil and
 //                  (own cells and ghost cells)                                the divergence of its own cells)
-// Per step there are two exchanges: v of boundary edges after the edge update, {eta,U} of boundary cells
-// after the cell update. Every rank derives all halos deterministically from the same global tables, so
+// Per step there is ONE exchange: v of the boundary edges, pushed by the edge update itself. Ghost cells are
+// not exchanged: every rank holds all edges of its ghost cells, so it repeats their (cheap, bit-identical)
+// eta update locally from the exchanged velocities. The cell send lists below describe ownership (who holds
+// the authoritative value of a ghost cell) for set/get and for tests. Every rank derives all halos deterministically from the same global tables, so
 // send lists need no negotiation: the sender knows the receiver's ghost slot of every entity.
 #pragma once
 #include <vector>
@@ -28,7 +30,13 @@ struct Partition {
     int world = 1, rank = 0;
     std::vector<int> cell_begin, edge_begin;   // [world+1] ranges in global device numbering
     int n_own_cells = 0, n_own_edges = 0;
-    std::vector<int> local_cells;              // global device ids: own range, then ghosts ascending
+    // Placement of the boundary inside the own ranges. Boundary edges (sent to a neighbour, or reading a ghost value: a
+    // non-own cell, or a non-own edge of their two cells) come FIRST, [0, n_bnd_edges): the edge kernel updates and pushes
+    // them before the interior, so the transfer overlaps the interior update. Boundary cells (a non-own edge in their
+    // divergence) come LAST among the own cells, [n_own_cells - n_bnd_cells, n_own_cells), right before the ghost cells:
+    // everything in the cell kernel that has to wait for the neighbours' velocities sits at the end of its iteration space.
+    int n_bnd_cells = 0, n_bnd_edges = 0;
+    std::vector<int> local_cells;              // global device ids: own (interior, then boundary), then ghosts ascending
     std::vector<int> local_edges;
     std::vector<HaloPeer> peers;               // ascending rank, only ranks that share a boundary
     int cell_owner(int c) const;

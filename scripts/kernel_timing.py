@@ -18,7 +18,8 @@ if level <= 6:   # correctness guard on small grids
 for bt in blocks:
     # block size 0: fused one-launch step; -1: default (two-launch staged edge + direct cell); -2: two-launch both staged;
     # > 0: two-launch both direct with that block size
-    sel = 1 if bt > 0 else (2 if bt == -2 else (0 if bt == -1 else 4))
+    # -3: default kernels without CUDA graph replay
+    sel = 1 if bt > 0 else (2 if bt == -2 else (0 if bt == -1 else (8 if bt == -3 else 4)))
     s = odis.Solver(mesh, dict(prm, block_threads=max(bt, 0), kernel_select=sel))
     if level <= 6:
         s.step(20)

@@ -115,10 +115,12 @@ def test_direct_and_pipelined_kernels_agree(odis, level):
     rng = np.random.default_rng(5)
     v0, e0 = rng.uniform(-1, 1, mesh.n_edges) * 1e-2, rng.uniform(-1, 1, mesh.n_cells)
     out = []
-    for sel in (0, 1, 2, 3, 4):              # every two-launch combination (0 = default) and the fused one-launch step
+    # every two-launch combination (0 = default: steady-state steps replayed from captured CUDA graphs; 8 = the same
+    # kernels launched one by one) and the fused one-launch step
+    for sel in (0, 1, 2, 3, 4, 8, 10):
         s = odis.Solver(mesh, dict(prm, kernel_select=sel))
         s.set_state(v0, e0)
-        s.step(33)
+        s.step(33); s.step(7); s.step(26)     # graph replays (12 steps each) start from different rotation phases
         out.append([s.field(f) for f in range(4)] + [s.dissipation_series()])
         s.close()
     for other in out[1:]:
