@@ -92,6 +92,14 @@ SIGNATURES = {
     "odis_get_launch_count": (C.c_int, [C.c_void_p, P(c_i64)]),
     "odis_synchronize": (C.c_int, [C.c_void_p]),
     "odis_destroy": (None, [C.c_void_p]),
+    "odis_ensemble_create": (C.c_int, [P(MeshView), C.c_void_p, c_i32, c_i32, P(C.c_void_p)]),
+    "odis_ensemble_set_state": (C.c_int, [C.c_void_p, c_i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64]),
+    "odis_ensemble_step": (C.c_int, [C.c_void_p, c_i32]),
+    "odis_ensemble_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
+    "odis_ensemble_get_field": (C.c_int, [C.c_void_p, c_i32, c_i32, C.c_void_p]),
+    "odis_ensemble_get_dissipation_series": (C.c_int, [C.c_void_p, c_i32, c_i64, c_i64, C.c_void_p]),
+    "odis_ensemble_get_info": (C.c_int, [C.c_void_p, P(c_i32), P(c_i64), P(c_i64), P(c_i64), P(c_i64)]),
+    "odis_ensemble_destroy": (None, [C.c_void_p]),
     "odis_h5_create": (C.c_int, [C.c_char_p, P(C.c_void_p)]),
     "odis_h5_add_dataset": (C.c_int, [C.c_void_p, C.c_char_p, c_i32, P(C.c_uint64), P(c_i32)]),
     "odis_h5_write_rows": (C.c_int, [C.c_void_p, c_i32, C.c_uint64, C.c_uint64, C.c_void_p]),

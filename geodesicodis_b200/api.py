@@ -99,10 +99,12 @@ def quantise_time_step(period: float, target_dt: float) -> tuple[float, int]:
 class Mesh:
     """C-grid tables (reference names, include/mesh.h:77-187) as numpy views into library memory."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, view=None, keep=None):
         self._h = handle
-        self.view = MeshView()
-        check(_lib.load().odis_mesh_get_view(self._h, C.byref(self.view)))
+        self.view = MeshView() if view is None else view
+        self._keep = keep                      # numpy arrays the view points into (from_tables)
+        if view is None:
+            check(_lib.load().odis_mesh_get_view(self._h, C.byref(self.view)))
         self.n_cells, self.n_edges, self.n_vertices = self.view.n_cells, self.view.n_edges, self.view.n_vertices
         self.radius = self.view.radius
         dims = {"N": self.n_cells, "F": self.n_edges, "V": self.n_vertices}
@@ -128,6 +130,36 @@ class Mesh:
         h = C.c_void_p()
         check(_lib.load().odis_mesh_from_arrays(pos.shape[0], pos.ctypes.data, fr.ctypes.data, cen.ctypes.data, radius, threads, C.byref(h)))
         return cls(h)
+
+    @classmethod
+    def from_tables(cls, tables: dict, radius: float) -> "Mesh":
+        """A mesh over caller-owned tables (reference names and layouts, as Mesh.tables holds them), e.g. tables built
+        once and shared between the ranks of a multi-GPU run. Nothing is recomputed or checked here."""
+        view = MeshView()
+        keep = {}
+        dims = {}
+        for name, code, (dim, cols) in MESH_VIEW_ARRAYS:
+            a = np.ascontiguousarray(tables[name], dtype=np.float64 if code == "d" else np.int32)
+            if a.size % cols:
+                raise ValueError(f"{name}: size {a.size} is not a multiple of {cols}")
+            if dims.setdefault(dim, a.size // cols) != a.size // cols:
+                raise ValueError(f"{name}: {a.size // cols} rows, expected {dims[dim]}")
+            keep[name] = a
+            setattr(view, name, a.ctypes.data)
+        view.n_cells, view.n_edges, view.n_vertices, view.radius = dims["N"], dims["F"], dims["V"], radius
+        return cls(None, view=view, keep=keep)
+
+    def save(self, directory: str) -> None:
+        """One .npy per table + radius.npy (np.load(..., mmap_mode='r') friendly)."""
+        os.makedirs(directory, exist_ok=True)
+        for name, a in self.tables.items():
+            np.save(os.path.join(directory, name + ".npy"), a)
+        np.save(os.path.join(directory, "radius.npy"), np.array([self.radius]))
+
+    @classmethod
+    def load(cls, directory: str, mmap: bool = True) -> "Mesh":
+        tables = {name: np.load(os.path.join(directory, name + ".npy"), mmap_mode="r" if mmap else None) for name, _, _ in MESH_VIEW_ARRAYS}
+        return cls.from_tables(tables, float(np.load(os.path.join(directory, "radius.npy"))[0]))
 
     @classmethod
     def from_globals(cls, g: Globals, run_dir: str, threads: int = 0) -> "Mesh":
@@ -343,6 +375,69 @@ class Solver:
     def close(self) -> None:
         if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
             _lib._lib.odis_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Ensemble:
+    """M independent runs on one grid advanced together (parameter sweeps; replaces M separate `./ODIS` runs).
+    `params_list`: one dict per member, as for Solver; members may differ in g, h, alpha, love_reduct, ecc, obl."""
+
+    def __init__(self, mesh: Mesh, params_list, device: int = 0):
+        self.mesh = mesh
+        self.M = len(params_list)
+        arr = (Params * self.M)()
+        for m, params in enumerate(params_list):
+            for k, v in params.items():
+                if k == "kernel_select":
+                    arr[m].reserved[0] = int(v)
+                else:
+                    setattr(arr[m], k, v)
+        self._h = C.c_void_p()
+        check(_lib.load().odis_ensemble_create(C.byref(mesh.view), C.cast(arr, C.c_void_p), self.M, device, C.byref(self._h)))
+        self.N, self.F = mesh.n_cells, mesh.n_edges
+        self._iter0 = 0
+
+    def set_state(self, member: int = -1, v=None, eta=None, dvdt=None, detadt=None, iter: int = 0) -> None:
+        k = [Solver._ptr(v, self.F), Solver._ptr(eta, self.N), Solver._ptr(dvdt, self.F * 3), Solver._ptr(detadt, self.N * 3)]
+        check(_lib.load().odis_ensemble_set_state(self._h, member, k[0][1], k[1][1], k[2][1], k[3][1], iter))
+        self._iter0 = iter
+
+    def step(self, nsteps: int = 1) -> None:
+        check(_lib.load().odis_ensemble_step(self._h, nsteps))
+
+    def step_timed(self, nsteps: int) -> float:
+        ms = C.c_float()
+        check(_lib.load().odis_ensemble_step_timed(self._h, nsteps, C.byref(ms)))
+        return ms.value
+
+    def field(self, member: int, fid: int) -> np.ndarray:
+        shape = tuple(self.F if d == "F" else self.N if d == "N" else d for d in _FIELD_SHAPES[fid])
+        out = np.empty(shape, dtype=np.float64)
+        check(_lib.load().odis_ensemble_get_field(self._h, member, fid, out.ctypes.data))
+        return out
+
+    def info(self) -> dict:
+        n, it, la, db, ab = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(_lib.load().odis_ensemble_get_info(self._h, C.byref(n), C.byref(it), C.byref(la), C.byref(db), C.byref(ab)))
+        return dict(n_members=n.value, iter=it.value, launches=la.value, device_bytes=db.value, algorithmic_bytes_per_step=ab.value)
+
+    @property
+    def iter(self) -> int:
+        return self.info()["iter"]
+
+    def dissipation_series(self, member: int, first: int = 0, count: int | None = None) -> np.ndarray:
+        if count is None:
+            count = self.iter - self._iter0 + 1 - first
+        out = np.empty(count, dtype=np.float64)
+        check(_lib.load().odis_ensemble_get_dissipation_series(self._h, member, first, count, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
+            _lib._lib.odis_ensemble_destroy(self._h)
             self._h = None
 
     def __del__(self):

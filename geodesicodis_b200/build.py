@@ -22,7 +22,7 @@ LIB = os.path.join(HERE, "libodis_b200.so")
 
 HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp", "odis_partition.cpp", "odis_h5lite.cpp",
                 "odis_run.cpp"]
-CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_fused.cu", "odis_engine.cu"]
+CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_fused.cu", "odis_engine.cu", "odis_ensemble.cu"]
 
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
@@ -38,7 +38,8 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)) + ["../build.py", "../../include/odis_b200.h"]:
+    names = [n for n in sorted(os.listdir(CSRC)) if os.path.isfile(os.path.join(CSRC, n))]
+    for name in names + ["../build.py", "../../include/odis_b200.h"]:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode())
             h.update(f.read())

@@ -223,6 +223,31 @@ int odis_synchronize(odis_solver* s);
 void odis_destroy(odis_solver* s);
 
 /* ------------------------------------------------------------------------------------------
+ * ensemble — M independent runs on one grid, advanced together (parameter sweeps over ocean thickness, drag, ...).
+ * The reference has no such mode: a sweep is M separate `./ODIS` runs, i.e. M times the loop of ab3Explicit
+ * (src/timeIntegrator.cpp:205-313) with a different input.in each. Members share the mesh, dt, omega, radius, shell
+ * thickness, potential / friction / surface type and init_load; g, h, alpha, love_reduct, ecc, obl may differ. Every
+ * member is bit-identical to an odis_solver run with the same odis_params. Fields cross in reference numbering.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct odis_ensemble odis_ensemble;
+int odis_ensemble_create(const odis_mesh_view* mesh, const odis_params* params /*[n_members]*/, int32_t n_members, int32_t device,
+                         odis_ensemble** out);
+/* State of one member (member = -1: the same state for every member); NULL pointers mean zeros. `iter` (shared by all
+ * members) restarts the step count; call it for the members before stepping. */
+int odis_ensemble_set_state(odis_ensemble* e, int32_t member, const double* v, const double* eta, const double* dvdt /*[F][3]*/,
+                            const double* detadt /*[N][3]*/, int64_t iter);
+int odis_ensemble_step(odis_ensemble* e, int32_t nsteps);
+int odis_ensemble_step_timed(odis_ensemble* e, int32_t nsteps, float* elapsed_ms_out);
+/* field: ODIS_FIELD_VELOCITY, _ETA, _DVDT, _DETADT or _POTENTIAL of one member. */
+int odis_ensemble_get_field(odis_ensemble* e, int32_t member, int32_t field, double* out);
+/* as odis_get_dissipation_series, for one member */
+int odis_ensemble_get_dissipation_series(odis_ensemble* e, int32_t member, int64_t first, int64_t count, double* out);
+/* any pointer may be NULL; algorithmic bytes per batched step = M*(40F + 56N) + 248F + 160N */
+int odis_ensemble_get_info(odis_ensemble* e, int32_t* n_members, int64_t* iter, int64_t* launches, int64_t* device_bytes,
+                           int64_t* algorithmic_bytes_per_step);
+void odis_ensemble_destroy(odis_ensemble* e);
+
+/* ------------------------------------------------------------------------------------------
  * output — replaces the HDF5 side of OutFiles: CreateHDF5Framework (src/outFiles.cpp:138-462: H5Fcreate +
  * one H5Dcreate(H5T_NATIVE_FLOAT, contiguous, fixed shape) per enabled field), DumpGridData (:464-520) and
  * DumpData's H5Sselect_hyperslab/H5Dwrite of one row per dump (:522-684). Writes the HDF5 file format
