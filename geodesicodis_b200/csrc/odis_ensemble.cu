@@ -134,8 +134,8 @@ __device__ __forceinline__ void ensemble_energy_sum(double2 acc, int pair, const
 struct __align__(16) EdgeStageRow {
     double2 cw[odis::kStencil];        // {Coriolis coefficient (-2 Omega sin(lat) w l_e' / d_e), w} per stencil slot
     double l[odis::kStencil];          // l_e' of the stencil edges
-    int id[odis::kStencil];            // stencil edge ids (pad slots: the edge itself, weight 0)
-    int2 c;                            // inner / outer cell
+    int id[odis::kStencil];            // stencil edge ids x Mp/2 (pad slots: the edge itself, weight 0)
+    int2 c;                            // inner / outer cell x Mp
     double2 G;
     double d, rd, le, pad;
 };
@@ -159,46 +159,61 @@ __global__ void __launch_bounds__(kEnsThreads, 2) ens_edge_step_kernel(EnsTables
     const int sj = threadIdx.x / Et, sk = threadIdx.x % Et;
     const bool stage_item = threadIdx.x < odis::kStencil * Et;
     const bool stage_scalar = threadIdx.x >= 192 && threadIdx.x < 192 + Et;
-    auto fetch_and_store = [&](int tile, int buf) {
+    // software pipeline: the next tile's table values are requested before this tile's gathers and turned into its
+    // stage rows (division included) after this tile's arithmetic
+    struct Fetched { int raw; double w, l, d, fc, le; int2 c; double2 G; bool ok; };
+    auto fetch = [&](int tile) {
+        Fetched f;
         const int e = tile * Et + (stage_scalar ? (int)threadIdx.x - 192 : sk);
-        if (tile >= n_tiles || e >= t.F) return;
+        f.ok = tile < n_tiles && e < t.F && (stage_item || stage_scalar);
+        f.raw = e; f.w = f.l = f.fc = f.le = 0.0; f.d = 1.0; f.c = make_int2(0, 0); f.G = make_double2(0.0, 0.0);
+        if (f.ok) {
+            f.d = t.dist[e];
+            if (stage_item) {
+                const size_t at = (size_t)sj * Fs + e;
+                const int raw = t.sid[at];
+                f.raw = raw < 0 ? e : raw;                 // pad slots (weight 0) gather the edge itself and add an exact zero
+                f.w = t.sw[at]; f.l = t.sl[at]; f.fc = t.fcor[e];
+            } else {
+                f.c = t.cells[e]; f.G = t.grad[e]; f.le = t.len[e];
+            }
+        }
+        return f;
+    };
+    const int Mp2 = Mp >> 1;
+    auto store = [&](const Fetched& f, int buf) {
+        if (!f.ok) return;
+        const double rd = __drcp_rn(f.d);
         if (stage_item) {
-            const size_t at = (size_t)sj * Fs + e;
-            const int raw = t.sid[at];
-            const double w = t.sw[at], l = t.sl[at], d = t.dist[e], fc = t.fcor[e];
             EdgeStageRow& r = stage[buf][sk];
-            r.id[sj] = raw < 0 ? e : raw;
-            r.l[sj] = l;
-            r.cw[sj] = make_double2(exact_div(fc * w * l, d, __drcp_rn(d)), w);       // mesh.cpp:2881
-        } else if (stage_scalar) {
+            r.id[sj] = f.raw * Mp2;                        // premultiplied: double2 index of (edge, pair 0)
+            r.l[sj] = f.l;
+            r.cw[sj] = make_double2(exact_div(f.fc * f.w * f.l, f.d, rd), f.w);       // mesh.cpp:2881
+        } else {
             EdgeStageRow& r = stage[buf][(int)threadIdx.x - 192];
-            const double d = t.dist[e];
-            r.c = t.cells[e]; r.G = t.grad[e]; r.d = d; r.rd = __drcp_rn(d); r.le = t.len[e];
+            r.c = make_int2(f.c.x * Mp, f.c.y * Mp); r.G = f.G; r.d = f.d; r.rd = rd; r.le = f.le;
         }
     };
+    const double2* vq = reinterpret_cast<const double2*>(v_in) + qa;
+    const double2* euq = eu + 2 * qa;
     double2 esum = make_double2(0.0, 0.0);
     int tile = blockIdx.x, buf = 0;
-    fetch_and_store(tile, 0);
+    store(fetch(tile), 0);
     __syncthreads();
     for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         const int e = tile * Et + ge;
         const bool work = active && e < t.F;
         const EdgeStageRow& r = stage[buf][ge];
-        double2 own, f1, f2, in_a, in_b, out_a, out_b, nb[odis::kStencil];
-        size_t o = 0;
+        const Fetched nxt = fetch(tile + gridDim.x);         // requested first: these come from DRAM
         if (work) {
-            o = ((size_t)e * Mp >> 1) + qa;                                  // double2 index of (e, pair q)
-            own = reinterpret_cast<const double2*>(v_in)[o];
-            f1 = reinterpret_cast<const double2*>(h1)[o];
-            f2 = reinterpret_cast<const double2*>(h2)[o];
+            const size_t o = (size_t)e * Mp2 + qa;                             // double2 index of (e, pair q)
+            double2 nb[odis::kStencil];
 #pragma unroll
-            for (int j = 0; j < odis::kStencil; j++) nb[j] = reinterpret_cast<const double2*>(v_in)[((size_t)r.id[j] * Mp >> 1) + qa];
+            for (int j = 0; j < odis::kStencil; j++) nb[j] = vq[r.id[j]];
+            const double2 own = reinterpret_cast<const double2*>(v_in)[o];
+            const double2 f1 = reinterpret_cast<const double2*>(h1)[o], f2 = reinterpret_cast<const double2*>(h2)[o];
             const int2 c = r.c;
-            in_a = eu[(size_t)c.x * Mp + 2 * qa]; in_b = eu[(size_t)c.x * Mp + 2 * qa + 1];
-            out_a = eu[(size_t)c.y * Mp + 2 * qa]; out_b = eu[(size_t)c.y * Mp + 2 * qa + 1];
-        }
-        fetch_and_store(tile + gridDim.x, buf ^ 1);          // the next tile's rows travel while the gathers above are in flight
-        if (work) {
+            const double2 in_a = euq[c.x], in_b = euq[c.x + 1], out_a = euq[c.y], out_b = euq[c.y + 1];
             double cor_a = 0.0, cor_b = 0.0, vt_a = 0.0, vt_b = 0.0;
 #pragma unroll
             for (int j = 0; j < odis::kStencil; j++) {
@@ -229,6 +244,7 @@ __global__ void __launch_bounds__(kEnsThreads, 2) ens_edge_step_kernel(EnsTables
             if (mode == odis::AB3_SECOND) reinterpret_cast<double2*>(h1)[o] = make_double2(f0a, f0b);
             else reinterpret_cast<double2*>(h2)[o] = make_double2(f0a, f0b);
         }
+        store(nxt, buf ^ 1);
         __syncthreads();                                     // stage[buf ^ 1] is complete, stage[buf] is free
     }
     ensemble_energy_sum(active ? esum : make_double2(0.0, 0.0), active ? q : -1, t, block_partial, ticket, energy_out);
@@ -531,6 +547,7 @@ int odis_ensemble_create(const odis_mesh_view* mv, const odis_params* params, in
     const int N = s->N, F = s->F, Mp = s->Mp;
     s->Ns = (N + 31) / 32 * 32; s->Fs = (F + 31) / 32 * 32;
     const int Ns = s->Ns, Fs = s->Fs;
+    if ((long long)F * Mp >= (1ll << 31)) return bail(fail(ODIS_ERR_ARG, "ensemble too large: edges x members must stay below 2^31"));
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "cudaStreamCreate failed"));
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
 
