@@ -84,6 +84,11 @@ SIGNATURES = {
     "odis_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
     "odis_step_profiled": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float)]),
+    "odis_enable_self_gravity": (C.c_int, [C.c_void_p, P(MeshView), c_i32, C.c_void_p]),
+    "odis_get_sh_coefficients": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "odis_step_profiled_sh": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float), P(C.c_float)]),
+    "odis_sh_basis": (C.c_int, [c_i32, C.c_void_p, c_i32, C.c_void_p]),
+    "odis_sh_normal_inverse": (C.c_int, [c_i32, C.c_void_p, c_i32, C.c_void_p]),
     "odis_get_field": (C.c_int, [C.c_void_p, c_i32, C.c_void_p]),
     "odis_get_dissipation_avg": (C.c_int, [C.c_void_p, P(c_f64)]),
     "odis_get_dissipation_series": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p]),

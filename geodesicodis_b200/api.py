@@ -206,6 +206,24 @@ def params_from_globals(g: Globals, dt: float, reorder: bool = True) -> dict:
                 friction=g.fric_type, surface=g.surface_type, init_load=int(g.initial_condition == 1), reorder=int(reorder))
 
 
+def sh_basis(pos_sph, l_max: int) -> np.ndarray:
+    """Basis rows Y[(l_max+1)^2][n] at (lat, lon) [n][2] (radians): 4-pi normalised, Condon-Shortley phase, degree-major,
+    per degree m = 0 then (cos, sin) for m = 1..l (host only)."""
+    pos = np.ascontiguousarray(pos_sph, dtype=np.float64)
+    out = np.empty(((l_max + 1) ** 2, pos.shape[0]), dtype=np.float64)
+    check(_lib.load().odis_sh_basis(pos.shape[0], pos.ctypes.data, l_max, out.ctypes.data))
+    return out
+
+
+def sh_normal_inverse(pos_sph, l_max: int) -> np.ndarray:
+    """(Y Y^T)^-1 of the least-squares fit over the given points (host only)."""
+    pos = np.ascontiguousarray(pos_sph, dtype=np.float64)
+    r = (l_max + 1) ** 2
+    out = np.empty((r, r), dtype=np.float64)
+    check(_lib.load().odis_sh_normal_inverse(pos.shape[0], pos.ctypes.data, l_max, out.ctypes.data))
+    return out
+
+
 def partition_plan(mesh: Mesh, rank: int, world: int, reorder: bool = True) -> dict:
     """Host-only view of the domain decomposition rank `rank` of `world` would use (numpy copies)."""
     lib = _lib.load()
@@ -333,6 +351,27 @@ class Solver:
         a, b = C.c_float(), C.c_float()
         check(_lib.load().odis_step_profiled(self._h, nsteps, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def step_profiled_sh(self, nsteps: int) -> tuple[float, float, float]:
+        """(edge ms, cell ms, self-gravity ms) summed over nsteps."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        check(_lib.load().odis_step_profiled_sh(self._h, nsteps, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def enable_self_gravity(self, l_max: int, factor) -> None:
+        """Spherical-harmonic self-gravity / shell-pressure term (pressureGradientSH): factor[l] for l = 0..l_max
+        (globals->shell_factor_beta or loading_factor); degrees 0 and 1 are never applied."""
+        f = np.ascontiguousarray(factor, dtype=np.float64)
+        if f.size != l_max + 1:
+            raise ValueError("factor must have l_max + 1 entries")
+        check(_lib.load().odis_enable_self_gravity(self._h, C.byref(self.mesh.view), l_max, f.ctypes.data))
+        self.sh_rows = (l_max + 1) ** 2
+
+    def sh_coefficients(self) -> np.ndarray:
+        """Least-squares harmonic coefficients of the eta the current potential was built from, (l_max+1)^2 values."""
+        out = np.empty(self.sh_rows, dtype=np.float64)
+        check(_lib.load().odis_get_sh_coefficients(self._h, out.ctypes.data))
+        return out
 
     def field(self, fid: int) -> np.ndarray:
         shape = tuple(self.F if d == "F" else self.N if d == "N" else d for d in _FIELD_SHAPES[fid])

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/odis_b200.h"
 #include "odis_config.h"
@@ -10,6 +11,7 @@
 #include "odis_gridgen.h"
 #include "odis_mesh.h"
 #include "odis_partition.h"
+#include "odis_sh.h"
 
 struct odis_config {
     odis::Config cfg;
@@ -33,6 +35,25 @@ extern "C" {
 
 const char* odis_last_error(void) { return odis::g_last_error.c_str(); }
 const char* odis_version(void) { return "odis_b200 0.1 sm_100a"; }
+
+// ------------------------------------------------------------------ spherical harmonics (host helpers) ----
+int odis_sh_basis(int32_t n, const double* pos_sph, int32_t l_max, double* Y_out) {
+    if (!pos_sph || !Y_out || n <= 0) return fail(ODIS_ERR_ARG, "NULL or empty argument");
+    if (l_max < 0 || l_max > 31) return fail(ODIS_ERR_ARG, "sh degree must be in 0..31");
+    odis::sh_basis(n, pos_sph, l_max, (size_t)n, Y_out);
+    return ODIS_OK;
+}
+
+int odis_sh_normal_inverse(int32_t n, const double* pos_sph, int32_t l_max, double* Ginv_out) {
+    if (!pos_sph || !Ginv_out || n <= 0) return fail(ODIS_ERR_ARG, "NULL or empty argument");
+    if (l_max < 0 || l_max > 31) return fail(ODIS_ERR_ARG, "sh degree must be in 0..31");
+    const int rows = odis::sh_rows(l_max);
+    std::vector<double> Y((size_t)rows * n), G;
+    odis::sh_basis(n, pos_sph, l_max, (size_t)n, Y.data());
+    if (odis::sh_normal_inverse(rows, n, (size_t)n, Y.data(), 0, G) != 0) return fail(ODIS_ERR_ARG, "normal matrix is not positive definite");
+    std::memcpy(Ginv_out, G.data(), G.size() * sizeof(double));
+    return ODIS_OK;
+}
 
 // ------------------------------------------------------------------ config ----
 int odis_config_create(odis_config** out) {

@@ -22,6 +22,8 @@
 #include "odis_kernels.cuh"
 #include "odis_partition.h"
 #include "odis_reorder.h"
+#include "odis_sh.cuh"
+#include "odis_sh.h"
 #include "odis_sphere.h"
 
 using odis::fail;
@@ -103,6 +105,20 @@ struct odis_solver {
     unsigned int* d_halo_ticket = nullptr;
     odis::HaloRemote remote_v[2], remote_c[2];             // peers' vl[0], vl[1], eu[0], eu[1] + their flag arrays
     void* ipc_opened[kMaxPeers][5] = {{nullptr}};
+
+    // spherical-harmonic self-gravity / shell-pressure term (odis_enable_self_gravity)
+    bool sh_on = false;
+    int sh_lmax = 0, sh_rows = 0;
+    double *d_shY = nullptr, *d_shGinv = nullptr, *d_shFactor = nullptr, *d_sh_partial = nullptr, *d_sh_b = nullptr, *d_sh_s = nullptr;
+    unsigned int* d_sh_ticket = nullptr;
+    std::vector<double> sh_ginv_host;
+    odis::ShTables sh_tables() const {
+        odis::ShTables t;
+        t.rows = sh_rows; t.stride = Np; t.Y = d_shY; t.Ginv = d_shGinv; t.factor = d_shFactor;
+        return t;
+    }
+    odis::ShWork sh_work() const { return odis::ShWork{d_sh_partial, d_sh_ticket, d_sh_b, d_sh_s}; }
+    int sh_launches() const { return !sh_on ? 0 : sh_rows <= odis::kShInlineRows ? 2 : 3; }
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
@@ -194,6 +210,18 @@ int ensure_series(odis_solver* s, size_t need) {
 }
 
 int halo_drain(odis_solver* s);
+
+// U += g * sum_{l >= 2} factor_l * (least-squares harmonic coefficients of eta) * Y_lm on {eta,U} buffer `eu`
+// (pressureGradientSH, spatialOperators.cpp:387-462)
+int enqueue_self_gravity(odis_solver* s, double2* eu) {
+    if (!s->sh_on) return ODIS_OK;
+    const odis::ShTables t = s->sh_tables();
+    const odis::ShWork w = s->sh_work();
+    odis::launch_sh_analysis(t, w, eu, s->No, s->prm.g, s->stream);
+    if (s->sh_rows > odis::kShInlineRows) odis::launch_sh_solve(t, w, s->prm.g, s->stream);
+    odis::launch_sh_synthesis(t, w, eu, s->N, s->stream);
+    return ODIS_OK;
+}
 
 int run_diagnostics(odis_solver* s, bool want_fields) {
     if (s->diag_current && !want_fields) return ODIS_OK;
@@ -661,8 +689,74 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), odis::CELL_UPDATE_U, s->prm.block_threads,
                            nullptr, s->stream);
     s->launches++;
+    if ((rc = enqueue_self_gravity(s, s->d_eu[s->ecur]))) return rc;
+    s->launches += s->sh_launches();
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    return ODIS_OK;
+}
+
+int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l_max, const double* factor) {
+    if (!s || !mv || !factor) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (l_max < 2 || l_max > 31) return fail(ODIS_ERR_ARG, "sh degree must be in 2..31");
+    if (mv->n_cells != s->Ng) return fail(ODIS_ERR_ARG, "mesh does not match the solver");
+    if (s->fused) return fail(ODIS_ERR_UNSUPPORTED, "the self-gravity term needs the two-launch step kernels");
+    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "the self-gravity term is not available on partitioned solvers yet");
+    if (s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is already enabled");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const int rows = odis::sh_rows(l_max);
+    if (rows >= s->Ng) return fail(ODIS_ERR_ARG, "sh degree too high for this grid");
+    // normal-matrix inverse of the least-squares fit over ALL cells, in reference order (the same on every rank)
+    {
+        std::vector<double> Yg((size_t)rows * s->Ng);
+        odis::sh_basis(s->Ng, mv->node_pos_sph, l_max, (size_t)s->Ng, Yg.data());
+        if (odis::sh_normal_inverse(rows, s->Ng, (size_t)s->Ng, Yg.data(), 0, s->sh_ginv_host) != 0)
+            return fail(ODIS_ERR_ARG, "spherical-harmonic normal matrix is not positive definite");
+    }
+    // basis rows of the held cells in device order; padded cells keep 0
+    std::vector<double> pos((size_t)s->N * 2), Y((size_t)rows * s->Np, 0.0), fac((size_t)rows, 0.0);
+    for (int i = 0; i < s->N; i++) {
+        pos[2 * (size_t)i] = mv->node_pos_sph[2 * (size_t)s->cell_perm[(size_t)i]];
+        pos[2 * (size_t)i + 1] = mv->node_pos_sph[2 * (size_t)s->cell_perm[(size_t)i] + 1];
+    }
+    odis::sh_basis(s->N, pos.data(), l_max, (size_t)s->Np, Y.data());
+    for (int k = odis::kShSkipRows; k < rows; k++) fac[(size_t)k] = factor[odis::sh_row_degree(k)];
+    s->sh_lmax = l_max; s->sh_rows = rows;
+    const int blocks = odis::sh_analysis_blocks(s->No);
+    int rc;
+    if ((rc = upload(s, &s->d_shY, Y)) || (rc = upload(s, &s->d_shGinv, s->sh_ginv_host)) || (rc = upload(s, &s->d_shFactor, fac)) ||
+        (rc = dev_alloc(s, &s->d_sh_partial, (size_t)blocks * rows)) || (rc = dev_alloc(s, &s->d_sh_b, (size_t)rows)) ||
+        (rc = dev_alloc(s, &s->d_sh_s, (size_t)rows)) || (rc = dev_alloc(s, &s->d_sh_ticket, (size_t)1)))
+        return rc;
+    ODIS_CUDA(cudaMemsetAsync(s->d_sh_ticket, 0, sizeof(unsigned int), s->stream));
+    ODIS_CUDA(cudaMemsetAsync(s->d_sh_b, 0, (size_t)rows * sizeof(double), s->stream));
+    ODIS_CUDA(cudaMemsetAsync(s->d_sh_s, 0, (size_t)rows * sizeof(double), s->stream));
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);     // captured without the extra launches
+    s->graphs.clear();
+    s->sh_on = true;
+    // the potential of the pending step gets the term of the current eta (as odis_set_state does from now on)
+    if (s->have_state) {
+        if ((rc = enqueue_self_gravity(s, s->d_eu[s->ecur]))) return rc;
+        s->launches += s->sh_launches();
+        ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return ODIS_OK;
+}
+
+int odis_get_sh_coefficients(odis_solver* s, double* out) {
+    if (!s || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (!s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is not enabled");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const size_t R = (size_t)s->sh_rows;
+    std::vector<double> b(R);
+    ODIS_CUDA(cudaMemcpyAsync(b.data(), s->d_sh_b, R * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t j = 0; j < R; j++) {
+        double acc = 0.0;
+        for (size_t k = 0; k < R; k++) acc += s->sh_ginv_host[j * R + k] * b[k];
+        out[j] = acc;
+    }
     return ODIS_OK;
 }
 
@@ -671,25 +765,40 @@ static int check_halo_timeout(odis_solver* s);
 
 int odis_step(odis_solver* s, int32_t nsteps) { return step_impl(s, nsteps, nullptr); }
 
-int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out) {
-    if (!s || !edge_ms_out || !cell_ms_out) return fail(ODIS_ERR_ARG, "NULL argument");
+static int step_profiled_impl(odis_solver* s, int32_t nsteps, float out[3]) {
     if (nsteps < 0 || nsteps > 100000) return fail(ODIS_ERR_ARG, "nsteps out of range");
     ODIS_CUDA(cudaSetDevice(s->device));
-    std::vector<cudaEvent_t> marks((size_t)nsteps * 3);
+    std::vector<cudaEvent_t> marks((size_t)nsteps * 4);
     for (auto& e : marks) ODIS_CUDA(cudaEventCreate(&e));
     int rc = step_impl(s, nsteps, &marks);
     if (!rc && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(ODIS_ERR_CUDA, "synchronize failed");
-    double edge = 0.0, cell = 0.0;
+    double sum[3] = {0.0, 0.0, 0.0};
     if (!rc) {
-        for (int k = 0; k < nsteps; k++) {
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, marks[(size_t)k * 3], marks[(size_t)k * 3 + 1]);
-            cudaEventElapsedTime(&b, marks[(size_t)k * 3 + 1], marks[(size_t)k * 3 + 2]);
-            edge += a; cell += b;
-        }
+        for (int k = 0; k < nsteps; k++)
+            for (int q = 0; q < 3; q++) {
+                float a = 0.f;
+                cudaEventElapsedTime(&a, marks[(size_t)k * 4 + q], marks[(size_t)k * 4 + q + 1]);
+                sum[q] += a;
+            }
     }
     for (auto& e : marks) cudaEventDestroy(e);
-    *edge_ms_out = (float)edge; *cell_ms_out = (float)cell;
+    for (int q = 0; q < 3; q++) out[q] = (float)sum[q];
+    return rc;
+}
+
+int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out) {
+    if (!s || !edge_ms_out || !cell_ms_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    float out[3];
+    int rc = step_profiled_impl(s, nsteps, out);
+    *edge_ms_out = out[0]; *cell_ms_out = out[1];
+    return rc;
+}
+
+int odis_step_profiled_sh(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out, float* sh_ms_out) {
+    if (!s || !edge_ms_out || !cell_ms_out || !sh_ms_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    float out[3];
+    int rc = step_profiled_impl(s, nsteps, out);
+    *edge_ms_out = out[0]; *cell_ms_out = out[1]; *sh_ms_out = out[2];
     return rc;
 }
 
@@ -729,7 +838,7 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
     es.energy_out = dev_ctl ? nullptr : s->d_series + (s->iter - s->iter0);
     es.ctl = dev_ctl ? s->d_ctl : nullptr; es.series = s->d_series; es.scal = s->d_scal;
-    if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4], s->stream);
     // partitioned: ONE exchange per step, of v^{n+1} on the boundary edges. The staged edge kernel pushes it itself
     // (HaloInline) and the direct cell kernel waits for the neighbours' in its last CTAs; the other variants get a separate
     // exchange launch (which also waits). Ghost cells are updated locally, so {eta,U} is never exchanged.
@@ -743,7 +852,7 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
         int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
         if (rc2) return rc2;
     }
-    if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream);
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 1], s->stream);
     if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
     // the staged edge kernel finishes its own energy sum; the direct one leaves per-warp partials to the cell kernel
     odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
@@ -761,11 +870,13 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     }
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;
-    if (marks) cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream);
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
+    { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 3], s->stream);
     s->cur = 1 - s->cur;
     s->iter++;
     s->last_mode = mode;
-    s->launches += 2;
+    s->launches += 2 + s->sh_launches();
     return ODIS_OK;
 }
 
@@ -791,7 +902,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             fs.block_partial = s->d_block_partial; fs.ticket = s->d_ticket;
             fs.energy_out = s->d_series + (s->iter - s->iter0);
             const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
-            if (marks) cudaEventRecord((*marks)[(size_t)k * 3], s->stream);
+            if (marks) cudaEventRecord((*marks)[(size_t)k * 4], s->stream);
             ODIS_CUDA(odis::launch_step_fused(ft, s->phys, fs, mode, s->mode_lag, s->eta_lag ? 1 : 0, step_scalars(s->prm.omega, tnext), s->stream));
             if (s->eta_lag) rotate_cell_history(s, s->mode_lag);
             s->ecur = 1 - s->ecur;
@@ -799,7 +910,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
                 int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
                 if (rc2) return rc2;
             }
-            if (marks) { cudaEventRecord((*marks)[(size_t)k * 3 + 1], s->stream); cudaEventRecord((*marks)[(size_t)k * 3 + 2], s->stream); }
+            if (marks) for (int q = 1; q < 4; q++) cudaEventRecord((*marks)[(size_t)k * 4 + q], s->stream);
             if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
             s->cur = 1 - s->cur;
             s->iter++;
@@ -848,7 +959,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             for (int r = 0; r < reps; r++) ODIS_CUDA(cudaGraphLaunch(it->second, s->stream));
             const int adv = reps * kGraphSteps;
             s->graph_launches += reps;
-            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0));
+            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0) + s->sh_launches());
             s->iter += adv;
             s->last_mode = odis::AB3_FULL;
             done += adv;
@@ -977,7 +1088,11 @@ int odis_get_iter(odis_solver* s, int64_t* iter_out) {
 int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* alg_bytes_out) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL argument");
     if (device_bytes_out) *device_bytes_out = (int64_t)s->device_bytes;
-    if (alg_bytes_out) *alg_bytes_out = 200LL * s->Fo + 128LL * s->No;    // SURVEY.md §8(d), this rank's share
+    if (alg_bytes_out) {
+        *alg_bytes_out = 200LL * s->Fo + 128LL * s->No;    // SURVEY.md §8(d), this rank's share
+        // self-gravity: Y streamed by the analysis (all rows) and the synthesis (degrees >= 2), {eta,U} read twice, U written
+        if (s->sh_on) *alg_bytes_out += 8LL * s->sh_rows * s->No + 8LL * (s->sh_rows - odis::kShSkipRows) * s->N + 16LL * s->No + 24LL * s->N;
+    }
     return ODIS_OK;
 }
 
@@ -1014,7 +1129,8 @@ void odis_destroy(odis_solver* s) {
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,
-                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket};
+                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket, s->d_shY, s->d_shGinv, s->d_shFactor, s->d_sh_partial, s->d_sh_b, s->d_sh_s,
+                    s->d_sh_ticket};
     for (int k = 0; k < kMaxPeers; k++)
         for (int j = 0; j < 5; j++)
             if (s->ipc_opened[k][j]) cudaIpcCloseMemHandle(s->ipc_opened[k][j]);

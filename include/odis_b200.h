@@ -207,6 +207,26 @@ int odis_step_timed(odis_solver* s, int32_t nsteps, float* elapsed_ms_out);
 /* As odis_step, with every kernel launch bracketed by its own CUDA event pair; returns the summed device
  * time (ms) of the edge-update and of the cell-update launches separately (roofline instrumentation). */
 int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out);
+/* Self-gravity / shell-pressure term by spherical harmonics — the reference's pressureGradientSH
+ * (src/spatialOperators.cpp:387-462, commented out at HEAD) with the basis of Mesh::CalcLegendreFuncs
+ * (src/mesh.cpp:2154-2260) and the least-squares coefficients of getSHCoeffsGG (src/sphericalHarmonics.cpp:16-72 ->
+ * src/extractSHCoeffGG.f95). From this call on, every step adds
+ *     g * sum_{l=2..l_max} factor[l] * sum_m (C_lm cos(m lon) + S_lm sin(m lon)) Pbar_lm(cos colat)
+ * to forcing_potential, C_lm/S_lm being the least-squares (degrees 0..l_max) coefficients of eta at the start of
+ * the step. factor[l] = globals->shell_factor_beta[l] (= 1 - beta_l, boundaryConditions.cpp:373) for the LID_*
+ * surfaces, globals->loading_factor[l] for FREE_LOADING; 4-pi normalised harmonics with the Condon-Shortley phase
+ * (src/legendre.f95). On the device: a dense matrix-vector product per direction (analysis, synthesis). Call it
+ * after odis_create, before or after odis_set_state; `mesh` is the mesh the solver was created from. */
+int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mesh, int32_t l_max, const double* factor /*[l_max+1]*/);
+/* Least-squares coefficients of the eta the last potential was built from: [(l_max+1)^2], degree-major, per degree
+ * m = 0, then (cos, sin) for m = 1..l. */
+int odis_get_sh_coefficients(odis_solver* s, double* out);
+/* As odis_step_profiled, with the self-gravity launches timed separately. */
+int odis_step_profiled_sh(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out, float* sh_ms_out);
+/* Host-only helpers (no GPU): the basis rows Y[(l_max+1)^2][n] at the given (lat, lon) [n][2] in radians, and the
+ * inverse normal matrix (Y Y^T)^-1 [(l_max+1)^2][(l_max+1)^2] of the least-squares fit over those points. */
+int odis_sh_basis(int32_t n, const double* pos_sph, int32_t l_max, double* Y_out);
+int odis_sh_normal_inverse(int32_t n, const double* pos_sph, int32_t l_max, double* Ginv_out);
 /* Device -> host, reference numbering and layout. */
 int odis_get_field(odis_solver* s, int32_t field, double* out);
 /* Area-mean dissipated energy flux after the last step (e_diss of updateEnergy, energy.cpp:60). */

@@ -52,6 +52,11 @@ typedef struct {
     double *tmp_f, *tmp_n;
     long iter;
     double e_diss;
+    /* optional spherical-harmonic self-gravity term (oracle/sh_oracle.py builds the matrices) */
+    int sh_rows;
+    const double* sh_Y;        /* [rows][N] basis */
+    const double* sh_T;        /* [rows][rows] factor_l * (Y Y^T)^-1, rows of degree 0 and 1 zero */
+    double *sh_b, *sh_s;
 } oracle_ctx;
 
 static const double pi = 3.1415926535897932384626433832795028841971693993751058;  /* mathRoutines.h:10 */
@@ -305,6 +310,31 @@ static void updateEnergy(const oracle_ctx* c, double* avg_flux_out, double* e_fl
     *avg_flux_out = avg_flux;
 }
 
+/* pressureGradientSH, spatialOperators.cpp:387-462 (commented out at reference HEAD; restated from it):
+ * coefficients of eta by least squares over the cell centres (sphericalHarmonics.cpp:16-72, extractSHCoeffGG.f95), then
+ * forcing_potential += g * sh_matrix * coefficients (:446, dgemv alpha = factor = g, beta = 1) for degrees >= 2, the
+ * basis rows carrying factor_l (mesh.cpp:2228-2238). */
+static void self_gravity(oracle_ctx* c, double* potential, const double* eta) {
+    const int R = c->sh_rows, N = c->N;
+    int i, j, k;
+    if (!R) return;
+    for (k = 0; k < R; k++) {
+        long double acc = 0.0L;
+        for (i = 0; i < N; i++) acc += (long double)c->sh_Y[(size_t)k * N + i] * eta[i];
+        c->sh_b[k] = (double)acc;
+    }
+    for (j = 0; j < R; j++) {
+        long double acc = 0.0L;
+        for (k = 0; k < R; k++) acc += (long double)c->sh_T[(size_t)j * R + k] * c->sh_b[k];
+        c->sh_s[j] = c->p.g * (double)acc;
+    }
+    for (i = 0; i < N; i++) {
+        double acc = 0.0;
+        for (k = 4; k < R; k++) acc = acc + c->sh_Y[(size_t)k * N + i] * c->sh_s[k];
+        potential[i] = potential[i] + acc;
+    }
+}
+
 /* ---------------------------------------------------------------- public ---- */
 oracle_ctx* oracle_create(const oracle_mesh* mesh, const oracle_params* params) {
     oracle_ctx* c = (oracle_ctx*)calloc(1, sizeof(oracle_ctx));
@@ -328,8 +358,17 @@ void oracle_destroy(oracle_ctx* c) {
     free(c->trigLat); free(c->trigLon); free(c->trig2Lat); free(c->trig2Lon); free(c->trigSqLat);
     free(c->v_t0); free(c->p_t0); free(c->dv_dt); free(c->dp_dt); free(c->dv_dt_t0); free(c->dp_dt_t0);
     free(c->drag_term); free(c->forcing_potential); free(c->v_avg); free(c->energy_diss); free(c->tmp_f); free(c->tmp_n);
+    free(c->sh_b); free(c->sh_s);
     free(c);
 }
+
+/* Y, T stay owned by the caller */
+void oracle_set_sh(oracle_ctx* c, int rows, const double* Y, const double* T) {
+    free(c->sh_b); free(c->sh_s);
+    c->sh_rows = rows; c->sh_Y = Y; c->sh_T = T;
+    c->sh_b = (double*)calloc((size_t)rows + 1, 8); c->sh_s = (double*)calloc((size_t)rows + 1, 8);
+}
+void oracle_get_sh_b(const oracle_ctx* c, double* out) { memcpy(out, c->sh_b, (size_t)c->sh_rows * 8); }
 
 /* state as ab3Explicit holds it after getInitialConditions (timeIntegrator.cpp:168-178) */
 void oracle_set_state(oracle_ctx* c, const double* v, const double* eta, const double* dvdt, const double* detadt, long iter) {
@@ -356,6 +395,7 @@ void oracle_step(oracle_ctx* c, int nsteps, double* diss_series) {
         spmv_add(&c->cor, c->v_t0, c->dv_dt_t0);
         for (i = 0; i < F; ++i) c->dv_dt[i * 3] = c->dv_dt_t0[i];       /* :215 */
         forcing(c, c->forcing_potential, current_time + dt);             /* :218 */
+        self_gravity(c, c->forcing_potential, c->p_t0);
         spmv_assign(&c->drag, c->v_t0, c->drag_term);                    /* :219 */
         spmv_add(&c->grad, c->forcing_potential, c->drag_term);
         integrateAB3scalar(c, c->v_t0, c->dv_dt, c->iter, F);            /* :239 */

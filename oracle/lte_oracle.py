@@ -41,6 +41,8 @@ def _load():
         lib.oracle_get_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.oracle_get_dissipation_avg.restype = C.c_double
         lib.oracle_get_dissipation_avg.argtypes = [C.c_void_p]
+        lib.oracle_set_sh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.oracle_get_sh_b.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_get_iter.restype = C.c_long
         lib.oracle_get_iter.argtypes = [C.c_void_p]
         _lib = lib
@@ -85,6 +87,14 @@ class LteOracle:
     def set_state(self, v=None, eta=None, dvdt=None, detadt=None, iter: int = 0):
         k = [self._ptr(v, self.F), self._ptr(eta, self.N), self._ptr(dvdt, self.F * 3), self._ptr(detadt, self.N * 3)]
         _load().oracle_set_state(self._h, k[0][1], k[1][1], k[2][1], k[3][1], iter)
+
+    def set_self_gravity(self, Y, T) -> None:
+        """Y [rows][N] basis, T [rows][rows] = factor_l * (Y Y^T)^-1 (oracle/sh_oracle.py)."""
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        assert Y.shape[1] == self.N and T.shape == (Y.shape[0], Y.shape[0])
+        self._keep["sh_Y"], self._keep["sh_T"] = Y, T
+        _load().oracle_set_sh(self._h, Y.shape[0], Y.ctypes.data, T.ctypes.data)
 
     def step(self, nsteps: int) -> np.ndarray:
         series = np.zeros(nsteps, dtype=np.float64)
