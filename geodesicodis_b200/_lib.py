@@ -84,7 +84,7 @@ SIGNATURES = {
     "odis_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
     "odis_step_profiled": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float)]),
-    "odis_enable_self_gravity": (C.c_int, [C.c_void_p, P(MeshView), c_i32, C.c_void_p]),
+    "odis_enable_self_gravity": (C.c_int, [C.c_void_p, P(MeshView), c_i32, C.c_void_p, c_i32]),
     "odis_get_sh_coefficients": (C.c_int, [C.c_void_p, C.c_void_p]),
     "odis_step_profiled_sh": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float), P(C.c_float)]),
     "odis_sh_basis": (C.c_int, [c_i32, C.c_void_p, c_i32, C.c_void_p]),

@@ -358,13 +358,14 @@ class Solver:
         check(_lib.load().odis_step_profiled_sh(self._h, nsteps, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def enable_self_gravity(self, l_max: int, factor) -> None:
+    def enable_self_gravity(self, l_max: int, factor, stored_basis: bool = False) -> None:
         """Spherical-harmonic self-gravity / shell-pressure term (pressureGradientSH): factor[l] for l = 0..l_max
-        (globals->shell_factor_beta or loading_factor); degrees 0 and 1 are never applied."""
+        (globals->shell_factor_beta or loading_factor); degrees 0 and 1 are never applied. stored_basis: keep the basis
+        matrix in HBM (two GEMVs per step) instead of rebuilding it per cell (matrix-free, the default)."""
         f = np.ascontiguousarray(factor, dtype=np.float64)
         if f.size != l_max + 1:
             raise ValueError("factor must have l_max + 1 entries")
-        check(_lib.load().odis_enable_self_gravity(self._h, C.byref(self.mesh.view), l_max, f.ctypes.data))
+        check(_lib.load().odis_enable_self_gravity(self._h, C.byref(self.mesh.view), l_max, f.ctypes.data, int(stored_basis)))
         self.sh_rows = (l_max + 1) ** 2
 
     def sh_coefficients(self) -> np.ndarray:

@@ -109,16 +109,28 @@ struct odis_solver {
     // spherical-harmonic self-gravity / shell-pressure term (odis_enable_self_gravity)
     bool sh_on = false;
     int sh_lmax = 0, sh_rows = 0;
+    bool sh_stored = false;          // basis rows kept in HBM (GEMV) instead of rebuilt per cell
+    double* d_shRec = nullptr;
     double *d_shY = nullptr, *d_shGinv = nullptr, *d_shFactor = nullptr, *d_sh_partial = nullptr, *d_sh_b = nullptr, *d_sh_s = nullptr;
-    unsigned int* d_sh_ticket = nullptr;
     std::vector<double> sh_ginv_host;
+    unsigned char* d_sh_xblock = nullptr;             // partitioned: this rank's exchange block (odis_sh.cuh), mapped by every other rank
+    unsigned long long* d_sh_xctl = nullptr;
+    unsigned char* sh_xremote[odis::kShMaxWorld] = {nullptr};
+    void* sh_ipc_opened[odis::kShMaxWorld] = {nullptr};
+    odis::ShExchange sh_exchange() const {
+        odis::ShExchange x;
+        x.world = world; x.rank = rank; x.ctl = d_sh_xctl;
+        for (int r = 0; r < odis::kShMaxWorld; r++) x.block[r] = r < world ? sh_xremote[r] : nullptr;
+        return x;
+    }
     odis::ShTables sh_tables() const {
         odis::ShTables t;
-        t.rows = sh_rows; t.stride = Np; t.Y = d_shY; t.Ginv = d_shGinv; t.factor = d_shFactor;
+        t.rows = sh_rows; t.stride = Np; t.Y = sh_stored ? d_shY : nullptr; t.Ginv = d_shGinv; t.factor = d_shFactor;
+        t.l_max = sh_lmax; t.trig = d_trig; t.rec = d_shRec;
         return t;
     }
-    odis::ShWork sh_work() const { return odis::ShWork{d_sh_partial, d_sh_ticket, d_sh_b, d_sh_s}; }
-    int sh_launches() const { return !sh_on ? 0 : sh_rows <= odis::kShInlineRows ? 2 : 3; }
+    odis::ShWork sh_work() const { return odis::ShWork{d_sh_partial, odis::kShMaxBlocks, 0, d_sh_b, d_sh_s}; }
+    int sh_launches() const { return !sh_on ? 0 : odis::sh_analysis_launches(sh_rows, world > 1) + 1; }
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
@@ -141,8 +153,8 @@ struct odis_solver {
 struct HaloBlob {                     // what one rank publishes to the others (odis_halo_export)
     int32_t rank, world;
     int64_t pid;
-    void* raw[5];                     // vl[0], vl[1], eu[0], eu[1], flags — usable directly inside one process
-    cudaIpcMemHandle_t ipc[5];
+    void* raw[6];                     // vl[0], vl[1], eu[0], eu[1], flags, self-gravity exchange block — usable directly inside one process
+    cudaIpcMemHandle_t ipc[6];
     int32_t device;
     int32_t pad;
 };
@@ -217,8 +229,9 @@ int enqueue_self_gravity(odis_solver* s, double2* eu) {
     if (!s->sh_on) return ODIS_OK;
     const odis::ShTables t = s->sh_tables();
     const odis::ShWork w = s->sh_work();
-    odis::launch_sh_analysis(t, w, eu, s->No, s->prm.g, s->stream);
-    if (s->sh_rows > odis::kShInlineRows) odis::launch_sh_solve(t, w, s->prm.g, s->stream);
+    odis::ShExchange x;
+    if (s->world > 1) x = s->sh_exchange();
+    odis::launch_sh_analysis(t, w, eu, s->No, s->prm.g, s->world > 1 ? &x : nullptr, s->stream);
     odis::launch_sh_synthesis(t, w, eu, s->N, s->stream);
     return ODIS_OK;
 }
@@ -508,9 +521,14 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
             }
         }
         if ((rc = upload(s, &s->d_csr_e_first, first)) || (rc = upload(s, &s->d_csr_e_peer, pk)) || (rc = upload(s, &s->d_csr_e_remote, rm)) ||
-            (rc = dev_alloc(s, &s->d_halo_done, (size_t)1)))
+            (rc = dev_alloc(s, &s->d_halo_done, (size_t)1)) || (rc = dev_alloc(s, &s->d_sh_xblock, odis::kShXBytes)) ||
+            (rc = dev_alloc(s, &s->d_sh_xctl, (size_t)4)))
             return bail(rc);
+        if (world > odis::kShMaxWorld) return bail(fail(ODIS_ERR_ARG, "at most 8 ranks"));
         cudaMemsetAsync(s->d_halo_done, 0, sizeof(unsigned int), s->stream);
+        cudaMemsetAsync(s->d_sh_xblock, 0, odis::kShXBytes, s->stream);
+        cudaMemsetAsync(s->d_sh_xctl, 0, 4 * sizeof(unsigned long long), s->stream);
+        s->sh_xremote[rank] = s->d_sh_xblock;
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "halo table upload failed"));
     }
     *out = s;
@@ -598,9 +616,9 @@ int odis_halo_export(odis_solver* s, void* blob_out) {
     HaloBlob b;
     std::memset(&b, 0, sizeof b);
     b.rank = s->rank; b.world = s->world; b.pid = (int64_t)getpid(); b.device = s->device;
-    b.raw[0] = s->d_vl[0]; b.raw[1] = s->d_vl[1]; b.raw[2] = s->d_eu[0]; b.raw[3] = s->d_eu[1]; b.raw[4] = s->d_flags;
+    b.raw[0] = s->d_vl[0]; b.raw[1] = s->d_vl[1]; b.raw[2] = s->d_eu[0]; b.raw[3] = s->d_eu[1]; b.raw[4] = s->d_flags; b.raw[5] = s->d_sh_xblock;
     if (s->world > 1)
-        for (int k = 0; k < 5; k++) ODIS_CUDA(cudaIpcGetMemHandle(&b.ipc[k], b.raw[k]));
+        for (int k = 0; k < 6; k++) ODIS_CUDA(cudaIpcGetMemHandle(&b.ipc[k], b.raw[k]));
     std::memcpy(blob_out, &b, sizeof b);
     return ODIS_OK;
 }
@@ -630,6 +648,25 @@ int odis_halo_connect(odis_solver* s, const void* all_blobs) {
         s->remote_v[0].data[k] = (double2*)p[0]; s->remote_v[1].data[k] = (double2*)p[1];
         s->remote_c[0].data[k] = (double2*)p[2]; s->remote_c[1].data[k] = (double2*)p[3];
         s->remote_v[0].flags[k] = s->remote_v[1].flags[k] = s->remote_c[0].flags[k] = s->remote_c[1].flags[k] = (unsigned long long*)p[4];
+    }
+    // the self-gravity exchange blocks of ALL ranks (the harmonic sums are global, not a neighbour exchange)
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) continue;
+        const HaloBlob& b = blobs[r];
+        if (b.rank != r || b.world != s->world) return fail(ODIS_ERR_ARG, "halo blobs are not ordered by rank");
+        if (b.pid == (int64_t)getpid()) {
+            if (b.device != s->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ODIS_ERR_CUDA, "cudaDeviceEnablePeerAccess failed");
+                cudaGetLastError();
+            }
+            s->sh_xremote[r] = (unsigned char*)b.raw[5];
+        } else {
+            void* p = nullptr;
+            ODIS_CUDA(cudaIpcOpenMemHandle(&p, b.ipc[5], cudaIpcMemLazyEnablePeerAccess));
+            s->sh_ipc_opened[r] = p;
+            s->sh_xremote[r] = (unsigned char*)p;
+        }
     }
     s->connected = true;
     return ODIS_OK;
@@ -692,16 +729,19 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     if ((rc = enqueue_self_gravity(s, s->d_eu[s->ecur]))) return rc;
     s->launches += s->sh_launches();
     ODIS_CUDA(cudaGetLastError());
-    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    // partitioned + self-gravity: the harmonic sums wait for every rank's share, so the call must not block here (one host
+    // thread may be driving all ranks in turn); the stream keeps the order
+    if (!(s->world > 1 && s->sh_on)) ODIS_CUDA(cudaStreamSynchronize(s->stream));
     return ODIS_OK;
 }
 
-int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l_max, const double* factor) {
+int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l_max, const double* factor, int32_t stored_basis) {
     if (!s || !mv || !factor) return fail(ODIS_ERR_ARG, "NULL argument");
     if (l_max < 2 || l_max > 31) return fail(ODIS_ERR_ARG, "sh degree must be in 2..31");
     if (mv->n_cells != s->Ng) return fail(ODIS_ERR_ARG, "mesh does not match the solver");
     if (s->fused) return fail(ODIS_ERR_UNSUPPORTED, "the self-gravity term needs the two-launch step kernels");
-    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "the self-gravity term is not available on partitioned solvers yet");
+    if (s->world > 1 && !s->connected) return fail(ODIS_ERR_STATE, "call odis_halo_connect before odis_enable_self_gravity on a partitioned solver");
+    if (s->world > 1 && !s->pipe_edge) return fail(ODIS_ERR_UNSUPPORTED, "partitioned self-gravity needs the default step kernels");
     if (s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is already enabled");
     ODIS_CUDA(cudaSetDevice(s->device));
     const int rows = odis::sh_rows(l_max);
@@ -713,22 +753,27 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
         if (odis::sh_normal_inverse(rows, s->Ng, (size_t)s->Ng, Yg.data(), 0, s->sh_ginv_host) != 0)
             return fail(ODIS_ERR_ARG, "spherical-harmonic normal matrix is not positive definite");
     }
-    // basis rows of the held cells in device order; padded cells keep 0
-    std::vector<double> pos((size_t)s->N * 2), Y((size_t)rows * s->Np, 0.0), fac((size_t)rows, 0.0);
-    for (int i = 0; i < s->N; i++) {
-        pos[2 * (size_t)i] = mv->node_pos_sph[2 * (size_t)s->cell_perm[(size_t)i]];
-        pos[2 * (size_t)i + 1] = mv->node_pos_sph[2 * (size_t)s->cell_perm[(size_t)i] + 1];
-    }
-    odis::sh_basis(s->N, pos.data(), l_max, (size_t)s->Np, Y.data());
+    std::vector<double> fac((size_t)rows, 0.0), rec((size_t)odis::kShRecDoubles);
     for (int k = odis::kShSkipRows; k < rows; k++) fac[(size_t)k] = factor[odis::sh_row_degree(k)];
-    s->sh_lmax = l_max; s->sh_rows = rows;
-    const int blocks = odis::sh_analysis_blocks(s->No);
+    odis::sh_recurrence_table(rec.data());
+    s->sh_lmax = l_max; s->sh_rows = rows; s->sh_stored = stored_basis != 0;
     int rc;
-    if ((rc = upload(s, &s->d_shY, Y)) || (rc = upload(s, &s->d_shGinv, s->sh_ginv_host)) || (rc = upload(s, &s->d_shFactor, fac)) ||
-        (rc = dev_alloc(s, &s->d_sh_partial, (size_t)blocks * rows)) || (rc = dev_alloc(s, &s->d_sh_b, (size_t)rows)) ||
-        (rc = dev_alloc(s, &s->d_sh_s, (size_t)rows)) || (rc = dev_alloc(s, &s->d_sh_ticket, (size_t)1)))
+    if (s->sh_stored) {
+        // basis rows of the held cells in device order; padded cells keep 0
+        std::vector<double> pos((size_t)s->N * 2), Y((size_t)rows * s->Np, 0.0);
+        for (int i = 0; i < s->N; i++) {
+            pos[2 * (size_t)i] = mv->node_pos_sph[2 * (size_t)s->cell_perm[(size_t)i]];
+            pos[2 * (size_t)i + 1] = mv->node_pos_sph[2 * (size_t)s->cell_perm[(size_t)i] + 1];
+        }
+        odis::sh_basis(s->N, pos.data(), l_max, (size_t)s->Np, Y.data());
+        if ((rc = upload(s, &s->d_shY, Y))) return rc;
+        ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    ODIS_CUDA(odis::sh_configure());
+    if ((rc = upload(s, &s->d_shRec, rec)) || (rc = upload(s, &s->d_shGinv, s->sh_ginv_host)) || (rc = upload(s, &s->d_shFactor, fac)) ||
+        (rc = dev_alloc(s, &s->d_sh_partial, (size_t)odis::kShMaxBlocks * rows)) || (rc = dev_alloc(s, &s->d_sh_b, (size_t)rows)) ||
+        (rc = dev_alloc(s, &s->d_sh_s, (size_t)rows)))
         return rc;
-    ODIS_CUDA(cudaMemsetAsync(s->d_sh_ticket, 0, sizeof(unsigned int), s->stream));
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_b, 0, (size_t)rows * sizeof(double), s->stream));
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_s, 0, (size_t)rows * sizeof(double), s->stream));
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
@@ -739,7 +784,7 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
     if (s->have_state) {
         if ((rc = enqueue_self_gravity(s, s->d_eu[s->ecur]))) return rc;
         s->launches += s->sh_launches();
-        ODIS_CUDA(cudaStreamSynchronize(s->stream));
+        if (s->world == 1) ODIS_CUDA(cudaStreamSynchronize(s->stream));
     }
     return ODIS_OK;
 }
@@ -1091,7 +1136,9 @@ int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* alg_b
     if (alg_bytes_out) {
         *alg_bytes_out = 200LL * s->Fo + 128LL * s->No;    // SURVEY.md §8(d), this rank's share
         // self-gravity: Y streamed by the analysis (all rows) and the synthesis (degrees >= 2), {eta,U} read twice, U written
-        if (s->sh_on) *alg_bytes_out += 8LL * s->sh_rows * s->No + 8LL * (s->sh_rows - odis::kShSkipRows) * s->N + 16LL * s->No + 24LL * s->N;
+        if (s->sh_on && s->sh_stored) *alg_bytes_out += 8LL * s->sh_rows * s->No + 8LL * (s->sh_rows - odis::kShSkipRows) * s->N + 16LL * s->No + 24LL * s->N;
+        // matrix-free: 4 trig values + {eta,U} per cell per pass, U written
+        if (s->sh_on && !s->sh_stored) *alg_bytes_out += 48LL * s->No + 56LL * s->N;
     }
     return ODIS_OK;
 }
@@ -1108,6 +1155,10 @@ static int check_halo_timeout(odis_solver* s) {
     unsigned long long flag = 0;
     ODIS_CUDA(cudaMemcpy(&flag, &s->d_ctl->pad, sizeof flag, cudaMemcpyDeviceToHost));
     if (flag) return fail(ODIS_ERR_STATE, "halo exchange timed out: a neighbouring rank did not take the same steps (results are invalid)");
+    if (s->sh_on) {
+        ODIS_CUDA(cudaMemcpy(&flag, s->d_sh_xctl + 2, sizeof flag, cudaMemcpyDeviceToHost));
+        if (flag) return fail(ODIS_ERR_STATE, "self-gravity all-reduce timed out: a rank did not take the same steps (results are invalid)");
+    }
     return ODIS_OK;
 }
 
@@ -1129,11 +1180,12 @@ void odis_destroy(odis_solver* s) {
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,
-                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket, s->d_shY, s->d_shGinv, s->d_shFactor, s->d_sh_partial, s->d_sh_b, s->d_sh_s,
-                    s->d_sh_ticket};
+                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket, s->d_shY, s->d_shRec, s->d_shGinv, s->d_shFactor, s->d_sh_partial, s->d_sh_b, s->d_sh_s, s->d_sh_xblock, s->d_sh_xctl};
     for (int k = 0; k < kMaxPeers; k++)
         for (int j = 0; j < 5; j++)
             if (s->ipc_opened[k][j]) cudaIpcCloseMemHandle(s->ipc_opened[k][j]);
+    for (int r = 0; r < odis::kShMaxWorld; r++)
+        if (s->sh_ipc_opened[r]) cudaIpcCloseMemHandle(s->sh_ipc_opened[r]);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -3,9 +3,9 @@
 // Per time step, after the cell update has produced eta^{n+1} and the tidal potential of the next step:
 //   sh_analysis   b = Y eta            dense (rows x cells) matrix-vector product, Y streamed once: the GEMV the reference did
 //                                      through SHExpandLSQ (src/extractSHCoeffGG.f95), with the fixed normal-matrix inverse
-//                                      hoisted out of the loop; per-CTA partial sums, last CTA adds them in index order and
-//                                      (small bases) applies  s = g * factor_l * (Ginv b)_{l >= 2}
-//   sh_solve      the same  s = ...    as its own launch when the basis is too large for one CTA
+//                                      hoisted out of the loop; persistent CTAs leave per-CTA partial sums
+//   sh_reduce_solve                    adds the partials in CTA order and applies  s = g * factor_l * (Ginv b)_{l >= 2}
+//                                      (two launches, reduce then solve, when the basis has more than 128 rows)
 //   sh_synthesis  U_i += sum_k Y_ki s_k   the dgemv of pressureGradientSH (src/spatialOperators.cpp:446), fused with the
 //                                      add into forcing_potential; rows of degree >= 2 only
 // Algorithmic bytes per step: 8*rows*N (analysis) + 8*(rows-4)*N (synthesis) + 8N (eta) + 16N ({eta,U} r/w).
@@ -16,24 +16,58 @@ namespace odis {
 
 struct ShTables {
     int rows;                 // (l_max+1)^2 basis rows; rows 0..3 (degrees 0, 1) are fitted but never applied
-    int stride;               // cells per row of Y (held cells rounded up)
-    const double* Y;          // [rows][stride] device cell numbering
+    int stride;               // cells per row of Y / trig (held cells rounded up)
+    const double* Y;          // [rows][stride] device cell numbering; nullptr: matrix-free (basis recomputed per cell)
+    int l_max;
+    const double* trig;       // matrix-free: [4][stride] cos lat, sin lat, cos lon, sin lon (the cell kernel's table)
+    const double* rec;        // matrix-free: recurrence coefficients, see sh_recurrence_table()
     const double* Ginv;       // [rows][rows] inverse normal matrix of the least-squares fit
     const double* factor;     // [rows] factor_l of the row's degree (1 - beta_l, or the loading factor); 0 for degrees 0, 1
 };
 
+constexpr int kShMaxBlocks = 296;     // analysis CTAs: persistent, two per SM
 struct ShWork {
-    double* partial;          // [blocks][rows] per-CTA sums
-    unsigned int* ticket;
+    double* partial;          // [rows][partial_stride] per-CTA sums
+    int partial_stride;       // >= kShMaxBlocks
+    int n_blocks;             // filled by launch_sh_analysis
     double* b;                // [rows] Y eta
     double* s;                // [rows] g * factor * (Ginv b)
 };
 
-constexpr int kShInlineRows = 128;    // up to here the last analysis CTA does the solve itself
-int sh_analysis_blocks(int n_cells);
-// eu: {eta, U} per cell; only the first n_own cells enter the fit
-void launch_sh_analysis(const ShTables& t, const ShWork& w, const double2* eu, int n_own, double g, cudaStream_t stream);
-void launch_sh_solve(const ShTables& t, const ShWork& w, double g, cudaStream_t stream);
+// Matrix-free variant (Y == nullptr): both kernels rebuild the basis values of a cell from (sin lat, cos lat, cos lon,
+// sin lon) with the Legendre column recurrences and the rotation recurrence for cos/sin(m lon) — 32 B per cell instead of
+// 8*rows: FP64-pipe-bound instead of HBM-bound, ~8x less time at l_max = 8. These two kernels use fused multiply-adds
+// (the term has no bit-exact reference to follow).
+constexpr int kShRecStride = 32;      // l_max <= 31
+constexpr int kShRecDoubles = 2 * kShRecStride * kShRecStride + 2 * kShRecStride;
+// [a_lm | b_lm | sectoral(m) | first(m)]: Pbar_lm = a_lm (z Pbar_{l-1,m} - b_lm Pbar_{l-2,m}); Pbar_mm = sectoral(m) u Pbar_{m-1,m-1}
+// (sign of the Condon-Shortley phase included); Pbar_{m+1,m} = first(m) z Pbar_mm.   Host side; fills kShRecDoubles values.
+void sh_recurrence_table(double* rec);
+cudaError_t sh_configure();           // dynamic shared-memory opt-in of the matrix-free kernels (before any capture)
+
+// Partitioned runs: every rank fits its own cells, the sums b are all-reduced through peer memory inside the kernels (no host
+// call, graph-replayable). Each rank owns one exchange block, mapped by all the others:
+//     [kShMaxWorld epoch flags (u64)] [2][kShXRows] doubles: this rank's b of even / odd epochs
+//   sh_reduce_publish  this rank's b into its own block (parity of the new epoch); its last CTA then raises this rank's flag in
+//                      every rank's block (system-scope release)
+//   sh_allsolve        waits until all flags show the epoch (system-scope acquire, bounded), adds the ranks' b in rank order — the
+//                      same bits on every rank — and applies the solve
+// A rank cannot be more than one epoch ahead of any other (the next allsolve needs everyone's publish), hence two buffers.
+constexpr int kShMaxWorld = 8;
+constexpr int kShXRows = 1024;
+constexpr size_t kShXBytes = kShMaxWorld * sizeof(unsigned long long) + 2 * (size_t)kShXRows * sizeof(double);
+struct ShExchange {
+    int world, rank;
+    unsigned long long* ctl;                 // local: [0] epoch, [1] ticket, [2] set to 1 when a wait gave up
+    unsigned char* block[kShMaxWorld];       // every rank's exchange block, own included
+};
+
+constexpr int kShInlineRows = 128;    // up to here one launch both sums the per-CTA partials and applies the solve
+// launches per call of launch_sh_analysis (analysis + reduce/solve)
+inline int sh_analysis_launches(int rows, bool partitioned) { return partitioned || rows > kShInlineRows ? 3 : 2; }
+// eu: {eta, U} per cell; only the first n_own cells enter the fit. Leaves b and s = g * factor * (Ginv b) in `w`.
+// x != nullptr: partitioned run, b is summed over all ranks.
+void launch_sh_analysis(const ShTables& t, ShWork w, const double2* eu, int n_own, double g, const ShExchange* x, cudaStream_t stream);
 // U of the first n_cells cells (own + halo)
 void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_cells, cudaStream_t stream);
 

@@ -215,9 +215,13 @@ int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float
  * to forcing_potential, C_lm/S_lm being the least-squares (degrees 0..l_max) coefficients of eta at the start of
  * the step. factor[l] = globals->shell_factor_beta[l] (= 1 - beta_l, boundaryConditions.cpp:373) for the LID_*
  * surfaces, globals->loading_factor[l] for FREE_LOADING; 4-pi normalised harmonics with the Condon-Shortley phase
- * (src/legendre.f95). On the device: a dense matrix-vector product per direction (analysis, synthesis). Call it
- * after odis_create, before or after odis_set_state; `mesh` is the mesh the solver was created from. */
-int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mesh, int32_t l_max, const double* factor /*[l_max+1]*/);
+ * (src/legendre.f95). On the device: a dense matrix-vector product per direction (analysis, synthesis) —
+ * stored_basis = 1: the basis matrix lives in HBM and is streamed twice per step (the reference's dgemv on
+ * sh_matrix_fort); stored_basis = 0 (recommended): matrix-free, the basis values of a cell are rebuilt from its
+ * latitude / longitude by recurrence inside both kernels, which moves 32 B per cell instead of 8 (l_max+1)^2.
+ * Call it after odis_create, before or after odis_set_state; `mesh` is the mesh the solver was created from. */
+int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mesh, int32_t l_max, const double* factor /*[l_max+1]*/,
+                             int32_t stored_basis);
 /* Least-squares coefficients of the eta the last potential was built from: [(l_max+1)^2], degree-major, per degree
  * m = 0, then (cos, sin) for m = 1..l. */
 int odis_get_sh_coefficients(odis_solver* s, double* out);

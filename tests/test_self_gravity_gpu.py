@@ -36,10 +36,11 @@ def setup(odis, level, l_max, seed=11):
     return mesh, pos, prm, factor, state, s, o, Y
 
 
+@pytest.mark.parametrize("stored", [False, True])           # matrix-free (default) and stored-basis GEMV kernels
 @pytest.mark.parametrize("level,l_max", [(4, 2), (5, 2), (5, 8), (6, 4), (5, 12)])     # l_max 12: 169 rows, the separate solve launch
-def test_time_steps_match_oracle(odis, level, l_max):
+def test_time_steps_match_oracle(odis, level, l_max, stored):
     mesh, pos, prm, factor, state, s, o, Y = setup(odis, level, l_max)
-    s.enable_self_gravity(l_max, factor)
+    s.enable_self_gravity(l_max, factor, stored_basis=stored)
     s.set_state(*state, iter=5)
     o.set_state(*state, iter=5)
     # potential of the pending step = tide + g * sum factor_l c_lm Y_lm of the eta just loaded
@@ -60,7 +61,8 @@ def test_time_steps_match_oracle(odis, level, l_max):
     assert rel_err(tide_only.field(odis.FIELD_ETA), o.field(1)) > 1e-6
 
 
-def test_band_limited_eta_is_recovered_on_device(odis):
+@pytest.mark.parametrize("stored", [False, True])
+def test_band_limited_eta_is_recovered_on_device(odis, stored):
     """Size-independent property at a larger grid (163,842 cells): eta synthesised from known coefficients ->
     the device analysis returns them, and the potential gets exactly g * factor_l * c_lm Y_lm."""
     l_max = 6
@@ -71,7 +73,7 @@ def test_band_limited_eta_is_recovered_on_device(odis):
                shell_thickness=0.0, semimajor_axis=0.0, potential=16, friction=0, surface=0, init_load=0, reorder=1)
     s = odis.Solver(mesh, prm)
     factor = np.linspace(1.0, 0.2, l_max + 1)
-    s.enable_self_gravity(l_max, factor)
+    s.enable_self_gravity(l_max, factor, stored_basis=stored)
     Y = odis.sh_basis(pos, l_max)
     rng = np.random.default_rng(2)
     c = rng.uniform(-1, 1, Y.shape[0])
@@ -83,6 +85,25 @@ def test_band_limited_eta_is_recovered_on_device(odis):
     assert np.abs(u - ref).max() <= 1e-11 * np.abs(ref).max()
 
 
+def test_high_degree_matrix_free(odis):
+    """l_max = 30 (961 rows, the dynamic shared-memory path) on a 40,962-cell grid: band-limited recovery."""
+    l_max = 30
+    pos, fr, cen = odis.generate_grid(7)
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, 1.0e6)
+    prm = dict(g=1.3, h=1.0e3, alpha=1e-6, dt=5.0, radius=1.0e6, omega=2e-5, love_reduct=1.0, ecc=0.0, obl=0.0,
+               shell_thickness=0.0, semimajor_axis=0.0, potential=16, friction=0, surface=0, init_load=0, reorder=1)
+    s = odis.Solver(mesh, prm)
+    factor = 1.0 / (1.0 + np.arange(l_max + 1))
+    s.enable_self_gravity(l_max, factor)
+    Y = odis.sh_basis(pos, l_max)
+    c = np.random.default_rng(4).uniform(-1, 1, Y.shape[0])
+    s.set_state(eta=Y.T @ c)
+    assert np.abs(s.sh_coefficients() - c).max() <= 1e-10
+    f = factor[so.row_degree(l_max)].copy(); f[:4] = 0.0
+    ref = prm["g"] * (Y.T @ (f * c))
+    assert np.abs(s.field(odis.FIELD_POTENTIAL) - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
 def test_enable_errors(odis):
     pos, fr, cen = odis.generate_grid(3)
     mesh = odis.Mesh.from_arrays(pos, fr, cen, 1.0e6)
@@ -92,7 +113,7 @@ def test_enable_errors(odis):
     with pytest.raises(odis.OdisError):
         s.enable_self_gravity(1, [0.0, 0.0])
     with pytest.raises(odis.OdisError):
-        s.sh_coefficients() if hasattr(s, "sh_rows") else s.enable_self_gravity(40, np.zeros(41))
+        s.enable_self_gravity(40, np.zeros(41))
     s.enable_self_gravity(2, [0.0, 0.0, 0.5])
     with pytest.raises(odis.OdisError):
         s.enable_self_gravity(2, [0.0, 0.0, 0.5])               # already on
