@@ -40,6 +40,17 @@ UNIT = "timesteps/s"
 
 # Enceladus subsurface ocean (literature values, not in the reference)
 ENCELADUS = dict(radius=252.1e3, shell=23e3, h=38e3, g=0.113, omega=5.307e-5, ecc=0.0047, alpha=1e-7, love_reduct=0.9)
+# Shell pressure coefficients beta_l, l = 0..8, for a 23 km shell: column 23 of the reference's
+# input_files/LOVE_SHELL_COEFFS/ENCELADUS/beta_hs_1km_to_50km_lmax30.txt (row l; the reference reads one column of it as
+# input_files/beta.txt, src/boundaryConditions.cpp:139-158). The term applies factor_l = 1 - beta_l (:373).
+BETA_23KM = [0.0, 0.0, 2.970754525850653494e+01, 3.846475509963270412e+01, 4.902765616416872518e+01, 6.693284467155693562e+01,
+             9.640980297755693584e+01, 1.414891137087704465e+02, 2.060167851185478298e+02]
+
+
+def shell_factor(l_max: int) -> np.ndarray:
+    f = 1.0 - np.array(BETA_23KM[:l_max + 1])
+    f[:2] = 0.0                                   # degrees 0, 1 are never applied
+    return f
 
 
 def workload_params(mesh, member: int = 0, n_members: int = 1) -> dict:
@@ -116,18 +127,23 @@ def ncu_traffic_per_launch() -> float | None:
         return None
 
 
-def cpu_baseline_port(mesh, prm: dict, budget_s: float = 15.0) -> dict:
+def cpu_baseline_port(mesh, prm: dict, budget_s: float = 15.0, sh_degree: int = 0) -> dict:
     """The oracle's plain-C restatement of the reference loop (bit-identical to the reference solver, see
     tests/test_oracle_pinned.py) timed on one host core on a bounded sample of the same workload."""
     from oracle.lte_oracle import LteOracle
     keys = ("g", "h", "alpha", "dt", "radius", "omega", "love_reduct", "ecc", "obl", "shell_thickness", "potential", "friction", "surface", "init_load")
     o = LteOracle(mesh.tables, {k: prm[k] for k in keys})
+    if sh_degree >= 2:
+        from oracle import sh_oracle
+        Y = sh_oracle.basis(mesh.tables["node_pos_sph"], sh_degree)
+        o.set_self_gravity(Y, sh_oracle.apply_operator(Y, shell_factor(sh_degree)))
     o.set_state()
     t0 = time.perf_counter(); o.step(3); probe = (time.perf_counter() - t0) / 3
     n = int(max(5, min(2000, budget_s / max(probe, 1e-9))))
     t0 = time.perf_counter(); o.step(n); el = time.perf_counter() - t0
     return {"value": n / el, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n} LTE steps of the same {mesh.n_cells}-cell workload, oracle/lte_oracle.c (gcc -O2), single thread"}
+            "sample": f"{n} LTE steps of the same {mesh.n_cells}-cell workload"
+                      + (f" (self-gravity term to degree {sh_degree} included)" if sh_degree >= 2 else "") + ", oracle/lte_oracle.c (gcc -O2), single thread"}
 
 
 def run_ours(args) -> None:
@@ -178,6 +194,9 @@ def run_ours(args) -> None:
         dist.all_gather_object(blobs, solver.halo_blob())
         solver.halo_connect(blobs)
         dist.barrier()
+    L = args.sh_degree
+    if L >= 2:                                      # self-gravity / shell-pressure term (BASELINE config 3), matrix-free kernels
+        solver.enable_self_gravity(L, shell_factor(L))
     N, F = mesh.n_cells, mesh.n_edges
     S, K, W = args.substeps, args.steps, max(args.warmup, 3)
     dev_bytes, alg_bytes = solver.footprint()
@@ -194,14 +213,16 @@ def run_ours(args) -> None:
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     launches = solver.launches - launches0
+    if not math.isfinite(solver.dissipation_avg()):
+        raise SystemExit("bench.py: the run blew up (non-finite dissipation); the timing would be meaningless")
     barrier()
     ms = max_over_ranks(ms)
     value = K * S / (ms * 1e-3)                  # all ranks advance the same K*S steps of the one global grid
 
     # ---- per-kernel timing for the roofline (live, CUDA events around every launch) --------------
-    edge_ms, cell_ms = solver.step_profiled(min(K * S, 400))
     nprof = min(K * S, 400)
-    edge_us, cell_us = edge_ms / nprof * 1e3, cell_ms / nprof * 1e3
+    edge_ms, cell_ms, sh_ms = solver.step_profiled_sh(nprof)
+    edge_us, cell_us, sh_us = edge_ms / nprof * 1e3, cell_ms / nprof * 1e3, sh_ms / nprof * 1e3
     peak, peak_src = measured_peak()
     part = solver.partition()
     edge_alg = 200 * part["own_edges"]          # per-edge algorithmic bytes x edges per launch (this rank's)
@@ -211,6 +232,8 @@ def run_ours(args) -> None:
                 "algorithmic_bytes_per_launch": edge_alg, "avg_launch_us": round(edge_us, 2),
                 "cell_step_kernel": {"algorithmic_bytes_per_launch": 128 * part["own_cells"], "avg_launch_us": round(cell_us, 2),
                                      "achieved": round(128 * part["own_cells"] / (cell_us * 1e-6) / 1e9, 1)},
+                "self_gravity_kernels": {"avg_us_per_step": round(sh_us, 2), "launches_per_step": 3 if L >= 2 else 0, "bound": "fp64 pipe (matrix-free: "
+                                         "the harmonic basis is rebuilt per cell by recurrence instead of streaming 8*(l_max+1)^2 B per cell)"},
                 "whole_step": {"algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes * value / 1e9, 1),
                                "frac": round(alg_bytes * value / 1e9 / peak, 4), "frac_of_8TBs_nominal": round(alg_bytes * value / 8e12, 4),
                                "note": "per GPU: this rank's share of the grid; for N>1 the halo exchange is part of the two kernels"}}
@@ -249,12 +272,28 @@ def run_ours(args) -> None:
     e2e = {"value": round(Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * (4 * F + 4 * N),
            "d2h_bytes_per_step": 8 * (F + N + 1), "intervals_timed": Ke}
 
+    variants = None
+    if world == 1 and not args.no_variants:
+        variants = {}
+        for name, deg in (("no_self_gravity", 0), ("self_gravity_degree_8", 8)):
+            if deg == L:
+                continue
+            alt = odis.Solver(mesh, prm, device=local_rank)
+            if deg >= 2:
+                alt.enable_self_gravity(deg, shell_factor(deg))
+            alt.step(2 * S)
+            n = max(S, min(K * S, 1000))
+            variants[name] = {"timesteps_per_s": round(n / (alt.step_timed(n) * 1e-3), 1)}
+            alt.close()
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (icosahedral-bisection grid generated in the reference's grid_lN.txt conventions; zero initial state, tidal forcing)",
                 "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE, 23 km shell), ECC tide, linear drag, {N} cells / {F} edges "
-                                       f"(reference file level {args.level} = BASELINE 'L{args.level - 1}'); SH self-gravity term is dead code at reference HEAD and not run",
+                                       f"(reference file level {args.level} = BASELINE 'L{args.level - 1}'); "
+                                       + (f"self-gravity / shell-pressure term by spherical harmonics to degree {L} (least-squares analysis + synthesis every step; "
+                                          f"factors 1 - beta_l of the reference's 23 km Enceladus table)" if L >= 2 else "no self-gravity term"),
+                           "sh_degree": L,
                            "cells": N, "edges": F, "lte_steps_per_bench_step": S, "dt_s": prm["dt"],
                            "cache": f"working set {dev_bytes / 1e6:.0f} MB device, {alg_bytes / 1e6:.0f} MB streamed per LTE step > 126 MB L2 (no flush needed)",
                            "parallelism": "1 GPU" if world == 1 else
@@ -263,8 +302,10 @@ def run_ours(args) -> None:
                            f"(rank 0: {part['own_cells']} own + {part['ghost_cells']} ghost cells, {part['n_peers']} neighbours)"},
                 "cell_updates_per_s": round(value * N, 1), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}
+        if variants:
+            line["variants"] = variants
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_port(mesh, prm)
+            line["cpu_baseline"] = cpu_baseline_port(mesh, prm, sh_degree=L)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -296,8 +337,9 @@ def run_reference(args) -> None:
         binary, cores = reference_binary(level), 1
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE), ECC tide, linear drag, {N} cells / {F} edges", "cells": N, "edges": F,
-                       "lte_steps_per_bench_step": S}}
+            "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE), ECC tide, linear drag, {N} cells / {F} edges; the reference's "
+                                   "self-gravity term is commented out at HEAD (src/spatialOperators.cpp:387-462), so its loop runs without it",
+                       "cells": N, "edges": F, "lte_steps_per_bench_step": S}}
     if binary is not None:
         d = tempfile.mkdtemp(prefix="odis_ref_bench_")
         try:
@@ -350,6 +392,9 @@ def main() -> None:
     ap.add_argument("--substeps", type=int, default=100, help="LTE time steps per bench step (one output interval)")
     ap.add_argument("--ref-substeps", type=int, default=2, help="LTE time steps per bench step for --impl reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra device-resident timings with other --sh-degree values")
+    ap.add_argument("--sh-degree", type=int, default=2, help="self-gravity term by spherical harmonics to this degree (the shipped input.in's "
+                    "'sh degree' is 2); 0 = off, as at reference HEAD where the term is commented out")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -42,7 +42,7 @@ class PartitionPlan(C.Structure):
 
 
 class RunOptions(C.Structure):
-    _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("reserved", c_i32), ("max_steps", c_i64)]
+    _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("self_gravity", c_i32), ("max_steps", c_i64)]
 
 
 class RunResult(C.Structure):

@@ -272,10 +272,11 @@ class H5Writer:
             pass
 
 
-def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False, max_steps: int = 0) -> dict:
+def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False, max_steps: int = 0, self_gravity: int = 0) -> dict:
     """`./ODIS` in run_dir: main -> solveODIS -> ab3Explicit (src/main.cpp:46-68), writing DATA/ and
-    InitialConditions/ like the reference. Returns the run summary."""
-    opt = _lib.RunOptions(device, int(reorder), int(echo), 0, max_steps)
+    InitialConditions/ like the reference. Returns the run summary. self_gravity: 0 as reference HEAD; 1 the
+    spherical-harmonic self-gravity / shell-pressure term with input.in's "sh degree" (2: stored-basis kernels)."""
+    opt = _lib.RunOptions(device, int(reorder), int(echo), int(self_gravity), max_steps)
     res = _lib.RunResult()
     check(_lib.load().odis_run(os.fsencode(run_dir), C.byref(opt), C.byref(res)))
     return {n: getattr(res, n) for n, _ in _lib.RunResult._fields_ if n != "reserved"}

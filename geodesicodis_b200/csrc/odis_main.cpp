@@ -15,8 +15,9 @@ int main(int argc, char** argv) {
         if (!std::strcmp(argv[i], "--device") && i + 1 < argc) opt.device = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--max-steps") && i + 1 < argc) opt.max_steps = std::atoll(argv[++i]);
         else if (!std::strcmp(argv[i], "--quiet")) opt.echo = 0;
+        else if (!std::strcmp(argv[i], "--self-gravity")) opt.self_gravity = 1;   // pressureGradientSH, off at reference HEAD
         else if (!std::strcmp(argv[i], "--dir") && i + 1 < argc) dir = argv[++i];
-        else { std::fprintf(stderr, "usage: ODIS [--dir RUN_DIR] [--device N] [--max-steps K] [--quiet]\n"); return 2; }
+        else { std::fprintf(stderr, "usage: ODIS [--dir RUN_DIR] [--device N] [--max-steps K] [--quiet] [--self-gravity]\n"); return 2; }
     }
     odis_run_result res{};
     const int rc = odis_run(dir, &opt, &res);

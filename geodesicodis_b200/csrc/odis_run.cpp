@@ -252,6 +252,17 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     odis_solver* s = nullptr;
     int rc = odis_create(&mv, &p, opt.device, &s);
     if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+    if (opt.self_gravity) {
+        // pressureGradientSH (spatialOperators.cpp:387-462), dead code at reference HEAD: opt-in only
+        const int l_max = cfg.get_int("sh degree");
+        const std::vector<double>* factor = cfg.surface_type == odis::FREE_LOADING ? &cfg.loading_factor
+                                            : (cfg.surface_type == odis::LID_LOVE || cfg.surface_type == odis::LID_MEMBR) ? &cfg.shell_factor_beta : nullptr;
+        if (!factor || (int)factor->size() < l_max + 1)
+            return terminate(ODIS_ERR_CONFIG, "self-gravity needs a FREE_LOADING or LID_* surface with its per-degree factors (boundaryConditions.cpp)");
+        rc = odis_enable_self_gravity(s, &mv, l_max, factor->data(), opt.self_gravity == 2 ? 1 : 0);
+        if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+        log.out("self-gravity / shell pressure term: spherical harmonics to degree " + std::to_string(l_max));
+    }
 
     std::vector<double> v((size_t)F, 0.0), eta((size_t)N, 0.0), dv((size_t)F * 3, 0.0), de((size_t)N * 3, 0.0);
     if (cfg.initial_condition == odis::INIT_LOAD) {                           // initialConditions.cpp:19-144

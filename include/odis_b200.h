@@ -298,7 +298,8 @@ typedef struct odis_run_options {
     int32_t device;       /* CUDA device ordinal */
     int32_t reorder;      /* as odis_params.reorder (default 1 when options == NULL) */
     int32_t echo;         /* 1: copy OUTPUT.txt lines to stdout */
-    int32_t reserved;
+    int32_t self_gravity; /* 0: as reference HEAD (term commented out). 1: odis_enable_self_gravity with input.in's "sh degree" and
+                           * the surface type's per-degree factors (matrix-free kernels); 2: the same with the stored basis */
     int64_t max_steps;    /* > 0: stop after this many steps even if the loop bound is larger */
 } odis_run_options;
 
