@@ -99,6 +99,8 @@ SIGNATURES = {
     "odis_destroy": (None, [C.c_void_p]),
     "odis_ensemble_create": (C.c_int, [P(MeshView), C.c_void_p, c_i32, c_i32, P(C.c_void_p)]),
     "odis_ensemble_set_state": (C.c_int, [C.c_void_p, c_i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64]),
+    "odis_ensemble_enable_self_gravity": (C.c_int, [C.c_void_p, P(MeshView), c_i32, C.c_void_p]),
+    "odis_ensemble_get_sh_coefficients": (C.c_int, [C.c_void_p, c_i32, C.c_void_p]),
     "odis_ensemble_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_ensemble_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
     "odis_ensemble_get_field": (C.c_int, [C.c_void_p, c_i32, c_i32, C.c_void_p]),

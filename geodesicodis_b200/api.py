@@ -446,6 +446,20 @@ class Ensemble:
         check(_lib.load().odis_ensemble_set_state(self._h, member, k[0][1], k[1][1], k[2][1], k[3][1], iter))
         self._iter0 = iter
 
+    def enable_self_gravity(self, l_max: int, factor) -> None:
+        """Self-gravity / shell-pressure term for every member (see Solver.enable_self_gravity); l_max <= 10. Analysis and
+        synthesis of all members run as FP64 tensor-core GEMMs."""
+        f = np.ascontiguousarray(factor, dtype=np.float64)
+        if f.size != l_max + 1:
+            raise ValueError("factor must have l_max + 1 entries")
+        check(_lib.load().odis_ensemble_enable_self_gravity(self._h, C.byref(self.mesh.view), l_max, f.ctypes.data))
+        self.sh_rows = (l_max + 1) ** 2
+
+    def sh_coefficients(self, member: int) -> np.ndarray:
+        out = np.empty(self.sh_rows, dtype=np.float64)
+        check(_lib.load().odis_ensemble_get_sh_coefficients(self._h, member, out.ctypes.data))
+        return out
+
     def step(self, nsteps: int = 1) -> None:
         check(_lib.load().odis_ensemble_step(self._h, nsteps))
 

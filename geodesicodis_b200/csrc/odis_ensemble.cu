@@ -24,6 +24,8 @@
 #include "odis_error.h"
 #include "odis_kernels.cuh"
 #include "odis_reorder.h"
+#include "odis_sh.cuh"
+#include "odis_sh.h"
 #include "odis_sphere.h"
 
 using odis::fail;
@@ -432,6 +434,11 @@ struct odis_ensemble {
     bool diag_current = false;
     int64_t launches = 0;
     size_t device_bytes = 0;
+    // spherical-harmonic self-gravity term (odis_ensemble_enable_self_gravity): batched FP64 tensor-core GEMMs
+    bool sh_on = false;
+    odis::EnsShTables sh{};
+    odis::EnsShWork shw{};
+    std::vector<double> sh_ginv_host;
 };
 
 namespace {
@@ -748,8 +755,70 @@ int odis_ensemble_set_state(odis_ensemble* s, int32_t member, const double* v, c
         s->tab, s->d_v[0], s->d_eu[0], s->d_eu[0], s->d_he[0], s->d_he[1], s->d_he[2], odis::AB3_FULL, step_scalars(s->prm[0].omega, tt),
         odis::CELL_UPDATE_U);
     s->launches++;
+    if (s->sh_on) { odis::launch_ens_self_gravity(s->sh, s->shw, s->d_eu[0], s->stream); s->launches += odis::kEnsShLaunches; }
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    return ODIS_OK;
+}
+
+int odis_ensemble_enable_self_gravity(odis_ensemble* s, const odis_mesh_view* mv, int32_t l_max, const double* factor) {
+    if (!s || !mv || !factor) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (mv->n_cells != s->N) return fail(ODIS_ERR_ARG, "mesh does not match the ensemble");
+    if (s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is already enabled");
+    const int rows = odis::sh_rows(l_max);
+    if (l_max < 2 || rows > odis::kEnsShMaxRows) return fail(ODIS_ERR_ARG, "ensemble self-gravity: sh degree must be in 2..10");
+    if (rows >= s->N) return fail(ODIS_ERR_ARG, "sh degree too high for this grid");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    ODIS_CUDA(odis::sh_configure());
+    const int N = s->N, Ns = s->Ns, Mp = s->Mp;
+    {
+        std::vector<double> Yg((size_t)rows * N);
+        odis::sh_basis(N, mv->node_pos_sph, l_max, (size_t)N, Yg.data());
+        if (odis::sh_normal_inverse(rows, N, (size_t)N, Yg.data(), 0, s->sh_ginv_host) != 0)
+            return fail(ODIS_ERR_ARG, "spherical-harmonic normal matrix is not positive definite");
+    }
+    std::vector<int> perm((size_t)N);
+    ODIS_CUDA(cudaMemcpy(perm.data(), s->d_cell_perm, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<double> pos((size_t)N * 2), Y((size_t)rows * Ns, 0.0), fac((size_t)rows, 0.0), g((size_t)Mp);
+    for (int i = 0; i < N; i++) {
+        pos[2 * (size_t)i] = mv->node_pos_sph[2 * (size_t)perm[(size_t)i]];
+        pos[2 * (size_t)i + 1] = mv->node_pos_sph[2 * (size_t)perm[(size_t)i] + 1];
+    }
+    odis::sh_basis(N, pos.data(), l_max, (size_t)Ns, Y.data());
+    for (int k = odis::kShSkipRows; k < rows; k++) fac[(size_t)k] = factor[odis::sh_row_degree(k)];
+    for (int m = 0; m < Mp; m++) g[(size_t)m] = s->prm[(size_t)std::min(m, s->M - 1)].g;
+    odis::EnsShTables& t = s->sh;
+    t.rows = rows; t.rows_pad = (rows + 7) / 8 * 8; t.stride = Ns; t.n_cells = N; t.Mp = Mp;
+    const int blocks = odis::ens_sh_analysis_blocks(N, Mp);
+    int rc;
+    if ((rc = ens_upload(s, &t.Y, Y)) || (rc = ens_upload(s, &t.Ginv, s->sh_ginv_host)) || (rc = ens_upload(s, &t.factor, fac)) ||
+        (rc = ens_upload(s, &t.g, g)) || (rc = ens_alloc(s, &s->shw.partial, (size_t)blocks * t.rows_pad * Mp)) ||
+        (rc = ens_alloc(s, &s->shw.b, (size_t)t.rows_pad * Mp)) || (rc = ens_alloc(s, &s->shw.s, (size_t)t.rows_pad * Mp)))
+        return rc;
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    s->sh_on = true;
+    // the pending step's potential gets the term of the current eta
+    odis::launch_ens_self_gravity(s->sh, s->shw, s->d_eu[s->ecur], s->stream);
+    s->launches += odis::kEnsShLaunches;
+    ODIS_CUDA(cudaGetLastError());
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    return ODIS_OK;
+}
+
+int odis_ensemble_get_sh_coefficients(odis_ensemble* s, int32_t member, double* out) {
+    if (!s || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (!s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is not enabled");
+    if (member < 0 || member >= s->M) return fail(ODIS_ERR_ARG, "member out of range");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const size_t R = (size_t)s->sh.rows;
+    std::vector<double> b((size_t)s->sh.rows_pad * s->Mp);
+    ODIS_CUDA(cudaMemcpyAsync(b.data(), s->shw.b, b.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t j = 0; j < R; j++) {
+        double acc = 0.0;
+        for (size_t k = 0; k < R; k++) acc += s->sh_ginv_host[j * R + k] * b[k * (size_t)s->Mp + (size_t)member];
+        out[j] = acc;
+    }
     return ODIS_OK;
 }
 
@@ -773,6 +842,7 @@ int odis_ensemble_step(odis_ensemble* s, int32_t nsteps) {
                                                                        odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U);
         ens_rotate_cell_history(s, mode);
         s->ecur = 1 - s->ecur;
+        if (s->sh_on) { odis::launch_ens_self_gravity(s->sh, s->shw, s->d_eu[s->ecur], s->stream); s->launches += odis::kEnsShLaunches; }
         s->cur = 1 - s->cur;
         s->iter++;
         s->last_mode = mode;
@@ -874,7 +944,11 @@ int odis_ensemble_get_info(odis_ensemble* s, int32_t* n_members, int64_t* iter, 
     // per batched step: state M*(40F + 56N) (v r/w 16 + history 24 per edge; {eta,U} r/w 32 + history 24 per cell) and the
     // tables once (edge: ids 40, weights 80, stencil lengths 80, cells 8, grad 16, f 8, d 8, l 8 = 248F; cell: ids 24, lengths 48,
     // area 8, trig 80 = 160N)
-    if (algorithmic_bytes_per_step) *algorithmic_bytes_per_step = (int64_t)s->M * (40LL * s->F + 56LL * s->N) + 248LL * s->F + 160LL * s->N;
+    if (algorithmic_bytes_per_step) {
+        *algorithmic_bytes_per_step = (int64_t)s->M * (40LL * s->F + 56LL * s->N) + 248LL * s->F + 160LL * s->N;
+        // self-gravity: Y streamed twice (shared by the members), {eta,U} read by the analysis, read + written by the synthesis
+        if (s->sh_on) *algorithmic_bytes_per_step += 8LL * (2 * s->sh.rows - 4) * s->N + 40LL * s->M * s->N;
+    }
     return ODIS_OK;
 }
 

@@ -12,6 +12,7 @@ constexpr int kShWarps = kShThreads / 32;
 constexpr int kShRowChunk = 32;
 constexpr int kShMaxRows = 1024;         // l_max <= 31
 constexpr int kShReduceThreads = 1024;
+constexpr int kShSkip = 4;               // rows of degree 0 and 1
 constexpr int kShMaxPartialsPerLane = (kShMaxBlocks + 31) / 32;
 
 __device__ __forceinline__ double warp_sum(double x) {          // butterfly: every lane ends with the same, order-fixed sum
@@ -391,6 +392,165 @@ __global__ void __launch_bounds__(kShThreads) sh_synthesis_mf_kernel(ShTables t,
     if (i < n_cells) eu[i].y = u0 + acc;
 }
 
+// ---- ensembles: FP64 tensor-core GEMMs ------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int kEnsKC = 32;            // cells per K chunk of the analysis / cells per tile of the synthesis
+constexpr int kEnsLd = 36;            // shared-memory row stride (doubles): conflict-free fragment reads for both operands
+constexpr int kEnsMB = 32;            // members per CTA (4 n-tiles)
+constexpr int kEnsMaxMT = kEnsShMaxRows / 8;
+
+// B = Y . Eta for one block of 32 members over this CTA's share of the cells. Warp w owns n-tile w % 4 (8 members) and the
+// m-tiles (8 harmonic rows each) w / 4, w / 4 + 2, ...: accumulators stay in registers across the whole K range.
+__global__ void __launch_bounds__(kShThreads) ens_sh_analysis_kernel(EnsShTables t, EnsShWork w, const double2* __restrict__ eu) {
+    __shared__ double Ys[kEnsShMaxRows * kEnsLd];      // [rows_pad][kEnsLd]: Y[row][cell chunk]
+    __shared__ double Es[kEnsKC * kEnsLd];             // [cell][member]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * kEnsMB;
+    const int MT = t.rows_pad / 8;
+    const int nt = warp & 3, mt0 = warp >> 2;
+    double acc[kEnsMaxMT / 2][2];
+#pragma unroll
+    for (int j = 0; j < kEnsMaxMT / 2; j++) acc[j][0] = acc[j][1] = 0.0;
+    // this CTA's chunks of 32 cells: consecutive, dealt out evenly
+    const int chunks = (t.n_cells + kEnsKC - 1) / kEnsKC;
+    const int per = chunks / gridDim.x, extra = chunks % gridDim.x;
+    const int c0 = blockIdx.x * per + min((int)blockIdx.x, extra), c1 = c0 + per + ((int)blockIdx.x < extra ? 1 : 0);
+    // software pipeline: the next chunk's values travel into registers while the tensor cores work on the current one
+    constexpr int kYPer = kEnsShMaxRows * kEnsKC / kShThreads, kEPer = kEnsKC * kEnsMB / kShThreads;
+    double yreg[kYPer], ereg[kEPer];
+    auto fetch = [&](int ch) {
+        const int cell0 = ch * kEnsKC;
+#pragma unroll
+        for (int u = 0; u < kYPer; u++) {
+            const int q = tid + u * kShThreads, r = q / kEnsKC, c = q % kEnsKC;
+            yreg[u] = (ch < c1 && r < t.rows && cell0 + c < t.n_cells) ? __ldcs(t.Y + (size_t)r * t.stride + cell0 + c) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kEPer; u++) {
+            const int q = tid + u * kShThreads, c = q / kEnsMB, m = q % kEnsMB;
+            ereg[u] = (ch < c1 && cell0 + c < t.n_cells && m0 + m < t.Mp) ? eu[(size_t)(cell0 + c) * t.Mp + m0 + m].x : 0.0;
+        }
+    };
+    fetch(c0);
+    for (int ch = c0; ch < c1; ch++) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kYPer; u++) {
+            const int q = tid + u * kShThreads, r = q / kEnsKC, c = q % kEnsKC;
+            if (r < t.rows_pad) Ys[r * kEnsLd + c] = yreg[u];
+        }
+#pragma unroll
+        for (int u = 0; u < kEPer; u++) {
+            const int q = tid + u * kShThreads;
+            Es[(q / kEnsMB) * kEnsLd + q % kEnsMB] = ereg[u];
+        }
+        __syncthreads();
+        fetch(ch + 1);
+#pragma unroll
+        for (int k = 0; k < kEnsKC; k += 4) {
+            const double bfrag = Es[(k + (lane & 3)) * kEnsLd + nt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int j = 0; j < kEnsMaxMT / 2; j++) {
+                const int mt = mt0 + 2 * j;
+                if (mt < MT) dmma_m8n8k4(acc[j][0], acc[j][1], Ys[(mt * 8 + (lane >> 2)) * kEnsLd + k + (lane & 3)], bfrag);
+            }
+        }
+    }
+    // C fragment: row = lane / 4, columns 2 * (lane % 4) + {0, 1}
+    double* out = w.partial + (size_t)blockIdx.x * t.rows_pad * t.Mp;
+#pragma unroll
+    for (int j = 0; j < kEnsMaxMT / 2; j++) {
+        const int mt = mt0 + 2 * j;
+        if (mt >= MT) continue;
+        const int row = mt * 8 + (lane >> 2), m = m0 + nt * 8 + 2 * (lane & 3);
+        if (m < t.Mp) { out[(size_t)row * t.Mp + m] = acc[j][0]; out[(size_t)row * t.Mp + m + 1] = acc[j][1]; }
+    }
+}
+
+// b[k][m] = sum over the analysis CTAs, CTA order fixed: one warp per (row, member), lanes over the CTAs, then the butterfly
+__global__ void __launch_bounds__(kShThreads) ens_sh_reduce_kernel(EnsShTables t, EnsShWork w) {
+    const int item = blockIdx.x * kShWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= t.rows_pad * t.Mp) return;
+    const size_t step = (size_t)t.rows_pad * t.Mp;
+    constexpr int kPer = (kEnsShMaxBlocks + 31) / 32;
+    double v[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+        const int blk = lane + 32 * q;
+        v[q] = blk < w.n_blocks ? __ldcg(w.partial + (size_t)blk * step + item) : 0.0;
+    }
+    double a = v[0];
+#pragma unroll
+    for (int q = 1; q < kPer; q++) a = a + v[q];
+    a = warp_sum(a);
+    if (lane == 0) w.b[item] = a;
+}
+
+// s[j][m] = g_m factor_j sum_k Ginv[j][k] b[k][m]: a CTA owns 32 rows j x 8 members; its slice of Ginv and of b goes through
+// shared memory so that the inner products run without a global load
+__global__ void __launch_bounds__(kShThreads) ens_sh_solve_kernel(EnsShTables t, EnsShWork w) {
+    __shared__ double Gs[32][kEnsShMaxRows + 1];
+    __shared__ double bsh[kEnsShMaxRows][8];
+    const int tid = threadIdx.x, j0 = blockIdx.y * 32, mb = blockIdx.x * 8;
+    for (int q = tid; q < 32 * t.rows; q += kShThreads) {
+        const int jj = q / t.rows, k = q % t.rows;
+        Gs[jj][k] = j0 + jj < t.rows ? t.Ginv[(size_t)(j0 + jj) * t.rows + k] : 0.0;
+    }
+    for (int q = tid; q < t.rows * 8; q += kShThreads) bsh[q >> 3][q & 7] = w.b[(size_t)(q >> 3) * t.Mp + mb + (q & 7)];
+    __syncthreads();
+    const int jj = tid >> 3, m = tid & 7, j = j0 + jj;
+    if (j >= t.rows_pad) return;
+    const double f = j < t.rows ? t.factor[j] : 0.0;
+    double a = 0.0;
+    for (int k = 0; k < t.rows; k++) a = a + Gs[jj][k] * bsh[k][m];
+    w.s[(size_t)j * t.Mp + mb + m] = (t.g[mb + m] * f) * a;
+}
+
+// U += Ysel^T . S: a CTA walks tiles of 32 cells for one block of 32 members; warp w owns the cell m-tile w % 4 (8 cells) and the
+// member n-tiles w / 4, w / 4 + 2
+__global__ void __launch_bounds__(kShThreads) ens_sh_synthesis_kernel(EnsShTables t, EnsShWork w, double2* __restrict__ eu) {
+    extern __shared__ double dyn[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * kEnsMB;
+    const int K = (t.rows - kShSkip + 3) / 4 * 4;      // harmonic rows of degree >= 2, padded to the MMA depth with zeros
+    double* Ss = dyn;                                  // [K][kEnsLd]: S[row - 4][member]
+    double* Ys = dyn + (size_t)K * kEnsLd;             // [K][kEnsLd]: Y[row - 4][cell]
+    for (int q = tid; q < K * kEnsMB; q += kShThreads) {
+        const int r = q / kEnsMB, m = q % kEnsMB;
+        Ss[r * kEnsLd + m] = (r + kShSkip < t.rows && m0 + m < t.Mp) ? w.s[(size_t)(r + kShSkip) * t.Mp + m0 + m] : 0.0;
+    }
+    const int mt = warp & 3, nt0 = warp >> 2;
+    const int tiles = (t.n_cells + kEnsKC - 1) / kEnsKC;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int cell0 = tile * kEnsKC;
+        __syncthreads();
+        for (int q = tid; q < K * kEnsKC; q += kShThreads) {
+            const int r = q / kEnsKC, c = q % kEnsKC;
+            Ys[r * kEnsLd + c] = (r + kShSkip < t.rows && cell0 + c < t.n_cells) ? __ldcs(t.Y + (size_t)(r + kShSkip) * t.stride + cell0 + c) : 0.0;
+        }
+        __syncthreads();
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int k = 0; k < K; k += 4) {
+            const double a = Ys[(k + (lane & 3)) * kEnsLd + mt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma_m8n8k4(acc[j][0], acc[j][1], a, Ss[(k + (lane & 3)) * kEnsLd + (nt0 + 2 * j) * 8 + (lane >> 2)]);
+        }
+        const int cell = cell0 + mt * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int m = m0 + (nt0 + 2 * j) * 8 + 2 * (lane & 3);
+            if (cell < t.n_cells && m < t.Mp) {
+                double2* p = eu + (size_t)cell * t.Mp + m;
+                p[0].y = p[0].y + acc[j][0];
+                p[1].y = p[1].y + acc[j][1];
+            }
+        }
+    }
+}
+
 }  // namespace
 
 static int analysis_grid(int n_cells) {
@@ -421,6 +581,9 @@ cudaError_t sh_configure() {
     sh_recurrence_table(rec);
     if ((e = cudaMemcpyToSymbol(c_rec, rec, sizeof rec)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(sh_analysis_mf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analysis_mf_smem(kShRecStride - 1))) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(ens_sh_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * (size_t)kEnsShMaxRows * kEnsLd * sizeof(double)))) != cudaSuccess)
         return e;
     return cudaFuncSetAttribute(sh_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analysis_smem(kShMaxRows));
 }
@@ -463,6 +626,31 @@ void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_
         return;
     }
     sh_synthesis_kernel<<<(n_cells + kShThreads - 1) / kShThreads, kShThreads, 0, stream>>>(t, w, eu, n_cells);
+}
+
+}  // namespace odis
+
+namespace odis {
+
+int ens_sh_analysis_blocks(int n_cells, int Mp) {
+    const int chunks = (n_cells + 31) / 32, yb = (Mp + 31) / 32;
+    int bx = 296 / yb;                                // two CTAs per SM over both grid dimensions
+    if (bx > kEnsShMaxBlocks) bx = kEnsShMaxBlocks;
+    if (bx > chunks) bx = chunks;
+    return bx < 1 ? 1 : bx;
+}
+
+void launch_ens_self_gravity(const EnsShTables& t, EnsShWork w, double2* eu, cudaStream_t stream) {
+    const int yb = (t.Mp + 31) / 32;
+    w.n_blocks = ens_sh_analysis_blocks(t.n_cells, t.Mp);
+    ens_sh_analysis_kernel<<<dim3((unsigned)w.n_blocks, (unsigned)yb), 256, 0, stream>>>(t, w, eu);
+    ens_sh_reduce_kernel<<<(t.rows_pad * t.Mp + 7) / 8, 256, 0, stream>>>(t, w);
+    ens_sh_solve_kernel<<<dim3((unsigned)(t.Mp / 8), (unsigned)((t.rows_pad + 31) / 32)), 256, 0, stream>>>(t, w);
+    const int tiles = (t.n_cells + 31) / 32;
+    int bx = 592 / yb;
+    if (bx > tiles) bx = tiles;
+    const int K = (t.rows - 4 + 3) / 4 * 4;
+    ens_sh_synthesis_kernel<<<dim3((unsigned)(bx < 1 ? 1 : bx), (unsigned)yb), 256, 2 * (size_t)K * 36 * sizeof(double), stream>>>(t, w, eu);
 }
 
 }  // namespace odis

@@ -72,3 +72,34 @@ void launch_sh_analysis(const ShTables& t, ShWork w, const double2* eu, int n_ow
 void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_cells, cudaStream_t stream);
 
 }  // namespace odis
+
+// ---- ensembles: M members on one grid, state member-innermost ({eta,U}[cell][Mp]) ---------------------------------------
+// The harmonic analysis / synthesis of all members is one FP64 GEMM per direction on the tensor cores
+// (mma.sync.aligned.m8n8k4.f64, DMMA):   B[rows x Mp] = Y[rows x N] . Eta[N x Mp]      (analysis, K = cells)
+//                                        U[N x Mp]  += Ysel^T[N x rows'] . S[rows' x Mp]  (synthesis, K = harmonic rows >= 4)
+// Y is the stored basis (shared by all members). rows <= 128 (degree <= 10).
+namespace odis {
+
+struct EnsShTables {
+    int rows, rows_pad;       // basis rows, rounded up to a multiple of 8
+    int stride;               // cells per row of Y
+    int n_cells, Mp;          // Mp: members padded to a multiple of 8
+    const double* Y;          // [rows][stride]
+    const double* Ginv;       // [rows][rows]
+    const double* factor;     // [rows]
+    const double* g;          // [Mp] member gravity
+};
+struct EnsShWork {
+    double* partial;          // [blocks][rows_pad][Mp]
+    int n_blocks;
+    double* b;                // [rows_pad][Mp]
+    double* s;                // [rows_pad][Mp]
+};
+constexpr int kEnsShMaxRows = 128;
+constexpr int kEnsShMaxBlocks = 448;
+int ens_sh_analysis_blocks(int n_cells, int Mp);
+// four launches: analysis GEMM, reduce over its CTAs, per-member solve, synthesis GEMM
+constexpr int kEnsShLaunches = 4;
+void launch_ens_self_gravity(const EnsShTables& t, EnsShWork w, double2* eu, cudaStream_t stream);
+
+}  // namespace odis

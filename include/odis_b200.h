@@ -260,6 +260,11 @@ int odis_ensemble_create(const odis_mesh_view* mesh, const odis_params* params /
  * members) restarts the step count; call it for the members before stepping. */
 int odis_ensemble_set_state(odis_ensemble* e, int32_t member, const double* v, const double* eta, const double* dvdt /*[F][3]*/,
                             const double* detadt /*[N][3]*/, int64_t iter);
+/* Self-gravity / shell-pressure term for every member (see odis_enable_self_gravity; the members' own g applies, the
+ * per-degree factors are shared). The harmonic analysis and synthesis of all members are one FP64 tensor-core GEMM each
+ * (basis matrix x member-innermost state). l_max <= 10. */
+int odis_ensemble_enable_self_gravity(odis_ensemble* e, const odis_mesh_view* mesh, int32_t l_max, const double* factor /*[l_max+1]*/);
+int odis_ensemble_get_sh_coefficients(odis_ensemble* e, int32_t member, double* out /*[(l_max+1)^2]*/);
 int odis_ensemble_step(odis_ensemble* e, int32_t nsteps);
 int odis_ensemble_step_timed(odis_ensemble* e, int32_t nsteps, float* elapsed_ms_out);
 /* field: ODIS_FIELD_VELOCITY, _ETA, _DVDT, _DETADT or _POTENTIAL of one member. */
