@@ -57,6 +57,12 @@ typedef struct {
     const double* sh_Y;        /* [rows][N] basis */
     const double* sh_T;        /* [rows][rows] factor_l * (Y Y^T)^-1, rows of degree 0 and 1 zero */
     double *sh_b, *sh_s;
+    /* optional nonlinear branch (advection; true): operators handed in as CSR, see oracle_set_nonlinear */
+    int nl_on, V;
+    csr curl, rbf, d2;                  /* operatorCurl VxF, operatorRBFinterp 3NxF, operatorDirectionalSecondDeriv 2FxN */
+    const double *vertex_sinlat, *vertex_area, *vertex_R;   /* [V], [V], [V][3] */
+    const int *vertex_nodes, *face_vertexes;                /* [V][3], [F][2] */
+    double *h_total, *ekin, *vorticity_v, *vorticity_e, *thickness_e, *vel_xyz, *d2v, *flux;
 } oracle_ctx;
 
 static const double pi = 3.1415926535897932384626433832795028841971693993751058;  /* mathRoutines.h:10 */
@@ -335,6 +341,75 @@ static void self_gravity(oracle_ctx* c, double* potential, const double* eta) {
     }
 }
 
+/* calculateMomentumAdvection, momAdvection.cpp:11-268 (live lines only) */
+static void calculateMomentumAdvection(oracle_ctx* c, double* dvdt, const double* vel, const double* thickness_n, double* Ekin) {
+    const oracle_mesh* m = &c->m;
+    const int N = c->N, F = c->F, V = c->V;
+    const double rot_rate = c->p.omega;
+    int i, j;
+    spmv_assign(&c->curl, vel, c->vorticity_v);                                   /* :31 */
+    for (i = 0; i < V; i++) {                                                     /* :39-67 */
+        double f = -2 * rot_rate * c->vertex_sinlat[i];
+        double thickness = 0.0;
+        for (j = 0; j < 3; j++) {
+            const int node_ID = c->vertex_nodes[i * 3 + j];
+            thickness += thickness_n[node_ID] * m->control_volume_surf_area_map[node_ID] * c->vertex_R[i * 3 + j];
+        }
+        thickness *= 1.0 / c->vertex_area[i];                                     /* vertex_area_r, mesh.cpp:1147 */
+        c->vorticity_v[i] = (c->vorticity_v[i] + f) / thickness;
+    }
+    for (i = 0; i < F; i++) {                                                     /* :77-91 */
+        const int v1 = c->face_vertexes[i * 2], v2 = c->face_vertexes[i * 2 + 1];
+        const int n1 = m->face_nodes[i * 2], n2 = m->face_nodes[i * 2 + 1];
+        c->vorticity_e[i] = 0.5 * (c->vorticity_v[v1] + c->vorticity_v[v2]);
+        c->thickness_e[i] = 0.5 * (thickness_n[n1] + thickness_n[n2]);
+    }
+    for (i = 0; i < F; ++i) {                                                     /* :100-142 */
+        int friend_num = 10;
+        const int n1 = m->face_nodes[i * 2], n2 = m->face_nodes[i * 2 + 1];
+        double q_e, F_tang_q = 0.0;
+        if (m->node_friends[n1 * 6 + 5] < 0) friend_num--;
+        if (m->node_friends[n2 * 6 + 5] < 0) friend_num--;
+        q_e = c->vorticity_e[i];
+        for (j = 0; j < friend_num; j++) {
+            const int f_ID = m->face_interp_friends[i * 10 + j];
+            const double q_e2 = c->vorticity_e[f_ID];
+            const double F_e = c->thickness_e[f_ID] * vel[f_ID];
+            const double coeff = m->face_interp_weights[i * 10 + j] * m->face_len[f_ID] * (1.0 / m->face_node_dist[i]);   /* face_node_dist_r, mesh.cpp:624 */
+            F_tang_q += coeff * F_e * (q_e + q_e2) * 0.5;
+        }
+        dvdt[i] -= -F_tang_q;
+    }
+    spmv_assign(&c->rbf, vel, c->vel_xyz);                                        /* interpolateVelocityCartRBF, interpolation.cpp:116 */
+    for (i = 0; i < N; i++)
+        Ekin[i] = 0.5 * (c->vel_xyz[i * 3] * c->vel_xyz[i * 3] + c->vel_xyz[i * 3 + 1] * c->vel_xyz[i * 3 + 1] + c->vel_xyz[i * 3 + 2] * c->vel_xyz[i * 3 + 2]);
+    {                                                                             /* :267: dvdt += -G * Ekin, -G materialised first */
+        int k;
+        for (i = 0; i < F; i++) {
+            double tmp = 0;
+            for (k = c->grad.ptr[i]; k < c->grad.ptr[i + 1]; k++) tmp += (-c->grad.val[k]) * Ekin[c->grad.idx[k]];
+            dvdt[i] += 1.0 * tmp;
+        }
+    }
+}
+
+/* interpolateLSQFlux, interpolation.cpp:311-364 */
+static void interpolateLSQFlux(oracle_ctx* c, double* flux, const double* edge_vel, const double* node_scalar) {
+    const oracle_mesh* m = &c->m;
+    const double fact = 1. / 12.0, beta = 1.0;
+    int i;
+    spmv_assign(&c->d2, node_scalar, c->d2v);
+    for (i = 0; i < c->F; ++i) {
+        const double dx = m->face_node_dist[i];
+        const double dx2 = dx * dx * fact;
+        const double vel = edge_vel[i];
+        const int inner_ID = m->face_nodes[i * 2], outer_ID = m->face_nodes[i * 2 + 1];
+        const double d2_outer = c->d2v[2 * i + 1], d2_inner = c->d2v[2 * i];
+        flux[i] = vel * 0.5 * (node_scalar[inner_ID] + node_scalar[outer_ID]) - dx2 * (d2_outer + d2_inner) * vel +
+                  dx2 * beta * fabs(vel) * (d2_outer - d2_inner);
+    }
+}
+
 /* ---------------------------------------------------------------- public ---- */
 oracle_ctx* oracle_create(const oracle_mesh* mesh, const oracle_params* params) {
     oracle_ctx* c = (oracle_ctx*)calloc(1, sizeof(oracle_ctx));
@@ -362,6 +437,34 @@ void oracle_destroy(oracle_ctx* c) {
     free(c);
 }
 
+/* Nonlinear branch on: the three operators as CSR (row pointers, ascending columns, values: exactly what the reference built,
+ * e.g. from oracle/_ref's table dump) and the vertex tables; all arrays stay owned by the caller. Call before oracle_set_state. */
+static void csr_borrow_copy(csr* A, int nr, int nc, const int* ptr, const int* idx, const double* val) {
+    const size_t nnz = (size_t)ptr[nr];
+    A->nr = nr; A->nc = nc;
+    A->ptr = (int*)malloc(((size_t)nr + 1) * sizeof(int)); memcpy(A->ptr, ptr, ((size_t)nr + 1) * sizeof(int));
+    A->idx = (int*)malloc((nnz + 1) * sizeof(int)); memcpy(A->idx, idx, nnz * sizeof(int));
+    A->val = (double*)malloc((nnz + 1) * sizeof(double)); memcpy(A->val, val, nnz * sizeof(double));
+}
+void oracle_set_nonlinear(oracle_ctx* c, int V, const int* curl_ptr, const int* curl_idx, const double* curl_val, const int* rbf_ptr,
+                          const int* rbf_idx, const double* rbf_val, const int* d2_ptr, const int* d2_idx, const double* d2_val,
+                          const double* vertex_sinlat, const double* vertex_area, const double* vertex_R, const int* vertex_nodes,
+                          const int* face_vertexes) {
+    const size_t N = (size_t)c->N, F = (size_t)c->F;
+    size_t i;
+    c->V = V;
+    csr_borrow_copy(&c->curl, V, c->F, curl_ptr, curl_idx, curl_val);
+    csr_borrow_copy(&c->rbf, 3 * c->N, c->F, rbf_ptr, rbf_idx, rbf_val);
+    csr_borrow_copy(&c->d2, 2 * c->F, c->N, d2_ptr, d2_idx, d2_val);
+    c->vertex_sinlat = vertex_sinlat; c->vertex_area = vertex_area; c->vertex_R = vertex_R;
+    c->vertex_nodes = vertex_nodes; c->face_vertexes = face_vertexes;
+    c->h_total = (double*)calloc(N, 8); c->ekin = (double*)calloc(N, 8); c->vorticity_v = (double*)calloc((size_t)V, 8);
+    c->vorticity_e = (double*)calloc(F, 8); c->thickness_e = (double*)calloc(F, 8); c->vel_xyz = (double*)calloc(3 * N, 8);
+    c->d2v = (double*)calloc(2 * F, 8); c->flux = (double*)calloc(F, 8);
+    for (i = 0; i < N; i++) c->h_total[i] = c->p.h + c->p_t0[i];
+    c->nl_on = 1;
+}
+
 /* Y, T stay owned by the caller */
 void oracle_set_sh(oracle_ctx* c, int rows, const double* Y, const double* T) {
     free(c->sh_b); free(c->sh_s);
@@ -378,6 +481,7 @@ void oracle_set_state(oracle_ctx* c, const double* v, const double* eta, const d
     if (dvdt) memcpy(c->dv_dt, dvdt, F * 24); else memset(c->dv_dt, 0, F * 24);
     if (detadt) memcpy(c->dp_dt, detadt, N * 24); else memset(c->dp_dt, 0, N * 24);
     c->iter = iter;
+    if (c->nl_on) { size_t i; for (i = 0; i < N; i++) c->h_total[i] = c->p.h + c->p_t0[i]; }   /* timeIntegrator.cpp:203 */
     interpolateVelocity(c, c->v_avg, c->v_t0);
     updateEnergy(c, &c->e_diss, c->energy_diss, c->v_avg, c->m.face_area);
 }
@@ -392,7 +496,8 @@ void oracle_step(oracle_ctx* c, int nsteps, double* diss_series) {
         const double current_time = dt * c->iter;                       /* :187,277 */
         /* updateMomentum, updateMomentum.cpp:42: dvdt = -g*(1-GAMMA*IMPLICIT)*G*eta + C*v */
         spmv_scaled_assign(&c->grad, -g * (1 - 0.5 * 0), c->p_t0, c->dv_dt_t0);
-        spmv_add(&c->cor, c->v_t0, c->dv_dt_t0);
+        if (c->nl_on) calculateMomentumAdvection(c, c->dv_dt_t0, c->v_t0, c->h_total, c->ekin);   /* updateMomentum.cpp:37-38 */
+        else spmv_add(&c->cor, c->v_t0, c->dv_dt_t0);
         for (i = 0; i < F; ++i) c->dv_dt[i * 3] = c->dv_dt_t0[i];       /* :215 */
         forcing(c, c->forcing_potential, current_time + dt);             /* :218 */
         self_gravity(c, c->forcing_potential, c->p_t0);
@@ -400,11 +505,16 @@ void oracle_step(oracle_ctx* c, int nsteps, double* diss_series) {
         spmv_add(&c->grad, c->forcing_potential, c->drag_term);
         integrateAB3scalar(c, c->v_t0, c->dv_dt, c->iter, F);            /* :239 */
         for (i = 0; i < F; ++i) c->v_t0[i] += dt * c->drag_term[i];      /* :242 */
-        spmv_scaled_assign(&c->div, h, c->v_t0, c->dp_dt_t0);            /* updateEta.cpp:39 */
+        if (c->nl_on) {                                                  /* updateEta.cpp:32-33 */
+            interpolateLSQFlux(c, c->flux, c->v_t0, c->h_total);
+            spmv_assign(&c->div, c->flux, c->dp_dt_t0);
+        } else
+            spmv_scaled_assign(&c->div, h, c->v_t0, c->dp_dt_t0);        /* updateEta.cpp:39 */
         for (i = 0; i < N; ++i) c->dp_dt[i * 3] = c->dp_dt_t0[i];       /* :251 */
         integrateAB3scalar(c, c->p_t0, c->dp_dt, c->iter, N);            /* :253 */
         interpolateVelocity(c, c->v_avg, c->v_t0);                       /* :261 */
         updateEnergy(c, &c->e_diss, c->energy_diss, c->v_avg, c->m.face_area);   /* :262 */
+        if (c->nl_on) for (i = 0; i < N; i++) c->h_total[i] = h + c->p_t0[i];    /* :266-269 */
         c->iter++;                                                       /* :276 */
         if (diss_series) diss_series[k] = c->e_diss;
     }

@@ -43,6 +43,7 @@ def _load():
         lib.oracle_get_dissipation_avg.argtypes = [C.c_void_p]
         lib.oracle_set_sh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.oracle_get_sh_b.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_set_nonlinear.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 14
         lib.oracle_get_iter.restype = C.c_long
         lib.oracle_get_iter.argtypes = [C.c_void_p]
         _lib = lib
@@ -87,6 +88,20 @@ class LteOracle:
     def set_state(self, v=None, eta=None, dvdt=None, detadt=None, iter: int = 0):
         k = [self._ptr(v, self.F), self._ptr(eta, self.N), self._ptr(dvdt, self.F * 3), self._ptr(detadt, self.N * 3)]
         _load().oracle_set_state(self._h, k[0][1], k[1][1], k[2][1], k[3][1], iter)
+
+    def set_nonlinear(self, nl: dict) -> None:
+        """Nonlinear branch (advection; true). nl: the reference's operators and vertex tables, keys as the reference names them:
+        operatorCurl / operatorRBFinterp / operatorDirectionalSecondDeriv + '.indptr' '.indices' '.data', vertex_sinlat,
+        vertex_area, vertex_R, vertex_nodes, face_vertexes."""
+        a = []
+        for op in ("operatorCurl", "operatorRBFinterp", "operatorDirectionalSecondDeriv"):
+            for part, dt in ((".indptr", np.int32), (".indices", np.int32), (".data", np.float64)):
+                a.append(np.ascontiguousarray(nl[op + part], dtype=dt))
+        for name, dt in (("vertex_sinlat", np.float64), ("vertex_area", np.float64), ("vertex_R", np.float64), ("vertex_nodes", np.int32),
+                         ("face_vertexes", np.int32)):
+            a.append(np.ascontiguousarray(nl[name], dtype=dt))
+        self._keep["nl"] = a
+        _load().oracle_set_nonlinear(self._h, int(a[9].shape[0]), *[x.ctypes.data for x in a])
 
     def set_self_gravity(self, Y, T) -> None:
         """Y [rows][N] basis, T [rows][rows] = factor_l * (Y Y^T)^-1 (oracle/sh_oracle.py)."""

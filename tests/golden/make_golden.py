@@ -73,8 +73,12 @@ SCALARS = ["radius", "angVel", "period", "g", "h", "alpha", "loveReduct", "shell
            "endTime", "totalIter", "outputTime", "tide_type", "fric_type", "surface_type", "advection"]
 
 
+NL_TABLES = ["vertex_sinlat", "vertex_area", "vertex_R", "vertex_nodes", "face_vertexes"] + \
+            [f"{op}.{part}" for op in ("operatorCurl", "operatorRBFinterp", "operatorDirectionalSecondDeriv") for part in ("indptr", "indices", "data")]
+
+
 def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: bool, full_tables: bool,
-             init_state: dict | None = None):
+             init_state: dict | None = None, nl_tables: bool = False):
     binary = os.path.join(ROOT, "oracle", "_ref", f"odis_ref_l{level}")
     with tempfile.TemporaryDirectory() as d:
         os.makedirs(d + "/input_files"); os.makedirs(d + "/DATA")
@@ -123,6 +127,12 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
             out[f"sha256_{op}.{part}"] = np.array(digest(tab[f"{op}.{part}"]))
             if full_tables:
                 out[f"table_{op}.{part}"] = tab[f"{op}.{part}"]
+    if nl_tables:                       # what the nonlinear branch (advection; true) reads besides the linear tables
+        for t in NL_TABLES:
+            out["nl_" + t] = tab[t]
+        for t in TABLES:
+            if "table_" + t not in out:
+                out["table_" + t] = tab[t]
     for k, v in fin.items():
         out["final_" + k] = v
     # per-dump FP64 arrays: "<slice>:<tag>"
@@ -161,6 +171,13 @@ def random_state(level: int, seed: int):
 if __name__ == "__main__":
     built = build_reference((3, 4, 5, 6))
     assert len(built) == 4, built
+    only = sys.argv[1:]                  # case names to (re)generate; none = all
+    _run = run_case
+
+    def run_case(name, *a, **k):         # noqa: F811
+        if not only or name in only:
+            _run(name, *a, **k)
+
     earth = {"radius": "6.37122e6", "angular velocity": "7.292e-5", "surface gravity": "9.80616", "semimajor axis": "671100000.0",
              "eccentricity": "0.01", "obliquity": "-2.0", "ocean thickness": "8e3", "time step": "30", "potential": "OBLIQ_WEST"}
     # (1) shipped default physics (Earth-like, OBLIQ_WEST) on the shipped L3 grid, linear path, full tables
@@ -181,6 +198,13 @@ if __name__ == "__main__":
     # (8) one whole orbit on L3 with the HDF5 rows the reference wrote (11 slices) and dissipation output on
     run_case("l3_ecc_full_orbit", 3, {"time step": "100", "output time": "10", "simulation end time": "1", "dissipation output": "true"},
              0, every_step_dumps=False, full_tables=False)
+    # (9) nonlinear branch: the shipped input.in physics WITH advection true (as shipped) on L3, and a loaded random state on L4
+    shipped = dict({"radius": "6.37122e6", "angular velocity": "7.292e-5", "surface gravity": "9.80616", "semimajor axis": "671100000.0",
+                    "eccentricity": "0.01", "obliquity": "-2.0", "ocean thickness": "8e3", "time step": "30", "potential": "OBLIQ_WEST"},
+                   advection="true")
+    run_case("l3_advection_shipped", 3, shipped, 150, every_step_dumps=True, full_tables=True, nl_tables=True)
+    run_case("l4_advection_loaded", 4, {"advection": "true", "potential": "FULL", "time step": "40", "ocean thickness": "2e3"}, 40,
+             every_step_dumps=True, full_tables=False, init_state=random_state(4, 21), nl_tables=True)
     # (7) no forcing, decaying loaded state on L5
     run_case("l5_none_loaded", 5, {"potential": "NONE", "time step": "20"}, 30, every_step_dumps=False, full_tables=False,
              init_state=random_state(5, 5))

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ALL_CASES, case_params, load_case, make_run_dir
+from conftest import ALL_CASES, NL_CASES, case_params, load_case, make_run_dir, nonlinear_tables
 from oracle.lte_oracle import LteOracle
 
 
@@ -17,6 +17,8 @@ def oracle_for(odis, tmp_path, case):
     mesh = odis.Mesh.from_file(os.path.join(d, "input_files", "grid_l%d.txt" % int(case["level"])), float(case["scalar_radius"][0]))
     loaded = "init_v" in case
     o = LteOracle(mesh.tables, case_params(case, init_load=int(loaded)))
+    if int(case["scalar_advection"][0]):
+        o.set_nonlinear(nonlinear_tables(case))
     if loaded:
         o.set_state(case["init_v"], case["init_eta"], case["init_dvdt"], case["init_detadt"])
     else:
@@ -24,7 +26,7 @@ def oracle_for(odis, tmp_path, case):
     return mesh, o
 
 
-@pytest.mark.parametrize("name", ALL_CASES)
+@pytest.mark.parametrize("name", ALL_CASES + NL_CASES)
 def test_oracle_reproduces_reference_state(odis, tmp_path, name):
     case = load_case(name)
     mesh, o = oracle_for(odis, tmp_path, case)
