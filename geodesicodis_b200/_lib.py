@@ -35,6 +35,15 @@ class Params(C.Structure):
                [("reserved", c_i32 * 4)]
 
 
+class CsrView(C.Structure):
+    _fields_ = [("n_rows", c_i32), ("n_cols", c_i32), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("data", C.c_void_p)]
+
+
+class NonlinearView(C.Structure):
+    _fields_ = [("curl", CsrView), ("rbf_interp", CsrView), ("directional_second_deriv", CsrView), ("vertex_sinlat", C.c_void_p),
+                ("vertex_area", C.c_void_p)]
+
+
 class PartitionPlan(C.Structure):
     _fields_ = [(n, c_i32) for n in ("rank", "world", "own_cells", "own_edges", "local_cells", "local_edges", "n_peers", "reserved")] + \
                [(n, P(c_i32)) for n in ("local_cell_ref", "local_edge_ref", "peer_rank", "peer_counts", "send_edge_ref", "send_edge_slot",
@@ -84,6 +93,10 @@ SIGNATURES = {
     "odis_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),
     "odis_step_profiled": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float)]),
+    "odis_nonlinear_create": (C.c_int, [C.c_void_p, c_f64, P(C.c_void_p)]),
+    "odis_nonlinear_get_view": (C.c_int, [C.c_void_p, P(NonlinearView)]),
+    "odis_nonlinear_free": (None, [C.c_void_p]),
+    "odis_enable_advection": (C.c_int, [C.c_void_p, P(MeshView), P(NonlinearView)]),
     "odis_enable_self_gravity": (C.c_int, [C.c_void_p, P(MeshView), c_i32, C.c_void_p, c_i32]),
     "odis_get_sh_coefficients": (C.c_int, [C.c_void_p, C.c_void_p]),
     "odis_step_profiled_sh": (C.c_int, [C.c_void_p, c_i32, P(C.c_float), P(C.c_float), P(C.c_float)]),

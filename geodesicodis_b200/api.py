@@ -224,6 +224,31 @@ def sh_normal_inverse(pos_sph, l_max: int) -> np.ndarray:
     return out
 
 
+def nonlinear_tables(mesh: Mesh, rbf_eps: float) -> dict:
+    """The tables only the nonlinear branch (`advection; true`) reads, built from the mesh on the host: a dict keyed like the
+    reference's members ('operatorCurl.indptr' ... 'vertex_sinlat', 'vertex_area'), ready for Solver.enable_advection."""
+    if mesh._h is None:
+        raise ValueError("nonlinear_tables needs a mesh built by the library (Mesh.from_file / from_arrays)")
+    h = C.c_void_p()
+    check(_lib.load().odis_nonlinear_create(mesh._h, rbf_eps, C.byref(h)))
+    try:
+        view = _lib.NonlinearView()
+        check(_lib.load().odis_nonlinear_get_view(h, C.byref(view)))
+        out = {}
+        for name, csr in (("operatorCurl", view.curl), ("operatorRBFinterp", view.rbf_interp), ("operatorDirectionalSecondDeriv", view.directional_second_deriv)):
+            ptr = np.ctypeslib.as_array(C.cast(csr.indptr, C.POINTER(C.c_int32)), shape=(csr.n_rows + 1,)).copy()
+            nnz = int(ptr[-1])
+            out[name + ".indptr"] = ptr
+            out[name + ".indices"] = np.ctypeslib.as_array(C.cast(csr.indices, C.POINTER(C.c_int32)), shape=(nnz,)).copy()
+            out[name + ".data"] = np.ctypeslib.as_array(C.cast(csr.data, C.POINTER(C.c_double)), shape=(nnz,)).copy()
+        V = mesh.n_vertices
+        out["vertex_sinlat"] = np.ctypeslib.as_array(C.cast(view.vertex_sinlat, C.POINTER(C.c_double)), shape=(V,)).copy()
+        out["vertex_area"] = np.ctypeslib.as_array(C.cast(view.vertex_area, C.POINTER(C.c_double)), shape=(V,)).copy()
+        return out
+    finally:
+        _lib.load().odis_nonlinear_free(h)
+
+
 def partition_plan(mesh: Mesh, rank: int, world: int, reorder: bool = True) -> dict:
     """Host-only view of the domain decomposition rank `rank` of `world` would use (numpy copies)."""
     lib = _lib.load()
@@ -358,6 +383,32 @@ class Solver:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         check(_lib.load().odis_step_profiled_sh(self._h, nsteps, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def enable_advection(self, nl: dict) -> None:
+        """Nonlinear branch (`advection; true`). nl: the reference's operators as CSR and its vertex tables, keyed by the reference's
+        names: 'operatorCurl' / 'operatorRBFinterp' / 'operatorDirectionalSecondDeriv' + '.indptr', '.indices', '.data'; 'vertex_sinlat';
+        'vertex_area'."""
+        keep = []
+        view = _lib.NonlinearView()
+
+        def csr(name, n_rows, n_cols):
+            ptr = np.ascontiguousarray(nl[name + ".indptr"], dtype=np.int32)
+            idx = np.ascontiguousarray(nl[name + ".indices"], dtype=np.int32)
+            val = np.ascontiguousarray(nl[name + ".data"], dtype=np.float64)
+            if ptr.size != n_rows + 1:
+                raise ValueError(f"{name}: expected {n_rows} rows")
+            keep.extend([ptr, idx, val])
+            return _lib.CsrView(n_rows, n_cols, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data)
+
+        V = self.mesh.n_vertices
+        view.curl = csr("operatorCurl", V, self.F)
+        view.rbf_interp = csr("operatorRBFinterp", 3 * self.N, self.F)
+        view.directional_second_deriv = csr("operatorDirectionalSecondDeriv", 2 * self.F, self.N)
+        vs = np.ascontiguousarray(nl["vertex_sinlat"], dtype=np.float64)
+        va = np.ascontiguousarray(nl["vertex_area"], dtype=np.float64)
+        keep.extend([vs, va])
+        view.vertex_sinlat, view.vertex_area = vs.ctypes.data, va.ctypes.data
+        check(_lib.load().odis_enable_advection(self._h, C.byref(self.mesh.view), C.byref(view)))
 
     def enable_self_gravity(self, l_max: int, factor, stored_basis: bool = False) -> None:
         """Spherical-harmonic self-gravity / shell-pressure term (pressureGradientSH): factor[l] for l = 0..l_max

@@ -10,6 +10,7 @@
 #include "odis_error.h"
 #include "odis_gridgen.h"
 #include "odis_mesh.h"
+#include "odis_mesh_nl.h"
 #include "odis_partition.h"
 #include "odis_sh.h"
 
@@ -19,6 +20,9 @@ struct odis_config {
 };
 struct odis_mesh {
     odis::MeshTables t;
+};
+struct odis_nonlinear {
+    odis::NonlinearTables t;
 };
 
 namespace odis {
@@ -35,6 +39,37 @@ extern "C" {
 
 const char* odis_last_error(void) { return odis::g_last_error.c_str(); }
 const char* odis_version(void) { return "odis_b200 0.1 sm_100a"; }
+
+// ------------------------------------------------------------------ nonlinear-branch tables ----
+int odis_nonlinear_create(const odis_mesh* mesh, double rbf_eps, odis_nonlinear** out) {
+    if (!mesh || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    odis_nonlinear* n = new (std::nothrow) odis_nonlinear();
+    if (!n) return fail(ODIS_ERR_ARG, "out of memory");
+    std::string err;
+    if (odis::build_nonlinear_tables(mesh->t, mesh->t.radius, rbf_eps, n->t, err) != 0) {
+        delete n;
+        return fail(ODIS_ERR_ARG, err);
+    }
+    *out = n;
+    return ODIS_OK;
+}
+
+int odis_nonlinear_get_view(const odis_nonlinear* nl, odis_nonlinear_view* view) {
+    if (!nl || !view) return fail(ODIS_ERR_ARG, "NULL argument");
+    auto csr = [](const odis::Csr& A) {
+        odis_csr_view v;
+        v.n_rows = A.n_rows; v.n_cols = A.n_cols; v.indptr = A.indptr.data(); v.indices = A.indices.data(); v.data = A.data.data();
+        return v;
+    };
+    view->curl = csr(nl->t.curl);
+    view->rbf_interp = csr(nl->t.rbf_interp);
+    view->directional_second_deriv = csr(nl->t.directional_second_deriv);
+    view->vertex_sinlat = nl->t.vertex_sinlat.data();
+    view->vertex_area = nl->t.vertex_area.data();
+    return ODIS_OK;
+}
+
+void odis_nonlinear_free(odis_nonlinear* nl) { delete nl; }
 
 // ------------------------------------------------------------------ spherical harmonics (host helpers) ----
 int odis_sh_basis(int32_t n, const double* pos_sph, int32_t l_max, double* Y_out) {

@@ -20,6 +20,7 @@
 #include <unistd.h>
 
 #include "odis_kernels.cuh"
+#include "odis_kernels_nl.cuh"
 #include "odis_partition.h"
 #include "odis_reorder.h"
 #include "odis_sh.cuh"
@@ -106,6 +107,12 @@ struct odis_solver {
     odis::HaloRemote remote_v[2], remote_c[2];             // peers' vl[0], vl[1], eu[0], eu[1] + their flag arrays
     void* ipc_opened[kMaxPeers][5] = {{nullptr}};
 
+    // nonlinear branch (odis_enable_advection)
+    bool nl_on = false;
+    odis::NlTables nl{};
+    double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
+    double2* d_nl_fq = nullptr;
+    std::vector<void*> nl_owned;
     // spherical-harmonic self-gravity / shell-pressure term (odis_enable_self_gravity)
     bool sh_on = false;
     int sh_lmax = 0, sh_rows = 0;
@@ -789,6 +796,116 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
     return ODIS_OK;
 }
 
+// ELL form (device numbering) of a reference-numbered CSR operator: rows through row_map, columns through col_map, slots in the
+// CSR's own (ascending reference column) order. row_of(r) gives the reference row of sub-row r; n_rows device rows of stride `stride`.
+static int build_ell(odis_solver* s, const odis_csr_view& A, int n_rows, int stride, int row_mul, int row_off, const std::vector<int>& row_ref,
+                     const std::vector<int>& col_map, odis::Ell* out) {
+    int width = 0;
+    for (int r = 0; r < n_rows; r++) {
+        const int rr = row_ref[(size_t)r] * row_mul + row_off;
+        width = std::max(width, A.indptr[rr + 1] - A.indptr[rr]);
+    }
+    if (width > 16) return fail(ODIS_ERR_ARG, "nonlinear operator has more than 16 entries in a row");
+    std::vector<int> id((size_t)width * stride, -1);
+    std::vector<double> w((size_t)width * stride, 0.0);
+    for (int r = 0; r < n_rows; r++) {
+        const int rr = row_ref[(size_t)r] * row_mul + row_off;
+        int k = 0;
+        for (int q = A.indptr[rr]; q < A.indptr[rr + 1]; q++, k++) {
+            const int col = A.indices[q];
+            if (col < 0 || col >= (int)col_map.size()) return fail(ODIS_ERR_ARG, "nonlinear operator column out of range");
+            id[(size_t)k * stride + r] = col_map[(size_t)col];
+            w[(size_t)k * stride + r] = A.data[q];
+        }
+    }
+    int* did = nullptr; double* dw = nullptr;
+    int rc;
+    if ((rc = upload(s, &did, id)) || (rc = upload(s, &dw, w))) return rc;
+    s->nl_owned.push_back(did); s->nl_owned.push_back(dw);
+    out->width = width; out->stride = stride; out->id = did; out->w = dw;
+    return ODIS_OK;
+}
+
+int odis_enable_advection(odis_solver* s, const odis_mesh_view* mv, const odis_nonlinear_view* nv) {
+    if (!s || !mv || !nv) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (s->nl_on) return fail(ODIS_ERR_STATE, "the nonlinear branch is already enabled");
+    if (s->world > 1 || s->fused) return fail(ODIS_ERR_UNSUPPORTED, "the nonlinear branch runs on a single, unpartitioned solver with the two-launch kernels");
+    if (mv->n_cells != s->Ng || mv->n_edges != s->Fg) return fail(ODIS_ERR_ARG, "mesh does not match the solver");
+    const int N = s->N, F = s->F, V = mv->n_vertices;
+    if (nv->curl.n_rows != V || nv->curl.n_cols != F || nv->rbf_interp.n_rows != 3 * N || nv->rbf_interp.n_cols != F ||
+        nv->directional_second_deriv.n_rows != 2 * F || nv->directional_second_deriv.n_cols != N)
+        return fail(ODIS_ERR_ARG, "nonlinear operators have the wrong shapes (curl VxF, rbf 3NxF, second derivative 2FxN)");
+    if (!mv->vertex_nodes || !mv->vertex_R || !mv->face_vertexes || !nv->vertex_sinlat || !nv->vertex_area)
+        return fail(ODIS_ERR_ARG, "vertex tables missing");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    // reference id -> device id
+    std::vector<int> cmap((size_t)N), emap((size_t)F), vmap((size_t)V), vref((size_t)V);
+    for (int i = 0; i < N; i++) cmap[(size_t)s->cell_perm[(size_t)i]] = i;
+    for (int e = 0; e < F; e++) emap[(size_t)s->edge_perm[(size_t)e]] = e;
+    // vertices follow their lowest-numbered cell (locality of the gathers)
+    {
+        std::vector<std::pair<int, int>> key((size_t)V);
+        for (int v = 0; v < V; v++) {
+            int lo = N;
+            for (int j = 0; j < 3; j++) lo = std::min(lo, cmap[(size_t)mv->vertex_nodes[(size_t)v * 3 + j]]);
+            key[(size_t)v] = {lo, v};
+        }
+        std::sort(key.begin(), key.end());
+        for (int k = 0; k < V; k++) { vref[(size_t)k] = key[(size_t)k].second; vmap[(size_t)key[(size_t)k].second] = k; }
+    }
+    const int Vs = (V + 31) / 32 * 32, Fp = s->Fp, Np = s->Np;
+    odis::NlTables& t = s->nl;
+    t.n_vertices = V; t.n_edges = F; t.n_cells = N; t.vstride = Vs; t.estride = Fp; t.cstride = Np; t.omega = s->prm.omega;
+    int rc;
+    if ((rc = build_ell(s, nv->curl, V, Vs, 1, 0, vref, emap, &t.curl))) return rc;
+    for (int c = 0; c < 3; c++)
+        if ((rc = build_ell(s, nv->rbf_interp, N, Np, 3, c, s->cell_perm, emap, &t.rbf[c]))) return rc;
+    for (int c = 0; c < 2; c++)
+        if ((rc = build_ell(s, nv->directional_second_deriv, F, Fp, 2, c, s->edge_perm, cmap, &t.d2[c]))) return rc;
+    std::vector<int> vnode((size_t)3 * Vs, 0), nid((size_t)odis::kStencil * Fp, -1);
+    std::vector<double> vR((size_t)3 * Vs, 0.0), vsin((size_t)Vs, 0.0), varea_r((size_t)Vs, 1.0), ncoef((size_t)odis::kStencil * Fp, 0.0);
+    std::vector<int2> fvert((size_t)Fp, make_int2(0, 0));
+    for (int k = 0; k < V; k++) {
+        const int v = vref[(size_t)k];
+        for (int j = 0; j < 3; j++) {
+            vnode[(size_t)j * Vs + k] = cmap[(size_t)mv->vertex_nodes[(size_t)v * 3 + j]];
+            vR[(size_t)j * Vs + k] = mv->vertex_R[(size_t)v * 3 + j];
+        }
+        vsin[(size_t)k] = nv->vertex_sinlat[v];
+        varea_r[(size_t)k] = 1.0 / nv->vertex_area[v];                              // mesh.cpp:1147
+    }
+    for (int e = 0; e < F; e++) {
+        const int er = s->edge_perm[(size_t)e];
+        fvert[(size_t)e] = make_int2(vmap[(size_t)mv->face_vertexes[(size_t)er * 2]], vmap[(size_t)mv->face_vertexes[(size_t)er * 2 + 1]]);
+        int friend_num = 10;                                                        // momAdvection.cpp:104-111
+        if (mv->node_friends[(size_t)mv->face_nodes[(size_t)er * 2] * 6 + 5] < 0) friend_num--;
+        if (mv->node_friends[(size_t)mv->face_nodes[(size_t)er * 2 + 1] * 6 + 5] < 0) friend_num--;
+        const double dist_r = 1.0 / mv->face_node_dist[er];                         // mesh.cpp:624
+        for (int j = 0; j < friend_num; j++) {
+            const int f = mv->face_interp_friends[(size_t)er * 10 + j];
+            nid[(size_t)j * Fp + e] = emap[(size_t)f];
+            ncoef[(size_t)j * Fp + e] = mv->face_interp_weights[(size_t)er * 10 + j] * mv->face_len[f] * dist_r;   // momAdvection.cpp:129
+        }
+    }
+    int* d_vnode = nullptr; int* d_nid = nullptr; int2* d_fvert = nullptr;
+    double *d_vR = nullptr, *d_vsin = nullptr, *d_varea_r = nullptr, *d_ncoef = nullptr;
+    if ((rc = upload(s, &d_vnode, vnode)) || (rc = upload(s, &d_vR, vR)) || (rc = upload(s, &d_vsin, vsin)) || (rc = upload(s, &d_varea_r, varea_r)) ||
+        (rc = upload(s, &d_fvert, fvert)) || (rc = upload(s, &d_nid, nid)) || (rc = upload(s, &d_ncoef, ncoef)) ||
+        (rc = dev_alloc(s, &s->d_nl_qv, (size_t)Vs)) || (rc = dev_alloc(s, &s->d_nl_fq, (size_t)Fp)) || (rc = dev_alloc(s, &s->d_nl_ekin, (size_t)Np)) ||
+        (rc = dev_alloc(s, &s->d_nl_flux, (size_t)Fp)))
+        return rc;
+    for (void* p : {(void*)d_vnode, (void*)d_vR, (void*)d_vsin, (void*)d_varea_r, (void*)d_fvert, (void*)d_nid, (void*)d_ncoef, (void*)s->d_nl_qv,
+                    (void*)s->d_nl_fq, (void*)s->d_nl_ekin, (void*)s->d_nl_flux})
+        s->nl_owned.push_back(p);
+    t.vnode = d_vnode; t.vR = d_vR; t.vsin = d_vsin; t.varea_r = d_varea_r; t.carea = s->d_area; t.fvert = d_fvert; t.nid = d_nid; t.ncoef = d_ncoef;
+    t.cells = s->d_cells; t.grad = s->d_grad; t.dist = s->d_dist; t.eid = s->d_eid; t.area = s->d_area;
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);
+    s->graphs.clear();
+    s->nl_on = true;
+    return ODIS_OK;
+}
+
 int odis_get_sh_coefficients(odis_solver* s, double* out) {
     if (!s || !out) return fail(ODIS_ERR_ARG, "NULL argument");
     if (!s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is not enabled");
@@ -874,7 +991,39 @@ static int finalize_eta(odis_solver* s) {
 constexpr int kGraphSteps = 12;      // steps per captured graph: a multiple of the rotation period (2 x 2 x 3 -> 6)
 
 // Launches of one time step on the solver's stream (also under stream capture) and the rotation of the buffers.
+// One step of the nonlinear branch: diagnostics of v^n (the linear edge kernel produces them on the fly), the six launches of
+// odis_kernels_nl.cu, the potential pass for the next step.
+static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEvent_t>* marks, int k) {
+    odis::launch_edge_diagnostics(s->edge_tables(), s->phys, s->d_vl[s->cur], s->d_normal, nullptr, nullptr, s->d_block_partial, s->d_ticket,
+                                  s->d_series + (s->iter - s->iter0), s->prm.block_threads, s->stream);
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4], s->stream);
+    odis::NlState ns;
+    ns.vl_in = s->d_vl[s->cur]; ns.vl_out = s->d_vl[1 - s->cur];
+    ns.eu_in = s->d_eu[s->ecur]; ns.eu_out = s->d_eu[1 - s->ecur];
+    ns.h1 = s->d_hv[s->hv1]; ns.h2 = s->d_hv[1 - s->hv1];
+    ns.ch1 = s->d_he[s->he1]; ns.ch2 = s->d_he[s->he2]; ns.chw = s->d_he[s->hefree];
+    ns.qv = s->d_nl_qv; ns.fq = s->d_nl_fq; ns.ekin = s->d_nl_ekin; ns.flux = s->d_nl_flux;
+    odis::launch_step_nonlinear(s->nl, s->phys, ns, mode, s->stream);
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 1], s->stream);
+    if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
+    rotate_cell_history(s, mode);
+    s->ecur = 1 - s->ecur;
+    // forcing for the next step (current_time = dt*(iter+1), evaluated at current_time + dt), in place on the new {eta,U}
+    odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
+    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, s->prm.dt * (double)(s->iter + 1) + s->prm.dt),
+                           odis::CELL_UPDATE_U, s->prm.block_threads, nullptr, s->stream);
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
+    { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
+    if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 3], s->stream);
+    s->cur = 1 - s->cur;
+    s->iter++;
+    s->last_mode = mode;
+    s->launches += 2 + odis::kNlLaunches + s->sh_launches();
+    return ODIS_OK;
+}
+
 static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cudaEvent_t>* marks, int k) {
+    if (s->nl_on) return enqueue_step_nonlinear(s, mode, marks, k);
     const odis::EdgeTables et = s->edge_tables();
     const odis::CellTables ct = s->cell_tables(s->world > 1 ? s->N : s->No);     // partitioned: ghost cells are updated locally
     odis::EdgeState es;
@@ -969,7 +1118,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
         return ODIS_OK;
     }
     // ---- two launches per step (+ one halo exchange launch after each when partitioned) ----
-    const bool dev_ctl = s->pipe_edge;       // the staged edge kernel keeps the step counter / time factors on the device
+    const bool dev_ctl = s->pipe_edge && !s->nl_on;   // the staged edge kernel keeps the step counter / time factors on the device
     if (dev_ctl && nsteps > 0) {             // time factors of every step of this call, uploaded ahead (tidalPotentials.cpp:55-61)
         std::vector<odis::StepScalars> sc((size_t)nsteps);
         // forcing for the NEXT step: current_time = dt*(iter+1), evaluated at current_time + dt
@@ -1187,6 +1336,8 @@ void odis_destroy(odis_solver* s) {
     for (int r = 0; r < odis::kShMaxWorld; r++)
         if (s->sh_ipc_opened[r]) cudaIpcCloseMemHandle(s->sh_ipc_opened[r]);
     for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (void* p : s->nl_owned)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);

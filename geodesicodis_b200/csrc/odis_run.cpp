@@ -23,6 +23,7 @@
 #include "odis_error.h"
 #include "odis_h5lite.h"
 #include "odis_mesh.h"
+#include "odis_mesh_nl.h"
 #include "odis_sphere.h"
 
 using odis::fail;
@@ -174,10 +175,6 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     for (const std::string& k : cfg.unassigned())                             // globals.cpp:445-466
         log.err("WARNING: Unassigned global constant: " + k + ". \nAssigning default value could be risky...\nUsing Titan value\n");
     if (cfg.finalize(err) != 0) return terminate(ODIS_ERR_CONFIG, err);
-    if (cfg.get_bool("advection"))
-        return terminate(ODIS_ERR_UNSUPPORTED, "advection; true selects the nonlinear branch (momAdvection.cpp), which is outside the LTE hot path");
-    if (cfg.get_bool("velocity cartesian output"))
-        return terminate(ODIS_ERR_UNSUPPORTED, "velocity cartesian output needs the RBF interpolation operator (interpolation.cpp:64-174), outside the LTE hot path");
     if (cfg.solver_type != odis::AB3) return terminate(ODIS_ERR_UNSUPPORTED, "only solver type AB3 has a live implementation (solver.cpp:25-50)");
     if (cfg.initial_condition == odis::INIT_ANALYTICAL) return terminate(ODIS_ERR_UNSUPPORTED, "initial conditions; ANALYTICAL is not provided");
     for (const char* k : {"pressure output", "kinetic output", "dummy2 output"})
@@ -208,7 +205,12 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     const uint64_t T = (uint64_t)((int)end_time * output_time + 1);            // outFiles.cpp:149-150,179
     const uint64_t dims_f[2] = {T, (uint64_t)F}, dims_n[2] = {T, (uint64_t)N}, dims_t[1] = {T}, dims_fp[1] = {(uint64_t)F};
     int ds_u = -1, ds_v = -1, ds_eta = -1, ds_diss = -1, ds_avg = -1, ds_kin = -1, ds_d1 = -1;
+    int ds_ux = -1, ds_uy = -1, ds_uz = -1;
     if (cfg.get_bool("velocity output")) { ds_u = h5.add_dataset("east velocity", 2, dims_f, err); ds_v = h5.add_dataset("north velocity", 2, dims_f, err); }
+    if (cfg.get_bool("velocity cartesian output")) {                           // outFiles.cpp:255-272
+        ds_ux = h5.add_dataset("x velocity", 2, dims_n, err); ds_uy = h5.add_dataset("y velocity", 2, dims_n, err);
+        ds_uz = h5.add_dataset("z velocity", 2, dims_n, err);
+    }
     if (cfg.get_bool("displacement output")) ds_eta = h5.add_dataset("displacement", 2, dims_n, err);
     if (cfg.get_bool("dissipation output")) ds_diss = h5.add_dataset("dissipated energy", 2, dims_f, err);
     if (cfg.get_bool("dissipation avg output")) ds_avg = h5.add_dataset("dissipation avg output", 1, dims_t, err);
@@ -252,6 +254,24 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     odis_solver* s = nullptr;
     int rc = odis_create(&mv, &p, opt.device, &s);
     if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+    // tables of the nonlinear branch: the step needs them with `advection; true` (updateMomentum.cpp:37, updateEta.cpp:32), the
+    // Cartesian velocity output needs operatorRBFinterp either way (timeIntegrator.cpp:173,290)
+    odis::NonlinearTables nlt;
+    if (cfg.get_bool("advection") || ds_ux >= 0) {
+        if (odis::build_nonlinear_tables(mesh, mesh.radius, cfg.get_double("rbf epsilon"), nlt, err) != 0) return terminate(ODIS_ERR_GRID, err);
+    }
+    if (cfg.get_bool("advection")) {
+        auto csr = [](const odis::Csr& A) {
+            odis_csr_view v;
+            v.n_rows = A.n_rows; v.n_cols = A.n_cols; v.indptr = A.indptr.data(); v.indices = A.indices.data(); v.data = A.data.data();
+            return v;
+        };
+        odis_nonlinear_view nv{};
+        nv.curl = csr(nlt.curl); nv.rbf_interp = csr(nlt.rbf_interp); nv.directional_second_deriv = csr(nlt.directional_second_deriv);
+        nv.vertex_sinlat = nlt.vertex_sinlat.data(); nv.vertex_area = nlt.vertex_area.data();
+        rc = odis_enable_advection(s, &mv, &nv);
+        if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+    }
     if (opt.self_gravity) {
         // pressureGradientSH (spatialOperators.cpp:387-462), dead code at reference HEAD: opt-in only
         const int l_max = cfg.get_int("sh degree");
@@ -279,7 +299,7 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     const bool stepping = cfg.surface_type == odis::FREE || cfg.surface_type == odis::FREE_LOADING ||
                           cfg.surface_type == odis::LID_LOVE || cfg.surface_type == odis::LID_MEMBR;      // timeIntegrator.cpp:207-210
     const double r = cfg.get_double("radius"), period = cfg.get_double("orbital period");
-    std::vector<double> ven((size_t)F * 2), ediss((size_t)F);
+    std::vector<double> ven((size_t)F * 2), ediss((size_t)F), vcur((size_t)F);
     std::vector<float> fa((size_t)std::max(F, N)), fb((size_t)F);
     int out_count = 1;
     int64_t iter = 0;
@@ -295,6 +315,18 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
                 for (int i = 0; i < F; i++) { fa[i] = (float)ven[(size_t)i * 2]; fb[i] = (float)ven[(size_t)i * 2 + 1]; }   // outFiles.cpp:546-553
                 h5.write_rows(ds_u, row, 1, fa.data(), err);
                 h5.write_rows(ds_v, row, 1, fb.data(), err);
+            }
+            if (ds_ux >= 0) {                                                  // interpolateVelocityCartRBF, interpolation.cpp:116; outFiles.cpp:567-590
+                if ((rc2 = odis_get_field(s, ODIS_FIELD_VELOCITY, vcur.data()))) return rc2;
+                const odis::Csr& A = nlt.rbf_interp;
+                for (int c = 0; c < 3; c++) {
+                    for (int i = 0; i < N; i++) {
+                        double tmp = 0;
+                        for (int k = A.indptr[(size_t)3 * i + c]; k < A.indptr[(size_t)3 * i + c + 1]; k++) tmp += A.data[(size_t)k] * vcur[(size_t)A.indices[(size_t)k]];
+                        fa[i] = (float)tmp;
+                    }
+                    h5.write_rows(c == 0 ? ds_ux : c == 1 ? ds_uy : ds_uz, row, 1, fa.data(), err);
+                }
             }
             if (ds_eta >= 0) {
                 if ((rc2 = odis_get_field(s, ODIS_FIELD_ETA, eta.data()))) return rc2;

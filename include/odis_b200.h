@@ -207,6 +207,36 @@ int odis_step_timed(odis_solver* s, int32_t nsteps, float* elapsed_ms_out);
 /* As odis_step, with every kernel launch bracketed by its own CUDA event pair; returns the summed device
  * time (ms) of the edge-update and of the cell-update launches separately (roofline instrumentation). */
 int odis_step_profiled(odis_solver* s, int32_t nsteps, float* edge_ms_out, float* cell_ms_out);
+/* Nonlinear branch of the step (`advection; true`): calculateMomentumAdvection (src/momAdvection.cpp:11-268: potential-vorticity
+ * flux over the TRiSK stencil + gradient of the kinetic energy from operatorRBFinterp) replaces the Coriolis product in
+ * updateMomentum (src/updateMomentum.cpp:37-38), and updateEta takes the divergence of the third-order edge flux of
+ * interpolateLSQFlux (src/updateEta.cpp:32-33, src/interpolation.cpp:311-364). The three operators only this branch uses are
+ * handed over as the reference builds them — row-major CSR, columns ascending (Eigen's compressed storage: outerIndexPtr /
+ * innerIndexPtr / valuePtr of Mesh::operatorCurl, ::operatorRBFinterp, ::operatorDirectionalSecondDeriv, src/mesh.cpp:3122-3175,
+ * 2263-2361, 2364-2719) — with Mesh::vertex_sinlat and ::vertex_area; `mesh` must carry vertex_nodes, vertex_R and face_vertexes.
+ * Fields then match the reference's nonlinear solver bit for bit. Single, unpartitioned solvers only. */
+typedef struct odis_csr_view {
+    int32_t n_rows, n_cols;
+    const int32_t* indptr;   /* [n_rows + 1] */
+    const int32_t* indices;  /* [nnz] */
+    const double* data;      /* [nnz] */
+} odis_csr_view;
+typedef struct odis_nonlinear_view {
+    odis_csr_view curl;                      /* V x F */
+    odis_csr_view rbf_interp;                /* 3N x F, rows 3i, 3i+1, 3i+2 = x, y, z at cell i */
+    odis_csr_view directional_second_deriv;  /* 2F x N, rows 2e, 2e+1 = inner, outer cell side of edge e */
+    const double* vertex_sinlat;             /* [V] */
+    const double* vertex_area;               /* [V] */
+} odis_nonlinear_view;
+int odis_enable_advection(odis_solver* s, const odis_mesh_view* mesh, const odis_nonlinear_view* nl);
+/* The same tables built by the library from its own mesh (host only): the vertex part of Mesh::AssignFaces
+ * (src/mesh.cpp:910-1147), CalcControlVolumeInterpMatrix (:199-434), CalcRBFInterpMatrix (:2263-2361), CalcRBFInterpMatrix2
+ * (:2364-2719), CalcCurlOperatorCoeffs (:3122-3175). rbf_eps = input.in's "rbf epsilon". The view stays valid until
+ * odis_nonlinear_free. */
+typedef struct odis_nonlinear odis_nonlinear;
+int odis_nonlinear_create(const odis_mesh* mesh, double rbf_eps, odis_nonlinear** out);
+int odis_nonlinear_get_view(const odis_nonlinear* nl, odis_nonlinear_view* view);
+void odis_nonlinear_free(odis_nonlinear* nl);
 /* Self-gravity / shell-pressure term by spherical harmonics — the reference's pressureGradientSH
  * (src/spatialOperators.cpp:387-462, commented out at HEAD) with the basis of Mesh::CalcLegendreFuncs
  * (src/mesh.cpp:2154-2260) and the least-squares coefficients of getSHCoeffsGG (src/sphericalHarmonics.cpp:16-72 ->

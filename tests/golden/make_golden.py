@@ -130,9 +130,6 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
     if nl_tables:                       # what the nonlinear branch (advection; true) reads besides the linear tables
         for t in NL_TABLES:
             out["nl_" + t] = tab[t]
-        for t in TABLES:
-            if "table_" + t not in out:
-                out["table_" + t] = tab[t]
     for k, v in fin.items():
         out["final_" + k] = v
     # per-dump FP64 arrays: "<slice>:<tag>"
@@ -205,6 +202,18 @@ if __name__ == "__main__":
     run_case("l3_advection_shipped", 3, shipped, 150, every_step_dumps=True, full_tables=True, nl_tables=True)
     run_case("l4_advection_loaded", 4, {"advection": "true", "potential": "FULL", "time step": "40", "ocean thickness": "2e3"}, 40,
              every_step_dumps=True, full_tables=False, init_state=random_state(4, 21), nl_tables=True)
+    # (10) the shipped input.in VERBATIM (advection true, velocity cartesian output true, ...) except for the grid level (3) and the
+    #      end time (1 orbit = 48,100 steps at the shipped 30 s step): the whole-run drop-in check, HDF5 rows included
+    verbatim = {}
+    for line in open("/root/reference/input.in"):
+        parts = [x.strip() for x in line.split(";")]
+        if len(parts) >= 2 and parts[0] in BASE:
+            verbatim[parts[0]] = parts[1]
+    verbatim["simulation end time"] = "1"
+    run_case("l3_shipped_verbatim", 3, verbatim, 0, every_step_dumps=False, full_tables=False)
+    run_case("l5_advection_ecc", 5, {"advection": "true", "potential": "ECC", "time step": "20", "ocean thickness": "1e3", "eccentricity": "0.05",
+                                     "friction type": "QUADRATIC", "friction coefficient": "1e-3"}, 60, every_step_dumps=False, full_tables=False,
+             init_state=random_state(5, 31), nl_tables=True)
     # (7) no forcing, decaying loaded state on L5
     run_case("l5_none_loaded", 5, {"potential": "NONE", "time step": "20"}, 30, every_step_dumps=False, full_tables=False,
              init_state=random_state(5, 5))

@@ -129,3 +129,21 @@ def test_generated_l7_grid_against_live_reference(odis, tmp_path):
     mesh = odis.Mesh.from_file(d + "/input_files/grid_l7.txt", float(ref["radius"][0]))
     for t in TABLES:
         assert np.array_equal(mesh.tables[t].reshape(-1), ref[t].reshape(-1)), t
+
+
+@pytest.mark.parametrize("name", ["l3_advection_shipped", "l4_advection_loaded", "l5_advection_ecc"])
+def test_nonlinear_operators_bit_identical(odis, tmp_path, name):
+    """Tables only the nonlinear branch reads — operatorCurl, operatorRBFinterp, operatorDirectionalSecondDeriv (CSR, built by the
+    reference as chains of Eigen sparse products and small dense inverses) and the vertex geometry — entry for entry against what
+    the reference built (fixtures from the unmodified reference run with advection on)."""
+    from conftest import load_case, make_run_dir, nonlinear_tables
+    case = load_case(name)
+    d = make_run_dir(tmp_path, case)
+    mesh = odis.Mesh.from_file(os.path.join(d, "input_files", "grid_l%d.txt" % int(case["level"])), float(case["scalar_radius"][0]))
+    ref = nonlinear_tables(case)
+    got = odis.nonlinear_tables(mesh, 0.5)                   # "rbf epsilon; 0.5" in every fixture's input.in
+    for key in ("vertex_sinlat", "vertex_area"):
+        assert np.array_equal(got[key], ref[key]), key
+    for op in ("operatorCurl", "operatorRBFinterp", "operatorDirectionalSecondDeriv"):
+        for part in (".indptr", ".indices", ".data"):
+            assert np.array_equal(got[op + part], ref[op + part]), op + part

@@ -49,6 +49,34 @@ def test_full_orbit_run_matches_reference_outputs(odis, tmp_path):
     assert np.array_equal(pres[:, 0], fmt(case["final_eta"])) and np.array_equal(pres[:, 1:], fmt(case["final_detadt"]))
 
 
+def test_shipped_input_in_runs_verbatim(odis, tmp_path):
+    """BASELINE config 0: the reference's shipped input.in as it is (advection true -> nonlinear branch, velocity cartesian
+    output true, OBLIQ_WEST, Earth-like) on the shipped L3 grid for one orbit, against the reference's own run of it."""
+    case = load_case("l3_shipped_verbatim")
+    assert "advection; \t true;" in str(case["input_in"]) and "velocity cartesian output; \t true;" in str(case["input_in"])
+    d = make_run_dir(tmp_path, case)
+    res = odis.run(d)
+    assert res["steps"] == int(case["nsteps"]) == 2900 and res["dumps"] == 11 and res["interrupted"] == 0
+    h5 = read_h5(os.path.join(d, "DATA", "data.h5"))
+    ref = {k[3:]: case[k] for k in case if k.startswith("h5_")}
+    assert sorted(h5) == sorted(ref) and "x velocity" in h5
+    for name, r in ref.items():
+        assert h5[name].dtype == np.float32 and h5[name].shape == r.shape, name
+    # eta and v are bit-identical in FP64 on the nonlinear branch too; the Cartesian velocity is operatorRBFinterp * v in the
+    # reference's own order
+    for name in ("displacement", "x velocity", "y velocity", "z velocity", "face longitude", "face latitude"):
+        assert np.array_equal(h5[name], ref[name]), name
+    for name in ("east velocity", "north velocity", "dissipation avg output"):
+        assert np.abs(h5[name] - ref[name]).max() <= 2e-7 * np.abs(ref[name]).max(), name
+    out = open(os.path.join(d, "DATA", "OUTPUT.txt")).read()
+    assert dumping_lines(out) == dumping_lines(str(case["output_txt"]))
+    vel = np.array([[float(x) for x in re.split(r",\s*", l.strip())] for l in open(os.path.join(d, "InitialConditions", "vel_init.txt"))])
+    pres = np.array([[float(x) for x in re.split(r",\s*", l.strip())] for l in open(os.path.join(d, "InitialConditions", "pres_init.txt"))])
+    fmt = lambda a: np.array([float("%1.6E" % x) for x in a.ravel()]).reshape(a.shape)
+    assert np.array_equal(vel[:, 0], fmt(case["final_v"])) and np.array_equal(vel[:, 1:], fmt(case["final_dvdt"]))
+    assert np.array_equal(pres[:, 0], fmt(case["final_eta"])) and np.array_equal(pres[:, 1:], fmt(case["final_detadt"]))
+
+
 def test_restart_run_continues_from_files(odis, tmp_path):
     """initial conditions; LOAD reads InitialConditions/*.txt and uses the 3-level AB3 formula from step 0."""
     case = load_case("l3_full_loaded")
@@ -73,11 +101,11 @@ def test_restart_run_continues_from_files(odis, tmp_path):
 def test_unsupported_configurations_fail_loudly(odis, tmp_path):
     case = load_case("l3_obliqwest_earth")
     d = make_run_dir(tmp_path, case)
-    text = open(os.path.join(d, "input.in")).read().replace("advection; \t false;", "advection; \t true;")
+    text = open(os.path.join(d, "input.in")).read().replace("solver type; \t AB3;", "solver type; \t RK4;")
     open(os.path.join(d, "input.in"), "w").write(text)
     with pytest.raises(odis.OdisError) as e:
         odis.run(d)
-    assert e.value.code == -6 and "advection" in str(e.value)
+    assert e.value.code == -6 and "AB3" in str(e.value)
     assert "TERMINATING ODIS." in open(os.path.join(d, "DATA", "ERROR.txt")).read()
 
 
