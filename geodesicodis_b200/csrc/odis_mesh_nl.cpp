@@ -77,14 +77,45 @@ struct RowAcc {
     void sort() { std::sort(e.begin(), e.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; }); }
 };
 
-void push_row(Csr& A, RowAcc& row, bool prune_zeros) {
-    row.sort();
-    for (auto& p : row.e) {
-        if (prune_zeros && p.second == 0.0) continue;
-        A.indices.push_back(p.first);
-        A.data.push_back(p.second);
+// Rows are independent: chunks of them are filled in parallel into fixed-width buffers (fill(r, row) leaves row r in `row`), then
+// appended in order. max_width bounds the entries of one row.
+template <typename Fill>
+int build_csr(Csr& A, int n_rows, int n_cols, int max_width, bool prune_zeros, Fill fill) {
+    A.n_rows = n_rows; A.n_cols = n_cols;
+    A.indptr.assign(1, 0); A.indices.clear(); A.data.clear();
+    const int chunk = 1 << 18;
+    std::vector<int> cols((size_t)chunk * max_width), cnt((size_t)chunk);
+    std::vector<double> vals((size_t)chunk * max_width);
+    int bad = 0;
+    for (int r0 = 0; r0 < n_rows; r0 += chunk) {
+        const int r1 = std::min(n_rows, r0 + chunk);
+#pragma omp parallel reduction(+ : bad)
+        {
+            RowAcc row;
+#pragma omp for schedule(static)
+            for (int r = r0; r < r1; r++) {
+                row.clear();
+                fill(r, row);
+                row.sort();
+                int k = 0;
+                for (auto& p : row.e) {
+                    if (prune_zeros && p.second == 0.0) continue;
+                    if (k >= max_width) { bad++; break; }
+                    cols[(size_t)(r - r0) * max_width + k] = p.first;
+                    vals[(size_t)(r - r0) * max_width + k] = p.second;
+                    k++;
+                }
+                cnt[(size_t)(r - r0)] = k;
+            }
+        }
+        for (int r = r0; r < r1; r++) {
+            const int k = cnt[(size_t)(r - r0)];
+            A.indices.insert(A.indices.end(), cols.begin() + (size_t)(r - r0) * max_width, cols.begin() + (size_t)(r - r0) * max_width + k);
+            A.data.insert(A.data.end(), vals.begin() + (size_t)(r - r0) * max_width, vals.begin() + (size_t)(r - r0) * max_width + k);
+            A.indptr.push_back((int)A.indices.size());
+        }
     }
-    A.indptr.push_back((int)A.indices.size());
+    return bad;
 }
 
 }  // namespace
@@ -129,22 +160,17 @@ int build_nonlinear_tables(const MeshTables& m, double radius, double rbf_eps, N
     }
 
     // ---- operatorCurl, mesh.cpp:3122-3175
-    {
-        Csr& A = out.curl;
-        A.n_rows = V; A.n_cols = F; A.indptr.assign(1, 0);
-        RowAcc row;
-        for (int v = 0; v < V; v++) {
-            row.clear();
+    for (int v = 0; v < V; v++)
+        for (int j = 0; j < 3; j++)
+            if (out.vertex_faces[(size_t)v * 3 + j] < 0) { err = "vertex with fewer than three edges"; return -2; }
+    if (build_csr(out.curl, V, F, 3, false, [&](int v, RowAcc& row) {
             const double area = out.vertex_area[(size_t)v];
             for (int j = 0; j < 3; j++) {
                 const int e = out.vertex_faces[(size_t)v * 3 + j];
-                if (e < 0) { err = "vertex with fewer than three edges"; return -2; }
                 const double t_ev = out.vertex_face_dir[(size_t)v * 3 + j];
                 row.add(e, m.face_node_dist[(size_t)e] * t_ev / area);
             }
-            push_row(A, row, false);
-        }
-    }
+        })) { err = "operatorCurl row too wide"; return -3; }
 
     // ---- per-cell map coordinates of the neighbours (mesh.cpp:1384-1425), per-edge Cartesian normal (:641) and the
     //      velocity-transform angles between the edge and its two cells (:1335-1382)
@@ -182,46 +208,55 @@ int build_nonlinear_tables(const MeshTables& m, double radius, double rbf_eps, N
 
     // ---- operatorRBFinterp = RBF * (Vinv * node2faceAdj), mesh.cpp:359-432 (per-cell matrix and its inverse), :2263-2361
     {
-        Csr& A = out.rbf_interp;
-        A.n_rows = 3 * N; A.n_cols = F; A.indptr.assign(1, 0);
-        RowAcc row;
-        std::vector<double> mat, phi_nf(6);
-        for (int i = 0; i < N; i++) {
-            const int n = sides(i);
-            mat.assign((size_t)n * n, 0.0);
-            for (int j1 = 0; j1 < n; j1++) {
-                const int fj = m.faces[(size_t)i * 6 + j1];
-                for (int j2 = 0; j2 < n; j2++) {
-                    const int fi = m.faces[(size_t)i * 6 + j2];
-                    const double arc = arc_angle_atan2(face_centre(fj), face_centre(fi));
-                    const double phi = rbf(arc, 1.0);
-                    mat[(size_t)j1 * n + j2] = phi * (normal_xyz[(size_t)fj * 3] * normal_xyz[(size_t)fi * 3] + normal_xyz[(size_t)fj * 3 + 1] * normal_xyz[(size_t)fi * 3 + 1] +
-                                                      normal_xyz[(size_t)fj * 3 + 2] * normal_xyz[(size_t)fi * 3 + 2]);
+        // per cell: the inverse of its RBF-normal matrix (6 x 6 slots) and the node-to-face RBF values
+        std::vector<double> inv_all((size_t)N * 36), phi_all((size_t)N * 6);
+#pragma omp parallel
+        {
+            std::vector<double> mat;
+#pragma omp for schedule(static)
+            for (int i = 0; i < N; i++) {
+                const int n = sides(i);
+                mat.assign((size_t)n * n, 0.0);
+                for (int j1 = 0; j1 < n; j1++) {
+                    const int fj = m.faces[(size_t)i * 6 + j1];
+                    for (int j2 = 0; j2 < n; j2++) {
+                        const int fi = m.faces[(size_t)i * 6 + j2];
+                        const double arc = arc_angle_atan2(face_centre(fj), face_centre(fi));
+                        const double phi = rbf(arc, 1.0);
+                        mat[(size_t)j1 * n + j2] = phi * (normal_xyz[(size_t)fj * 3] * normal_xyz[(size_t)fi * 3] + normal_xyz[(size_t)fj * 3 + 1] * normal_xyz[(size_t)fi * 3 + 1] +
+                                                          normal_xyz[(size_t)fj * 3 + 2] * normal_xyz[(size_t)fi * 3 + 2]);
+                    }
+                    phi_all[(size_t)i * 6 + j1] = rbf(arc_angle_atan2(node(i), face_centre(fj)), 1.0);      // node_face_RBF
                 }
-                phi_nf[(size_t)j1] = rbf(arc_angle_atan2(node(i), face_centre(fj)), 1.0);      // node_face_RBF
+                const std::vector<double> inv = dense_inverse(mat, n);
+                for (int x = 0; x < n; x++)
+                    for (int y = 0; y < n; y++) inv_all[(size_t)i * 36 + (size_t)x * 6 + y] = inv[(size_t)x * n + y];
             }
-            const std::vector<double> inv = dense_inverse(mat, n);
-            for (int c = 0; c < 3; c++) {
-                row.clear();
+        }
+        if (build_csr(out.rbf_interp, 3 * N, F, 6, false, [&](int r, RowAcc& row) {
+                const int i = r / 3, c = r % 3, n = sides(i);
                 for (int x = 0; x < n; x++) {                                      // RBF row entries, ascending slot
-                    const double a = phi_nf[(size_t)x] * normal_xyz[(size_t)m.faces[(size_t)i * 6 + x] * 3 + c];
+                    const double a = phi_all[(size_t)i * 6 + x] * normal_xyz[(size_t)m.faces[(size_t)i * 6 + x] * 3 + c];
                     // (Vinv * adj) row (i, x): one entry per face of the cell, ascending face id
                     RowAcc t;
-                    for (int y = 0; y < n; y++) t.add(m.faces[(size_t)i * 6 + y], inv[(size_t)x * n + y] * 1.0);
+                    for (int y = 0; y < n; y++) t.add(m.faces[(size_t)i * 6 + y], inv_all[(size_t)i * 36 + (size_t)x * 6 + y] * 1.0);
                     t.sort();
                     for (auto& p : t.e) row.add(p.first, a * p.second);
                 }
-                push_row(A, row, false);
-            }
-        }
+            })) { err = "operatorRBFinterp row too wide"; return -3; }
     }
 
     // ---- operatorDirectionalSecondDeriv = N * R * (r^-2 rbfDeriv2 * vandermondeInv * node2nodeAdj), mesh.cpp:280-345, :2364-2719
     {
         const double r_recip = 1.0 / r, s2 = r_recip * r_recip;
         // second-derivative rows (xx, xy, yy) at every cell over the cell and its neighbours
-        std::vector<RowAcc> sd((size_t)3 * N);
-        std::vector<double> mat, nn_rbf(7), x1v(6), y1v(6);
+        // stored as fixed-width rows: [3N][7] (column, value), sorted by column
+        std::vector<int> sd_col((size_t)3 * N * 7, -1);
+        std::vector<double> sd_val((size_t)3 * N * 7, 0.0);
+#pragma omp parallel
+        {
+        std::vector<double> mat, nn_rbf(7);
+#pragma omp for schedule(static)
         for (int i = 0; i < N; i++) {
             const int n = sides(i), n1 = n + 1;
             mat.assign((size_t)n1 * n1, 0.0);
@@ -277,18 +312,20 @@ int build_nonlinear_tables(const MeshTables& m, double radius, double rbf_eps, N
                     }
                 }
                 // ... * node2nodeAdj: slot y -> the cell itself (y = 0) or its y-th neighbour
-                RowAcc& row = sd[(size_t)3 * i + c];
+                RowAcc row;
                 for (int y = 0; y < n1; y++) row.add(y == 0 ? i : m.node_friends[(size_t)i * 6 + y - 1], wv[y] * 1.0);
                 row.sort();
+                for (size_t q = 0; q < row.e.size(); q++) {
+                    sd_col[((size_t)3 * i + c) * 7 + q] = row.e[q].first;
+                    sd_val[((size_t)3 * i + c) * 7 + q] = row.e[q].second;
+                }
             }
         }
-        Csr& A = out.directional_second_deriv;
-        A.n_rows = 2 * F; A.n_cols = N; A.indptr.assign(1, 0);
-        RowAcc row;
-        for (int e = 0; e < F; e++) {
-            const double nx = m.face_normal_vec_map[(size_t)e * 2], ny = m.face_normal_vec_map[(size_t)e * 2 + 1];
-            const double nc[3] = {nx * nx, 2 * nx * ny, ny * ny};                  // N rows, mesh.cpp:2690-2698
-            for (int k = 0; k < 2; k++) {
+        }
+        if (build_csr(out.directional_second_deriv, 2 * F, N, 7, true, [&](int r2, RowAcc& row) {
+                const int e = r2 / 2, k = r2 % 2;
+                const double nx = m.face_normal_vec_map[(size_t)e * 2], ny = m.face_normal_vec_map[(size_t)e * 2 + 1];
+                const double nc[3] = {nx * nx, 2 * nx * ny, ny * ny};              // N rows, mesh.cpp:2690-2698
                 const int cell = m.face_nodes[(size_t)e * 2 + k];
                 const double cosa = vel_trans[(size_t)e * 4 + (size_t)k * 2], sina = vel_trans[(size_t)e * 4 + (size_t)k * 2 + 1];
                 const double R[3][3] = {{cosa * cosa, -2 * cosa * sina, sina * sina},          // mesh.cpp:2585-2680
@@ -300,12 +337,12 @@ int build_nonlinear_tables(const MeshTables& m, double radius, double rbf_eps, N
                     nr[c] += nc[1] * R[1][c];
                     nr[c] += nc[2] * R[2][c];
                 }
-                row.clear();
                 for (int c = 0; c < 3; c++)
-                    for (auto& p : sd[(size_t)3 * cell + c].e) row.add(p.first, nr[c] * p.second);
-                push_row(A, row, true);                                            // prune(0.0), mesh.cpp:2717
-            }
-        }
+                    for (int q = 0; q < 7; q++) {
+                        const int col = sd_col[((size_t)3 * cell + c) * 7 + q];
+                        if (col >= 0) row.add(col, nr[c] * sd_val[((size_t)3 * cell + c) * 7 + q]);
+                    }
+            })) { err = "operatorDirectionalSecondDeriv row too wide"; return -3; }                  // prune(0.0), mesh.cpp:2717
     }
     return 0;
 }

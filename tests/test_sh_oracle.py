@@ -87,3 +87,25 @@ def test_argument_errors(odis):
         odis.sh_basis(pos, 40)
     with pytest.raises(odis.OdisError):
         odis.sh_normal_inverse(pos[:3], 2)          # 3 points cannot fix 9 coefficients
+
+
+def test_c_oracle_term_matches_numpy_restatement(odis):
+    """oracle/lte_oracle.c: self_gravity() (what the GPU parity tests compare with) against oracle/sh_oracle.py computed
+    independently (numpy lstsq instead of the normal-matrix operator): potential 'NONE', so forcing_potential is the term alone."""
+    from oracle.lte_oracle import LteOracle
+    pos, fr, cen = odis.generate_grid(4)
+    r = 1.0e6
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, r)
+    prm = dict(g=1.3, h=1.0e3, alpha=1e-6, dt=5.0, radius=r, omega=2e-5, love_reduct=1.0, ecc=0.0, obl=0.0, shell_thickness=0.0,
+               potential=16, friction=0, surface=0, init_load=0)
+    l_max = 5
+    factor = np.linspace(0.9, 0.1, l_max + 1)
+    Y = so.basis(pos, l_max)
+    o = LteOracle(mesh.tables, prm)
+    o.set_self_gravity(Y, so.apply_operator(Y, factor))
+    eta = np.random.default_rng(9).uniform(-1, 1, mesh.n_cells)
+    o.set_state(eta=eta)
+    o.step(1)                                              # forcing_potential of this step is built from eta as loaded
+    ref = so.self_gravity_potential(Y, factor, prm["g"], eta)
+    got = o.field(6)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
