@@ -236,9 +236,57 @@ int Config::finalize(std::string& err) {
             for (int l = 0; l < l_max + 1; l++) shell_factor_beta[l] = 1.0 - shell_factor_beta[l];
             break;
         }
-        case LID_MEMBR:
-            err = "surface type LID_MEMBR (membrane shell constants) is outside the LTE hot path and not provided";
-            return -7;
+        case LID_MEMBR: {                                                     // :80-110 + membraneNuBeta, membraneConstants.cpp:9-143
+            // Beuthe (2016) membrane shell, Enceladus constants hard-wired in the reference. Besides beta_l and the tidal
+            // prefactor nu_2 it REPLACES g by the gravity at the ocean top and the radius by the ocean-top radius.
+            const double G = 6.67384e-11, pois_ratio = 0.5, rigid_shell = 3.5e9, rigid_core = 40e9;
+            const double shell_thickness = entries_["shell thickness"].d, ocean_thickness = entries_["ocean thickness"].d;
+            const double radius = entries_["radius"].d;
+            const double radius_core = radius - (shell_thickness + ocean_thickness), radius_ocean = radius - (shell_thickness);
+            const double mass_total = 1.08e20, den_ocean = 1000.0, den_shell = 940.0;
+            const double grav_surf = G * mass_total / std::pow(radius, 2.0);
+            const double vol_total = 4. / 3. * kPi * std::pow(radius, 3.0);
+            const double vol_core = 4. / 3. * kPi * std::pow(radius_core, 3.0);
+            const double vol_ocean = 4. / 3. * kPi * std::pow(radius_ocean, 3.0) - vol_core;
+            const double vol_shell = vol_total - 4. / 3. * kPi * std::pow(radius_ocean, 3.0);
+            const double den_bulk = mass_total / vol_total;
+            const double mass_ocean = vol_ocean * den_ocean, mass_shell = vol_shell * den_shell;
+            const double mass_core = mass_total - (mass_ocean + mass_shell);
+            const double den_core = mass_core / vol_core;
+            const double grav_core = G * mass_core / std::pow(radius_core, 2.0);
+            const double grav_ocean = G * (mass_core + mass_ocean) / std::pow(radius_ocean, 2.0);
+            shell_factor_beta.assign((size_t)l_max + 1, 0.0);
+            std::vector<double> nu((size_t)l_max + 1, 0.0);
+            for (int l = 0; l < l_max + 1; l++) {
+                const double rigid_eff = (double)(2 * l * l + 4 * l + 3) / ((double)l) * rigid_core / (den_core * grav_core * radius_core);
+                const double rigid_factor = 1. / (1. + rigid_eff);
+                double kt = rigid_factor * 3. / ((double)(2 * (l - 1)));
+                double ht = rigid_factor * (double)(2 * l + 1) / ((double)(2 * (l - 1)));
+                if (l == 1) { kt = 0.0; ht = 0.0; }
+                const double kl = -rigid_factor;
+                const double hl = -rigid_factor * (double)(2 * l + 1) / 3.0;
+                const double gam_tide = 1.0 + kt - ht;
+                const double gam_load = 1.0 + kl - hl;
+                const double x = (double)((l - 1) * (l + 2));
+                const double bendRigidity = rigid_shell * std::pow(shell_thickness, 3.0) / (6. * (1. - pois_ratio));
+                const double sprMembrane = 2. * x * (1. + pois_ratio) / (x + 1. + pois_ratio) * rigid_shell / (den_ocean * grav_surf * radius) *
+                                           shell_thickness / radius;
+                const double sprBending = std::pow(x, 2.0) * (x + 2.) / (x + 1. + pois_ratio) * bendRigidity /
+                                          (den_ocean * grav_surf * std::pow(radius, 4.0));
+                const double sprConst = sprMembrane + sprBending;
+                const double xi = 3.0 / (2. * (double)l + 1.0) * (den_ocean / den_bulk);
+                double dsprConst = 1. - std::pow((1. + xi * hl), 2.0) / (1. + xi * (ht - hl) * sprConst);
+                dsprConst *= -sprConst;
+                double dgam_tide = (1. + xi * hl) * ht / (1. + xi * (ht - hl) * sprConst);
+                dgam_tide *= -sprConst;
+                shell_factor_beta[(size_t)l] = 1. - xi * gam_load + sprConst + dsprConst;     // beta(l): used as it is (:99), not 1 - beta
+                nu[(size_t)l] = gam_tide + dgam_tide;
+            }
+            entries_["surface gravity"].d = grav_ocean;                       // membraneConstants.cpp:135-136
+            entries_["radius"].d = radius_ocean;
+            if (l_max >= 2) entries_["love reduction factor"].d = nu[2];      // boundaryConditions.cpp:101 reads (*nu)(2)
+            break;
+        }
         case LID_INF:
             break;
     }

@@ -202,6 +202,9 @@ if __name__ == "__main__":
     run_case("l3_advection_shipped", 3, shipped, 150, every_step_dumps=True, full_tables=True, nl_tables=True)
     run_case("l4_advection_loaded", 4, {"advection": "true", "potential": "FULL", "time step": "40", "ocean thickness": "2e3"}, 40,
              every_step_dumps=True, full_tables=False, init_state=random_state(4, 21), nl_tables=True)
+    # (11) Beuthe membrane shell (LID_MEMBR): g, radius and the tidal prefactor are replaced by membraneNuBeta's values
+    run_case("l3_ecc_lidmembr", 3, {"surface type": "LID_MEMBR", "shell thickness": "10e3", "sh degree": "4", "time step": "60",
+                                    "eccentricity": "0.0047"}, 40, every_step_dumps=True, full_tables=False)
     # (10) the shipped input.in VERBATIM (advection true, velocity cartesian output true, ...) except for the grid level (3) and the
     #      end time (1 orbit = 48,100 steps at the shipped 30 s step): the whole-run drop-in check, HDF5 rows included
     verbatim = {}
