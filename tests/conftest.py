@@ -65,7 +65,8 @@ def case_params(case: dict, init_load: int = 0) -> dict:
 
 
 ALL_CASES = ["l3_obliqwest_earth", "l4_ecc_enceladus", "l6_obliqwest_earth", "l3_full_loaded", "l3_obliq_quadratic",
-             "l4_full2_lidlove", "l5_none_loaded", "l3_ecc_full_orbit", "l3_ecc_lidmembr"]
+             "l4_full2_lidlove", "l5_none_loaded", "l3_ecc_full_orbit", "l3_ecc_lidmembr",
+             "l3_obliq_freeloading"]
 
 NL_CASES = ["l3_advection_shipped", "l4_advection_loaded", "l5_advection_ecc"]     # advection; true (nonlinear branch)
 

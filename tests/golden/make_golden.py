@@ -205,6 +205,9 @@ if __name__ == "__main__":
     # (11) Beuthe membrane shell (LID_MEMBR): g, radius and the tidal prefactor are replaced by membraneNuBeta's values
     run_case("l3_ecc_lidmembr", 3, {"surface type": "LID_MEMBR", "shell thickness": "10e3", "sh degree": "4", "time step": "60",
                                     "eccentricity": "0.0047"}, 40, every_step_dumps=True, full_tables=False)
+    # (12) FREE_LOADING: loading Love numbers change the tidal prefactor (boundaryConditions.cpp:29-77)
+    run_case("l3_obliq_freeloading", 3, {"surface type": "FREE_LOADING", "potential": "OBLIQ", "sh degree": "3", "time step": "70"}, 45,
+             every_step_dumps=True, full_tables=False)
     # (10) the shipped input.in VERBATIM (advection true, velocity cartesian output true, ...) except for the grid level (3) and the
     #      end time (1 orbit = 48,100 steps at the shipped 30 s step): the whole-run drop-in check, HDF5 rows included
     verbatim = {}
