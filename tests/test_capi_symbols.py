@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from conftest import ROOT
 
 
@@ -50,3 +52,16 @@ def test_solver_fails_loudly_without_gpu(odis):
         assert e.code == -5 and "no CPU fallback" in str(e)
     else:
         raise AssertionError("odis_create succeeded without a CUDA device")
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/odis_b200.h must compile as C99 (no C++ types leak into the signatures)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "chk.c"
+    src.write_text('#include "odis_b200.h"\nint main(void) { odis_params p; (void)p; return ODIS_OK; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc, "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
