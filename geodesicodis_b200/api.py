@@ -437,6 +437,52 @@ class Solver:
         check(_lib.load().odis_get_dissipation_avg(self._h, C.byref(d)))
         return d.value
 
+    # ---- operator surface: the reference's loop-level free functions, one call each (odis_op_*). Host arrays in
+    # reference numbering; the solver's state is scratch afterwards (call set_state before stepping again). ----
+    def updateMomentum(self, v, eta) -> np.ndarray:
+        """dvdt = -g G eta + C v  (updateMomentum, src/updateMomentum.cpp:42), [F]."""
+        a, b = self._ptr(v, self.F), self._ptr(eta, self.N)
+        out = np.empty(self.F, dtype=np.float64)
+        check(_lib.load().odis_op_update_momentum(self._h, a[1], b[1], out.ctypes.data))
+        return out
+
+    def updateEta(self, v) -> np.ndarray:
+        """detadt = h Div v  (updateEta, src/updateEta.cpp:39), [N]."""
+        a = self._ptr(v, self.F)
+        out = np.empty(self.N, dtype=np.float64)
+        check(_lib.load().odis_op_update_eta(self._h, a[1], out.ctypes.data))
+        return out
+
+    def forcing(self, time: float) -> np.ndarray:
+        """Tidal potential at `time`  (forcing, src/tidalPotentials.cpp:29-328), [N]."""
+        out = np.empty(self.N, dtype=np.float64)
+        check(_lib.load().odis_op_forcing(self._h, float(time), out.ctypes.data))
+        return out
+
+    def integrateAB3scalar(self, solution, dsolution_dt, iter: int):
+        """(solution, dsolution_dt[n][3]) after one Adams-Bashforth update  (src/temporalOperators.cpp:17-68); copies."""
+        sol = np.array(solution, dtype=np.float64, order="C").ravel()
+        hist = np.array(dsolution_dt, dtype=np.float64, order="C")
+        if hist.size != sol.size * 3:
+            raise ValueError("dsolution_dt must be [n][3]")
+        check(_lib.load().odis_op_integrate_ab3_scalar(self._h, sol.ctypes.data, hist.ctypes.data, iter, sol.size))
+        return sol, hist.reshape(sol.size, 3)
+
+    def interpolateVelocity(self, v) -> np.ndarray:
+        """East/north velocity components at the edges  (src/interpolation.cpp:26-62), [F][2]."""
+        a = self._ptr(v, self.F)
+        out = np.empty((self.F, 2), dtype=np.float64)
+        check(_lib.load().odis_op_interpolate_velocity(self._h, a[1], out.ctypes.data))
+        return out
+
+    def updateEnergy(self, v_avg, areas):
+        """(e_flux [F], area-mean flux) from the east/north components and the edge areas  (src/energy.cpp:13-62)."""
+        a, b = self._ptr(v_avg, self.F * 2), self._ptr(areas, self.F)
+        out = np.empty(self.F, dtype=np.float64)
+        avg = C.c_double()
+        check(_lib.load().odis_op_update_energy(self._h, a[1], b[1], out.ctypes.data, C.byref(avg)))
+        return out, avg.value
+
     def dissipation_series(self, first: int = 0, count: int | None = None) -> np.ndarray:
         if count is None:
             count = self.steps_since_state + 1 - first

@@ -1273,6 +1273,130 @@ int odis_get_dissipation_series(odis_solver* s, int64_t first, int64_t count, do
     return ODIS_OK;
 }
 
+// ---- operator surface: the free functions the reference's loop calls (timeIntegrator.cpp:205-313), one call each, on host
+// arrays in reference numbering. Built from the step kernels themselves (an AB3_FIRST launch leaves exactly the operator's
+// result in the tendency slot), so each result is the same arithmetic as inside odis_step. The solver's device state is
+// the scratch space: afterwards odis_step refuses to run until odis_set_state is called again. ----
+static int op_begin(odis_solver* s) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
+    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "operator calls need an unpartitioned solver");
+    if (s->nl_on) return fail(ODIS_ERR_UNSUPPORTED, "operator calls cover the linear branch (advection; false) only");
+    if (s->fused) return fail(ODIS_ERR_UNSUPPORTED, "operator calls need the two-launch step kernels");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    int rc = ensure_series(s, 1);
+    if (rc) return rc;
+    s->have_state = false;          // the state arrays are about to be overwritten
+    s->diag_current = false;
+    s->eta_lag = false;
+    return ODIS_OK;
+}
+static int op_load_velocity(odis_solver* s, const double* v) {
+    ODIS_CUDA(cudaMemcpyAsync(s->d_stage, v, (size_t)s->Fg * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    odis::launch_scatter_x(s->F, s->d_edge_perm, s->d_stage, s->d_vl[s->cur], 0, s->stream);
+    s->launches++;
+    return ODIS_OK;
+}
+static int op_finish(odis_solver* s, double* out, size_t count) {
+    ODIS_CUDA(cudaGetLastError());
+    ODIS_CUDA(cudaMemcpyAsync(out, s->d_stage, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    return ODIS_OK;
+}
+
+int odis_op_update_momentum(odis_solver* s, const double* v, const double* eta, double* dvdt_out) {
+    if (!v || !eta || !dvdt_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    int rc = op_begin(s);
+    if (rc || (rc = op_load_velocity(s, v))) return rc;
+    ODIS_CUDA(cudaMemcpyAsync(s->d_stage, eta, (size_t)s->Ng * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    odis::launch_scatter_x(s->N, s->d_cell_perm, s->d_stage, s->d_eu[s->ecur], 1, s->stream);
+    // one edge update in start-up mode: the tendency -g G eta + C v (updateMomentum.cpp:42) lands in history level 2
+    odis::EdgeState es;
+    es.vl_in = s->d_vl[s->cur]; es.vl_out = s->d_vl[1 - s->cur]; es.eu = s->d_eu[s->ecur];
+    es.h1 = s->d_hv[s->hv1]; es.h2 = s->d_hv[1 - s->hv1];
+    es.block_partial = s->d_block_partial; es.ticket = s->d_ticket;
+    es.energy_out = s->d_series; es.ctl = nullptr; es.series = s->d_series; es.scal = s->d_scal;
+    odis::launch_edge_step(s->edge_tables(), s->phys, es, odis::AB3_FIRST, s->prm.block_threads, s->stream);
+    odis::launch_gather_scalar(s->Fo, s->d_edge_perm, s->d_hv[1 - s->hv1], s->d_stage, s->stream);
+    s->launches += 3;
+    return op_finish(s, dvdt_out, (size_t)s->Fg);
+}
+
+int odis_op_update_eta(odis_solver* s, const double* v, double* detadt_out) {
+    if (!v || !detadt_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    int rc = op_begin(s);
+    if (rc || (rc = op_load_velocity(s, v))) return rc;
+    // one cell update in start-up mode: h Div v (updateEta.cpp:39) lands in the free tendency slot
+    odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
+                       nullptr, 0, nullptr, nullptr};
+    odis::launch_cell_step(s->cell_tables(s->No), s->phys, cs, odis::AB3_FIRST, odis::StepScalars{}, odis::CELL_UPDATE_ETA, s->prm.block_threads,
+                           nullptr, s->stream);
+    odis::launch_gather_scalar(s->No, s->d_cell_perm, s->d_he[s->hefree], s->d_stage, s->stream);
+    s->launches += 2;
+    return op_finish(s, detadt_out, (size_t)s->Ng);
+}
+
+int odis_op_forcing(odis_solver* s, double time, double* potential_out) {
+    if (!potential_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    int rc = op_begin(s);
+    if (rc) return rc;
+    double2* eu = s->d_eu[1 - s->ecur];
+    ODIS_CUDA(cudaMemsetAsync(eu, 0, (size_t)s->Np * sizeof(double2), s->stream));     // potential NONE leaves the array as it was: zeros
+    odis::CellState cs{s->d_vl[s->cur], eu, eu, s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
+    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, time), odis::CELL_UPDATE_U,
+                           s->prm.block_threads, nullptr, s->stream);
+    odis::launch_gather_component(s->No, s->d_cell_perm, eu, 1, s->d_stage, s->stream);
+    s->launches += 2;
+    return op_finish(s, potential_out, (size_t)s->Ng);
+}
+
+int odis_op_integrate_ab3_scalar(odis_solver* s, double* solution, double* dsolution_dt, int64_t iter, int32_t n) {
+    if (!solution || !dsolution_dt) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
+    int rc = op_begin(s);
+    if (rc) return rc;
+    if (n < 0 || n > s->Fg) return fail(ODIS_ERR_ARG, "n must be between 0 and the number of edges");
+    if (n == 0) return ODIS_OK;
+    double* d_sol = s->d_ediss;        // [F]
+    double* d_hist = s->d_stage;       // [3F]
+    ODIS_CUDA(cudaMemcpyAsync(d_sol, solution, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    ODIS_CUDA(cudaMemcpyAsync(d_hist, dsolution_dt, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    odis::launch_ab3_scalar(n, d_sol, d_hist, s->prm.dt, ab3_mode(s, iter), s->stream);
+    s->launches++;
+    ODIS_CUDA(cudaGetLastError());
+    ODIS_CUDA(cudaMemcpyAsync(solution, d_sol, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return op_finish(s, dsolution_dt, (size_t)n * 3);
+}
+
+int odis_op_interpolate_velocity(odis_solver* s, const double* v, double* v_avg_out) {
+    if (!v || !v_avg_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    int rc = op_begin(s);
+    if (rc || (rc = op_load_velocity(s, v))) return rc;
+    odis::launch_edge_diagnostics(s->edge_tables(), s->phys, s->d_vl[s->cur], s->d_normal, s->d_vavg, s->d_ediss, s->d_block_partial, s->d_ticket,
+                                  s->d_series, s->prm.block_threads, s->stream);
+    odis::launch_gather_pair(s->Fo, s->d_edge_perm, s->d_vavg, s->d_stage, s->stream);
+    s->launches += 2;
+    return op_finish(s, v_avg_out, (size_t)s->Fg * 2);
+}
+
+int odis_op_update_energy(odis_solver* s, const double* v_avg, const double* areas, double* e_flux_out, double* avg_flux_out) {
+    if (!v_avg || !areas || !e_flux_out || !avg_flux_out) return fail(ODIS_ERR_ARG, "NULL argument");
+    int rc = op_begin(s);
+    if (rc) return rc;
+    const size_t F = (size_t)s->Fg;
+    ODIS_CUDA(cudaMemcpyAsync(s->d_stage, v_avg, 2 * F * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    ODIS_CUDA(cudaMemcpyAsync(s->d_stage + 2 * F, areas, F * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    odis::launch_energy_from_components(s->Fg, s->phys, s->d_stage, s->d_stage + 2 * F, s->d_ediss, s->d_block_partial, s->d_ticket, s->d_series,
+                                        s->stream);
+    s->launches++;
+    ODIS_CUDA(cudaGetLastError());
+    double sum = 0.0;
+    ODIS_CUDA(cudaMemcpyAsync(e_flux_out, s->d_ediss, F * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ODIS_CUDA(cudaMemcpyAsync(&sum, s->d_series, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    *avg_flux_out = sum / sphere_area(s);        // energy.cpp:60
+    return ODIS_OK;
+}
+
 int odis_get_iter(odis_solver* s, int64_t* iter_out) {
     if (!s || !iter_out) return fail(ODIS_ERR_ARG, "NULL argument");
     *iter_out = s->iter;

@@ -459,6 +459,37 @@ __global__ void gather_history_kernel(int n, const int* __restrict__ perm, const
     dst3[o + 2] = a2;
 }
 
+// ---- operator surface (odis_op_*, odis_engine.cu): the two loop-level functions of the reference that no step kernel
+// covers on their own. Both work on reference-ordered arrays staged on the device. ----
+// integrateAB3scalar (temporalOperators.cpp:17-68): the solution and its [n][3] tendency history, updated in place
+__global__ void ab3_scalar_kernel(int n, double* __restrict__ sol, double* __restrict__ hist, double dt, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t o = (size_t)i * 3;
+    const double f0 = hist[o], f1 = hist[o + 1], f2 = hist[o + 2];
+    sol[i] += ab3_increment(f0, f1, f2, dt, mode);
+    if (mode == AB3_FULL) { hist[o + 2] = f1; hist[o + 1] = f0; }      // :44-45
+    else if (mode == AB3_FIRST) hist[o + 2] = f0;                       // :55
+    else hist[o + 1] = f0;                                              // :64
+}
+// updateEnergy (energy.cpp:13-62) from the east/north components [F][2] and the edge areas [F]
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) energy_from_components_kernel(int n, Physics p, const double* __restrict__ vel2,
+                                                                          const double* __restrict__ areas, double* __restrict__ e_flux,
+                                                                          double* block_partial, unsigned int* ticket, double* energy_out) {
+    const int e = blockIdx.x * kThreads + threadIdx.x;
+    double e_area = 0.0;
+    if (e < n) {
+        const double u = vel2[(size_t)e * 2], v = vel2[(size_t)e * 2 + 1];
+        double eps;
+        if (p.friction == 0) eps = p.alpha * 1000.0 * p.h * (u * u + v * v);            // energy.cpp:34
+        else eps = p.alpha / p.h * sqrt(u * u + v * v) * (u * u + v * v);                // energy.cpp:48-49
+        e_flux[e] = eps;
+        e_area = eps * areas[e];                                                          // energy.cpp:36,51
+    }
+    block_sum_and_publish<kThreads>(e_area, block_partial, ticket, energy_out);
+}
+
 template <typename F>
 void dispatch_threads(int block_threads, F&& f) {
     switch (block_threads) {
@@ -533,5 +564,14 @@ void launch_gather_history(int n, const int* perm, const double* lvl0_new, const
                            double* dst_ref3, cudaStream_t stream) {
     gather_history_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, lvl0_new, h1_new, h2_new, which0, dst_ref3);
 }
+
+void launch_ab3_scalar(int n, double* sol, double* hist3, double dt, int mode, cudaStream_t stream) {
+    if (n > 0) ab3_scalar_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sol, hist3, dt, mode);
+}
+void launch_energy_from_components(int n, const Physics& p, const double* vel2, const double* areas, double* e_flux, double* block_partial,
+                                   unsigned int* ticket, double* energy_out, cudaStream_t stream) {
+    energy_from_components_kernel<128><<<(n + 127) / 128, 128, 0, stream>>>(n, p, vel2, areas, e_flux, block_partial, ticket, energy_out);
+}
+
 
 }  // namespace odis

@@ -225,4 +225,12 @@ void launch_gather_scalar(int n, const int* perm, const double* src_new, double*
 void launch_gather_history(int n, const int* perm, const double* lvl0_new, const double* h1_new, const double* h2_new, int which0,
                            double* dst_ref3, cudaStream_t stream);
 
+// ---- operator surface (odis_op_*): reference-ordered arrays staged on the device ----
+// integrateAB3scalar (temporalOperators.cpp:17-68) in place on sol[n] and hist3[n][3]
+void launch_ab3_scalar(int n, double* sol, double* hist3, double dt, int mode, cudaStream_t stream);
+// updateEnergy (energy.cpp:13-62): e_flux[n] from vel2[n][2]; energy_out = sum e_flux*areas (block tree; block_partial needs
+// ceil(n/128) entries)
+void launch_energy_from_components(int n, const Physics& p, const double* vel2, const double* areas, double* e_flux, double* block_partial,
+                                   unsigned int* ticket, double* energy_out, cudaStream_t stream);
+
 }  // namespace odis

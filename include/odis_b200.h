@@ -268,6 +268,26 @@ int odis_get_dissipation_avg(odis_solver* s, double* out);
 /* Per-step series of the same quantity counted from the last odis_set_state: entry j (first <= j <
  * first+count) is the value for the state after j steps, j = 0 being the state as set. */
 int odis_get_dissipation_series(odis_solver* s, int64_t first, int64_t count, double* out);
+/* operators — the free functions the reference's loop calls (src/timeIntegrator.cpp:205-313), one call each, for a caller
+ * that keeps the reference's own ab3Explicit and swaps single functions (integration/operators_b200.cpp holds the wrappers
+ * with the reference's C++ signatures). Host arrays, reference numbering; each call copies its arguments to the device, runs
+ * the same kernels odis_step runs (so the arithmetic is identical) and copies the result back. Linear branch
+ * (`advection; false`), unpartitioned solver. The solver's device state is used as scratch space: after any odis_op_* call
+ * odis_step / odis_get_* return ODIS_ERR_STATE until odis_set_state is called again.
+ *   odis_op_update_momentum      updateMomentum, src/updateMomentum.cpp:16-47 (:42): dvdt = -g G eta + C v           [F]
+ *   odis_op_update_eta           updateEta, src/updateEta.cpp:7-44 (:39): detadt = h Div v                             [N]
+ *   odis_op_forcing              forcing, src/tidalPotentials.cpp:29-328: tidal potential at `time` (the solver's potential type) [N]
+ *   odis_op_integrate_ab3_scalar integrateAB3scalar, src/temporalOperators.cpp:17-68: solution[n] and dsolution_dt[n][3] in place,
+ *                                n <= number of edges; `iter` selects the start-up formulas (:36,:49,:59)
+ *   odis_op_interpolate_velocity interpolateVelocity, src/interpolation.cpp:26-62: east/north components                [F][2]
+ *   odis_op_update_energy        updateEnergy, src/energy.cpp:13-62: e_flux [F] and the area-mean flux from v_avg [F][2] and
+ *                                the edge areas [F] (grid->face_area) */
+int odis_op_update_momentum(odis_solver* s, const double* v, const double* eta, double* dvdt_out);
+int odis_op_update_eta(odis_solver* s, const double* v, double* detadt_out);
+int odis_op_forcing(odis_solver* s, double time, double* potential_out);
+int odis_op_integrate_ab3_scalar(odis_solver* s, double* solution, double* dsolution_dt, int64_t iter, int32_t n);
+int odis_op_interpolate_velocity(odis_solver* s, const double* v, double* v_avg_out);
+int odis_op_update_energy(odis_solver* s, const double* v_avg, const double* areas, double* e_flux_out, double* avg_flux_out);
 int odis_get_iter(odis_solver* s, int64_t* iter_out);
 /* Bytes of device memory held, and the algorithmic HBM bytes one step moves. */
 int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* algorithmic_bytes_per_step_out);

@@ -542,3 +542,23 @@ void oracle_get_operator(const oracle_ctx* c, int which, int* nr, int* nc, const
     const csr* A = which == 0 ? &c->grad : which == 1 ? &c->div : which == 2 ? &c->cor : &c->drag;
     *nr = A->nr; *nc = A->nc; *ptr = A->ptr; *idx = A->idx; *val = A->val;
 }
+
+/* The loop-level functions one at a time, on caller arrays (parity checks of the odis_op_* entry points). Same routines
+ * oracle_step runs, so they are pinned through it (tests/test_oracle_pinned.py::test_operator_calls_compose_to_a_step). */
+void oracle_op_update_momentum(oracle_ctx* c, const double* v, const double* eta, double* dvdt) {   /* updateMomentum.cpp:42 */
+    spmv_scaled_assign(&c->grad, -c->p.g * (1 - 0.5 * 0), eta, dvdt);
+    spmv_add(&c->cor, v, dvdt);
+}
+void oracle_op_update_eta(oracle_ctx* c, const double* v, double* detadt) { spmv_scaled_assign(&c->div, c->p.h, v, detadt); }   /* updateEta.cpp:39 */
+void oracle_op_forcing(oracle_ctx* c, double time, double* potential) { forcing(c, potential, time); }
+void oracle_op_drag_forcing(oracle_ctx* c, const double* v, const double* potential, double* drag_term) {   /* timeIntegrator.cpp:219 */
+    spmv_assign(&c->drag, v, drag_term);
+    spmv_add(&c->grad, potential, drag_term);
+}
+void oracle_op_integrate_ab3_scalar(const oracle_ctx* c, double* s, double* ds_dt, long iter, int num) { integrateAB3scalar(c, s, ds_dt, iter, num); }
+void oracle_op_interpolate_velocity(const oracle_ctx* c, const double* v, double* v_avg) { interpolateVelocity(c, v_avg, v); }
+double oracle_op_update_energy(const oracle_ctx* c, const double* v_avg, const double* areas, double* e_flux) {
+    double avg = 0.0;
+    updateEnergy(c, &avg, e_flux, v_avg, areas);
+    return avg;
+}

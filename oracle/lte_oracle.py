@@ -46,6 +46,14 @@ def _load():
         lib.oracle_set_nonlinear.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 14
         lib.oracle_get_iter.restype = C.c_long
         lib.oracle_get_iter.argtypes = [C.c_void_p]
+        lib.oracle_op_update_momentum.argtypes = [C.c_void_p] * 4
+        lib.oracle_op_update_eta.argtypes = [C.c_void_p] * 3
+        lib.oracle_op_forcing.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        lib.oracle_op_drag_forcing.argtypes = [C.c_void_p] * 4
+        lib.oracle_op_integrate_ab3_scalar.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+        lib.oracle_op_interpolate_velocity.argtypes = [C.c_void_p] * 3
+        lib.oracle_op_update_energy.restype = C.c_double
+        lib.oracle_op_update_energy.argtypes = [C.c_void_p] * 4
         _lib = lib
     return _lib
 
@@ -128,3 +136,46 @@ class LteOracle:
     @property
     def iter(self) -> int:
         return int(_load().oracle_get_iter(self._h))
+
+    # ---- the loop-level functions one at a time (checkers of the odis_op_* entry points) ----
+    def updateMomentum(self, v, eta) -> np.ndarray:
+        a, b = self._ptr(v, self.F), self._ptr(eta, self.N)
+        out = np.zeros(self.F)
+        _load().oracle_op_update_momentum(self._h, a[1], b[1], out.ctypes.data)
+        return out
+
+    def updateEta(self, v) -> np.ndarray:
+        a = self._ptr(v, self.F)
+        out = np.zeros(self.N)
+        _load().oracle_op_update_eta(self._h, a[1], out.ctypes.data)
+        return out
+
+    def forcing(self, time: float) -> np.ndarray:
+        out = np.zeros(self.N)
+        _load().oracle_op_forcing(self._h, float(time), out.ctypes.data)
+        return out
+
+    def dragForcing(self, v, potential) -> np.ndarray:
+        a, b = self._ptr(v, self.F), self._ptr(potential, self.N)
+        out = np.zeros(self.F)
+        _load().oracle_op_drag_forcing(self._h, a[1], b[1], out.ctypes.data)
+        return out
+
+    def integrateAB3scalar(self, solution, dsolution_dt, iter: int):
+        sol = np.array(solution, dtype=np.float64, order="C").ravel()
+        hist = np.array(dsolution_dt, dtype=np.float64, order="C")
+        assert hist.size == 3 * sol.size
+        _load().oracle_op_integrate_ab3_scalar(self._h, sol.ctypes.data, hist.ctypes.data, iter, sol.size)
+        return sol, hist.reshape(sol.size, 3)
+
+    def interpolateVelocity(self, v) -> np.ndarray:
+        a = self._ptr(v, self.F)
+        out = np.zeros((self.F, 2))
+        _load().oracle_op_interpolate_velocity(self._h, a[1], out.ctypes.data)
+        return out
+
+    def updateEnergy(self, v_avg, areas):
+        a, b = self._ptr(v_avg, self.F * 2), self._ptr(areas, self.F)
+        out = np.zeros(self.F)
+        avg = _load().oracle_op_update_energy(self._h, a[1], b[1], out.ctypes.data)
+        return out, float(avg)

@@ -205,6 +205,10 @@ public:
     int nonZeros() const { flush(); return (int)idx.size(); }
     template <typename T> void reserve(const T&) {}
     void makeCompressed() { flush(); }
+    // compressed-storage accessors of Eigen::SparseMatrix (what integration/*.cpp hands to the C ABI)
+    const int* outerIndexPtr() const { flush(); return ptr.data(); }
+    const int* innerIndexPtr() const { flush(); return idx.data(); }
+    const S* valuePtr() const { flush(); return val.data(); }
 
     void buildFrom(std::vector<Triplet<S>>& t) {
         // stable by (row, col); duplicates summed in input order

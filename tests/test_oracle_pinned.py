@@ -75,3 +75,28 @@ def test_dumped_fields_match(odis, tmp_path):
     assert np.array_equal(o.field(4), case["dump_velocity_en"][-1])
     # and the float32 rows the reference handed to HDF5
     assert np.array_equal(o.field(1).astype(np.float32), case["h5_displacement"][last - 1] if case["h5_displacement"].shape[0] >= last else o.field(1).astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["l3_obliqwest_earth", "l3_full_loaded", "l3_obliq_quadratic"])
+def test_operator_calls_compose_to_a_step(odis, tmp_path, name):
+    """The oracle's loop-level functions called one by one (the checkers of the odis_op_* entry points) in the order of
+    timeIntegrator.cpp:205-277 reproduce the reference's final state bit for bit."""
+    case = load_case(name)
+    mesh, o = oracle_for(odis, tmp_path, case)
+    prm = case_params(case)
+    dt = prm["dt"]
+    v, eta, dv, de = o.field(0), o.field(1), o.field(2), o.field(3)
+    it = 0
+    for _ in range(int(case["nsteps"])):
+        dv[:, 0] = o.updateMomentum(v, eta)
+        drag = o.dragForcing(v, o.forcing(dt * it + dt))
+        v, dv = o.integrateAB3scalar(v, dv, it)              # start-up formulas unless the case was loaded (INIT_LOAD)
+        v = v + dt * drag
+        de[:, 0] = o.updateEta(v)
+        eta, de = o.integrateAB3scalar(eta, de, it)
+        it += 1
+    assert np.array_equal(v, case["final_v"]) and np.array_equal(eta, case["final_eta"])
+    assert np.array_equal(dv, case["final_dvdt"]) and np.array_equal(de, case["final_detadt"])
+    v_avg = o.interpolateVelocity(v)
+    e_flux, avg = o.updateEnergy(v_avg, mesh.tables["face_area"])
+    assert avg == case["dump_dissipation_avg"][-1]
