@@ -120,6 +120,16 @@ struct odis_solver {
     double* d_shRec = nullptr;
     double *d_shY = nullptr, *d_shGinv = nullptr, *d_shFactor = nullptr, *d_sh_partial = nullptr, *d_sh_b = nullptr, *d_sh_s = nullptr;
     std::vector<double> sh_ginv_host;
+    // 3-launch variant (params.reserved[0] bit 4): harmonic analysis folded into the cell update, solve folded into the synthesis
+    bool sh_fused_req = false, sh_fused = false;
+    double *d_sg_cta = nullptr, *d_sg_group = nullptr;
+    unsigned int* d_sg_ticket = nullptr;
+    int sg_cta_stride = 0, sg_group_stride = 0;
+    odis::CellSgWork sg_work() const {
+        return odis::CellSgWork{sh_lmax, No, d_sg_cta, sg_cta_stride, d_sg_group, sg_group_stride, d_sg_ticket};
+    }
+    int sg_groups() const { return (odis::cell_sg_ctas(No) + odis::kCellSgGroup - 1) / odis::kCellSgGroup; }
+    int sh_step_launches() const { return !sh_on ? 0 : (sh_fused ? 1 : sh_launches()); }     // per time step, after the cell update
     unsigned char* d_sh_xblock = nullptr;             // partitioned: this rank's exchange block (odis_sh.cuh), mapped by every other rank
     unsigned long long* d_sh_xctl = nullptr;
     unsigned char* sh_xremote[odis::kShMaxWorld] = {nullptr};
@@ -325,6 +335,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->pipe_cell = (prm->reserved[0] & 2) != 0;
     s->fused = (prm->reserved[0] & 4) != 0;
     s->use_graph = (prm->reserved[0] & 8) == 0;
+    s->sh_fused_req = (prm->reserved[0] & 16) != 0;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -783,6 +794,20 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
         return rc;
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_b, 0, (size_t)rows * sizeof(double), s->stream));
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_s, 0, (size_t)rows * sizeof(double), s->stream));
+    if (s->sh_fused_req) {
+        if (s->world > 1 || s->sh_stored || s->pipe_cell || !odis::cell_sg_supports(l_max))
+            return fail(ODIS_ERR_UNSUPPORTED, "the 3-launch self-gravity variant needs an unpartitioned solver, the matrix-free basis, the direct cell kernel and sh degree <= 4");
+        ODIS_CUDA(odis::cell_sg_configure());
+        s->sg_cta_stride = (odis::cell_sg_ctas(s->No) + 31) / 32 * 32;
+        s->sg_group_stride = (s->sg_groups() + 31) / 32 * 32;
+        if ((rc = dev_alloc(s, &s->d_sg_cta, (size_t)rows * s->sg_cta_stride)) || (rc = dev_alloc(s, &s->d_sg_group, (size_t)rows * s->sg_group_stride)) ||
+            (rc = dev_alloc(s, &s->d_sg_ticket, (size_t)s->sg_group_stride)))
+            return rc;
+        ODIS_CUDA(cudaMemsetAsync(s->d_sg_cta, 0, (size_t)rows * s->sg_cta_stride * sizeof(double), s->stream));
+        ODIS_CUDA(cudaMemsetAsync(s->d_sg_group, 0, (size_t)rows * s->sg_group_stride * sizeof(double), s->stream));
+        ODIS_CUDA(cudaMemsetAsync(s->d_sg_ticket, 0, (size_t)s->sg_group_stride * sizeof(unsigned int), s->stream));
+        s->sh_fused = true;
+    }
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);     // captured without the extra launches
     s->graphs.clear();
@@ -1056,6 +1081,9 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     if (s->pipe_cell) {
         if (inline_e) { int rc2 = halo_drain(s); if (rc2) return rc2; }
         ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, s->stream));
+    } else if (s->sh_on && s->sh_fused) {
+        // 3-launch variant: the cell update leaves the harmonic sums of eta^{n+1} over groups of its CTAs
+        odis::launch_cell_step_sg(ct, s->phys, cs, mode, next, s->sg_work(), s->stream);
     } else {
         odis::HaloInline hc;
         if (inline_e) hc = halo_inline_cell(s);
@@ -1065,12 +1093,15 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
-    { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
+    if (s->sh_on && s->sh_fused)
+        odis::launch_sh_solve_synthesis(s->sh_tables(), s->sh_work(), s->d_sg_group, s->sg_group_stride, s->sg_groups(), s->prm.g, s->d_eu[s->ecur], s->N,
+                                        s->stream);
+    else { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 3], s->stream);
     s->cur = 1 - s->cur;
     s->iter++;
     s->last_mode = mode;
-    s->launches += 2 + s->sh_launches();
+    s->launches += 2 + s->sh_step_launches();
     return ODIS_OK;
 }
 
@@ -1153,7 +1184,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             for (int r = 0; r < reps; r++) ODIS_CUDA(cudaGraphLaunch(it->second, s->stream));
             const int adv = reps * kGraphSteps;
             s->graph_launches += reps;
-            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0) + s->sh_launches());
+            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0) + s->sh_step_launches());
             s->iter += adv;
             s->last_mode = odis::AB3_FULL;
             done += adv;
@@ -1453,7 +1484,8 @@ void odis_destroy(odis_solver* s) {
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,
-                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket, s->d_shY, s->d_shRec, s->d_shGinv, s->d_shFactor, s->d_sh_partial, s->d_sh_b, s->d_sh_s, s->d_sh_xblock, s->d_sh_xctl};
+                    s->d_send_c_peer, s->d_flags, s->d_halo_ticket, s->d_shY, s->d_shRec, s->d_shGinv, s->d_shFactor, s->d_sh_partial, s->d_sh_b, s->d_sh_s, s->d_sh_xblock, s->d_sh_xctl,
+                    s->d_sg_cta, s->d_sg_group, s->d_sg_ticket};
     for (int k = 0; k < kMaxPeers; k++)
         for (int j = 0; j < 5; j++)
             if (s->ipc_opened[k][j]) cudaIpcCloseMemHandle(s->ipc_opened[k][j]);

@@ -1,5 +1,6 @@
 // LTE time-step kernels (see odis_kernels.cuh for the mapping onto the reference functions).
 #include "odis_kernels.cuh"
+#include "odis_sh.cuh"
 
 namespace odis {
 
@@ -340,6 +341,135 @@ __global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physi
     }
 }
 
+// ---- cell update with the harmonic analysis of eta^{n+1} folded in (self-gravity term, opt-in variant) ----
+// Recurrence coefficients of the normalised Legendre functions, this translation unit's copy (layout of sh_recurrence_table()).
+__constant__ double c_sg_rec[kShRecDoubles];
+struct SgRec {
+    __device__ __forceinline__ double a(int m, int l) const { return c_sg_rec[l * kShRecStride + m]; }
+    __device__ __forceinline__ double b(int m, int l) const { return c_sg_rec[kShRecStride * kShRecStride + l * kShRecStride + m]; }
+    __device__ __forceinline__ double sect(int m) const { return c_sg_rec[2 * kShRecStride * kShRecStride + m]; }
+    __device__ __forceinline__ double first(int m) const { return c_sg_rec[2 * kShRecStride * kShRecStride + kShRecStride + m]; }
+};
+__device__ __forceinline__ double warp_sum_all(double x) {      // butterfly: fixed association, every lane gets the sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// cell_step_kernel (unpartitioned, eta and potential both updated) + b_k += Y_k(i) eta_i^{n+1} for the cells [0, n_fit):
+// the basis values of the cell are rebuilt from (cos lat, sin lat, cos lon, sin lon) exactly as sh_analysis_mf_kernel does
+// (odis_sh.cu); each warp reduces its 32 cells, the CTA leaves one partial per basis row, and the LAST CTA of every group of
+// kCellSgGroup consecutive CTAs to finish adds the group's partials in CTA order. Sums are therefore independent of the
+// order in which CTAs run. sh_solve_synthesis (odis_sh.cu) finishes the sum over the groups.
+template <int kThreads, int LT>
+__global__ void __launch_bounds__(kThreads) cell_step_sg_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next, CellSgWork sg) {
+    constexpr int kRows = (LT + 1) * (LT + 1);
+    constexpr int kWarps = kThreads / 32;
+    static_assert(kRows <= kThreads, "one thread per basis row writes the CTA partial");
+    __shared__ double red[kRows * kWarps];
+    __shared__ bool group_last;
+    if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
+        block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = t.n_cells;
+    const bool active = i < t.n_active;
+    const int at = i < N ? i : N - 1;                   // padded rows of the trig table hold zeros: finite basis, e = 0
+    // ---- phase A: independent loads ----
+    int packed[kCellEdges];
+#pragma unroll
+    for (int j = 0; j < kCellEdges; j++) packed[j] = active ? ld_stream(t.eid + (size_t)j * N + i) : -1;
+    double2 st = active ? ld_gather(s.eu_in + i) : make_double2(0.0, 0.0);
+    const double area = active ? ld_stream(t.area + i) : 1.0;
+    const double f1 = active ? ld_plain(s.h1 + i) : 0.0, f2 = active ? ld_plain(s.h2 + i) : 0.0;
+    TrigValues tv = load_trig(t, active ? p.potential : (int)P_NONE, at);
+    const double bu = t.trig[at], bz = t.trig[(size_t)N + at], bc1 = t.trig[2 * (size_t)N + at], bs1 = t.trig[3 * (size_t)N + at];
+    if (s.next_dev != nullptr) {                         // graph replay: this step's time factors were left by the edge kernel
+        next.cosM = ld_plain(&s.next_dev->cosM);
+        next.sinM = ld_plain(&s.next_dev->sinM);
+        if (p.potential == P_FULL2) {
+            next.cos2M = ld_plain(&s.next_dev->cos2M); next.sin2M = ld_plain(&s.next_dev->sin2M);
+            next.cos3M = ld_plain(&s.next_dev->cos3M); next.cos4M = ld_plain(&s.next_dev->cos4M);
+        }
+    }
+    // ---- phase B: gathers ----
+    double2 ed[kCellEdges];
+#pragma unroll
+    for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+    // ---- phase C: as cell_step_kernel ----
+    if (active) {
+        double div = 0.0;
+        const double ra = __drcp_rn(area);
+#pragma unroll
+        for (int j = 0; j < kCellEdges; j++) {
+            if (packed[j] != -1) {
+                const double ndir = (packed[j] < 0) ? 1.0 : -1.0;
+                const double coeff = exact_div(ndir * ed[j].y, area, ra);
+                div += (p.h * coeff) * ed[j].x;
+            }
+        }
+        const double f0 = div;
+        st.x += ab3_increment(f0, f1, f2, p.dt, mode);
+        s.hw[i] = f0;
+        if (p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
+        s.eu_out[i] = st;
+    }
+    // ---- phase D: this cell's share of b = Y eta^{n+1} ----
+    {
+        const SgRec rc;
+        const double e = (active && i < sg.n_fit) ? st.x : 0.0;
+        double cm = 1.0, sn = 0.0, pmm = 1.0;
+#pragma unroll
+        for (int m = 0; m <= LT; m++) {
+            if (m > 0) {
+                const double cn = __fma_rn(cm, bc1, -(sn * bs1));       // cos(m lon), sin(m lon) by rotation
+                sn = __fma_rn(sn, bc1, cm * bs1);
+                cm = cn;
+                pmm = rc.sect(m) * bu * pmm;
+            }
+            const double ec = e * cm, es = e * sn;
+            double p1 = pmm, p2 = 0.0;
+#pragma unroll
+            for (int l = m; l <= LT; l++) {
+                if (l > m) {
+                    const double a = l == m + 1 ? rc.first(m) : rc.a(m, l);
+                    const double b = l == m + 1 ? 0.0 : rc.b(m, l);
+                    const double pn = a * __fma_rn(bz, p1, -(b * p2));
+                    p2 = p1; p1 = pn;
+                }
+                const int row = l * l + (m ? 2 * m - 1 : 0);
+                const double pc = warp_sum_all(p1 * ec);
+                if (lane == 0) red[row * kWarps + warp] = pc;
+                if (m > 0) {
+                    const double ps = warp_sum_all(p1 * es);
+                    if (lane == 0) red[(row + 1) * kWarps + warp] = ps;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kRows) {
+        double a = red[threadIdx.x * kWarps];
+#pragma unroll
+        for (int q = 1; q < kWarps; q++) a = a + red[threadIdx.x * kWarps + q];
+        sg.cta_partial[(size_t)threadIdx.x * sg.cta_stride + blockIdx.x] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    const int group = blockIdx.x / kCellSgGroup;
+    const int members = min(kCellSgGroup, (int)gridDim.x - group * kCellSgGroup);
+    if (threadIdx.x == 0) group_last = atomicAdd(sg.group_ticket + group, 1u) == (unsigned int)(members - 1);
+    __syncthreads();
+    if (!group_last) return;
+    __threadfence();
+    for (int k = warp; k < kRows; k += kWarps) {
+        const double v = lane < members ? __ldcg(sg.cta_partial + (size_t)k * sg.cta_stride + group * kCellSgGroup + lane) : 0.0;
+        const double tot = warp_sum_all(v);
+        if (lane == 0) sg.group_partial[(size_t)k * sg.group_stride + group] = tot;
+    }
+    if (threadIdx.x == 0) sg.group_ticket[group] = 0u;
+}
+
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads) edge_diag_kernel(EdgeTables t, Physics p, const double2* vl, const double2* normal,
                                                              double2* v_avg, double* energy_diss, double* block_partial,
@@ -523,6 +653,22 @@ void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s,
         constexpr int kT = decltype(bt)::value;
         cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
     });
+}
+cudaError_t cell_sg_configure() {
+    double rec[kShRecDoubles];
+    sh_recurrence_table(rec);
+    return cudaMemcpyToSymbol(c_sg_rec, rec, sizeof rec);
+}
+int cell_sg_ctas(int n_active) { return (n_active + kCellSgThreads - 1) / kCellSgThreads; }
+bool cell_sg_supports(int l_max) { return l_max >= 2 && l_max <= kCellSgMaxDegree; }
+void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
+                         cudaStream_t stream) {
+    const int grid = cell_sg_ctas(t.n_active);
+    switch (sg.l_max) {
+        case 2: cell_step_sg_kernel<kCellSgThreads, 2><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+        case 3: cell_step_sg_kernel<kCellSgThreads, 3><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+        default: cell_step_sg_kernel<kCellSgThreads, 4><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+    }
 }
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream) {
     halo_drain_kernel<<<1, 32, 0, stream>>>(wait_v, ctl);

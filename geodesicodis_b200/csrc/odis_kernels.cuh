@@ -144,6 +144,27 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
 // flags: CellFlags (update eta and/or the potential)
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                       int flags, int block_threads, const HaloInline* halo, cudaStream_t stream);
+// Opt-in variant for runs with the self-gravity term (odis_params.reserved[0] bit 4): the cell update also accumulates the
+// harmonic analysis b = Y eta^{n+1} of the cells [0, n_fit) (matrix-free basis, degrees 2..kCellSgMaxDegree), leaving sums over
+// groups of kCellSgGroup consecutive CTAs; launch_sh_solve_synthesis (odis_sh.cuh) finishes the sum, solves and adds the term
+// to the potential: 3 launches per step instead of 5. Unpartitioned solvers.
+constexpr int kCellSgThreads = 128;
+constexpr int kCellSgGroup = 32;
+constexpr int kCellSgMaxDegree = 4;
+struct CellSgWork {
+    int l_max;
+    int n_fit;                      // cells [0, n_fit) enter the least-squares fit
+    double* cta_partial;            // [rows][cta_stride]
+    int cta_stride;                 // >= cell_sg_ctas(n_active)
+    double* group_partial;          // [rows][group_stride]
+    int group_stride;               // >= ceil(cell_sg_ctas / kCellSgGroup)
+    unsigned int* group_ticket;     // [group_stride], zero before the first launch (each launch leaves it zero again)
+};
+cudaError_t cell_sg_configure();    // recurrence coefficients -> constant memory (once per device, before any capture)
+int cell_sg_ctas(int n_active);
+bool cell_sg_supports(int l_max);
+void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
+                         cudaStream_t stream);
 // spins (bounded by kHaloSpinCycles) until every neighbour's flag has reached ctl->epoch[0]: all pushes of the
 // exchanges this rank took part in have landed
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream);

@@ -392,6 +392,39 @@ __global__ void __launch_bounds__(kShThreads) sh_synthesis_mf_kernel(ShTables t,
     if (i < n_cells) eu[i].y = u0 + acc;
 }
 
+// Second half of the 3-launch variant (cell_step_sg_kernel, odis_kernels.cu, leaves sums over groups of CTAs): persistent
+// CTAs; each one finishes b = sum over the groups (group order, lane-strided partial sums + butterfly: the same bits in every
+// CTA), solves s = g factor (Ginv b) in shared memory and adds the term to the potential of its cells.
+template <int LT>
+__global__ void __launch_bounds__(kShThreads) sh_solve_synthesis_mf_kernel(ShTables t, ShWork w, const double* __restrict__ group_partial, int group_stride,
+                                                                           int n_groups, double g, double2* __restrict__ eu, int n_cells) {
+    __shared__ double bsh[kShInlineRows];
+    __shared__ double ssh[kShInlineRows];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < t.rows; k += kShWarps) {
+        const double* __restrict__ row = group_partial + (size_t)k * group_stride;
+        double a = 0.0;
+#pragma unroll 4
+        for (int q = lane; q < n_groups; q += 32) a = a + __ldcg(row + q);
+        a = warp_sum(a);
+        if (lane == 0) {
+            bsh[k] = a;
+            if (blockIdx.x == 0) w.b[k] = a;
+        }
+    }
+    __syncthreads();
+    solve_rows(t, bsh, g, ssh, warp, kShWarps);
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < t.rows; k += kShThreads) w.s[k] = ssh[k];
+    const RecConst rc;
+    for (int i = blockIdx.x * kShThreads + threadIdx.x; i < n_cells; i += gridDim.x * kShThreads) {
+        const double u = t.trig[i], z = t.trig[(size_t)t.stride + i], c1 = t.trig[2 * (size_t)t.stride + i], s1 = t.trig[3 * (size_t)t.stride + i];
+        const double u0 = eu[i].y;
+        eu[i].y = u0 + synthesis_mf_cell<LT>(t, rc, ssh, u, z, c1, s1);
+    }
+}
+
 // ---- ensembles: FP64 tensor-core GEMMs ------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -626,6 +659,17 @@ void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_
         return;
     }
     sh_synthesis_kernel<<<(n_cells + kShThreads - 1) / kShThreads, kShThreads, 0, stream>>>(t, w, eu, n_cells);
+}
+
+void launch_sh_solve_synthesis(const ShTables& t, const ShWork& w, const double* group_partial, int group_stride, int n_groups, double g, double2* eu,
+                               int n_cells, cudaStream_t stream) {
+    int grid = (n_cells + kShThreads - 1) / kShThreads;
+    if (grid > kShMaxBlocks) grid = kShMaxBlocks;               // persistent: two CTAs per SM
+    switch (t.l_max) {
+        case 2: sh_solve_synthesis_mf_kernel<2><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
+        case 3: sh_solve_synthesis_mf_kernel<3><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
+        default: sh_solve_synthesis_mf_kernel<4><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
+    }
 }
 
 }  // namespace odis

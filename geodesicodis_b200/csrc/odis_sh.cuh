@@ -71,6 +71,12 @@ void launch_sh_analysis(const ShTables& t, ShWork w, const double2* eu, int n_ow
 // U of the first n_cells cells (own + halo)
 void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_cells, cudaStream_t stream);
 
+// 3-launch variant (unpartitioned, matrix-free, l_max <= 4): the analysis is folded into the cell update (launch_cell_step_sg,
+// odis_kernels.cuh), which leaves group_partial[rows][group_stride], sums over groups of CTAs; this launch adds the n_groups
+// partials of every row in group order, solves, and adds the term to U of the cells [0, n_cells). Leaves b and s in `w` too.
+void launch_sh_solve_synthesis(const ShTables& t, const ShWork& w, const double* group_partial, int group_stride, int n_groups, double g, double2* eu,
+                               int n_cells, cudaStream_t stream);
+
 }  // namespace odis
 
 // ---- ensembles: M members on one grid, state member-innermost ({eta,U}[cell][Mp]) ---------------------------------------

@@ -145,7 +145,10 @@ typedef struct odis_params {
     int32_t reserved[4];    /* [0] kernel selection, 0 = default: two launches per step, bulk-async staged edge kernel +
                              *     direct-load cell kernel. bit 0: direct-load edge kernel; bit 1: staged cell kernel; bit 2: ONE fused
                              *     kernel per step (cell update of the previous step + edge update; one halo exchange per step).
-                             *     Every selection gives bit-identical fields. Rest must be 0. */
+                             *     Every selection gives bit-identical fields. bit 3: no CUDA-graph replay. bit 4 (with
+                             *     odis_enable_self_gravity, degree <= 4, unpartitioned): 3 launches per step instead of 5 — the harmonic
+                             *     analysis is folded into the cell update and the solve into the synthesis (sums associate differently:
+                             *     fields agree with the default to ~1e-13 relative, not bit for bit). Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {
