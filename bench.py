@@ -257,8 +257,8 @@ def run_ours(args) -> None:
     def e2e_interval(k: int):
         solver.set_state(h_v, h_eta, h_dv, h_de, iter=it0 + k * S)          # H2D of the interval's inputs
         solver.step(S)
-        h_eta[:] = solver.field(odis.FIELD_ETA)                              # D2H of what a dump reads
-        h_v[:] = solver.field(odis.FIELD_VELOCITY)
+        solver.field(odis.FIELD_ETA, out=h_eta)                              # D2H of what a dump reads, straight into the pinned buffers
+        solver.field(odis.FIELD_VELOCITY, out=h_v)
         return solver.dissipation_avg()
 
     e2e_interval(0)

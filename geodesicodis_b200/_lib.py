@@ -51,7 +51,13 @@ class PartitionPlan(C.Structure):
 
 
 class RunOptions(C.Structure):
-    _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("self_gravity", c_i32), ("max_steps", c_i64)]
+    _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("self_gravity", c_i32), ("max_steps", c_i64),
+                ("overlap_output", c_i32), ("reserved", c_i32)]
+
+
+class SnapshotView(C.Structure):
+    _fields_ = [("eta", C.c_void_p), ("velocity_en", C.c_void_p), ("dissipation", C.c_void_p), ("velocity", C.c_void_p),
+                ("dissipation_avg", c_f64), ("iter", c_i64)]
 
 
 class RunResult(C.Structure):
@@ -111,6 +117,8 @@ SIGNATURES = {
     "odis_op_integrate_ab3_scalar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i32]),
     "odis_op_interpolate_velocity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_op_update_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(c_f64)]),
+    "odis_snapshot_begin": (C.c_int, [C.c_void_p, c_i32, C.c_uint32]),
+    "odis_snapshot_wait": (C.c_int, [C.c_void_p, c_i32, P(SnapshotView)]),
     "odis_get_iter": (C.c_int, [C.c_void_p, P(c_i64)]),
     "odis_get_footprint": (C.c_int, [C.c_void_p, P(c_i64), P(c_i64)]),
     "odis_get_launch_count": (C.c_int, [C.c_void_p, P(c_i64)]),

@@ -297,11 +297,13 @@ class H5Writer:
             pass
 
 
-def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False, max_steps: int = 0, self_gravity: int = 0) -> dict:
+def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False, max_steps: int = 0, self_gravity: int = 0,
+        overlap_output: bool = False) -> dict:
     """`./ODIS` in run_dir: main -> solveODIS -> ab3Explicit (src/main.cpp:46-68), writing DATA/ and
     InitialConditions/ like the reference. Returns the run summary. self_gravity: 0 as reference HEAD; 1 the
-    spherical-harmonic self-gravity / shell-pressure term with input.in's "sh degree" (2: stored-basis kernels)."""
-    opt = _lib.RunOptions(device, int(reorder), int(echo), int(self_gravity), max_steps)
+    spherical-harmonic self-gravity / shell-pressure term with input.in's "sh degree" (2: stored-basis kernels).
+    overlap_output: dumps are copied out and written while the next output interval is being computed."""
+    opt = _lib.RunOptions(device, int(reorder), int(echo), int(self_gravity), max_steps, int(overlap_output), 0)
     res = _lib.RunResult()
     check(_lib.load().odis_run(os.fsencode(run_dir), C.byref(opt), C.byref(res)))
     return {n: getattr(res, n) for n, _ in _lib.RunResult._fields_ if n != "reserved"}
@@ -426,10 +428,33 @@ class Solver:
         check(_lib.load().odis_get_sh_coefficients(self._h, out.ctypes.data))
         return out
 
-    def field(self, fid: int) -> np.ndarray:
+    def field(self, fid: int, out: np.ndarray | None = None) -> np.ndarray:
+        """Device -> host, reference numbering. `out`: a C-contiguous float64 array of the field's size to fill in place
+        (e.g. page-locked memory, which the copy then reaches by DMA without a staging pass); default: a new array."""
         shape = tuple(self.F if d == "F" else self.N if d == "N" else d for d in _FIELD_SHAPES[fid])
-        out = np.empty(shape, dtype=np.float64)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != int(np.prod(shape)):
+            raise ValueError(f"out must be a C-contiguous float64 array of {int(np.prod(shape))} elements")
         check(_lib.load().odis_get_field(self._h, fid, out.ctypes.data))
+        return out
+
+    SNAP_ETA, SNAP_VELOCITY_EN, SNAP_DISSIPATION, SNAP_VELOCITY = 1, 2, 4, 8
+
+    def snapshot_begin(self, slot: int, fields: int) -> None:
+        """Enqueue the copy-out of `fields` (SNAP_* bits) behind the steps taken so far; returns at once (odis_snapshot_begin)."""
+        check(_lib.load().odis_snapshot_begin(self._h, slot, fields))
+
+    def snapshot_wait(self, slot: int) -> dict:
+        """Block until the slot's copy has landed; arrays are COPIES of the library's page-locked buffers."""
+        view = _lib.SnapshotView()
+        check(_lib.load().odis_snapshot_wait(self._h, slot, C.byref(view)))
+        out = {"dissipation_avg": view.dissipation_avg, "iter": view.iter}
+        for name, n, shape in (("eta", self.N, (self.N,)), ("velocity_en", 2 * self.F, (self.F, 2)), ("dissipation", self.F, (self.F,)),
+                               ("velocity", self.F, (self.F,))):
+            ptr = getattr(view, name)
+            if ptr:
+                out[name] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(shape).copy()
         return out
 
     def dissipation_avg(self) -> float:

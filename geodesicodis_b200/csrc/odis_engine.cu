@@ -149,6 +149,18 @@ struct odis_solver {
     odis::ShWork sh_work() const { return odis::ShWork{d_sh_partial, odis::kShMaxBlocks, 0, d_sh_b, d_sh_s}; }
     int sh_launches() const { return !sh_on ? 0 : odis::sh_analysis_launches(sh_rows, world > 1) + 1; }
 
+    // output snapshots that overlap with stepping (odis_snapshot_begin / _wait): two slots, each a device staging buffer in
+    // reference order [eta N | v_avg 2F | energy_diss F | v F | dissipation sum 1] and its page-locked host copy
+    struct SnapshotSlot {
+        double* d_buf = nullptr;
+        double* h_buf = nullptr;
+        cudaEvent_t ready = nullptr, done = nullptr;
+        uint32_t fields = 0;
+        bool pending = false;
+        int64_t iter = 0;
+    } snap[2];
+    cudaStream_t copy_stream = nullptr;
+
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
     int last_mode = -1;
@@ -1428,6 +1440,71 @@ int odis_op_update_energy(odis_solver* s, const double* v_avg, const double* are
     return ODIS_OK;
 }
 
+// ---- output snapshots overlapped with stepping (the dump pipeline) ----
+// begin: on the solver's stream, the diagnostics + renumbering of the requested fields into the slot's device buffer; on a
+// second stream, behind an event, the device -> host copy into page-locked memory. The call returns at once and the caller
+// can enqueue the next interval's steps: they run while the copy and the caller's file output proceed.
+int odis_snapshot_begin(odis_solver* s, int32_t slot, uint32_t fields) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
+    if (slot < 0 || slot > 1) return fail(ODIS_ERR_ARG, "snapshot slot must be 0 or 1");
+    if (!s->have_state) return fail(ODIS_ERR_STATE, "no state");
+    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "snapshots need an unpartitioned solver");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const size_t N = (size_t)s->Ng, F = (size_t)s->Fg, total = N + 4 * F + 1;
+    odis_solver::SnapshotSlot& sl = s->snap[slot];
+    if (!s->copy_stream) ODIS_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    if (!sl.d_buf) {
+        int rc = dev_alloc(s, &sl.d_buf, total);
+        if (rc) return rc;
+        ODIS_CUDA(cudaHostAlloc((void**)&sl.h_buf, total * sizeof(double), cudaHostAllocDefault));
+        ODIS_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+        ODIS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    if (sl.pending) ODIS_CUDA(cudaStreamWaitEvent(s->stream, sl.done, 0));     // the slot's previous copy must have left the buffer
+    int rc = finalize_eta(s);
+    if (rc) return rc;
+    const bool want_diag_fields = (fields & (ODIS_SNAP_VELOCITY_EN | ODIS_SNAP_DISSIPATION)) != 0;
+    if ((rc = run_diagnostics(s, want_diag_fields))) return rc;
+    double* d_eta = sl.d_buf; double* d_ven = d_eta + N; double* d_diss = d_ven + 2 * F; double* d_v = d_diss + F; double* d_sum = d_v + F;
+    if (fields & ODIS_SNAP_ETA) { odis::launch_gather_component(s->No, s->d_cell_perm, s->d_eu[s->ecur], 0, d_eta, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_VELOCITY_EN) { odis::launch_gather_pair(s->Fo, s->d_edge_perm, s->d_vavg, d_ven, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_DISSIPATION) { odis::launch_gather_scalar(s->Fo, s->d_edge_perm, s->d_ediss, d_diss, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_VELOCITY) { odis::launch_gather_component(s->Fo, s->d_edge_perm, s->d_vl[s->cur], 0, d_v, s->stream); s->launches++; }
+    ODIS_CUDA(cudaGetLastError());
+    ODIS_CUDA(cudaMemcpyAsync(d_sum, s->d_series + (s->iter - s->iter0), sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    ODIS_CUDA(cudaEventRecord(sl.ready, s->stream));
+    ODIS_CUDA(cudaStreamWaitEvent(s->copy_stream, sl.ready, 0));
+    auto d2h = [&](const double* d, size_t n) { return cudaMemcpyAsync(sl.h_buf + (d - sl.d_buf), d, n * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream); };
+    if (fields & ODIS_SNAP_ETA) ODIS_CUDA(d2h(d_eta, N));
+    if (fields & ODIS_SNAP_VELOCITY_EN) ODIS_CUDA(d2h(d_ven, 2 * F));
+    if (fields & ODIS_SNAP_DISSIPATION) ODIS_CUDA(d2h(d_diss, F));
+    if (fields & ODIS_SNAP_VELOCITY) ODIS_CUDA(d2h(d_v, F));
+    ODIS_CUDA(d2h(d_sum, 1));
+    ODIS_CUDA(cudaEventRecord(sl.done, s->copy_stream));
+    sl.fields = fields;
+    sl.pending = true;
+    sl.iter = s->iter;
+    return ODIS_OK;
+}
+
+int odis_snapshot_wait(odis_solver* s, int32_t slot, odis_snapshot_view* out) {
+    if (!s || !out) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (slot < 0 || slot > 1) return fail(ODIS_ERR_ARG, "snapshot slot must be 0 or 1");
+    odis_solver::SnapshotSlot& sl = s->snap[slot];
+    if (!sl.pending) return fail(ODIS_ERR_STATE, "no snapshot was begun on this slot");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    ODIS_CUDA(cudaEventSynchronize(sl.done));
+    const size_t N = (size_t)s->Ng, F = (size_t)s->Fg;
+    const double* h = sl.h_buf;
+    out->eta = (sl.fields & ODIS_SNAP_ETA) ? h : nullptr;
+    out->velocity_en = (sl.fields & ODIS_SNAP_VELOCITY_EN) ? h + N : nullptr;
+    out->dissipation = (sl.fields & ODIS_SNAP_DISSIPATION) ? h + N + 2 * F : nullptr;
+    out->velocity = (sl.fields & ODIS_SNAP_VELOCITY) ? h + N + 3 * F : nullptr;
+    out->dissipation_avg = h[N + 4 * F] / sphere_area(s);
+    out->iter = sl.iter;
+    return ODIS_OK;
+}
+
 int odis_get_iter(odis_solver* s, int64_t* iter_out) {
     if (!s || !iter_out) return fail(ODIS_ERR_ARG, "NULL argument");
     *iter_out = s->iter;
@@ -1495,6 +1572,14 @@ void odis_destroy(odis_solver* s) {
         if (p) cudaFree(p);
     for (void* p : s->nl_owned)
         if (p) cudaFree(p);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    for (auto& sl : s->snap) {
+        if (sl.d_buf) cudaFree(sl.d_buf);
+        if (sl.h_buf) cudaFreeHost(sl.h_buf);
+        if (sl.ready) cudaEventDestroy(sl.ready);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);

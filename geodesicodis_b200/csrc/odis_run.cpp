@@ -347,11 +347,73 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         return ODIS_OK;
     };
 
+    // Overlapped output (options.overlap_output): a dump is split into begin (the copy-out is enqueued behind the steps taken so far,
+    // odis_snapshot_begin) and finish (wait for the copy, log line, float conversion, data.h5 rows). The next interval's steps are
+    // enqueued between the two, so the GPU computes them while the host writes. Same files as the synchronous path.
+    const bool overlap = opt.overlap_output != 0;
+    uint32_t snap_fields = 0;
+    if (ds_u >= 0) snap_fields |= ODIS_SNAP_VELOCITY_EN;
+    if (ds_ux >= 0) snap_fields |= ODIS_SNAP_VELOCITY;
+    if (ds_eta >= 0) snap_fields |= ODIS_SNAP_ETA;
+    if (ds_diss >= 0) snap_fields |= ODIS_SNAP_DISSIPATION;
+    int snap_slot = 0, pending_slot = -1;
+    double pending_time = 0.0;
+    auto begin_dump = [&](double current_time) -> int {
+        const int rc2 = odis_snapshot_begin(s, snap_slot, snap_fields);
+        if (rc2) return rc2;
+        pending_slot = snap_slot;
+        pending_time = current_time;
+        snap_slot ^= 1;
+        return ODIS_OK;
+    };
+    auto finish_dump = [&]() -> int {
+        if (pending_slot < 0) return ODIS_OK;
+        odis_snapshot_view view{};
+        const int rc2 = odis_snapshot_wait(s, pending_slot, &view);
+        pending_slot = -1;
+        if (rc2) return rc2;
+        e_diss = view.dissipation_avg;
+        log.out(fmt("DUMPING DATA AT %f AVG DISS: %e GW%d", pending_time / period, e_diss * 4 * odis::kPi * r * r / 1e9, out_count));
+        const uint64_t row = (uint64_t)(out_count - 1);
+        if (row < T) {
+            if (ds_u >= 0) {
+                for (int i = 0; i < F; i++) { fa[i] = (float)view.velocity_en[(size_t)i * 2]; fb[i] = (float)view.velocity_en[(size_t)i * 2 + 1]; }
+                h5.write_rows(ds_u, row, 1, fa.data(), err);
+                h5.write_rows(ds_v, row, 1, fb.data(), err);
+            }
+            if (ds_ux >= 0) {
+                const odis::Csr& A = nlt.rbf_interp;
+                for (int c = 0; c < 3; c++) {
+                    for (int i = 0; i < N; i++) {
+                        double tmp = 0;
+                        for (int k = A.indptr[(size_t)3 * i + c]; k < A.indptr[(size_t)3 * i + c + 1]; k++) tmp += A.data[(size_t)k] * view.velocity[(size_t)A.indices[(size_t)k]];
+                        fa[i] = (float)tmp;
+                    }
+                    h5.write_rows(c == 0 ? ds_ux : c == 1 ? ds_uy : ds_uz, row, 1, fa.data(), err);
+                }
+            }
+            if (ds_eta >= 0) {
+                for (int i = 0; i < N; i++) fa[i] = (float)view.eta[i];
+                h5.write_rows(ds_eta, row, 1, fa.data(), err);
+            }
+            if (ds_diss >= 0) {
+                for (int i = 0; i < F; i++) fa[i] = (float)view.dissipation[i];
+                h5.write_rows(ds_diss, row, 1, fa.data(), err);
+            }
+            if (ds_avg >= 0) { const float x = (float)e_diss; h5.write_rows(ds_avg, row, 1, &x, err); }
+            if (ds_kin >= 0) { const float x = (float)pending_time; h5.write_rows(ds_kin, row, 1, &x, err); }
+            if (ds_d1 >= 0) { std::fill(fa.begin(), fa.begin() + N, 0.0f); h5.write_rows(ds_d1, row, 1, fa.data(), err); }
+        }
+        out_count++;
+        res->dumps++;
+        return ODIS_OK;
+    };
+
     g_sigint = 0;
     struct sigaction sa_new {}, sa_old {};
     sa_new.sa_handler = on_sigint;
     sigaction(SIGINT, &sa_new, &sa_old);                                       // timeIntegrator.cpp:120
-    rc = dump(dt * (double)iter);
+    rc = overlap ? begin_dump(dt * (double)iter) : dump(dt * (double)iter);
     const double bound = (double)total_iter * end_time;                        // timeIntegrator.cpp:205
     while (rc == ODIS_OK && (double)iter < bound) {
         // advance to the next output step, the loop bound or the caller's step budget, whichever is first
@@ -360,16 +422,19 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         if (n > left) n = left;
         if (opt.max_steps > 0 && iter + n > opt.max_steps) n = opt.max_steps - iter;
         if (n <= 0) break;
-        if (stepping) rc = odis_step(s, (int32_t)n);
+        if (stepping) rc = odis_step(s, (int32_t)n);                           // asynchronous: enqueued behind a pending snapshot
         if (rc != ODIS_OK) break;
+        if (overlap && (rc = finish_dump()) != ODIS_OK) break;                 // the previous dump is written while these steps run
         iter += n;
-        if (iter % out_freq == 0) rc = dump(dt * (double)iter);                // timeIntegrator.cpp:280-304
+        if (iter % out_freq == 0) rc = overlap ? begin_dump(dt * (double)iter) : dump(dt * (double)iter);   // timeIntegrator.cpp:280-304
         else rc = odis_synchronize(s);
         if (g_sigint) {                                                        // :307-312
+            if (overlap && rc == ODIS_OK) rc = finish_dump();
             log.out("Terminate signal caught...");
             break;
         }
     }
+    if (overlap && rc == ODIS_OK) rc = finish_dump();
     sigaction(SIGINT, &sa_old, nullptr);
     if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
 

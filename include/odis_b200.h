@@ -291,6 +291,26 @@ int odis_op_forcing(odis_solver* s, double time, double* potential_out);
 int odis_op_integrate_ab3_scalar(odis_solver* s, double* solution, double* dsolution_dt, int64_t iter, int32_t n);
 int odis_op_interpolate_velocity(odis_solver* s, const double* v, double* v_avg_out);
 int odis_op_update_energy(odis_solver* s, const double* v_avg, const double* areas, double* e_flux_out, double* avg_flux_out);
+/* Output snapshots that overlap with stepping — the DumpData side of the loop (src/timeIntegrator.cpp:280-304, src/outFiles.cpp:522-684)
+ * without stalling it. odis_snapshot_begin enqueues, behind the steps taken so far, the diagnostics and the device -> host copy of the
+ * requested fields (ODIS_SNAP_* bits; the dissipation average always) into page-locked memory owned by the library, on a second
+ * stream, and returns; the caller enqueues the next interval with odis_step and then calls odis_snapshot_wait, which blocks only until
+ * that copy has landed and hands out pointers valid until the slot's next odis_snapshot_begin. Two slots (0, 1) for double buffering.
+ * Unpartitioned solvers. */
+#define ODIS_SNAP_ETA 1u          /* p_t0        [N]    */
+#define ODIS_SNAP_VELOCITY_EN 2u  /* v_avg       [F][2] */
+#define ODIS_SNAP_DISSIPATION 4u  /* energy_diss [F]    */
+#define ODIS_SNAP_VELOCITY 8u     /* v_t0        [F]    */
+typedef struct odis_snapshot_view {
+    const double* eta;
+    const double* velocity_en;
+    const double* dissipation;
+    const double* velocity;        /* NULL for fields that were not requested */
+    double dissipation_avg;        /* as odis_get_dissipation_avg */
+    int64_t iter;                  /* steps taken when the snapshot was begun */
+} odis_snapshot_view;
+int odis_snapshot_begin(odis_solver* s, int32_t slot, uint32_t fields);
+int odis_snapshot_wait(odis_solver* s, int32_t slot, odis_snapshot_view* out);
 int odis_get_iter(odis_solver* s, int64_t* iter_out);
 /* Bytes of device memory held, and the algorithmic HBM bytes one step moves. */
 int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* algorithmic_bytes_per_step_out);
@@ -359,6 +379,9 @@ typedef struct odis_run_options {
     int32_t self_gravity; /* 0: as reference HEAD (term commented out). 1: odis_enable_self_gravity with input.in's "sh degree" and
                            * the surface type's per-degree factors (matrix-free kernels); 2: the same with the stored basis */
     int64_t max_steps;    /* > 0: stop after this many steps even if the loop bound is larger */
+    int32_t overlap_output; /* 1: dumps go through odis_snapshot_begin/_wait: the next output interval is computed while the previous
+                             * dump is copied out and written to data.h5 (same files, byte for byte). 0: synchronous dumps */
+    int32_t reserved;
 } odis_run_options;
 
 typedef struct odis_run_result {

@@ -1,0 +1,52 @@
+"""Overlapped output (odis_run_options.overlap_output / `ODIS --overlap-output`; odis_snapshot_begin / _wait): the next output
+interval is computed while the previous dump is copied out and written. It must leave the same files as the synchronous
+path, byte for byte, and the snapshot calls must return what odis_get_field returns."""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_case, make_run_dir
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["l3_ecc_full_orbit", "l3_shipped_verbatim", "l4_ecc_enceladus"])
+def test_overlapped_run_writes_the_same_files(odis, tmp_path, name):
+    case = load_case(name)
+    a, b = make_run_dir(tmp_path / "sync", case), make_run_dir(tmp_path / "overlap", case)
+    ra, rb = odis.run(a), odis.run(b, overlap_output=True)
+    assert ra["steps"] == rb["steps"] and ra["dumps"] == rb["dumps"] and ra["last_dissipation_avg"] == rb["last_dissipation_avg"]
+    assert filecmp.cmp(os.path.join(a, "DATA", "data.h5"), os.path.join(b, "DATA", "data.h5"), shallow=False)
+    lines = lambda d: [l for l in open(os.path.join(d, "DATA", "OUTPUT.txt")) if l.startswith("DUMPING DATA AT")]
+    assert lines(a) == lines(b) and len(lines(a)) == ra["dumps"]
+    for f in ("vel_init.txt", "pres_init.txt"):
+        assert filecmp.cmp(os.path.join(a, "InitialConditions", f), os.path.join(b, "InitialConditions", f), shallow=False)
+
+
+def test_snapshots_equal_field_reads_while_stepping_continues(odis):
+    pos, fr, cen = odis.generate_grid(5)
+    r = 252.1e3
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, r)
+    prm = dict(g=0.113, h=38e3, alpha=1e-7, dt=30.0, radius=r, omega=5.307e-5, love_reduct=1.0, ecc=0.0047, obl=0.0,
+               shell_thickness=0.0, semimajor_axis=0.0, potential=5, friction=0, surface=0, init_load=0, reorder=1)
+    s, ref = odis.Solver(mesh, prm), odis.Solver(mesh, prm)
+    every = s.SNAP_ETA | s.SNAP_VELOCITY_EN | s.SNAP_DISSIPATION | s.SNAP_VELOCITY
+    expected = []
+    for k in range(4):                                        # reference: synchronous reads every 30 steps
+        ref.step(30)
+        expected.append({"eta": ref.field(odis.FIELD_ETA), "velocity_en": ref.field(odis.FIELD_VELOCITY_EN),
+                         "dissipation": ref.field(odis.FIELD_DISSIPATION), "velocity": ref.field(odis.FIELD_VELOCITY),
+                         "dissipation_avg": ref.dissipation_avg(), "iter": 30 * (k + 1)})
+    s.step(30)
+    for k in range(4):
+        s.snapshot_begin(k & 1, every)
+        s.step(30)                                            # runs while the snapshot is copied out
+        got = s.snapshot_wait(k & 1)
+        for key, val in expected[k].items():
+            assert np.array_equal(got[key], val), (k, key)
+    with pytest.raises(odis.OdisError):
+        s.snapshot_wait(2)
+    with pytest.raises(odis.OdisError):
+        odis.Solver(mesh, prm).snapshot_wait(0)               # nothing begun on this slot
