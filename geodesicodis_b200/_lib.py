@@ -95,6 +95,7 @@ SIGNATURES = {
     "odis_get_partition": (C.c_int, [C.c_void_p] + [P(c_i32)] * 7),
     "odis_partition_plan": (C.c_int, [P(MeshView), c_i32, c_i32, c_i32, P(PartitionPlan)]),
     "odis_partition_plan_free": (None, [P(PartitionPlan)]),
+    "odis_analytical_state": (C.c_int, [P(MeshView), P(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64]),
     "odis_step": (C.c_int, [C.c_void_p, c_i32]),
     "odis_step_timed": (C.c_int, [C.c_void_p, c_i32, P(C.c_float)]),

@@ -206,6 +206,19 @@ def params_from_globals(g: Globals, dt: float, reorder: bool = True) -> dict:
                 friction=g.fric_type, surface=g.surface_type, init_load=int(g.initial_condition == 1), reorder=int(reorder))
 
 
+def analytical_state(mesh: "Mesh", params: dict):
+    """(v [F], dvdt [F][3], eta [N], detadt [N][3]) of `initial conditions; ANALYTICAL` (OBLIQ_WEST only), as the reference's
+    analyticalInitialConditions builds them (src/initialConditions.cpp:146-208). Host only."""
+    p = Params()
+    for k, val in params.items():
+        if k != "kernel_select":
+            setattr(p, k, val)
+    N, F = mesh.n_cells, mesh.n_edges
+    v, dv, eta, de = np.empty(F), np.empty((F, 3)), np.empty(N), np.empty((N, 3))
+    check(_lib.load().odis_analytical_state(C.byref(mesh.view), C.byref(p), v.ctypes.data, dv.ctypes.data, eta.ctypes.data, de.ctypes.data))
+    return v, dv, eta, de
+
+
 def sh_basis(pos_sph, l_max: int) -> np.ndarray:
     """Basis rows Y[(l_max+1)^2][n] at (lat, lon) [n][2] (radians): 4-pi normalised, Condon-Shortley phase, degree-major,
     per degree m = 0 then (cos, sin) for m = 1..l (host only)."""

@@ -21,7 +21,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libodis_b200.so")
 
 HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp", "odis_partition.cpp", "odis_h5lite.cpp",
-                "odis_run.cpp", "odis_sh.cpp", "odis_mesh_nl.cpp"]
+                "odis_run.cpp", "odis_sh.cpp", "odis_mesh_nl.cpp", "odis_analytic.cpp"]
 CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_fused.cu", "odis_engine.cu", "odis_ensemble.cu", "odis_sh.cu", "odis_kernels_nl.cu"]
 
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 
+#include "odis_analytic.h"
 #include "../../include/odis_b200.h"
 #include "odis_config.h"
 #include "odis_error.h"
@@ -179,6 +180,18 @@ int odis_config_get_enum(const odis_config* cfg, int32_t which, int32_t* out) {
     return ODIS_OK;
 }
 void odis_config_free(odis_config* cfg) { delete cfg; }
+
+int odis_analytical_state(const odis_mesh_view* mv, const odis_params* prm, double* v, double* dvdt, double* eta, double* detadt) {
+    if (!mv || !prm || !v || !dvdt || !eta || !detadt) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (!mv->node_pos_sph || !mv->face_centre_pos_sph || !mv->face_normal_vec_map) return fail(ODIS_ERR_ARG, "mesh view lacks the position / normal tables");
+    if (prm->potential != 1 /*OBLIQ_WEST*/)
+        return fail(ODIS_ERR_UNSUPPORTED, "the analytical solution exists for potential OBLIQ_WEST only (analyticalLTE.cpp:133; other types return nothing there)");
+    if (!(prm->omega != 0.0) || !(prm->g * prm->h > 0.0)) return fail(ODIS_ERR_ARG, "omega, g and h must be non-zero");
+    const odis::AnalyticParams ap{prm->radius, prm->omega, prm->g, prm->h, prm->alpha, prm->obl, prm->dt};
+    odis::analytical_state_obliq_west(ap, mv->n_cells, mv->n_edges, mv->node_pos_sph, mv->face_centre_pos_sph, mv->face_normal_vec_map, v, dvdt, eta,
+                                      detadt);
+    return ODIS_OK;
+}
 
 int odis_quantise_time_step(double period, double target_dt, double* dt_out, int32_t* steps_out) {
     if (!dt_out || !steps_out) return fail(ODIS_ERR_ARG, "NULL argument");

@@ -176,7 +176,8 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         log.err("WARNING: Unassigned global constant: " + k + ". \nAssigning default value could be risky...\nUsing Titan value\n");
     if (cfg.finalize(err) != 0) return terminate(ODIS_ERR_CONFIG, err);
     if (cfg.solver_type != odis::AB3) return terminate(ODIS_ERR_UNSUPPORTED, "only solver type AB3 has a live implementation (solver.cpp:25-50)");
-    if (cfg.initial_condition == odis::INIT_ANALYTICAL) return terminate(ODIS_ERR_UNSUPPORTED, "initial conditions; ANALYTICAL is not provided");
+    if (cfg.initial_condition == odis::INIT_ANALYTICAL && cfg.tide_type != 1 /*OBLIQ_WEST*/)
+        return terminate(ODIS_ERR_UNSUPPORTED, "initial conditions; ANALYTICAL exists for potential OBLIQ_WEST only (analyticalLTE.cpp:133)");
     for (const char* k : {"pressure output", "kinetic output", "dummy2 output"})
         if (cfg.get_bool(k)) log.err(std::string("WARNING: '") + k + "' would create a second dataset named 'displacement' (outFiles.cpp:286,308,338); ignored.");
 
@@ -292,6 +293,11 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         if (load_restart(fp, (size_t)N, eta, de) == 0) log.out("\nFound initial conditions file: " + fp);
         else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fp);
         rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
+        if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
+    }
+    if (cfg.initial_condition == odis::INIT_ANALYTICAL) {                     // initialConditions.cpp:311-313
+        rc = odis_analytical_state(&mv, &p, v.data(), dv.data(), eta.data(), de.data());
+        if (rc == ODIS_OK) rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
         if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
     }
     log.out("Defining arrays for Adams-Bashforth time integration...");       // timeIntegrator.cpp:140

@@ -199,6 +199,12 @@ typedef struct odis_partition_plan_t {
 int odis_partition_plan(const odis_mesh_view* mesh, int32_t reorder, int32_t rank, int32_t world, odis_partition_plan_t* plan_out);
 void odis_partition_plan_free(odis_partition_plan_t* plan);
 
+/* `initial conditions; ANALYTICAL` (host only): the state getInitialConditions hands to the loop from analyticalInitialConditions
+ * (src/initialConditions.cpp:146-208) / analyticalLTE (src/analyticalLTE.cpp:47-181) — the two-mode analytical response to the westward
+ * obliquity tide at t = 0 with tendencies at 0, -dt, -2dt: v[F], dvdt[F][3], eta[N], detadt[N][3], ready for odis_set_state(..., 0)
+ * (params.init_load stays 0: the reference starts such runs with its Euler / two-level steps, src/temporalOperators.cpp:36).
+ * params.potential must be OBLIQ_WEST, the only type the reference has a solution for. Bit-identical to the reference's arrays. */
+int odis_analytical_state(const odis_mesh_view* mesh, const odis_params* params, double* v, double* dvdt, double* eta, double* detadt);
 /* Host -> device state in reference numbering. NULL pointers mean zeros. `iter` is the number of
  * steps already taken (current_time = dt*iter, src/timeIntegrator.cpp:187,277). */
 int odis_set_state(odis_solver* s, const double* v, const double* eta, const double* dvdt /*[F][3]*/,

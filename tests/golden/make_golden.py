@@ -78,7 +78,7 @@ NL_TABLES = ["vertex_sinlat", "vertex_area", "vertex_R", "vertex_nodes", "face_v
 
 
 def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: bool, full_tables: bool,
-             init_state: dict | None = None, nl_tables: bool = False):
+             init_state: dict | None = None, nl_tables: bool = False, capture_start: bool = False):
     binary = os.path.join(ROOT, "oracle", "_ref", f"odis_ref_l{level}")
     with tempfile.TemporaryDirectory() as d:
         os.makedirs(d + "/input_files"); os.makedirs(d + "/DATA")
@@ -104,6 +104,11 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
             with open(d + "/InitialConditions/pres_init.txt", "w") as f:
                 for i in range(init_state["eta"].shape[0]):
                     f.write("%.17g, %.17g, %.17g, %.17g\n" % (init_state["eta"][i], *init_state["detadt"][i]))
+        start = None
+        if capture_start:              # the state getInitialConditions built, before any step: a run whose loop bound is 0
+            open(d + "/input.in", "w").write(input_text(dict(over, **{"simulation end time": "0"})))
+            subprocess.run([binary, "--quiet-restart"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            start = read_records(d + "/DATA/ref_final.bin")
         text = input_text(over)
         open(d + "/input.in", "w").write(text)
         subprocess.run([binary], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -152,6 +157,9 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
     if init_state is not None:
         for k, v in init_state.items():
             out["init_" + k] = v
+    if start is not None:
+        for k, v in start.items():
+            out["start_" + k] = v
     path = os.path.join(HERE, f"case_{name}.npz")
     np.savez_compressed(path, **out)
     print(f"{name}: level {level}, {nsteps} steps, totalIter {total}, dumps {len(slices)} -> {os.path.getsize(path) / 1e6:.2f} MB")
@@ -208,6 +216,10 @@ if __name__ == "__main__":
     # (12) FREE_LOADING: loading Love numbers change the tidal prefactor (boundaryConditions.cpp:29-77)
     run_case("l3_obliq_freeloading", 3, {"surface type": "FREE_LOADING", "potential": "OBLIQ", "sh degree": "3", "time step": "70"}, 45,
              every_step_dumps=True, full_tables=False)
+    # (13) `initial conditions; ANALYTICAL`: the reference's analytical OBLIQ_WEST response as the start state (initialConditions.cpp:146-208),
+    #      captured before any step ("start_*") and after 80 steps
+    run_case("l3_obliqwest_analytical", 3, dict(earth, **{"initial conditions": "ANALYTICAL", "friction coefficient": "1e-6"}), 80,
+             every_step_dumps=True, full_tables=False, capture_start=True)
     # (10) the shipped input.in VERBATIM (advection true, velocity cartesian output true, ...) except for the grid level (3) and the
     #      end time (1 orbit = 48,100 steps at the shipped 30 s step): the whole-run drop-in check, HDF5 rows included
     verbatim = {}
