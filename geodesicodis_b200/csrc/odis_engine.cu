@@ -109,6 +109,8 @@ struct odis_solver {
 
     // nonlinear branch (odis_enable_advection)
     bool nl_on = false;
+    bool nl_fused = false;           // params.reserved[0] bit 5: the 4-launch variant of the nonlinear step
+    int nl_launches() const { return nl_fused ? odis::kNlLaunchesFused : odis::kNlLaunches; }
     odis::NlTables nl{};
     double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
     double2* d_nl_fq = nullptr;
@@ -348,6 +350,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->fused = (prm->reserved[0] & 4) != 0;
     s->use_graph = (prm->reserved[0] & 8) == 0;
     s->sh_fused_req = (prm->reserved[0] & 16) != 0;
+    s->nl_fused = (prm->reserved[0] & 32) != 0;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -1040,7 +1043,8 @@ static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEven
     ns.h1 = s->d_hv[s->hv1]; ns.h2 = s->d_hv[1 - s->hv1];
     ns.ch1 = s->d_he[s->he1]; ns.ch2 = s->d_he[s->he2]; ns.chw = s->d_he[s->hefree];
     ns.qv = s->d_nl_qv; ns.fq = s->d_nl_fq; ns.ekin = s->d_nl_ekin; ns.flux = s->d_nl_flux;
-    odis::launch_step_nonlinear(s->nl, s->phys, ns, mode, s->stream);
+    if (s->nl_fused) odis::launch_step_nonlinear_fused(s->nl, s->phys, ns, mode, s->stream);
+    else odis::launch_step_nonlinear(s->nl, s->phys, ns, mode, s->stream);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 1], s->stream);
     if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
     rotate_cell_history(s, mode);
@@ -1055,7 +1059,7 @@ static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEven
     s->cur = 1 - s->cur;
     s->iter++;
     s->last_mode = mode;
-    s->launches += 2 + odis::kNlLaunches + s->sh_launches();
+    s->launches += 2 + s->nl_launches() + s->sh_launches();
     return ODIS_OK;
 }
 

@@ -133,6 +133,74 @@ __global__ void __launch_bounds__(kNlThreads) nl_cell_step_kernel(NlTables t, Ph
     s.eu_out[i] = st;
 }
 
+// ---- 4-launch variant (opt-in, odis_params.reserved[0] bit 5): the same arithmetic in fewer passes ----
+// (a) vertex potential vorticity and cell kinetic energy have no dependency on each other: one grid, the first blocks take the
+//     vertices, the rest the cells;
+// (b) the third-order thickness flux of an edge needs only that edge's own new velocity (in a register at the end of the edge
+//     update) and second derivatives of h + eta^n: computed there instead of in a pass of its own, which also saves re-reading
+//     {v^{n+1}, l} and the cell ids.
+// The bodies repeat nl_vertex / nl_cell_ekin / nl_edge_step / nl_flux statement for statement (same order of operations).
+__global__ void __launch_bounds__(kNlThreads) nl_vertex_ekin_kernel(NlTables t, Physics p, NlState s, int vertex_blocks) {
+    if ((int)blockIdx.x < vertex_blocks) {
+        const int i = blockIdx.x * kNlThreads + threadIdx.x;
+        if (i >= t.n_vertices) return;
+        const double zeta = ell_row(t.curl, i, [&](int e) { return s.vl_in[e].x; });
+        const double f = -2 * t.omega * t.vsin[i];
+        double thickness = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int node = t.vnode[(size_t)j * t.vstride + i];
+            const double hn = p.h + s.eu_in[node].x;
+            thickness += hn * t.carea[node] * t.vR[(size_t)j * t.vstride + i];
+        }
+        thickness *= t.varea_r[i];
+        s.qv[i] = (zeta + f) / thickness;
+    } else {
+        const int i = ((int)blockIdx.x - vertex_blocks) * kNlThreads + threadIdx.x;
+        if (i >= t.n_cells) return;
+        auto vel = [&](int e) { return s.vl_in[e].x; };
+        const double x = ell_row(t.rbf[0], i, vel), y = ell_row(t.rbf[1], i, vel), z = ell_row(t.rbf[2], i, vel);
+        s.ekin[i] = 0.5 * (x * x + y * y + z * z);
+    }
+}
+
+__global__ void __launch_bounds__(kNlThreads) nl_edge_step_flux_kernel(NlTables t, Physics p, NlState s, int mode) {
+    const int e = blockIdx.x * kNlThreads + threadIdx.x;
+    if (e >= t.n_edges) return;
+    const int2 c = t.cells[e];
+    const double2 G = t.grad[e];
+    const double2 own = s.vl_in[e];
+    const double2 in = s.eu_in[c.x], out = s.eu_in[c.y];
+    double dv = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;
+    const double q_e = s.fq[e].y;
+    double F_tang_q = 0.0;
+#pragma unroll
+    for (int j = 0; j < kStencil; j++) {
+        const int f = t.nid[(size_t)j * t.estride + e];
+        if (f >= 0) {
+            const double2 o = s.fq[f];
+            F_tang_q += t.ncoef[(size_t)j * t.estride + e] * o.x * (q_e + o.y) * 0.5;
+        }
+    }
+    dv -= -F_tang_q;
+    dv += (-G.x) * s.ekin[c.x] + (-G.y) * s.ekin[c.y];
+    const double f0 = dv;
+    const double drag = (-p.alpha) * own.x + (G.x * in.y + G.y * out.y);
+    double v = own.x + ab3_increment(f0, s.h1[e], s.h2[e], p.dt, mode);
+    v += p.dt * drag;
+    s.vl_out[e] = make_double2(v, own.y);
+    if (mode == AB3_SECOND) s.h1[e] = f0;
+    else s.h2[e] = f0;
+    // interpolateLSQFlux (interpolation.cpp:311-364) for this edge, with the velocity just computed
+    auto htot = [&](int i) { return p.h + s.eu_in[i].x; };
+    const double d2_inner = ell_row(t.d2[0], e, htot), d2_outer = ell_row(t.d2[1], e, htot);
+    const double fact = 1. / 12.0, beta = 1.0;
+    const double dx = t.dist[e];
+    const double dx2 = dx * dx * fact;
+    const double vel = v;
+    s.flux[e] = vel * 0.5 * (htot(c.x) + htot(c.y)) - dx2 * (d2_outer + d2_inner) * vel + dx2 * beta * fabs(vel) * (d2_outer - d2_inner);
+}
+
 }  // namespace
 
 void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream) {
@@ -142,6 +210,15 @@ void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s
     nl_cell_ekin_kernel<<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, s);
     nl_edge_step_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
     nl_flux_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s);
+    nl_cell_step_kernel<<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode);
+}
+
+void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream) {
+    auto grid = [](int n) { return (unsigned)((n + kNlThreads - 1) / kNlThreads); };
+    const unsigned vb = grid(t.n_vertices);
+    nl_vertex_ekin_kernel<<<vb + grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, (int)vb);
+    nl_edge_prep_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s);
+    nl_edge_step_flux_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
     nl_cell_step_kernel<<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode);
 }
 

@@ -68,5 +68,9 @@ struct NlState {
 // edge update, flux, cell update
 constexpr int kNlLaunches = 6;
 void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream);
+// Opt-in variant, same arithmetic in 4 launches: vertex PV + cell Ekin in one grid; edge {F_e, q_e}; edge update + thickness flux;
+// cell update. Bit-identical fields.
+constexpr int kNlLaunchesFused = 4;
+void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream);
 
 }  // namespace odis

@@ -148,7 +148,8 @@ typedef struct odis_params {
                              *     Every selection gives bit-identical fields. bit 3: no CUDA-graph replay. bit 4 (with
                              *     odis_enable_self_gravity, degree <= 4, unpartitioned): 3 launches per step instead of 5 — the harmonic
                              *     analysis is folded into the cell update and the solve into the synthesis (sums associate differently:
-                             *     fields agree with the default to ~1e-13 relative, not bit for bit). Rest must be 0. */
+                             *     fields agree with the default to ~1e-13 relative, not bit for bit). bit 5 (with odis_enable_advection):
+                             *     the nonlinear step in 4 gather launches instead of 6 (bit-identical fields). Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {

@@ -15,8 +15,8 @@ dmin = float(mesh.tables["face_node_dist"].min())
 prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.2 * dmin / np.sqrt(9.80616 * 8e3), radius=r, omega=7.292e-5, love_reduct=1.0, ecc=0.01,
            obl=np.deg2rad(-2.0), shell_thickness=0.0, semimajor_axis=0.0, potential=1, friction=0, surface=0, init_load=0, reorder=1)
 out = []
-for adv in (False, True):
-    s = odis.Solver(mesh, prm)
+for adv in (False, True, "4-launch variant (kernel_select=32)"):
+    s = odis.Solver(mesh, dict(prm, kernel_select=32) if isinstance(adv, str) else prm)
     if adv:
         s.enable_advection(nl)
     s.step(50)
@@ -25,4 +25,4 @@ for adv in (False, True):
     eta = s.field(odis.FIELD_ETA)
     print(f"level {level} ({mesh.n_cells} cells) advection={adv}: {ms * 1e3:.1f} us/step, max|eta| {np.abs(eta).max():.4e}, finite {bool(np.isfinite(eta).all())}", flush=True)
     s.close()
-print(f"nonlinear tables built on the host in {t_tab:.2f} s; nonlinear / linear step time = {out[1] / out[0]:.2f}")
+print(f"nonlinear tables built on the host in {t_tab:.2f} s; nonlinear / linear step time = {out[1] / out[0]:.2f} (4-launch variant: {out[2] / out[0]:.2f})")
