@@ -1,0 +1,245 @@
+"""TEST INFRASTRUCTURE — builds tests/_build/libodis_b200_emu.so: the library's own sources (csrc/*.cu, engine included) with
+the CUDA-only syntax rewritten for a host compiler and compiled against tests/simt/simt_emu.h (a host emulation of the CUDA
+execution model). Host .cpp files are compiled as they are. Used by tests/test_emulated_kernels.py to run kernel logic and the
+engine's launch sequencing on the CPU; it is never loaded by the product path (geodesicodis_b200/_lib.py loads
+libodis_b200.so) and is no substitute for the B200 runs.
+
+Not emulated: the bulk-async staged kernels of odis_kernels_pipe.cu / odis_kernels_fused.cu (cp.async.bulk / mbarrier PTX) — the engine is switched to
+the direct-load kernels, which are the same arithmetic — multi-GPU peer flags, and the FP64 tensor-core mma of the ensemble
+self-gravity GEMMs (aborts if reached)."""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "geodesicodis_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "_build")
+LIB = os.path.join(OUT, "libodis_b200_emu.so")
+
+CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_nl.cu", "odis_sh.cu", "odis_ensemble.cu", "odis_engine.cu"]
+PIPE_STUB = r'''// stand-in for odis_kernels_pipe.cu and odis_kernels_fused.cu (cp.async.bulk / mbarrier kernels are not emulated; the engine is switched to
+// the direct-load two-launch kernels)
+#include "odis_kernels.cuh"
+#include <cstdlib>
+namespace odis {
+int pipe_tile() { return 128; }
+cudaError_t pipe_configure() { return cudaSuccess; }
+cudaError_t launch_edge_step_pipe(const EdgeTables&, const Physics&, const EdgeState&, int, const HaloInline*, cudaStream_t) { std::abort(); }
+cudaError_t launch_cell_step_pipe(const CellTables&, const Physics&, const CellState&, int, const StepScalars&, cudaStream_t) { std::abort(); }
+cudaError_t launch_step_fused(const FusedTables&, const Physics&, const FusedState&, int, int, int, const StepScalars&, cudaStream_t) { std::abort(); }
+}
+'''
+
+
+SWITCH_SRC = r'''// context switch of the SIMT emulation's fibers (tests/simt/simt_emu.h): x86-64 System V, callee-saved registers + stack pointer
+#if !defined(__x86_64__)
+#error "the SIMT emulation's context switch is written for x86-64"
+#endif
+asm(R"(
+    .text
+    .globl simt_switch
+    .type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size simt_switch,.-simt_switch
+    .section .note.GNU-stack,"",@progbits
+)");
+'''
+
+
+def _match_paren(s: str, i: int) -> int:
+    """index of the ')' matching the '(' at s[i] (string literals skipped)"""
+    depth, k = 0, i
+    while k < len(s):
+        c = s[k]
+        if c == '"':
+            k += 1
+            while s[k] != '"':
+                k += 2 if s[k] == "\\" else 1
+        elif c == "(":
+            depth += 1
+        elif c == ")":
+            depth -= 1
+            if depth == 0:
+                return k
+        k += 1
+    raise ValueError("unbalanced parentheses")
+
+
+def _split_top(s: str, sep: str) -> list[str]:
+    parts, depth, cur, k = [], 0, [], 0
+    while k < len(s):
+        c = s[k]
+        if c == '"':
+            j = k + 1
+            while s[j] != '"':
+                j += 2 if s[j] == "\\" else 1
+            cur.append(s[k:j + 1]); k = j + 1
+            continue
+        if c in "([{":
+            depth += 1
+        elif c in ")]}":
+            depth -= 1
+        if c == sep and depth == 0:
+            parts.append("".join(cur)); cur = []
+        else:
+            cur.append(c)
+        k += 1
+    parts.append("".join(cur))
+    return parts
+
+
+def rewrite_launches(s: str) -> tuple[str, int]:
+    n = 0
+    while True:
+        p = s.find("<<<")
+        if p < 0:
+            return s, n
+        i = p
+        if s[i - 1] == ">":                                 # template arguments of the kernel
+            depth = 0
+            while True:
+                i -= 1
+                if s[i] == ">":
+                    depth += 1
+                elif s[i] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+        while i > 0 and (s[i - 1].isalnum() or s[i - 1] in "_:"):
+            i -= 1
+        kernel = s[i:p]
+        q = s.index(">>>", p)
+        cfg = [c.strip() for c in _split_top(s[p + 3:q], ",")]
+        cfg += ["0", "nullptr"][len(cfg) - 2:] if len(cfg) < 4 else []
+        a = q + 3
+        while s[a].isspace():
+            a += 1
+        assert s[a] == "(", s[p - 40:q + 40]
+        b = _match_paren(s, a)
+        args = s[a + 1:b].strip()
+        s = s[:i] + f"simt::launch({cfg[0]}, {cfg[1]}, {cfg[2]}, {cfg[3]}, {kernel}{', ' + args if args else ''})" + s[b + 1:]
+        n += 1
+
+
+def _operands(section: str) -> list[str]:
+    out = []
+    for part in _split_top(section, ","):
+        part = part.strip()
+        if not part:
+            continue
+        a = part.index("(")
+        out.append(part[a + 1:_match_paren(part, a)].strip())
+    return out
+
+
+def rewrite_asm(s: str) -> tuple[str, int]:
+    n = 0
+    for m in reversed(list(re.finditer(r"\basm\s*(?:volatile\s*)?\(", s))):
+        a = m.end() - 1
+        b = _match_paren(s, a)
+        end = b + 1
+        while s[end].isspace():
+            end += 1
+        assert s[end] == ";", s[m.start():end + 10]
+        sections = _split_top(s[a + 1:b], ":")
+        ptx = "".join(re.findall(r'"((?:[^"\\]|\\.)*)"', sections[0]))
+        outs = _operands(sections[1]) if len(sections) > 1 else []
+        ins = _operands(sections[2]) if len(sections) > 2 else []
+        if ptx.startswith("createpolicy"):
+            rep = f"{outs[0]} = 0;"
+        elif ptx.startswith("ld.") and "{%0, %1}" in ptx:
+            rep = f"{{ const auto* simt_p_ = ({ins[0]}); {outs[0]} = simt_p_->x; {outs[1]} = simt_p_->y; }}"
+        elif ptx.startswith("ld."):
+            rep = f"{outs[0]} = *({ins[0]});"
+        elif ptx.startswith("st."):
+            rep = f"*({ins[0]}) = ({ins[1]});"
+        elif ptx.startswith("mma.sync"):
+            rep = 'do { std::fprintf(stderr, "simt_emu: tensor-core mma is not emulated\\n"); std::abort(); } while (0);'
+        else:
+            raise ValueError("no emulation for PTX: " + ptx)
+        s = s[:m.start()] + rep + s[end + 1:]
+        n += 1
+    return s, n
+
+
+def transform(name: str, text: str) -> str:
+    text, n_launch = rewrite_launches(text)
+    text, n_asm = rewrite_asm(text)
+    text, n_dyn = re.subn(r"extern\s+__shared__\s+(\w+)\s+(\w+)\s*\[\s*\]\s*;",
+                          r"\1* \2 = reinterpret_cast<\1*>(simt::dynamic_shared);", text)
+    if name == "odis_engine.cu":
+        # the staged (cp.async.bulk / mbarrier) kernels are not emulated: same arithmetic through the direct-load kernels
+        for old, new in (("s->pipe_edge = (prm->reserved[0] & 1) == 0;", "s->pipe_edge = false;"),
+                         ("s->pipe_cell = (prm->reserved[0] & 2) != 0;", "s->pipe_cell = false;"),
+                         ("s->fused = (prm->reserved[0] & 4) != 0;", "s->fused = false;")):
+            assert text.count(old) == 1, old
+            text = text.replace(old, new)
+    return f"// generated by tests/simt/build_emu.py from csrc/{name}: {n_launch} launches, {n_asm} asm statements, {n_dyn} dynamic shared arrays rewritten\n" + text
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    from geodesicodis_b200.build import HOST_SOURCES, HOST_FLAGS
+    src_dir = os.path.join(OUT, "emu_src")
+    os.makedirs(src_dir, exist_ok=True)
+    newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))
+    newest = max(newest, os.path.getmtime(os.path.join(HERE, "simt_emu.h")), os.path.getmtime(os.path.abspath(__file__)),
+                 os.path.getmtime(os.path.join(ROOT, "include", "odis_b200.h")))
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
+    jobs = []
+    for name in CUDA_SOURCES:
+        with open(os.path.join(CSRC, name)) as f:
+            text = transform(name, f.read())
+        text = text.replace('#include "../../include/odis_b200.h"', f'#include "{os.path.join(ROOT, "include", "odis_b200.h")}"')
+        path = os.path.join(src_dir, name + ".cpp")
+        with open(path, "w") as f:
+            f.write(text)
+        jobs.append((["g++", *flags, "-c", path, "-o", path + ".o"], path + ".o"))
+    switch = os.path.join(src_dir, "simt_switch.cpp")
+    with open(switch, "w") as f:
+        f.write(SWITCH_SRC)
+    jobs.append((["g++", *flags, "-c", switch, "-o", switch + ".o"], switch + ".o"))
+    stub = os.path.join(src_dir, "pipe_stub.cpp")
+    with open(stub, "w") as f:
+        f.write(PIPE_STUB)
+    jobs.append((["g++", *flags, "-c", stub, "-o", stub + ".o"], stub + ".o"))
+    for name in HOST_SOURCES:                                   # host code as it is (no CUDA in it)
+        obj = os.path.join(src_dir, name + ".o")
+        jobs.append((["g++", *HOST_FLAGS, "-w", "-c", os.path.join(CSRC, name), "-o", obj], obj))
+    procs = [(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), cmd) for cmd, _ in jobs]
+    for p, cmd in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("emulation build failed: %s\n%s" % (" ".join(cmd), out[-6000:]))
+        if verbose and out.strip():
+            print(out)
+    link = ["g++", "-shared", "-o", LIB, *[o for _, o in jobs], "-fopenmp"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("emulation link failed:\n" + r.stdout[-4000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,287 @@
+// TEST INFRASTRUCTURE — never part of libodis_b200.so, never on the product path.
+//
+// A small host emulation of the CUDA execution model, enough to run this repository's kernel SOURCE on the CPU so that kernel
+// logic (indexing, operation order, barriers, warp shuffles, last-block reductions, launch sequencing in the engine) can be
+// checked in the `-m "not gpu"` suite, where no GPU exists. tests/simt/build_emu.py rewrites the launch syntax
+// (`k<<<g, b, s, st>>>(args)` -> simt::launch), `extern __shared__` and the inline PTX of csrc/*.cu and compiles the result
+// against this header (found as <cuda_runtime.h> through tests/simt/stub/) into tests/_build/libodis_b200_emu.so.
+//
+// Model: CTAs run one after another; the threads of a CTA are fibers (a 10-instruction x86-64 context switch) that run until they reach __syncthreads or a
+// warp shuffle, where they wait for their CTA / warp. Shared memory is `static` storage (one CTA is alive at a time), global
+// memory is the host heap, streams and events are no-ops (everything executes at once, in program order), a captured graph
+// is the list of its launches. What this does NOT model: memory consistency between concurrently running CTAs or GPUs,
+// timing, caches. It is a logic check, not a substitute for the B200 runs.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#define ODIS_SIMT_EMULATION 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+#define __align__(n) alignas(n)
+
+using std::max;
+using std::min;
+
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
+inline int2 make_int2(int a, int b) { return int2{a, b}; }
+
+inline uint3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0};
+inline dim3 blockDim, gridDim;
+
+// ---- CUDA runtime subset: synchronous, host heap ----
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0, cudaErrorUnknown = 999, cudaErrorPeerAccessAlreadyEnabled = 704;
+typedef struct simt_stream* cudaStream_t;
+typedef struct simt_event* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeRelaxed };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+
+namespace simt {
+using Closure = std::function<void()>;
+struct Graph { std::vector<Closure> launches; };
+inline Graph* capturing = nullptr;
+inline long long fake_clock = 0;
+inline long long kernels_run = 0;
+}  // namespace simt
+typedef simt::Graph* cudaGraph_t;
+typedef simt::Graph* cudaGraphExec_t;
+
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime: unsupported call"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorUnknown; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
+    for (size_t r = 0; r < h; r++) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+template <class T>
+inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t n) { std::memcpy((void*)&symbol, src, n); return cudaSuccess; }
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)std::malloc(1); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)std::malloc(1); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorUnknown; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorUnknown; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { simt::capturing = new simt::Graph(); return cudaSuccess; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = simt::capturing; simt::capturing = nullptr; return cudaSuccess; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = new simt::Graph(*g); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) { for (auto& c : g->launches) c(); return cudaSuccess; }
+
+// ---- device intrinsics ----
+inline double __drcp_rn(double x) { return 1.0 / x; }                   // rcp.rn.f64 is correctly rounded, as IEEE division
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline long long clock64() { return simt::fake_clock += 1000; }
+
+namespace simt {
+
+constexpr int kStackBytes = 256 * 1024;
+enum State { RUNNABLE, AT_BARRIER, AT_SHUFFLE, DONE };
+// x86-64 System V context switch (callee-saved registers + stack pointer), defined once in simt_switch.cpp (build_emu.py):
+// saves the caller's context on its own stack, stores that stack pointer in *from_sp and resumes the context at to_sp.
+extern "C" void simt_switch(void** from_sp, void* to_sp);
+struct Fiber {
+    void* sp = nullptr;
+    char* stack = nullptr;
+    State state = DONE;
+};
+struct WarpExchange { uint64_t pending[32], result[32]; };
+struct Cta {
+    std::vector<Fiber> fibers;
+    std::vector<WarpExchange> warps;
+    void* scheduler_sp = nullptr;
+    int current = -1;
+    const Closure* body = nullptr;
+};
+inline Cta cta;
+alignas(16) inline unsigned char dynamic_shared[228 * 1024];
+
+inline void fiber_entry() {
+    (*cta.body)();
+    Fiber& f = cta.fibers[(size_t)cta.current];
+    f.state = DONE;
+    simt_switch(&f.sp, cta.scheduler_sp);          // never resumed
+    std::abort();
+}
+inline void yield(State why) {
+    Fiber& f = cta.fibers[(size_t)cta.current];
+    f.state = why;
+    simt_switch(&f.sp, cta.scheduler_sp);
+}
+// a fresh context that simt_switch can resume: six callee-saved register slots, the entry address its `ret` jumps to, and a
+// null return address so that the entry function starts with the ABI's stack alignment
+inline void prepare(Fiber& f) {
+    uintptr_t top = ((uintptr_t)f.stack + kStackBytes) & ~(uintptr_t)15;
+    void** slot = (void**)top;
+    *--slot = nullptr;                              // fake return address of fiber_entry
+    *--slot = (void*)&fiber_entry;
+    for (int r = 0; r < 6; r++) *--slot = nullptr;  // rbp rbx r12 r13 r14 r15
+    f.sp = (void*)slot;
+}
+inline void set_thread(int linear, const dim3& block) {
+    threadIdx.x = (unsigned)linear % block.x;
+    threadIdx.y = ((unsigned)linear / block.x) % block.y;
+    threadIdx.z = (unsigned)linear / (block.x * block.y);
+}
+
+// one CTA: fibers run round-robin to their next barrier / shuffle / end
+inline void run_cta(const dim3& block, const Closure& body) {
+    const int n = (int)(block.x * block.y * block.z);
+    if ((int)cta.fibers.size() < n) {
+        const size_t old = cta.fibers.size();
+        cta.fibers.resize((size_t)n);
+        for (size_t i = old; i < (size_t)n; i++) cta.fibers[i].stack = (char*)std::malloc(kStackBytes);
+    }
+    cta.warps.assign((size_t)(n + 31) / 32, WarpExchange{});
+    cta.body = &body;
+    for (int i = 0; i < n; i++) {
+        Fiber& f = cta.fibers[(size_t)i];
+        prepare(f);
+        f.state = RUNNABLE;
+    }
+    int alive = n;
+    while (alive > 0) {
+        bool progressed = false;
+        for (int i = 0; i < n; i++) {
+            Fiber& f = cta.fibers[(size_t)i];
+            if (f.state != RUNNABLE) continue;
+            cta.current = i;
+            set_thread(i, block);
+            simt_switch(&cta.scheduler_sp, f.sp);
+            progressed = true;
+            if (f.state == DONE) alive--;
+        }
+        // warps whose live lanes all wait at a shuffle exchange their values
+        for (int w = 0; w < (n + 31) / 32; w++) {
+            int waiting = 0, live = 0;
+            for (int l = 0; l < 32 && w * 32 + l < n; l++) {
+                const State st = cta.fibers[(size_t)(w * 32 + l)].state;
+                live += st != DONE;
+                waiting += st == AT_SHUFFLE;
+            }
+            if (live > 0 && waiting == live) {
+                std::memcpy(cta.warps[(size_t)w].result, cta.warps[(size_t)w].pending, sizeof cta.warps[(size_t)w].result);
+                for (int l = 0; l < 32 && w * 32 + l < n; l++)
+                    if (cta.fibers[(size_t)(w * 32 + l)].state == AT_SHUFFLE) cta.fibers[(size_t)(w * 32 + l)].state = RUNNABLE;
+                progressed = true;
+            }
+        }
+        // the barrier opens when every live thread of the CTA has arrived
+        int at_barrier = 0, live = 0;
+        for (int i = 0; i < n; i++) {
+            live += cta.fibers[(size_t)i].state != DONE;
+            at_barrier += cta.fibers[(size_t)i].state == AT_BARRIER;
+        }
+        if (live > 0 && at_barrier == live) {
+            for (int i = 0; i < n; i++)
+                if (cta.fibers[(size_t)i].state == AT_BARRIER) cta.fibers[(size_t)i].state = RUNNABLE;
+            progressed = true;
+        }
+        if (!progressed && alive > 0) {
+            std::fprintf(stderr, "simt_emu: deadlock in a CTA (divergent barrier / shuffle)\n");
+            std::abort();
+        }
+    }
+}
+
+inline void run_grid(dim3 grid, dim3 block, const Closure& body) {
+    gridDim = grid;
+    blockDim = block;
+    for (unsigned z = 0; z < grid.z; z++)
+        for (unsigned y = 0; y < grid.y; y++)
+            for (unsigned x = 0; x < grid.x; x++) {
+                blockIdx = uint3{x, y, z};
+                run_cta(block, body);
+            }
+    kernels_run++;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...): arguments are copied at launch time, as CUDA does
+template <class K, class... A>
+inline void launch(dim3 grid, dim3 block, size_t /*smem*/, cudaStream_t, K kernel, A&&... args) {
+    auto bound = std::make_tuple(std::decay_t<A>(std::forward<A>(args))...);
+    Closure run = [grid, block, kernel, bound]() mutable {
+        Closure body = [&]() { std::apply([&](auto&... a) { kernel(a...); }, bound); };
+        run_grid(grid, block, body);
+    };
+    if (capturing) capturing->launches.push_back(run);
+    else run();
+}
+
+template <class T>
+inline T shuffle(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    const int linear = cta.current, lane = linear & 31;
+    WarpExchange& w = cta.warps[(size_t)(linear >> 5)];
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    w.pending[lane] = bits;
+    yield(AT_SHUFFLE);
+    if (src_lane < 0 || src_lane > 31) src_lane = lane;
+    T out;
+    std::memcpy(&out, &w.result[src_lane], sizeof(T));
+    return out;
+}
+
+}  // namespace simt
+
+inline void __syncthreads() { simt::yield(simt::AT_BARRIER); }
+inline void __nanosleep(unsigned) {}
+template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) { const int lane = simt::cta.current & 31; return simt::shuffle(v, lane + delta < 32 ? lane + delta : lane); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask) { return simt::shuffle(v, (simt::cta.current & 31) ^ mask); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return simt::shuffle(v, src & 31); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; }
+inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; *p = old + v; return old; }

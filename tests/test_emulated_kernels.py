@@ -1,0 +1,63 @@
+"""Kernel logic and engine sequencing checked WITHOUT a GPU: the `-m gpu` parity tests themselves, run in a subprocess against
+tests/_build/libodis_b200_emu.so — the library's own kernel and engine sources compiled for the host against a small emulation
+of the CUDA execution model (tests/simt/simt_emu.h: CTAs in sequence, threads as fibers, barriers, warp shuffles, atomics,
+captured graphs; tests/simt/build_emu.py rewrites launch syntax and inline PTX). The arithmetic is the kernels' own, so the
+bit-for-bit assertions against the reference fixtures and the oracle hold or fail exactly as they would for the device code's
+logic. What this cannot show: anything about speed, memory-ordering between concurrently running CTAs, the bulk-async staged
+kernels (cp.async.bulk / mbarrier; the engine is switched to the direct-load kernels, same arithmetic), multi-GPU peer traffic,
+tensor-core mma. It is test infrastructure: the product library has no CPU path and `geodesicodis_b200` never loads this file
+unless ODIS_B200_LIB says so (as this test's subprocess does).
+
+Two groups: a control group of tests that have passed on real B200s (the emulation must agree with the hardware's verdict), and
+the tests of code written after the last GPU run (operator surface, hybrids, 3-launch self-gravity, 4-launch nonlinear step,
+overlapped output, analytical start)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "tests/test_run_gpu.py", "tests/test_self_gravity_gpu.py"]
+NEW = ["tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
+       "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py"]
+# not meaningful under emulation: full-size grids; tests that the one-launch fused / staged kernels (not emulated) are selected or
+# rejected; the slowest parameter sets
+SKIP = ("not large_grid and not enable_errors and not enable_advection_errors and not pipelined_kernels_agree "
+        "and not high_degree_matrix_free and not 5-12 and not 6-4 and not 6-2")
+
+
+@pytest.fixture(scope="module")
+def emulated_library(built_library):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    import build_emu
+    lib = build_emu.build()
+    libdir = os.path.join(os.path.dirname(lib), "emu_libdir")            # for the hybrid programs, which link libodis_b200.so by name
+    os.makedirs(libdir, exist_ok=True)
+    link = os.path.join(libdir, "libodis_b200.so")
+    if not os.path.islink(link):
+        os.symlink(os.path.join("..", os.path.basename(lib)), link)
+    return lib, libdir
+
+
+def run_gpu_tests_on_the_emulation(lib, libdir, files):
+    env = dict(os.environ, ODIS_B200_LIB=lib, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    cmd = [sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x", "-k", SKIP, "-p", "no:cacheprovider"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    tail = r.stdout[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail, tail
+    return tail
+
+
+def test_emulation_agrees_with_hardware_on_validated_kernels(emulated_library):
+    tail = run_gpu_tests_on_the_emulation(*emulated_library, CONTROL)
+    passed = int(tail.split(" passed")[0].split()[-1])
+    assert passed >= 50, tail
+
+
+def test_code_written_after_the_last_gpu_run(emulated_library):
+    tail = run_gpu_tests_on_the_emulation(*emulated_library, NEW)
+    passed = int(tail.split(" passed")[0].split()[-1])
+    assert passed >= 30, tail
