@@ -21,7 +21,7 @@ from conftest import ROOT
 
 CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "tests/test_run_gpu.py", "tests/test_self_gravity_gpu.py"]
 NEW = ["tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
-       "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py"]
+       "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py"]
 # not meaningful under emulation: full-size grids; tests that the one-launch fused / staged kernels (not emulated) are selected or
 # rejected; the slowest parameter sets
 SKIP = ("not large_grid and not enable_errors and not enable_advection_errors and not pipelined_kernels_agree "
