@@ -492,7 +492,9 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
     // ---- state ----
-    const int blocks = Fp / 32;             // one energy partial per warp of edges (>= blocks of edge_diagnostics)
+    // one energy partial per warp of edges (>= blocks of edge_diagnostics); with block_threads 256 / 512 the direct edge kernel's last
+    // block writes partials for warps beyond the 128-edge tile padding, hence the slack
+    const int blocks = Fp / 32 + 16;
     if ((rc = dev_alloc(s, &s->d_eu[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_eu[1], (size_t)Np)) ||
         (rc = dev_alloc(s, &s->d_hv[0], (size_t)Fp)) || (rc = dev_alloc(s, &s->d_hv[1], (size_t)Fp)) ||
         (rc = dev_alloc(s, &s->d_he[0], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[1], (size_t)Np)) || (rc = dev_alloc(s, &s->d_he[2], (size_t)Np)) ||

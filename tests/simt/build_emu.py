@@ -40,7 +40,7 @@ SWITCH_SRC = r'''// context switch of the SIMT emulation's fibers (tests/simt/si
 #error "the SIMT emulation's context switch is written for x86-64"
 #endif
 asm(R"(
-    .text
+    .pushsection .text
     .globl simt_switch
     .type simt_switch,@function
 simt_switch:
@@ -60,7 +60,7 @@ simt_switch:
     popq %rbp
     ret
     .size simt_switch,.-simt_switch
-    .section .note.GNU-stack,"",@progbits
+    .popsection
 )");
 '''
 
@@ -196,16 +196,22 @@ def transform(name: str, text: str) -> str:
     return f"// generated by tests/simt/build_emu.py from csrc/{name}: {n_launch} launches, {n_asm} asm statements, {n_dyn} dynamic shared arrays rewritten\n" + text
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str:
+    """asan: AddressSanitizer build (libodis_b200_emu_asan.so; load with LD_PRELOAD=$(gcc -print-file-name=libasan.so)): device
+    arrays are host heap blocks, so an out-of-range access in a kernel is reported like compute-sanitizer's memcheck would."""
     from geodesicodis_b200.build import HOST_SOURCES, HOST_FLAGS
-    src_dir = os.path.join(OUT, "emu_src")
+    global LIB
+    lib = os.path.join(OUT, "libodis_b200_emu_asan.so" if asan else "libodis_b200_emu.so")
+    LIB = lib
+    src_dir = os.path.join(OUT, "emu_src_asan" if asan else "emu_src")
     os.makedirs(src_dir, exist_ok=True)
     newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))
     newest = max(newest, os.path.getmtime(os.path.join(HERE, "simt_emu.h")), os.path.getmtime(os.path.abspath(__file__)),
                  os.path.getmtime(os.path.join(ROOT, "include", "odis_b200.h")))
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
-    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
+    san = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    flags = ["-O1", *san, "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
     jobs = []
     for name in CUDA_SOURCES:
         with open(os.path.join(CSRC, name)) as f:
@@ -233,7 +239,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("emulation build failed: %s\n%s" % (" ".join(cmd), out[-6000:]))
         if verbose and out.strip():
             print(out)
-    link = ["g++", "-shared", "-o", LIB, *[o for _, o in jobs], "-fopenmp"]
+    link = ["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", LIB, *[o for _, o in jobs], "-fopenmp"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulation link failed:\n" + r.stdout[-4000:])
@@ -242,4 +248,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, asan="--asan" in sys.argv))

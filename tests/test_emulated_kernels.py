@@ -41,9 +41,10 @@ def emulated_library(built_library):
     return lib, libdir
 
 
-def run_gpu_tests_on_the_emulation(lib, libdir, files):
+def run_gpu_tests_on_the_emulation(lib, libdir, files, extra_env=None, select=SKIP):
     env = dict(os.environ, ODIS_B200_LIB=lib, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
-    cmd = [sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x", "-k", SKIP, "-p", "no:cacheprovider"]
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x", "-k", select, "-p", "no:cacheprovider"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     tail = r.stdout[-3000:]
     assert r.returncode == 0, tail
@@ -61,3 +62,19 @@ def test_code_written_after_the_last_gpu_run(emulated_library):
     tail = run_gpu_tests_on_the_emulation(*emulated_library, NEW)
     passed = int(tail.split(" passed")[0].split()[-1])
     assert passed >= 30, tail
+
+
+def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
+    """The emulation built with -fsanitize=address: device arrays are host heap blocks, so any out-of-range load or store of a
+    kernel (padding rows, the last partial block, per-CTA partial buffers with 256 / 512-thread blocks) aborts the run."""
+    import build_emu
+    asan_rt = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    if not os.path.isabs(asan_rt) or not os.path.exists(asan_rt):
+        pytest.skip("no AddressSanitizer runtime with this compiler")
+    lib = build_emu.build(asan=True)
+    files = ["tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py",
+             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py"]
+    select = SKIP + " and not l5_ and not l6_ and not 5-8 and not 6-4 and not full_orbit and not random_state"
+    tail = run_gpu_tests_on_the_emulation(lib, emulated_library[1], files, select=select,
+                                          extra_env={"LD_PRELOAD": asan_rt, "ASAN_OPTIONS": "detect_leaks=0:halt_on_error=1"})
+    assert int(tail.split(" passed")[0].split()[-1]) >= 40, tail
