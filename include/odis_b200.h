@@ -387,7 +387,7 @@ typedef struct odis_run_options {
                            * the surface type's per-degree factors (matrix-free kernels); 2: the same with the stored basis */
     int64_t max_steps;    /* > 0: stop after this many steps even if the loop bound is larger */
     int32_t overlap_output; /* 1: dumps go through odis_snapshot_begin/_wait: the next output interval is computed while the previous
-                             * dump is copied out and written to data.h5 (same files, byte for byte). 0: synchronous dumps */
+                             * dump is copied out and written to data.h5 (same datasets, log lines and restart files). 0: synchronous dumps */
     int32_t reserved;
 } odis_run_options;
 
