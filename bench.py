@@ -146,6 +146,68 @@ def cpu_baseline_port(mesh, prm: dict, budget_s: float = 15.0, sh_degree: int = 
                       + (f" (self-gravity term to degree {sh_degree} included)" if sh_degree >= 2 else "") + ", oracle/lte_oracle.c (gcc -O2), single thread"}
 
 
+def variant_probe(args) -> None:
+    """Child process of the N = 1 bench (own CUDA context, so a fault in an opt-in kernel selection cannot take the headline
+    measurement with it): times one selection and checks it against the default selection; prints one JSON line."""
+    import geodesicodis_b200 as odis
+    name = args.variant_probe
+    out = {"probe": name}
+    if name == "self_gravity_3_launch":
+        pos, fr, cen = odis.generate_grid(args.level)
+        mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
+        prm, L, S = workload_params(mesh), max(args.sh_degree, 2), args.substeps
+        ref, alt = odis.Solver(mesh, prm), odis.Solver(mesh, dict(prm, kernel_select=16))
+        for sv in (ref, alt):
+            sv.enable_self_gravity(L, shell_factor(L))
+            sv.step(2 * S)
+        a, b = ref.field(odis.FIELD_ETA), alt.field(odis.FIELD_ETA)
+        out["max_rel_diff_eta_vs_default_after_%d_steps" % (2 * S)] = float(np.abs(a - b).max() / np.abs(a).max())
+        n = 10 * S
+        l0 = alt.launches
+        out["timesteps_per_s"] = round(n / (alt.step_timed(n) * 1e-3), 1)
+        out["launches_per_step"] = (alt.launches - l0) / n
+        out["default_timesteps_per_s_same_process"] = round(n / (ref.step_timed(n) * 1e-3), 1)
+        e, c, g = alt.step_profiled_sh(200)
+        out["avg_us"] = {"edge": round(e / 200 * 1e3, 2), "cell_with_analysis": round(c / 200 * 1e3, 2), "solve_synthesis": round(g / 200 * 1e3, 2)}
+    elif name == "nonlinear":
+        level = args.probe_level                                 # 8: 163,842 cells (BASELINE 'L7'), the shipped input.in physics
+        pos, fr, cen = odis.generate_grid(level)
+        r = 6.37122e6
+        mesh = odis.Mesh.from_arrays(pos, fr, cen, r)
+        nl = odis.nonlinear_tables(mesh, 0.5)
+        dmin = float(mesh.tables["face_node_dist"].min())
+        prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.2 * dmin / math.sqrt(9.80616 * 8e3), radius=r, omega=7.292e-5, love_reduct=1.0, ecc=0.01,
+                   obl=math.radians(-2.0), shell_thickness=0.0, semimajor_axis=0.0, potential=1, friction=0, surface=0, init_load=0, reorder=1)
+        res = {}
+        for key, sel in (("6_launch_default", 0), ("4_launch", 32)):
+            sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
+            sv.enable_advection(nl)
+            sv.step(60)
+            res[key] = sv.field(odis.FIELD_ETA)
+            out[key + "_timesteps_per_s"] = round(400 / (sv.step_timed(400) * 1e-3), 1)
+            sv.close()
+        out["cells"] = mesh.n_cells
+        out["fields_identical"] = bool(np.array_equal(res["6_launch_default"], res["4_launch"]))
+    else:
+        out["error"] = "unknown probe"
+    print(json.dumps(out), flush=True)
+
+
+def run_probe(name: str, args) -> dict:
+    """Runs `bench.py --variant-probe name` in a subprocess; any failure is recorded instead of raised."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--variant-probe", name, "--level", str(args.level), "--sh-degree", str(args.sh_degree),
+           "--substeps", str(args.substeps)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"probe": name, "error": f"exit {r.returncode}: {(r.stderr or r.stdout)[-300:]}"}
+    except Exception as e:                                           # timeout, spawn failure, bad JSON
+        return {"probe": name, "error": repr(e)[:300]}
+
+
 def run_ours(args) -> None:
     import torch
     import geodesicodis_b200 as odis
@@ -285,6 +347,10 @@ def run_ours(args) -> None:
             n = max(S, min(K * S, 1000))
             variants[name] = {"timesteps_per_s": round(n / (alt.step_timed(n) * 1e-3), 1)}
             alt.close()
+    if variants is not None and not args.no_probes:
+        # opt-in kernel selections that are not the default, each timed in its own process (not part of `value`)
+        torch.cuda.synchronize()
+        variants["opt_in_selections"] = [run_probe("self_gravity_3_launch", args), run_probe("nonlinear", args)]
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
@@ -393,10 +459,15 @@ def main() -> None:
     ap.add_argument("--ref-substeps", type=int, default=2, help="LTE time steps per bench step for --impl reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra device-resident timings with other --sh-degree values")
+    ap.add_argument("--no-probes", action="store_true", help="skip the subprocess timings of the opt-in kernel selections")
+    ap.add_argument("--variant-probe", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--probe-level", type=int, default=8, help=argparse.SUPPRESS)
     ap.add_argument("--sh-degree", type=int, default=2, help="self-gravity term by spherical harmonics to this degree (the shipped input.in's "
                     "'sh degree' is 2); 0 = off, as at reference HEAD where the term is commented out")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.variant_probe:
+        variant_probe(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
