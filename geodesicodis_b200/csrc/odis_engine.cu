@@ -110,6 +110,7 @@ struct odis_solver {
     // nonlinear branch (odis_enable_advection)
     bool nl_on = false;
     bool nl_fused = false;           // params.reserved[0] bit 5: the 4-launch variant of the nonlinear step
+    bool cell_occ = false;           // params.reserved[0] bit 6: per-step cell update with the register-capped (50 % occupancy) kernel
     int nl_launches() const { return nl_fused ? odis::kNlLaunchesFused : odis::kNlLaunches; }
     odis::NlTables nl{};
     double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
@@ -351,6 +352,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->use_graph = (prm->reserved[0] & 8) == 0;
     s->sh_fused_req = (prm->reserved[0] & 16) != 0;
     s->nl_fused = (prm->reserved[0] & 32) != 0;
+    s->cell_occ = (prm->reserved[0] & 64) != 0;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -1101,12 +1103,12 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
         ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, s->stream));
     } else if (s->sh_on && s->sh_fused) {
         // 3-launch variant: the cell update leaves the harmonic sums of eta^{n+1} over groups of its CTAs
-        odis::launch_cell_step_sg(ct, s->phys, cs, mode, next, s->sg_work(), s->stream);
+        odis::launch_cell_step_sg(ct, s->phys, cs, mode, next, s->sg_work(), s->cell_occ, s->stream);
     } else {
         odis::HaloInline hc;
         if (inline_e) hc = halo_inline_cell(s);
-        odis::launch_cell_step(ct, s->phys, cs, mode, next, odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U, s->prm.block_threads,
-                               inline_e ? &hc : nullptr, s->stream);
+        odis::launch_cell_step(ct, s->phys, cs, mode, next, odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U,
+                               s->cell_occ ? odis::kCellOccupancyVariant : s->prm.block_threads, inline_e ? &hc : nullptr, s->stream);
     }
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;

@@ -275,9 +275,11 @@ __device__ __forceinline__ double tidal_potential(const Physics& p, const StepSc
     }
 }
 
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                             int flags, HaloInline halo) {
+// kMinBlocks > 0 caps the registers so that that many CTAs fit an SM (opt-in variant: 8 x 128 threads = 50 % occupancy instead of
+// 37.5 %, at the price of a few spilled values); 0 = no cap, the default.
+template <int kThreads, int kMinBlocks = 0>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
+                                                                         int flags, HaloInline halo) {
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -361,8 +363,9 @@ __device__ __forceinline__ double warp_sum_all(double x) {      // butterfly: fi
 // (odis_sh.cu); each warp reduces its 32 cells, the CTA leaves one partial per basis row, and the LAST CTA of every group of
 // kCellSgGroup consecutive CTAs to finish adds the group's partials in CTA order. Sums are therefore independent of the
 // order in which CTAs run. sh_solve_synthesis (odis_sh.cu) finishes the sum over the groups.
-template <int kThreads, int LT>
-__global__ void __launch_bounds__(kThreads) cell_step_sg_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next, CellSgWork sg) {
+template <int kThreads, int LT, int kMinBlocks = 0>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
+                                                                            CellSgWork sg) {
     constexpr int kRows = (LT + 1) * (LT + 1);
     constexpr int kWarps = kThreads / 32;
     static_assert(kRows <= kThreads, "one thread per basis row writes the CTA partial");
@@ -649,6 +652,10 @@ void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s,
     HaloInline none;
     none.n_bnd = 0;
     none.wait_from = 0x7fffffff;
+    if (block_threads == kCellOccupancyVariant) {        // 128 threads, registers capped for 8 CTAs per SM
+        cell_step_kernel<128, 8><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
+        return;
+    }
     dispatch_threads(block_threads, [&](auto bt) {
         constexpr int kT = decltype(bt)::value;
         cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
@@ -662,8 +669,16 @@ cudaError_t cell_sg_configure() {
 int cell_sg_ctas(int n_active) { return (n_active + kCellSgThreads - 1) / kCellSgThreads; }
 bool cell_sg_supports(int l_max) { return l_max >= 2 && l_max <= kCellSgMaxDegree; }
 void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
-                         cudaStream_t stream) {
+                         bool cap_registers, cudaStream_t stream) {
     const int grid = cell_sg_ctas(t.n_active);
+    if (cap_registers) {                                  // 64 registers: 8 CTAs per SM instead of 5
+        switch (sg.l_max) {
+            case 2: cell_step_sg_kernel<kCellSgThreads, 2, 8><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+            case 3: cell_step_sg_kernel<kCellSgThreads, 3, 8><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+            default: cell_step_sg_kernel<kCellSgThreads, 4, 8><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+        }
+        return;
+    }
     switch (sg.l_max) {
         case 2: cell_step_sg_kernel<kCellSgThreads, 2><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
         case 3: cell_step_sg_kernel<kCellSgThreads, 3><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;

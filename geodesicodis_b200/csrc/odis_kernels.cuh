@@ -141,7 +141,9 @@ cudaError_t launch_step_fused(const FusedTables& t, const Physics& p, const Fuse
 
 void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, int block_threads,
                       cudaStream_t stream);
-// flags: CellFlags (update eta and/or the potential)
+// flags: CellFlags (update eta and/or the potential). block_threads: 128 (default), 256, 512, or kCellOccupancyVariant (128 threads with
+// the register count capped at 64 for 50 % occupancy; opt-in, odis_params.reserved[0] bit 6)
+constexpr int kCellOccupancyVariant = -128;
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                       int flags, int block_threads, const HaloInline* halo, cudaStream_t stream);
 // Opt-in variant for runs with the self-gravity term (odis_params.reserved[0] bit 4): the cell update also accumulates the
@@ -164,7 +166,7 @@ cudaError_t cell_sg_configure();    // recurrence coefficients -> constant memor
 int cell_sg_ctas(int n_active);
 bool cell_sg_supports(int l_max);
 void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
-                         cudaStream_t stream);
+                         bool cap_registers, cudaStream_t stream);
 // spins (bounded by kHaloSpinCycles) until every neighbour's flag has reached ctl->epoch[0]: all pushes of the
 // exchanges this rank took part in have landed
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream);

@@ -149,7 +149,8 @@ typedef struct odis_params {
                              *     odis_enable_self_gravity, degree <= 4, unpartitioned): 3 launches per step instead of 5 — the harmonic
                              *     analysis is folded into the cell update and the solve into the synthesis (sums associate differently:
                              *     fields agree with the default to ~1e-13 relative, not bit for bit). bit 5 (with odis_enable_advection):
-                             *     the nonlinear step in 4 gather launches instead of 6 (bit-identical fields). Rest must be 0. */
+                             *     the nonlinear step in 4 gather launches instead of 6 (bit-identical fields). bit 6: the per-step cell
+                             *     update compiled with a 64-register cap (50 % instead of 37.5 % occupancy; bit-identical fields). Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {

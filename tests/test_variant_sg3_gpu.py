@@ -9,10 +9,11 @@ from test_self_gravity_gpu import rel_err, setup
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("select", [16, 80])                       # 80: the same with the cell kernel's registers capped at 64
 @pytest.mark.parametrize("level,l_max", [(4, 2), (5, 2), (6, 2), (5, 3), (6, 4)])
-def test_three_launch_variant_matches_oracle_and_default_path(odis, level, l_max):
+def test_three_launch_variant_matches_oracle_and_default_path(odis, level, l_max, select):
     mesh, pos, prm, factor, state, s_default, o, Y = setup(odis, level, l_max)
-    s = odis.Solver(mesh, dict(prm, reorder=1, semimajor_axis=0.0, kernel_select=16))
+    s = odis.Solver(mesh, dict(prm, reorder=1, semimajor_axis=0.0, kernel_select=select))
     for solver in (s, s_default):
         solver.enable_self_gravity(l_max, factor)
         solver.set_state(*state, iter=5)
@@ -31,7 +32,7 @@ def test_three_launch_variant_matches_oracle_and_default_path(odis, level, l_max
     assert np.allclose(s.dissipation_series()[1:], series_o, rtol=1e-10, atol=0.0)
     assert np.abs(s.sh_coefficients() - s_default.sh_coefficients()).max() <= 1e-11 * max(1.0, np.abs(s_default.sh_coefficients()).max())
     # repeatable to the bit: the sums do not depend on the order in which CTAs finish
-    again = odis.Solver(mesh, dict(prm, reorder=1, semimajor_axis=0.0, kernel_select=16))
+    again = odis.Solver(mesh, dict(prm, reorder=1, semimajor_axis=0.0, kernel_select=select))
     again.enable_self_gravity(l_max, factor)
     again.set_state(*state, iter=5)
     again.step(n)
