@@ -193,6 +193,33 @@ def variant_probe(args) -> None:
             sv.close()
         out["cells"] = mesh.n_cells
         out["fields_identical"] = bool(np.array_equal(res["6_launch_default"], res["4_launch"]))
+    elif name == "other_configs":
+        # the remaining single-GPU shapes of BASELINE.json's configs, each a short device-resident timing (kernels that have run on B200s
+        # before): [1] Enceladus free-surface ocean, 163,842 cells, linear drag, no self-gravity; [4] one GPU's share of the ensemble
+        # sweep: 32 members (ocean thickness x drag) on 40,962 cells, self-gravity to degree 8 as batched FP64 tensor-core GEMMs
+        pos, fr, cen = odis.generate_grid(args.probe_level)
+        mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"])
+        prm = dict(workload_params(mesh), surface=0, shell_thickness=0.0, love_reduct=1.0)
+        sv = odis.Solver(mesh, prm)
+        sv.step(200)
+        ms = sv.step_timed(2000) / 2000
+        _, alg = sv.footprint()
+        out["free_surface_%d_cells" % mesh.n_cells] = {"timesteps_per_s": round(1e3 / ms, 1), "cell_updates_per_s": round(mesh.n_cells * 1e3 / ms, 1),
+                                            "algorithmic_GBps": round(alg / (ms * 1e-3) / 1e9, 1)}
+        print(json.dumps(out), flush=True)
+        sv.close()
+        pos, fr, cen = odis.generate_grid(args.probe_level - 1)
+        mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
+        M = 32
+        plist = [workload_params(mesh, m, M) for m in range(M)]
+        ens = odis.Ensemble(mesh, plist)
+        ens.enable_self_gravity(8, shell_factor(8))
+        ens.step(40)
+        ms = ens.step_timed(400) / 400
+        info = ens.info()
+        out["ensemble_32_members_%d_cells_sh8" % mesh.n_cells] = {"batched_steps_per_s": round(1e3 / ms, 1), "member_steps_per_s": round(M * 1e3 / ms, 1),
+                                                      "algorithmic_GBps": round(info["algorithmic_bytes_per_step"] / (ms * 1e-3) / 1e9, 1)}
+        ens.close()
     else:
         out["error"] = "unknown probe"
     print(json.dumps(out), flush=True)
@@ -357,6 +384,7 @@ def run_ours(args) -> None:
         # opt-in kernel selections that are not the default, each timed in its own process (not part of `value`)
         torch.cuda.synchronize()
         variants["opt_in_selections"] = [run_probe("headline_selections", args), run_probe("nonlinear", args)]
+        variants["other_baseline_configs"] = run_probe("other_configs", args)
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
