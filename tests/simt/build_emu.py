@@ -4,8 +4,8 @@ execution model). Host .cpp files are compiled as they are. Used by tests/test_e
 engine's launch sequencing on the CPU; it is never loaded by the product path (geodesicodis_b200/_lib.py loads
 libodis_b200.so) and is no substitute for the B200 runs.
 
-Not emulated: the bulk-async staged kernels of odis_kernels_pipe.cu / odis_kernels_fused.cu (cp.async.bulk / mbarrier PTX) — the engine is switched to
-the direct-load kernels, which are the same arithmetic — multi-GPU peer flags, and the FP64 tensor-core mma of the ensemble
+The bulk-async staged kernels run too: mbarrier objects, cp.async.bulk (completing at once) and named barriers are modelled in
+simt_emu.h. Not emulated: multi-GPU peer flags (a second GPU never runs concurrently) and the FP64 tensor-core mma of the ensemble
 self-gravity GEMMs (aborts if reached)."""
 from __future__ import annotations
 
@@ -20,21 +20,7 @@ CSRC = os.path.join(ROOT, "geodesicodis_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_build")
 LIB = os.path.join(OUT, "libodis_b200_emu.so")
 
-CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_nl.cu", "odis_sh.cu", "odis_ensemble.cu", "odis_engine.cu"]
-PIPE_STUB = r'''// stand-in for odis_kernels_pipe.cu and odis_kernels_fused.cu (cp.async.bulk / mbarrier kernels are not emulated; the engine is switched to
-// the direct-load two-launch kernels)
-#include "odis_kernels.cuh"
-#include <cstdlib>
-namespace odis {
-int pipe_tile() { return 128; }
-cudaError_t pipe_configure() { return cudaSuccess; }
-cudaError_t launch_edge_step_pipe(const EdgeTables&, const Physics&, const EdgeState&, int, const HaloInline*, cudaStream_t) { std::abort(); }
-cudaError_t launch_cell_step_pipe(const CellTables&, const Physics&, const CellState&, int, const StepScalars&, cudaStream_t) { std::abort(); }
-cudaError_t launch_step_fused(const FusedTables&, const Physics&, const FusedState&, int, int, int, const StepScalars&, cudaStream_t) { std::abort(); }
-}
-'''
-
-
+CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_fused.cu", "odis_kernels_nl.cu", "odis_sh.cu", "odis_ensemble.cu", "odis_engine.cu"]
 SWITCH_SRC = r'''// context switch of the SIMT emulation's fibers (tests/simt/simt_emu.h): x86-64 System V, callee-saved registers + stack pointer
 #if !defined(__x86_64__)
 #error "the SIMT emulation's context switch is written for x86-64"
@@ -172,6 +158,22 @@ def rewrite_asm(s: str) -> tuple[str, int]:
             rep = f"{outs[0]} = *({ins[0]});"
         elif ptx.startswith("st."):
             rep = f"*({ins[0]}) = ({ins[1]});"
+        elif ptx.startswith("mbarrier.init"):
+            rep = f"simt::mbar_init({ins[0]}, {ins[1]});"
+        elif ptx.startswith("mbarrier.arrive.expect_tx"):
+            rep = f"simt::mbar_arrive({ins[0]}, {ins[1]});"
+        elif ptx.startswith("mbarrier.arrive"):
+            rep = f"simt::mbar_arrive({ins[0]}, 0);"
+        elif "mbarrier.try_wait.parity" in ptx:
+            rep = f"simt::mbar_wait({ins[0]}, {ins[1]});"
+        elif ptx.startswith("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"):
+            rep = f"simt::bulk_copy({ins[0]}, {ins[1]}, {ins[2]}, {ins[3]});"
+        elif ptx.startswith("fence."):
+            rep = ";"
+        elif ptx.startswith("bar.sync %0, %1"):
+            rep = f"simt::named_barrier({ins[0]}, {ins[1]});"
+        elif ptx.startswith("bar.sync 1, %0"):
+            rep = f"simt::named_barrier(1, {ins[0]});"
         elif ptx.startswith("mma.sync"):
             rep = 'do { std::fprintf(stderr, "simt_emu: tensor-core mma is not emulated\\n"); std::abort(); } while (0);'
         else:
@@ -184,15 +186,8 @@ def rewrite_asm(s: str) -> tuple[str, int]:
 def transform(name: str, text: str) -> str:
     text, n_launch = rewrite_launches(text)
     text, n_asm = rewrite_asm(text)
-    text, n_dyn = re.subn(r"extern\s+__shared__\s+(\w+)\s+(\w+)\s*\[\s*\]\s*;",
+    text, n_dyn = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?((?:unsigned\s+)?\w+)\s+(\w+)\s*\[\s*\]\s*;",
                           r"\1* \2 = reinterpret_cast<\1*>(simt::dynamic_shared);", text)
-    if name == "odis_engine.cu":
-        # the staged (cp.async.bulk / mbarrier) kernels are not emulated: same arithmetic through the direct-load kernels
-        for old, new in (("s->pipe_edge = (prm->reserved[0] & 1) == 0;", "s->pipe_edge = false;"),
-                         ("s->pipe_cell = (prm->reserved[0] & 2) != 0;", "s->pipe_cell = false;"),
-                         ("s->fused = (prm->reserved[0] & 4) != 0;", "s->fused = false;")):
-            assert text.count(old) == 1, old
-            text = text.replace(old, new)
     return f"// generated by tests/simt/build_emu.py from csrc/{name}: {n_launch} launches, {n_asm} asm statements, {n_dyn} dynamic shared arrays rewritten\n" + text
 
 
@@ -225,10 +220,6 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str
     with open(switch, "w") as f:
         f.write(SWITCH_SRC)
     jobs.append((["g++", *flags, "-c", switch, "-o", switch + ".o"], switch + ".o"))
-    stub = os.path.join(src_dir, "pipe_stub.cpp")
-    with open(stub, "w") as f:
-        f.write(PIPE_STUB)
-    jobs.append((["g++", *flags, "-c", stub, "-o", stub + ".o"], stub + ".o"))
     for name in HOST_SOURCES:                                   # host code as it is (no CUDA in it)
         obj = os.path.join(src_dir, name + ".o")
         jobs.append((["g++", *HOST_FLAGS, "-w", "-c", os.path.join(CSRC, name), "-o", obj], obj))

@@ -128,7 +128,7 @@ inline long long clock64() { return simt::fake_clock += 1000; }
 namespace simt {
 
 constexpr int kStackBytes = 256 * 1024;
-enum State { RUNNABLE, AT_BARRIER, AT_SHUFFLE, DONE };
+enum State { RUNNABLE, AT_BARRIER, AT_SHUFFLE, AT_NAMED_BARRIER, DONE };
 // x86-64 System V context switch (callee-saved registers + stack pointer), defined once in simt_switch.cpp (build_emu.py):
 // saves the caller's context on its own stack, stores that stack pointer in *from_sp and resumes the context at to_sp.
 extern "C" void simt_switch(void** from_sp, void* to_sp);
@@ -136,6 +136,8 @@ struct Fiber {
     void* sp = nullptr;
     char* stack = nullptr;
     State state = DONE;
+    int named_id = 0, named_count = 0;      // bar.sync id, count
+    long long spins = 0;                    // consecutive unsuccessful polls of an mbarrier
 };
 struct WarpExchange { uint64_t pending[32], result[32]; };
 struct Cta {
@@ -190,6 +192,7 @@ inline void run_cta(const dim3& block, const Closure& body) {
         Fiber& f = cta.fibers[(size_t)i];
         prepare(f);
         f.state = RUNNABLE;
+        f.spins = 0;
     }
     int alive = n;
     while (alive > 0) {
@@ -215,6 +218,17 @@ inline void run_cta(const dim3& block, const Closure& body) {
                 std::memcpy(cta.warps[(size_t)w].result, cta.warps[(size_t)w].pending, sizeof cta.warps[(size_t)w].result);
                 for (int l = 0; l < 32 && w * 32 + l < n; l++)
                     if (cta.fibers[(size_t)(w * 32 + l)].state == AT_SHUFFLE) cta.fibers[(size_t)(w * 32 + l)].state = RUNNABLE;
+                progressed = true;
+            }
+        }
+        // named barriers (bar.sync id, count): open when `count` threads wait on the id
+        for (int id = 1; id < 16; id++) {
+            int waiting = 0, need = 0;
+            for (int i = 0; i < n; i++)
+                if (cta.fibers[(size_t)i].state == AT_NAMED_BARRIER && cta.fibers[(size_t)i].named_id == id) { waiting++; need = cta.fibers[(size_t)i].named_count; }
+            if (waiting > 0 && waiting >= need) {
+                for (int i = 0; i < n; i++)
+                    if (cta.fibers[(size_t)i].state == AT_NAMED_BARRIER && cta.fibers[(size_t)i].named_id == id) cta.fibers[(size_t)i].state = RUNNABLE;
                 progressed = true;
             }
         }
@@ -275,9 +289,58 @@ inline T shuffle(T v, int src_lane) {
     return out;
 }
 
+// ---- shared-window addresses, mbarrier, 1-D bulk copies (the staged kernels) ----
+// Dynamic shared memory is one static buffer; a "shared address" is the offset into it.
+inline uint32_t shared_address(const void* p) {
+    const std::ptrdiff_t off = (const unsigned char*)p - dynamic_shared;
+    if (off < 0 || off >= (std::ptrdiff_t)sizeof dynamic_shared) { std::fprintf(stderr, "simt_emu: address is not in dynamic shared memory\n"); std::abort(); }
+    return (uint32_t)off;
+}
+inline void* shared_pointer(uint32_t a) { return dynamic_shared + a; }
+// mbarrier object in its 64-bit shared-memory word: phase parity, arrivals still pending in this phase, the count they are reset
+// to, and the transaction bytes still expected (may go negative when a copy completes before its expect_tx, as in hardware)
+struct Mbarrier { uint32_t phase : 1; uint32_t pending : 15; uint32_t count : 15; int32_t tx; };
+static_assert(sizeof(Mbarrier) == 8, "mbarrier fits its shared-memory word");
+inline void mbar_check(Mbarrier* b) {
+    if (b->pending == 0 && b->tx == 0) { b->phase ^= 1u; b->pending = b->count; }
+}
+inline void mbar_init(uint32_t a, uint32_t count) { Mbarrier* b = (Mbarrier*)shared_pointer(a); b->phase = 0; b->pending = count; b->count = count; b->tx = 0; }
+inline void mbar_arrive(uint32_t a, uint32_t expect_bytes) {
+    Mbarrier* b = (Mbarrier*)shared_pointer(a);
+    if (b->pending == 0) { std::fprintf(stderr, "simt_emu: more arrivals than the mbarrier expects\n"); std::abort(); }
+    b->tx += (int32_t)expect_bytes;
+    b->pending -= 1;
+    mbar_check(b);
+}
+inline void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    if ((bytes & 15u) || (dst & 15u) || ((uintptr_t)src & 15u)) { std::fprintf(stderr, "simt_emu: cp.async.bulk needs 16-byte alignment and size\n"); std::abort(); }
+    std::memcpy(shared_pointer(dst), src, bytes);                  // completes at once
+    Mbarrier* b = (Mbarrier*)shared_pointer(bar);
+    b->tx -= (int32_t)bytes;
+    mbar_check(b);
+}
+// mbarrier.try_wait.parity loop: the phase with the given parity has completed when the barrier has moved on to the other parity
+inline void mbar_wait(uint32_t a, uint32_t parity) {
+    const Mbarrier* b = (const Mbarrier*)shared_pointer(a);
+    Fiber& f = cta.fibers[(size_t)cta.current];
+    while (b->phase == (parity & 1u)) {
+        if (++f.spins > 50000000) { std::fprintf(stderr, "simt_emu: mbarrier wait never satisfied (deadlock)\n"); std::abort(); }
+        yield(RUNNABLE);
+    }
+    f.spins = 0;
+}
+inline void named_barrier(int id, int count) {
+    Fiber& f = cta.fibers[(size_t)cta.current];
+    f.named_id = id;
+    f.named_count = count;
+    yield(AT_NAMED_BARRIER);
+}
+
 }  // namespace simt
 
 inline void __syncthreads() { simt::yield(simt::AT_BARRIER); }
+inline void __syncwarp(unsigned = 0xffffffffu) { (void)simt::shuffle(0, simt::cta.current & 31); }       // the warp's live lanes meet here
+inline size_t __cvta_generic_to_shared(const void* p) { return simt::shared_address(p); }
 inline void __nanosleep(unsigned) {}
 template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) { const int lane = simt::cta.current & 31; return simt::shuffle(v, lane + delta < 32 ? lane + delta : lane); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask) { return simt::shuffle(v, (simt::cta.current & 31) ^ mask); }
