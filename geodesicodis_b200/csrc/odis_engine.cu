@@ -209,8 +209,23 @@ int upload(odis_solver* s, T** p, const std::vector<T>& h) {
 }
 
 // Host-evaluated time factors for the potential at `time` (tidalPotentials.cpp:55-61).
-odis::StepScalars step_scalars(double omega, double time) {
+odis::StepScalars step_scalars(const odis_solver* s, double time) {
     odis::StepScalars m;
+    const double omega = s->prm.omega;
+    if (s->prm.potential == odis::P_PLANET) {
+        // PLANET (tidalPotentials.cpp:176-213): a companion on the inner 2:1 orbit with the reference's hard-wired mass and orbit (Io);
+        // the kernel gets cosphi, sinphi, factor, p in the slots cosM, sinM, cos2M, sin2M
+        const double m2 = 8.931938e+22, a1 = 421800000.0, a2 = s->prm.semimajor_axis;
+        const double n2 = omega, n1 = n2 * 2.0, nij = (n1 - n2);
+        const double cosnt = std::cos(nij * time), sinnt = std::sin(nij * time);
+        const double pp = std::pow(a1, 2.0) + std::pow(a2, 2.0) - 2. * a1 * a2 * cosnt;
+        m.cosM = (a1 - a2 * cosnt);
+        m.sinM = a2 * sinnt;
+        m.cos2M = 0.5 * 6.67408e-11 * m2 * std::pow(s->forcing_radius / pp, 2.0) / std::sqrt(pp);
+        m.sin2M = pp;
+        m.cos3M = m.cos4M = 0.0;
+        return m;
+    }
     m.cosM = std::cos(omega * time);
     m.sinM = std::sin(omega * time);
     m.cos2M = std::cos(2 * omega * time);
@@ -219,6 +234,13 @@ odis::StepScalars step_scalars(double omega, double time) {
     m.cos4M = std::cos(4 * omega * time);
     return m;
 }
+
+// PLANET forcing: the step kernels leave U = 0 for this type; one more pass writes it (before any self-gravity term is added)
+void enqueue_planet(odis_solver* s, double2* eu, int n_cells, const odis::StepScalars& host, const odis::StepScalars* dev) {
+    if (s->prm.potential != odis::P_PLANET) return;
+    odis::launch_planet_potential(s->cell_tables(n_cells), host, dev, eu, n_cells, s->stream);
+}
+int planet_launches(const odis_solver* s) { return s->prm.potential == odis::P_PLANET ? 1 : 0; }
 
 int ab3_mode(const odis_solver* s, int64_t iter) {
     if (iter > 1 || s->prm.init_load) return odis::AB3_FULL;      // temporalOperators.cpp:36
@@ -290,6 +312,9 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     if (world > mv->n_cells / 16) return fail(ODIS_ERR_ARG, "too many ranks for this grid");
     switch (prm->potential) {
         case odis::P_OBLIQ: case odis::P_OBLIQ_WEST: case odis::P_ECC: case odis::P_FULL: case odis::P_FULL2: case odis::P_NONE: break;
+        case odis::P_PLANET:
+            if (!(prm->semimajor_axis > 0.0)) return fail(ODIS_ERR_ARG, "potential PLANET needs the semimajor axis (globals->a)");
+            break;
         default:
             return fail(ODIS_ERR_UNSUPPORTED, "potential type has no expression in the reference (tidalPotentials.cpp:80-285) or is outside the hot path");
     }
@@ -348,7 +373,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->Fp = (s->Fo + tile - 1) / tile * tile;
     s->pipe_edge = (prm->reserved[0] & 1) == 0;
     s->pipe_cell = (prm->reserved[0] & 2) != 0;
-    s->fused = (prm->reserved[0] & 4) != 0;
+    s->fused = (prm->reserved[0] & 4) != 0 && prm->potential != odis::P_PLANET;      // PLANET forcing is a pass of its own (two-launch kernels)
     s->use_graph = (prm->reserved[0] & 8) == 0;
     s->sh_fused_req = (prm->reserved[0] & 16) != 0;
     s->nl_fused = (prm->reserved[0] & 32) != 0;
@@ -760,9 +785,10 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     // held cell, halo included
     const double t = s->prm.dt * (double)iter + s->prm.dt;
     odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
-    odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, t), odis::CELL_UPDATE_U, s->prm.block_threads,
+    odis::launch_cell_step(s->cell_tables(N), s->phys, cs, odis::AB3_FULL, step_scalars(s, t), odis::CELL_UPDATE_U, s->prm.block_threads,
                            nullptr, s->stream);
-    s->launches++;
+    enqueue_planet(s, s->d_eu[s->ecur], N, step_scalars(s, t), nullptr);
+    s->launches += 1 + planet_launches(s);
     if ((rc = enqueue_self_gravity(s, s->d_eu[s->ecur]))) return rc;
     s->launches += s->sh_launches();
     ODIS_CUDA(cudaGetLastError());
@@ -1055,15 +1081,16 @@ static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEven
     s->ecur = 1 - s->ecur;
     // forcing for the next step (current_time = dt*(iter+1), evaluated at current_time + dt), in place on the new {eta,U}
     odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
-    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, s->prm.dt * (double)(s->iter + 1) + s->prm.dt),
+    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt),
                            odis::CELL_UPDATE_U, s->prm.block_threads, nullptr, s->stream);
+    enqueue_planet(s, s->d_eu[s->ecur], s->N, step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt), nullptr);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
     { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 3], s->stream);
     s->cur = 1 - s->cur;
     s->iter++;
     s->last_mode = mode;
-    s->launches += 2 + s->nl_launches() + s->sh_launches();
+    s->launches += 2 + s->nl_launches() + planet_launches(s) + s->sh_launches();
     return ODIS_OK;
 }
 
@@ -1097,7 +1124,7 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
                        s->d_block_partial, (s->Fo + 31) / 32, s->pipe_edge ? nullptr : es.energy_out, dev_ctl ? &s->d_ctl->cur : nullptr};
     // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
-    const odis::StepScalars next = dev_ctl ? odis::StepScalars{} : step_scalars(s->prm.omega, s->prm.dt * (double)(s->iter + 1) + s->prm.dt);
+    const odis::StepScalars next = dev_ctl ? odis::StepScalars{} : step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt);
     if (s->pipe_cell) {
         if (inline_e) { int rc2 = halo_drain(s); if (rc2) return rc2; }
         ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, s->stream));
@@ -1112,6 +1139,7 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     }
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;
+    enqueue_planet(s, s->d_eu[s->ecur], ct.n_active, next, dev_ctl ? &s->d_ctl->cur : nullptr);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
     if (s->sh_on && s->sh_fused)
         odis::launch_sh_solve_synthesis(s->sh_tables(), s->sh_work(), s->d_sg_group, s->sg_group_stride, s->sg_groups(), s->prm.g, s->d_eu[s->ecur], s->N,
@@ -1121,7 +1149,7 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     s->cur = 1 - s->cur;
     s->iter++;
     s->last_mode = mode;
-    s->launches += 2 + s->sh_step_launches();
+    s->launches += 2 + planet_launches(s) + s->sh_step_launches();
     return ODIS_OK;
 }
 
@@ -1148,7 +1176,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             fs.energy_out = s->d_series + (s->iter - s->iter0);
             const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
             if (marks) cudaEventRecord((*marks)[(size_t)k * 4], s->stream);
-            ODIS_CUDA(odis::launch_step_fused(ft, s->phys, fs, mode, s->mode_lag, s->eta_lag ? 1 : 0, step_scalars(s->prm.omega, tnext), s->stream));
+            ODIS_CUDA(odis::launch_step_fused(ft, s->phys, fs, mode, s->mode_lag, s->eta_lag ? 1 : 0, step_scalars(s, tnext), s->stream));
             if (s->eta_lag) rotate_cell_history(s, s->mode_lag);
             s->ecur = 1 - s->ecur;
             if (s->world > 1) {                   // one exchange per step: v^{n+1} of my boundary edges
@@ -1173,7 +1201,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
     if (dev_ctl && nsteps > 0) {             // time factors of every step of this call, uploaded ahead (tidalPotentials.cpp:55-61)
         std::vector<odis::StepScalars> sc((size_t)nsteps);
         // forcing for the NEXT step: current_time = dt*(iter+1), evaluated at current_time + dt
-        for (int k = 0; k < nsteps; k++) sc[(size_t)k] = step_scalars(s->prm.omega, s->prm.dt * (double)(s->iter + k + 1) + s->prm.dt);
+        for (int k = 0; k < nsteps; k++) sc[(size_t)k] = step_scalars(s, s->prm.dt * (double)(s->iter + k + 1) + s->prm.dt);
         ODIS_CUDA(cudaMemcpyAsync(s->d_scal + (s->iter - s->iter0), sc.data(), sc.size() * sizeof(odis::StepScalars), cudaMemcpyHostToDevice, s->stream));
     }
     int done = 0;
@@ -1204,7 +1232,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             for (int r = 0; r < reps; r++) ODIS_CUDA(cudaGraphLaunch(it->second, s->stream));
             const int adv = reps * kGraphSteps;
             s->graph_launches += reps;
-            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0) + s->sh_step_launches());
+            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0) + planet_launches(s) + s->sh_step_launches());
             s->iter += adv;
             s->last_mode = odis::AB3_FULL;
             done += adv;
@@ -1393,10 +1421,11 @@ int odis_op_forcing(odis_solver* s, double time, double* potential_out) {
     double2* eu = s->d_eu[1 - s->ecur];
     ODIS_CUDA(cudaMemsetAsync(eu, 0, (size_t)s->Np * sizeof(double2), s->stream));     // potential NONE leaves the array as it was: zeros
     odis::CellState cs{s->d_vl[s->cur], eu, eu, s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
-    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s->prm.omega, time), odis::CELL_UPDATE_U,
+    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s, time), odis::CELL_UPDATE_U,
                            s->prm.block_threads, nullptr, s->stream);
+    enqueue_planet(s, eu, s->N, step_scalars(s, time), nullptr);
     odis::launch_gather_component(s->No, s->d_cell_perm, eu, 1, s->d_stage, s->stream);
-    s->launches += 2;
+    s->launches += 2 + planet_launches(s);
     return op_finish(s, potential_out, (size_t)s->Ng);
 }
 

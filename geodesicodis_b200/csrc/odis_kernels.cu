@@ -592,6 +592,19 @@ __global__ void gather_history_kernel(int n, const int* __restrict__ perm, const
     dst3[o + 2] = a2;
 }
 
+// PLANET forcing, tidalPotentials.cpp:215-221 (see launch_planet_potential)
+__global__ void __launch_bounds__(256) planet_potential_kernel(CellTables t, StepScalars m, const StepScalars* dev, double2* eu, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (dev != nullptr) {
+        m.cosM = ld_plain(&dev->cosM); m.sinM = ld_plain(&dev->sinM); m.cos2M = ld_plain(&dev->cos2M); m.sin2M = ld_plain(&dev->sin2M);
+    }
+    const size_t N = (size_t)t.n_cells;
+    const double cosLat = t.trig[i], cosLon = t.trig[2 * N + i], sinLon = t.trig[3 * N + i];
+    const double cosgam = cosLat * (cosLon * m.cosM + sinLon * m.sinM);
+    eu[i].y = m.cos2M * (3. * (cosgam * cosgam) - m.sin2M);
+}
+
 // ---- operator surface (odis_op_*, odis_engine.cu): the two loop-level functions of the reference that no step kernel
 // covers on their own. Both work on reference-ordered arrays staged on the device. ----
 // integrateAB3scalar (temporalOperators.cpp:17-68): the solution and its [n][3] tendency history, updated in place
@@ -726,6 +739,9 @@ void launch_gather_history(int n, const int* perm, const double* lvl0_new, const
     gather_history_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, perm, lvl0_new, h1_new, h2_new, which0, dst_ref3);
 }
 
+void launch_planet_potential(const CellTables& t, const StepScalars& host, const StepScalars* dev, double2* eu, int n, cudaStream_t stream) {
+    if (n > 0) planet_potential_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, host, dev, eu, n);
+}
 void launch_ab3_scalar(int n, double* sol, double* hist3, double dt, int mode, cudaStream_t stream) {
     if (n > 0) ab3_scalar_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sol, hist3, dt, mode);
 }

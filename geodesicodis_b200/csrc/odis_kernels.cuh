@@ -28,7 +28,7 @@ constexpr int kStencil = 10;   // TRiSK tangential stencil width (9 beside penta
 constexpr int kCellEdges = 6;  // edges per cell (5 for the 12 pentagons)
 
 // potential types handled on device; values follow enum Potential (include/globals.h:60-76)
-enum DevPotential : int { P_OBLIQ = 0, P_OBLIQ_WEST = 1, P_ECC = 5, P_FULL = 8, P_FULL2 = 9, P_NONE = 16 };
+enum DevPotential : int { P_OBLIQ = 0, P_OBLIQ_WEST = 1, P_ECC = 5, P_FULL = 8, P_FULL2 = 9, P_PLANET = 13, P_NONE = 16 };
 
 // AB3 start-up modes (temporalOperators.cpp:36-65)
 enum Ab3Mode : int { AB3_FIRST = 0, AB3_SECOND = 1, AB3_FULL = 2 };
@@ -247,6 +247,12 @@ void launch_gather_scalar(int n, const int* perm, const double* src_new, double*
 // history levels in device order -> reference-ordered [n][3]; level 0 is lvl0_new, h1_new or h2_new depending on `which0` (0,1,2)
 void launch_gather_history(int n, const int* perm, const double* lvl0_new, const double* h1_new, const double* h2_new, int which0,
                            double* dst_ref3, cudaStream_t stream);
+
+// PLANET forcing (tidalPotentials.cpp:176-225) in a pass of its own over the cells [0, n) after the cell update (the step kernels
+// leave U = 0 for this type): U_i = factor (3 (cos lat_i (cos lon_i cosphi + sin lon_i sinphi))^2 - p), with the four time factors
+// evaluated on the host and handed over in StepScalars {cosM: cosphi, sinM: sinphi, cos2M: factor, sin2M: p} — by value, or read
+// from `dev` (StepCtl::cur) under graph replay.
+void launch_planet_potential(const CellTables& t, const StepScalars& host, const StepScalars* dev, double2* eu, int n, cudaStream_t stream);
 
 // ---- operator surface (odis_op_*): reference-ordered arrays staged on the device ----
 // integrateAB3scalar (temporalOperators.cpp:17-68) in place on sol[n] and hist3[n][3]

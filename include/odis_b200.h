@@ -135,7 +135,7 @@ typedef struct odis_params {
     double ecc;             /* eccentricity                          globals->e            */
     double obl;             /* obliquity (rad)                       globals->theta        */
     double shell_thickness; /* added back to r in forcing for LID_*  tidalPotentials.cpp:50-53 */
-    double semimajor_axis;  /* PLANET forcing only                   globals->a            */
+    double semimajor_axis;  /* PLANET forcing only (required > 0 there) globals->a         */
     int32_t potential;      /* enum Potential, include/globals.h:60-76 */
     int32_t friction;       /* enum Friction (only the diagnostic differs, energy.cpp:46-55) */
     int32_t surface;        /* enum Surface */

@@ -35,7 +35,7 @@ typedef struct {
 } oracle_mesh;
 
 typedef struct {
-    double g, h, alpha, dt, radius, omega, love_reduct, ecc, obl, shell_thickness;
+    double g, h, alpha, dt, radius, omega, love_reduct, ecc, obl, shell_thickness, semimajor_axis;
     int potential, friction, surface, init_load;
 } oracle_params;
 
@@ -249,6 +249,20 @@ static void forcing(oracle_ctx* c, double* potential, double time) {
                                factor2 * cosM * sin2Lat[j] * cosLon[j];
             }
             break;
+        case 13: { /* PLANET, tidalPotentials.cpp:176-225: a companion moon on the inner 2:1 orbit (hard-wired mass and orbit of Io) */
+            const double m2 = 8.931938e+22, a1 = 421800000.0, a2 = p->semimajor_axis;
+            const double n2 = omega, n1 = n2 * 2.0, nij = (n1 - n2);
+            const double cosnt = cos(nij * time), sinnt = sin(nij * time);
+            const double pp = pow(a1, 2.0) + pow(a2, 2.0) - 2. * a1 * a2 * cosnt;
+            const double cosphi = (a1 - a2 * cosnt), sinphi = a2 * sinnt;
+            factor = 0.5 * 6.67408e-11 * m2 * pow(radius / pp, 2.0) / sqrt(pp);
+            for (i = 0; i < N; ++i) {
+                j = i * 2;
+                const double cosgam = cosLat[j] * (cosLon[j] * cosphi + sinLon[j] * sinphi);
+                potential[i] = factor * (3. * pow(cosgam, 2.0) - pp);
+            }
+            break;
+        }
         default: /* NONE */
             break;
     }

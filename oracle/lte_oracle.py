@@ -22,7 +22,8 @@ class _Mesh(C.Structure):
 
 
 class _Params(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("g", "h", "alpha", "dt", "radius", "omega", "love_reduct", "ecc", "obl", "shell_thickness")] + \
+    _fields_ = [(n, C.c_double) for n in ("g", "h", "alpha", "dt", "radius", "omega", "love_reduct", "ecc", "obl", "shell_thickness",
+                                          "semimajor_axis")] + \
                [(n, C.c_int) for n in ("potential", "friction", "surface", "init_load")]
 
 

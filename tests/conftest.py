@@ -56,17 +56,28 @@ def make_run_dir(tmp_path, case: dict) -> str:
     return d
 
 
+def input_value(case: dict, key: str) -> str:
+    """Value text of an input.in key of the case (`key; value; note;` lines)."""
+    for line in str(case["input_in"]).splitlines():
+        parts = [x.strip() for x in line.split(";")]
+        if len(parts) >= 2 and parts[0].lower() == key:
+            return parts[1]
+    raise KeyError(key)
+
+
 def case_params(case: dict, init_load: int = 0) -> dict:
-    """Solver scalars as the reference derived them (dumped by oracle/ref_build/ref_driver.cpp)."""
+    """Solver scalars as the reference derived them (dumped by oracle/ref_build/ref_driver.cpp); the semimajor axis (PLANET
+    forcing only) is not among the dumped scalars and comes from the case's input.in, which the reference reads verbatim."""
     s = lambda k: float(case["scalar_" + k][0])
     return dict(g=s("g"), h=s("h"), alpha=s("alpha"), dt=s("timeStep"), radius=s("radius"), omega=s("angVel"),
                 love_reduct=s("loveReduct"), ecc=s("e"), obl=s("theta"), shell_thickness=s("shell_thickness"),
+                semimajor_axis=float(input_value(case, "semimajor axis")),
                 potential=int(s("tide_type")), friction=int(s("fric_type")), surface=int(s("surface_type")), init_load=init_load)
 
 
 ALL_CASES = ["l3_obliqwest_earth", "l4_ecc_enceladus", "l6_obliqwest_earth", "l3_full_loaded", "l3_obliq_quadratic",
              "l4_full2_lidlove", "l5_none_loaded", "l3_ecc_full_orbit", "l3_ecc_lidmembr",
-             "l3_obliq_freeloading"]
+             "l3_obliq_freeloading", "l3_planet_europa"]
 
 NL_CASES = ["l3_advection_shipped", "l4_advection_loaded", "l5_advection_ecc"]     # advection; true (nonlinear branch, SURVEY §8 a11)
 

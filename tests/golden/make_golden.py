@@ -220,6 +220,10 @@ if __name__ == "__main__":
     #      captured before any step ("start_*") and after 80 steps
     run_case("l3_obliqwest_analytical", 3, dict(earth, **{"initial conditions": "ANALYTICAL", "friction coefficient": "1e-6"}), 80,
              every_step_dumps=True, full_tables=False, capture_start=True)
+    # (14) PLANET forcing (moon-moon tides: a companion on the inner 2:1 orbit, tidalPotentials.cpp:176-225) on a Europa-like ocean
+    run_case("l3_planet_europa", 3, {"potential": "PLANET", "radius": "1560.8e3", "angular velocity": "2.0478e-5", "surface gravity": "1.315",
+                                     "semimajor axis": "671100000.0", "ocean thickness": "100e3", "orbital period": "306822.0", "time step": "200",
+                                     "friction coefficient": "1e-6"}, 90, every_step_dumps=True, full_tables=False)
     # (10) the shipped input.in VERBATIM (advection true, velocity cartesian output true, ...) except for the grid level (3) and the
     #      end time (1 orbit = 48,100 steps at the shipped 30 s step): the whole-run drop-in check, HDF5 rows included
     verbatim = {}

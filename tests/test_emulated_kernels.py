@@ -19,7 +19,7 @@ import pytest
 from conftest import ROOT
 
 CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "tests/test_run_gpu.py", "tests/test_self_gravity_gpu.py"]
-NEW = ["tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
+NEW = ["tests/test_surface_planet_gpu.py", "tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
        "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py"]
 # left out under emulation: full-size grids and the slowest parameter sets
 SKIP = "not large_grid and not high_degree_matrix_free and not 5-12 and not 5-8 and not 6-4 and not 6-2 and not l6_obliqwest and not band_limited"

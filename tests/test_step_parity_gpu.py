@@ -27,7 +27,7 @@ def solver_for_case(odis, tmp_path, case, reorder=1):
     mesh = odis.Mesh.from_file(os.path.join(d, "input_files", "grid_l%d.txt" % int(case["level"])), float(case["scalar_radius"][0]))
     loaded = "init_v" in case
     prm = case_params(case, init_load=int(loaded))
-    s = odis.Solver(mesh, dict(prm, reorder=reorder, semimajor_axis=0.0))
+    s = odis.Solver(mesh, dict(prm, reorder=reorder))
     if loaded:
         s.set_state(case["init_v"], case["init_eta"], case["init_dvdt"], case["init_detadt"])
     return mesh, s
