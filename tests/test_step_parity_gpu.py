@@ -190,7 +190,7 @@ def test_error_paths(odis):
     good = dict(g=1.0, h=1.0e3, alpha=1e-7, dt=10.0, radius=1.0e6, omega=1e-5, love_reduct=1.0, ecc=0.01, obl=0.0,
                 shell_thickness=0.0, semimajor_axis=0.0, potential=5, friction=0, surface=0, init_load=0, reorder=1)
     with pytest.raises(odis.OdisError) as e:
-        odis.Solver(mesh, dict(good, potential=13))                      # PLANET: outside the hot path
+        odis.Solver(mesh, dict(good, potential=15))                      # GENERAL: no usable expression in the reference
     assert e.value.code == -6
     with pytest.raises(odis.OdisError):
         odis.Solver(mesh, dict(good, dt=0.0))
