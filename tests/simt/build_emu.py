@@ -5,8 +5,8 @@ engine's launch sequencing on the CPU; it is never loaded by the product path (g
 libodis_b200.so) and is no substitute for the B200 runs.
 
 The bulk-async staged kernels run too: mbarrier objects, cp.async.bulk (completing at once) and named barriers are modelled in
-simt_emu.h. Not emulated: multi-GPU peer flags (a second GPU never runs concurrently) and the FP64 tensor-core mma of the ensemble
-self-gravity GEMMs (aborts if reached)."""
+simt_emu.h. The FP64 tensor-core mma.sync.m8n8k4 of the ensemble GEMMs is modelled by its fragment layout. Not emulated: multi-GPU peer
+flags (a second GPU never runs concurrently)."""
 from __future__ import annotations
 
 import os
@@ -174,8 +174,9 @@ def rewrite_asm(s: str) -> tuple[str, int]:
             rep = f"simt::named_barrier({ins[0]}, {ins[1]});"
         elif ptx.startswith("bar.sync 1, %0"):
             rep = f"simt::named_barrier(1, {ins[0]});"
-        elif ptx.startswith("mma.sync"):
-            rep = 'do { std::fprintf(stderr, "simt_emu: tensor-core mma is not emulated\\n"); std::abort(); } while (0);'
+        elif ptx.startswith("mma.sync.aligned.m8n8k4.row.col.f64"):
+            rep = f"simt::dmma_m8n8k4({outs[0]}, {outs[1]}, {ins[0]}, {ins[1]});"
+
         else:
             raise ValueError("no emulation for PTX: " + ptx)
         s = s[:m.start()] + rep + s[end + 1:]

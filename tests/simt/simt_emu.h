@@ -289,6 +289,22 @@ inline T shuffle(T v, int src_lane) {
     return out;
 }
 
+// mma.sync.aligned.m8n8k4.row.col.f64: D[8x8] = A[8x4] B[4x8] + C. Fragment layout: lane holds A[lane/4][lane%4], B[lane%4][lane/4]
+// and C/D[lane/4][2*(lane%4) + {0,1}]. Emulated with two warp-wide exchanges (every lane publishes its element, then reads the four
+// it needs); the products are accumulated with fused multiply-adds in k order.
+inline void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    const int lane = cta.current & 31, row = lane >> 2, col0 = (lane & 3) * 2;
+    WarpExchange& w = cta.warps[(size_t)(cta.current >> 5)];
+    double A[4], B0[4], B1[4];
+    auto publish = [&](double v) { uint64_t bits; std::memcpy(&bits, &v, 8); w.pending[lane] = bits; yield(AT_SHUFFLE); };
+    auto read = [&](int src) { double v; std::memcpy(&v, &w.result[src], 8); return v; };
+    publish(a);
+    for (int k = 0; k < 4; k++) A[k] = read(row * 4 + k);
+    publish(b);
+    for (int k = 0; k < 4; k++) { B0[k] = read(col0 * 4 + k); B1[k] = read((col0 + 1) * 4 + k); }
+    for (int k = 0; k < 4; k++) { c0 = std::fma(A[k], B0[k], c0); c1 = std::fma(A[k], B1[k], c1); }
+}
+
 // ---- shared-window addresses, mbarrier, 1-D bulk copies (the staged kernels) ----
 // Dynamic shared memory is one static buffer; a "shared address" is the offset into it.
 inline uint32_t shared_address(const void* p) {
