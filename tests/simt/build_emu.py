@@ -5,8 +5,8 @@ engine's launch sequencing on the CPU; it is never loaded by the product path (g
 libodis_b200.so) and is no substitute for the B200 runs.
 
 The bulk-async staged kernels run too: mbarrier objects, cp.async.bulk (completing at once) and named barriers are modelled in
-simt_emu.h. The FP64 tensor-core mma.sync.m8n8k4 of the ensemble GEMMs is modelled by its fragment layout. Not emulated: multi-GPU peer
-flags (a second GPU never runs concurrently)."""
+simt_emu.h. The FP64 tensor-core mma.sync.m8n8k4 of the ensemble GEMMs is modelled by its fragment layout. Streams are worker threads, so
+several solvers ("devices") of one process run concurrently and exchange halos through each other's memory and flags."""
 from __future__ import annotations
 
 import os
@@ -154,8 +154,14 @@ def rewrite_asm(s: str) -> tuple[str, int]:
             rep = f"{outs[0]} = 0;"
         elif ptx.startswith("ld.") and "{%0, %1}" in ptx:
             rep = f"{{ const auto* simt_p_ = ({ins[0]}); {outs[0]} = simt_p_->x; {outs[1]} = simt_p_->y; }}"
+        elif ptx.startswith("ld.acquire"):
+            rep = f"{outs[0]} = __atomic_load_n({ins[0]}, __ATOMIC_ACQUIRE);"
+        elif ptx.startswith("ld.relaxed.sys"):
+            rep = f"{outs[0]} = *(const volatile decltype({outs[0]})*)({ins[0]});"
         elif ptx.startswith("ld."):
             rep = f"{outs[0]} = *({ins[0]});"
+        elif ptx.startswith("st.release"):
+            rep = f"__atomic_store_n({ins[0]}, (unsigned long long)({ins[1]}), __ATOMIC_RELEASE);"
         elif ptx.startswith("st."):
             rep = f"*({ins[0]}) = ({ins[1]});"
         elif ptx.startswith("mbarrier.init"):
@@ -188,7 +194,7 @@ def transform(name: str, text: str) -> str:
     text, n_launch = rewrite_launches(text)
     text, n_asm = rewrite_asm(text)
     text, n_dyn = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?((?:unsigned\s+)?\w+)\s+(\w+)\s*\[\s*\]\s*;",
-                          r"\1* \2 = reinterpret_cast<\1*>(simt::dynamic_shared);", text)
+                          r"\1* \2 = reinterpret_cast<\1*>(simt::dynamic_shared());", text)
     return f"// generated by tests/simt/build_emu.py from csrc/{name}: {n_launch} launches, {n_asm} asm statements, {n_dyn} dynamic shared arrays rewritten\n" + text
 
 
@@ -207,7 +213,7 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     san = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
-    flags = ["-O1", *san, "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
+    flags = ["-O1", *san, "-mtls-dialect=gnu2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
     jobs = []
     for name in CUDA_SOURCES:
         with open(os.path.join(CSRC, name)) as f:
@@ -231,7 +237,7 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str
             raise RuntimeError("emulation build failed: %s\n%s" % (" ".join(cmd), out[-6000:]))
         if verbose and out.strip():
             print(out)
-    link = ["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", LIB, *[o for _, o in jobs], "-fopenmp"]
+    link = ["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", LIB, *[o for _, o in jobs], "-fopenmp", "-pthread"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulation link failed:\n" + r.stdout[-4000:])

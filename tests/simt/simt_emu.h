@@ -6,15 +6,24 @@
 // (`k<<<g, b, s, st>>>(args)` -> simt::launch), `extern __shared__` and the inline PTX of csrc/*.cu and compiles the result
 // against this header (found as <cuda_runtime.h> through tests/simt/stub/) into tests/_build/libodis_b200_emu.so.
 //
-// Model: CTAs run one after another; the threads of a CTA are fibers (a 10-instruction x86-64 context switch) that run until they reach __syncthreads or a
-// warp shuffle, where they wait for their CTA / warp. Shared memory is `static` storage (one CTA is alive at a time), global
-// memory is the host heap, streams and events are no-ops (everything executes at once, in program order), a captured graph
-// is the list of its launches. What this does NOT model: memory consistency between concurrently running CTAs or GPUs,
-// timing, caches. It is a logic check, not a substitute for the B200 runs.
+// Model: a stream is a worker thread with a FIFO of operations (launches, copies, memsets, event records / waits), so calls return
+// before the work is done, streams run concurrently and a missing synchronisation shows. Within a launch the CTAs run one after
+// another; the threads of a CTA are fibers (a 10-instruction x86-64 context switch) that run until they reach __syncthreads, a
+// warp shuffle or an mbarrier wait, where they wait for their CTA / warp / barrier. Shared memory is `static thread_local`
+// storage (one CTA is alive per stream at a time), global memory is the host heap, a captured graph is the list of its launches.
+// Several "devices" are just several streams: kernels of different solvers run at the same time and talk through peer flags
+// (system-scope acquire / release accesses become __atomic operations). What this does NOT model: memory consistency between
+// the CTAs of one launch, timing, caches. It is a logic check, not a substitute for the B200 runs.
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +39,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __constant__ static
 #define __align__(n) alignas(n)
 
@@ -47,14 +56,12 @@ struct dim3 {
 inline double2 make_double2(double a, double b) { return double2{a, b}; }
 inline int2 make_int2(int a, int b) { return int2{a, b}; }
 
-inline uint3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0};
-inline dim3 blockDim, gridDim;
+// threadIdx / blockIdx / blockDim / gridDim live in the per-stream-thread state (simt::ThreadState, below) behind one thread-local
+// pointer (built with -mtls-dialect=gnu2: TLS descriptors keep that access cheap in a dlopen'ed library)
 
-// ---- CUDA runtime subset: synchronous, host heap ----
+// ---- CUDA runtime subset: streams are worker threads, memory is the host heap ----
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0, cudaErrorUnknown = 999, cudaErrorPeerAccessAlreadyEnabled = 704;
-typedef struct simt_stream* cudaStream_t;
-typedef struct simt_event* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
@@ -65,55 +72,194 @@ struct cudaIpcMemHandle_t { char reserved[64]; };
 namespace simt {
 using Closure = std::function<void()>;
 struct Graph { std::vector<Closure> launches; };
-inline Graph* capturing = nullptr;
-inline long long fake_clock = 0;
-inline long long kernels_run = 0;
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace simt
+
+struct simt_stream {
+    std::thread worker;
+    std::mutex m;
+    std::condition_variable wake, idle;
+    std::deque<simt::Closure> q;
+    bool stop = false, busy = false;
+    int device = 0;                          // the device that was current when the stream was created
+    bool blocking = true;                    // false: created with cudaStreamNonBlocking, the legacy stream does not synchronise with it
+    simt::Graph* capture = nullptr;          // non-null between cudaStreamBeginCapture and cudaStreamEndCapture (host side)
+    void run() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            wake.wait(lk, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;
+            simt::Closure op = std::move(q.front());
+            q.pop_front();
+            busy = true;
+            lk.unlock();
+            op();
+            lk.lock();
+            busy = false;
+            if (q.empty()) idle.notify_all();
+        }
+    }
+    void push(simt::Closure op) {
+        { std::lock_guard<std::mutex> lk(m); q.push_back(std::move(op)); }
+        wake.notify_one();
+    }
+    void drain() {
+        std::unique_lock<std::mutex> lk(m);
+        idle.wait(lk, [&] { return q.empty() && !busy; });
+    }
+};
+struct simt_event {
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned long long recorded = 0, completed = 0;
+    double t_ms = 0.0;
+};
+typedef simt_stream* cudaStream_t;
+typedef simt_event* cudaEvent_t;
 typedef simt::Graph* cudaGraph_t;
 typedef simt::Graph* cudaGraphExec_t;
 
+namespace simt {
+inline std::mutex registry_mutex;
+inline std::vector<simt_stream*> streams;
+inline long long kernels_run = 0;
+inline thread_local int current_device = 0;
+// device-wide synchronisation (cudaFree, cudaDeviceSynchronize): every stream of the calling thread's current device
+inline void drain_device() {
+    std::vector<simt_stream*> copy;
+    { std::lock_guard<std::mutex> lk(registry_mutex); copy = streams; }
+    for (simt_stream* st : copy) if (st->device == current_device) st->drain();
+}
+// what the legacy default stream synchronises with: the BLOCKING streams of the current device only. Streams created with
+// cudaStreamNonBlocking (all of the engine's) are not waited for, as on the hardware -- a cudaMemcpy that relied on it would show.
+inline void drain_legacy() {
+    std::vector<simt_stream*> copy;
+    { std::lock_guard<std::mutex> lk(registry_mutex); copy = streams; }
+    for (simt_stream* st : copy) if (st->device == current_device && st->blocking) st->drain();
+}
+// an operation issued to `st`: in order behind what was issued before
+inline void issue(simt_stream* st, Closure op) {
+    if (st == nullptr) { drain_legacy(); op(); return; }
+    st->push(std::move(op));
+}
+}  // namespace simt
+
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime: unsupported call"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 8; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int d) { simt::current_device = d; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = simt::current_device; return cudaSuccess; }
+// a small "GPU": persistent kernels size their grids from this, so each emulated CTA works through many tiles (stage reuse and
+// mbarrier parity wrap-around get exercised on small grids) and fewer idle fibers are created
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 6; return cudaSuccess; }
 inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorUnknown; }
-inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
-inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
-inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
-inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
-inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
-    for (size_t r = 0; r < h; r++) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+inline cudaError_t cudaFree(void* p) { simt::drain_device(); std::free(p); return cudaSuccess; }
+// page-locked host blocks are remembered: an asynchronous copy into one really is asynchronous (the caller must wait for it)
+namespace simt {
+inline std::vector<std::pair<const unsigned char*, size_t>> pinned_blocks;
+inline bool is_pinned(const void* p) {
+    std::lock_guard<std::mutex> lk(registry_mutex);
+    for (auto& b : pinned_blocks) if ((const unsigned char*)p >= b.first && (const unsigned char*)p < b.first + b.second) return true;
+    return false;
+}
+}  // namespace simt
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
+    if (cudaMalloc(p, n) != cudaSuccess) return cudaErrorUnknown;
+    std::lock_guard<std::mutex> lk(simt::registry_mutex);
+    simt::pinned_blocks.emplace_back((const unsigned char*)*p, n ? n : 1);
     return cudaSuccess;
 }
-inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) {
+    {
+        std::lock_guard<std::mutex> lk(simt::registry_mutex);
+        for (size_t i = 0; i < simt::pinned_blocks.size(); i++)
+            if (simt::pinned_blocks[i].first == (const unsigned char*)p) { simt::pinned_blocks.erase(simt::pinned_blocks.begin() + (long)i); break; }
+    }
+    return cudaFree(p);
+}
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { simt::drain_legacy(); std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t st = nullptr) {
+    if ((k == cudaMemcpyHostToDevice || k == cudaMemcpyHostToHost) && !simt::is_pinned(s)) {   // pageable source: staged at call time, as the driver does
+        auto staged = std::make_shared<std::vector<unsigned char>>((const unsigned char*)s, (const unsigned char*)s + n);
+        simt::issue(st, [d, staged]() { std::memcpy(d, staged->data(), staged->size()); });
+    } else {
+        simt::issue(st, [d, s, n]() { std::memmove(d, s, n); });
+        if (k == cudaMemcpyDeviceToHost && st && !simt::is_pinned(d)) st->drain();   // pageable destination: the call returns when the data is there
+    }
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t st = nullptr) {
+    simt::issue(st, [=]() { for (size_t r = 0; r < h; r++) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w); });
+    if (st) st->drain();
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = nullptr) { simt::issue(st, [d, v, n]() { std::memset(d, v, n); }); return cudaSuccess; }
 template <class T>
-inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t n) { std::memcpy((void*)&symbol, src, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t n) { simt::drain_legacy(); std::memcpy((void*)&symbol, src, n); return cudaSuccess; }
 template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)std::malloc(1); return cudaSuccess; }
-inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
-inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)std::malloc(1); return cudaSuccess; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* out) {
+    simt_stream* st = new simt_stream();
+    st->device = simt::current_device;
+    st->worker = std::thread([st] { st->run(); });
+    { std::lock_guard<std::mutex> lk(simt::registry_mutex); simt::streams.push_back(st); }
+    *out = st;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) { cudaStreamCreate(s); (*s)->blocking = !(flags & cudaStreamNonBlocking); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t st) { if (st) st->drain(); else simt::drain_legacy(); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t st) {
+    st->drain();
+    { std::lock_guard<std::mutex> lk(simt::registry_mutex); simt::streams.erase(std::remove(simt::streams.begin(), simt::streams.end(), st), simt::streams.end()); }
+    { std::lock_guard<std::mutex> lk(st->m); st->stop = true; }
+    st->wake.notify_one();
+    st->worker.join();
+    delete st;
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new simt_event(); return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
-inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
-inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorUnknown; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorUnknown; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { simt::drain_device(); delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr) {
+    unsigned long long ticket;
+    { std::lock_guard<std::mutex> lk(e->m); ticket = ++e->recorded; }
+    simt::issue(st, [e, ticket]() {
+        { std::lock_guard<std::mutex> lk(e->m); e->completed = ticket; e->t_ms = simt::now_ms(); }
+        e->cv.notify_all();
+    });
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+    std::unique_lock<std::mutex> lk(e->m);
+    const unsigned long long ticket = e->recorded;
+    e->cv.wait(lk, [&] { return e->completed >= ticket; });
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned) {
+    unsigned long long ticket;
+    { std::lock_guard<std::mutex> lk(e->m); ticket = e->recorded; }
+    simt::issue(st, [e, ticket]() { std::unique_lock<std::mutex> lk(e->m); e->cv.wait(lk, [&] { return e->completed >= ticket; }); });
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    cudaEventSynchronize(a); cudaEventSynchronize(b);
+    *ms = (float)std::max(b->t_ms - a->t_ms, 1e-6);
+    return cudaSuccess;
+}
+// one process holds every "device": peers use each other's pointers directly (odis_halo_connect's same-process branch)
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
-inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { simt::capturing = new simt::Graph(); return cudaSuccess; }
-inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = simt::capturing; simt::capturing = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode) { st->capture = new simt::Graph(); return cudaSuccess; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g) { *g = st->capture; st->capture = nullptr; return cudaSuccess; }
 inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = new simt::Graph(*g); return cudaSuccess; }
 inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
-inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) { for (auto& c : g->launches) c(); return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { simt::drain_device(); delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t st) {
+    simt::issue(st, [g]() { for (auto& c : g->launches) c(); });
+    return cudaSuccess;
+}
 
 // ---- device intrinsics ----
 inline double __drcp_rn(double x) { return 1.0 / x; }                   // rcp.rn.f64 is correctly rounded, as IEEE division
@@ -121,9 +267,9 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
-inline void __threadfence() {}
-inline void __threadfence_system() {}
-inline long long clock64() { return simt::fake_clock += 1000; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline long long clock64() { return (long long)(simt::now_ms() * 1.0e6); }          // "cycles" = nanoseconds: the kernels' spin bounds stay seconds
 
 namespace simt {
 
@@ -147,8 +293,25 @@ struct Cta {
     int current = -1;
     const Closure* body = nullptr;
 };
-inline Cta cta;
-alignas(16) inline unsigned char dynamic_shared[228 * 1024];
+// everything a stream's worker thread needs while it runs kernels
+struct ThreadState {
+    uint3 tid{0, 0, 0}, bid{0, 0, 0};
+    dim3 bdim, gdim;
+    Cta cta_;
+    unsigned char* dyn = nullptr;              // dynamic shared memory of the CTA in flight
+};
+inline thread_local ThreadState* self_ = nullptr;
+inline void ensure_thread_state() {
+    if (self_) return;
+    self_ = new ThreadState();
+    self_->dyn = (unsigned char*)std::aligned_alloc(128, 228 * 1024);
+}
+#define threadIdx (simt::self_->tid)
+#define blockIdx (simt::self_->bid)
+#define blockDim (simt::self_->bdim)
+#define gridDim (simt::self_->gdim)
+#define cta self_->cta_
+inline unsigned char* dynamic_shared() { return self_->dyn; }
 
 inline void fiber_entry() {
     (*cta.body)();
@@ -158,9 +321,10 @@ inline void fiber_entry() {
     std::abort();
 }
 inline void yield(State why) {
-    Fiber& f = cta.fibers[(size_t)cta.current];
+    Cta& c = self_->cta_;
+    Fiber& f = c.fibers[(size_t)c.current];
     f.state = why;
-    simt_switch(&f.sp, cta.scheduler_sp);
+    simt_switch(&f.sp, c.scheduler_sp);
 }
 // a fresh context that simt_switch can resume: six callee-saved register slots, the entry address its `ret` jumps to, and a
 // null return address so that the entry function starts with the ABI's stack alignment
@@ -180,16 +344,18 @@ inline void set_thread(int linear, const dim3& block) {
 
 // one CTA: fibers run round-robin to their next barrier / shuffle / end
 inline void run_cta(const dim3& block, const Closure& body) {
+    ThreadState* const me = self_;             // one thread-local lookup; the fibers of this CTA share it
+    Cta& c = me->cta_;
     const int n = (int)(block.x * block.y * block.z);
-    if ((int)cta.fibers.size() < n) {
-        const size_t old = cta.fibers.size();
-        cta.fibers.resize((size_t)n);
-        for (size_t i = old; i < (size_t)n; i++) cta.fibers[i].stack = (char*)std::malloc(kStackBytes);
+    if ((int)c.fibers.size() < n) {
+        const size_t old = c.fibers.size();
+        c.fibers.resize((size_t)n);
+        for (size_t i = old; i < (size_t)n; i++) c.fibers[i].stack = (char*)std::malloc(kStackBytes);
     }
-    cta.warps.assign((size_t)(n + 31) / 32, WarpExchange{});
-    cta.body = &body;
+    c.warps.assign((size_t)(n + 31) / 32, WarpExchange{});
+    c.body = &body;
     for (int i = 0; i < n; i++) {
-        Fiber& f = cta.fibers[(size_t)i];
+        Fiber& f = c.fibers[(size_t)i];
         prepare(f);
         f.state = RUNNABLE;
         f.spins = 0;
@@ -198,11 +364,11 @@ inline void run_cta(const dim3& block, const Closure& body) {
     while (alive > 0) {
         bool progressed = false;
         for (int i = 0; i < n; i++) {
-            Fiber& f = cta.fibers[(size_t)i];
+            Fiber& f = c.fibers[(size_t)i];
             if (f.state != RUNNABLE) continue;
-            cta.current = i;
-            set_thread(i, block);
-            simt_switch(&cta.scheduler_sp, f.sp);
+            c.current = i;
+            me->tid.x = (unsigned)i % block.x; me->tid.y = ((unsigned)i / block.x) % block.y; me->tid.z = (unsigned)i / (block.x * block.y);
+            simt_switch(&c.scheduler_sp, f.sp);
             progressed = true;
             if (f.state == DONE) alive--;
         }
@@ -210,14 +376,14 @@ inline void run_cta(const dim3& block, const Closure& body) {
         for (int w = 0; w < (n + 31) / 32; w++) {
             int waiting = 0, live = 0;
             for (int l = 0; l < 32 && w * 32 + l < n; l++) {
-                const State st = cta.fibers[(size_t)(w * 32 + l)].state;
+                const State st = c.fibers[(size_t)(w * 32 + l)].state;
                 live += st != DONE;
                 waiting += st == AT_SHUFFLE;
             }
             if (live > 0 && waiting == live) {
-                std::memcpy(cta.warps[(size_t)w].result, cta.warps[(size_t)w].pending, sizeof cta.warps[(size_t)w].result);
+                std::memcpy(c.warps[(size_t)w].result, c.warps[(size_t)w].pending, sizeof c.warps[(size_t)w].result);
                 for (int l = 0; l < 32 && w * 32 + l < n; l++)
-                    if (cta.fibers[(size_t)(w * 32 + l)].state == AT_SHUFFLE) cta.fibers[(size_t)(w * 32 + l)].state = RUNNABLE;
+                    if (c.fibers[(size_t)(w * 32 + l)].state == AT_SHUFFLE) c.fibers[(size_t)(w * 32 + l)].state = RUNNABLE;
                 progressed = true;
             }
         }
@@ -225,22 +391,22 @@ inline void run_cta(const dim3& block, const Closure& body) {
         for (int id = 1; id < 16; id++) {
             int waiting = 0, need = 0;
             for (int i = 0; i < n; i++)
-                if (cta.fibers[(size_t)i].state == AT_NAMED_BARRIER && cta.fibers[(size_t)i].named_id == id) { waiting++; need = cta.fibers[(size_t)i].named_count; }
+                if (c.fibers[(size_t)i].state == AT_NAMED_BARRIER && c.fibers[(size_t)i].named_id == id) { waiting++; need = c.fibers[(size_t)i].named_count; }
             if (waiting > 0 && waiting >= need) {
                 for (int i = 0; i < n; i++)
-                    if (cta.fibers[(size_t)i].state == AT_NAMED_BARRIER && cta.fibers[(size_t)i].named_id == id) cta.fibers[(size_t)i].state = RUNNABLE;
+                    if (c.fibers[(size_t)i].state == AT_NAMED_BARRIER && c.fibers[(size_t)i].named_id == id) c.fibers[(size_t)i].state = RUNNABLE;
                 progressed = true;
             }
         }
         // the barrier opens when every live thread of the CTA has arrived
         int at_barrier = 0, live = 0;
         for (int i = 0; i < n; i++) {
-            live += cta.fibers[(size_t)i].state != DONE;
-            at_barrier += cta.fibers[(size_t)i].state == AT_BARRIER;
+            live += c.fibers[(size_t)i].state != DONE;
+            at_barrier += c.fibers[(size_t)i].state == AT_BARRIER;
         }
         if (live > 0 && at_barrier == live) {
             for (int i = 0; i < n; i++)
-                if (cta.fibers[(size_t)i].state == AT_BARRIER) cta.fibers[(size_t)i].state = RUNNABLE;
+                if (c.fibers[(size_t)i].state == AT_BARRIER) c.fibers[(size_t)i].state = RUNNABLE;
             progressed = true;
         }
         if (!progressed && alive > 0) {
@@ -251,38 +417,43 @@ inline void run_cta(const dim3& block, const Closure& body) {
 }
 
 inline void run_grid(dim3 grid, dim3 block, const Closure& body) {
-    gridDim = grid;
-    blockDim = block;
+    ensure_thread_state();
+    ThreadState* const me = self_;
+    me->gdim = grid;
+    me->bdim = block;
     for (unsigned z = 0; z < grid.z; z++)
         for (unsigned y = 0; y < grid.y; y++)
             for (unsigned x = 0; x < grid.x; x++) {
-                blockIdx = uint3{x, y, z};
+                me->bid = uint3{x, y, z};
                 run_cta(block, body);
             }
-    kernels_run++;
+    __atomic_fetch_add(&kernels_run, 1, __ATOMIC_RELAXED);
 }
 
 // kernel<<<grid, block, smem, stream>>>(args...): arguments are copied at launch time, as CUDA does
 template <class K, class... A>
-inline void launch(dim3 grid, dim3 block, size_t /*smem*/, cudaStream_t, K kernel, A&&... args) {
+inline void launch(dim3 grid, dim3 block, size_t /*smem*/, cudaStream_t st, K kernel, A&&... args) {
     auto bound = std::make_tuple(std::decay_t<A>(std::forward<A>(args))...);
     Closure run = [grid, block, kernel, bound]() mutable {
         Closure body = [&]() { std::apply([&](auto&... a) { kernel(a...); }, bound); };
         run_grid(grid, block, body);
     };
-    if (capturing) capturing->launches.push_back(run);
-    else run();
+    if (st && st->capture) st->capture->launches.push_back(run);
+    else issue(st, run);
 }
 
 template <class T>
 inline T shuffle(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle payload");
-    const int linear = cta.current, lane = linear & 31;
-    WarpExchange& w = cta.warps[(size_t)(linear >> 5)];
+    Cta& c = self_->cta_;
+    const int linear = c.current, lane = linear & 31;
+    WarpExchange& w = c.warps[(size_t)(linear >> 5)];
     uint64_t bits = 0;
     std::memcpy(&bits, &v, sizeof(T));
     w.pending[lane] = bits;
-    yield(AT_SHUFFLE);
+    Fiber& f = c.fibers[(size_t)linear];
+    f.state = AT_SHUFFLE;
+    simt_switch(&f.sp, c.scheduler_sp);
     if (src_lane < 0 || src_lane > 31) src_lane = lane;
     T out;
     std::memcpy(&out, &w.result[src_lane], sizeof(T));
@@ -308,11 +479,11 @@ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
 // ---- shared-window addresses, mbarrier, 1-D bulk copies (the staged kernels) ----
 // Dynamic shared memory is one static buffer; a "shared address" is the offset into it.
 inline uint32_t shared_address(const void* p) {
-    const std::ptrdiff_t off = (const unsigned char*)p - dynamic_shared;
-    if (off < 0 || off >= (std::ptrdiff_t)sizeof dynamic_shared) { std::fprintf(stderr, "simt_emu: address is not in dynamic shared memory\n"); std::abort(); }
+    const std::ptrdiff_t off = (const unsigned char*)p - dynamic_shared();
+    if (off < 0 || off >= (std::ptrdiff_t)(228 * 1024)) { std::fprintf(stderr, "simt_emu: address is not in dynamic shared memory\n"); std::abort(); }
     return (uint32_t)off;
 }
-inline void* shared_pointer(uint32_t a) { return dynamic_shared + a; }
+inline void* shared_pointer(uint32_t a) { return dynamic_shared() + a; }
 // mbarrier object in its 64-bit shared-memory word: phase parity, arrivals still pending in this phase, the count they are reset
 // to, and the transaction bytes still expected (may go negative when a copy completes before its expect_tx, as in hardware)
 struct Mbarrier { uint32_t phase : 1; uint32_t pending : 15; uint32_t count : 15; int32_t tx; };
@@ -361,6 +532,6 @@ inline void __nanosleep(unsigned) {}
 template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) { const int lane = simt::cta.current & 31; return simt::shuffle(v, lane + delta < 32 ? lane + delta : lane); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask) { return simt::shuffle(v, (simt::cta.current & 31) ^ mask); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return simt::shuffle(v, src & 31); }
-inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; }
-inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
-inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; *p = old + v; return old; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

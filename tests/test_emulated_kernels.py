@@ -1,10 +1,11 @@
 """Kernel logic and engine sequencing checked WITHOUT a GPU: the `-m gpu` parity tests themselves, run in a subprocess against
 tests/_build/libodis_b200_emu.so — the library's own kernel and engine sources compiled for the host against a small emulation
-of the CUDA execution model (tests/simt/simt_emu.h: CTAs in sequence, threads as fibers, barriers, warp shuffles, atomics,
-captured graphs; tests/simt/build_emu.py rewrites launch syntax and inline PTX). The arithmetic is the kernels' own, so the
+of the CUDA execution model (tests/simt/simt_emu.h: streams as worker threads, CTAs of a launch in sequence, threads as fibers,
+barriers, warp shuffles, atomics, captured graphs; tests/simt/build_emu.py rewrites launch syntax and inline PTX). The arithmetic is the kernels' own, so the
 bit-for-bit assertions against the reference fixtures and the oracle hold or fail exactly as they would for the device code's
 logic — the default bulk-async staged kernels included (mbarrier objects, cp.async.bulk, named barriers are modelled). What this
-cannot show: anything about speed, memory ordering between concurrently running CTAs, multi-GPU peer traffic. It is test infrastructure: the product library has no CPU path and `geodesicodis_b200` never loads this file
+cannot show: anything about speed or memory ordering between the CTAs of one launch. Partitioned runs are covered: every solver's stream
+is a thread of its own, so the "devices" really run concurrently and exchange halos / harmonic sums through each other's memory and flags. It is test infrastructure: the product library has no CPU path and `geodesicodis_b200` never loads this file
 unless ODIS_B200_LIB says so (as this test's subprocess does).
 
 Two groups: a control group of tests that have passed on real B200s (the emulation must agree with the hardware's verdict), and
@@ -44,7 +45,7 @@ def emulated_library(built_library):
 def run_gpu_tests_on_the_emulation(lib, libdir, files, extra_env=None, select=SKIP):
     env = dict(os.environ, ODIS_B200_LIB=lib, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     env.update(extra_env or {})
-    cmd = [sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x", "-k", select, "-p", "no:cacheprovider",
+    cmd = [sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x", *(["-k", select] if select else []), "-p", "no:cacheprovider",
            *[a for d in DESELECT for a in ("--deselect", d)]]
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     tail = r.stdout[-3000:]
@@ -63,6 +64,15 @@ def test_code_written_after_the_last_gpu_run(emulated_library):
     tail = run_gpu_tests_on_the_emulation(*emulated_library, NEW)
     passed = int(tail.split(" passed")[0].split()[-1])
     assert passed >= 30, tail
+
+
+def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
+    """tests/test_multigpu.py (2 and 4 ranks: halo exchange bit-identical to one device, self-gravity all-reduce through peer memory) with
+    every rank's stream running as a thread of its own: the in-kernel flag waits really wait for the neighbour, a missing host-side
+    synchronisation or a call that blocks on another rank's progress shows as a time-out or a mismatch. (The same tests run on
+    2 and 4 B200s with `-m gpu`.)"""
+    tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py"], extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="")
+    assert int(tail.split(" passed")[0].split()[-1]) == 6 and "skipped" not in tail, tail
 
 
 def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):

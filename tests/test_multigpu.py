@@ -7,6 +7,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _device_count():
+    import os
+    emulated = int(os.environ.get("ODIS_B200_EMULATED_DEVICES", "0"))      # set by tests/test_emulated_kernels.py only: every stream of the
+    if emulated:                                                            # emulation is a "device" of its own
+        return emulated
     import torch
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
