@@ -158,7 +158,7 @@ def variant_probe(args) -> None:
         prm, L, S = workload_params(mesh), max(args.sh_degree, 2), args.substeps
         ref_eta = None
         for key, sel in (("default", 0), ("cell_update_64_registers", 64), ("self_gravity_3_launch", 16),
-                         ("self_gravity_3_launch_64_registers", 80)):
+                         ("self_gravity_3_launch_64_registers", 80), ("edge_ids_16bit", 128), ("edge_ids_16bit_self_gravity_3_launch", 144)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_self_gravity(L, shell_factor(L))
             sv.step(2 * S)

@@ -59,6 +59,10 @@ struct odis_solver {
     double2* d_grad = nullptr;
     double *d_fcor = nullptr, *d_dist = nullptr, *d_sw = nullptr;
     int* d_sid = nullptr;
+    short* d_sid16 = nullptr;                // params.reserved[0] bit 7: narrow stencil ids of the staged edge kernel ([tiles][10][128] offsets)
+    unsigned char* d_tile_wide = nullptr;    //   + per-tile flag "an offset does not fit, read this tile from d_sid"
+    bool edge_ids16 = false;
+    int wide_tiles = 0;
     double2* d_normal = nullptr;
     int* d_eid = nullptr;
     double *d_area = nullptr, *d_trig = nullptr, *d_trig_sq = nullptr;
@@ -378,6 +382,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->sh_fused_req = (prm->reserved[0] & 16) != 0;
     s->nl_fused = (prm->reserved[0] & 32) != 0;
     s->cell_occ = (prm->reserved[0] & 64) != 0;
+    s->edge_ids16 = (prm->reserved[0] & 128) != 0 && s->pipe_edge;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -472,6 +477,31 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
             (rc = upload(s, &s->d_normal, normal)) || (rc = upload(s, &s->d_vl[0], vl)) || (rc = upload(s, &s->d_vl[1], vl)) ||
             (rc = upload(s, &s->d_cmap, cmap)))
             return bail(rc);
+        if (s->edge_ids16) {
+            // narrow ids: offsets from the edge's own id, tile-major; a tile with an offset beyond 16 bits stays on the int rows.
+            // reserved[0] bit 8 (tests): pretend the range is +-1023 so that small grids have wide tiles too
+            const int T = odis::pipe_tile(), n_tiles = Fp / T, lim = (prm->reserved[0] & 256) ? 1023 : 32767;
+            std::vector<short> sid16((size_t)n_tiles * odis::kStencil * T, (short)0);
+            std::vector<unsigned char> wide((size_t)(n_tiles + 15) / 16 * 16, (unsigned char)0);
+            int n_wide = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n_wide)
+            for (int tile = 0; tile < n_tiles; tile++) {
+                bool w = false;
+                for (int j = 0; j < odis::kStencil; j++)
+                    for (int k = 0; k < T; k++) {
+                        const int en = tile * T + k, id = sid[(size_t)j * Fp + en];
+                        const int off = id < 0 ? 0 : id - en;
+                        if (off > lim || off < -lim) w = true;
+                        sid16[((size_t)tile * odis::kStencil + j) * T + k] = (short)off;
+                    }
+                wide[(size_t)tile] = w ? 1 : 0;
+                n_wide += w;
+            }
+            s->wide_tiles = n_wide;
+            if (std::getenv("ODIS_B200_TRACE_IDS16")) std::fprintf(stderr, "ids16: %d of %d tiles wide (rank %d of %d)\n", n_wide, n_tiles, s->rank, s->world);
+            if (!odis::edge_ids16_fits(Fo)) s->edge_ids16 = false;      // more tiles per CTA than the flag buffer holds: stays on the int rows
+            else if ((rc = upload(s, &s->d_sid16, sid16)) || (rc = upload(s, &s->d_tile_wide, wide))) return bail(rc);
+        }
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "table upload failed"));
     }
     // ---- cell tables (SoA stride N = all local cells: ghosts need their potential at set_state) ----
@@ -1112,7 +1142,8 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     if (s->pipe_edge) {
         odis::HaloInline hv;
         if (inline_e) hv = halo_inline_edge(s, 1 - s->cur);
-        ODIS_CUDA(odis::launch_edge_step_pipe(et, s->phys, es, mode, inline_e ? &hv : nullptr, s->stream));
+        if (s->edge_ids16) ODIS_CUDA(odis::launch_edge_step_pipe16(et, s->phys, es, mode, inline_e ? &hv : nullptr, s->d_sid16, s->d_tile_wide, s->stream));
+        else ODIS_CUDA(odis::launch_edge_step_pipe(et, s->phys, es, mode, inline_e ? &hv : nullptr, s->stream));
     } else odis::launch_edge_step(et, s->phys, es, mode, s->prm.block_threads, s->stream);
     if (part && !inline_e) {
         int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
@@ -1594,7 +1625,7 @@ void odis_destroy(odis_solver* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);
     void* ptrs[] = {s->d_csr_e_first, s->d_csr_e_peer, s->d_csr_e_remote, s->d_halo_done,
-                    s->d_ctl, s->d_scal, s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_normal, s->d_eid, s->d_area, s->d_trig,
+                    s->d_ctl, s->d_scal, s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_sid16, s->d_tile_wide, s->d_normal, s->d_eid, s->d_area, s->d_trig,
                     s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,

@@ -187,6 +187,12 @@ cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const E
                                   cudaStream_t stream);
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                                   cudaStream_t stream);
+// Opt-in: the staged edge kernel with narrow stencil ids. sid16 = [tiles][10][128] 16-bit offsets from the edge's own id (0 for an
+// empty slot), tile_wide[tile] != 0 where an offset does not fit (that tile is read from EdgeTables.sid as usual). Bit-identical results.
+// edge_ids16_fits: false when a CTA would hold more tiles than its flag buffer (the launcher then returns cudaErrorInvalidValue).
+bool edge_ids16_fits(int n_edges);
+cudaError_t launch_edge_step_pipe16(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, const HaloInline* halo,
+                                    const short* sid16, const unsigned char* tile_wide, cudaStream_t stream);
 
 // ---- halo exchange between ranks (one GPU each): peers' arrays are mapped into this process ----
 constexpr int kHaloMaxPeers = 8;

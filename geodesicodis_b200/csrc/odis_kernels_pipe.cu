@@ -119,13 +119,28 @@ struct __align__(16) EdgeStage {
 constexpr uint32_t kEdgeStageBytes = sizeof(EdgeStage);
 static_assert(kEdgeStageBytes == 24576, "edge stage layout");
 
-__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
-                                                                          HaloInline halo) {
+// Narrow stencil ids (opt-in, kIds16): the ten ids of an edge are stored as 16-bit offsets from the edge's own id, tile-major
+// ([tile][10][128] shorts = one 2560-byte bulk copy per tile instead of ten 512-byte rows). Along the space-filling-curve numbering
+// 99 % of the offsets fit; a tile in which one does not is marked "wide" and its ids come from the ordinary int rows (per-tile flag,
+// preloaded into shared memory so that the producer knows each tile's byte count without a global load). 180 B per edge instead of
+// 200 for the narrow tiles; the arithmetic is untouched (the id only addresses the gather).
+constexpr int kMaxTilesPerCta16 = 4096;
+constexpr uint32_t kNarrowIdBytes = kStencil * kTile * sizeof(short);    // 2560
+
+template <bool kIds16>
+__device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, int n_tiles,
+                                                    const HaloInline& halo, const short* __restrict__ sid16,
+                                                    const unsigned char* __restrict__ tile_wide) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     EdgeStage* stages = reinterpret_cast<EdgeStage*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(EdgeStage));
     uint64_t* empty = full + kStages;
+    unsigned char* wide_s = smem_raw + kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t);     // [my_tiles], kIds16 only
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (kIds16) {
+        const int mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        for (int i = threadIdx.x; i < mine; i += kPipeThreads) wide_s[i] = tile_wide[(size_t)blockIdx.x + (size_t)i * gridDim.x];
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; i++) {
             mbar_init(full + i, 1);               // one arrive (the producer's expect_tx) + the copies' bytes
@@ -145,9 +160,13 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
                 if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
                 EdgeStage* d = stages + st;
                 const size_t e0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile;
-                mbar_expect_tx(full + st, kEdgeStageBytes);
+                const bool narrow = kIds16 && wide_s[i] == 0;
+                mbar_expect_tx(full + st, narrow ? kEdgeStageBytes - (uint32_t)sizeof(d->sid) + kNarrowIdBytes : kEdgeStageBytes);
+                if (narrow) bulk_g2s(d->sid, sid16 + (e0 / kTile) * (size_t)(kStencil * kTile), kNarrowIdBytes, full + st, pol);
+                else {
 #pragma unroll
-                for (int j = 0; j < kStencil; j++) bulk_g2s(d->sid[j], t.sid + j * S + e0, kTile * 4, full + st, pol);
+                    for (int j = 0; j < kStencil; j++) bulk_g2s(d->sid[j], t.sid + j * S + e0, kTile * 4, full + st, pol);
+                }
 #pragma unroll
                 for (int j = 0; j < kStencil; j++) bulk_g2s(d->sw[j], t.sw + j * S + e0, kTile * 8, full + st, pol);
                 bulk_g2s(d->cells, t.cells + e0, kTile * 8, full + st, pol);
@@ -176,10 +195,16 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
         if (e < t.n_edges) {
             // gathers first (their addresses come from shared memory), arithmetic after
             double2 nb[kStencil];
+            if (kIds16 && wide_s[i] == 0) {
+                const short* off = reinterpret_cast<const short*>(d->sid);        // [10][128] offsets from e; 0 = empty slot (weight 0)
 #pragma unroll
-            for (int j = 0; j < kStencil; j++) {
-                const int id = d->sid[j][tl];
-                nb[j] = ld_gather(s.vl_in + (id < 0 ? e : id));
+                for (int j = 0; j < kStencil; j++) nb[j] = ld_gather(s.vl_in + (e + (int)off[j * kTile + tl]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < kStencil; j++) {
+                    const int id = d->sid[j][tl];
+                    nb[j] = ld_gather(s.vl_in + (id < 0 ? e : id));
+                }
             }
             const int2 c = d->cells[tl];
             const double2 in = ld_gather(s.eu + c.x), out = ld_gather(s.eu + c.y);
@@ -253,6 +278,15 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTab
             *s.ticket = 0u;
         }
     }
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
+                                                                          HaloInline halo) {
+    edge_step_pipe_body<false>(t, p, s, mode, n_tiles, halo, nullptr, nullptr);
+}
+__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe16_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
+                                                                            HaloInline halo, const short* sid16, const unsigned char* tile_wide) {
+    edge_step_pipe_body<true>(t, p, s, mode, n_tiles, halo, sid16, tile_wide);
 }
 
 // ---------------------------------------------------------------- cell step ----
@@ -460,6 +494,35 @@ cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const E
     HaloInline none;
     none.n_bnd = 0;
     edge_step_pipe_kernel<<<grid, kPipeThreads, smem, stream>>>(t, p, s, mode, n_tiles, halo ? *halo : none);
+    return cudaGetLastError();
+}
+
+bool edge_ids16_fits(int n_edges) {
+    const int n_tiles = (n_edges + kTile - 1) / kTile;
+    const int grid = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
+    return grid > 0 && (n_tiles + grid - 1) / grid <= kMaxTilesPerCta16;
+}
+
+cudaError_t launch_edge_step_pipe16(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, const HaloInline* halo,
+                                    const short* sid16, const unsigned char* tile_wide, cudaStream_t stream) {
+    static bool configured_dev[64] = {false};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 63];
+    const int n_tiles = (t.n_edges + kTile - 1) / kTile;
+    const int grid = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
+    if (!edge_ids16_fits(t.n_edges)) return cudaErrorInvalidValue;
+    const int per_cta = (n_tiles + grid - 1) / grid;
+    const size_t smem_max = kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t) + kMaxTilesPerCta16;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(edge_step_pipe16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const size_t smem = kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t) + (size_t)((per_cta + 15) / 16 * 16);
+    HaloInline none;
+    none.n_bnd = 0;
+    edge_step_pipe16_kernel<<<grid, kPipeThreads, smem, stream>>>(t, p, s, mode, n_tiles, halo ? *halo : none, sid16, tile_wide);
     return cudaGetLastError();
 }
 

@@ -150,7 +150,10 @@ typedef struct odis_params {
                              *     analysis is folded into the cell update and the solve into the synthesis (sums associate differently:
                              *     fields agree with the default to ~1e-13 relative, not bit for bit). bit 5 (with odis_enable_advection):
                              *     the nonlinear step in 4 gather launches instead of 6 (bit-identical fields). bit 6: the per-step cell
-                             *     update compiled with a 64-register cap (50 % instead of 37.5 % occupancy; bit-identical fields). Rest must be 0. */
+                             *     update compiled with a 64-register cap (50 % instead of 37.5 % occupancy; bit-identical fields). bit 7 (staged edge
+                             *     kernel): stencil ids travel as 16-bit offsets from the edge's own id, one bulk copy per tile; tiles where an
+                             *     offset does not fit stay on the 32-bit rows (180 instead of 200 B per edge; bit-identical fields). bit 8
+                             *     (tests): offset range +-1023 instead of +-32767. Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {

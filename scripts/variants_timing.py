@@ -20,7 +20,9 @@ prm = dict(g=0.113, h=38e3, alpha=1e-7, dt=0.2 * dmin / np.sqrt(0.113 * 38e3), r
            obl=0.0, shell_thickness=23e3, semimajor_axis=0.0, potential=5, friction=0, surface=2, init_load=0, reorder=1)
 factor = 0.1 * np.ones(l_max + 1)
 factor[:2] = 0.0
-SELECTIONS = [("default (5 launches/step)", 0), ("3-launch self-gravity (bit 4)", 16), ("3-launch + direct edge kernel (bits 0,4)", 17)]
+SELECTIONS = [("default (5 launches/step)", 0), ("3-launch self-gravity (bit 4)", 16), ("3-launch + direct edge kernel (bits 0,4)", 17),
+              ("16-bit stencil ids in the staged edge kernel (bit 7)", 128), ("16-bit ids + 3-launch self-gravity (bits 4,7)", 144),
+              ("16-bit ids + 3-launch + 64-register cell update (bits 4,6,7)", 208)]
 ref = None
 for name, sel in SELECTIONS:
     s = odis.Solver(mesh, dict(prm, kernel_select=sel))

@@ -61,7 +61,7 @@ inline int2 make_int2(int a, int b) { return int2{a, b}; }
 
 // ---- CUDA runtime subset: streams are worker threads, memory is the host heap ----
 typedef int cudaError_t;
-constexpr cudaError_t cudaSuccess = 0, cudaErrorUnknown = 999, cudaErrorPeerAccessAlreadyEnabled = 704;
+constexpr cudaError_t cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorUnknown = 999, cudaErrorPeerAccessAlreadyEnabled = 704;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };

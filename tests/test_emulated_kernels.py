@@ -23,7 +23,7 @@ CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "test
            "tests/test_ensemble_gpu.py::test_members_match_oracle",
            "tests/test_ensemble_gpu.py::test_ensemble_self_gravity_matches_oracle[4-5-2]"]      # FP64 mma.sync fragments modelled
 NEW = ["tests/test_surface_planet_gpu.py", "tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
-       "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py"]
+       "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py", "tests/test_variant_ids16_gpu.py"]
 # left out under emulation: full-size grids and the slowest parameter sets
 SKIP = "not large_grid and not high_degree_matrix_free and not 5-12 and not 5-8 and not 6-4 and not 6-2 and not l6_obliqwest and not band_limited"
 DESELECT = ["tests/test_step_parity_gpu.py::test_direct_and_pipelined_kernels_agree[6]"]
@@ -71,8 +71,9 @@ def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
     every rank's stream running as a thread of its own: the in-kernel flag waits really wait for the neighbour, a missing host-side
     synchronisation or a call that blocks on another rank's progress shows as a time-out or a mismatch. (The same tests run on
     2 and 4 B200s with `-m gpu`.)"""
-    tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py"], extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="")
-    assert int(tail.split(" passed")[0].split()[-1]) == 6 and "skipped" not in tail, tail
+    tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py", "tests/test_variant_ids16_gpu.py::test_narrow_ids_on_a_partitioned_grid"],
+                                          extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="")
+    assert int(tail.split(" passed")[0].split()[-1]) == 8 and "skipped" not in tail, tail
 
 
 def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
