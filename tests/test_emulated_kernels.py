@@ -19,6 +19,8 @@ import pytest
 
 from conftest import ROOT
 
+pytestmark = pytest.mark.timeout(2400)          # whole groups of -m gpu tests run inside one test here
+
 CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "tests/test_run_gpu.py", "tests/test_self_gravity_gpu.py",
            "tests/test_ensemble_gpu.py::test_members_match_oracle",
            "tests/test_ensemble_gpu.py::test_ensemble_self_gravity_matches_oracle[4-5-2]"]      # FP64 mma.sync fragments modelled
