@@ -87,8 +87,10 @@ def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
         pytest.skip("no AddressSanitizer runtime with this compiler")
     lib = build_emu.build(asan=True)
     files = ["tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py",
-             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py"]
+             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py", "tests/test_variant_ids16_gpu.py",
+             "tests/test_multigpu.py::test_partitioned_run_matches_single_gpu[2]",                    # halo push / wait between two concurrent "devices"
+             "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]"]     # + all-reduce through peer memory
     select = SKIP + " and not l5_ and not l6_ and not 5-2 and not 5-3 and not full_orbit and not random_state and not kernels_agree"
     tail = run_gpu_tests_on_the_emulation(lib, emulated_library[1], files, select=select,
-                                          extra_env={"LD_PRELOAD": asan_rt, "ASAN_OPTIONS": "detect_leaks=0:halt_on_error=1"})
-    assert int(tail.split(" passed")[0].split()[-1]) >= 35, tail
+                                          extra_env={"LD_PRELOAD": asan_rt, "ASAN_OPTIONS": "detect_leaks=0:halt_on_error=1", "ODIS_B200_EMULATED_DEVICES": "2"})
+    assert int(tail.split(" passed")[0].split()[-1]) >= 45, tail
