@@ -2,6 +2,8 @@
 #include "odis_kernels.cuh"
 #include "odis_sh.cuh"
 
+#include <mutex>
+
 namespace odis {
 
 namespace {
@@ -674,10 +676,18 @@ void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s,
         cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
     });
 }
-cudaError_t cell_sg_configure() {
+cudaError_t cell_sg_configure() {          // once per device (see sh_configure)
+    static std::mutex once;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(once);
+    if (done[dev & 63]) return cudaSuccess;
     double rec[kShRecDoubles];
     sh_recurrence_table(rec);
-    return cudaMemcpyToSymbol(c_sg_rec, rec, sizeof rec);
+    const cudaError_t e = cudaMemcpyToSymbol(c_sg_rec, rec, sizeof rec);
+    if (e == cudaSuccess) done[dev & 63] = true;
+    return e;
 }
 int cell_sg_ctas(int n_active) { return (n_active + kCellSgThreads - 1) / kCellSgThreads; }
 bool cell_sg_supports(int l_max) { return l_max >= 2 && l_max <= kCellSgMaxDegree; }

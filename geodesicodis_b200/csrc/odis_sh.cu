@@ -2,6 +2,7 @@
 #include "odis_sh.cuh"
 
 #include <cmath>
+#include <mutex>
 
 namespace odis {
 
@@ -608,7 +609,15 @@ static size_t analysis_smem(int rows) { return (size_t)rows * kShWarps * sizeof(
 static size_t analysis_mf_smem(int l_max) { return ((size_t)(l_max + 1) * (l_max + 1) * kShWarps + rec_shared_doubles(l_max)) * sizeof(double); }
 static size_t synthesis_mf_smem(int l_max) { return ((size_t)(l_max + 1) * (l_max + 1) + rec_shared_doubles(l_max)) * sizeof(double); }
 
+// once per device: another solver on the same GPU may have kernels in flight that read c_rec, and the legacy stream of
+// cudaMemcpyToSymbol does not wait for the solvers' non-blocking streams
 cudaError_t sh_configure() {
+    static std::mutex once;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(once);
+    if (done[dev & 63]) return cudaSuccess;
     cudaError_t e;
     double rec[kShRecDoubles];
     sh_recurrence_table(rec);
@@ -618,7 +627,9 @@ cudaError_t sh_configure() {
     if ((e = cudaFuncSetAttribute(ens_sh_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (size_t)kEnsShMaxRows * kEnsLd * sizeof(double)))) != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(sh_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analysis_smem(kShMaxRows));
+    if ((e = cudaFuncSetAttribute(sh_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analysis_smem(kShMaxRows))) != cudaSuccess) return e;
+    done[dev & 63] = true;
+    return cudaSuccess;
 }
 
 // degrees with a fully unrolled specialisation of the matrix-free kernels

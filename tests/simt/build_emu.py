@@ -198,14 +198,19 @@ def transform(name: str, text: str) -> str:
     return f"// generated by tests/simt/build_emu.py from csrc/{name}: {n_launch} launches, {n_asm} asm statements, {n_dyn} dynamic shared arrays rewritten\n" + text
 
 
-def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, asan: bool = False, tsan: bool = False) -> str:
     """asan: AddressSanitizer build (libodis_b200_emu_asan.so; load with LD_PRELOAD=$(gcc -print-file-name=libasan.so)): device
-    arrays are host heap blocks, so an out-of-range access in a kernel is reported like compute-sanitizer's memcheck would."""
+    arrays are host heap blocks, so an out-of-range access in a kernel is reported like compute-sanitizer's memcheck would.
+    tsan: ThreadSanitizer build (libodis_b200_emu_tsan.so, LD_PRELOAD libtsan.so, OMP_NUM_THREADS=1): every stream is a thread, so an
+    access of one "device" that is not ordered after another device's (or the host's) write by a flag, an event or a stream
+    synchronisation is reported as a data race -- a racecheck of the halo / all-reduce protocol and of the engine's host-side waits.
+    Function entry/exit instrumentation is off because the fibers switch stacks behind the sanitizer's back."""
     from geodesicodis_b200.build import HOST_SOURCES, HOST_FLAGS
     global LIB
-    lib = os.path.join(OUT, "libodis_b200_emu_asan.so" if asan else "libodis_b200_emu.so")
+    tag = "_asan" if asan else "_tsan" if tsan else ""
+    lib = os.path.join(OUT, f"libodis_b200_emu{tag}.so")
     LIB = lib
-    src_dir = os.path.join(OUT, "emu_src_asan" if asan else "emu_src")
+    src_dir = os.path.join(OUT, "emu_src" + tag)
     os.makedirs(src_dir, exist_ok=True)
     newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))
     newest = max(newest, os.path.getmtime(os.path.join(HERE, "simt_emu.h")), os.path.getmtime(os.path.abspath(__file__)),
@@ -213,6 +218,8 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     san = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    if tsan:
+        san = ["-g", "-fsanitize=thread", "--param=tsan-instrument-func-entry-exit=0"]
     flags = ["-O1", *san, "-mtls-dialect=gnu2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
     jobs = []
     for name in CUDA_SOURCES:
@@ -237,7 +244,7 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str
             raise RuntimeError("emulation build failed: %s\n%s" % (" ".join(cmd), out[-6000:]))
         if verbose and out.strip():
             print(out)
-    link = ["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", LIB, *[o for _, o in jobs], "-fopenmp", "-pthread"]
+    link = ["g++", "-shared", *(["-fsanitize=address"] if asan else ["-fsanitize=thread"] if tsan else []), "-o", LIB, *[o for _, o in jobs], "-fopenmp", "-pthread"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulation link failed:\n" + r.stdout[-4000:])
@@ -246,4 +253,4 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False) -> str
 
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, asan="--asan" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, asan="--asan" in sys.argv, tsan="--tsan" in sys.argv))

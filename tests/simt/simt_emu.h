@@ -196,7 +196,13 @@ inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t s
 }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = nullptr) { simt::issue(st, [d, v, n]() { std::memset(d, v, n); }); return cudaSuccess; }
 template <class T>
-inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t n) { simt::drain_legacy(); std::memcpy((void*)&symbol, src, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t n) {
+    simt::drain_legacy();
+    // a __constant__ symbol has one instance per device in CUDA, one for all "devices" here: an identical upload by the next device is not
+    // repeated (it would look like a write under a kernel of the first device that is reading the table)
+    if (std::memcmp((const void*)&symbol, src, n) != 0) std::memcpy((void*)&symbol, src, n);
+    return cudaSuccess;
+}
 template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* out) {
