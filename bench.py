@@ -283,6 +283,8 @@ def run_ours(args) -> None:
         pos, fr, cen = odis.generate_grid(args.level)
         mesh = odis.Mesh.from_arrays(pos, fr, cen, radius)
     prm = workload_params(mesh)
+    if args.kernel_select:                          # experiments only (odis_params.reserved[0]); the default line is selection 0
+        prm = dict(prm, kernel_select=args.kernel_select)
     solver = odis.Solver(mesh, prm, device=local_rank, rank=rank, world=world)
     if world > 1:                                   # every rank publishes its halo buffers; neighbours map them
         blobs = [None] * world
@@ -373,7 +375,7 @@ def run_ours(args) -> None:
         for name, deg in (("no_self_gravity", 0), ("self_gravity_degree_8", 8)):
             if deg == L:
                 continue
-            alt = odis.Solver(mesh, prm, device=local_rank)
+            alt = odis.Solver(mesh, workload_params(mesh), device=local_rank)
             if deg >= 2:
                 alt.enable_self_gravity(deg, shell_factor(deg))
             alt.step(2 * S)
@@ -393,7 +395,7 @@ def run_ours(args) -> None:
                                        f"(reference file level {args.level} = BASELINE 'L{args.level - 1}'); "
                                        + (f"self-gravity / shell-pressure term by spherical harmonics to degree {L} (least-squares analysis + synthesis every step; "
                                           f"factors 1 - beta_l of the reference's 23 km Enceladus table)" if L >= 2 else "no self-gravity term"),
-                           "sh_degree": L,
+                           "sh_degree": L, "kernel_select": args.kernel_select,
                            "cells": N, "edges": F, "lte_steps_per_bench_step": S, "dt_s": prm["dt"],
                            "cache": f"working set {dev_bytes / 1e6:.0f} MB device, {alg_bytes / 1e6:.0f} MB streamed per LTE step > 126 MB L2 (no flush needed)",
                            "parallelism": "1 GPU" if world == 1 else
@@ -494,6 +496,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra device-resident timings with other --sh-degree values")
     ap.add_argument("--no-probes", action="store_true", help="skip the subprocess timings of the opt-in kernel selections")
+    ap.add_argument("--kernel-select", type=int, default=0, help="opt-in kernel selection bits (include/odis_b200.h, odis_params.reserved[0]); "
+                    "0 = the default kernels. E.g. 16: self-gravity step in 3 launches (also on partitioned grids), 128: 16-bit stencil ids")
     ap.add_argument("--variant-probe", default="", help=argparse.SUPPRESS)
     ap.add_argument("--probe-level", type=int, default=8, help=argparse.SUPPRESS)
     ap.add_argument("--sh-degree", type=int, default=2, help="self-gravity term by spherical harmonics to this degree (the shipped input.in's "

@@ -135,7 +135,8 @@ struct odis_solver {
     odis::CellSgWork sg_work() const {
         return odis::CellSgWork{sh_lmax, No, d_sg_cta, sg_cta_stride, d_sg_group, sg_group_stride, d_sg_ticket};
     }
-    int sg_groups() const { return (odis::cell_sg_ctas(No) + odis::kCellSgGroup - 1) / odis::kCellSgGroup; }
+    int sg_cells() const { return world > 1 ? N : No; }        // cells the cell update covers (partitioned: ghost cells too)
+    int sg_groups() const { return (odis::cell_sg_ctas(sg_cells()) + odis::kCellSgGroup - 1) / odis::kCellSgGroup; }
     int sh_step_launches() const { return !sh_on ? 0 : (sh_fused ? 1 : sh_launches()); }     // per time step, after the cell update
     unsigned char* d_sh_xblock = nullptr;             // partitioned: this rank's exchange block (odis_sh.cuh), mapped by every other rank
     unsigned long long* d_sh_xctl = nullptr;
@@ -870,17 +871,19 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_b, 0, (size_t)rows * sizeof(double), s->stream));
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_s, 0, (size_t)rows * sizeof(double), s->stream));
     if (s->sh_fused_req) {
-        if (s->world > 1 || s->sh_stored || s->pipe_cell || !odis::cell_sg_supports(l_max))
-            return fail(ODIS_ERR_UNSUPPORTED, "the 3-launch self-gravity variant needs an unpartitioned solver, the matrix-free basis, the direct cell kernel and sh degree <= 4");
+        if (s->sh_stored || s->pipe_cell || !odis::cell_sg_supports(l_max) || (s->world > 1 && (s->cell_occ || !s->pipe_edge)))
+            return fail(ODIS_ERR_UNSUPPORTED, "the 3-launch self-gravity variant needs the matrix-free basis, the direct cell kernel and sh degree <= 4 "
+                                              "(partitioned solvers: the staged edge kernel, no register cap)");
         ODIS_CUDA(odis::cell_sg_configure());
-        s->sg_cta_stride = (odis::cell_sg_ctas(s->No) + 31) / 32 * 32;
+        s->sg_cta_stride = (odis::cell_sg_ctas(s->sg_cells()) + 31) / 32 * 32;
         s->sg_group_stride = (s->sg_groups() + 31) / 32 * 32;
+        // one more ticket behind the per-group ones: the groups that have finished (partitioned solvers)
         if ((rc = dev_alloc(s, &s->d_sg_cta, (size_t)rows * s->sg_cta_stride)) || (rc = dev_alloc(s, &s->d_sg_group, (size_t)rows * s->sg_group_stride)) ||
-            (rc = dev_alloc(s, &s->d_sg_ticket, (size_t)s->sg_group_stride)))
+            (rc = dev_alloc(s, &s->d_sg_ticket, (size_t)s->sg_group_stride + 32)))
             return rc;
         ODIS_CUDA(cudaMemsetAsync(s->d_sg_cta, 0, (size_t)rows * s->sg_cta_stride * sizeof(double), s->stream));
         ODIS_CUDA(cudaMemsetAsync(s->d_sg_group, 0, (size_t)rows * s->sg_group_stride * sizeof(double), s->stream));
-        ODIS_CUDA(cudaMemsetAsync(s->d_sg_ticket, 0, (size_t)s->sg_group_stride * sizeof(unsigned int), s->stream));
+        ODIS_CUDA(cudaMemsetAsync(s->d_sg_ticket, 0, ((size_t)s->sg_group_stride + 32) * sizeof(unsigned int), s->stream));
         s->sh_fused = true;
     }
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
@@ -1161,7 +1164,10 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
         ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, s->stream));
     } else if (s->sh_on && s->sh_fused) {
         // 3-launch variant: the cell update leaves the harmonic sums of eta^{n+1} over groups of its CTAs
-        odis::launch_cell_step_sg(ct, s->phys, cs, mode, next, s->sg_work(), s->cell_occ, s->stream);
+        if (part) {
+            const odis::HaloInline hc = halo_inline_cell(s);
+            odis::launch_cell_step_sgx(ct, s->phys, cs, mode, next, s->sg_work(), hc, s->sh_exchange(), s->stream);
+        } else odis::launch_cell_step_sg(ct, s->phys, cs, mode, next, s->sg_work(), s->cell_occ, s->stream);
     } else {
         odis::HaloInline hc;
         if (inline_e) hc = halo_inline_cell(s);
@@ -1172,7 +1178,9 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     s->ecur = 1 - s->ecur;
     enqueue_planet(s, s->d_eu[s->ecur], ct.n_active, next, dev_ctl ? &s->d_ctl->cur : nullptr);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
-    if (s->sh_on && s->sh_fused)
+    if (s->sh_on && s->sh_fused && part)
+        odis::launch_sh_allsolve_synthesis(s->sh_tables(), s->sh_work(), s->sh_exchange(), s->prm.g, s->d_eu[s->ecur], s->N, s->stream);
+    else if (s->sh_on && s->sh_fused)
         odis::launch_sh_solve_synthesis(s->sh_tables(), s->sh_work(), s->d_sg_group, s->sg_group_stride, s->sg_groups(), s->prm.g, s->d_eu[s->ecur], s->N,
                                         s->stream);
     else { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }

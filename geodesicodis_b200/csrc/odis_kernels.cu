@@ -365,9 +365,21 @@ __device__ __forceinline__ double warp_sum_all(double x) {      // butterfly: fi
 // (odis_sh.cu); each warp reduces its 32 cells, the CTA leaves one partial per basis row, and the LAST CTA of every group of
 // kCellSgGroup consecutive CTAs to finish adds the group's partials in CTA order. Sums are therefore independent of the
 // order in which CTAs run. sh_solve_synthesis (odis_sh.cu) finishes the sum over the groups.
-template <int kThreads, int LT, int kMinBlocks = 0>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                                            CellSgWork sg) {
+// kPart (partitioned solvers): the trailing CTAs wait for the neighbours' halo push like cell_step_kernel does, the fit covers the own
+// cells only (sg.n_fit) while the ghost cells are updated too, and the LAST group to finish adds the groups in group order and publishes
+// this rank's sums for the in-kernel all-reduce (the protocol of sh_reduce_publish_kernel, odis_sh.cu: sums into this rank's exchange
+// block at the parity of the new epoch, then the epoch into this rank's flag in every rank's block, system-scope release).
+__device__ __forceinline__ unsigned long long* sgx_flags(unsigned char* block) { return reinterpret_cast<unsigned long long*>(block); }
+__device__ __forceinline__ double* sgx_pub(unsigned char* block, int parity) {
+    return reinterpret_cast<double*>(block + kShMaxWorld * sizeof(unsigned long long)) + (size_t)parity * kShXRows;
+}
+__device__ __forceinline__ void sgx_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int kThreads, int LT, bool kPart>
+__device__ __forceinline__ void cell_step_sg_body(const CellTables& t, const Physics& p, const CellState& s, int mode, StepScalars next,
+                                                  const CellSgWork& sg, const HaloInline& halo, const ShExchange& x) {
     constexpr int kRows = (LT + 1) * (LT + 1);
     constexpr int kWarps = kThreads / 32;
     static_assert(kRows <= kThreads, "one thread per basis row writes the CTA partial");
@@ -375,6 +387,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(Cell
     __shared__ bool group_last;
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
+    bool bnd_cta = false;
+    if (kPart) {
+        bnd_cta = (int)((blockIdx.x + 1) * kThreads) > halo.wait_from;
+        if (bnd_cta) {
+            if (threadIdx.x == 0) halo_wait_all(halo.wait_v, halo.ctl);
+            __syncthreads();
+        }
+    }
     const int i = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = t.n_cells;
@@ -399,8 +419,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(Cell
     }
     // ---- phase B: gathers ----
     double2 ed[kCellEdges];
+    if (!kPart || !bnd_cta) {
 #pragma unroll
-    for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+        for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+    } else {                                              // ghost slots are written by other GPUs while the kernel runs
+#pragma unroll
+        for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather_cg(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+    }
     // ---- phase C: as cell_step_kernel ----
     if (active) {
         double div = 0.0;
@@ -473,6 +498,44 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(Cell
         if (lane == 0) sg.group_partial[(size_t)k * sg.group_stride + group] = tot;
     }
     if (threadIdx.x == 0) sg.group_ticket[group] = 0u;
+    if (!kPart) return;
+    // ---- partitioned: the last group to finish publishes this rank's sums ----
+    __shared__ bool rank_last;
+    const int n_groups = ((int)gridDim.x + kCellSgGroup - 1) / kCellSgGroup;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) rank_last = atomicAdd(sg.group_ticket + sg.group_stride, 1u) == (unsigned int)(n_groups - 1);
+    __syncthreads();
+    if (!rank_last) return;
+    __threadfence();
+    const unsigned long long epoch = x.ctl[0] + 1ull;
+    double* pub = sgx_pub(x.block[x.rank], (int)(epoch & 1ull));
+    for (int k = warp; k < kRows; k += kWarps) {
+        const double* row = sg.group_partial + (size_t)k * sg.group_stride;
+        double a = 0.0;
+        for (int q = lane; q < n_groups; q += 32) a = a + __ldcg(row + q);
+        a = warp_sum_all(a);
+        if (lane == 0) pub[k] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    __threadfence_system();
+    if ((int)threadIdx.x < x.world) sgx_st_release_sys(sgx_flags(x.block[threadIdx.x]) + x.rank, epoch);
+    if (threadIdx.x == 0) {
+        sg.group_ticket[sg.group_stride] = 0u;
+        x.ctl[0] = epoch;
+    }
+}
+
+template <int kThreads, int LT, int kMinBlocks = 0>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
+                                                                            CellSgWork sg) {
+    cell_step_sg_body<kThreads, LT, false>(t, p, s, mode, next, sg, HaloInline{}, ShExchange{});
+}
+template <int kThreads, int LT>
+__global__ void __launch_bounds__(kThreads) cell_step_sgx_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next, CellSgWork sg,
+                                                                 HaloInline halo, ShExchange x) {
+    cell_step_sg_body<kThreads, LT, true>(t, p, s, mode, next, sg, halo, x);
 }
 
 template <int kThreads>
@@ -706,6 +769,15 @@ void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState&
         case 2: cell_step_sg_kernel<kCellSgThreads, 2><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
         case 3: cell_step_sg_kernel<kCellSgThreads, 3><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
         default: cell_step_sg_kernel<kCellSgThreads, 4><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
+    }
+}
+void launch_cell_step_sgx(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
+                          const HaloInline& halo, const ShExchange& x, cudaStream_t stream) {
+    const int grid = cell_sg_ctas(t.n_active);
+    switch (sg.l_max) {
+        case 2: cell_step_sgx_kernel<kCellSgThreads, 2><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg, halo, x); break;
+        case 3: cell_step_sgx_kernel<kCellSgThreads, 3><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg, halo, x); break;
+        default: cell_step_sgx_kernel<kCellSgThreads, 4><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg, halo, x); break;
     }
 }
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream) {

@@ -167,6 +167,13 @@ int cell_sg_ctas(int n_active);
 bool cell_sg_supports(int l_max);
 void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
                          bool cap_registers, cudaStream_t stream);
+// The same on a partitioned solver (t.n_active = own + ghost cells, sg.n_fit = own cells): boundary CTAs wait for the neighbours' halo push,
+// and the last group of CTAs to finish publishes this rank's harmonic sums for the in-kernel all-reduce that
+// launch_sh_allsolve_synthesis (odis_sh.cuh) completes. sg.group_ticket needs one more counter at [group_stride].
+struct HaloInline;
+struct ShExchange;
+void launch_cell_step_sgx(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
+                          const HaloInline& halo, const ShExchange& x, cudaStream_t stream);
 // spins (bounded by kHaloSpinCycles) until every neighbour's flag has reached ctl->epoch[0]: all pushes of the
 // exchanges this rank took part in have landed
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream);

@@ -426,6 +426,44 @@ __global__ void __launch_bounds__(kShThreads) sh_solve_synthesis_mf_kernel(ShTab
     }
 }
 
+// Partitioned form of the kernel above (cell_step_sgx_kernel has published every rank's sums): waits for all ranks' epoch flags,
+// adds the ranks' sums in rank order (the same bits on every rank and in every CTA), solves and adds the term to the potential of the
+// held cells (own + ghost). The wait / sum protocol is sh_allsolve_kernel's.
+template <int LT>
+__global__ void __launch_bounds__(kShThreads) sh_allsolve_synthesis_mf_kernel(ShTables t, ShWork w, ShExchange x, double g, double2* __restrict__ eu,
+                                                                              int n_cells) {
+    __shared__ double bsh[kShInlineRows];
+    __shared__ double ssh[kShInlineRows];
+    const int warp = threadIdx.x >> 5;
+    const unsigned long long epoch = x.ctl[0];
+    if ((int)threadIdx.x < x.world) {
+        const unsigned long long* f = x_flags(x.block[x.rank]) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < epoch) {
+            if (clock64() - t0 > kShSpinCycles) { x.ctl[2] = 1ull; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < t.rows; k += kShThreads) {
+        double a = 0.0;
+        for (int r = 0; r < x.world; r++) a = a + ld_relaxed_sys(x_pub(x.block[r], (int)(epoch & 1)) + k);
+        bsh[k] = a;
+        if (blockIdx.x == 0) w.b[k] = a;
+    }
+    __syncthreads();
+    solve_rows(t, bsh, g, ssh, warp, kShWarps);
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < t.rows; k += kShThreads) w.s[k] = ssh[k];
+    const RecConst rc;
+    for (int i = blockIdx.x * kShThreads + threadIdx.x; i < n_cells; i += gridDim.x * kShThreads) {
+        const double u = t.trig[i], z = t.trig[(size_t)t.stride + i], c1 = t.trig[2 * (size_t)t.stride + i], s1 = t.trig[3 * (size_t)t.stride + i];
+        const double u0 = eu[i].y;
+        eu[i].y = u0 + synthesis_mf_cell<LT>(t, rc, ssh, u, z, c1, s1);
+    }
+}
+
 // ---- ensembles: FP64 tensor-core GEMMs ------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -680,6 +718,16 @@ void launch_sh_solve_synthesis(const ShTables& t, const ShWork& w, const double*
         case 2: sh_solve_synthesis_mf_kernel<2><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
         case 3: sh_solve_synthesis_mf_kernel<3><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
         default: sh_solve_synthesis_mf_kernel<4><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
+    }
+}
+
+void launch_sh_allsolve_synthesis(const ShTables& t, const ShWork& w, const ShExchange& x, double g, double2* eu, int n_cells, cudaStream_t stream) {
+    int grid = (n_cells + kShThreads - 1) / kShThreads;
+    if (grid > kShMaxBlocks) grid = kShMaxBlocks;
+    switch (t.l_max) {
+        case 2: sh_allsolve_synthesis_mf_kernel<2><<<grid, kShThreads, 0, stream>>>(t, w, x, g, eu, n_cells); break;
+        case 3: sh_allsolve_synthesis_mf_kernel<3><<<grid, kShThreads, 0, stream>>>(t, w, x, g, eu, n_cells); break;
+        default: sh_allsolve_synthesis_mf_kernel<4><<<grid, kShThreads, 0, stream>>>(t, w, x, g, eu, n_cells); break;
     }
 }
 

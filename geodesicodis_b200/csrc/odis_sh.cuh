@@ -76,6 +76,9 @@ void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_
 // partials of every row in group order, solves, and adds the term to U of the cells [0, n_cells). Leaves b and s in `w` too.
 void launch_sh_solve_synthesis(const ShTables& t, const ShWork& w, const double* group_partial, int group_stride, int n_groups, double g, double2* eu,
                                int n_cells, cudaStream_t stream);
+// The same on a partitioned solver (launch_cell_step_sgx has published every rank's sums into the exchange blocks): waits for all
+// ranks, adds their sums in rank order, solves, adds the term to U of the held cells. One launch instead of three.
+void launch_sh_allsolve_synthesis(const ShTables& t, const ShWork& w, const ShExchange& x, double g, double2* eu, int n_cells, cudaStream_t stream);
 
 }  // namespace odis
 

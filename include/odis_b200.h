@@ -146,7 +146,7 @@ typedef struct odis_params {
                              *     direct-load cell kernel. bit 0: direct-load edge kernel; bit 1: staged cell kernel; bit 2: ONE fused
                              *     kernel per step (cell update of the previous step + edge update; one halo exchange per step).
                              *     Every selection gives bit-identical fields. bit 3: no CUDA-graph replay. bit 4 (with
-                             *     odis_enable_self_gravity, degree <= 4, unpartitioned): 3 launches per step instead of 5 — the harmonic
+                             *     odis_enable_self_gravity, degree <= 4; partitioned solvers too): 3 launches per step instead of 5 (6) — the harmonic
                              *     analysis is folded into the cell update and the solve into the synthesis (sums associate differently:
                              *     fields agree with the default to ~1e-13 relative, not bit for bit). bit 5 (with odis_enable_advection):
                              *     the nonlinear step in 4 gather launches instead of 6 (bit-identical fields). bit 6: the per-step cell
