@@ -118,6 +118,8 @@ SIGNATURES = {
     "odis_op_integrate_ab3_scalar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i32]),
     "odis_op_interpolate_velocity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_op_update_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(c_f64)]),
+    "odis_stage_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "odis_commit_state": (C.c_int, [C.c_void_p, c_i64]),
     "odis_snapshot_begin": (C.c_int, [C.c_void_p, c_i32, C.c_uint32]),
     "odis_snapshot_wait": (C.c_int, [C.c_void_p, c_i32, P(SnapshotView)]),
     "odis_get_iter": (C.c_int, [C.c_void_p, P(c_i64)]),

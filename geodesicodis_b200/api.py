@@ -379,6 +379,25 @@ class Solver:
         check(_lib.load().odis_set_state(self._h, k[0][1], k[1][1], k[2][1], k[3][1], iter))
         self._iter0 = iter
 
+    def stage_state(self, v=None, eta=None, dvdt=None, detadt=None) -> None:
+        """Starts the host -> device copies of the NEXT state on the second stream and returns; stepping goes on meanwhile. The arrays
+        must be float64, contiguous (no conversion copy is made: they have to outlive the call) and unchanged until commit_state."""
+        ptrs = []
+        for a, n in ((v, self.F), (eta, self.N), (dvdt, self.F * 3), (detadt, self.N * 3)):
+            if a is None:
+                ptrs.append(None)
+                continue
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == n):
+                raise ValueError("stage_state needs contiguous float64 arrays of the state's sizes")
+            ptrs.append(a.ctypes.data)
+        self._staged = (v, eta, dvdt, detadt)                    # keep them alive until the commit
+        check(_lib.load().odis_stage_state(self._h, *ptrs))
+
+    def commit_state(self, iter: int = 0) -> None:
+        """Makes the staged arrays the state, behind the steps enqueued so far; does not wait on the host."""
+        check(_lib.load().odis_commit_state(self._h, iter))
+        self._iter0 = iter
+
     def step(self, nsteps: int = 1) -> None:
         check(_lib.load().odis_step(self._h, nsteps))
 
@@ -458,8 +477,9 @@ class Solver:
         """Enqueue the copy-out of `fields` (SNAP_* bits) behind the steps taken so far; returns at once (odis_snapshot_begin)."""
         check(_lib.load().odis_snapshot_begin(self._h, slot, fields))
 
-    def snapshot_wait(self, slot: int) -> dict:
-        """Block until the slot's copy has landed; arrays are COPIES of the library's page-locked buffers."""
+    def snapshot_wait(self, slot: int, copy: bool = True) -> dict:
+        """Block until the slot's copy has landed; arrays are COPIES of the library's page-locked buffers (copy=False: views of them,
+        valid until the slot's next snapshot_begin)."""
         view = _lib.SnapshotView()
         check(_lib.load().odis_snapshot_wait(self._h, slot, C.byref(view)))
         out = {"dissipation_avg": view.dissipation_avg, "iter": view.iter}
@@ -467,7 +487,8 @@ class Solver:
                                ("velocity", self.F, (self.F,))):
             ptr = getattr(view, name)
             if ptr:
-                out[name] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(shape).copy()
+                a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)
+                out[name] = a.copy() if copy else a
         return out
 
     def dissipation_avg(self) -> float:

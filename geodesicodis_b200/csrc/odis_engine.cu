@@ -168,6 +168,12 @@ struct odis_solver {
         int64_t iter = 0;
     } snap[2];
     cudaStream_t copy_stream = nullptr;
+    // next state staged while the current interval runs (odis_stage_state / odis_commit_state): reference-ordered device copy
+    // [v F | dvdt 3F | eta N | detadt 3N], filled on the copy stream
+    double* d_stage_next = nullptr;
+    cudaEvent_t staged = nullptr, consumed = nullptr;
+    bool stage_pending = false, stage_used = false;
+    unsigned stage_mask = 0;                 // bit k: array k of the staged state was given (others are zero)
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
@@ -778,6 +784,8 @@ int odis_get_partition(odis_solver* s, int32_t* rank, int32_t* world, int32_t* o
     return ODIS_OK;
 }
 
+static int finish_set_state(odis_solver* s, int64_t iter, bool sync);
+
 int odis_set_state(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt, int64_t iter) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
@@ -804,6 +812,13 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     s->he1 = 0; s->he2 = 1; s->hefree = 2;
     // the history of every held cell is kept (halo cells are updated locally by the fused kernel)
     odis::launch_scatter_history(N, s->d_cell_perm, detadt ? s->d_stage : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    return finish_set_state(s, iter, true);
+}
+
+// after the four scatter launches of odis_set_state / odis_commit_state: counters, the potential of the first step
+static int finish_set_state(odis_solver* s, int64_t iter, bool sync) {
+    const int N = s->N;
+    int rc;
     s->launches += 4;
     ODIS_CUDA(cudaMemsetAsync(&s->d_ctl->count, 0, sizeof(unsigned long long), s->stream));
     s->iter = iter;
@@ -825,8 +840,65 @@ int odis_set_state(odis_solver* s, const double* v, const double* eta, const dou
     ODIS_CUDA(cudaGetLastError());
     // partitioned + self-gravity: the harmonic sums wait for every rank's share, so the call must not block here (one host
     // thread may be driving all ranks in turn); the stream keeps the order
-    if (!(s->world > 1 && s->sh_on)) ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    if (sync && !(s->world > 1 && s->sh_on)) ODIS_CUDA(cudaStreamSynchronize(s->stream));
     return ODIS_OK;
+}
+
+// ---- the next interval's state staged while the current one runs ------------------------------------------------------
+// odis_stage_state: host -> device copies of the (reference-ordered) arrays on the copy stream into a staging area of their own;
+// returns at once, the caller keeps stepping. The host arrays must stay unchanged until odis_commit_state (page-locked memory makes
+// the copies truly asynchronous). odis_commit_state: the solver's stream waits for the copies, renumbers the staged arrays into the
+// state (the four scatter launches of odis_set_state) and evaluates the first potential; it does not wait on the host. A further
+// odis_stage_state waits (on the device) until the commit has consumed the staging area.
+int odis_stage_state(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
+    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "staged state needs an unpartitioned solver");
+    if (s->stage_pending) return fail(ODIS_ERR_STATE, "a staged state is waiting for odis_commit_state");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const size_t F = (size_t)s->Fg, N = (size_t)s->Ng;
+    if (!s->copy_stream) ODIS_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    if (!s->d_stage_next) {
+        int rc = dev_alloc(s, &s->d_stage_next, 4 * F + 4 * N);
+        if (rc) return rc;
+        ODIS_CUDA(cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming));
+        ODIS_CUDA(cudaEventCreateWithFlags(&s->consumed, cudaEventDisableTiming));
+    }
+    if (s->stage_used) ODIS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->consumed, 0));     // the previous commit's scatter launches have read it
+    double* d = s->d_stage_next;
+    const double* host[4] = {v, dvdt, eta, detadt};
+    const size_t count[4] = {F, 3 * F, N, 3 * N};
+    s->stage_mask = 0;
+    for (int k = 0; k < 4; k++) {
+        if (host[k]) {
+            ODIS_CUDA(cudaMemcpyAsync(d, host[k], count[k] * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));
+            s->stage_mask |= 1u << k;
+        }
+        d += count[k];
+    }
+    ODIS_CUDA(cudaEventRecord(s->staged, s->copy_stream));
+    s->stage_pending = true;
+    return ODIS_OK;
+}
+
+int odis_commit_state(odis_solver* s, int64_t iter) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
+    if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
+    if (!s->stage_pending) return fail(ODIS_ERR_STATE, "odis_stage_state has not been called");
+    ODIS_CUDA(cudaSetDevice(s->device));
+    const size_t F = (size_t)s->Fg, N = (size_t)s->Ng;
+    const double* d_v = s->d_stage_next; const double* d_dv = d_v + F; const double* d_eta = d_dv + 3 * F; const double* d_de = d_eta + N;
+    const unsigned m = s->stage_mask;
+    ODIS_CUDA(cudaStreamWaitEvent(s->stream, s->staged, 0));
+    odis::launch_scatter_x(s->F, s->d_edge_perm, (m & 1u) ? d_v : nullptr, s->d_vl[s->cur], 0, s->stream);
+    s->hv1 = 0;
+    odis::launch_scatter_history(s->Fo, s->d_edge_perm, (m & 2u) ? d_dv : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
+    odis::launch_scatter_x(s->N, s->d_cell_perm, (m & 4u) ? d_eta : nullptr, s->d_eu[s->ecur], 1, s->stream);
+    s->he1 = 0; s->he2 = 1; s->hefree = 2;
+    odis::launch_scatter_history(s->N, s->d_cell_perm, (m & 8u) ? d_de : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    ODIS_CUDA(cudaEventRecord(s->consumed, s->stream));
+    s->stage_pending = false;
+    s->stage_used = true;
+    return finish_set_state(s, iter, false);
 }
 
 int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l_max, const double* factor, int32_t stored_basis) {
@@ -1655,6 +1727,9 @@ void odis_destroy(odis_solver* s) {
         if (sl.ready) cudaEventDestroy(sl.ready);
         if (sl.done) cudaEventDestroy(sl.done);
     }
+    if (s->d_stage_next) cudaFree(s->d_stage_next);
+    if (s->staged) cudaEventDestroy(s->staged);
+    if (s->consumed) cudaEventDestroy(s->consumed);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);

@@ -322,6 +322,14 @@ typedef struct odis_snapshot_view {
 } odis_snapshot_view;
 int odis_snapshot_begin(odis_solver* s, int32_t slot, uint32_t fields);
 int odis_snapshot_wait(odis_solver* s, int32_t slot, odis_snapshot_view* out);
+/* The input side of the same pipeline: the NEXT state (a restart, the next case of a sweep, coupled-model input — arrays as in
+ * odis_set_state, the reference's getInitialConditions / loadInitialConditions arrays, src/initialConditions.cpp:19-144) travels to the
+ * device on the second stream while the current interval is still stepping. odis_stage_state returns at once; the host arrays must stay
+ * unchanged until odis_commit_state (page-locked memory makes the copies asynchronous). odis_commit_state makes the staged arrays the
+ * solver's state behind the steps enqueued so far (same renumbering launches and first potential as odis_set_state) without waiting on
+ * the host. One staged state at a time; unpartitioned solvers. */
+int odis_stage_state(odis_solver* s, const double* v, const double* eta, const double* dvdt /*[F][3]*/, const double* detadt /*[N][3]*/);
+int odis_commit_state(odis_solver* s, int64_t iter);
 int odis_get_iter(odis_solver* s, int64_t* iter_out);
 /* Bytes of device memory held, and the algorithmic HBM bytes one step moves. */
 int odis_get_footprint(odis_solver* s, int64_t* device_bytes_out, int64_t* algorithmic_bytes_per_step_out);
