@@ -44,10 +44,11 @@ def emulated_library(built_library):
     return lib, libdir
 
 
-def run_gpu_tests_on_the_emulation(lib, libdir, files, extra_env=None, select=SKIP):
+def run_gpu_tests_on_the_emulation(lib, libdir, files, extra_env=None, select=SKIP, workers=4):
     env = dict(os.environ, ODIS_B200_LIB=lib, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x", *(["-k", select] if select else []), "-p", "no:cacheprovider",
+           *(["-n", str(workers)] if workers > 1 else []),           # independent tests, one process each (pytest-xdist)
            *[a for d in DESELECT for a in ("--deselect", d)]]
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     tail = r.stdout[-3000:]
@@ -75,7 +76,7 @@ def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
     2 and 4 B200s with `-m gpu`.)"""
     tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py", "tests/test_variant_ids16_gpu.py::test_narrow_ids_on_a_partitioned_grid",
                                                               "tests/test_variant_sg3_gpu.py::test_three_launch_variant_on_a_partitioned_grid"],
-                                          extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="")
+                                          extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="", workers=3)
     assert int(tail.split(" passed")[0].split()[-1]) == 12 and "skipped" not in tail, tail
 
 
@@ -115,7 +116,7 @@ def test_racecheck_of_partitioned_runs_under_thread_sanitizer(emulated_library):
             os.remove(os.path.join(os.path.dirname(lib), f))
     files = ["tests/test_multigpu.py::test_partitioned_run_matches_single_gpu[2]",
              "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]"]
-    tail = run_gpu_tests_on_the_emulation(lib, emulated_library[1], files, select="",
+    tail = run_gpu_tests_on_the_emulation(lib, emulated_library[1], files, select="", workers=2,
                                           extra_env={"LD_PRELOAD": tsan_rt, "OMP_NUM_THREADS": "1", "ODIS_B200_EMULATED_DEVICES": "2",
                                                      "TSAN_OPTIONS": f"halt_on_error=0:report_signal_unsafe=0:exitcode=0:log_path={report}"})
     assert int(tail.split(" passed")[0].split()[-1]) == 2, tail
