@@ -158,7 +158,8 @@ def variant_probe(args) -> None:
         prm, L, S = workload_params(mesh), max(args.sh_degree, 2), args.substeps
         ref_eta = None
         for key, sel in (("default", 0), ("cell_update_64_registers", 64), ("self_gravity_3_launch", 16),
-                         ("self_gravity_3_launch_64_registers", 80), ("edge_ids_16bit", 128), ("edge_ids_16bit_self_gravity_3_launch", 144)):
+                         ("self_gravity_3_launch_64_registers", 80), ("edge_ids_16bit", 128), ("edge_ids_16bit_self_gravity_3_launch", 144),
+                         ("cell_update_l2_prefetch", 512), ("cell_update_l2_prefetch_64_registers", 576), ("edge_ids_16bit_cell_l2_prefetch", 640)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_self_gravity(L, shell_factor(L))
             sv.step(2 * S)

@@ -115,6 +115,11 @@ struct odis_solver {
     bool nl_on = false;
     bool nl_fused = false;           // params.reserved[0] bit 5: the 4-launch variant of the nonlinear step
     bool cell_occ = false;           // params.reserved[0] bit 6: per-step cell update with the register-capped (50 % occupancy) kernel
+    bool cell_prefetch = false;      // params.reserved[0] bit 9: per-step cell update prefetches the next wave's rows into L2
+    int cell_variant() const {
+        return cell_prefetch ? (cell_occ ? odis::kCellPrefetchOccupancyVariant : odis::kCellPrefetchVariant)
+                             : (cell_occ ? odis::kCellOccupancyVariant : prm.block_threads);
+    }
     int nl_launches() const { return nl_fused ? odis::kNlLaunchesFused : odis::kNlLaunches; }
     odis::NlTables nl{};
     double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
@@ -390,6 +395,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->nl_fused = (prm->reserved[0] & 32) != 0;
     s->cell_occ = (prm->reserved[0] & 64) != 0;
     s->edge_ids16 = (prm->reserved[0] & 128) != 0 && s->pipe_edge;
+    s->cell_prefetch = (prm->reserved[0] & 512) != 0;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -1244,7 +1250,7 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
         odis::HaloInline hc;
         if (inline_e) hc = halo_inline_cell(s);
         odis::launch_cell_step(ct, s->phys, cs, mode, next, odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U,
-                               s->cell_occ ? odis::kCellOccupancyVariant : s->prm.block_threads, inline_e ? &hc : nullptr, s->stream);
+                               s->cell_variant(), inline_e ? &hc : nullptr, s->stream);
     }
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;

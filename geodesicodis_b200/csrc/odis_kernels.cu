@@ -277,11 +277,51 @@ __device__ __forceinline__ double tidal_potential(const Physics& p, const StepSc
     }
 }
 
+// Opt-in (kPrefetch): one thread of every CTA asks the memory system to bring the streamed rows of the tile `ahead` CTAs further on
+// into L2 (cp.async.bulk.prefetch.L2: no registers, no completion to wait for). The CTAs of one wave issue their loads, gather and
+// compute more or less in step, so DRAM idles while they gather and compute; with the rows of the next wave already on their way the
+// stream never stops, and a CTA's first loads become L2 hits. `ahead` = CTAs resident on the GPU (flags >> 8).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned int bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <int kThreads>
+__device__ __forceinline__ void prefetch_cell_tile(const CellTables& t, const Physics& p, const CellState& s, int flags, size_t tile) {
+    const size_t i0 = tile * kThreads, N = (size_t)t.n_cells;
+    if (i0 + kThreads > N) return;                        // whole tiles inside the arrays only
+    if (flags & CELL_UPDATE_ETA) {
+#pragma unroll
+        for (int j = 0; j < kCellEdges; j++) l2_prefetch_bulk(t.eid + (size_t)j * N + i0, kThreads * sizeof(int));
+        l2_prefetch_bulk(t.area + i0, kThreads * sizeof(double));
+        l2_prefetch_bulk(s.h1 + i0, kThreads * sizeof(double));
+        l2_prefetch_bulk(s.h2 + i0, kThreads * sizeof(double));
+    }
+    l2_prefetch_bulk(s.eu_in + i0, kThreads * sizeof(double2));
+    if (flags & CELL_UPDATE_U) {
+        unsigned int rows = 0, sq = 0;                    // bit r: row r of trig / trig_sq, as load_trig reads them
+        switch (p.potential) {
+            case P_ECC: rows = 0xC0u; sq = 3u; break;
+            case P_OBLIQ: rows = 0x24u; break;
+            case P_OBLIQ_WEST: rows = 0x0Fu; break;
+            case P_FULL: rows = 0xE4u; sq = 3u; break;
+            case P_FULL2: rows = 0xDFu; sq = 1u; break;
+            default: break;
+        }
+        for (int r = 0; r < 8; r++)
+            if (rows >> r & 1u) l2_prefetch_bulk(t.trig + (size_t)r * N + i0, kThreads * sizeof(double));
+        for (int r = 0; r < 2; r++)
+            if (sq >> r & 1u) l2_prefetch_bulk(t.trig_sq + (size_t)r * N + i0, kThreads * sizeof(double));
+    }
+}
+
 // kMinBlocks > 0 caps the registers so that that many CTAs fit an SM (opt-in variant: 8 x 128 threads = 50 % occupancy instead of
 // 37.5 %, at the price of a few spilled values); 0 = no cap, the default.
-template <int kThreads, int kMinBlocks = 0>
+template <int kThreads, int kMinBlocks = 0, bool kPrefetch = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
                                                                          int flags, HaloInline halo) {
+    if (kPrefetch) {
+        if (threadIdx.x == kThreads - 32) prefetch_cell_tile<kThreads>(t, p, s, flags, (size_t)blockIdx.x + (size_t)(flags >> 8));
+        flags &= 0xff;
+    }
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -732,6 +772,20 @@ void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s,
     none.wait_from = 0x7fffffff;
     if (block_threads == kCellOccupancyVariant) {        // 128 threads, registers capped for 8 CTAs per SM
         cell_step_kernel<128, 8><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
+        return;
+    }
+    if (block_threads == kCellPrefetchVariant || block_threads == kCellPrefetchOccupancyVariant) {
+        // rows of the tile one GPU-full of CTAs ahead travel into L2 while this CTA works (arrays are padded to whole 128-cell tiles)
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        }
+        const bool capped = block_threads == kCellPrefetchOccupancyVariant;
+        const int ahead = sms * (capped ? 8 : 6), f = (flags & 0xff) | (ahead << 8);
+        if (capped) cell_step_kernel<128, 8, true><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, f, halo ? *halo : none);
+        else cell_step_kernel<128, 0, true><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, f, halo ? *halo : none);
         return;
     }
     dispatch_threads(block_threads, [&](auto bt) {

@@ -144,6 +144,9 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
 // flags: CellFlags (update eta and/or the potential). block_threads: 128 (default), 256, 512, or kCellOccupancyVariant (128 threads with
 // the register count capped at 64 for 50 % occupancy; opt-in, odis_params.reserved[0] bit 6)
 constexpr int kCellOccupancyVariant = -128;
+// 128 threads + the streamed rows of the tile one GPU-full of CTAs ahead prefetched into L2 (default registers / capped at 64)
+constexpr int kCellPrefetchVariant = -129;
+constexpr int kCellPrefetchOccupancyVariant = -130;
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                       int flags, int block_threads, const HaloInline* halo, cudaStream_t stream);
 // Opt-in variant for runs with the self-gravity term (odis_params.reserved[0] bit 4): the cell update also accumulates the

@@ -153,7 +153,8 @@ typedef struct odis_params {
                              *     update compiled with a 64-register cap (50 % instead of 37.5 % occupancy; bit-identical fields). bit 7 (staged edge
                              *     kernel): stencil ids travel as 16-bit offsets from the edge's own id, one bulk copy per tile; tiles where an
                              *     offset does not fit stay on the 32-bit rows (180 instead of 200 B per edge; bit-identical fields). bit 8
-                             *     (tests): offset range +-1023 instead of +-32767. Rest must be 0. */
+                             *     (tests): offset range +-1023 instead of +-32767. bit 9: the per-step cell update prefetches the streamed rows
+                             *     of the tile one GPU-full of CTAs ahead into L2 (cp.async.bulk.prefetch.L2; bit-identical fields). Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {

@@ -22,7 +22,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 #    error in one cannot fail the others)
 run 900 tests_validated python -m pytest tests -m gpu -x -q -k "not surface_ and not variant_"
 for f in tests/test_surface_ops_gpu.py tests/test_surface_planet_gpu.py tests/test_surface_analytical_gpu.py tests/test_surface_hybrid_gpu.py \
-         tests/test_surface_sigint_gpu.py tests/test_variant_blocks_gpu.py tests/test_variant_ids16_gpu.py tests/test_variant_sg3_gpu.py \
+         tests/test_surface_sigint_gpu.py tests/test_variant_blocks_gpu.py tests/test_variant_ids16_gpu.py tests/test_variant_prefetch_gpu.py tests/test_variant_sg3_gpu.py \
          tests/test_variant_nl4_gpu.py tests/test_variant_overlap_gpu.py; do
     run 600 "$(basename $f .py)" python -m pytest $f -m gpu -q
 done

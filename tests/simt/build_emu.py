@@ -154,6 +154,8 @@ def rewrite_asm(s: str) -> tuple[str, int]:
             rep = f"{outs[0]} = 0;"
         elif ptx.startswith("ld.") and "{%0, %1}" in ptx:
             rep = f"{{ const auto* simt_p_ = ({ins[0]}); {outs[0]} = simt_p_->x; {outs[1]} = simt_p_->y; }}"
+        elif ptx.startswith("cp.async.bulk.prefetch"):          # no data moves; touching both ends lets the address sanitizer check the range
+            rep = f"{{ const volatile unsigned char* simt_p_ = (const volatile unsigned char*)({ins[0]}); (void)simt_p_[0]; (void)simt_p_[({ins[1]}) - 1]; }}"
         elif ptx.startswith("ld.acquire"):
             rep = f"{outs[0]} = __atomic_load_n({ins[0]}, __ATOMIC_ACQUIRE);"
         elif ptx.startswith("ld.relaxed.sys"):

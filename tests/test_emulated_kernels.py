@@ -25,7 +25,7 @@ CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "test
            "tests/test_ensemble_gpu.py::test_members_match_oracle",
            "tests/test_ensemble_gpu.py::test_ensemble_self_gravity_matches_oracle[4-5-2]"]      # FP64 mma.sync fragments modelled
 NEW = ["tests/test_surface_planet_gpu.py", "tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
-       "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py", "tests/test_variant_ids16_gpu.py"]
+       "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py", "tests/test_variant_ids16_gpu.py", "tests/test_variant_prefetch_gpu.py"]
 # left out under emulation: full-size grids and the slowest parameter sets
 SKIP = "not large_grid and not high_degree_matrix_free and not 5-12 and not 5-8 and not 6-4 and not 6-2 and not l6_obliqwest and not band_limited"
 DESELECT = ["tests/test_step_parity_gpu.py::test_direct_and_pipelined_kernels_agree[6]"]
@@ -89,7 +89,7 @@ def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
         pytest.skip("no AddressSanitizer runtime with this compiler")
     lib = build_emu.build(asan=True)
     files = ["tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py",
-             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py", "tests/test_variant_ids16_gpu.py",
+             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py", "tests/test_variant_ids16_gpu.py", "tests/test_variant_prefetch_gpu.py",
              "tests/test_multigpu.py::test_partitioned_run_matches_single_gpu[2]",                    # halo push / wait between two concurrent "devices"
              "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]"]     # + all-reduce through peer memory
     select = SKIP + " and not l5_ and not l6_ and not 5-2 and not 5-3 and not full_orbit and not random_state and not kernels_agree"
