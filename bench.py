@@ -159,7 +159,8 @@ def variant_probe(args) -> None:
         ref_eta = None
         for key, sel in (("default", 0), ("cell_update_64_registers", 64), ("self_gravity_3_launch", 16),
                          ("self_gravity_3_launch_64_registers", 80), ("edge_ids_16bit", 128), ("edge_ids_16bit_self_gravity_3_launch", 144),
-                         ("cell_update_l2_prefetch", 512), ("cell_update_l2_prefetch_64_registers", 576), ("edge_ids_16bit_cell_l2_prefetch", 640)):
+                         ("cell_update_l2_prefetch", 512), ("cell_update_l2_prefetch_64_registers", 576), ("edge_ids_16bit_cell_l2_prefetch", 640),
+                         ("self_gravity_3_launch_edge_ids_16bit_cell_l2_prefetch", 16 + 128 + 512)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_self_gravity(L, shell_factor(L))
             sv.step(2 * S)

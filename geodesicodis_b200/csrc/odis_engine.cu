@@ -138,7 +138,8 @@ struct odis_solver {
     unsigned int* d_sg_ticket = nullptr;
     int sg_cta_stride = 0, sg_group_stride = 0;
     odis::CellSgWork sg_work() const {
-        return odis::CellSgWork{sh_lmax, No, d_sg_cta, sg_cta_stride, d_sg_group, sg_group_stride, d_sg_ticket};
+        return odis::CellSgWork{sh_lmax, No, d_sg_cta, sg_cta_stride, d_sg_group, sg_group_stride, d_sg_ticket,
+                                cell_prefetch ? odis::resident_cell_ctas(cell_occ && world == 1) : 0};
     }
     int sg_cells() const { return world > 1 ? N : No; }        // cells the cell update covers (partitioned: ghost cells too)
     int sg_groups() const { return (odis::cell_sg_ctas(sg_cells()) + odis::kCellSgGroup - 1) / odis::kCellSgGroup; }

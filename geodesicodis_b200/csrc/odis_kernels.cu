@@ -425,6 +425,12 @@ __device__ __forceinline__ void cell_step_sg_body(const CellTables& t, const Phy
     static_assert(kRows <= kThreads, "one thread per basis row writes the CTA partial");
     __shared__ double red[kRows * kWarps];
     __shared__ bool group_last;
+    if (sg.prefetch_ahead > 0 && threadIdx.x == kThreads - 32) {      // opt-in: next wave's rows into L2 (see cell_step_kernel)
+        const size_t tile = (size_t)blockIdx.x + (size_t)sg.prefetch_ahead, i0 = tile * kThreads, N = (size_t)t.n_cells;
+        prefetch_cell_tile<kThreads>(t, p, s, CELL_UPDATE_ETA | CELL_UPDATE_U, tile);
+        if (i0 + kThreads <= N)
+            for (int r = 0; r < 4; r++) l2_prefetch_bulk(t.trig + (size_t)r * N + i0, kThreads * sizeof(double));     // the basis' rows
+    }
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     bool bnd_cta = false;
@@ -765,6 +771,16 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
     });
 }
 
+int resident_cell_ctas(bool capped) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms * (capped ? 8 : 6);
+}
+
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                       int flags, int block_threads, const HaloInline* halo, cudaStream_t stream) {
     HaloInline none;
@@ -776,14 +792,8 @@ void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s,
     }
     if (block_threads == kCellPrefetchVariant || block_threads == kCellPrefetchOccupancyVariant) {
         // rows of the tile one GPU-full of CTAs ahead travel into L2 while this CTA works (arrays are padded to whole 128-cell tiles)
-        static int sms = 0;
-        if (sms == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        }
         const bool capped = block_threads == kCellPrefetchOccupancyVariant;
-        const int ahead = sms * (capped ? 8 : 6), f = (flags & 0xff) | (ahead << 8);
+        const int ahead = resident_cell_ctas(capped), f = (flags & 0xff) | (ahead << 8);
         if (capped) cell_step_kernel<128, 8, true><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, f, halo ? *halo : none);
         else cell_step_kernel<128, 0, true><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, f, halo ? *halo : none);
         return;

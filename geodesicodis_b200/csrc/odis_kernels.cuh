@@ -164,7 +164,9 @@ struct CellSgWork {
     double* group_partial;          // [rows][group_stride]
     int group_stride;               // >= ceil(cell_sg_ctas / kCellSgGroup)
     unsigned int* group_ticket;     // [group_stride], zero before the first launch (each launch leaves it zero again)
+    int prefetch_ahead;             // > 0: prefetch the rows of the tile this many CTAs ahead into L2 (CTAs resident on the GPU); 0: off
 };
+int resident_cell_ctas(bool capped);   // 128-thread cell-update CTAs resident on the current GPU (SMs x 6, or x 8 with the register cap)
 cudaError_t cell_sg_configure();    // recurrence coefficients -> constant memory (once per device, before any capture)
 int cell_sg_ctas(int n_active);
 bool cell_sg_supports(int l_max);

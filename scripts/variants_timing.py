@@ -24,7 +24,7 @@ SELECTIONS = [("default (5 launches/step)", 0), ("3-launch self-gravity (bit 4)"
               ("16-bit stencil ids in the staged edge kernel (bit 7)", 128), ("16-bit ids + 3-launch self-gravity (bits 4,7)", 144),
               ("16-bit ids + 3-launch + 64-register cell update (bits 4,6,7)", 208),
               ("L2 prefetch in the cell update (bit 9)", 512), ("L2 prefetch + 64 registers (bits 6,9)", 576),
-              ("16-bit ids + L2 prefetch (bits 7,9)", 640)]
+              ("16-bit ids + L2 prefetch (bits 7,9)", 640), ("3-launch + 16-bit ids + L2 prefetch (bits 4,7,9)", 656)]
 ref = None
 for name, sel in SELECTIONS:
     s = odis.Solver(mesh, dict(prm, kernel_select=sel))

@@ -53,3 +53,42 @@ def test_prefetching_cell_update_on_a_partitioned_grid(odis, world):
             p.step(n)
     for fid in (odis.FIELD_VELOCITY, odis.FIELD_ETA, odis.FIELD_DVDT):
         assert np.array_equal(sum(p.field(fid) for p in parts), ref.field(fid)), fid
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_prefetch_with_the_three_launch_self_gravity_step(odis, world):
+    """Bits 4 + 9: the cell update that also carries the harmonic analysis prefetches too (single solver: same bits as without the
+    prefetch; partitioned: against the single-device default, 1e-10)."""
+    from test_multigpu import _device_count
+    if world > 1 and _device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    pos, fr, cen = odis.generate_grid(6)
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, PRM["radius"])
+    prm = dict(PRM, potential=5, reorder=1, semimajor_axis=0.0, friction=0)
+    factor = np.array([0.0, 0.0, 0.4])
+    rng = np.random.default_rng(9)
+    v0, e0 = rng.uniform(-1, 1, mesh.n_edges) * 1e-2, rng.uniform(-1, 1, mesh.n_cells)
+    ref = odis.Solver(mesh, dict(prm, kernel_select=16 if world == 1 else 0), device=0)
+    ref.enable_self_gravity(2, factor)
+    ref.set_state(v0, e0)
+    ref.step(40)
+    parts = [odis.Solver(mesh, dict(prm, kernel_select=16 + 512), device=k, rank=k, world=world) for k in range(world)]
+    if world > 1:
+        blobs = [p.halo_blob() for p in parts]
+        for p in parts:
+            p.halo_connect(blobs)
+    for p in parts:
+        p.enable_self_gravity(2, factor)
+    for p in parts:
+        p.set_state(v0, e0)
+    for n in (15, 25):
+        for p in parts:
+            p.step(n)
+    for fid in (odis.FIELD_VELOCITY, odis.FIELD_ETA, odis.FIELD_POTENTIAL):
+        total, want = sum(p.field(fid) for p in parts), ref.field(fid)
+        if world == 1:
+            assert np.array_equal(total, want), fid
+        else:
+            assert float(np.abs(total - want).max() / np.abs(want).max()) <= 1e-10, fid
+    for p in parts:
+        p.synchronize()
