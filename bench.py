@@ -157,9 +157,10 @@ def variant_probe(args) -> None:
         mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
         prm, L, S = workload_params(mesh), max(args.sh_degree, 2), args.substeps
         ref_eta = None
-        for key, sel in (("default", 0), ("cell_update_64_registers", 64), ("self_gravity_3_launch", 16),
-                         ("self_gravity_3_launch_64_registers", 80), ("edge_ids_16bit", 128), ("edge_ids_16bit_self_gravity_3_launch", 144),
-                         ("cell_update_l2_prefetch", 512), ("cell_update_l2_prefetch_64_registers", 576), ("edge_ids_16bit_cell_l2_prefetch", 640),
+        # selections that reuse validated synchronisation first; the new mbarrier byte accounting (16-bit ids) last
+        for key, sel in (("default", 0), ("cell_update_64_registers", 64), ("cell_update_l2_prefetch", 512),
+                         ("cell_update_l2_prefetch_64_registers", 576), ("self_gravity_3_launch", 16), ("self_gravity_3_launch_64_registers", 80),
+                         ("self_gravity_3_launch_cell_l2_prefetch", 16 + 512), ("edge_ids_16bit", 128), ("edge_ids_16bit_cell_l2_prefetch", 640),
                          ("self_gravity_3_launch_edge_ids_16bit_cell_l2_prefetch", 16 + 128 + 512)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_self_gravity(L, shell_factor(L))
@@ -273,19 +274,38 @@ def variant_probe(args) -> None:
     print(json.dumps(out), flush=True)
 
 
-def run_probe(name: str, args) -> dict:
-    """Runs `bench.py --variant-probe name` in a subprocess; any failure is recorded instead of raised."""
+PROBE_BUDGET_S = 420.0          # all child-process probes of one bench run together (each also has its own limit)
+_probe_deadline = [None]
+
+
+def run_probe(name: str, args, limit: float = 180.0) -> dict:
+    """Runs `bench.py --variant-probe name` in a subprocess; any failure is recorded instead of raised. A probe that does not return
+    (a kernel selection that has never run on this hardware) is killed at its limit and what it had printed until then is kept."""
+    if _probe_deadline[0] is None:
+        _probe_deadline[0] = time.time() + PROBE_BUDGET_S
+    limit = min(limit, _probe_deadline[0] - time.time())
+    if limit < 20.0:
+        return {"probe": name, "error": "skipped: the probes' time budget of this bench run is spent"}
     cmd = [sys.executable, os.path.abspath(__file__), "--variant-probe", name, "--level", str(args.level), "--sh-degree", str(args.sh_degree),
            "--substeps", str(args.substeps)]
+    last_line = lambda text: ([l for l in (text or "").splitlines() if l.startswith("{") and l.endswith("}")] or [None])[-1]
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=limit,
                            env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
-        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-        res = json.loads(lines[-1]) if lines else {"probe": name}
-        if r.returncode != 0 or not lines:                          # keep what was measured before the failure
+        line = last_line(r.stdout)
+        res = json.loads(line) if line else {"probe": name}
+        if r.returncode != 0 or not line:                           # keep what was measured before the failure
             res["error"] = f"exit {r.returncode}: {(r.stderr or r.stdout)[-300:]}"
         return res
-    except Exception as e:                                           # timeout, spawn failure, bad JSON
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else e.stdout
+        try:
+            res = json.loads(last_line(out)) if last_line(out) else {"probe": name}
+        except Exception:
+            res = {"probe": name}
+        res["error"] = f"killed after {limit:.0f} s; the entries above had been measured by then"
+        return res
+    except Exception as e:                                           # spawn failure, bad JSON
         return {"probe": name, "error": repr(e)[:300]}
 
 
@@ -433,9 +453,9 @@ def run_ours(args) -> None:
     if variants is not None and not args.no_probes:
         # opt-in kernel selections that are not the default, each timed in its own process (not part of `value`)
         torch.cuda.synchronize()
-        variants["opt_in_selections"] = [run_probe("headline_selections", args), run_probe("nonlinear", args)]
-        variants["other_baseline_configs"] = run_probe("other_configs", args)
-        variants["e2e_pipelined"] = run_probe("e2e_pipelined", args)
+        variants["other_baseline_configs"] = run_probe("other_configs", args, 120.0)      # kernels that have run on B200s before
+        variants["e2e_pipelined"] = run_probe("e2e_pipelined", args, 120.0)
+        variants["opt_in_selections"] = [run_probe("nonlinear", args, 120.0), run_probe("headline_selections", args, 240.0)]
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
