@@ -21,8 +21,66 @@ __device__ __forceinline__ double ab3_increment(double f0, double f1, double f2,
 }
 
 // row r of an ELL operator times a scalar field read through `get(id)`: columns ascending, accumulator from 0 (Eigen's row-major product)
+// The loads are batched: all ids and weights of the row first, then all gathers, then the sum in slot order -- one DRAM round trip and
+// one gather round trip per row instead of one of each per slot (the per-slot loop kept every load behind the previous slot's branch).
+// Same products, same order of additions.
+// Table values (ids, weights: streamed once) are read with ld.volatile: neither nvcc nor ptxas may reorder volatile accesses among
+// themselves, so all of a row's table loads are issued back to back before the first gather has to wait for its id. (With plain loads
+// ptxas sinks each slot's loads next to their use to save registers -- 32 registers, and ten serial DRAM + gather round trips per edge.)
+// Gathers of field values stay ordinary cached loads.
+__device__ __forceinline__ int ldt(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldt(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldo(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldo(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldo_x(const double2* p) { return ldo(reinterpret_cast<const double*>(p)); }
+__device__ __forceinline__ double ldo_y(const double2* p) { return ldo(reinterpret_cast<const double*>(p) + 1); }
+
+template <int W, typename Get>
+__device__ __forceinline__ double ell_row_batched(const Ell& A, int r, Get get) {
+    int id[W];
+    double w[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        const bool in = k < A.width;
+        id[k] = in ? ldt(A.id + (size_t)k * A.stride + r) : -1;
+        w[k] = in ? ldt(A.w + (size_t)k * A.stride + r) : 0.0;
+    }
+    // z is 0 (ids are >= -1, so their AND is never 0x80000001), but only at run time: every gather address depends on every table
+    // value, so all table loads are issued before the first gather -- ptxas otherwise interleaves load, gather and arithmetic slot by slot
+    int all_ids = id[0], all_hi = __double2hiint(w[0]);
+#pragma unroll
+    for (int k = 1; k < W; k++) { all_ids &= id[k]; all_hi &= __double2hiint(w[k]); }
+    const int z = (int)(all_ids == (int)0x80000001) & (int)(all_hi == (int)0x80000001);
+    double x[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) x[k] = get((id[k] >= 0 ? id[k] : 0) + z);
+    double tmp = 0.0;
+#pragma unroll
+    for (int k = 0; k < W; k++)
+        if (id[k] >= 0) tmp += w[k] * x[k];
+    return tmp;
+}
 template <typename Get>
 __device__ __forceinline__ double ell_row(const Ell& A, int r, Get get) {
+    if (A.width <= 3) return ell_row_batched<3>(A, r, get);       // curl
+    if (A.width <= 6) return ell_row_batched<6>(A, r, get);       // RBF reconstruction
+    if (A.width <= 8) return ell_row_batched<8>(A, r, get);       // directional second derivative (<= 7)
     double tmp = 0.0;
     for (int k = 0; k < A.width; k++) {
         const int id = A.id[(size_t)k * A.stride + r];
@@ -35,7 +93,7 @@ __device__ __forceinline__ double ell_row(const Ell& A, int r, Get get) {
 __global__ void __launch_bounds__(kNlThreads) nl_vertex_kernel(NlTables t, Physics p, NlState s) {
     const int i = blockIdx.x * kNlThreads + threadIdx.x;
     if (i >= t.n_vertices) return;
-    const double zeta = ell_row(t.curl, i, [&](int e) { return s.vl_in[e].x; });
+    const double zeta = ell_row(t.curl, i, [&](int e) { return ldo_x(s.vl_in + e); });
     const double f = -2 * t.omega * t.vsin[i];
     double thickness = 0.0;
 #pragma unroll
@@ -62,7 +120,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_edge_prep_kernel(NlTables t, Ph
 __global__ void __launch_bounds__(kNlThreads) nl_cell_ekin_kernel(NlTables t, NlState s) {
     const int i = blockIdx.x * kNlThreads + threadIdx.x;
     if (i >= t.n_cells) return;
-    auto vel = [&](int e) { return s.vl_in[e].x; };
+    auto vel = [&](int e) { return ldo_x(s.vl_in + e); };
     const double x = ell_row(t.rbf[0], i, vel), y = ell_row(t.rbf[1], i, vel), z = ell_row(t.rbf[2], i, vel);
     s.ekin[i] = 0.5 * (x * x + y * y + z * z);
 }
@@ -78,12 +136,27 @@ __global__ void __launch_bounds__(kNlThreads) nl_edge_step_kernel(NlTables t, Ph
     double dv = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;                       // dvdt = -g G eta
     const double q_e = s.fq[e].y;
     double F_tang_q = 0.0;
+    int nf[kStencil];
+    double nc[kStencil];
+    double2 no[kStencil];
+#pragma unroll
+    for (int j = 0; j < kStencil; j++) {                                           // table values, then gathers, then the sum in slot order
+        nf[j] = ldt(t.nid + (size_t)j * t.estride + e);
+        nc[j] = ldt(t.ncoef + (size_t)j * t.estride + e);
+    }
+    // every gather address depends on every table value (z is 0: ids are >= -1 and never all 0x80000001 ... but only at run time), so
+    // the table loads have to be issued, all of them, before the first gather -- ptxas otherwise interleaves slot by slot
+    int all_ids = nf[0], all_hi = __double2hiint(nc[0]);
+#pragma unroll
+    for (int j = 1; j < kStencil; j++) { all_ids &= nf[j]; all_hi &= __double2hiint(nc[j]); }
+    const int z = (int)(all_ids == (int)0x80000001) & (int)(all_hi == (int)0x80000001);
+#pragma unroll
+    for (int j = 0; j < kStencil; j++) no[j] = ldo(s.fq + ((nf[j] >= 0 ? nf[j] : e) + z));   // {F_e', q_e'}
 #pragma unroll
     for (int j = 0; j < kStencil; j++) {
-        const int f = t.nid[(size_t)j * t.estride + e];
-        if (f >= 0) {
-            const double2 o = s.fq[f];                                            // {F_e', q_e'}
-            F_tang_q += t.ncoef[(size_t)j * t.estride + e] * o.x * (q_e + o.y) * 0.5;
+        if (nf[j] >= 0) {
+            const double2 o = no[j];
+            F_tang_q += nc[j] * o.x * (q_e + o.y) * 0.5;
         }
     }
     dv -= -F_tang_q;
@@ -101,7 +174,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_edge_step_kernel(NlTables t, Ph
 __global__ void __launch_bounds__(kNlThreads) nl_flux_kernel(NlTables t, Physics p, NlState s) {
     const int e = blockIdx.x * kNlThreads + threadIdx.x;
     if (e >= t.n_edges) return;
-    auto htot = [&](int i) { return p.h + s.eu_in[i].x; };
+    auto htot = [&](int i) { return p.h + ldo_x(s.eu_in + i); };
     const double d2_inner = ell_row(t.d2[0], e, htot), d2_outer = ell_row(t.d2[1], e, htot);
     const int2 c = t.cells[e];
     const double fact = 1. / 12.0, beta = 1.0;
@@ -118,14 +191,26 @@ __global__ void __launch_bounds__(kNlThreads) nl_cell_step_kernel(NlTables t, Ph
     double2 st = s.eu_in[i];
     const double area = t.area[i], ra = __drcp_rn(area);
     double div = 0.0;
+    int packed[kCellEdges];
+    double le[kCellEdges], fl[kCellEdges];
+#pragma unroll
+    for (int j = 0; j < kCellEdges; j++) packed[j] = ldt(t.eid + (size_t)j * t.cstride + i);
+    int all_and = packed[0], all_or = packed[0];
+#pragma unroll
+    for (int j = 1; j < kCellEdges; j++) { all_and &= packed[j]; all_or |= packed[j]; }
+    const int z = (int)(all_and < 0) & (int)(all_or >= 0);                         // never both (see ell_row_batched): 0, known at run time only
+#pragma unroll
+    for (int j = 0; j < kCellEdges; j++) {                                        // gathers together, arithmetic after
+        const int e = (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)) + z;
+        le[j] = ldo_y(s.vl_out + e);
+        fl[j] = ldo(s.flux + e);
+    }
 #pragma unroll
     for (int j = 0; j < kCellEdges; j++) {
-        const int packed = t.eid[(size_t)j * t.cstride + i];
-        if (packed != -1) {
-            const int e = packed & 0x7fffffff;
-            const double ndir = (packed < 0) ? 1.0 : -1.0;                        // -dir, mesh.cpp:3246
-            const double coeff = exact_div(ndir * s.vl_out[e].y, area, ra);
-            div += coeff * s.flux[e];
+        if (packed[j] != -1) {
+            const double ndir = (packed[j] < 0) ? 1.0 : -1.0;                     // -dir, mesh.cpp:3246
+            const double coeff = exact_div(ndir * le[j], area, ra);
+            div += coeff * fl[j];
         }
     }
     st.x += ab3_increment(div, s.ch1[i], s.ch2[i], p.dt, mode);
@@ -144,7 +229,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_vertex_ekin_kernel(NlTables t, 
     if ((int)blockIdx.x < vertex_blocks) {
         const int i = blockIdx.x * kNlThreads + threadIdx.x;
         if (i >= t.n_vertices) return;
-        const double zeta = ell_row(t.curl, i, [&](int e) { return s.vl_in[e].x; });
+        const double zeta = ell_row(t.curl, i, [&](int e) { return ldo_x(s.vl_in + e); });
         const double f = -2 * t.omega * t.vsin[i];
         double thickness = 0.0;
 #pragma unroll
@@ -158,7 +243,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_vertex_ekin_kernel(NlTables t, 
     } else {
         const int i = ((int)blockIdx.x - vertex_blocks) * kNlThreads + threadIdx.x;
         if (i >= t.n_cells) return;
-        auto vel = [&](int e) { return s.vl_in[e].x; };
+        auto vel = [&](int e) { return ldo_x(s.vl_in + e); };
         const double x = ell_row(t.rbf[0], i, vel), y = ell_row(t.rbf[1], i, vel), z = ell_row(t.rbf[2], i, vel);
         s.ekin[i] = 0.5 * (x * x + y * y + z * z);
     }
@@ -174,12 +259,27 @@ __global__ void __launch_bounds__(kNlThreads) nl_edge_step_flux_kernel(NlTables 
     double dv = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;
     const double q_e = s.fq[e].y;
     double F_tang_q = 0.0;
+    int nf[kStencil];
+    double nc[kStencil];
+    double2 no[kStencil];
+#pragma unroll
+    for (int j = 0; j < kStencil; j++) {                                           // table values, then gathers, then the sum in slot order
+        nf[j] = ldt(t.nid + (size_t)j * t.estride + e);
+        nc[j] = ldt(t.ncoef + (size_t)j * t.estride + e);
+    }
+    // every gather address depends on every table value (z is 0: ids are >= -1 and never all 0x80000001 ... but only at run time), so
+    // the table loads have to be issued, all of them, before the first gather -- ptxas otherwise interleaves slot by slot
+    int all_ids = nf[0], all_hi = __double2hiint(nc[0]);
+#pragma unroll
+    for (int j = 1; j < kStencil; j++) { all_ids &= nf[j]; all_hi &= __double2hiint(nc[j]); }
+    const int z = (int)(all_ids == (int)0x80000001) & (int)(all_hi == (int)0x80000001);
+#pragma unroll
+    for (int j = 0; j < kStencil; j++) no[j] = ldo(s.fq + ((nf[j] >= 0 ? nf[j] : e) + z));   // {F_e', q_e'}
 #pragma unroll
     for (int j = 0; j < kStencil; j++) {
-        const int f = t.nid[(size_t)j * t.estride + e];
-        if (f >= 0) {
-            const double2 o = s.fq[f];
-            F_tang_q += t.ncoef[(size_t)j * t.estride + e] * o.x * (q_e + o.y) * 0.5;
+        if (nf[j] >= 0) {
+            const double2 o = no[j];
+            F_tang_q += nc[j] * o.x * (q_e + o.y) * 0.5;
         }
     }
     dv -= -F_tang_q;
@@ -192,7 +292,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_edge_step_flux_kernel(NlTables 
     if (mode == AB3_SECOND) s.h1[e] = f0;
     else s.h2[e] = f0;
     // interpolateLSQFlux (interpolation.cpp:311-364) for this edge, with the velocity just computed
-    auto htot = [&](int i) { return p.h + s.eu_in[i].x; };
+    auto htot = [&](int i) { return p.h + ldo_x(s.eu_in + i); };
     const double d2_inner = ell_row(t.d2[0], e, htot), d2_outer = ell_row(t.d2[1], e, htot);
     const double fact = 1. / 12.0, beta = 1.0;
     const double dx = t.dist[e];

@@ -268,6 +268,7 @@ inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t st) {
 }
 
 // ---- device intrinsics ----
+inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, sizeof b); return (int)(b >> 32); }
 inline double __drcp_rn(double x) { return 1.0 / x; }                   // rcp.rn.f64 is correctly rounded, as IEEE division
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
