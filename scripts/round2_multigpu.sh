@@ -22,3 +22,8 @@ try:
 except Exception as e: print("no line", e)')" | tee -a $OUT/SUMMARY.txt
     done
 done
+# BASELINE config 5: 256-member sweep, 32 members per GPU (replicas only)
+PORT=$((PORT + 1))
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --master-addr 127.0.0.1 --master-port $PORT \
+    scripts/ensemble_multigpu.py 7 32 8 > $OUT/ensemble_n${NMAX}.log 2>&1
+echo "ensemble n=$NMAX exit $?: $(grep '^{' $OUT/ensemble_n${NMAX}.log | tail -1)" | tee -a $OUT/SUMMARY.txt
