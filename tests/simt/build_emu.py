@@ -157,7 +157,7 @@ def rewrite_asm(s: str) -> tuple[str, int]:
         elif ptx.startswith("cp.async.bulk.prefetch"):          # no data moves; touching both ends lets the address sanitizer check the range
             rep = f"{{ const volatile unsigned char* simt_p_ = (const volatile unsigned char*)({ins[0]}); (void)simt_p_[0]; (void)simt_p_[({ins[1]}) - 1]; }}"
         elif ptx.startswith("ld.acquire"):
-            rep = f"{outs[0]} = __atomic_load_n({ins[0]}, __ATOMIC_ACQUIRE);"
+            rep = f"{outs[0]} = (std::this_thread::yield(), __atomic_load_n({ins[0]}, __ATOMIC_ACQUIRE));"     # flag polls: let the other "devices" run
         elif ptx.startswith("ld.relaxed.sys"):
             rep = f"{outs[0]} = *(const volatile decltype({outs[0]})*)({ins[0]});"
         elif ptx.startswith("ld."):

@@ -535,7 +535,7 @@ inline void named_barrier(int id, int count) {
 inline void __syncthreads() { simt::yield(simt::AT_BARRIER); }
 inline void __syncwarp(unsigned = 0xffffffffu) { (void)simt::shuffle(0, simt::cta.current & 31); }       // the warp's live lanes meet here
 inline size_t __cvta_generic_to_shared(const void* p) { return simt::shared_address(p); }
-inline void __nanosleep(unsigned) {}
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) { const int lane = simt::cta.current & 31; return simt::shuffle(v, lane + delta < 32 ? lane + delta : lane); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask) { return simt::shuffle(v, (simt::cta.current & 31) ^ mask); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return simt::shuffle(v, src & 31); }
