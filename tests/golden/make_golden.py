@@ -165,6 +165,61 @@ def run_case(name: str, level: int, over: dict, nsteps: int, every_step_dumps: b
     print(f"{name}: level {level}, {nsteps} steps, totalIter {total}, dumps {len(slices)} -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def run_shipped_l6_checkpoints(name: str = "l6_shipped_verbatim", checkpoints=(10, 100, 1000, 2900)):
+    """BASELINE config 0 at its real size: /root/reference/input.in UNCHANGED except for the end time (1 orbit = 2,900 steps instead of
+    150 orbits) on the shipped grid_l6.txt (10,242 cells; advection true, velocity cartesian output true). One reference run per
+    checkpoint (the loop bound is the only thing that changes), FP64 state kept at each: v and eta everywhere, both AB3 histories at
+    step 1000. The grid itself is the one case_l6_obliqwest_earth.npz already holds, so it is not stored twice.
+    NOTE (found by running it): the reference's own solver DIVERGES on this configuration — its dissipation grows orbit-resonantly and
+    the state is NaN from some step between 1,160 and 1,450 on (its OUTPUT.txt prints "AVG DISS: -nan" from the 6th dump on). The
+    checkpoint at 2,900 therefore records non-finite arrays; the comparison there is "non-finite in the same entries"."""
+    level = 6
+    binary = os.path.join(ROOT, "oracle", "_ref", f"odis_ref_l{level}")
+    verbatim = []
+    for line in open("/root/reference/input.in"):
+        parts = [x.strip() for x in line.split(";")]
+        if len(parts) >= 2 and parts[0] == "simulation end time":
+            continue
+        verbatim.append(line)
+    out = {"level": np.array(level), "checkpoints": np.array(checkpoints), "grid_case": np.array("l6_obliqwest_earth")}
+    total = None
+    for n in checkpoints:
+        with tempfile.TemporaryDirectory() as d:
+            os.makedirs(d + "/input_files"); os.makedirs(d + "/DATA")
+            os.symlink(f"{REF_GRIDS}/grid_l{level}.txt", f"{d}/input_files/grid_l{level}.txt")
+            if total is None:
+                open(d + "/input.in", "w").write("".join(verbatim) + "simulation end time; 0; endTime;\n")
+                subprocess.run([binary, "--no-run"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                tab = read_records(d + "/DATA/ref_tables.bin")
+                total = int(tab["totalIter"][0])
+                for s in SCALARS:
+                    out["scalar_" + s] = tab[s]
+                for t in TABLES + NL_TABLES:
+                    out["sha256_" + t] = np.array(digest(tab[t]))
+            end = "1" if n == total else repr((n - 0.5) / total)
+            text = "".join(verbatim) + f"simulation end time; {end}; endTime;\n"
+            open(d + "/input.in", "w").write(text)
+            subprocess.run([binary, "--quiet-restart"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            fin = read_records(d + "/DATA/ref_final.bin")
+            out[f"step{n}_v"], out[f"step{n}_eta"] = fin["v"], fin["eta"]
+            if n == 1000:
+                out[f"step{n}_dvdt"], out[f"step{n}_detadt"] = fin["dvdt"], fin["detadt"]
+            if n == total:             # the whole orbit as ./ODIS would run it: progress lines and the dissipation row of data.h5
+                out["input_in"] = np.array(text)
+                out["output_txt"] = np.array(open(d + "/DATA/OUTPUT.txt").read())
+                dumps = read_records(d + "/DATA/ref_dumps.bin")
+                diss = [(int(k.split(":")[0]), v[0]) for k, v in dumps.items() if k.split(":")[1] == "dissipation avg output"]
+                out["dump_slices"] = np.array([s for s, _ in diss])
+                out["dump_dissipation_avg"] = np.array([v for _, v in diss])
+                eta_d = [v for k, v in dumps.items() if k.split(":")[1] == "displacement output"]
+                out["dump_displacement_first5"] = np.array(eta_d[:5])          # steps 0, 290, 580, 870, 1160: all finite
+    out["nsteps"] = np.array(total)
+    path = os.path.join(HERE, f"case_{name}.npz")
+    np.savez_compressed(path, **out)
+    finite = {n: bool(np.isfinite(out[f"step{n}_v"]).all() and np.isfinite(out[f"step{n}_eta"]).all()) for n in checkpoints}
+    print(f"{name}: level {level}, totalIter {total}, checkpoints finite: {finite} -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def random_state(level: int, seed: int):
     n = 10 * 4 ** (level - 1) + 2
     f = 3 * n - 6
@@ -236,6 +291,9 @@ if __name__ == "__main__":
     run_case("l5_advection_ecc", 5, {"advection": "true", "potential": "ECC", "time step": "20", "ocean thickness": "1e3", "eccentricity": "0.05",
                                      "friction type": "QUADRATIC", "friction coefficient": "1e-3"}, 60, every_step_dumps=False, full_tables=False,
              init_state=random_state(5, 31), nl_tables=True)
+    # (15) BASELINE config 0 at its real size: the shipped input.in on the shipped L6 grid, FP64 checkpoints at steps 10 / 100 / 1000 / 2900
+    if not only or "l6_shipped_verbatim" in only:
+        run_shipped_l6_checkpoints()
     # (7) no forcing, decaying loaded state on L5
     run_case("l5_none_loaded", 5, {"potential": "NONE", "time step": "20"}, 30, every_step_dumps=False, full_tables=False,
              init_state=random_state(5, 5))
