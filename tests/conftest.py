@@ -18,9 +18,7 @@ def pytest_configure(config):
 # Test files whose kernels / engine paths have not run on a B200 yet go last, the ones that could take the process with them (new
 # mbarrier / peer-flag code: a wait that never ends is cut by pytest.ini's timeout, which exits the process) at the very end, so that a
 # `-x` run on the GPU box reports everything that was validated before before it reaches them. Emptied once they have passed on hardware.
-NOT_YET_ON_HARDWARE = ["test_surface_analytical_gpu", "test_surface_sigint_gpu", "test_surface_ops_gpu", "test_surface_planet_gpu",
-                       "test_surface_hybrid_gpu", "test_variant_blocks_gpu", "test_variant_overlap_gpu", "test_variant_nl4_gpu",
-                       "test_variant_prefetch_gpu", "test_variant_sg3_gpu", "test_variant_ids16_gpu"]
+NOT_YET_ON_HARDWARE = []      # all of round 1's files passed on the driver's B200 (GPUTEST_r01.json)
 
 
 def pytest_collection_modifyitems(session, config, items):
