@@ -118,18 +118,41 @@ def measured_peak() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch() -> float | None:
-    """dram bytes per edge_step launch from the committed ncu summary, if one exists."""
+def ncu_traffic_per_launch(kernel: str) -> float | None:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at 655,362 cells on one GPU, from the committed
+    `ncu --set full` summary (profiles/edge_step_summary.json: one entry per kernel name), if one exists."""
     p = os.path.join(ROOT, "profiles", "edge_step_summary.json")
     try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
+        d = json.load(open(p))
+        return float(d["kernels"][kernel]["dram_bytes_per_launch"])
     except Exception:
         return None
 
 
-def cpu_baseline_port(mesh, prm: dict, budget_s: float = 15.0, sh_degree: int = 0) -> dict:
-    """The oracle's plain-C restatement of the reference loop (bit-identical to the reference solver, see
-    tests/test_oracle_pinned.py) timed on one host core on a bounded sample of the same workload."""
+def sg_alg_bytes(N: int, L: int) -> int:
+    """Matrix-free self-gravity term: 4 basis inputs per cell for the analysis (folded into the cell update for L <= 4) + 4 basis
+    inputs and {eta,U} read + written by the synthesis."""
+    return 0 if L < 2 else (32 + 64) * N
+
+
+def workload_config(N: int, F: int, level: int, L: int, S: int, dt: float, world: int, kernel_select: int = 0) -> dict:
+    """The `config` of a bench line; both arms build it from the same inputs so that the driver sees one configuration."""
+    alg = 200 * F + 128 * N + sg_alg_bytes(N, L)
+    return {"workload": f"Enceladus subsurface ocean (LID_LOVE, 23 km shell), ECC tide, linear drag, {N} cells / {F} edges "
+                        f"(reference file level {level} = BASELINE 'L{level - 1}'); "
+                        + (f"self-gravity / shell-pressure term by spherical harmonics to degree {L} (least-squares analysis + synthesis every step; "
+                           f"factors 1 - beta_l of the reference's 23 km Enceladus table)" if L >= 2 else "no self-gravity term"),
+            "sh_degree": L, "kernel_select": kernel_select, "cells": N, "edges": F, "lte_steps_per_bench_step": S, "dt_s": dt,
+            "cache": f"inputs larger than L2: {alg / 1e6:.0f} MB algorithmic bytes streamed per LTE step ({alg / world / 1e6:.0f} MB per GPU) vs 126 MB L2; "
+                     "no flush between steps" + ("" if alg / world > 126e6 else " (per-GPU share below the L2 size: the tables may stay resident, stated)"),
+            "parallelism": "1 GPU" if world == 1 else
+            f"{world} GPUs, the one grid cut into {world} space-filling-curve parts, one-ring halo, one exchange per step (boundary-edge "
+            f"velocities pushed by the edge kernel itself as NVLink peer stores; ghost cells updated locally; harmonic sums all-reduced through peer memory)"}
+
+
+def oracle_run(mesh, prm: dict, sh_degree: int, nsteps: int, budget_s: float | None = None):
+    """The oracle's plain-C restatement of the reference loop (bit-identical to the reference solver, tests/test_oracle_pinned.py) from
+    the zero state: returns (oracle, steps taken, seconds). budget_s: size the run to about that much CPU time instead of nsteps."""
     from oracle.lte_oracle import LteOracle
     keys = ("g", "h", "alpha", "dt", "radius", "omega", "love_reduct", "ecc", "obl", "shell_thickness", "potential", "friction", "surface", "init_load")
     o = LteOracle(mesh.tables, {k: prm[k] for k in keys})
@@ -138,17 +161,107 @@ def cpu_baseline_port(mesh, prm: dict, budget_s: float = 15.0, sh_degree: int = 
         Y = sh_oracle.basis(mesh.tables["node_pos_sph"], sh_degree)
         o.set_self_gravity(Y, sh_oracle.apply_operator(Y, shell_factor(sh_degree)))
     o.set_state()
-    t0 = time.perf_counter(); o.step(3); probe = (time.perf_counter() - t0) / 3
-    n = int(max(5, min(2000, budget_s / max(probe, 1e-9))))
-    t0 = time.perf_counter(); o.step(n); el = time.perf_counter() - t0
-    return {"value": n / el, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n} LTE steps of the same {mesh.n_cells}-cell workload"
+    done, el = 0, 0.0
+    if budget_s is not None:
+        t0 = time.perf_counter(); o.step(3); probe = (time.perf_counter() - t0) / 3
+        done, el = 3, probe * 3
+        nsteps = int(max(5, min(2000, budget_s / max(probe, 1e-9)))) - 3
+    t0 = time.perf_counter(); o.step(nsteps); el += time.perf_counter() - t0
+    return o, done + nsteps, el
+
+
+def cpu_baseline_and_parity(odis, mesh, prm: dict, sh_degree: int, device: int, budget_s: float = 15.0) -> tuple[dict, dict]:
+    """cpu_baseline: the oracle timed on one host core on a bounded sample of the headline workload. parity: the SAME oracle runs are
+    kept and compared with the CUDA path after the same number of steps from the same (zero) state — with the self-gravity term
+    (tolerance 1e-10: the term has no reference arithmetic to follow) and without it (bit equality required)."""
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    o, n, el = oracle_run(mesh, prm, sh_degree, 0, budget_s)
+    base = {"value": n / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} LTE steps of the same {mesh.n_cells}-cell workload from the zero state"
                       + (f" (self-gravity term to degree {sh_degree} included)" if sh_degree >= 2 else "") + ", oracle/lte_oracle.c (gcc -O2), single thread"}
+    parity = {"oracle": "oracle/lte_oracle.c, pinned bit for bit to the reference's own solver (tests/test_oracle_pinned.py)", "tolerance_rel": 1e-10}
+
+    def compare(oracle, nsteps, degree):
+        sv = odis.Solver(mesh, prm, device=device)
+        if degree >= 2:
+            sv.enable_self_gravity(degree, shell_factor(degree))
+        sv.step(nsteps)
+        v, eta = sv.field(odis.FIELD_VELOCITY), sv.field(odis.FIELD_ETA)
+        ov, oe = oracle.field(0), oracle.field(1)
+        out = {"steps": nsteps, "max_rel_eta": rel(eta, oe), "max_rel_v": rel(v, ov),
+               "bit_identical": bool(np.array_equal(v, ov) and np.array_equal(eta, oe)),
+               "within_tolerance": bool(rel(eta, oe) <= 1e-10 and rel(v, ov) <= 1e-10)}
+        sv.close()
+        return out
+
+    if sh_degree >= 2:
+        parity["with_self_gravity_term"] = compare(o, n, sh_degree)
+        o2, n2, _ = oracle_run(mesh, prm, 0, 40)
+        parity["without_self_gravity_term"] = compare(o2, n2, 0)
+    else:
+        parity["without_self_gravity_term"] = compare(o, n, 0)
+    parity["ok"] = bool(parity["without_self_gravity_term"]["bit_identical"] and
+                        parity.get("with_self_gravity_term", {"within_tolerance": True})["within_tolerance"])
+    return base, parity
+
+
+def e2e_pipelined(odis, sv, mesh, S: int, Ke: int, pin) -> dict:
+    """One output interval end to end through the C ABI with page-locked HOST buffers, copies overlapped with stepping:
+    odis_stage_state / odis_commit_state bring interval k+1's state in (H2D on the second stream) while interval k steps,
+    odis_snapshot_begin / _wait take interval k's eta / v / dissipation out while interval k+1 steps. Same bytes per interval as the
+    synchronous calls, whose result for the last interval is the check."""
+    import torch
+    N, F = mesh.n_cells, mesh.n_edges
+    h_v, h_eta = pin(sv.field(odis.FIELD_VELOCITY)), pin(sv.field(odis.FIELD_ETA))
+    h_dv, h_de = pin(sv.field(odis.FIELD_DVDT).ravel()), pin(sv.field(odis.FIELD_DETADT).ravel())
+    it0, fields = sv.iter, sv.SNAP_ETA | sv.SNAP_VELOCITY
+
+    def run(n):
+        check = 0.0
+        sv.stage_state(h_v, h_eta, h_dv, h_de)
+        for k in range(n):
+            sv.commit_state(iter=it0 + k * S)
+            if k + 1 < n:
+                sv.stage_state(h_v, h_eta, h_dv, h_de)
+            sv.step(S)
+            sv.snapshot_begin(k & 1, fields)
+            if k > 0:
+                check += sv.snapshot_wait((k - 1) & 1, copy=False)["dissipation_avg"]
+        last = sv.snapshot_wait((n - 1) & 1, copy=False)
+        sv.synchronize()
+        return check + last["dissipation_avg"], last
+
+    run(2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, last = run(Ke)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    # the same interval with the synchronous calls: the comparison value and the check of the pipelined result
+    def sync_interval(k):
+        sv.set_state(h_v, h_eta, h_dv, h_de, iter=it0 + k * S)
+        sv.step(S)
+        e = sv.field(odis.FIELD_ETA)
+        v = sv.field(odis.FIELD_VELOCITY)
+        sv.dissipation_avg()
+        return e, v
+    sync_interval(0)
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        e, v = sync_interval(Ke - 1)
+    torch.cuda.synchronize()
+    el_sync = time.perf_counter() - t0
+    same = bool(np.array_equal(e, last["eta"]) and np.array_equal(v, last["velocity"]))
+    return {"value": round(Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * (4 * F + 4 * N), "d2h_bytes_per_step": 8 * (F + N + 1),
+            "intervals_timed": Ke,
+            "path": "odis_stage_state / odis_commit_state (H2D of the next interval's state on a second stream) + odis_step + odis_snapshot_begin / "
+                    "_wait (D2H of eta, v, dissipation while the next interval steps); pipeline fill (the first, unoverlapped upload) inside the timed region",
+            "synchronous_calls_value": round(Ke * S / el_sync, 2), "fields_identical_to_synchronous_calls": same}
 
 
 def variant_probe(args) -> None:
-    """Child process of the N = 1 bench (own CUDA context, so a fault in an opt-in kernel selection cannot take the headline
-    measurement with it): times one selection and checks it against the default selection; prints one JSON line."""
+    """Child process of the N = 1 bench (own CUDA context and host memory, so nothing here can disturb the headline measurement):
+    prints one JSON line."""
     import geodesicodis_b200 as odis
     name = args.variant_probe
     out = {"probe": name}
@@ -157,11 +270,7 @@ def variant_probe(args) -> None:
         mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
         prm, L, S = workload_params(mesh), max(args.sh_degree, 2), args.substeps
         ref_eta = None
-        # selections that reuse validated synchronisation first; the new mbarrier byte accounting (16-bit ids) last
-        for key, sel in (("default", 0), ("cell_update_64_registers", 64), ("cell_update_l2_prefetch", 512),
-                         ("cell_update_l2_prefetch_64_registers", 576), ("self_gravity_3_launch", 16), ("self_gravity_3_launch_64_registers", 80),
-                         ("self_gravity_3_launch_cell_l2_prefetch", 16 + 512), ("edge_ids_16bit", 128), ("edge_ids_16bit_cell_l2_prefetch", 640),
-                         ("self_gravity_3_launch_edge_ids_16bit_cell_l2_prefetch", 16 + 128 + 512)):
+        for key, sel in (("default", 0), ("stencil_ids_32bit_only", 128), ("direct_load_baseline_kernels_5_launches", 1)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_self_gravity(L, shell_factor(L))
             sv.step(2 * S)
@@ -177,52 +286,6 @@ def variant_probe(args) -> None:
             out[key] = rec
             print(json.dumps(out), flush=True)                   # the parent reads the last complete line
             sv.close()
-    elif name == "e2e_pipelined":
-        # the e2e interval of the main line (state H2D, S steps, eta / v / dissipation D2H, all through the C ABI with page-locked host
-        # buffers) with the copies on the second stream: odis_stage_state / odis_commit_state bring interval k+1's state in while
-        # interval k steps, odis_snapshot_begin / _wait take interval k's fields out while interval k+1 steps. Same bytes per interval.
-        import torch
-        pos, fr, cen = odis.generate_grid(args.level)
-        mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
-        prm, L, S = workload_params(mesh), args.sh_degree, args.substeps
-        N, F = mesh.n_cells, mesh.n_edges
-        sv = odis.Solver(mesh, prm)
-        if L >= 2:
-            sv.enable_self_gravity(L, shell_factor(L))
-        sv.step(2 * S)
-        def pin(a):
-            a = np.ascontiguousarray(a, dtype=np.float64)
-            return torch.from_numpy(a).pin_memory().numpy() if torch.cuda.is_available() else a      # (no CUDA: the emulated library in tests)
-        h_v, h_eta = pin(sv.field(odis.FIELD_VELOCITY)), pin(sv.field(odis.FIELD_ETA))
-        h_dv, h_de = pin(sv.field(odis.FIELD_DVDT).ravel()), pin(sv.field(odis.FIELD_DETADT).ravel())
-        it0, Ke, fields = sv.iter, 20, sv.SNAP_ETA | sv.SNAP_VELOCITY
-
-        def run(n):
-            check = 0.0
-            sv.stage_state(h_v, h_eta, h_dv, h_de)
-            for k in range(n):
-                sv.commit_state(iter=it0 + k * S)
-                if k + 1 < n:
-                    sv.stage_state(h_v, h_eta, h_dv, h_de)
-                sv.step(S)
-                sv.snapshot_begin(k & 1, fields)
-                if k > 0:
-                    check += sv.snapshot_wait((k - 1) & 1, copy=False)["dissipation_avg"]
-            last = sv.snapshot_wait((n - 1) & 1, copy=False)
-            sv.synchronize()
-            return check + last["dissipation_avg"], last
-
-        run(2)
-        t0 = time.perf_counter()
-        _, last = run(Ke)
-        el = time.perf_counter() - t0
-        # the same interval, synchronous calls, for the comparison and as the check of the pipelined result
-        sv.set_state(h_v, h_eta, h_dv, h_de, iter=it0 + (Ke - 1) * S)
-        sv.step(S)
-        same = bool(np.array_equal(sv.field(odis.FIELD_ETA), last["eta"]) and np.array_equal(sv.field(odis.FIELD_VELOCITY), last["velocity"]))
-        out.update({"value": round(Ke * S / el, 2), "unit": UNIT, "intervals_timed": Ke, "h2d_bytes_per_step": 8 * (4 * F + 4 * N),
-                    "d2h_bytes_per_step": 8 * (F + N + 1), "fields_identical_to_synchronous_calls": same,
-                    "note": "pipeline fill (the first, unoverlapped upload) is inside the timed region"})
     elif name == "nonlinear":
         level = args.probe_level                                 # 8: 163,842 cells (BASELINE 'L7'), the shipped input.in physics
         pos, fr, cen = odis.generate_grid(level)
@@ -233,7 +296,7 @@ def variant_probe(args) -> None:
         prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.2 * dmin / math.sqrt(9.80616 * 8e3), radius=r, omega=7.292e-5, love_reduct=1.0, ecc=0.01,
                    obl=math.radians(-2.0), shell_thickness=0.0, semimajor_axis=0.0, potential=1, friction=0, surface=0, init_load=0, reorder=1)
         res = {}
-        for key, sel in (("6_launch_default", 0), ("4_launch", 32)):
+        for key, sel in (("4_launch_default", 0), ("6_launch_baseline", 1)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_advection(nl)
             sv.step(60)
@@ -241,11 +304,28 @@ def variant_probe(args) -> None:
             out[key + "_timesteps_per_s"] = round(400 / (sv.step_timed(400) * 1e-3), 1)
             sv.close()
         out["cells"] = mesh.n_cells
-        out["fields_identical"] = bool(np.array_equal(res["6_launch_default"], res["4_launch"]))
+        out["fields_identical"] = bool(np.array_equal(res["4_launch_default"], res["6_launch_baseline"]))
+    elif name == "synthetic_l10_1gpu":
+        # BASELINE config 4's grid on ONE GPU (the N = 1 point of the 10,485,762-cell scaling curve): free-surface LTE, ECC, linear drag
+        t0 = time.time()
+        pos, fr, cen = odis.generate_grid(11)
+        mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"])
+        del pos, fr, cen
+        prm = dict(workload_params(mesh), surface=0, shell_thickness=0.0, love_reduct=1.0)
+        sv = odis.Solver(mesh, prm)
+        sv.step(24)
+        ms = sv.step_timed(200)
+        _, alg = sv.footprint()
+        peak, _ = measured_peak()
+        out.update({"cells": mesh.n_cells, "timesteps_per_s": round(200 / (ms * 1e-3), 2), "steps_timed": 200, "n_gpus": 1,
+                    "cell_updates_per_s": round(mesh.n_cells * 200 / (ms * 1e-3), 1), "algorithmic_GBps": round(alg * 200 / (ms * 1e-3) / 1e9, 1),
+                    "frac_of_measured_hbm_peak": round(alg * 200 / (ms * 1e-3) / 1e9 / peak, 4), "finite": bool(math.isfinite(sv.dissipation_avg())),
+                    "setup_s": round(time.time() - t0, 1)})
+        sv.close()
     elif name == "other_configs":
-        # the remaining single-GPU shapes of BASELINE.json's configs, each a short device-resident timing (kernels that have run on B200s
-        # before): [1] Enceladus free-surface ocean, 163,842 cells, linear drag, no self-gravity; [4] one GPU's share of the ensemble
-        # sweep: 32 members (ocean thickness x drag) on 40,962 cells, self-gravity to degree 8 as batched FP64 tensor-core GEMMs
+        # the remaining single-GPU shapes of BASELINE.json's configs, each a short device-resident timing: [1] Enceladus free-surface
+        # ocean, 163,842 cells, linear drag, no self-gravity; [4] one GPU's share of the ensemble sweep: 32 members (ocean thickness x drag)
+        # on 40,962 cells, self-gravity to degree 8 as batched FP64 tensor-core GEMMs
         pos, fr, cen = odis.generate_grid(args.probe_level)
         mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"])
         prm = dict(workload_params(mesh), surface=0, shell_thickness=0.0, love_reduct=1.0)
@@ -266,21 +346,23 @@ def variant_probe(args) -> None:
         ens.step(40)
         ms = ens.step_timed(400) / 400
         info = ens.info()
+        peak, _ = measured_peak()
         out["ensemble_32_members_%d_cells_sh8" % mesh.n_cells] = {"batched_steps_per_s": round(1e3 / ms, 1), "member_steps_per_s": round(M * 1e3 / ms, 1),
-                                                      "algorithmic_GBps": round(info["algorithmic_bytes_per_step"] / (ms * 1e-3) / 1e9, 1)}
+                                                      "algorithmic_GBps": round(info["algorithmic_bytes_per_step"] / (ms * 1e-3) / 1e9, 1),
+                                                      "frac_of_measured_hbm_peak": round(info["algorithmic_bytes_per_step"] / (ms * 1e-3) / 1e9 / peak, 4)}
         ens.close()
     else:
         out["error"] = "unknown probe"
     print(json.dumps(out), flush=True)
 
 
-PROBE_BUDGET_S = 420.0          # all child-process probes of one bench run together (each also has its own limit)
+PROBE_BUDGET_S = 520.0          # all child-process probes of one bench run together (each also has its own limit)
 _probe_deadline = [None]
 
 
 def run_probe(name: str, args, limit: float = 180.0) -> dict:
     """Runs `bench.py --variant-probe name` in a subprocess; any failure is recorded instead of raised. A probe that does not return
-    (a kernel selection that has never run on this hardware) is killed at its limit and what it had printed until then is kept."""
+    is killed at its limit and what it had printed until then is kept."""
     if _probe_deadline[0] is None:
         _probe_deadline[0] = time.time() + PROBE_BUDGET_S
     limit = min(limit, _probe_deadline[0] - time.time())
@@ -330,40 +412,86 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op="max") -> float:
         if dist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op])
         return float(t.item())
 
+    def connect(solver):                            # every rank publishes its halo buffers; neighbours map them
+        if world > 1:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, solver.halo_blob())
+            solver.halo_connect(blobs)
+            dist.barrier()
+
+    def whole(solver, field):                       # a partitioned solver returns its own entries, zeros elsewhere
+        a = solver.field(field)
+        if dist is not None:
+            t = torch.from_numpy(a).cuda()
+            dist.all_reduce(t)
+            a = t.cpu().numpy()
+        return a
+
+    def timed_steps(solver, n):                     # CUDA events on the solver's own stream, max over ranks
+        barrier()
+        ms = solver.step_timed(n)
+        torch.cuda.synchronize()
+        barrier()
+        return reduce_ranks(ms)
+
     radius = ENCELADUS["radius"] - ENCELADUS["shell"]                 # LID_LOVE: boundaryConditions.cpp:126
-    if world > 1 and args.level >= 10:
-        # large grids: the node's first rank builds the tables once, the others map them (np.load mmap) from /dev/shm
-        shared = f"/dev/shm/odis_b200_mesh_l{args.level}_{os.environ.get('MASTER_PORT', '0')}"
-        if local_rank == 0:
-            pos, fr, cen = odis.generate_grid(args.level)
-            odis.Mesh.from_arrays(pos, fr, cen, radius).save(shared)
-            del pos, fr, cen
-        dist.barrier()
-        mesh = odis.Mesh.load(shared)
-    else:
-        pos, fr, cen = odis.generate_grid(args.level)
-        mesh = odis.Mesh.from_arrays(pos, fr, cen, radius)
+    pos, fr, cen = odis.generate_grid(args.level)
+    mesh = odis.Mesh.from_arrays(pos, fr, cen, radius)
     prm = workload_params(mesh)
     if args.kernel_select:                          # experiments only (odis_params.reserved[0]); the default line is selection 0
         prm = dict(prm, kernel_select=args.kernel_select)
-    solver = odis.Solver(mesh, prm, device=local_rank, rank=rank, world=world)
-    if world > 1:                                   # every rank publishes its halo buffers; neighbours map them
-        blobs = [None] * world
-        dist.all_gather_object(blobs, solver.halo_blob())
-        solver.halo_connect(blobs)
-        dist.barrier()
     L = args.sh_degree
-    if L >= 2:                                      # self-gravity / shell-pressure term (BASELINE config 3), matrix-free kernels
-        solver.enable_self_gravity(L, shell_factor(L))
     N, F = mesh.n_cells, mesh.n_edges
     S, K, W = args.substeps, args.steps, max(args.warmup, 3)
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+    # ---- N > 1: the partitioned run against the single-GPU solver, same steps from the same state (rank 0 holds the single one) -------
+    parity_multi = None
+    value_no_sg = None
+    if world > 1:
+        P = 60
+        parity_multi = {"steps": P, "tolerance_rel": 1e-10}
+        for key, deg in (("without_self_gravity_term", 0), ("with_self_gravity_term", L)):
+            if key == "with_self_gravity_term" and L < 2:
+                continue
+            part_solver = odis.Solver(mesh, prm, device=local_rank, rank=rank, world=world)
+            connect(part_solver)
+            if deg >= 2:
+                part_solver.enable_self_gravity(deg, shell_factor(deg))
+            part_solver.step(P)
+            v, eta = whole(part_solver, odis.FIELD_VELOCITY), whole(part_solver, odis.FIELD_ETA)
+            if rank == 0:
+                single = odis.Solver(mesh, prm, device=local_rank)
+                if deg >= 2:
+                    single.enable_self_gravity(deg, shell_factor(deg))
+                single.step(P)
+                sv_, se_ = single.field(odis.FIELD_VELOCITY), single.field(odis.FIELD_ETA)
+                single.close()
+                parity_multi[key] = {"max_rel_eta": rel(eta, se_), "max_rel_v": rel(v, sv_),
+                                     "bit_identical": bool(np.array_equal(v, sv_) and np.array_equal(eta, se_)),
+                                     "within_tolerance": bool(rel(eta, se_) <= 1e-10 and rel(v, sv_) <= 1e-10)}
+            if deg == 0:                            # the same run without the term, timed: comparable with the reference arm (which has no term)
+                for _ in range(W):
+                    part_solver.step(S)
+                value_no_sg = round(K * S / (timed_steps(part_solver, K * S) * 1e-3), 2)
+            part_solver.synchronize()
+            barrier()
+            part_solver.close()
+        if rank == 0:
+            parity_multi["ok"] = bool(parity_multi["without_self_gravity_term"]["bit_identical"] and
+                                      parity_multi.get("with_self_gravity_term", {"within_tolerance": True})["within_tolerance"])
+
+    solver = odis.Solver(mesh, prm, device=local_rank, rank=rank, world=world)
+    connect(solver)
+    if L >= 2:                                      # self-gravity / shell-pressure term (BASELINE config 3), matrix-free kernels
+        solver.enable_self_gravity(L, shell_factor(L))
     dev_bytes, alg_bytes = solver.footprint()
 
     # ---- device-resident throughput -------------------------------------------------------------
@@ -381,7 +509,7 @@ def run_ours(args) -> None:
     if not math.isfinite(solver.dissipation_avg()):
         raise SystemExit("bench.py: the run blew up (non-finite dissipation); the timing would be meaningless")
     barrier()
-    ms = max_over_ranks(ms)
+    ms = reduce_ranks(ms)
     value = K * S / (ms * 1e-3)                  # all ranks advance the same K*S steps of the one global grid
 
     # ---- per-kernel timing for the roofline (live, CUDA events around every launch) --------------
@@ -390,54 +518,70 @@ def run_ours(args) -> None:
     edge_us, cell_us, sh_us = edge_ms / nprof * 1e3, cell_ms / nprof * 1e3, sh_ms / nprof * 1e3
     peak, peak_src = measured_peak()
     part = solver.partition()
-    edge_alg = 200 * part["own_edges"]          # per-edge algorithmic bytes x edges per launch (this rank's)
+    narrow = (args.kernel_select & (1 | 128)) == 0
+    edge_bytes = (180 if narrow else 200)       # 16-bit stencil ids stream 20 B per edge instead of 40
+    edge_alg = edge_bytes * part["own_edges"]   # per-edge algorithmic bytes x edges per launch (this rank's)
+    edge_kernel = "edge_step_kernel" if (args.kernel_select & 1) else ("edge_step_pipe16_kernel" if narrow else "edge_step_pipe_kernel")
     achieved = edge_alg / (edge_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "edge_step_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+    fused_sg = L >= 2 and L <= 4 and not (args.kernel_select & 1)
+    cell_alg = (128 + (32 if fused_sg else 0)) * part["own_cells"]
+    roofline = {"bound": "hbm", "kernel": edge_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic_per_launch(edge_kernel) if world == 1 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": edge_alg, "avg_launch_us": round(edge_us, 2),
-                "cell_step_kernel": {"algorithmic_bytes_per_launch": 128 * part["own_cells"], "avg_launch_us": round(cell_us, 2),
-                                     "achieved": round(128 * part["own_cells"] / (cell_us * 1e-6) / 1e9, 1)},
-                "self_gravity_kernels": {"avg_us_per_step": round(sh_us, 2), "launches_per_step": 3 if L >= 2 else 0, "bound": "fp64 pipe (matrix-free: "
-                                         "the harmonic basis is rebuilt per cell by recurrence instead of streaming 8*(l_max+1)^2 B per cell)"},
+                "algorithmic_bytes_per_edge": edge_bytes,
+                "cell_step_kernel": {"kernel": "cell_step_kernel" if (args.kernel_select & 1) else "cell_step_pipe_kernel",
+                                     "algorithmic_bytes_per_launch": cell_alg, "avg_launch_us": round(cell_us, 2),
+                                     "achieved": round(cell_alg / (cell_us * 1e-6) / 1e9, 1), "frac": round(cell_alg / (cell_us * 1e-6) / 1e9 / peak, 4),
+                                     "note": "with the self-gravity term to degree <= 4 the harmonic analysis is accumulated inside this launch (+32 B per cell)"},
+                "self_gravity_kernels": {"avg_us_per_step": round(sh_us, 2), "launches_per_step": (1 if fused_sg else 3) if L >= 2 else 0,
+                                         "algorithmic_bytes_per_step": 64 * part["own_cells"] if L >= 2 else 0,
+                                         "note": "matrix-free: the harmonic basis is rebuilt per cell by recurrence instead of streaming 8*(l_max+1)^2 B per cell"},
                 "whole_step": {"algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes * value / 1e9, 1),
                                "frac": round(alg_bytes * value / 1e9 / peak, 4), "frac_of_8TBs_nominal": round(alg_bytes * value / 8e12, 4),
+                               "survey_b_alg_bytes": 200 * part["own_edges"] + 128 * part["own_cells"],
+                               "frac_on_survey_b_alg": round((200 * part["own_edges"] + 128 * part["own_cells"]) * value / 1e9 / peak, 4),
                                "note": "per GPU: this rank's share of the grid; for N>1 the halo exchange is part of the two kernels"}}
+    if world > 1:
+        roofline["traffic_note"] = "no ncu capture of a partitioned rank (ncu is single-GPU here); the N = 1 line carries the measured DRAM bytes"
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
-    pin = lambda n: torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
-    h_v, h_eta, h_dv, h_de = pin(F), pin(N), pin(3 * F), pin(3 * N)
-    def whole(field):                            # a partitioned solver returns its own entries, zeros elsewhere
-        a = solver.field(field)
-        if dist is not None:
-            t = torch.from_numpy(a).cuda()
-            dist.all_reduce(t)
-            a = t.cpu().numpy()
-        return a
-
-    h_v[:] = whole(odis.FIELD_VELOCITY); h_eta[:] = whole(odis.FIELD_ETA)
-    h_dv[:] = whole(odis.FIELD_DVDT).ravel(); h_de[:] = whole(odis.FIELD_DETADT).ravel()
-    it0 = solver.iter
+    def pin(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return torch.from_numpy(a).pin_memory().numpy()
     Ke = max(1, min(K, 20))
+    if world == 1:
+        e2e = e2e_pipelined(odis, solver, mesh, S, Ke, pin)
+    else:
+        h_v, h_eta = pin(whole(solver, odis.FIELD_VELOCITY)), pin(whole(solver, odis.FIELD_ETA))
+        h_dv, h_de = pin(whole(solver, odis.FIELD_DVDT).ravel()), pin(whole(solver, odis.FIELD_DETADT).ravel())
+        it0 = solver.iter
 
-    def e2e_interval(k: int):
-        solver.set_state(h_v, h_eta, h_dv, h_de, iter=it0 + k * S)          # H2D of the interval's inputs
-        solver.step(S)
-        solver.field(odis.FIELD_ETA, out=h_eta)                              # D2H of what a dump reads, straight into the pinned buffers
-        solver.field(odis.FIELD_VELOCITY, out=h_v)
-        return solver.dissipation_avg()
+        def e2e_interval(k: int):
+            solver.set_state(h_v, h_eta, h_dv, h_de, iter=it0 + k * S)          # H2D of this rank's part of the interval's inputs
+            solver.step(S)
+            solver.field(odis.FIELD_ETA, out=h_eta)                              # D2H of this rank's part of what a dump reads
+            solver.field(odis.FIELD_VELOCITY, out=h_v)
+            return solver.dissipation_avg()
 
-    e2e_interval(0)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        e2e_interval(k + 1)
-    torch.cuda.synchronize()
-    el = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e = {"value": round(Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * (4 * F + 4 * N),
-           "d2h_bytes_per_step": 8 * (F + N + 1), "intervals_timed": Ke}
+        e2e_interval(0)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            e2e_interval(k + 1)
+        torch.cuda.synchronize()
+        el = reduce_ranks(time.perf_counter() - t0)
+        barrier()
+        loc_e, loc_c = part["own_edges"] + part["ghost_edges"], part["own_cells"] + part["ghost_cells"]
+        h2d = reduce_ranks(8.0 * (loc_e + 3 * part["own_edges"] + 4 * loc_c), "sum")
+        d2h = reduce_ranks(8.0 * (part["own_edges"] + part["own_cells"] + 1), "sum")
+        e2e = {"value": round(Ke * S / el, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "intervals_timed": Ke,
+               "path": "synchronous calls per rank (odis_set_state: the rank packs and uploads only the entries it holds; odis_step; odis_get_field: "
+                       "only the rank's own entries come back); bytes are summed over the ranks"}
 
+    # ---- BASELINE config 4 inside the same launch: synthetic 10,485,762-cell grid partitioned over the N GPUs -------------------------
     variants = None
+    if world > 1 and not args.no_variants:
+        variants = {"synthetic_l10": synthetic_l10_partitioned(odis, dist, torch, rank, local_rank, world, reduce_ranks, barrier)}
     if world == 1 and not args.no_variants:
         variants = {}
         for name, deg in (("no_self_gravity", 0), ("self_gravity_degree_8", 8)):
@@ -450,53 +594,118 @@ def run_ours(args) -> None:
             n = max(S, min(K * S, 1000))
             variants[name] = {"timesteps_per_s": round(n / (alt.step_timed(n) * 1e-3), 1)}
             alt.close()
-    if variants is not None and not args.no_probes:
-        # opt-in kernel selections that are not the default, each timed in its own process (not part of `value`)
+        value_no_sg = variants.get("no_self_gravity", {}).get("timesteps_per_s", round(value, 2) if L < 2 else None)
+    cpu_base = parity = None
+    if world == 1 and not args.no_cpu:
+        cpu_base, parity = cpu_baseline_and_parity(odis, mesh, prm, L, local_rank)
+    if variants is not None and world == 1 and not args.no_probes:
+        # other configurations and selections, each timed in its own process (not part of `value`)
         torch.cuda.synchronize()
-        variants["other_baseline_configs"] = run_probe("other_configs", args, 120.0)      # kernels that have run on B200s before
-        variants["e2e_pipelined"] = run_probe("e2e_pipelined", args, 120.0)
-        variants["opt_in_selections"] = [run_probe("nonlinear", args, 120.0), run_probe("headline_selections", args, 240.0)]
+        variants["synthetic_l10_1gpu"] = run_probe("synthetic_l10_1gpu", args, 330.0)
+        variants["other_baseline_configs"] = run_probe("other_configs", args, 120.0)
+        variants["kernel_selections"] = [run_probe("nonlinear", args, 120.0), run_probe("headline_selections", args, 150.0)]
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (icosahedral-bisection grid generated in the reference's grid_lN.txt conventions; zero initial state, tidal forcing)",
-                "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE, 23 km shell), ECC tide, linear drag, {N} cells / {F} edges "
-                                       f"(reference file level {args.level} = BASELINE 'L{args.level - 1}'); "
-                                       + (f"self-gravity / shell-pressure term by spherical harmonics to degree {L} (least-squares analysis + synthesis every step; "
-                                          f"factors 1 - beta_l of the reference's 23 km Enceladus table)" if L >= 2 else "no self-gravity term"),
-                           "sh_degree": L, "kernel_select": args.kernel_select,
-                           "cells": N, "edges": F, "lte_steps_per_bench_step": S, "dt_s": prm["dt"],
-                           "cache": f"working set {dev_bytes / 1e6:.0f} MB device, {alg_bytes / 1e6:.0f} MB streamed per LTE step > 126 MB L2 (no flush needed)",
-                           "parallelism": "1 GPU" if world == 1 else
-                           f"{world} GPUs, grid cut into {world} space-filling-curve parts, one-ring halo, one exchange per step (boundary-edge "
-                           f"velocities pushed by the edge kernel itself as NVLink peer stores; ghost cells updated locally) "
-                           f"(rank 0: {part['own_cells']} own + {part['ghost_cells']} ghost cells, {part['n_peers']} neighbours)"},
+                "config": workload_config(N, F, args.level, L, S, prm["dt"], world, args.kernel_select),
+                "partition": {"rank0_own_cells": part["own_cells"], "rank0_ghost_cells": part["ghost_cells"], "rank0_neighbours": part["n_peers"]},
+                "value_no_self_gravity": value_no_sg,
                 "cell_updates_per_s": round(value * N, 1), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}
+        if parity is not None:
+            line["parity"] = parity
+        if parity_multi is not None:
+            line["parity_vs_single_gpu"] = parity_multi
         if variants:
             line["variants"] = variants
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_port(mesh, prm, sh_degree=L)
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
-        if world > 1 and args.level >= 10 and local_rank == 0:
-            shutil.rmtree(shared, ignore_errors=True)
         dist.destroy_process_group()
 
 
+def synthetic_l10_partitioned(odis, dist, torch, rank, local_rank, world, reduce_ranks, barrier) -> dict:
+    """BASELINE config 4: synthetic icosahedral-bisection grid with 10,485,762 cells (reference file level 11), free-surface LTE (no
+    self-gravity term), partitioned over the N GPUs of this launch, 200 timed steps. Every stage ends in an all-reduce of an ok flag so
+    that a failure on one rank ends the variant on all of them instead of hanging a collective."""
+    out = {"cells": 10485762, "n_gpus": world, "steps_timed": 200, "config": "free-surface Enceladus ocean, ECC tide, linear drag, no self-gravity term"}
+    shared = f"/dev/shm/odis_b200_mesh_l11_{os.environ.get('MASTER_PORT', '0')}"
+    t0 = time.time()
+
+    def stage(fn):
+        ok, res, err = 1.0, None, ""
+        try:
+            res = fn()
+        except Exception as e:                                   # noqa: BLE001
+            ok, err = 0.0, repr(e)[:300]
+        if reduce_ranks(ok, "min") < 0.5:
+            raise RuntimeError(err or "another rank failed")
+        return res
+
+    solver = None
+    try:
+        def make_mesh():
+            if local_rank == 0:
+                pos, fr, cen = odis.generate_grid(11)
+                odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"]).save(shared)
+        stage(make_mesh)
+        mesh = stage(lambda: odis.Mesh.load(shared))
+        prm = dict(workload_params(mesh), surface=0, shell_thickness=0.0, love_reduct=1.0)
+        solver = stage(lambda: odis.Solver(mesh, prm, device=local_rank, rank=rank, world=world))
+
+        def connect():
+            blobs = [None] * world
+            dist.all_gather_object(blobs, solver.halo_blob())
+            solver.halo_connect(blobs)
+        stage(connect)
+        out["setup_s"] = round(time.time() - t0, 1)
+        stage(lambda: solver.step(24))
+        barrier()
+        ms = stage(lambda: solver.step_timed(200))
+        torch.cuda.synchronize()
+        barrier()
+        ms = reduce_ranks(ms)
+        _, alg = solver.footprint()
+        peak, _ = measured_peak()
+        part = solver.partition()
+        finite = reduce_ranks(1.0 if math.isfinite(solver.dissipation_avg()) else 0.0, "min") > 0.5
+        out.update({"timesteps_per_s": round(200 / (ms * 1e-3), 2), "cell_updates_per_s": round(10485762 * 200 / (ms * 1e-3), 1),
+                    "per_gpu_algorithmic_GBps": round(alg * 200 / (ms * 1e-3) / 1e9, 1),
+                    "per_gpu_frac_of_measured_hbm_peak": round(alg * 200 / (ms * 1e-3) / 1e9 / peak, 4), "finite": bool(finite),
+                    "rank0_own_cells": part["own_cells"], "rank0_ghost_cells": part["ghost_cells"]})
+    except Exception as e:                                       # noqa: BLE001
+        out["error"] = repr(e)[:300]
+    finally:
+        if solver is not None:
+            try:
+                solver.synchronize()
+            except Exception:                                    # noqa: BLE001
+                pass
+        barrier()
+        if solver is not None:
+            solver.close()
+        if local_rank == 0:
+            shutil.rmtree(shared, ignore_errors=True)
+    return out
+
+
 def run_reference(args) -> None:
-    """The reference's own CPU implementation of the path on this box's host cores (rank 0 only)."""
+    """The reference's own CPU implementation of the path on this box's host cores (rank 0 only). The input files are written through the
+    host-only library (no CUDA mapped into this process or the reference's)."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    os.environ["ODIS_B200_HOST_ONLY"] = "1"
     import geodesicodis_b200 as odis
     from oracle.build_oracle import reference_binary
     level = args.level
-    S = args.ref_substeps
+    S, S_ref = args.substeps, args.ref_substeps
     K, W = args.steps, max(args.warmup, 0)
-    nsteps = (K + W) * S
+    nsteps = (K + W) * S_ref
     pos, fr, cen = odis.generate_grid(level)
     mesh = odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"] - ENCELADUS["shell"])
     prm = workload_params(mesh)
@@ -507,10 +716,13 @@ def run_reference(args) -> None:
     if binary is None:
         binary, cores = reference_binary(level), 1
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Enceladus subsurface ocean (LID_LOVE), ECC tide, linear drag, {N} cells / {F} edges; the reference's "
-                                   "self-gravity term is commented out at HEAD (src/spatialOperators.cpp:387-462), so its loop runs without it",
-                       "cells": N, "edges": F, "lte_steps_per_bench_step": S}}
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (icosahedral-bisection grid generated in the reference's grid_lN.txt conventions; zero initial state, tidal forcing)",
+            "config": workload_config(N, F, level, args.sh_degree, S, prm["dt"], world, 0),
+            "reference_notes": f"each bench step (one output interval of {S} LTE steps) is timed on a bounded sample of {S_ref} of its steps and scaled; "
+                               "the reference's self-gravity term is commented out at its HEAD (src/spatialOperators.cpp:387-462), so its own loop runs "
+                               "the configuration without that term (compare with the GPU arm's value_no_self_gravity)",
+            "sampled_lte_steps_per_bench_step": S_ref}
     if binary is not None:
         d = tempfile.mkdtemp(prefix="odis_ref_bench_")
         try:
@@ -545,8 +757,9 @@ def run_reference(args) -> None:
         finally:
             shutil.rmtree(d, ignore_errors=True)
     else:
-        base = cpu_baseline_port(mesh, prm, budget_s=20.0)
-        value, kind, cores, sample = base["value"], "port", 1, base["sample"] + " (oracle/_ref binary for this level not present)"
+        o, n, el = oracle_run(mesh, prm, 0, 0, 20.0)
+        value, kind, cores = n / el, "port", 1
+        sample = f"{n} LTE steps of the same {N}-cell workload, oracle/lte_oracle.c (gcc -O2), single thread (oracle/_ref binary for this level not present)"
     line.update({"value": round(value, 3), "ms_per_step": round(1e3 * S / value, 2),
                  "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -565,8 +778,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra device-resident timings with other --sh-degree values")
     ap.add_argument("--no-probes", action="store_true", help="skip the subprocess timings of the opt-in kernel selections")
-    ap.add_argument("--kernel-select", type=int, default=0, help="opt-in kernel selection bits (include/odis_b200.h, odis_params.reserved[0]); "
-                    "0 = the default kernels. E.g. 16: self-gravity step in 3 launches (also on partitioned grids), 128: 16-bit stencil ids")
+    ap.add_argument("--kernel-select", type=int, default=0, help="kernel selection bits (include/odis_b200.h, odis_params.reserved[0]); "
+                    "0 = the default kernels; 1: direct-load baseline kernels, 8: no CUDA-graph replay, 128: 32-bit stencil ids only")
     ap.add_argument("--variant-probe", default="", help=argparse.SUPPRESS)
     ap.add_argument("--probe-level", type=int, default=8, help=argparse.SUPPRESS)
     ap.add_argument("--sh-degree", type=int, default=2, help="self-gravity term by spherical harmonics to this degree (the shipped input.in's "

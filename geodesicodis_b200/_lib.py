@@ -7,7 +7,10 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # ODIS_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
-LIB_PATH = os.environ.get("ODIS_B200_LIB") or os.path.join(HERE, "libodis_b200.so")
+# ODIS_B200_HOST_ONLY=1: the host-only part of the ABI (libodis_b200_host.so: grid generator, mesh tables, configuration; no CUDA, no
+# solver) — what bench.py's reference arm uses to write the reference's input files without mapping the CUDA library
+HOST_ONLY = os.environ.get("ODIS_B200_HOST_ONLY", "") not in ("", "0")
+LIB_PATH = os.environ.get("ODIS_B200_LIB") or os.path.join(HERE, "libodis_b200_host.so" if HOST_ONLY else "libodis_b200.so")
 
 c_i32, c_i64, c_f64 = C.c_int32, C.c_int64, C.c_double
 P = C.POINTER
@@ -162,6 +165,8 @@ def load() -> C.CDLL:
                 "or __graft_entry__.build()). geodesicodis_b200 has no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if HOST_ONLY and not hasattr(lib, name):
+                continue                 # solver / run entry points live in the CUDA library only
             fn = getattr(lib, name)      # AttributeError here means the header and the library disagree
             fn.restype = res
             fn.argtypes = args

@@ -19,10 +19,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libodis_b200.so")
+# host-only part of the same C ABI (grid generator, mesh tables, input.in, time-step quantisation — no CUDA): what bench.py's
+# `--impl reference` arm uses to write the reference's input files, so that the reference process never maps the CUDA library
+HOST_LIB = os.path.join(HERE, "libodis_b200_host.so")
+HOST_ONLY_EXCLUDE = ["odis_run.cpp"]        # drives the device engine
 
 HOST_SOURCES = ["odis_capi_host.cpp", "odis_config.cpp", "odis_mesh.cpp", "odis_gridgen.cpp", "odis_reorder.cpp", "odis_partition.cpp", "odis_h5lite.cpp",
                 "odis_run.cpp", "odis_sh.cpp", "odis_mesh_nl.cpp", "odis_analytic.cpp"]
-CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_fused.cu", "odis_engine.cu", "odis_ensemble.cu", "odis_sh.cu", "odis_kernels_nl.cu"]
+CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_engine.cu", "odis_ensemble.cu", "odis_sh.cu", "odis_kernels_nl.cu"]
 
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
@@ -71,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp.txt")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if not force and os.path.exists(LIB) and os.path.exists(HOST_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     nvcc = _nvcc()
     objs = []
@@ -95,6 +99,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(link), r.stdout))
+    host_objs = [os.path.join(BUILD, src + ".o") for src in HOST_SOURCES if src not in HOST_ONLY_EXCLUDE]
+    r = subprocess.run(["g++", "-shared", "-Wl,-z,defs", "-o", HOST_LIB, *host_objs, "-fopenmp"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link of the host-only library failed:\n" + r.stdout)
     # the drop-in executable: `ODIS` run from a directory holding input.in (src/main.cpp)
     exe = os.path.join(HERE, "bin", "ODIS")
     os.makedirs(os.path.dirname(exe), exist_ok=True)

@@ -46,7 +46,8 @@ struct odis_solver {
     int N = 0, F = 0;                // local sizes including the halo
     int No = 0, Fo = 0;              // owned cells / edges (the kernels' iteration spaces)
     int Np = 0, Fp = 0;              // SoA strides: N and Fo rounded up to the pipelined kernels' tile
-    bool pipe_edge = true, pipe_cell = false;  // params.reserved[0]: bit 0 = direct-load edge kernel, bit 1 = staged cell kernel
+    bool pipe_edge = true;           // params.reserved[0] bit 0 clear: the staged (bulk-async) kernels; set: the direct-load baseline kernels
+    bool pipe_cell = true;           // staged cell update (with the staged edge kernel; ODIS_B200_DIRECT_CELL=1 keeps the direct one for A/B timing)
     int rank = 0, world = 1;
     odis_params prm{};
     odis::Physics phys{};
@@ -75,10 +76,6 @@ struct odis_solver {
     double* d_he[3] = {nullptr, nullptr, nullptr};   // cell tendency history: levels 1, 2 and the slot the next update writes
     int hv1 = 0;                     // which of the two edge arrays holds history level 1
     int he1 = 0, he2 = 1, hefree = 2;
-    unsigned long long* d_cmap = nullptr;   // fused kernel: per-edge slot map of its two cells
-    bool fused = false;              // one fused kernel per step (params.reserved[0] bit 2) instead of the two-launch kernels
-    bool eta_lag = false;            // fused stepping: eta is one step behind v until finalize_eta()
-    int mode_lag = 0;                // AB3 mode of the pending cell update
     double* d_block_partial = nullptr;
     unsigned int* d_ticket = nullptr;
     double* d_series = nullptr;
@@ -113,13 +110,7 @@ struct odis_solver {
 
     // nonlinear branch (odis_enable_advection)
     bool nl_on = false;
-    bool nl_fused = false;           // params.reserved[0] bit 5: the 4-launch variant of the nonlinear step
-    bool cell_occ = false;           // params.reserved[0] bit 6: per-step cell update with the register-capped (50 % occupancy) kernel
-    bool cell_prefetch = false;      // params.reserved[0] bit 9: per-step cell update prefetches the next wave's rows into L2
-    int cell_variant() const {
-        return cell_prefetch ? (cell_occ ? odis::kCellPrefetchOccupancyVariant : odis::kCellPrefetchVariant)
-                             : (cell_occ ? odis::kCellOccupancyVariant : prm.block_threads);
-    }
+    bool nl_fused = true;            // the 4-launch nonlinear step (measured +11 %); the baseline selection (bit 0) keeps the 6-launch one
     int nl_launches() const { return nl_fused ? odis::kNlLaunchesFused : odis::kNlLaunches; }
     odis::NlTables nl{};
     double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
@@ -132,18 +123,19 @@ struct odis_solver {
     double* d_shRec = nullptr;
     double *d_shY = nullptr, *d_shGinv = nullptr, *d_shFactor = nullptr, *d_sh_partial = nullptr, *d_sh_b = nullptr, *d_sh_s = nullptr;
     std::vector<double> sh_ginv_host;
-    // 3-launch variant (params.reserved[0] bit 4): harmonic analysis folded into the cell update, solve folded into the synthesis
-    bool sh_fused_req = false, sh_fused = false;
-    double *d_sg_cta = nullptr, *d_sg_group = nullptr;
-    unsigned int* d_sg_ticket = nullptr;
-    int sg_cta_stride = 0, sg_group_stride = 0;
-    odis::CellSgWork sg_work() const {
-        return odis::CellSgWork{sh_lmax, No, d_sg_cta, sg_cta_stride, d_sg_group, sg_group_stride, d_sg_ticket,
-                                cell_prefetch ? odis::resident_cell_ctas(cell_occ && world == 1) : 0};
+    // default for degrees 2..4 with the matrix-free basis: the harmonic analysis is folded into the staged cell update, the solve into the
+    // synthesis launch (3 launches per step: edge, cell, synthesis)
+    // ... and, on hardware, solve + synthesis behind a grid-wide barrier inside the same launch (sh_merged: 2 launches per step)
+    bool sh_fused = false, sh_merged = false;
+    double* d_sg_cta = nullptr;
+    unsigned int* d_sg_ticket = nullptr;     // [0] last-CTA ticket, [8..9] grid barrier (arrival count, generation)
+    int sg_cta_stride = 0;
+    odis::CellSgAccum sg_accum() const {
+        return odis::CellSgAccum{sh_lmax, No, d_sg_cta, sg_cta_stride, d_sh_b, d_sg_ticket, sh_merged ? 1 : 0, d_shGinv, d_shFactor, prm.g, d_sh_s,
+                                 d_sg_ticket + 8};
     }
     int sg_cells() const { return world > 1 ? N : No; }        // cells the cell update covers (partitioned: ghost cells too)
-    int sg_groups() const { return (odis::cell_sg_ctas(sg_cells()) + odis::kCellSgGroup - 1) / odis::kCellSgGroup; }
-    int sh_step_launches() const { return !sh_on ? 0 : (sh_fused ? 1 : sh_launches()); }     // per time step, after the cell update
+    int sh_step_launches() const { return !sh_on ? 0 : (sh_fused ? (sh_merged ? 0 : 1) : sh_launches()); }     // per time step, after the cell update
     unsigned char* d_sh_xblock = nullptr;             // partitioned: this rank's exchange block (odis_sh.cuh), mapped by every other rank
     unsigned long long* d_sh_xctl = nullptr;
     unsigned char* sh_xremote[odis::kShMaxWorld] = {nullptr};
@@ -180,6 +172,12 @@ struct odis_solver {
     cudaEvent_t staged = nullptr, consumed = nullptr;
     bool stage_pending = false, stage_used = false;
     unsigned stage_mask = 0;                 // bit k: array k of the staged state was given (others are zero)
+
+    // partitioned solvers move only the entries they hold across PCIe: page-locked host buffer for the packed state / fields
+    double* h_pack = nullptr;
+    size_t h_pack_cap = 0;
+    cudaEvent_t pack_done = nullptr;         // the last H2D copy out of h_pack
+    bool pack_pending = false;
 
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
@@ -388,15 +386,14 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     const int tile = odis::pipe_tile();
     s->Np = (s->N + tile - 1) / tile * tile;
     s->Fp = (s->Fo + tile - 1) / tile * tile;
+    // kernel selection, odis_params.reserved[0] (include/odis_b200.h): bit 0 = the direct-load baseline kernels (edge, cell, separate
+    // self-gravity launches, 6-launch nonlinear step); bit 3 = no CUDA-graph replay; bit 7 = 32-bit stencil ids only (default: 16-bit
+    // offsets where they fit); bit 8 = test hook of the narrow ids (+-1023 range)
     s->pipe_edge = (prm->reserved[0] & 1) == 0;
-    s->pipe_cell = (prm->reserved[0] & 2) != 0;
-    s->fused = (prm->reserved[0] & 4) != 0 && prm->potential != odis::P_PLANET;      // PLANET forcing is a pass of its own (two-launch kernels)
+    s->pipe_cell = s->pipe_edge && !(std::getenv("ODIS_B200_DIRECT_CELL") && std::atoi(std::getenv("ODIS_B200_DIRECT_CELL")) != 0);
     s->use_graph = (prm->reserved[0] & 8) == 0;
-    s->sh_fused_req = (prm->reserved[0] & 16) != 0;
-    s->nl_fused = (prm->reserved[0] & 32) != 0;
-    s->cell_occ = (prm->reserved[0] & 64) != 0;
-    s->edge_ids16 = (prm->reserved[0] & 128) != 0 && s->pipe_edge;
-    s->cell_prefetch = (prm->reserved[0] & 512) != 0;
+    s->nl_fused = s->pipe_edge;
+    s->edge_ids16 = (prm->reserved[0] & 128) == 0 && s->pipe_edge;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
     auto local_cell = [&](int old_id) { return num.local_cell_of_ref(old_id); };
@@ -408,18 +405,6 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         std::vector<double2> grad((size_t)Fp, make_double2(0.0, 0.0)), normal((size_t)Fo), vl((size_t)Fvl, make_double2(0.0, 0.0));
         std::vector<double> fcor((size_t)Fp, 0.0), dist((size_t)Fp, 1.0), sw((size_t)Fp * odis::kStencil, 0.0);
         std::vector<int> sid((size_t)Fp * odis::kStencil, -1);
-        std::vector<unsigned long long> cmap((size_t)Fp, ~0ull >> 4);       // all slots "none", no store flags
-        // the edge of each local cell that stores it in the fused kernel: the lowest local edge this rank updates
-        std::vector<int> keeper((size_t)N, -1);
-        for (int en = Fo - 1; en >= 0; en--) {
-            const int eo = s->edge_perm[en];
-            for (int k = 0; k < 2; k++) {
-                const int lc = local_cell(mv->face_nodes[(size_t)eo * 2 + k]);
-                if (lc >= 0) keeper[(size_t)lc] = en;
-            }
-        }
-        for (int cn = 0; cn < N; cn++)
-            if (keeper[(size_t)cn] < 0) s->fused = false;    // a held cell without an updated edge: the two-launch kernels handle it
         int bad = 0;
 #pragma omp parallel for schedule(static)
         for (int en = 0; en < F; en++) vl[en] = make_double2(0.0, mv->face_len[s->edge_perm[en]]);
@@ -452,44 +437,11 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
                 sid[(size_t)j * Fp + en] = le;
                 sw[(size_t)j * Fp + en] = ws[j];
             }
-            // slot map of the two cells (fused kernel): the cell's edges in ascending reference id, each as
-            // "0 = this edge, j+1 = stencil slot j" + a sign bit (set when the cell is that edge's outer cell)
-            unsigned long long cm = 0;
-            const int cref[2] = {c0, c1};
-            for (int k = 0; k < 2; k++) {
-                const int co = cref[k];
-                const int n = (mv->node_friends[(size_t)co * 6 + 5] < 0) ? 5 : 6;
-                int cid[6], cdir[6];
-                for (int j = 0; j < n; j++) { cid[j] = mv->faces[(size_t)co * 6 + j]; cdir[j] = mv->node_face_dir[(size_t)co * 6 + j]; }
-                for (int a = 1; a < n; a++) {
-                    const int id = cid[a], dr = cdir[a];
-                    int b = a - 1;
-                    while (b >= 0 && cid[b] > id) { cid[b + 1] = cid[b]; cdir[b + 1] = cdir[b]; b--; }
-                    cid[b + 1] = id; cdir[b + 1] = dr;
-                }
-                for (int m = 0; m < 6; m++) {
-                    unsigned long long field = 15;
-                    if (m < n) {
-                        int slot = -1;
-                        if (cid[m] == eo) slot = 0;
-                        else
-                            for (int j = 0; j < cnt; j++)
-                                if (ids[j] == cid[m]) slot = j + 1;
-                        if (slot < 0) { bad++; continue; }
-                        field = (unsigned long long)slot | (cdir[m] < 0 ? 16ull : 0ull);
-                    }
-                    cm |= field << ((k * 6 + m) * 5);
-                }
-                const int lc = k == 0 ? cells[en].x : cells[en].y;
-                if (lc >= 0 && keeper[(size_t)lc] == en) cm |= 1ull << (60 + k);
-            }
-            cmap[en] = cm;
         }
         if (bad) return bail(fail(ODIS_ERR_ARG, "face_interp_friends / face_nodes hold out-of-range ids (or the halo is incomplete)"));
         if ((rc = upload(s, &s->d_cells, cells)) || (rc = upload(s, &s->d_grad, grad)) || (rc = upload(s, &s->d_fcor, fcor)) ||
             (rc = upload(s, &s->d_dist, dist)) || (rc = upload(s, &s->d_sid, sid)) || (rc = upload(s, &s->d_sw, sw)) ||
-            (rc = upload(s, &s->d_normal, normal)) || (rc = upload(s, &s->d_vl[0], vl)) || (rc = upload(s, &s->d_vl[1], vl)) ||
-            (rc = upload(s, &s->d_cmap, cmap)))
+            (rc = upload(s, &s->d_normal, normal)) || (rc = upload(s, &s->d_vl[0], vl)) || (rc = upload(s, &s->d_vl[1], vl)))
             return bail(rc);
         if (s->edge_ids16) {
             // narrow ids: offsets from the edge's own id, tile-major; a tile with an offset beyond 16 bits stays on the int rows.
@@ -574,7 +526,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         (rc = dev_alloc(s, &s->d_vavg, (size_t)Fo)) || (rc = dev_alloc(s, &s->d_ediss, (size_t)Fo)))
         return bail(rc);
     if ((rc = upload(s, &s->d_edge_perm, s->edge_perm)) || (rc = upload(s, &s->d_cell_perm, s->cell_perm)) ||
-        (rc = dev_alloc(s, &s->d_stage, (size_t)Fg * 3)) || (rc = dev_alloc(s, &s->d_lvl0_v, (size_t)Fo)) ||
+        (rc = dev_alloc(s, &s->d_stage, std::max((size_t)Fg * 3, (size_t)F + 3 * (size_t)Fo + 4 * (size_t)N))) || (rc = dev_alloc(s, &s->d_lvl0_v, (size_t)Fo)) ||
         (rc = dev_alloc(s, &s->d_lvl0_e, (size_t)Np)))
         return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
@@ -793,10 +745,71 @@ int odis_get_partition(odis_solver* s, int32_t* rank, int32_t* world, int32_t* o
 
 static int finish_set_state(odis_solver* s, int64_t iter, bool sync);
 
+// page-locked staging of a partitioned solver (at least `doubles` entries); waits for copies still reading the previous content
+static int ensure_pack(odis_solver* s, size_t doubles) {
+    if (s->pack_pending) {
+        ODIS_CUDA(cudaEventSynchronize(s->pack_done));
+        s->pack_pending = false;
+    }
+    if (doubles <= s->h_pack_cap) return ODIS_OK;
+    if (s->h_pack) cudaFreeHost(s->h_pack);
+    s->h_pack = nullptr; s->h_pack_cap = 0;
+    ODIS_CUDA(cudaHostAlloc((void**)&s->h_pack, doubles * sizeof(double), cudaHostAllocDefault));
+    s->h_pack_cap = doubles;
+    if (!s->pack_done) ODIS_CUDA(cudaEventCreateWithFlags(&s->pack_done, cudaEventDisableTiming));
+    return ODIS_OK;
+}
+
+// odis_set_state of a partitioned solver: the rank packs the entries it holds (own + halo) out of the caller's global arrays into
+// page-locked memory, in device order, and uploads only those — 1/world of the state instead of all of it per rank
+static int set_state_partitioned(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt) {
+    const size_t N = (size_t)s->N, F = (size_t)s->F, Fo = (size_t)s->Fo;
+    int rc = ensure_pack(s, F + 3 * Fo + 4 * N);
+    if (rc) return rc;
+    double* hv = s->h_pack; double* hdv = hv + F; double* he = hdv + 3 * Fo; double* hde = he + N;
+    const int* ep = s->edge_perm.data(); const int* cp = s->cell_perm.data();
+    if (v) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)F; i++) hv[i] = v[ep[i]];
+    }
+    if (dvdt) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)Fo; i++) { const size_t o = (size_t)ep[i] * 3; hdv[3 * i] = dvdt[o]; hdv[3 * i + 1] = dvdt[o + 1]; hdv[3 * i + 2] = dvdt[o + 2]; }
+    }
+    if (eta) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)N; i++) he[i] = eta[cp[i]];
+    }
+    if (detadt) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)N; i++) { const size_t o = (size_t)cp[i] * 3; hde[3 * i] = detadt[o]; hde[3 * i + 1] = detadt[o + 1]; hde[3 * i + 2] = detadt[o + 2]; }
+    }
+    // d_stage holds max(3 Fg, F + 3 Fo + 4 N) doubles (create_impl): the four packed arrays side by side
+    double* dv = s->d_stage; double* ddv = dv + F; double* de = ddv + 3 * Fo; double* dde = de + N;
+    if (v) ODIS_CUDA(cudaMemcpyAsync(dv, hv, F * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (dvdt) ODIS_CUDA(cudaMemcpyAsync(ddv, hdv, 3 * Fo * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (eta) ODIS_CUDA(cudaMemcpyAsync(de, he, N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (detadt) ODIS_CUDA(cudaMemcpyAsync(dde, hde, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    ODIS_CUDA(cudaEventRecord(s->pack_done, s->stream));
+    s->pack_pending = true;
+    odis::launch_scatter_x(s->F, nullptr, v ? dv : nullptr, s->d_vl[s->cur], 0, s->stream);
+    s->hv1 = 0;
+    odis::launch_scatter_history(s->Fo, nullptr, dvdt ? ddv : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
+    odis::launch_scatter_x(s->N, nullptr, eta ? de : nullptr, s->d_eu[s->ecur], 1, s->stream);
+    s->he1 = 0; s->he2 = 1; s->hefree = 2;
+    odis::launch_scatter_history(s->N, nullptr, detadt ? dde : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    return ODIS_OK;
+}
+
 int odis_set_state(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt, int64_t iter) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
     ODIS_CUDA(cudaSetDevice(s->device));
+    if (s->world > 1) {
+        int rcp = halo_drain(s);
+        if (rcp || (rcp = set_state_partitioned(s, v, eta, dvdt, detadt))) return rcp;
+        return finish_set_state(s, iter, true);
+    }
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo;
     // Reference-ordered (global) host arrays go through one device staging buffer and are renumbered by
     // small kernels; velocities keep the static edge length beside them (only .x is rewritten). A
@@ -833,7 +846,6 @@ static int finish_set_state(odis_solver* s, int64_t iter, bool sync) {
     s->last_mode = -1;
     s->diag_current = false;
     s->have_state = true;
-    s->eta_lag = false;
     // potential for the first step: forcing(current_time + dt), timeIntegrator.cpp:187,218 — for every
     // held cell, halo included
     const double t = s->prm.dt * (double)iter + s->prm.dt;
@@ -912,7 +924,6 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
     if (!s || !mv || !factor) return fail(ODIS_ERR_ARG, "NULL argument");
     if (l_max < 2 || l_max > 31) return fail(ODIS_ERR_ARG, "sh degree must be in 2..31");
     if (mv->n_cells != s->Ng) return fail(ODIS_ERR_ARG, "mesh does not match the solver");
-    if (s->fused) return fail(ODIS_ERR_UNSUPPORTED, "the self-gravity term needs the two-launch step kernels");
     if (s->world > 1 && !s->connected) return fail(ODIS_ERR_STATE, "call odis_halo_connect before odis_enable_self_gravity on a partitioned solver");
     if (s->world > 1 && !s->pipe_edge) return fail(ODIS_ERR_UNSUPPORTED, "partitioned self-gravity needs the default step kernels");
     if (s->sh_on) return fail(ODIS_ERR_STATE, "self-gravity is already enabled");
@@ -949,21 +960,14 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
         return rc;
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_b, 0, (size_t)rows * sizeof(double), s->stream));
     ODIS_CUDA(cudaMemsetAsync(s->d_sh_s, 0, (size_t)rows * sizeof(double), s->stream));
-    if (s->sh_fused_req) {
-        if (s->sh_stored || s->pipe_cell || !odis::cell_sg_supports(l_max) || (s->world > 1 && (s->cell_occ || !s->pipe_edge)))
-            return fail(ODIS_ERR_UNSUPPORTED, "the 3-launch self-gravity variant needs the matrix-free basis, the direct cell kernel and sh degree <= 4 "
-                                              "(partitioned solvers: the staged edge kernel, no register cap)");
-        ODIS_CUDA(odis::cell_sg_configure());
-        s->sg_cta_stride = (odis::cell_sg_ctas(s->sg_cells()) + 31) / 32 * 32;
-        s->sg_group_stride = (s->sg_groups() + 31) / 32 * 32;
-        // one more ticket behind the per-group ones: the groups that have finished (partitioned solvers)
-        if ((rc = dev_alloc(s, &s->d_sg_cta, (size_t)rows * s->sg_cta_stride)) || (rc = dev_alloc(s, &s->d_sg_group, (size_t)rows * s->sg_group_stride)) ||
-            (rc = dev_alloc(s, &s->d_sg_ticket, (size_t)s->sg_group_stride + 32)))
-            return rc;
+    if (s->pipe_cell && !s->nl_on && !s->sh_stored && odis::cell_pipe_supports_sg(l_max)) {
+        // degrees 2..4, matrix-free: the staged cell update accumulates the harmonic sums on the way (3 launches per step)
+        s->sg_cta_stride = (odis::cell_pipe_grid(s->sg_cells()) + 31) / 32 * 32;
+        if ((rc = dev_alloc(s, &s->d_sg_cta, (size_t)rows * s->sg_cta_stride)) || (rc = dev_alloc(s, &s->d_sg_ticket, (size_t)32))) return rc;
         ODIS_CUDA(cudaMemsetAsync(s->d_sg_cta, 0, (size_t)rows * s->sg_cta_stride * sizeof(double), s->stream));
-        ODIS_CUDA(cudaMemsetAsync(s->d_sg_group, 0, (size_t)rows * s->sg_group_stride * sizeof(double), s->stream));
-        ODIS_CUDA(cudaMemsetAsync(s->d_sg_ticket, 0, ((size_t)s->sg_group_stride + 32) * sizeof(unsigned int), s->stream));
+        ODIS_CUDA(cudaMemsetAsync(s->d_sg_ticket, 0, 32 * sizeof(unsigned int), s->stream));
         s->sh_fused = true;
+        s->sh_merged = odis::cell_pipe_merged();
     }
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);     // captured without the extra launches
@@ -1011,7 +1015,8 @@ static int build_ell(odis_solver* s, const odis_csr_view& A, int n_rows, int str
 int odis_enable_advection(odis_solver* s, const odis_mesh_view* mv, const odis_nonlinear_view* nv) {
     if (!s || !mv || !nv) return fail(ODIS_ERR_ARG, "NULL argument");
     if (s->nl_on) return fail(ODIS_ERR_STATE, "the nonlinear branch is already enabled");
-    if (s->world > 1 || s->fused) return fail(ODIS_ERR_UNSUPPORTED, "the nonlinear branch runs on a single, unpartitioned solver with the two-launch kernels");
+    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "the nonlinear branch runs on a single, unpartitioned solver");
+    if (s->sh_fused) return fail(ODIS_ERR_STATE, "call odis_enable_advection before odis_enable_self_gravity");
     if (mv->n_cells != s->Ng || mv->n_edges != s->Fg) return fail(ODIS_ERR_ARG, "mesh does not match the solver");
     const int N = s->N, F = s->F, V = mv->n_vertices;
     if (nv->curl.n_rows != V || nv->curl.n_cols != F || nv->rbf_interp.n_rows != 3 * N || nv->rbf_interp.n_cols != F ||
@@ -1154,22 +1159,6 @@ static void rotate_cell_history(odis_solver* s, int mode) {
     else { s->he1 = fr; s->he2 = l1; s->hefree = l2; }                                  // shift
 }
 
-// fused stepping leaves eta one step behind v; this runs the pending cell update (all held cells, so the
-// halo stays consistent) and keeps the potential the next edge update needs
-static int finalize_eta(odis_solver* s) {
-    if (!s->eta_lag) return ODIS_OK;
-    odis::CellState cs{s->d_vl[s->cur], s->d_eu[s->ecur], s->d_eu[1 - s->ecur], s->d_he[s->he1], s->d_he[s->he2], s->d_he[s->hefree],
-                       nullptr, 0, nullptr, nullptr};
-    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, s->mode_lag, odis::StepScalars{}, odis::CELL_UPDATE_ETA, s->prm.block_threads,
-                           nullptr, s->stream);
-    s->launches++;
-    ODIS_CUDA(cudaGetLastError());
-    rotate_cell_history(s, s->mode_lag);
-    s->ecur = 1 - s->ecur;
-    s->eta_lag = false;
-    return ODIS_OK;
-}
-
 constexpr int kGraphSteps = 12;      // steps per captured graph: a multiple of the rotation period (2 x 2 x 3 -> 6)
 
 // Launches of one time step on the solver's stream (also under stream capture) and the rotation of the buffers.
@@ -1239,30 +1228,30 @@ static int enqueue_step(odis_solver* s, int mode, bool dev_ctl, std::vector<cuda
     // the next step's forcing time: current_time = dt*(iter+1), evaluated at current_time + dt
     const odis::StepScalars next = dev_ctl ? odis::StepScalars{} : step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt);
     if (s->pipe_cell) {
-        if (inline_e) { int rc2 = halo_drain(s); if (rc2) return rc2; }
-        ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, s->stream));
-    } else if (s->sh_on && s->sh_fused) {
-        // 3-launch variant: the cell update leaves the harmonic sums of eta^{n+1} over groups of its CTAs
-        if (part) {
-            const odis::HaloInline hc = halo_inline_cell(s);
-            odis::launch_cell_step_sgx(ct, s->phys, cs, mode, next, s->sg_work(), hc, s->sh_exchange(), s->stream);
-        } else odis::launch_cell_step_sg(ct, s->phys, cs, mode, next, s->sg_work(), s->cell_occ, s->stream);
+        // staged cell update; with the self-gravity term to degree <= 4 it also leaves the harmonic sums of eta^{n+1} (this rank's cells)
+        odis::HaloInline hc;
+        if (inline_e) hc = halo_inline_cell(s);
+        const odis::CellSgAccum sg = s->sg_accum();
+        const odis::ShExchange x = s->sh_exchange();
+        const bool with_sg = s->sh_on && s->sh_fused;
+        ODIS_CUDA(odis::launch_cell_step_pipe(ct, s->phys, cs, mode, next, inline_e ? &hc : nullptr, with_sg ? &sg : nullptr,
+                                              with_sg && part ? &x : nullptr, s->stream));
     } else {
         odis::HaloInline hc;
         if (inline_e) hc = halo_inline_cell(s);
         odis::launch_cell_step(ct, s->phys, cs, mode, next, odis::CELL_UPDATE_ETA | odis::CELL_UPDATE_U,
-                               s->cell_variant(), inline_e ? &hc : nullptr, s->stream);
+                               s->prm.block_threads, inline_e ? &hc : nullptr, s->stream);
     }
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;
     enqueue_planet(s, s->d_eu[s->ecur], ct.n_active, next, dev_ctl ? &s->d_ctl->cur : nullptr);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
-    if (s->sh_on && s->sh_fused && part)
-        odis::launch_sh_allsolve_synthesis(s->sh_tables(), s->sh_work(), s->sh_exchange(), s->prm.g, s->d_eu[s->ecur], s->N, s->stream);
-    else if (s->sh_on && s->sh_fused)
-        odis::launch_sh_solve_synthesis(s->sh_tables(), s->sh_work(), s->d_sg_group, s->sg_group_stride, s->sg_groups(), s->prm.g, s->d_eu[s->ecur], s->N,
-                                        s->stream);
-    else { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
+    if (s->sh_on && s->sh_fused && s->sh_merged) {
+        // solve + synthesis happened inside the cell update's launch
+    } else if (s->sh_on && s->sh_fused) {
+        const odis::ShExchange x = s->sh_exchange();
+        odis::launch_sh_bsolve_synthesis(s->sh_tables(), s->sh_work(), part ? &x : nullptr, s->prm.g, s->d_eu[s->ecur], s->N, s->stream);
+    } else { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 3], s->stream);
     s->cur = 1 - s->cur;
     s->iter++;
@@ -1279,41 +1268,6 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
     int rc = ensure_series(s, (size_t)(s->iter - s->iter0) + (size_t)nsteps + 1);
     if (rc) return rc;
     if (s->world > 1 && !s->connected) return fail(ODIS_ERR_STATE, "odis_halo_connect has not been called on this partitioned solver");
-    const odis::EdgeTables et = s->edge_tables();
-    if (s->fused) {
-        odis::FusedTables ft;
-        ft.e = et; ft.cmap = s->d_cmap; ft.area = s->d_area; ft.trig = s->d_trig; ft.trig_sq = s->d_trig_sq; ft.cell_stride = s->Np;
-        for (int k = 0; k < nsteps; k++) {
-            const int mode = ab3_mode(s, s->iter);
-            odis::FusedState fs;
-            fs.vl_in = s->d_vl[s->cur]; fs.vl_out = s->d_vl[1 - s->cur];
-            fs.eu_in = s->d_eu[s->ecur]; fs.eu_out = s->d_eu[1 - s->ecur];
-            fs.h1 = s->d_hv[s->hv1]; fs.h2 = s->d_hv[1 - s->hv1];
-            fs.ch1 = s->d_he[s->he1]; fs.ch2 = s->d_he[s->he2]; fs.chw = s->d_he[s->hefree];
-            fs.block_partial = s->d_block_partial; fs.ticket = s->d_ticket;
-            fs.energy_out = s->d_series + (s->iter - s->iter0);
-            const double tnext = s->prm.dt * (double)(s->iter + 1) + s->prm.dt;
-            if (marks) cudaEventRecord((*marks)[(size_t)k * 4], s->stream);
-            ODIS_CUDA(odis::launch_step_fused(ft, s->phys, fs, mode, s->mode_lag, s->eta_lag ? 1 : 0, step_scalars(s, tnext), s->stream));
-            if (s->eta_lag) rotate_cell_history(s, s->mode_lag);
-            s->ecur = 1 - s->ecur;
-            if (s->world > 1) {                   // one exchange per step: v^{n+1} of my boundary edges
-                int rc2 = halo_exchange(s, 0, s->d_vl[1 - s->cur], 1 - s->cur);
-                if (rc2) return rc2;
-            }
-            if (marks) for (int q = 1; q < 4; q++) cudaEventRecord((*marks)[(size_t)k * 4 + q], s->stream);
-            if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
-            s->cur = 1 - s->cur;
-            s->iter++;
-            s->last_mode = mode;
-            s->eta_lag = true;
-            s->mode_lag = mode;
-            s->launches += 1;
-        }
-        if (nsteps > 0) s->diag_current = false;
-        ODIS_CUDA(cudaGetLastError());
-        return ODIS_OK;
-    }
     // ---- two launches per step (+ one halo exchange launch after each when partitioned) ----
     const bool dev_ctl = s->pipe_edge && !s->nl_on;   // the staged edge kernel keeps the step counter / time factors on the device
     if (dev_ctl && nsteps > 0) {             // time factors of every step of this call, uploaded ahead (tidalPotentials.cpp:55-61)
@@ -1350,7 +1304,7 @@ static int step_impl(odis_solver* s, int32_t nsteps, std::vector<cudaEvent_t>* m
             for (int r = 0; r < reps; r++) ODIS_CUDA(cudaGraphLaunch(it->second, s->stream));
             const int adv = reps * kGraphSteps;
             s->graph_launches += reps;
-            s->launches += (int64_t)adv * (2 + (s->world > 1 && s->pipe_cell ? 1 : 0) + planet_launches(s) + s->sh_step_launches());
+            s->launches += (int64_t)adv * (2 + planet_launches(s) + s->sh_step_launches());
             s->iter += adv;
             s->last_mode = odis::AB3_FULL;
             done += adv;
@@ -1386,34 +1340,35 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     ODIS_CUDA(cudaSetDevice(s->device));
     const int No = s->No, Fo = s->Fo;
     size_t count = 0;
-    {
-        int rcf = finalize_eta(s);
-        if (rcf) return rcf;
-    }
-    // a partitioned solver fills its own cells/edges of the global array and leaves zeros elsewhere
-    // (the caller sums the ranks' arrays)
-    auto clear = [&](size_t n) { if (s->world > 1) cudaMemsetAsync(s->d_stage, 0, n * sizeof(double), s->stream); };
+    // a partitioned solver fills its own cells/edges of the global array and leaves zeros elsewhere (the caller sums the ranks'
+    // arrays): the own entries come back compact, in device order (perm == nullptr below), and are spread over `out` on the host
+    const bool part = s->world > 1;
+    const int* eperm = part ? nullptr : s->d_edge_perm;
+    const int* cperm = part ? nullptr : s->d_cell_perm;
+    size_t own = 0, comps = 1;
+    const int* hperm = nullptr;
     switch (field) {
         case ODIS_FIELD_VELOCITY:
-            count = (size_t)s->Fg; clear(count);
-            odis::launch_gather_component(Fo, s->d_edge_perm, s->d_vl[s->cur], 0, s->d_stage, s->stream);
+            count = (size_t)s->Fg; own = (size_t)Fo; hperm = s->edge_perm.data();
+            odis::launch_gather_component(Fo, eperm, s->d_vl[s->cur], 0, s->d_stage, s->stream);
             break;
         case ODIS_FIELD_ETA:
         case ODIS_FIELD_POTENTIAL:
-            count = (size_t)s->Ng; clear(count);
-            odis::launch_gather_component(No, s->d_cell_perm, s->d_eu[s->ecur], field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
+            count = (size_t)s->Ng; own = (size_t)No; hperm = s->cell_perm.data();
+            odis::launch_gather_component(No, cperm, s->d_eu[s->ecur], field == ODIS_FIELD_ETA ? 0 : 1, s->d_stage, s->stream);
             break;
         case ODIS_FIELD_DVDT:
         case ODIS_FIELD_DETADT: {
             // level 0 = newest tendency: as loaded before any step, else where the last step stored it
             // (temporalOperators.cpp:47,56,65)
             const int which0 = s->last_mode < 0 ? 0 : (s->last_mode == odis::AB3_FIRST ? 2 : 1);
+            comps = 3;
             if (field == ODIS_FIELD_DVDT) {
-                count = (size_t)s->Fg * 3; clear(count);
-                odis::launch_gather_history(Fo, s->d_edge_perm, s->d_lvl0_v, s->d_hv[s->hv1], s->d_hv[1 - s->hv1], which0, s->d_stage, s->stream);
+                count = (size_t)s->Fg * 3; own = (size_t)Fo; hperm = s->edge_perm.data();
+                odis::launch_gather_history(Fo, eperm, s->d_lvl0_v, s->d_hv[s->hv1], s->d_hv[1 - s->hv1], which0, s->d_stage, s->stream);
             } else {
-                count = (size_t)s->Ng * 3; clear(count);
-                odis::launch_gather_history(No, s->d_cell_perm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[s->he2], which0, s->d_stage, s->stream);
+                count = (size_t)s->Ng * 3; own = (size_t)No; hperm = s->cell_perm.data();
+                odis::launch_gather_history(No, cperm, s->d_lvl0_e, s->d_he[s->he1], s->d_he[s->he2], which0, s->d_stage, s->stream);
             }
             break;
         }
@@ -1421,12 +1376,13 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
         case ODIS_FIELD_DISSIPATION: {
             int rc = run_diagnostics(s, true);
             if (rc) return rc;
+            own = (size_t)Fo; hperm = s->edge_perm.data();
             if (field == ODIS_FIELD_VELOCITY_EN) {
-                count = (size_t)s->Fg * 2; clear(count);
-                odis::launch_gather_pair(Fo, s->d_edge_perm, s->d_vavg, s->d_stage, s->stream);
+                count = (size_t)s->Fg * 2; comps = 2;
+                odis::launch_gather_pair(Fo, eperm, s->d_vavg, s->d_stage, s->stream);
             } else {
-                count = (size_t)s->Fg; clear(count);
-                odis::launch_gather_scalar(Fo, s->d_edge_perm, s->d_ediss, s->d_stage, s->stream);
+                count = (size_t)s->Fg;
+                odis::launch_gather_scalar(Fo, eperm, s->d_ediss, s->d_stage, s->stream);
             }
             break;
         }
@@ -1435,8 +1391,26 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     }
     s->launches++;
     ODIS_CUDA(cudaGetLastError());
-    ODIS_CUDA(cudaMemcpyAsync(out, s->d_stage, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (!part) {
+        ODIS_CUDA(cudaMemcpyAsync(out, s->d_stage, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        ODIS_CUDA(cudaStreamSynchronize(s->stream));
+        return check_halo_timeout(s);
+    }
+    // partitioned: only the own entries cross PCIe (compact, device order), the host spreads them over the zeroed global array
+    int rcp = ensure_pack(s, own * comps);
+    if (rcp) return rcp;
+    ODIS_CUDA(cudaMemcpyAsync(s->h_pack, s->d_stage, own * comps * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    std::memset(out, 0, count * sizeof(double));
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
+    const double* h = s->h_pack;
+    if (comps == 1) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)own; i++) out[hperm[i]] = h[i];
+    } else {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)own; i++)
+            for (size_t c = 0; c < comps; c++) out[(size_t)hperm[i] * comps + c] = h[(size_t)i * comps + c];
+    }
     return check_halo_timeout(s);
 }
 
@@ -1478,13 +1452,11 @@ static int op_begin(odis_solver* s) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "operator calls need an unpartitioned solver");
     if (s->nl_on) return fail(ODIS_ERR_UNSUPPORTED, "operator calls cover the linear branch (advection; false) only");
-    if (s->fused) return fail(ODIS_ERR_UNSUPPORTED, "operator calls need the two-launch step kernels");
     ODIS_CUDA(cudaSetDevice(s->device));
     int rc = ensure_series(s, 1);
     if (rc) return rc;
     s->have_state = false;          // the state arrays are about to be overwritten
     s->diag_current = false;
-    s->eta_lag = false;
     return ODIS_OK;
 }
 static int op_load_velocity(odis_solver* s, const double* v) {
@@ -1616,8 +1588,7 @@ int odis_snapshot_begin(odis_solver* s, int32_t slot, uint32_t fields) {
         ODIS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     }
     if (sl.pending) ODIS_CUDA(cudaStreamWaitEvent(s->stream, sl.done, 0));     // the slot's previous copy must have left the buffer
-    int rc = finalize_eta(s);
-    if (rc) return rc;
+    int rc;
     const bool want_diag_fields = (fields & (ODIS_SNAP_VELOCITY_EN | ODIS_SNAP_DISSIPATION)) != 0;
     if ((rc = run_diagnostics(s, want_diag_fields))) return rc;
     double* d_eta = sl.d_buf; double* d_ven = d_eta + N; double* d_diss = d_ven + 2 * F; double* d_v = d_diss + F; double* d_sum = d_v + F;
@@ -1713,11 +1684,11 @@ void odis_destroy(odis_solver* s) {
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);
     void* ptrs[] = {s->d_csr_e_first, s->d_csr_e_peer, s->d_csr_e_remote, s->d_halo_done,
                     s->d_ctl, s->d_scal, s->d_cells, s->d_grad, s->d_fcor, s->d_dist, s->d_sw, s->d_sid, s->d_sid16, s->d_tile_wide, s->d_normal, s->d_eid, s->d_area, s->d_trig,
-                    s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2], s->d_cmap,
+                    s->d_trig_sq, s->d_vl[0], s->d_vl[1], s->d_eu[0], s->d_eu[1], s->d_hv[0], s->d_hv[1], s->d_he[0], s->d_he[1], s->d_he[2],
                     s->d_block_partial, s->d_ticket, s->d_series, s->d_vavg, s->d_ediss, s->d_edge_perm, s->d_cell_perm, s->d_stage,
                     s->d_lvl0_v, s->d_lvl0_e, s->d_send_e_local, s->d_send_e_remote, s->d_send_e_peer, s->d_send_c_local, s->d_send_c_remote,
                     s->d_send_c_peer, s->d_flags, s->d_halo_ticket, s->d_shY, s->d_shRec, s->d_shGinv, s->d_shFactor, s->d_sh_partial, s->d_sh_b, s->d_sh_s, s->d_sh_xblock, s->d_sh_xctl,
-                    s->d_sg_cta, s->d_sg_group, s->d_sg_ticket};
+                    s->d_sg_cta, s->d_sg_ticket};
     for (int k = 0; k < kMaxPeers; k++)
         for (int j = 0; j < 5; j++)
             if (s->ipc_opened[k][j]) cudaIpcCloseMemHandle(s->ipc_opened[k][j]);
@@ -1734,6 +1705,8 @@ void odis_destroy(odis_solver* s) {
         if (sl.ready) cudaEventDestroy(sl.ready);
         if (sl.done) cudaEventDestroy(sl.done);
     }
+    if (s->h_pack) cudaFreeHost(s->h_pack);
+    if (s->pack_done) cudaEventDestroy(s->pack_done);
     if (s->d_stage_next) cudaFree(s->d_stage_next);
     if (s->staged) cudaEventDestroy(s->staged);
     if (s->consumed) cudaEventDestroy(s->consumed);

@@ -1,8 +1,5 @@
 // LTE time-step kernels (see odis_kernels.cuh for the mapping onto the reference functions).
 #include "odis_kernels.cuh"
-#include "odis_sh.cuh"
-
-#include <mutex>
 
 namespace odis {
 
@@ -277,51 +274,9 @@ __device__ __forceinline__ double tidal_potential(const Physics& p, const StepSc
     }
 }
 
-// Opt-in (kPrefetch): one thread of every CTA asks the memory system to bring the streamed rows of the tile `ahead` CTAs further on
-// into L2 (cp.async.bulk.prefetch.L2: no registers, no completion to wait for). The CTAs of one wave issue their loads, gather and
-// compute more or less in step, so DRAM idles while they gather and compute; with the rows of the next wave already on their way the
-// stream never stops, and a CTA's first loads become L2 hits. `ahead` = CTAs resident on the GPU (flags >> 8).
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned int bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 template <int kThreads>
-__device__ __forceinline__ void prefetch_cell_tile(const CellTables& t, const Physics& p, const CellState& s, int flags, size_t tile) {
-    const size_t i0 = tile * kThreads, N = (size_t)t.n_cells;
-    if (i0 + kThreads > N) return;                        // whole tiles inside the arrays only
-    if (flags & CELL_UPDATE_ETA) {
-#pragma unroll
-        for (int j = 0; j < kCellEdges; j++) l2_prefetch_bulk(t.eid + (size_t)j * N + i0, kThreads * sizeof(int));
-        l2_prefetch_bulk(t.area + i0, kThreads * sizeof(double));
-        l2_prefetch_bulk(s.h1 + i0, kThreads * sizeof(double));
-        l2_prefetch_bulk(s.h2 + i0, kThreads * sizeof(double));
-    }
-    l2_prefetch_bulk(s.eu_in + i0, kThreads * sizeof(double2));
-    if (flags & CELL_UPDATE_U) {
-        unsigned int rows = 0, sq = 0;                    // bit r: row r of trig / trig_sq, as load_trig reads them
-        switch (p.potential) {
-            case P_ECC: rows = 0xC0u; sq = 3u; break;
-            case P_OBLIQ: rows = 0x24u; break;
-            case P_OBLIQ_WEST: rows = 0x0Fu; break;
-            case P_FULL: rows = 0xE4u; sq = 3u; break;
-            case P_FULL2: rows = 0xDFu; sq = 1u; break;
-            default: break;
-        }
-        for (int r = 0; r < 8; r++)
-            if (rows >> r & 1u) l2_prefetch_bulk(t.trig + (size_t)r * N + i0, kThreads * sizeof(double));
-        for (int r = 0; r < 2; r++)
-            if (sq >> r & 1u) l2_prefetch_bulk(t.trig_sq + (size_t)r * N + i0, kThreads * sizeof(double));
-    }
-}
-
-// kMinBlocks > 0 caps the registers so that that many CTAs fit an SM (opt-in variant: 8 x 128 threads = 50 % occupancy instead of
-// 37.5 %, at the price of a few spilled values); 0 = no cap, the default.
-template <int kThreads, int kMinBlocks = 0, bool kPrefetch = false>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                                         int flags, HaloInline halo) {
-    if (kPrefetch) {
-        if (threadIdx.x == kThreads - 32) prefetch_cell_tile<kThreads>(t, p, s, flags, (size_t)blockIdx.x + (size_t)(flags >> 8));
-        flags &= 0xff;
-    }
+__global__ void __launch_bounds__(kThreads) cell_step_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
+                                                             int flags, HaloInline halo) {
     if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
         block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
     const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -383,205 +338,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_kernel(CellTab
         if ((flags & CELL_UPDATE_U) && p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
         s.eu_out[i] = st;
     }
-}
-
-// ---- cell update with the harmonic analysis of eta^{n+1} folded in (self-gravity term, opt-in variant) ----
-// Recurrence coefficients of the normalised Legendre functions, this translation unit's copy (layout of sh_recurrence_table()).
-__constant__ double c_sg_rec[kShRecDoubles];
-struct SgRec {
-    __device__ __forceinline__ double a(int m, int l) const { return c_sg_rec[l * kShRecStride + m]; }
-    __device__ __forceinline__ double b(int m, int l) const { return c_sg_rec[kShRecStride * kShRecStride + l * kShRecStride + m]; }
-    __device__ __forceinline__ double sect(int m) const { return c_sg_rec[2 * kShRecStride * kShRecStride + m]; }
-    __device__ __forceinline__ double first(int m) const { return c_sg_rec[2 * kShRecStride * kShRecStride + kShRecStride + m]; }
-};
-__device__ __forceinline__ double warp_sum_all(double x) {      // butterfly: fixed association, every lane gets the sum
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-}
-
-// cell_step_kernel (unpartitioned, eta and potential both updated) + b_k += Y_k(i) eta_i^{n+1} for the cells [0, n_fit):
-// the basis values of the cell are rebuilt from (cos lat, sin lat, cos lon, sin lon) exactly as sh_analysis_mf_kernel does
-// (odis_sh.cu); each warp reduces its 32 cells, the CTA leaves one partial per basis row, and the LAST CTA of every group of
-// kCellSgGroup consecutive CTAs to finish adds the group's partials in CTA order. Sums are therefore independent of the
-// order in which CTAs run. sh_solve_synthesis (odis_sh.cu) finishes the sum over the groups.
-// kPart (partitioned solvers): the trailing CTAs wait for the neighbours' halo push like cell_step_kernel does, the fit covers the own
-// cells only (sg.n_fit) while the ghost cells are updated too, and the LAST group to finish adds the groups in group order and publishes
-// this rank's sums for the in-kernel all-reduce (the protocol of sh_reduce_publish_kernel, odis_sh.cu: sums into this rank's exchange
-// block at the parity of the new epoch, then the epoch into this rank's flag in every rank's block, system-scope release).
-__device__ __forceinline__ unsigned long long* sgx_flags(unsigned char* block) { return reinterpret_cast<unsigned long long*>(block); }
-__device__ __forceinline__ double* sgx_pub(unsigned char* block, int parity) {
-    return reinterpret_cast<double*>(block + kShMaxWorld * sizeof(unsigned long long)) + (size_t)parity * kShXRows;
-}
-__device__ __forceinline__ void sgx_st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-template <int kThreads, int LT, bool kPart>
-__device__ __forceinline__ void cell_step_sg_body(const CellTables& t, const Physics& p, const CellState& s, int mode, StepScalars next,
-                                                  const CellSgWork& sg, const HaloInline& halo, const ShExchange& x) {
-    constexpr int kRows = (LT + 1) * (LT + 1);
-    constexpr int kWarps = kThreads / 32;
-    static_assert(kRows <= kThreads, "one thread per basis row writes the CTA partial");
-    __shared__ double red[kRows * kWarps];
-    __shared__ bool group_last;
-    if (sg.prefetch_ahead > 0 && threadIdx.x == kThreads - 32) {      // opt-in: next wave's rows into L2 (see cell_step_kernel)
-        const size_t tile = (size_t)blockIdx.x + (size_t)sg.prefetch_ahead, i0 = tile * kThreads, N = (size_t)t.n_cells;
-        prefetch_cell_tile<kThreads>(t, p, s, CELL_UPDATE_ETA | CELL_UPDATE_U, tile);
-        if (i0 + kThreads <= N)
-            for (int r = 0; r < 4; r++) l2_prefetch_bulk(t.trig + (size_t)r * N + i0, kThreads * sizeof(double));     // the basis' rows
-    }
-    if (blockIdx.x == 0 && s.energy_out != nullptr)      // finish the edge kernel's energy sum (see edge_step_kernel)
-        block_reduce_partials<kThreads>(s.energy_partial, s.n_energy_partials, s.energy_out);
-    bool bnd_cta = false;
-    if (kPart) {
-        bnd_cta = (int)((blockIdx.x + 1) * kThreads) > halo.wait_from;
-        if (bnd_cta) {
-            if (threadIdx.x == 0) halo_wait_all(halo.wait_v, halo.ctl);
-            __syncthreads();
-        }
-    }
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = t.n_cells;
-    const bool active = i < t.n_active;
-    const int at = i < N ? i : N - 1;                   // padded rows of the trig table hold zeros: finite basis, e = 0
-    // ---- phase A: independent loads ----
-    int packed[kCellEdges];
-#pragma unroll
-    for (int j = 0; j < kCellEdges; j++) packed[j] = active ? ld_stream(t.eid + (size_t)j * N + i) : -1;
-    double2 st = active ? ld_gather(s.eu_in + i) : make_double2(0.0, 0.0);
-    const double area = active ? ld_stream(t.area + i) : 1.0;
-    const double f1 = active ? ld_plain(s.h1 + i) : 0.0, f2 = active ? ld_plain(s.h2 + i) : 0.0;
-    TrigValues tv = load_trig(t, active ? p.potential : (int)P_NONE, at);
-    const double bu = t.trig[at], bz = t.trig[(size_t)N + at], bc1 = t.trig[2 * (size_t)N + at], bs1 = t.trig[3 * (size_t)N + at];
-    if (s.next_dev != nullptr) {                         // graph replay: this step's time factors were left by the edge kernel
-        next.cosM = ld_plain(&s.next_dev->cosM);
-        next.sinM = ld_plain(&s.next_dev->sinM);
-        if (p.potential == P_FULL2) {
-            next.cos2M = ld_plain(&s.next_dev->cos2M); next.sin2M = ld_plain(&s.next_dev->sin2M);
-            next.cos3M = ld_plain(&s.next_dev->cos3M); next.cos4M = ld_plain(&s.next_dev->cos4M);
-        }
-    }
-    // ---- phase B: gathers ----
-    double2 ed[kCellEdges];
-    if (!kPart || !bnd_cta) {
-#pragma unroll
-        for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
-    } else {                                              // ghost slots are written by other GPUs while the kernel runs
-#pragma unroll
-        for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather_cg(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
-    }
-    // ---- phase C: as cell_step_kernel ----
-    if (active) {
-        double div = 0.0;
-        const double ra = __drcp_rn(area);
-#pragma unroll
-        for (int j = 0; j < kCellEdges; j++) {
-            if (packed[j] != -1) {
-                const double ndir = (packed[j] < 0) ? 1.0 : -1.0;
-                const double coeff = exact_div(ndir * ed[j].y, area, ra);
-                div += (p.h * coeff) * ed[j].x;
-            }
-        }
-        const double f0 = div;
-        st.x += ab3_increment(f0, f1, f2, p.dt, mode);
-        s.hw[i] = f0;
-        if (p.potential != P_NONE) st.y = tidal_potential(p, next, tv);
-        s.eu_out[i] = st;
-    }
-    // ---- phase D: this cell's share of b = Y eta^{n+1} ----
-    {
-        const SgRec rc;
-        const double e = (active && i < sg.n_fit) ? st.x : 0.0;
-        double cm = 1.0, sn = 0.0, pmm = 1.0;
-#pragma unroll
-        for (int m = 0; m <= LT; m++) {
-            if (m > 0) {
-                const double cn = __fma_rn(cm, bc1, -(sn * bs1));       // cos(m lon), sin(m lon) by rotation
-                sn = __fma_rn(sn, bc1, cm * bs1);
-                cm = cn;
-                pmm = rc.sect(m) * bu * pmm;
-            }
-            const double ec = e * cm, es = e * sn;
-            double p1 = pmm, p2 = 0.0;
-#pragma unroll
-            for (int l = m; l <= LT; l++) {
-                if (l > m) {
-                    const double a = l == m + 1 ? rc.first(m) : rc.a(m, l);
-                    const double b = l == m + 1 ? 0.0 : rc.b(m, l);
-                    const double pn = a * __fma_rn(bz, p1, -(b * p2));
-                    p2 = p1; p1 = pn;
-                }
-                const int row = l * l + (m ? 2 * m - 1 : 0);
-                const double pc = warp_sum_all(p1 * ec);
-                if (lane == 0) red[row * kWarps + warp] = pc;
-                if (m > 0) {
-                    const double ps = warp_sum_all(p1 * es);
-                    if (lane == 0) red[(row + 1) * kWarps + warp] = ps;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < kRows) {
-        double a = red[threadIdx.x * kWarps];
-#pragma unroll
-        for (int q = 1; q < kWarps; q++) a = a + red[threadIdx.x * kWarps + q];
-        sg.cta_partial[(size_t)threadIdx.x * sg.cta_stride + blockIdx.x] = a;
-    }
-    __threadfence();
-    __syncthreads();
-    const int group = blockIdx.x / kCellSgGroup;
-    const int members = min(kCellSgGroup, (int)gridDim.x - group * kCellSgGroup);
-    if (threadIdx.x == 0) group_last = atomicAdd(sg.group_ticket + group, 1u) == (unsigned int)(members - 1);
-    __syncthreads();
-    if (!group_last) return;
-    __threadfence();
-    for (int k = warp; k < kRows; k += kWarps) {
-        const double v = lane < members ? __ldcg(sg.cta_partial + (size_t)k * sg.cta_stride + group * kCellSgGroup + lane) : 0.0;
-        const double tot = warp_sum_all(v);
-        if (lane == 0) sg.group_partial[(size_t)k * sg.group_stride + group] = tot;
-    }
-    if (threadIdx.x == 0) sg.group_ticket[group] = 0u;
-    if (!kPart) return;
-    // ---- partitioned: the last group to finish publishes this rank's sums ----
-    __shared__ bool rank_last;
-    const int n_groups = ((int)gridDim.x + kCellSgGroup - 1) / kCellSgGroup;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) rank_last = atomicAdd(sg.group_ticket + sg.group_stride, 1u) == (unsigned int)(n_groups - 1);
-    __syncthreads();
-    if (!rank_last) return;
-    __threadfence();
-    const unsigned long long epoch = x.ctl[0] + 1ull;
-    double* pub = sgx_pub(x.block[x.rank], (int)(epoch & 1ull));
-    for (int k = warp; k < kRows; k += kWarps) {
-        const double* row = sg.group_partial + (size_t)k * sg.group_stride;
-        double a = 0.0;
-        for (int q = lane; q < n_groups; q += 32) a = a + __ldcg(row + q);
-        a = warp_sum_all(a);
-        if (lane == 0) pub[k] = a;
-    }
-    __threadfence();
-    __syncthreads();
-    __threadfence_system();
-    if ((int)threadIdx.x < x.world) sgx_st_release_sys(sgx_flags(x.block[threadIdx.x]) + x.rank, epoch);
-    if (threadIdx.x == 0) {
-        sg.group_ticket[sg.group_stride] = 0u;
-        x.ctl[0] = epoch;
-    }
-}
-
-template <int kThreads, int LT, int kMinBlocks = 0>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) cell_step_sg_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                                            CellSgWork sg) {
-    cell_step_sg_body<kThreads, LT, false>(t, p, s, mode, next, sg, HaloInline{}, ShExchange{});
-}
-template <int kThreads, int LT>
-__global__ void __launch_bounds__(kThreads) cell_step_sgx_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next, CellSgWork sg,
-                                                                 HaloInline halo, ShExchange x) {
-    cell_step_sg_body<kThreads, LT, true>(t, p, s, mode, next, sg, halo, x);
 }
 
 template <int kThreads>
@@ -661,7 +417,7 @@ __global__ void scatter_x_kernel(int n, const int* __restrict__ perm, const doub
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2 v = dst[i];
-    v.x = src ? src[perm[i]] : 0.0;
+    v.x = src ? src[perm ? perm[i] : i] : 0.0;          // perm == nullptr: the source is already in device order
     if (zero_y) v.y = 0.0;
     dst[i] = v;
 }
@@ -669,7 +425,7 @@ __global__ void scatter_history_kernel(int n, const int* __restrict__ perm, cons
                                        double* h2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const size_t o = (size_t)perm[i] * 3;
+    const size_t o = (size_t)(perm ? perm[i] : i) * 3;
     lvl0[i] = src3 ? src3[o] : 0.0;
     h1[i] = src3 ? src3[o + 1] : 0.0;
     h2[i] = src3 ? src3[o + 2] : 0.0;
@@ -678,26 +434,26 @@ __global__ void gather_component_kernel(int n, const int* __restrict__ perm, con
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double2 v = src[i];
-    dst[perm[i]] = component ? v.y : v.x;
+    dst[perm ? perm[i] : i] = component ? v.y : v.x;    // perm == nullptr: compact, device order
 }
 __global__ void gather_pair_kernel(int n, const int* __restrict__ perm, const double2* __restrict__ src, double* dst2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double2 v = src[i];
-    const size_t o = (size_t)perm[i] * 2;
+    const size_t o = (size_t)(perm ? perm[i] : i) * 2;
     dst2[o] = v.x;
     dst2[o + 1] = v.y;
 }
 __global__ void gather_scalar_kernel(int n, const int* __restrict__ perm, const double* __restrict__ src, double* dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[perm[i]] = src[i];
+    if (i < n) dst[perm ? perm[i] : i] = src[i];
 }
 __global__ void gather_history_kernel(int n, const int* __restrict__ perm, const double* __restrict__ lvl0, const double* __restrict__ h1,
                                       const double* __restrict__ h2, int which0, double* dst3) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double a1 = h1[i], a2 = h2[i];
-    const size_t o = (size_t)perm[i] * 3;
+    const size_t o = (size_t)(perm ? perm[i] : i) * 3;
     dst3[o] = which0 == 0 ? lvl0[i] : (which0 == 1 ? a1 : a2);
     dst3[o + 1] = a1;
     dst3[o + 2] = a2;
@@ -771,78 +527,15 @@ void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s,
     });
 }
 
-int resident_cell_ctas(bool capped) {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    return sms * (capped ? 8 : 6);
-}
-
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                       int flags, int block_threads, const HaloInline* halo, cudaStream_t stream) {
     HaloInline none;
     none.n_bnd = 0;
     none.wait_from = 0x7fffffff;
-    if (block_threads == kCellOccupancyVariant) {        // 128 threads, registers capped for 8 CTAs per SM
-        cell_step_kernel<128, 8><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
-        return;
-    }
-    if (block_threads == kCellPrefetchVariant || block_threads == kCellPrefetchOccupancyVariant) {
-        // rows of the tile one GPU-full of CTAs ahead travel into L2 while this CTA works (arrays are padded to whole 128-cell tiles)
-        const bool capped = block_threads == kCellPrefetchOccupancyVariant;
-        const int ahead = resident_cell_ctas(capped), f = (flags & 0xff) | (ahead << 8);
-        if (capped) cell_step_kernel<128, 8, true><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, f, halo ? *halo : none);
-        else cell_step_kernel<128, 0, true><<<(t.n_active + 127) / 128, 128, 0, stream>>>(t, p, s, mode, next, f, halo ? *halo : none);
-        return;
-    }
     dispatch_threads(block_threads, [&](auto bt) {
         constexpr int kT = decltype(bt)::value;
         cell_step_kernel<kT><<<(t.n_active + kT - 1) / kT, kT, 0, stream>>>(t, p, s, mode, next, flags, halo ? *halo : none);
     });
-}
-cudaError_t cell_sg_configure() {          // once per device (see sh_configure)
-    static std::mutex once;
-    static bool done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(once);
-    if (done[dev & 63]) return cudaSuccess;
-    double rec[kShRecDoubles];
-    sh_recurrence_table(rec);
-    const cudaError_t e = cudaMemcpyToSymbol(c_sg_rec, rec, sizeof rec);
-    if (e == cudaSuccess) done[dev & 63] = true;
-    return e;
-}
-int cell_sg_ctas(int n_active) { return (n_active + kCellSgThreads - 1) / kCellSgThreads; }
-bool cell_sg_supports(int l_max) { return l_max >= 2 && l_max <= kCellSgMaxDegree; }
-void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
-                         bool cap_registers, cudaStream_t stream) {
-    const int grid = cell_sg_ctas(t.n_active);
-    if (cap_registers) {                                  // 64 registers: 8 CTAs per SM instead of 5
-        switch (sg.l_max) {
-            case 2: cell_step_sg_kernel<kCellSgThreads, 2, 8><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
-            case 3: cell_step_sg_kernel<kCellSgThreads, 3, 8><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
-            default: cell_step_sg_kernel<kCellSgThreads, 4, 8><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
-        }
-        return;
-    }
-    switch (sg.l_max) {
-        case 2: cell_step_sg_kernel<kCellSgThreads, 2><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
-        case 3: cell_step_sg_kernel<kCellSgThreads, 3><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
-        default: cell_step_sg_kernel<kCellSgThreads, 4><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg); break;
-    }
-}
-void launch_cell_step_sgx(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
-                          const HaloInline& halo, const ShExchange& x, cudaStream_t stream) {
-    const int grid = cell_sg_ctas(t.n_active);
-    switch (sg.l_max) {
-        case 2: cell_step_sgx_kernel<kCellSgThreads, 2><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg, halo, x); break;
-        case 3: cell_step_sgx_kernel<kCellSgThreads, 3><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg, halo, x); break;
-        default: cell_step_sgx_kernel<kCellSgThreads, 4><<<grid, kCellSgThreads, 0, stream>>>(t, p, s, mode, next, sg, halo, x); break;
-    }
 }
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream) {
     halo_drain_kernel<<<1, 32, 0, stream>>>(wait_v, ctl);

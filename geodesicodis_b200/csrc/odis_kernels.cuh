@@ -111,74 +111,11 @@ struct CellState {
 // cell update flags
 enum CellFlags : int { CELL_UPDATE_ETA = 1, CELL_UPDATE_U = 2 };
 
-// ---- fused step (odis_kernels_fused.cu): cell update of the previous step + edge update in one kernel ----
-struct FusedTables {
-    EdgeTables e;
-    const unsigned long long* cmap;   // [stride] per edge: for its two cells, which of {own, stencil slot 1..10} is the cell's
-                                      // m-th edge in ascending reference id (4 bits, 15 = none) + outer-cell sign bit,
-                                      // 6 entries x 5 bits per cell; bits 60/61: this edge stores cell 0 / cell 1
-    const double* area;               // [cell_stride]
-    const double* trig;               // [8][cell_stride]
-    const double* trig_sq;            // [2][cell_stride]
-    int cell_stride;
-};
-struct FusedState {
-    const double2* vl_in;
-    double2* vl_out;
-    const double2* eu_in;             // {eta^{n-1}, U(t_n+dt)} (eta^n already when update_eta == 0)
-    double2* eu_out;                  // {eta^n, U(t_{n+1}+dt)}
-    double* h1;                       // edge tendency history, updated in place as in edge_step
-    double* h2;
-    const double* ch1;                // cell tendency history levels 1, 2
-    const double* ch2;
-    double* chw;                      // new cell tendency
-    double* block_partial;            // [grid] one energy partial per CTA (summed in index order by the last CTA to finish)
-    unsigned int* ticket;
-    double* energy_out;
-};
-cudaError_t launch_step_fused(const FusedTables& t, const Physics& p, const FusedState& s, int mode_edge, int mode_cell, int update_eta,
-                              const StepScalars& next, cudaStream_t stream);
-
 void launch_edge_step(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, int block_threads,
                       cudaStream_t stream);
-// flags: CellFlags (update eta and/or the potential). block_threads: 128 (default), 256, 512, or kCellOccupancyVariant (128 threads with
-// the register count capped at 64 for 50 % occupancy; opt-in, odis_params.reserved[0] bit 6)
-constexpr int kCellOccupancyVariant = -128;
-// 128 threads + the streamed rows of the tile one GPU-full of CTAs ahead prefetched into L2 (default registers / capped at 64)
-constexpr int kCellPrefetchVariant = -129;
-constexpr int kCellPrefetchOccupancyVariant = -130;
+// flags: CellFlags (update eta and/or the potential). block_threads: 128 (default), 256, 512
 void launch_cell_step(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                       int flags, int block_threads, const HaloInline* halo, cudaStream_t stream);
-// Opt-in variant for runs with the self-gravity term (odis_params.reserved[0] bit 4): the cell update also accumulates the
-// harmonic analysis b = Y eta^{n+1} of the cells [0, n_fit) (matrix-free basis, degrees 2..kCellSgMaxDegree), leaving sums over
-// groups of kCellSgGroup consecutive CTAs; launch_sh_solve_synthesis (odis_sh.cuh) finishes the sum, solves and adds the term
-// to the potential: 3 launches per step instead of 5. Unpartitioned solvers.
-constexpr int kCellSgThreads = 128;
-constexpr int kCellSgGroup = 32;
-constexpr int kCellSgMaxDegree = 4;
-struct CellSgWork {
-    int l_max;
-    int n_fit;                      // cells [0, n_fit) enter the least-squares fit
-    double* cta_partial;            // [rows][cta_stride]
-    int cta_stride;                 // >= cell_sg_ctas(n_active)
-    double* group_partial;          // [rows][group_stride]
-    int group_stride;               // >= ceil(cell_sg_ctas / kCellSgGroup)
-    unsigned int* group_ticket;     // [group_stride], zero before the first launch (each launch leaves it zero again)
-    int prefetch_ahead;             // > 0: prefetch the rows of the tile this many CTAs ahead into L2 (CTAs resident on the GPU); 0: off
-};
-int resident_cell_ctas(bool capped);   // 128-thread cell-update CTAs resident on the current GPU (SMs x 6, or x 8 with the register cap)
-cudaError_t cell_sg_configure();    // recurrence coefficients -> constant memory (once per device, before any capture)
-int cell_sg_ctas(int n_active);
-bool cell_sg_supports(int l_max);
-void launch_cell_step_sg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
-                         bool cap_registers, cudaStream_t stream);
-// The same on a partitioned solver (t.n_active = own + ghost cells, sg.n_fit = own cells): boundary CTAs wait for the neighbours' halo push,
-// and the last group of CTAs to finish publishes this rank's harmonic sums for the in-kernel all-reduce that
-// launch_sh_allsolve_synthesis (odis_sh.cuh) completes. sg.group_ticket needs one more counter at [group_stride].
-struct HaloInline;
-struct ShExchange;
-void launch_cell_step_sgx(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, const CellSgWork& sg,
-                          const HaloInline& halo, const ShExchange& x, cudaStream_t stream);
 // spins (bounded by kHaloSpinCycles) until every neighbour's flag has reached ctl->epoch[0]: all pushes of the
 // exchanges this rank took part in have landed
 void launch_halo_drain(const HaloWait& wait_v, StepCtl* ctl, cudaStream_t stream);
@@ -197,8 +134,42 @@ int pipe_tile();
 cudaError_t pipe_configure();
 cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, const HaloInline* halo,
                                   cudaStream_t stream);
+// Staged cell update (the default with the staged edge kernel): persistent CTAs, bit-identical to launch_cell_step with
+// CELL_UPDATE_ETA | CELL_UPDATE_U. halo != nullptr: partitioned solver (the last tiles wait for the neighbours' push, ghost values are
+// read past L1). sg != nullptr: the harmonic analysis b = Y eta^{n+1} of the cells [0, sg->n_fit) is accumulated on the way (degrees
+// 2..4, matrix-free basis) and left in sg->b_out — or, partitioned (x != nullptr), published for the all-reduce through peer memory
+// that launch_sh_bsolve_synthesis (odis_sh.cuh) completes.
+constexpr int kCellMaxRows = 10;
+struct CellRows {             // which trig rows a launch stages, and where the potential / the harmonic basis find their inputs (bit fields:
+    int n;                    // the kernel indexes them with compile-time shifts)        rows staged
+    int n_pot;                // inputs of the potential
+    unsigned long long src;   // 4 bits per stage row k: its table row, 0..7 CellTables.trig, 8..9 CellTables.trig_sq
+    unsigned long long pot;   // 5 bits per input k of the potential: stage row; bit 4 set: the square of that row's value
+    unsigned basis;           // 4 bits each: stage rows of cos lat, sin lat, cos lon, sin lon
+};
+CellRows cell_rows_for(int potential, bool with_basis);
+struct CellSgAccum {
+    int l_max;                // 2..4 (0: off)
+    int n_fit;                // cells [0, n_fit) enter the least-squares fit
+    double* cta_partial;      // [rows][cta_stride] per-CTA sums
+    int cta_stride;           // >= cell_pipe_grid(n_active)
+    double* b_out;            // [rows] this rank's sums (unpartitioned: the final b; merged + partitioned: the all-reduced b, for read-back)
+    unsigned int* ticket;     // zero before the first launch (every launch leaves it zero again)
+    // merged kernel (cell_pipe_merged()): behind a grid-wide barrier every CTA solves s = g factor (Ginv b) and adds the term to U of
+    // the tiles it has just updated, so that the separate solve + synthesis launch is not needed (2 launches per step)
+    int merged;
+    const double* ginv;       // [rows][rows]
+    const double* factor;     // [rows]
+    double g;
+    double* s_out;            // [rows] for read-back
+    unsigned int* bar;        // [2] arrival count, generation (zero before the first launch)
+};
+struct ShExchange;
+bool cell_pipe_supports_sg(int l_max);
+bool cell_pipe_merged();              // the merged cell + solve + synthesis kernel is in use (cooperative launch; see odis_kernels_pipe.cu)
+int cell_pipe_grid(int n_cells);      // upper bound of the CTAs a launch over n_cells cells uses
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
-                                  cudaStream_t stream);
+                                  const HaloInline* halo, const CellSgAccum* sg, const ShExchange* x, cudaStream_t stream);
 // Opt-in: the staged edge kernel with narrow stencil ids. sid16 = [tiles][10][128] 16-bit offsets from the edge's own id (0 for an
 // empty slot), tile_wide[tile] != 0 where an offset does not fit (that tile is read from EdgeTables.sid as usual). Bit-identical results.
 // edge_ids16_fits: false when a CTA would hold more tiles than its flag buffer (the launcher then returns cudaErrorInvalidValue).

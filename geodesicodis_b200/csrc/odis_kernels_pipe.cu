@@ -17,6 +17,10 @@
 // A tile is 128 consecutive edges (or cells); table rows are SoA with a stride padded to 128, so
 // every row segment of a tile is one contiguous, 16-byte aligned bulk copy.
 #include "odis_kernels.cuh"
+#include "odis_sh.cuh"
+
+#include <cstdlib>
+#include <mutex>
 
 namespace odis {
 namespace {
@@ -25,6 +29,29 @@ constexpr int kTile = 128;            // edges (cells) per tile = one consumer g
 constexpr int kGroups = 2;            // consumer groups per CTA
 constexpr int kStages = 4;            // tiles in flight per CTA
 constexpr int kPipeThreads = 32 + kGroups * kTile;
+
+// Launch of a per-step kernel. cooperative: the grid carries a grid-wide barrier, so all of its CTAs must be resident together — the
+// cooperative attribute makes the driver schedule the grid as a whole (two such grids of different streams never interleave
+// partially) and refuse a grid that cannot fit. (Programmatic dependent launch between the step's kernels was measured on a B200 in
+// round 2: no gain under CUDA-graph replay, so it is not used.)
+template <typename T> struct launch_identity { using type = T; };
+template <typename... KArgs>
+static cudaError_t launch_step_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool cooperative,
+                                      typename launch_identity<KArgs>::type... args) {
+#ifdef __CUDACC__
+    if (cooperative) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, args...);
+    }
+#endif
+    kernel<<<grid, block, smem, stream>>>(args...);
+    return cudaGetLastError();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -60,6 +87,12 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+// the same without the evict-first hint: rows that the next kernel reads again (the harmonic basis inputs) should stay in L2
+__device__ __forceinline__ void bulk_g2s_keep(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ double2 ld_gather(const double2* p) {
@@ -290,21 +323,32 @@ __global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe16_kernel(EdgeT
 }
 
 // ---------------------------------------------------------------- cell step ----
+// Persistent, warp-specialised cell update: one producer lane streams the per-cell rows of the next tiles into shared memory with
+// cp.async.bulk (kS stages), kG consumer groups of 128 threads each take whole tiles. A consumer copies its table values out of the
+// stage into registers and releases the stage BEFORE it issues the six {v,l} gathers, so the producer refills while the gathers are in
+// flight. Same arithmetic, operation for operation, as cell_step_kernel (odis_kernels.cu): bit-identical eta and tendencies.
+//
+// Harmonic analysis folded in (LSG >= 2; self-gravity term): every consumer thread keeps the (LSG+1)^2 sums
+// b_k += Y_k(i) eta_i^{n+1} of ITS cells in registers across all of its tiles (basis values rebuilt from cos/sin of latitude and
+// longitude by the recurrences of sh_analysis_mf_kernel, odis_sh.cu) and the CTA reduces ONCE at the end: butterfly per warp, warps in
+// order, one partial per row and CTA; the last CTA to finish (ticket) adds the CTAs' partials in CTA order and leaves this rank's b.
+// Every level has a fixed order, so the sums do not depend on scheduling. Partitioned solvers: that last CTA also publishes the rank's
+// sums for the all-reduce through peer memory which the synthesis kernel completes (protocol of sh_reduce_publish_kernel, odis_sh.cu).
 struct __align__(16) CellStage {
-    int eid[kCellEdges][kTile];      // 3072 B
-    double area[kTile];              // 1024 B
-    double2 eu[kTile];               // 2048 B
-    double h1[kTile];                // 1024 B
-    double h2[kTile];                // 1024 B
-    double trig[8][kTile];           // 8192 B   rows used depend on the potential
+    int eid[kCellEdges][kTile];      //  3072 B
+    double area[kTile];              //  1024 B
+    double2 eu[kTile];               //  2048 B
+    double h1[kTile];                //  1024 B
+    double h2[kTile];                //  1024 B
+    double trig[kCellMaxRows][kTile];  // 10240 B   rows staged depend on the potential (+ the four basis rows with LSG)
 };
-constexpr uint32_t kCellStageBytes = sizeof(CellStage);
+constexpr uint32_t kCellFixedBytes = kCellEdges * kTile * 4 + kTile * 8 + kTile * 16 + 2 * kTile * 8;
 
-struct TrigRows {                    // which rows of CellTables.trig / trig_sq a potential reads (tidalPotentials.cpp:80-172)
-    int n;
+struct TrigRows {                    // which rows of CellTables.trig / trig_sq a potential reads (tidalPotentials.cpp:80-172), in the
+    int n;                           // order tidal_potential_in takes them
     int row[8];                      // 0..7 = trig rows, 8 = cos^2 lat, 9 = sin^2 lat
 };
-__host__ __device__ inline TrigRows trig_rows_for(int potential) {
+inline TrigRows trig_rows_for(int potential) {
     switch (potential) {
         case P_ECC: return TrigRows{4, {8, 9, 6, 7, 0, 0, 0, 0}};
         case P_OBLIQ: return TrigRows{2, {5, 2, 0, 0, 0, 0, 0, 0}};
@@ -315,28 +359,30 @@ __host__ __device__ inline TrigRows trig_rows_for(int potential) {
     }
 }
 
-__device__ __forceinline__ double tidal_potential_rows(const Physics& p, const StepScalars& m, const double (*T)[kTile], int tl) {
+// tidal potential from its inputs in trig_rows_for() order; expression shapes of tidalPotentials.cpp:80-172 (= tidal_potential(),
+// odis_kernels.cu)
+__device__ __forceinline__ double tidal_potential_in(const Physics& p, const StepScalars& m, const double* in) {
     switch (p.potential) {
         case P_ECC: {
-            const double cosSq = T[0][tl], sinSq = T[1][tl], cos2Lon = T[2][tl], sin2Lon = T[3][tl];
+            const double cosSq = in[0], sinSq = in[1], cos2Lon = in[2], sin2Lon = in[3];
             return p.factor * ((1. - 3. * sinSq) * m.cosM + cosSq * (3. * m.cosM * cos2Lon + 4. * m.sinM * sin2Lon));
         }
         case P_OBLIQ: {
-            const double sin2Lat = T[0][tl], cosLon = T[1][tl];
+            const double sin2Lat = in[0], cosLon = in[1];
             return p.factor * m.cosM * sin2Lat * cosLon;
         }
         case P_OBLIQ_WEST: {
-            const double cosLat = T[0][tl], sinLat = T[1][tl], cosLon = T[2][tl], sinLon = T[3][tl];
+            const double cosLat = in[0], sinLat = in[1], cosLon = in[2], sinLon = in[3];
             return 3 * p.factor * sinLat * cosLat * (cosLon * m.cosM - sinLon * m.sinM);
         }
         case P_FULL: {
-            const double cosSq = T[0][tl], sinSq = T[1][tl], cos2Lon = T[2][tl], sin2Lon = T[3][tl], sin2Lat = T[4][tl], cosLon = T[5][tl];
+            const double cosSq = in[0], sinSq = in[1], cos2Lon = in[2], sin2Lon = in[3], sin2Lat = in[4], cosLon = in[5];
             return p.factor * ((1 - 3 * sinSq) * m.cosM + cosSq * (3 * m.cosM * cos2Lon + 4 * m.sinM * sin2Lon)) +
                    p.factor2 * m.cosM * sin2Lat * cosLon;
         }
         case P_FULL2: {
-            const double cosLat = T[0][tl], sinLat = T[1][tl], cosLon = T[2][tl], sinLon = T[3][tl], cos2Lat = T[4][tl], cos2Lon = T[5][tl],
-                         sin2Lon = T[6][tl], cosSq = T[7][tl];
+            const double cosLat = in[0], sinLat = in[1], cosLon = in[2], sinLon = in[3], cos2Lat = in[4], cos2Lon = in[5],
+                         sin2Lon = in[6], cosSq = in[7];
             const double ecc = p.ecc, obl = p.obl;
             double T1, T2, T3;
             T1 = 3. * ecc * (4. - 7. * obl * obl) * m.cosM + 6 * (obl * obl + ecc * ecc * (3 - 7 * obl * obl)) * m.cos2M;
@@ -355,50 +401,135 @@ __device__ __forceinline__ double tidal_potential_rows(const Physics& p, const S
     }
 }
 
-__global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
-                                                                          int n_tiles) {
+// recurrence coefficients of the normalised Legendre functions (layout of sh_recurrence_table()), this translation unit's copy
+__constant__ double c_cell_rec[kShRecDoubles];
+struct CellRec {
+    __device__ __forceinline__ double a(int m, int l) const { return c_cell_rec[l * kShRecStride + m]; }
+    __device__ __forceinline__ double b(int m, int l) const { return c_cell_rec[kShRecStride * kShRecStride + l * kShRecStride + m]; }
+    __device__ __forceinline__ double sect(int m) const { return c_cell_rec[2 * kShRecStride * kShRecStride + m]; }
+    __device__ __forceinline__ double first(int m) const { return c_cell_rec[2 * kShRecStride * kShRecStride + kShRecStride + m]; }
+};
+__device__ __forceinline__ double warp_sum_all(double x) {      // butterfly: fixed association, every lane gets the sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double2 ld_gather_cg(const double2* p) {     // ghost slots are written by other GPUs while the kernel runs
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+// spin (bounded) until all neighbours have published the exchange ctl->epoch[0] (see HaloInline)
+__device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
+    const unsigned long long ev = ((volatile unsigned long long*)ctl->epoch)[0];
+    const long long t0 = clock64();
+    bool late = false;
+    for (int k = 0; k < w.n_peers; k++) {
+        unsigned long long seen;
+        const unsigned long long* fv = w.flag[k];
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fv) : "memory");
+        } while (seen < ev && clock64() - t0 < kHaloSpinCycles);
+        late |= seen < ev;
+    }
+    if (late) ctl->pad = 1ull;      // a neighbour never arrived: reported by the host (ODIS_ERR_STATE), no hang
+}
+__device__ __forceinline__ unsigned long long* cx_flags(unsigned char* block) { return reinterpret_cast<unsigned long long*>(block); }
+__device__ __forceinline__ double* cx_pub(unsigned char* block, int parity) {
+    return reinterpret_cast<double*>(block + kShMaxWorld * sizeof(unsigned long long)) + (size_t)parity * kShXRows;
+}
+
+// the synthesis of one cell: sum over degrees 2..LT of s_k Y_k (recurrences of sh_synthesis_mf_kernel, odis_sh.cu)
+template <int LT>
+__device__ __forceinline__ double cell_synthesis(const double* ssh, double u, double z, double c1, double s1) {
+    const CellRec rc;
+    double cm = 1.0, sn = 0.0, pmm = 1.0, acc = 0.0;
+#pragma unroll
+    for (int m = 0; m <= LT; m++) {
+        if (m > 0) {
+            const double cn = __fma_rn(cm, c1, -(sn * s1));
+            sn = __fma_rn(sn, c1, cm * s1);
+            cm = cn;
+            pmm = rc.sect(m) * u * pmm;
+        }
+        double p1 = pmm, p2 = 0.0;
+#pragma unroll
+        for (int l = m; l <= LT; l++) {
+            if (l > m) {
+                const double a = l == m + 1 ? rc.first(m) : rc.a(m, l);
+                const double b = l == m + 1 ? 0.0 : rc.b(m, l);
+                const double pn = a * __fma_rn(z, p1, -(b * p2));
+                p2 = p1; p1 = pn;
+            }
+            if (l >= 2) {
+                const int row = l * l + (m ? 2 * m - 1 : 0);
+                const double q = m ? __fma_rn(cm, ssh[row], sn * ssh[row + 1]) : ssh[row];
+                acc = __fma_rn(p1, q, acc);
+            }
+        }
+    }
+    return acc;
+}
+
+// Grid-wide barrier of the merged kernel (cooperative launch: every CTA is resident). bar[0] counts arrivals, bar[1] is the
+// generation; the caller is the CTA's one arriving thread. Returns true in the LAST CTA to arrive, which must call
+// grid_barrier_release afterwards; the others have waited (bounded) for that release when they return.
+__device__ __forceinline__ bool grid_barrier_arrive(unsigned int* bar, unsigned int gen0, StepCtl* ctl) {
+    __threadfence();
+    if (atomicAdd(bar, 1u) == gridDim.x - 1u) return true;
+    const long long t0 = clock64();
+    unsigned int gen;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    } while (gen == gen0 && clock64() - t0 < kHaloSpinCycles);
+    if (gen == gen0 && ctl != nullptr) ctl->pad = 1ull;      // reported by the host (ODIS_ERR_STATE), no hang
+    return false;
+}
+__device__ __forceinline__ void grid_barrier_release(unsigned int* bar, unsigned int gen0) {
+    bar[0] = 0u;
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen0 + 1u) : "memory");
+}
+
+template <int kG, int kS, int LSG, bool kPart, bool kMerged>
+__device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const Physics& p, const CellState& s, int mode, StepScalars next,
+                                                    int n_tiles, const CellRows& rows, const HaloInline& halo, const CellSgAccum& sg,
+                                                    const ShExchange& x) {
+    constexpr int kThreads = 32 + kG * kTile;
+    constexpr int kConsumerWarps = kG * kTile / 32;
+    constexpr int kRows = LSG > 0 ? (LSG + 1) * (LSG + 1) : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CellStage* stages = reinterpret_cast<CellStage*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(CellStage));
-    uint64_t* empty = full + kStages;
-    __shared__ double red[kPipeThreads / 32];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kS * sizeof(CellStage));
+    uint64_t* empty = full + kS;
+    __shared__ StepScalars nx;                               // time factors of the potential: operands from shared memory, not 12 registers
+    __shared__ double ginv_s[kMerged ? kRows * kRows : 1];
+    __shared__ double fac_s[kMerged ? kRows : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; i++) {
+        for (int i = 0; i < kS; i++) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, kTile / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        nx = s.next_dev != nullptr ? *s.next_dev : next;     // graph replay: the factors were left by the edge kernel (StepCtl::cur)
+    }
+    if (kMerged) {                                           // fixed operator of the harmonic solve: in shared memory before it is needed
+        for (int k = threadIdx.x; k < kRows * kRows; k += kThreads) ginv_s[k] = sg.ginv[k];
+        for (int k = threadIdx.x; k < kRows; k += kThreads) fac_s[k] = sg.factor[k];
     }
     __syncthreads();
-    // one extra CTA (the last) only finishes the edge kernel's energy sum; the others pipeline tiles
-    if (blockIdx.x == gridDim.x - 1) {
-        if (s.energy_out == nullptr) return;
-        double acc = 0.0;
-        for (int i = threadIdx.x; i < s.n_energy_partials; i += kPipeThreads) acc += s.energy_partial[i];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if (lane == 0) red[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < kPipeThreads / 32; w++) tot += red[w];
-            *s.energy_out = tot;
-        }
-        return;
-    }
-    const int n_workers = (int)gridDim.x - 1;
     const size_t S = (size_t)t.n_cells;                     // SoA stride (padded to the tile size by the host)
-    const TrigRows rows = trig_rows_for(p.potential);
-    const uint32_t stage_bytes = (uint32_t)(kCellEdges * kTile * 4 + kTile * 8 + kTile * 16 + 2 * kTile * 8 + rows.n * kTile * 8);
-    const int my_tiles = (n_tiles - (int)blockIdx.x + n_workers - 1) / n_workers;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
+            const uint32_t stage_bytes = kCellFixedBytes + (uint32_t)rows.n * kTile * 8;
             for (int i = 0; i < my_tiles; i++) {
-                const int st = i % kStages;
-                if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
+                const int st = i % kS;
+                if (i >= kS) mbar_wait(empty + st, ((i / kS) - 1) & 1);
                 CellStage* d = stages + st;
-                const size_t c0 = ((size_t)blockIdx.x + (size_t)i * n_workers) * kTile;
+                const size_t c0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile;
                 mbar_expect_tx(full + st, stage_bytes);
 #pragma unroll
                 for (int j = 0; j < kCellEdges; j++) bulk_g2s(d->eid[j], t.eid + j * S + c0, kTile * 4, full + st, pol);
@@ -406,52 +537,239 @@ __global__ void __launch_bounds__(kPipeThreads, 2) cell_step_pipe_kernel(CellTab
                 bulk_g2s(d->eu, s.eu_in + c0, kTile * 16, full + st, pol);
                 bulk_g2s(d->h1, s.h1 + c0, kTile * 8, full + st, pol);
                 bulk_g2s(d->h2, s.h2 + c0, kTile * 8, full + st, pol);
-                for (int k = 0; k < rows.n; k++) {
-                    const int r = rows.row[k];
-                    const double* src = r < 8 ? t.trig + (size_t)r * S + c0 : t.trig_sq + (size_t)(r - 8) * S + c0;
-                    bulk_g2s(d->trig[k], src, kTile * 8, full + st, pol);
+#pragma unroll
+                for (int k = 0; k < kCellMaxRows; k++) {
+                    if (k < rows.n) {
+                        const int r = (int)(rows.src >> (4 * k)) & 15;
+                        const double* src = r < 8 ? t.trig + (size_t)r * S + c0 : t.trig_sq + (size_t)(r - 8) * S + c0;
+                        // the four basis rows (stage rows 0..3 with LSG) are read again by the synthesis launch that follows
+                        if (LSG > 0 && k < 4) bulk_g2s_keep(d->trig[k], src, kTile * 8, full + st);
+                        else bulk_g2s(d->trig[k], src, kTile * 8, full + st, pol);
+                    }
                 }
             }
         }
         return;
     }
+    // ---- consumers: group g takes this CTA's tiles g, g+kG, ... ----
     const int g = (warp - 1) / (kTile / 32);
     const int tl = (int)threadIdx.x - 32 - g * kTile;
-    if (s.next_dev != nullptr) next = *s.next_dev;       // graph replay: time factors left by the edge kernel
-    for (int i = g; i < my_tiles; i += kGroups) {
-        const int st = i % kStages;
-        const CellStage* d = stages + st;
-        const int c = (int)(((size_t)blockIdx.x + (size_t)i * n_workers) * kTile) + tl;
-        mbar_wait(full + st, (i / kStages) & 1);
-        if (c < t.n_active) {
-            int packed[kCellEdges];
-            double2 ed[kCellEdges];
+    double acc[kRows];
 #pragma unroll
-            for (int j = 0; j < kCellEdges; j++) {
-                packed[j] = d->eid[j][tl];
-                ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+    for (int k = 0; k < kRows; k++) acc[k] = 0.0;
+    for (int i = g; i < my_tiles; i += kG) {
+        const int st = i % kS;
+        const CellStage* d = stages + st;
+        const int c0 = (int)(((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile);
+        const int c = c0 + tl;
+        // partitioned runs: the last tiles hold the cells that read ghost edges (own boundary cells, then the ghost cells)
+        const bool bnd_tile = kPart && (c0 + kTile > halo.wait_from);
+        mbar_wait(full + st, (i / kS) & 1);
+        int packed[kCellEdges];
+#pragma unroll
+        for (int j = 0; j < kCellEdges; j++) packed[j] = d->eid[j][tl];
+        if (bnd_tile) {
+            if (lane == 0) halo_wait_all(halo.wait_v, halo.ctl);
+            __syncwarp();
+        }
+        // the six {v,l} gathers go out first; the rest of the stage is read (and the stage released) while they are in flight
+        double2 ed[kCellEdges];
+        if (!bnd_tile) {
+#pragma unroll
+            for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+        } else {
+#pragma unroll
+            for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather_cg(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+        }
+        double2 stt = d->eu[tl];
+        const double area = d->area[tl], f1 = d->h1[tl], f2 = d->h2[tl];
+        if (p.potential != P_NONE) {
+            double in[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int slot = (int)(rows.pot >> (5 * k)) & 31;        // stage row of the potential's k-th input; bit 4: its square
+                const double v = (k < rows.n_pot) ? d->trig[slot & 15][tl] : 0.0;
+                in[k] = (slot & 16) ? v * v : v;                          // cos^2 / sin^2 lat from the basis rows (the product of mesh.cpp:2144-2145)
             }
-            double2 stt = d->eu[tl];
-            const double area = d->area[tl];
+            stt.y = tidal_potential_in(p, nx, in);
+        }
+        double bu = 0.0, bz = 0.0, bc1 = 0.0, bs1 = 0.0;
+        if (LSG > 0) {
+            bu = d->trig[rows.basis & 15][tl]; bz = d->trig[(rows.basis >> 4) & 15][tl];
+            bc1 = d->trig[(rows.basis >> 8) & 15][tl]; bs1 = d->trig[(rows.basis >> 12) & 15][tl];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);          // this warp no longer reads the stage
+        double e_fit = 0.0;
+        if (c < t.n_active) {
             double div = 0.0;                                                     // updateEta.cpp:39, mesh.cpp:3246
             const double ra = __drcp_rn(area);
 #pragma unroll
             for (int j = 0; j < kCellEdges; j++) {
-                if (packed[j] != -1) {
-                    const double ndir = (packed[j] < 0) ? 1.0 : -1.0;
+                if (packed[j] != -1) {                                            // the 12 pentagons have 5 edges
+                    const double ndir = (packed[j] < 0) ? 1.0 : -1.0;             // -dir: dir = -1 for the outer cell
                     const double coeff = exact_div(ndir * ed[j].y, area, ra);
                     div += (p.h * coeff) * ed[j].x;
                 }
             }
             const double f0 = div;
-            stt.x += ab3_increment(f0, d->h1[tl], d->h2[tl], p.dt, mode);
+            stt.x += ab3_increment(f0, f1, f2, p.dt, mode);
             s.hw[c] = f0;
-            if (p.potential != P_NONE) stt.y = tidal_potential_rows(p, next, d->trig, tl);
             s.eu_out[c] = stt;
+            if (c < sg.n_fit) e_fit = stt.x;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st);
+        if (LSG > 0) {
+            // this cell's share of b = Y eta^{n+1}; padded / unfitted cells carry e = 0 and finite (zero) basis inputs
+            const CellRec rc;
+            double cm = 1.0, sn = 0.0, pmm = 1.0;
+#pragma unroll
+            for (int m = 0; m <= LSG; m++) {
+                if (m > 0) {
+                    const double cn = __fma_rn(cm, bc1, -(sn * bs1));       // cos(m lon), sin(m lon) by rotation
+                    sn = __fma_rn(sn, bc1, cm * bs1);
+                    cm = cn;
+                    pmm = rc.sect(m) * bu * pmm;
+                }
+                const double ec = e_fit * cm, es = e_fit * sn;
+                double p1 = pmm, p2 = 0.0;
+#pragma unroll
+                for (int l = m; l <= LSG; l++) {
+                    if (l > m) {
+                        const double a = l == m + 1 ? rc.first(m) : rc.a(m, l);
+                        const double b = l == m + 1 ? 0.0 : rc.b(m, l);
+                        const double pn = a * __fma_rn(bz, p1, -(b * p2));
+                        p2 = p1; p1 = pn;
+                    }
+                    const int row = l * l + (m ? 2 * m - 1 : 0);
+                    acc[row] = __fma_rn(p1, ec, acc[row]);
+                    if (m > 0) acc[row + 1] = __fma_rn(p1, es, acc[row + 1]);
+                }
+            }
+        }
     }
+    if (LSG == 0) return;
+    // ---- the CTA's harmonic sums: once per CTA ----
+    __shared__ double red[kRows * kConsumerWarps];
+    __shared__ double bsh[kRows];
+    __shared__ double ssh[kRows];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int k = 0; k < kRows; k++) {
+        const double tot = warp_sum_all(acc[k]);
+        if (lane == 0) red[k * kConsumerWarps + (warp - 1)] = tot;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");      // consumers only (the producer warp has left)
+    const int ct = (int)threadIdx.x - 32;
+    unsigned int gen0 = 0u;
+    if (kMerged && ct == 0) gen0 = *(volatile unsigned int*)(sg.bar + 1);      // before this CTA arrives, so before anyone can release
+    if (ct < kRows) {
+        double a = red[ct * kConsumerWarps];
+#pragma unroll
+        for (int q = 1; q < kConsumerWarps; q++) a = a + red[ct * kConsumerWarps + q];
+        sg.cta_partial[(size_t)ct * sg.cta_stride + blockIdx.x] = a;
+    }
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+    if (ct == 0) is_last = kMerged ? grid_barrier_arrive(sg.bar, gen0, halo.ctl) : (atomicAdd(sg.ticket, 1u) == gridDim.x - 1);
+    asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+    unsigned long long epoch = 0ull;
+    if (kPart) epoch = x.ctl[0] + (is_last ? 1ull : 0ull);           // the last CTA publishes the next epoch (and records it below)
+    if (is_last) {
+        // the last CTA to arrive adds the CTAs' partials in CTA order: all of a lane's loads in flight together, then the butterfly
+        __threadfence();
+        double* bdst = kPart ? cx_pub(x.block[x.rank], (int)(epoch & 1ull)) : sg.b_out;
+        constexpr int kMaxPerLane = 10;                               // grid <= 2 x 148 CTAs (cell_pipe_grid)
+        for (int k = warp - 1; k < kRows; k += kConsumerWarps) {
+            const double* row = sg.cta_partial + (size_t)k * sg.cta_stride;
+            double v[kMaxPerLane];
+#pragma unroll
+            for (int q = 0; q < kMaxPerLane; q++) v[q] = (lane + 32 * q < (int)gridDim.x) ? __ldcg(row + lane + 32 * q) : 0.0;
+            double a = v[0];
+#pragma unroll
+            for (int q = 1; q < kMaxPerLane; q++) a = a + v[q];
+            for (int q = lane + 32 * kMaxPerLane; q < (int)gridDim.x; q += 32) a = a + __ldcg(row + q);
+            a = warp_sum_all(a);
+            if (lane == 0) bdst[k] = a;
+        }
+        if (!kMerged && ct == 0) *sg.ticket = 0u;
+        if (kPart) {
+            // publish this rank's sums: epoch flag into every rank's exchange block (system-scope release)
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+            __threadfence_system();
+            if (ct < x.world) {
+                unsigned long long* f = cx_flags(x.block[ct]) + x.rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+            }
+            if (ct == 0) x.ctl[0] = epoch;
+        }
+        if (kMerged) {
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+            if (ct == 0) grid_barrier_release(sg.bar, gen0);
+        }
+    }
+    if (!kMerged) return;
+    // ---- merged: every CTA is past the grid barrier, this rank's sums are complete. b (all ranks), solve, synthesis of the own tiles ----
+    if (kPart) {
+        if (!is_last) epoch = ((volatile unsigned long long*)x.ctl)[0];         // written by the last CTA before the release
+        if (ct < x.world) {
+            const unsigned long long* f = cx_flags(x.block[x.rank]) + ct;
+            const long long t0 = clock64();
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+            } while (seen < epoch && clock64() - t0 < kHaloSpinCycles);
+            if (seen < epoch) x.ctl[2] = 1ull;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+        if (ct < kRows) {
+            double a = 0.0;
+            for (int r = 0; r < x.world; r++) {               // rank order: the same bits on every rank and in every CTA
+                double v;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(cx_pub(x.block[r], (int)(epoch & 1ull)) + ct) : "memory");
+                a = a + v;
+            }
+            bsh[ct] = a;
+            if (blockIdx.x == 0) sg.b_out[ct] = a;
+        }
+    } else if (ct < kRows) bsh[ct] = __ldcg(sg.b_out + ct);
+    asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+    for (int j = warp - 1; j < kRows; j += kConsumerWarps) {   // s_j = (g factor_j) sum_k Ginv[j][k] b_k, order of solve_rows (odis_sh.cu)
+        const double f = fac_s[j];
+        double a = 0.0;
+        if (f != 0.0)
+            for (int k = lane; k < kRows; k += 32) a = a + ginv_s[j * kRows + k] * bsh[k];
+        a = warp_sum_all(a);
+        if (lane == 0) {
+            ssh[j] = (sg.g * f) * a;
+            if (blockIdx.x == 0) sg.s_out[j] = ssh[j];
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+    // U_i += sum_k s_k Y_k(i) on the tiles this thread updated above ({eta,U} as it wrote them; the basis rows from L2), two tiles per trip
+    const double* T = t.trig;
+    for (int i = g; i < my_tiles; i += 2 * kG) {
+        const int ca = (int)(((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile) + tl;
+        const int cb = (i + kG < my_tiles) ? (int)(((size_t)blockIdx.x + (size_t)(i + kG) * gridDim.x) * kTile) + tl : t.n_active;
+        const bool oka = ca < t.n_active, okb = cb < t.n_active;
+        const int xa = oka ? ca : 0, xb = okb ? cb : 0;
+        const double ua = T[xa], za = T[S + xa], c1a = T[2 * S + xa], s1a = T[3 * S + xa];
+        const double ub = T[xb], zb = T[S + xb], c1b = T[2 * S + xb], s1b = T[3 * S + xb];
+        const double2 sta = s.eu_out[xa], stb = s.eu_out[xb];
+        if (oka) s.eu_out[ca] = make_double2(sta.x, sta.y + cell_synthesis<LSG>(ssh, ua, za, c1a, s1a));
+        if (okb) s.eu_out[cb] = make_double2(stb.x, stb.y + cell_synthesis<LSG>(ssh, ub, zb, c1b, s1b));
+    }
+}
+
+// 288 threads (one producer warp, two consumer groups of 128), 4 stages, 2 CTAs per SM: the edge kernel's shape. Measured against a
+// deeper pipeline (6 stages: +1.3 us) and one wide CTA per SM (3 or 4 groups, 6-8 stages: +8.5 us) at 655,362 cells, round 2.
+constexpr int kCellGroups = 2, kCellStages = 4;
+template <int LSG, bool kPart, bool kMerged>
+__global__ void __launch_bounds__(32 + kCellGroups * kTile, 2) cell_step_pipe_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
+                                                                                      int n_tiles, CellRows rows, HaloInline halo, CellSgAccum sg,
+                                                                                      ShExchange x) {
+    cell_step_pipe_body<kCellGroups, kCellStages, LSG, kPart, kMerged>(t, p, s, mode, next, n_tiles, rows, halo, sg, x);
 }
 
 }  // namespace
@@ -469,12 +787,40 @@ static int num_sms() {
     return g_num_sms;
 }
 
+constexpr size_t kCellSmem = kCellStages * sizeof(CellStage) + 2 * kCellStages * sizeof(uint64_t);
+template <int LSG, bool kPart>
+static cudaError_t cell_pipe_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
+    if constexpr (LSG == 0) return e;
+    else {
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
+    }
+}
+
+// once per device, before any stream capture: dynamic shared-memory sizes of the staged kernels, recurrence coefficients of the
+// harmonic basis into this translation unit's constant memory (another solver on the same GPU may have kernels in flight that read
+// them, and the legacy stream of cudaMemcpyToSymbol does not wait for the solvers' non-blocking streams — hence once, not per solver)
 cudaError_t pipe_configure() {
+    static std::mutex once;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(once);
+    if (done[dev & 63]) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(edge_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t)));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(cell_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(kStages * sizeof(CellStage) + 2 * kStages * sizeof(uint64_t)));
+    if ((e = cell_pipe_attrs<0, false>()) != cudaSuccess || (e = cell_pipe_attrs<0, true>()) != cudaSuccess ||
+        (e = cell_pipe_attrs<2, false>()) != cudaSuccess || (e = cell_pipe_attrs<2, true>()) != cudaSuccess ||
+        (e = cell_pipe_attrs<3, false>()) != cudaSuccess || (e = cell_pipe_attrs<3, true>()) != cudaSuccess ||
+        (e = cell_pipe_attrs<4, false>()) != cudaSuccess || (e = cell_pipe_attrs<4, true>()) != cudaSuccess)
+        return e;
+    double rec[kShRecDoubles];
+    sh_recurrence_table(rec);
+    if ((e = cudaMemcpyToSymbol(c_cell_rec, rec, sizeof rec)) != cudaSuccess) return e;
+    done[dev & 63] = true;
+    return cudaSuccess;
 }
 
 cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const EdgeState& s, int mode, const HaloInline* halo,
@@ -493,8 +839,7 @@ cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const E
     const int grid = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
     HaloInline none;
     none.n_bnd = 0;
-    edge_step_pipe_kernel<<<grid, kPipeThreads, smem, stream>>>(t, p, s, mode, n_tiles, halo ? *halo : none);
-    return cudaGetLastError();
+    return launch_step_kernel(edge_step_pipe_kernel, grid, kPipeThreads, smem, stream, false, t, p, s, mode, n_tiles, halo ? *halo : none);
 }
 
 bool edge_ids16_fits(int n_edges) {
@@ -522,26 +867,99 @@ cudaError_t launch_edge_step_pipe16(const EdgeTables& t, const Physics& p, const
     const size_t smem = kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t) + (size_t)((per_cta + 15) / 16 * 16);
     HaloInline none;
     none.n_bnd = 0;
-    edge_step_pipe16_kernel<<<grid, kPipeThreads, smem, stream>>>(t, p, s, mode, n_tiles, halo ? *halo : none, sid16, tile_wide);
-    return cudaGetLastError();
+    return launch_step_kernel(edge_step_pipe16_kernel, grid, kPipeThreads, smem, stream, false, t, p, s, mode, n_tiles, halo ? *halo : none, sid16, tile_wide);
+}
+
+CellRows cell_rows_for(int potential, bool with_basis) {
+    CellRows r;
+    r.n = 0; r.n_pot = 0; r.src = 0ull; r.pot = 0ull; r.basis = 0u;
+    int src[kCellMaxRows];
+    auto slot_of = [&](int row) {
+        for (int k = 0; k < r.n; k++)
+            if (src[k] == row) return k;
+        src[r.n] = row;
+        return r.n++;
+    };
+    int basis[4] = {0, 0, 0, 0};
+    if (with_basis)
+        for (int k = 0; k < 4; k++) basis[k] = slot_of(k);            // cos lat, sin lat, cos lon, sin lon
+    const TrigRows pr = trig_rows_for(potential);
+    r.n_pot = pr.n;
+    for (int k = 0; k < pr.n; k++) {
+        const int row = pr.row[k];
+        // cos^2 / sin^2 of the latitude are the squares of rows 0 / 1 (built as cos(lat)*cos(lat), odis_engine.cu / mesh.cpp:2144-2145):
+        // with the basis rows staged anyway, the product is formed in the kernel instead of streaming 16 more bytes per cell
+        const int slot = (with_basis && row >= 8) ? (basis[row - 8] | 16) : slot_of(row);
+        r.pot |= (unsigned long long)slot << (5 * k);
+    }
+    for (int k = 0; k < r.n; k++) r.src |= (unsigned long long)src[k] << (4 * k);
+    for (int k = 0; k < 4; k++) r.basis |= (unsigned)basis[k] << (4 * k);
+    return r;
+}
+
+bool cell_pipe_supports_sg(int l_max) { return l_max >= 2 && l_max <= 4; }
+
+int cell_pipe_grid(int n_cells) {
+    const int n_tiles = (n_cells + kTile - 1) / kTile;
+    const int cap = 2 * num_sms();                          // the widest configuration (two CTAs per SM)
+    return n_tiles < cap ? (n_tiles > 0 ? n_tiles : 1) : cap;
+}
+
+// The merged kernel (cell update + grid barrier + solve + synthesis) needs every CTA resident: cooperative launch. Off in host
+// emulation builds (CTAs run one after another there) and with ODIS_B200_MERGED_SYNTH=0 (A/B timing).
+bool cell_pipe_merged() {
+#ifdef __CUDACC__
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("ODIS_B200_MERGED_SYNTH");
+        v = (e && std::atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+#else
+    return false;
+#endif
+}
+
+template <int LSG, bool kPart>
+static cudaError_t launch_cell_cfg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, int n_tiles,
+                                   const CellRows& rows, const HaloInline& halo, const CellSgAccum& sg, const ShExchange& x, cudaStream_t stream) {
+    const int cap = 2 * num_sms(), grid = n_tiles < cap ? n_tiles : cap;
+    if (LSG > 0 && sg.merged)
+        return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0)>, grid, 32 + kCellGroups * kTile, kCellSmem, stream, true, t, p, s, mode, next,
+                                  n_tiles, rows, halo, sg, x);
+    return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false>, grid, 32 + kCellGroups * kTile, kCellSmem, stream, false, t, p, s, mode, next, n_tiles,
+                              rows, halo, sg, x);
 }
 
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
-                                  cudaStream_t stream) {
-    static bool configured_dev[64] = {false};      // the opt-in shared-memory size is a per-device attribute
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    bool& configured = configured_dev[cur_dev & 63];
-    const size_t smem = kStages * sizeof(CellStage) + 2 * kStages * sizeof(uint64_t);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(cell_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+                                  const HaloInline* halo, const CellSgAccum* sg, const ShExchange* x, cudaStream_t stream) {
     const int n_tiles = (t.n_active + kTile - 1) / kTile;
-    const int workers = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
-    cell_step_pipe_kernel<<<workers + 1, kPipeThreads, smem, stream>>>(t, p, s, mode, next, n_tiles);
-    return cudaGetLastError();
+    if (n_tiles <= 0) return cudaSuccess;
+    const int l_sg = sg ? sg->l_max : 0;
+    if (l_sg != 0 && !cell_pipe_supports_sg(l_sg)) return cudaErrorInvalidValue;
+    const bool part = halo != nullptr;
+    if (part && l_sg != 0 && x == nullptr) return cudaErrorInvalidValue;
+    const CellRows rows = cell_rows_for(p.potential, l_sg != 0);
+    HaloInline none;
+    none.n_bnd = 0;
+    none.wait_from = 0x7fffffff;
+    none.ctl = nullptr;
+    CellSgAccum nosg = {};
+    ShExchange nox;
+    nox.world = 1; nox.rank = 0; nox.ctl = nullptr;
+    for (int r = 0; r < kShMaxWorld; r++) nox.block[r] = nullptr;
+    const HaloInline& h = halo ? *halo : none;
+    const CellSgAccum& a = sg ? *sg : nosg;
+    const ShExchange& xx = x ? *x : nox;
+#define ODIS_CELL_LAUNCH(L) (part ? launch_cell_cfg<L, true>(t, p, s, mode, next, n_tiles, rows, h, a, xx, stream) \
+                                 : launch_cell_cfg<L, false>(t, p, s, mode, next, n_tiles, rows, h, a, xx, stream))
+    switch (l_sg) {
+        case 2: return ODIS_CELL_LAUNCH(2);
+        case 3: return ODIS_CELL_LAUNCH(3);
+        case 4: return ODIS_CELL_LAUNCH(4);
+        default: return ODIS_CELL_LAUNCH(0);
+    }
+#undef ODIS_CELL_LAUNCH
 }
 
 }  // namespace odis

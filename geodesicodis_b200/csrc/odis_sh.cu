@@ -393,63 +393,36 @@ __global__ void __launch_bounds__(kShThreads) sh_synthesis_mf_kernel(ShTables t,
     if (i < n_cells) eu[i].y = u0 + acc;
 }
 
-// Second half of the 3-launch variant (cell_step_sg_kernel, odis_kernels.cu, leaves sums over groups of CTAs): persistent
-// CTAs; each one finishes b = sum over the groups (group order, lane-strided partial sums + butterfly: the same bits in every
-// CTA), solves s = g factor (Ginv b) in shared memory and adds the term to the potential of its cells.
+// Second half of the default self-gravity step (degrees 2..4): the staged cell update (cell_step_pipe_kernel, odis_kernels_pipe.cu) has
+// left this rank's harmonic sums b = Y eta^{n+1} — in w.b, or, on a partitioned solver, published in the exchange blocks. Persistent
+// CTAs: each one completes b (partitioned: waits for all ranks' epoch flags and adds the ranks' sums in rank order — the same bits on
+// every rank and in every CTA; the wait / sum protocol is sh_allsolve_kernel's), solves s = g factor (Ginv b) in shared memory and adds
+// the term to the potential of its cells (own + ghost), four cells per thread and trip so that their loads are in flight together.
 template <int LT>
-__global__ void __launch_bounds__(kShThreads) sh_solve_synthesis_mf_kernel(ShTables t, ShWork w, const double* __restrict__ group_partial, int group_stride,
-                                                                           int n_groups, double g, double2* __restrict__ eu, int n_cells) {
-    __shared__ double bsh[kShInlineRows];
-    __shared__ double ssh[kShInlineRows];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < t.rows; k += kShWarps) {
-        const double* __restrict__ row = group_partial + (size_t)k * group_stride;
-        double a = 0.0;
-#pragma unroll 4
-        for (int q = lane; q < n_groups; q += 32) a = a + __ldcg(row + q);
-        a = warp_sum(a);
-        if (lane == 0) {
-            bsh[k] = a;
-            if (blockIdx.x == 0) w.b[k] = a;
-        }
-    }
-    __syncthreads();
-    solve_rows(t, bsh, g, ssh, warp, kShWarps);
-    __syncthreads();
-    if (blockIdx.x == 0)
-        for (int k = threadIdx.x; k < t.rows; k += kShThreads) w.s[k] = ssh[k];
-    const RecConst rc;
-    for (int i = blockIdx.x * kShThreads + threadIdx.x; i < n_cells; i += gridDim.x * kShThreads) {
-        const double u = t.trig[i], z = t.trig[(size_t)t.stride + i], c1 = t.trig[2 * (size_t)t.stride + i], s1 = t.trig[3 * (size_t)t.stride + i];
-        const double u0 = eu[i].y;
-        eu[i].y = u0 + synthesis_mf_cell<LT>(t, rc, ssh, u, z, c1, s1);
-    }
-}
-
-// Partitioned form of the kernel above (cell_step_sgx_kernel has published every rank's sums): waits for all ranks' epoch flags,
-// adds the ranks' sums in rank order (the same bits on every rank and in every CTA), solves and adds the term to the potential of the
-// held cells (own + ghost). The wait / sum protocol is sh_allsolve_kernel's.
-template <int LT>
-__global__ void __launch_bounds__(kShThreads) sh_allsolve_synthesis_mf_kernel(ShTables t, ShWork w, ShExchange x, double g, double2* __restrict__ eu,
-                                                                              int n_cells) {
+__global__ void __launch_bounds__(kShThreads) sh_bsolve_synthesis_mf_kernel(ShTables t, ShWork w, ShExchange x, double g, double2* __restrict__ eu,
+                                                                            int n_cells) {
     __shared__ double bsh[kShInlineRows];
     __shared__ double ssh[kShInlineRows];
     const int warp = threadIdx.x >> 5;
-    const unsigned long long epoch = x.ctl[0];
-    if ((int)threadIdx.x < x.world) {
-        const unsigned long long* f = x_flags(x.block[x.rank]) + threadIdx.x;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) < epoch) {
-            if (clock64() - t0 > kShSpinCycles) { x.ctl[2] = 1ull; break; }
-            __nanosleep(64);
+    if (x.world > 1) {
+        const unsigned long long epoch = x.ctl[0];
+        if ((int)threadIdx.x < x.world) {
+            const unsigned long long* f = x_flags(x.block[x.rank]) + threadIdx.x;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) < epoch) {
+                if (clock64() - t0 > kShSpinCycles) { x.ctl[2] = 1ull; break; }
+                __nanosleep(64);
+            }
         }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < t.rows; k += kShThreads) {
-        double a = 0.0;
-        for (int r = 0; r < x.world; r++) a = a + ld_relaxed_sys(x_pub(x.block[r], (int)(epoch & 1)) + k);
-        bsh[k] = a;
-        if (blockIdx.x == 0) w.b[k] = a;
+        __syncthreads();
+        for (int k = threadIdx.x; k < t.rows; k += kShThreads) {
+            double a = 0.0;
+            for (int r = 0; r < x.world; r++) a = a + ld_relaxed_sys(x_pub(x.block[r], (int)(epoch & 1)) + k);
+            bsh[k] = a;
+            if (blockIdx.x == 0) w.b[k] = a;
+        }
+    } else {
+        for (int k = threadIdx.x; k < t.rows; k += kShThreads) bsh[k] = __ldcg(w.b + k);
     }
     __syncthreads();
     solve_rows(t, bsh, g, ssh, warp, kShWarps);
@@ -457,10 +430,23 @@ __global__ void __launch_bounds__(kShThreads) sh_allsolve_synthesis_mf_kernel(Sh
     if (blockIdx.x == 0)
         for (int k = threadIdx.x; k < t.rows; k += kShThreads) w.s[k] = ssh[k];
     const RecConst rc;
-    for (int i = blockIdx.x * kShThreads + threadIdx.x; i < n_cells; i += gridDim.x * kShThreads) {
-        const double u = t.trig[i], z = t.trig[(size_t)t.stride + i], c1 = t.trig[2 * (size_t)t.stride + i], s1 = t.trig[3 * (size_t)t.stride + i];
-        const double u0 = eu[i].y;
-        eu[i].y = u0 + synthesis_mf_cell<LT>(t, rc, ssh, u, z, c1, s1);
+    constexpr int kBatch = 4;
+    const int stride = gridDim.x * kShThreads;
+    for (int i0 = blockIdx.x * kShThreads + threadIdx.x; i0 < n_cells; i0 += kBatch * stride) {
+        double u[kBatch], z[kBatch], c1[kBatch], s1[kBatch];
+        double2 st[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; q++) {
+            const int i = i0 + q * stride, at = i < n_cells ? i : i0;
+            u[q] = __ldg(t.trig + at); z[q] = __ldg(t.trig + (size_t)t.stride + at);
+            c1[q] = __ldg(t.trig + 2 * (size_t)t.stride + at); s1[q] = __ldg(t.trig + 3 * (size_t)t.stride + at);
+            st[q] = eu[at];
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; q++) {
+            const int i = i0 + q * stride;
+            if (i < n_cells) eu[i] = make_double2(st[q].x, st[q].y + synthesis_mf_cell<LT>(t, rc, ssh, u[q], z[q], c1[q], s1[q]));
+        }
     }
 }
 
@@ -710,24 +696,17 @@ void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_
     sh_synthesis_kernel<<<(n_cells + kShThreads - 1) / kShThreads, kShThreads, 0, stream>>>(t, w, eu, n_cells);
 }
 
-void launch_sh_solve_synthesis(const ShTables& t, const ShWork& w, const double* group_partial, int group_stride, int n_groups, double g, double2* eu,
-                               int n_cells, cudaStream_t stream) {
+void launch_sh_bsolve_synthesis(const ShTables& t, const ShWork& w, const ShExchange* x, double g, double2* eu, int n_cells, cudaStream_t stream) {
     int grid = (n_cells + kShThreads - 1) / kShThreads;
     if (grid > kShMaxBlocks) grid = kShMaxBlocks;               // persistent: two CTAs per SM
+    ShExchange one;
+    one.world = 1; one.rank = 0; one.ctl = nullptr;
+    for (int r = 0; r < kShMaxWorld; r++) one.block[r] = nullptr;
+    const ShExchange& xx = x ? *x : one;
     switch (t.l_max) {
-        case 2: sh_solve_synthesis_mf_kernel<2><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
-        case 3: sh_solve_synthesis_mf_kernel<3><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
-        default: sh_solve_synthesis_mf_kernel<4><<<grid, kShThreads, 0, stream>>>(t, w, group_partial, group_stride, n_groups, g, eu, n_cells); break;
-    }
-}
-
-void launch_sh_allsolve_synthesis(const ShTables& t, const ShWork& w, const ShExchange& x, double g, double2* eu, int n_cells, cudaStream_t stream) {
-    int grid = (n_cells + kShThreads - 1) / kShThreads;
-    if (grid > kShMaxBlocks) grid = kShMaxBlocks;
-    switch (t.l_max) {
-        case 2: sh_allsolve_synthesis_mf_kernel<2><<<grid, kShThreads, 0, stream>>>(t, w, x, g, eu, n_cells); break;
-        case 3: sh_allsolve_synthesis_mf_kernel<3><<<grid, kShThreads, 0, stream>>>(t, w, x, g, eu, n_cells); break;
-        default: sh_allsolve_synthesis_mf_kernel<4><<<grid, kShThreads, 0, stream>>>(t, w, x, g, eu, n_cells); break;
+        case 2: sh_bsolve_synthesis_mf_kernel<2><<<grid, kShThreads, 0, stream>>>(t, w, xx, g, eu, n_cells); break;
+        case 3: sh_bsolve_synthesis_mf_kernel<3><<<grid, kShThreads, 0, stream>>>(t, w, xx, g, eu, n_cells); break;
+        default: sh_bsolve_synthesis_mf_kernel<4><<<grid, kShThreads, 0, stream>>>(t, w, xx, g, eu, n_cells); break;
     }
 }
 

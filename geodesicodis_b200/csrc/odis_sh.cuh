@@ -71,14 +71,11 @@ void launch_sh_analysis(const ShTables& t, ShWork w, const double2* eu, int n_ow
 // U of the first n_cells cells (own + halo)
 void launch_sh_synthesis(const ShTables& t, const ShWork& w, double2* eu, int n_cells, cudaStream_t stream);
 
-// 3-launch variant (unpartitioned, matrix-free, l_max <= 4): the analysis is folded into the cell update (launch_cell_step_sg,
-// odis_kernels.cuh), which leaves group_partial[rows][group_stride], sums over groups of CTAs; this launch adds the n_groups
-// partials of every row in group order, solves, and adds the term to U of the cells [0, n_cells). Leaves b and s in `w` too.
-void launch_sh_solve_synthesis(const ShTables& t, const ShWork& w, const double* group_partial, int group_stride, int n_groups, double g, double2* eu,
-                               int n_cells, cudaStream_t stream);
-// The same on a partitioned solver (launch_cell_step_sgx has published every rank's sums into the exchange blocks): waits for all
-// ranks, adds their sums in rank order, solves, adds the term to U of the held cells. One launch instead of three.
-void launch_sh_allsolve_synthesis(const ShTables& t, const ShWork& w, const ShExchange& x, double g, double2* eu, int n_cells, cudaStream_t stream);
+// Default self-gravity step for degrees 2..4 (matrix-free): the harmonic analysis is folded into the staged cell update
+// (launch_cell_step_pipe with a CellSgAccum, odis_kernels.cuh), which leaves this rank's sums in w.b — or, partitioned (x != nullptr),
+// published in the exchange blocks. This launch completes b (waits for all ranks and adds their sums in rank order), solves and adds
+// the term to U of the cells [0, n_cells): edge update, cell update, this = 3 launches per step. Leaves b and s in `w`.
+void launch_sh_bsolve_synthesis(const ShTables& t, const ShWork& w, const ShExchange* x, double g, double2* eu, int n_cells, cudaStream_t stream);
 
 }  // namespace odis
 

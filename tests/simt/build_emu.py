@@ -20,7 +20,7 @@ CSRC = os.path.join(ROOT, "geodesicodis_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_build")
 LIB = os.path.join(OUT, "libodis_b200_emu.so")
 
-CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_fused.cu", "odis_kernels_nl.cu", "odis_sh.cu", "odis_ensemble.cu", "odis_engine.cu"]
+CUDA_SOURCES = ["odis_kernels.cu", "odis_kernels_pipe.cu", "odis_kernels_nl.cu", "odis_sh.cu", "odis_ensemble.cu", "odis_engine.cu"]
 SWITCH_SRC = r'''// context switch of the SIMT emulation's fibers (tests/simt/simt_emu.h): x86-64 System V, callee-saved registers + stack pointer
 #if !defined(__x86_64__)
 #error "the SIMT emulation's context switch is written for x86-64"
@@ -176,7 +176,7 @@ def rewrite_asm(s: str) -> tuple[str, int]:
             rep = f"simt::mbar_wait({ins[0]}, {ins[1]});"
         elif ptx.startswith("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"):
             rep = f"simt::bulk_copy({ins[0]}, {ins[1]}, {ins[2]}, {ins[3]});"
-        elif ptx.startswith("fence."):
+        elif ptx.startswith("fence.") or ptx.startswith("griddepcontrol."):
             rep = ";"
         elif ptx.startswith("bar.sync %0, %1"):
             rep = f"simt::named_barrier({ins[0]}, {ins[1]});"

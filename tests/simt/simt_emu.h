@@ -274,6 +274,7 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline T __ldg(const T* p) { return *p; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline long long clock64() { return (long long)(simt::now_ms() * 1.0e6); }          // "cycles" = nanoseconds: the kernels' spin bounds stay seconds

@@ -25,7 +25,7 @@ CONTROL = ["tests/test_step_parity_gpu.py", "tests/test_nonlinear_gpu.py", "test
            "tests/test_ensemble_gpu.py::test_members_match_oracle",
            "tests/test_ensemble_gpu.py::test_ensemble_self_gravity_matches_oracle[4-5-2]"]      # FP64 mma.sync fragments modelled
 NEW = ["tests/test_surface_planet_gpu.py", "tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_surface_hybrid_gpu.py", "tests/test_surface_analytical_gpu.py",
-       "tests/test_surface_sigint_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py", "tests/test_variant_ids16_gpu.py", "tests/test_variant_prefetch_gpu.py"]
+       "tests/test_surface_sigint_gpu.py", "tests/test_self_gravity_step_gpu.py", "tests/test_variant_nl4_gpu.py", "tests/test_variant_overlap_gpu.py", "tests/test_variant_ids16_gpu.py"]
 # left out under emulation: full-size grids and the slowest parameter sets
 SKIP = "not large_grid and not high_degree_matrix_free and not 5-12 and not 5-8 and not 6-4 and not 6-2 and not l6_obliqwest and not band_limited"
 DESELECT = ["tests/test_step_parity_gpu.py::test_direct_and_pipelined_kernels_agree[6]"]
@@ -75,7 +75,7 @@ def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
     synchronisation or a call that blocks on another rank's progress shows as a time-out or a mismatch. (The same tests run on
     2 and 4 B200s with `-m gpu`.)"""
     tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py", "tests/test_variant_ids16_gpu.py::test_narrow_ids_on_a_partitioned_grid",
-                                                              "tests/test_variant_sg3_gpu.py::test_three_launch_variant_on_a_partitioned_grid"],
+                                                              "tests/test_self_gravity_step_gpu.py::test_three_launch_step_on_a_partitioned_grid"],
                                           extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="", workers=3)
     assert int(tail.split(" passed")[0].split()[-1]) == 12 and "skipped" not in tail, tail
 
@@ -88,8 +88,8 @@ def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
     if not os.path.isabs(asan_rt) or not os.path.exists(asan_rt):
         pytest.skip("no AddressSanitizer runtime with this compiler")
     lib = build_emu.build(asan=True)
-    files = ["tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_variant_sg3_gpu.py", "tests/test_variant_nl4_gpu.py",
-             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py", "tests/test_variant_ids16_gpu.py", "tests/test_variant_prefetch_gpu.py",
+    files = ["tests/test_variant_blocks_gpu.py", "tests/test_surface_ops_gpu.py", "tests/test_self_gravity_step_gpu.py", "tests/test_variant_nl4_gpu.py",
+             "tests/test_step_parity_gpu.py", "tests/test_self_gravity_gpu.py", "tests/test_variant_ids16_gpu.py",
              "tests/test_multigpu.py::test_partitioned_run_matches_single_gpu[2]",                    # halo push / wait between two concurrent "devices"
              "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]"]     # + all-reduce through peer memory
     select = SKIP + " and not l5_ and not l6_ and not 5-2 and not 5-3 and not full_orbit and not random_state and not kernels_agree"

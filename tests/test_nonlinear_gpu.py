@@ -76,6 +76,7 @@ def test_enable_advection_errors(odis, tmp_path):
     bad["operatorCurl.indptr"] = bad["operatorCurl.indptr"][:-1]
     with pytest.raises(ValueError):
         other.enable_advection(bad)
-    fused = odis.Solver(mesh, dict(prm, reorder=1, semimajor_axis=0.0, kernel_select=4))
+    late = odis.Solver(mesh, dict(prm, reorder=1, semimajor_axis=0.0))
+    late.enable_self_gravity(2, [0.0, 0.0, 0.5])             # the folded harmonic analysis belongs to the linear cell update
     with pytest.raises(odis.OdisError):
-        fused.enable_advection(nonlinear_tables(case))
+        late.enable_advection(nonlinear_tables(case))

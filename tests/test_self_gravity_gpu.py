@@ -117,6 +117,3 @@ def test_enable_errors(odis):
     s.enable_self_gravity(2, [0.0, 0.0, 0.5])
     with pytest.raises(odis.OdisError):
         s.enable_self_gravity(2, [0.0, 0.0, 0.5])               # already on
-    fused = odis.Solver(mesh, dict(prm, kernel_select=4))
-    with pytest.raises(odis.OdisError):
-        fused.enable_self_gravity(2, [0.0, 0.0, 0.5])

@@ -21,7 +21,7 @@ def setup(odis, tmp_path, **over):
     return case, d, mesh, prm
 
 
-@pytest.mark.parametrize("select", [0, 1, 2, 8, 64])           # default; direct edge kernel; staged cell kernel; no graphs; capped cell kernel
+@pytest.mark.parametrize("select", [0, 1, 8, 128])             # default; direct-load baseline kernels; no graphs; 32-bit stencil ids
 @pytest.mark.parametrize("reorder", [1, 0])
 def test_planet_forcing_matches_reference_solver(odis, tmp_path, reorder, select):
     case, d, mesh, prm = setup(odis, tmp_path)
