@@ -115,6 +115,7 @@ SIGNATURES = {
     "odis_get_field": (C.c_int, [C.c_void_p, c_i32, C.c_void_p]),
     "odis_get_dissipation_avg": (C.c_int, [C.c_void_p, P(c_f64)]),
     "odis_get_dissipation_series": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p]),
+    "odis_trim_dissipation_series": (C.c_int, [C.c_void_p]),
     "odis_op_update_momentum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_op_update_eta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_op_forcing": (C.c_int, [C.c_void_p, c_f64, C.c_void_p]),

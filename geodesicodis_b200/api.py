@@ -331,7 +331,7 @@ class Solver:
         self.mesh = mesh
         p = Params()
         for k, v in params.items():
-            if k == "kernel_select":             # odis_params.reserved[0], see include/odis_b200.h (0 = fused one-launch step)
+            if k == "kernel_select":             # odis_params.reserved[0], see include/odis_b200.h (0 = default kernels)
                 p.reserved[0] = int(v)
             else:
                 setattr(p, k, v)
@@ -548,6 +548,11 @@ class Solver:
         out = np.empty(count, dtype=np.float64)
         check(_lib.load().odis_get_dissipation_series(self._h, first, count, out.ctypes.data))
         return out
+
+    def trim_dissipation_series(self) -> None:
+        """Forget the per-step dissipation series before the current step (odis_trim_dissipation_series)."""
+        check(_lib.load().odis_trim_dissipation_series(self._h))
+        self._iter0 = self.iter
 
     @property
     def iter(self) -> int:

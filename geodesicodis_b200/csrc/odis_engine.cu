@@ -179,6 +179,7 @@ struct odis_solver {
     cudaEvent_t pack_done = nullptr;         // the last H2D copy out of h_pack
     bool pack_pending = false;
 
+    long long wait_cycles = 0;               // ODIS_B200_WAIT_TIMEOUT_S in clock64 ticks (0: the kernels' default)
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
     int last_mode = -1;
@@ -269,7 +270,11 @@ int ensure_series(odis_solver* s, size_t need) {
     double* nd = nullptr;
     odis::StepScalars* ns = nullptr;
     ODIS_CUDA(cudaMalloc((void**)&nd, cap * sizeof(double)));
-    ODIS_CUDA(cudaMalloc((void**)&ns, cap * sizeof(odis::StepScalars)));
+    if (cudaMalloc((void**)&ns, cap * sizeof(odis::StepScalars)) != cudaSuccess) {
+        cudaFree(nd);
+        cudaGetLastError();
+        return fail(ODIS_ERR_CUDA, "cudaMalloc of the time-factor table failed");
+    }
     ODIS_CUDA(cudaMemsetAsync(nd, 0, cap * sizeof(double), s->stream));
     ODIS_CUDA(cudaMemsetAsync(ns, 0, cap * sizeof(odis::StepScalars), s->stream));
     if (s->d_series) {
@@ -531,6 +536,14 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         return bail(rc);
     cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned int), s->stream);
     cudaMemsetAsync(s->d_ctl, 0, sizeof(odis::StepCtl), s->stream);
+    {   // upper bound of every in-kernel wait for another rank (halo flags, harmonic all-reduce): ~10 s unless the environment says otherwise.
+        // One host thread driving all ranks in turn must enqueue every rank's steps within this time of each other.
+        const char* e = std::getenv("ODIS_B200_WAIT_TIMEOUT_S");
+        const double sec = e ? std::atof(e) : 0.0;
+        s->wait_cycles = sec > 0.0 ? (long long)(sec * 2.0e9) : 0ll;
+        if (s->wait_cycles > 0)
+            cudaMemcpyAsync(&s->d_ctl->spin_cycles, &s->wait_cycles, sizeof(long long), cudaMemcpyHostToDevice, s->stream);
+    }
     if (cudaSuccess != odis::pipe_configure()) return bail(fail(ODIS_ERR_CUDA, "cudaFuncSetAttribute(shared memory size) failed"));
     cudaMemsetAsync(s->d_eu[0], 0, (size_t)Np * sizeof(double2), s->stream);
     cudaMemsetAsync(s->d_eu[1], 0, (size_t)Np * sizeof(double2), s->stream);
@@ -586,6 +599,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         cudaMemsetAsync(s->d_halo_done, 0, sizeof(unsigned int), s->stream);
         cudaMemsetAsync(s->d_sh_xblock, 0, odis::kShXBytes, s->stream);
         cudaMemsetAsync(s->d_sh_xctl, 0, 4 * sizeof(unsigned long long), s->stream);
+        if (s->wait_cycles > 0) cudaMemcpyAsync(s->d_sh_xctl + 3, &s->wait_cycles, sizeof(long long), cudaMemcpyHostToDevice, s->stream);
         s->sh_xremote[rank] = s->d_sh_xblock;
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(ODIS_ERR_CUDA, "halo table upload failed"));
     }
@@ -1426,6 +1440,21 @@ int odis_get_dissipation_avg(odis_solver* s, double* out) {
     ODIS_CUDA(cudaMemcpyAsync(&v, s->d_series + (s->iter - s->iter0), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     *out = v / sphere_area(s);
+    return ODIS_OK;
+}
+
+// Forget the per-step dissipation series before the current step (entry 0 becomes the current state's): whole runs read only the
+// newest entry, and the series / time-factor tables would otherwise grow by 56 B per step for as long as the run lasts.
+int odis_trim_dissipation_series(odis_solver* s) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL argument");
+    if (!s->have_state) return fail(ODIS_ERR_STATE, "no state");
+    if (s->iter == s->iter0) return ODIS_OK;
+    ODIS_CUDA(cudaSetDevice(s->device));
+    // the newest entry (if the diagnostics are current) moves to the front; the device-side step counter restarts with it
+    const size_t last = (size_t)(s->iter - s->iter0);
+    ODIS_CUDA(cudaMemcpyAsync(s->d_series, s->d_series + last, sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    ODIS_CUDA(cudaMemsetAsync(&s->d_ctl->count, 0, sizeof(unsigned long long), s->stream));
+    s->iter0 = s->iter;
     return ODIS_OK;
 }
 

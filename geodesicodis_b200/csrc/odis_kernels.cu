@@ -55,6 +55,7 @@ __device__ __forceinline__ double2 ld_gather_cg(const double2* p) {
 // spin (bounded) until all neighbours have published the exchange ctl->epoch[0] (see HaloInline)
 __device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
     const unsigned long long ev = ((volatile unsigned long long*)ctl->epoch)[0];
+    const long long limit = ctl->spin_cycles > 0 ? ctl->spin_cycles : kHaloSpinCycles;
     const long long t0 = clock64();
     bool late = false;
     for (int k = 0; k < w.n_peers; k++) {
@@ -62,7 +63,7 @@ __device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
         const unsigned long long* fv = w.flag[k];
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fv) : "memory");
-        } while (seen < ev && clock64() - t0 < kHaloSpinCycles);
+        } while (seen < ev && clock64() - t0 < limit);
         late |= seen < ev;
     }
     if (late) ctl->pad = 1ull;      // a neighbour never arrived: reported by the host (ODIS_ERR_STATE), no hang
@@ -393,10 +394,10 @@ __global__ void halo_exchange_kernel(int n, const int* __restrict__ local_idx, c
         unsigned long long* f = remote.flags[threadIdx.x] + flag_slot;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
         unsigned long long seen;
-        const long long t0 = clock64();
+        const long long t0 = clock64(), limit = ctl->spin_cycles > 0 ? ctl->spin_cycles : kHaloSpinCycles;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(w.flag[threadIdx.x]) : "memory");
-        } while (seen < epoch && clock64() - t0 < kHaloSpinCycles);
+        } while (seen < epoch && clock64() - t0 < limit);
         if (seen < epoch) ctl->pad = 1ull;
     }
     __syncthreads();

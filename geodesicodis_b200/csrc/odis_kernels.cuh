@@ -44,8 +44,10 @@ struct StepScalars {          // per-step host-evaluated trigonometry (tidalPote
 struct StepCtl {
     unsigned long long count;       // steps taken since odis_set_state
     unsigned long long epoch[2];    // [0] halo exchanges ({v,l} of the boundary edges) published so far; [1] unused
-    unsigned long long pad;         // set to 1 when a halo wait gave up (kHaloSpinCycles)
+    unsigned long long pad;         // set to 1 when a halo wait gave up
     StepScalars cur;
+    long long spin_cycles;          // upper bound of an in-kernel wait for another rank / CTA in clock64 ticks (0: kHaloSpinCycles);
+                                    // set at odis_create from ODIS_B200_WAIT_TIMEOUT_S
 };
 
 struct HaloInline;   // halo exchange fused into the step kernels, defined below
@@ -179,7 +181,8 @@ cudaError_t launch_edge_step_pipe16(const EdgeTables& t, const Physics& p, const
 
 // ---- halo exchange between ranks (one GPU each): peers' arrays are mapped into this process ----
 constexpr int kHaloMaxPeers = 8;
-constexpr long long kHaloSpinCycles = 20000000000ll;   // ~10 s: upper bound of any in-kernel wait for a neighbour
+constexpr long long kHaloSpinCycles = 20000000000ll;   // ~10 s: default upper bound of any in-kernel wait for a neighbour
+// (configurable per solver: StepCtl::spin_cycles, environment variable ODIS_B200_WAIT_TIMEOUT_S read by odis_create)
 struct HaloRemote {
     double2* data[kHaloMaxPeers];                 // the peer's {v,l} (or {eta,U}) array, its local numbering
     unsigned long long* flags[kHaloMaxPeers];     // the peer's epoch flags [2][world]

@@ -361,8 +361,9 @@ inline TrigRows trig_rows_for(int potential) {
 
 // tidal potential from its inputs in trig_rows_for() order; expression shapes of tidalPotentials.cpp:80-172 (= tidal_potential(),
 // odis_kernels.cu)
+template <int kPot>
 __device__ __forceinline__ double tidal_potential_in(const Physics& p, const StepScalars& m, const double* in) {
-    switch (p.potential) {
+    switch (kPot >= 0 ? kPot : p.potential) {
         case P_ECC: {
             const double cosSq = in[0], sinSq = in[1], cos2Lon = in[2], sin2Lon = in[3];
             return p.factor * ((1. - 3. * sinSq) * m.cosM + cosSq * (3. * m.cosM * cos2Lon + 4. * m.sinM * sin2Lon));
@@ -422,6 +423,7 @@ __device__ __forceinline__ double2 ld_gather_cg(const double2* p) {     // ghost
 // spin (bounded) until all neighbours have published the exchange ctl->epoch[0] (see HaloInline)
 __device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
     const unsigned long long ev = ((volatile unsigned long long*)ctl->epoch)[0];
+    const long long limit = ctl->spin_cycles > 0 ? ctl->spin_cycles : kHaloSpinCycles;
     const long long t0 = clock64();
     bool late = false;
     for (int k = 0; k < w.n_peers; k++) {
@@ -429,7 +431,7 @@ __device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
         const unsigned long long* fv = w.flag[k];
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fv) : "memory");
-        } while (seen < ev && clock64() - t0 < kHaloSpinCycles);
+        } while (seen < ev && clock64() - t0 < limit);
         late |= seen < ev;
     }
     if (late) ctl->pad = 1ull;      // a neighbour never arrived: reported by the host (ODIS_ERR_STATE), no hang
@@ -477,11 +479,11 @@ __device__ __forceinline__ double cell_synthesis(const double* ssh, double u, do
 __device__ __forceinline__ bool grid_barrier_arrive(unsigned int* bar, unsigned int gen0, StepCtl* ctl) {
     __threadfence();
     if (atomicAdd(bar, 1u) == gridDim.x - 1u) return true;
-    const long long t0 = clock64();
+    const long long t0 = clock64(), limit = (ctl != nullptr && ctl->spin_cycles > 0) ? ctl->spin_cycles : kHaloSpinCycles;
     unsigned int gen;
     do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-    } while (gen == gen0 && clock64() - t0 < kHaloSpinCycles);
+    } while (gen == gen0 && clock64() - t0 < limit);
     if (gen == gen0 && ctl != nullptr) ctl->pad = 1ull;      // reported by the host (ODIS_ERR_STATE), no hang
     return false;
 }
@@ -491,7 +493,9 @@ __device__ __forceinline__ void grid_barrier_release(unsigned int* bar, unsigned
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen0 + 1u) : "memory");
 }
 
-template <int kG, int kS, int LSG, bool kPart, bool kMerged>
+// kPot >= 0: the kernel is compiled for that one potential (P_ECC: the Enceladus / Europa case) — only its four inputs are ever live,
+// which keeps the harmonic accumulators of the self-gravity variants in registers; -1: any potential, selected at run time.
+template <int kG, int kS, int LSG, bool kPart, bool kMerged, int kPot>
 __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const Physics& p, const CellState& s, int mode, StepScalars next,
                                                     int n_tiles, const CellRows& rows, const HaloInline& halo, const CellSgAccum& sg,
                                                     const ShExchange& x) {
@@ -572,26 +576,35 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
             if (lane == 0) halo_wait_all(halo.wait_v, halo.ctl);
             __syncwarp();
         }
-        // the six {v,l} gathers go out first; the rest of the stage is read (and the stage released) while they are in flight
+        // the six {v,l} gathers go out first; the rest of the stage is read (and the stage released) while they are in flight. A cell's
+        // edges fill the slots from 0 (ascending reference id), so only slot 5 can be empty (the 12 pentagons); padded cells gather nothing.
         double2 ed[kCellEdges];
-        if (!bnd_tile) {
 #pragma unroll
-            for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
-        } else {
+        for (int j = 0; j < kCellEdges; j++) ed[j] = make_double2(0.0, 0.0);
+        if (c < t.n_active) {
+            const int last = packed[kCellEdges - 1] == -1 ? 0 : (packed[kCellEdges - 1] & 0x7fffffff);
+            if (!bnd_tile) {
 #pragma unroll
-            for (int j = 0; j < kCellEdges; j++) ed[j] = ld_gather_cg(s.vl + (packed[j] == -1 ? 0 : (packed[j] & 0x7fffffff)));
+                for (int j = 0; j < kCellEdges - 1; j++) ed[j] = ld_gather(s.vl + (packed[j] & 0x7fffffff));
+                ed[kCellEdges - 1] = ld_gather(s.vl + last);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kCellEdges - 1; j++) ed[j] = ld_gather_cg(s.vl + (packed[j] & 0x7fffffff));
+                ed[kCellEdges - 1] = ld_gather_cg(s.vl + last);
+            }
         }
         double2 stt = d->eu[tl];
         const double area = d->area[tl], f1 = d->h1[tl], f2 = d->h2[tl];
-        if (p.potential != P_NONE) {
-            double in[8];
+        if (kPot >= 0 || p.potential != P_NONE) {
+            constexpr int kIn = kPot == P_ECC ? 4 : 8;
+            double in[kIn];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < kIn; k++) {
                 const int slot = (int)(rows.pot >> (5 * k)) & 31;        // stage row of the potential's k-th input; bit 4: its square
                 const double v = (k < rows.n_pot) ? d->trig[slot & 15][tl] : 0.0;
                 in[k] = (slot & 16) ? v * v : v;                          // cos^2 / sin^2 lat from the basis rows (the product of mesh.cpp:2144-2145)
             }
-            stt.y = tidal_potential_in(p, nx, in);
+            stt.y = tidal_potential_in<kPot>(p, nx, in);
         }
         double bu = 0.0, bz = 0.0, bc1 = 0.0, bs1 = 0.0;
         if (LSG > 0) {
@@ -606,7 +619,7 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
             const double ra = __drcp_rn(area);
 #pragma unroll
             for (int j = 0; j < kCellEdges; j++) {
-                if (packed[j] != -1) {                                            // the 12 pentagons have 5 edges
+                if (j < kCellEdges - 1 || packed[j] != -1) {                      // the 12 pentagons have 5 edges
                     const double ndir = (packed[j] < 0) ? 1.0 : -1.0;             // -dir: dir = -1 for the outer cell
                     const double coeff = exact_div(ndir * ed[j].y, area, ra);
                     div += (p.h * coeff) * ed[j].x;
@@ -715,11 +728,11 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         if (!is_last) epoch = ((volatile unsigned long long*)x.ctl)[0];         // written by the last CTA before the release
         if (ct < x.world) {
             const unsigned long long* f = cx_flags(x.block[x.rank]) + ct;
-            const long long t0 = clock64();
+            const long long t0 = clock64(), limit = (long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kHaloSpinCycles;
             unsigned long long seen;
             do {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
-            } while (seen < epoch && clock64() - t0 < kHaloSpinCycles);
+            } while (seen < epoch && clock64() - t0 < limit);
             if (seen < epoch) x.ctl[2] = 1ull;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
@@ -765,11 +778,11 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
 // 288 threads (one producer warp, two consumer groups of 128), 4 stages, 2 CTAs per SM: the edge kernel's shape. Measured against a
 // deeper pipeline (6 stages: +1.3 us) and one wide CTA per SM (3 or 4 groups, 6-8 stages: +8.5 us) at 655,362 cells, round 2.
 constexpr int kCellGroups = 2, kCellStages = 4;
-template <int LSG, bool kPart, bool kMerged>
+template <int LSG, bool kPart, bool kMerged, int kPot>
 __global__ void __launch_bounds__(32 + kCellGroups * kTile, 2) cell_step_pipe_kernel(CellTables t, Physics p, CellState s, int mode, StepScalars next,
                                                                                       int n_tiles, CellRows rows, HaloInline halo, CellSgAccum sg,
                                                                                       ShExchange x) {
-    cell_step_pipe_body<kCellGroups, kCellStages, LSG, kPart, kMerged>(t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+    cell_step_pipe_body<kCellGroups, kCellStages, LSG, kPart, kMerged, kPot>(t, p, s, mode, next, n_tiles, rows, halo, sg, x);
 }
 
 }  // namespace
@@ -790,11 +803,13 @@ static int num_sms() {
 constexpr size_t kCellSmem = kCellStages * sizeof(CellStage) + 2 * kCellStages * sizeof(uint64_t);
 template <int LSG, bool kPart>
 static cudaError_t cell_pipe_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
+    cudaError_t e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
     if constexpr (LSG == 0) return e;
     else {
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
+        if ((e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, false, (int)P_ECC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, true, (int)P_ECC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem)) != cudaSuccess) return e;
+        return cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
     }
 }
 
@@ -924,11 +939,15 @@ template <int LSG, bool kPart>
 static cudaError_t launch_cell_cfg(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next, int n_tiles,
                                    const CellRows& rows, const HaloInline& halo, const CellSgAccum& sg, const ShExchange& x, cudaStream_t stream) {
     const int cap = 2 * num_sms(), grid = n_tiles < cap ? n_tiles : cap;
-    if (LSG > 0 && sg.merged)
-        return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0)>, grid, 32 + kCellGroups * kTile, kCellSmem, stream, true, t, p, s, mode, next,
-                                  n_tiles, rows, halo, sg, x);
-    return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false>, grid, 32 + kCellGroups * kTile, kCellSmem, stream, false, t, p, s, mode, next, n_tiles,
-                              rows, halo, sg, x);
+    constexpr int kBlock = 32 + kCellGroups * kTile;
+    constexpr int kEcc = LSG > 0 ? (int)P_ECC : -1;          // the one-potential build exists for the self-gravity variants (register pressure)
+    const bool ecc = LSG > 0 && p.potential == P_ECC;
+    if (LSG > 0 && sg.merged) {
+        if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), kEcc>, grid, kBlock, kCellSmem, stream, true, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+        return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), -1>, grid, kBlock, kCellSmem, stream, true, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+    }
+    if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, kEcc>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+    return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, -1>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
 }
 
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,

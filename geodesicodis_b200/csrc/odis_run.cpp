@@ -166,10 +166,13 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         log.err("TERMINATING ODIS.");
         return fail(code, msg);
     };
+    // a failed write (full disk, quota) must end the run with an error instead of leaving a silently truncated data.h5
+    int io_rc = ODIS_OK;
+    std::string io_err, err;
+    auto wr = [&](int r) { if (r != 0 && io_rc == ODIS_OK) { io_rc = ODIS_ERR_IO; io_err = err; } };
 
     // ---- Globals(0) ----
     odis::Config cfg;
-    std::string err;
     if (cfg.load(dir, err) != 0) return terminate(ODIS_ERR_IO, err);
     log.out("Found input file.");                                             // globals.cpp:351
     for (const std::string& k : cfg.unassigned())                             // globals.cpp:445-466
@@ -225,8 +228,8 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
             lats[i] = (float)((float)mesh.face_centre_pos_sph[(size_t)i * 2] * 180. / odis::kPi);
             lons[i] = (float)((float)mesh.face_centre_pos_sph[(size_t)i * 2 + 1] * 180. / odis::kPi);
         }
-        h5.write_rows(ds_lon, 0, (uint64_t)F, lons.data(), err);
-        h5.write_rows(ds_lat, 0, (uint64_t)F, lats.data(), err);
+        wr(h5.write_rows(ds_lon, 0, (uint64_t)F, lons.data(), err));
+        wr(h5.write_rows(ds_lat, 0, (uint64_t)F, lats.data(), err));
     }
     write_model_parameters(cfg, log);                                         // main.cpp:59
 
@@ -255,6 +258,10 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     odis_solver* s = nullptr;
     int rc = odis_create(&mv, &p, opt.device, &s);
     if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+    struct SolverGuard {                      // every return below releases the device memory and the stream
+        odis_solver*& h;
+        ~SolverGuard() { if (h) { odis_destroy(h); h = nullptr; } }
+    } solver_guard{s};
     // tables of the nonlinear branch: the step needs them with `advection; true` (updateMomentum.cpp:37, updateEta.cpp:32), the
     // Cartesian velocity output needs operatorRBFinterp either way (timeIntegrator.cpp:173,290)
     odis::NonlinearTables nlt;
@@ -288,17 +295,21 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     std::vector<double> v((size_t)F, 0.0), eta((size_t)N, 0.0), dv((size_t)F * 3, 0.0), de((size_t)N * 3, 0.0);
     if (cfg.initial_condition == odis::INIT_LOAD) {                           // initialConditions.cpp:19-144
         const std::string fv = dir + "/InitialConditions/vel_init.txt", fp = dir + "/InitialConditions/pres_init.txt";
-        if (load_restart(fv, (size_t)F, v, dv) == 0) log.out("\nFound initial conditions file: " + fv);
+        // a missing file is the reference's warning (initialConditions.cpp:40-44: the run goes on from zeros); a file that does not
+        // parse would leave half-loaded state, so that ends the run
+        const int lv = load_restart(fv, (size_t)F, v, dv), lp = load_restart(fp, (size_t)N, eta, de);
+        if (lv == -2 || lp == -2) return terminate(ODIS_ERR_CONFIG, "initial conditions file does not parse: " + (lv == -2 ? fv : fp));
+        if (lv == 0) log.out("\nFound initial conditions file: " + fv);
         else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fv);
-        if (load_restart(fp, (size_t)N, eta, de) == 0) log.out("\nFound initial conditions file: " + fp);
+        if (lp == 0) log.out("\nFound initial conditions file: " + fp);
         else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fp);
         rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
-        if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
+        if (rc != ODIS_OK) return terminate(rc, odis_last_error());
     }
     if (cfg.initial_condition == odis::INIT_ANALYTICAL) {                     // initialConditions.cpp:311-313
         rc = odis_analytical_state(&mv, &p, v.data(), dv.data(), eta.data(), de.data());
         if (rc == ODIS_OK) rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
-        if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
+        if (rc != ODIS_OK) return terminate(rc, odis_last_error());
     }
     log.out("Defining arrays for Adams-Bashforth time integration...");       // timeIntegrator.cpp:140
 
@@ -319,8 +330,8 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
             if (ds_u >= 0) {
                 if ((rc2 = odis_get_field(s, ODIS_FIELD_VELOCITY_EN, ven.data()))) return rc2;
                 for (int i = 0; i < F; i++) { fa[i] = (float)ven[(size_t)i * 2]; fb[i] = (float)ven[(size_t)i * 2 + 1]; }   // outFiles.cpp:546-553
-                h5.write_rows(ds_u, row, 1, fa.data(), err);
-                h5.write_rows(ds_v, row, 1, fb.data(), err);
+                wr(h5.write_rows(ds_u, row, 1, fa.data(), err));
+                wr(h5.write_rows(ds_v, row, 1, fb.data(), err));
             }
             if (ds_ux >= 0) {                                                  // interpolateVelocityCartRBF, interpolation.cpp:116; outFiles.cpp:567-590
                 if ((rc2 = odis_get_field(s, ODIS_FIELD_VELOCITY, vcur.data()))) return rc2;
@@ -331,22 +342,22 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
                         for (int k = A.indptr[(size_t)3 * i + c]; k < A.indptr[(size_t)3 * i + c + 1]; k++) tmp += A.data[(size_t)k] * vcur[(size_t)A.indices[(size_t)k]];
                         fa[i] = (float)tmp;
                     }
-                    h5.write_rows(c == 0 ? ds_ux : c == 1 ? ds_uy : ds_uz, row, 1, fa.data(), err);
+                    wr(h5.write_rows(c == 0 ? ds_ux : c == 1 ? ds_uy : ds_uz, row, 1, fa.data(), err));
                 }
             }
             if (ds_eta >= 0) {
                 if ((rc2 = odis_get_field(s, ODIS_FIELD_ETA, eta.data()))) return rc2;
                 for (int i = 0; i < N; i++) fa[i] = (float)eta[i];
-                h5.write_rows(ds_eta, row, 1, fa.data(), err);
+                wr(h5.write_rows(ds_eta, row, 1, fa.data(), err));
             }
             if (ds_diss >= 0) {
                 if ((rc2 = odis_get_field(s, ODIS_FIELD_DISSIPATION, ediss.data()))) return rc2;
                 for (int i = 0; i < F; i++) fa[i] = (float)ediss[i];
-                h5.write_rows(ds_diss, row, 1, fa.data(), err);
+                wr(h5.write_rows(ds_diss, row, 1, fa.data(), err));
             }
-            if (ds_avg >= 0) { const float x = (float)e_diss; h5.write_rows(ds_avg, row, 1, &x, err); }
-            if (ds_kin >= 0) { const float x = (float)current_time; h5.write_rows(ds_kin, row, 1, &x, err); }   // pp[] points at current_time, timeIntegrator.cpp:150
-            if (ds_d1 >= 0) { std::fill(fa.begin(), fa.begin() + N, 0.0f); h5.write_rows(ds_d1, row, 1, fa.data(), err); }
+            if (ds_avg >= 0) { const float x = (float)e_diss; wr(h5.write_rows(ds_avg, row, 1, &x, err)); }
+            if (ds_kin >= 0) { const float x = (float)current_time; wr(h5.write_rows(ds_kin, row, 1, &x, err)); }   // pp[] points at current_time, timeIntegrator.cpp:150
+            if (ds_d1 >= 0) { std::fill(fa.begin(), fa.begin() + N, 0.0f); wr(h5.write_rows(ds_d1, row, 1, fa.data(), err)); }
         }
         out_count++;
         res->dumps++;
@@ -384,8 +395,8 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         if (row < T) {
             if (ds_u >= 0) {
                 for (int i = 0; i < F; i++) { fa[i] = (float)view.velocity_en[(size_t)i * 2]; fb[i] = (float)view.velocity_en[(size_t)i * 2 + 1]; }
-                h5.write_rows(ds_u, row, 1, fa.data(), err);
-                h5.write_rows(ds_v, row, 1, fb.data(), err);
+                wr(h5.write_rows(ds_u, row, 1, fa.data(), err));
+                wr(h5.write_rows(ds_v, row, 1, fb.data(), err));
             }
             if (ds_ux >= 0) {
                 const odis::Csr& A = nlt.rbf_interp;
@@ -395,20 +406,20 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
                         for (int k = A.indptr[(size_t)3 * i + c]; k < A.indptr[(size_t)3 * i + c + 1]; k++) tmp += A.data[(size_t)k] * view.velocity[(size_t)A.indices[(size_t)k]];
                         fa[i] = (float)tmp;
                     }
-                    h5.write_rows(c == 0 ? ds_ux : c == 1 ? ds_uy : ds_uz, row, 1, fa.data(), err);
+                    wr(h5.write_rows(c == 0 ? ds_ux : c == 1 ? ds_uy : ds_uz, row, 1, fa.data(), err));
                 }
             }
             if (ds_eta >= 0) {
                 for (int i = 0; i < N; i++) fa[i] = (float)view.eta[i];
-                h5.write_rows(ds_eta, row, 1, fa.data(), err);
+                wr(h5.write_rows(ds_eta, row, 1, fa.data(), err));
             }
             if (ds_diss >= 0) {
                 for (int i = 0; i < F; i++) fa[i] = (float)view.dissipation[i];
-                h5.write_rows(ds_diss, row, 1, fa.data(), err);
+                wr(h5.write_rows(ds_diss, row, 1, fa.data(), err));
             }
-            if (ds_avg >= 0) { const float x = (float)e_diss; h5.write_rows(ds_avg, row, 1, &x, err); }
-            if (ds_kin >= 0) { const float x = (float)pending_time; h5.write_rows(ds_kin, row, 1, &x, err); }
-            if (ds_d1 >= 0) { std::fill(fa.begin(), fa.begin() + N, 0.0f); h5.write_rows(ds_d1, row, 1, fa.data(), err); }
+            if (ds_avg >= 0) { const float x = (float)e_diss; wr(h5.write_rows(ds_avg, row, 1, &x, err)); }
+            if (ds_kin >= 0) { const float x = (float)pending_time; wr(h5.write_rows(ds_kin, row, 1, &x, err)); }
+            if (ds_d1 >= 0) { std::fill(fa.begin(), fa.begin() + N, 0.0f); wr(h5.write_rows(ds_d1, row, 1, fa.data(), err)); }
         }
         out_count++;
         res->dumps++;
@@ -434,6 +445,10 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         iter += n;
         if (iter % out_freq == 0) rc = overlap ? begin_dump(dt * (double)iter) : dump(dt * (double)iter);   // timeIntegrator.cpp:280-304
         else rc = odis_synchronize(s);
+        if (rc == ODIS_OK && io_rc != ODIS_OK) break;                          // stop at the first failed write
+        // the run reads only the newest entry of the per-step dissipation series: forget the older ones, so that a 150-orbit run
+        // (7 million steps) keeps a few KB of series instead of growing it by 56 B per step
+        if (rc == ODIS_OK) rc = odis_trim_dissipation_series(s);
         if (g_sigint) {                                                        // :307-312
             if (overlap && rc == ODIS_OK) rc = finish_dump();
             log.out("Terminate signal caught...");
@@ -442,7 +457,8 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     }
     if (overlap && rc == ODIS_OK) rc = finish_dump();
     sigaction(SIGINT, &sa_old, nullptr);
-    if (rc != ODIS_OK) { odis_destroy(s); return terminate(rc, odis_last_error()); }
+    if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+    if (io_rc != ODIS_OK) return terminate(io_rc, "writing DATA/data.h5 failed: " + io_err);
 
     // restart files (writeInitialConditions, initialConditions.cpp:209-276)
     ::mkdir((dir + "/InitialConditions").c_str(), 0770);
@@ -454,7 +470,8 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     int64_t launches = 0;
     odis_get_launch_count(s, &launches);
     odis_destroy(s);
-    h5.close(err);
+    s = nullptr;                                                               // (the guard holds a reference to this pointer)
+    if (h5.close(err) != 0) return terminate(ODIS_ERR_IO, "closing DATA/data.h5 failed: " + err);
     res->steps = iter;
     res->n_cells = N; res->n_edges = F;
     res->dt = dt; res->steps_per_period = total_iter;

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kShThreads) sh_reduce_publish_kernel(ShTables 
     }
 }
 
-constexpr long long kShSpinCycles = 20000000000ll;   // ~10 s
+constexpr long long kShSpinCycles = 20000000000ll;   // ~10 s by default; x.ctl[3] > 0 overrides (ODIS_B200_WAIT_TIMEOUT_S, odis_create)
 
 __global__ void __launch_bounds__(kShThreads) sh_allsolve_kernel(ShTables t, ShWork w, ShExchange x, double g) {
     extern __shared__ double dyn[];
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kShThreads) sh_allsolve_kernel(ShTables t, ShW
         const unsigned long long* f = x_flags(x.block[x.rank]) + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < epoch) {
-            if (clock64() - t0 > kShSpinCycles) { x.ctl[2] = 1ull; break; }
+            if (clock64() - t0 > ((long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kShSpinCycles)) { x.ctl[2] = 1ull; break; }
             __nanosleep(64);
         }
     }
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kShThreads) sh_bsolve_synthesis_mf_kernel(ShTa
             const unsigned long long* f = x_flags(x.block[x.rank]) + threadIdx.x;
             const long long t0 = clock64();
             while (ld_acquire_sys(f) < epoch) {
-                if (clock64() - t0 > kShSpinCycles) { x.ctl[2] = 1ull; break; }
+                if (clock64() - t0 > ((long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kShSpinCycles)) { x.ctl[2] = 1ull; break; }
                 __nanosleep(64);
             }
         }

@@ -58,7 +58,7 @@ constexpr int kShXRows = 1024;
 constexpr size_t kShXBytes = kShMaxWorld * sizeof(unsigned long long) + 2 * (size_t)kShXRows * sizeof(double);
 struct ShExchange {
     int world, rank;
-    unsigned long long* ctl;                 // local: [0] epoch, [1] ticket, [2] set to 1 when a wait gave up
+    unsigned long long* ctl;                 // local: [0] epoch, [1] ticket, [2] set to 1 when a wait gave up, [3] wait limit in clock64 ticks (0: default)
     unsigned char* block[kShMaxWorld];       // every rank's exchange block, own included
 };
 

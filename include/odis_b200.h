@@ -142,19 +142,15 @@ typedef struct odis_params {
     int32_t init_load;      /* 1: AB3 uses the 3-level formula from step 0 (temporalOperators.cpp:36) */
     int32_t reorder;        /* 1: locality (space-filling-curve) renumbering on device; 0: reference order */
     int32_t block_threads;  /* 0 = default */
-    int32_t reserved[4];    /* [0] kernel selection, 0 = default: two launches per step, bulk-async staged edge kernel +
-                             *     direct-load cell kernel. bit 0: direct-load edge kernel; bit 1: staged cell kernel; bit 2: ONE fused
-                             *     kernel per step (cell update of the previous step + edge update; one halo exchange per step).
-                             *     Every selection gives bit-identical fields. bit 3: no CUDA-graph replay. bit 4 (with
-                             *     odis_enable_self_gravity, degree <= 4; partitioned solvers too): 3 launches per step instead of 5 (6) — the harmonic
-                             *     analysis is folded into the cell update and the solve into the synthesis (sums associate differently:
-                             *     fields agree with the default to ~1e-13 relative, not bit for bit). bit 5 (with odis_enable_advection):
-                             *     the nonlinear step in 4 gather launches instead of 6 (bit-identical fields). bit 6: the per-step cell
-                             *     update compiled with a 64-register cap (50 % instead of 37.5 % occupancy; bit-identical fields). bit 7 (staged edge
-                             *     kernel): stencil ids travel as 16-bit offsets from the edge's own id, one bulk copy per tile; tiles where an
-                             *     offset does not fit stay on the 32-bit rows (180 instead of 200 B per edge; bit-identical fields). bit 8
-                             *     (tests): offset range +-1023 instead of +-32767. bit 9: the per-step cell update prefetches the streamed rows
-                             *     of the tile one GPU-full of CTAs ahead into L2 (cp.async.bulk.prefetch.L2; bit-identical fields). Rest must be 0. */
+    int32_t reserved[4];    /* [0] kernel selection. 0 = default: per step one bulk-async staged edge kernel (stencil ids as 16-bit
+                             *     offsets from the edge's own id where they fit, 32-bit rows elsewhere) and one staged cell kernel; with
+                             *     odis_enable_self_gravity to degree <= 4 the cell kernel also accumulates the harmonic analysis and,
+                             *     behind a grid-wide barrier (cooperative launch), solves and adds the term: 2 launches per step, also on
+                             *     partitioned solvers. With odis_enable_advection: the nonlinear step in 4 gather launches.
+                             *     bit 0: the direct-load baseline kernels (edge, cell, separate analysis / reduce-solve / synthesis
+                             *     launches, 6-launch nonlinear step): same fields bit for bit (self-gravity term: within 1e-11).
+                             *     bit 3: no CUDA-graph replay. bit 7: 32-bit stencil ids only. bit 8 (tests): 16-bit offset range
+                             *     +-1023 instead of +-32767, so that small grids exercise the fallback rows. Rest must be 0. */
 } odis_params;
 
 typedef enum odis_field {
@@ -283,6 +279,10 @@ int odis_get_dissipation_avg(odis_solver* s, double* out);
 /* Per-step series of the same quantity counted from the last odis_set_state: entry j (first <= j <
  * first+count) is the value for the state after j steps, j = 0 being the state as set. */
 int odis_get_dissipation_series(odis_solver* s, int64_t first, int64_t count, double* out);
+/* Forgets the series before the current step: entry 0 becomes the current state's, the steps counted since odis_set_state restart at 0.
+ * Whole runs (odis_run) call it at every output interval — the reference keeps no per-step series at all (energy.cpp:13-62 overwrites
+ * one scalar) — so that the series does not grow with the length of the run. */
+int odis_trim_dissipation_series(odis_solver* s);
 /* operators — the free functions the reference's loop calls (src/timeIntegrator.cpp:205-313), one call each, for a caller
  * that keeps the reference's own ab3Explicit and swaps single functions (integration/operators_b200.cpp holds the wrappers
  * with the reference's C++ signatures). Host arrays, reference numbering; each call copies its arguments to the device, runs
