@@ -524,7 +524,10 @@ def run_ours(args) -> None:
     edge_kernel = "edge_step_kernel" if (args.kernel_select & 1) else ("edge_step_pipe16_kernel" if narrow else "edge_step_pipe_kernel")
     achieved = edge_alg / (edge_us * 1e-6) / 1e9
     fused_sg = L >= 2 and L <= 4 and not (args.kernel_select & 1)
-    cell_alg = (128 + (32 if fused_sg else 0)) * part["own_cells"]
+    launches_per_step = launches / (K * S)
+    merged_sg = fused_sg and launches_per_step < 2.5        # solve + synthesis behind a grid barrier inside the cell update's launch
+    # per cell: 128 B of the update; + 32 B basis inputs of the folded analysis; + 64 B of the merged synthesis (basis inputs, {eta,U} r/w)
+    cell_alg = (128 + (32 if fused_sg else 0) + (64 if merged_sg else 0)) * part["own_cells"]
     roofline = {"bound": "hbm", "kernel": edge_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic_per_launch(edge_kernel) if world == 1 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": edge_alg, "avg_launch_us": round(edge_us, 2),
@@ -532,9 +535,11 @@ def run_ours(args) -> None:
                 "cell_step_kernel": {"kernel": "cell_step_kernel" if (args.kernel_select & 1) else "cell_step_pipe_kernel",
                                      "algorithmic_bytes_per_launch": cell_alg, "avg_launch_us": round(cell_us, 2),
                                      "achieved": round(cell_alg / (cell_us * 1e-6) / 1e9, 1), "frac": round(cell_alg / (cell_us * 1e-6) / 1e9 / peak, 4),
-                                     "note": "with the self-gravity term to degree <= 4 the harmonic analysis is accumulated inside this launch (+32 B per cell)"},
-                "self_gravity_kernels": {"avg_us_per_step": round(sh_us, 2), "launches_per_step": (1 if fused_sg else 3) if L >= 2 else 0,
-                                         "algorithmic_bytes_per_step": 64 * part["own_cells"] if L >= 2 else 0,
+                                     "note": "with the self-gravity term to degree <= 4 the harmonic analysis is accumulated inside this launch (+32 B per cell) "
+                                             "and, merged, so are solve + synthesis behind a grid-wide barrier (+64 B per cell, mostly L2 hits)"},
+                "self_gravity_kernels": {"avg_us_per_step": round(sh_us, 2) if not merged_sg else 0.0,
+                                         "launches_per_step": ((0 if merged_sg else 1) if fused_sg else 3) if L >= 2 else 0,
+                                         "algorithmic_bytes_per_step": (0 if merged_sg else 64 * part["own_cells"]) if L >= 2 else 0,
                                          "note": "matrix-free: the harmonic basis is rebuilt per cell by recurrence instead of streaming 8*(l_max+1)^2 B per cell"},
                 "whole_step": {"algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes * value / 1e9, 1),
                                "frac": round(alg_bytes * value / 1e9 / peak, 4), "frac_of_8TBs_nominal": round(alg_bytes * value / 8e12, 4),

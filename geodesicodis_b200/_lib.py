@@ -55,7 +55,7 @@ class PartitionPlan(C.Structure):
 
 class RunOptions(C.Structure):
     _fields_ = [("device", c_i32), ("reorder", c_i32), ("echo", c_i32), ("self_gravity", c_i32), ("max_steps", c_i64),
-                ("overlap_output", c_i32), ("reserved", c_i32)]
+                ("overlap_output", c_i32), ("n_gpus", c_i32)]
 
 
 class SnapshotView(C.Structure):

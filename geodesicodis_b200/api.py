@@ -311,12 +311,13 @@ class H5Writer:
 
 
 def run(run_dir: str, device: int = 0, reorder: bool = True, echo: bool = False, max_steps: int = 0, self_gravity: int = 0,
-        overlap_output: bool = False) -> dict:
+        overlap_output: bool = False, n_gpus: int = 1) -> dict:
     """`./ODIS` in run_dir: main -> solveODIS -> ab3Explicit (src/main.cpp:46-68), writing DATA/ and
     InitialConditions/ like the reference. Returns the run summary. self_gravity: 0 as reference HEAD; 1 the
     spherical-harmonic self-gravity / shell-pressure term with input.in's "sh degree" (2: stored-basis kernels).
-    overlap_output: dumps are copied out and written while the next output interval is being computed."""
-    opt = _lib.RunOptions(device, int(reorder), int(echo), int(self_gravity), max_steps, int(overlap_output), 0)
+    overlap_output: dumps are copied out and written while the next output interval is being computed.
+    n_gpus > 1: the grid partitioned over that many GPUs of this process (`ODIS --gpus N`)."""
+    opt = _lib.RunOptions(device, int(reorder), int(echo), int(self_gravity), max_steps, int(overlap_output), int(n_gpus))
     res = _lib.RunResult()
     check(_lib.load().odis_run(os.fsencode(run_dir), C.byref(opt), C.byref(res)))
     return {n: getattr(res, n) for n, _ in _lib.RunResult._fields_ if n != "reserved"}

@@ -690,7 +690,8 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     if (is_last) {
         // the last CTA to arrive adds the CTAs' partials in CTA order: all of a lane's loads in flight together, then the butterfly
         __threadfence();
-        double* bdst = kPart ? cx_pub(x.block[x.rank], (int)(epoch & 1ull)) : sg.b_out;
+        // partitioned: this rank's sums go into ITS slot of its own exchange block first ([parity][rank][kShXSlot]) ...
+        double* bdst = kPart ? cx_pub(x.block[x.rank], (int)(epoch & 1ull)) + (size_t)x.rank * kShXSlot : sg.b_out;
         constexpr int kMaxPerLane = 10;                               // grid <= 2 x 148 CTAs (cell_pipe_grid)
         for (int k = warp - 1; k < kRows; k += kConsumerWarps) {
             const double* row = sg.cta_partial + (size_t)k * sg.cta_stride;
@@ -706,8 +707,15 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         }
         if (!kMerged && ct == 0) *sg.ticket = 0u;
         if (kPart) {
-            // publish this rank's sums: epoch flag into every rank's exchange block (system-scope release)
+            // ... and are then PUSHED into the same slot of every other rank's block (peer stores), followed by the epoch flag
+            // (system-scope release): the readers find all ranks' sums in their own memory, no remote load on the critical path
             __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
+            for (int q = ct; q < x.world * kRows; q += kG * kTile) {
+                const int r = q / kRows, k = q - r * kRows;
+                if (r != x.rank) cx_pub(x.block[r], (int)(epoch & 1ull))[(size_t)x.rank * kShXSlot + k] = __ldcg(bdst + k);
+            }
+            __threadfence_system();
             asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
             __threadfence_system();
             if (ct < x.world) {
@@ -739,8 +747,8 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         if (ct < kRows) {
             double a = 0.0;
             for (int r = 0; r < x.world; r++) {               // rank order: the same bits on every rank and in every CTA
-                double v;
-                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(cx_pub(x.block[r], (int)(epoch & 1ull)) + ct) : "memory");
+                double v;                                    // (pushed into this rank's own block by rank r)
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(cx_pub(x.block[x.rank], (int)(epoch & 1ull)) + (size_t)r * kShXSlot + ct) : "memory");
                 a = a + v;
             }
             bsh[ct] = a;
@@ -943,8 +951,10 @@ static cudaError_t launch_cell_cfg(const CellTables& t, const Physics& p, const 
     constexpr int kEcc = LSG > 0 ? (int)P_ECC : -1;          // the one-potential build exists for the self-gravity variants (register pressure)
     const bool ecc = LSG > 0 && p.potential == P_ECC;
     if (LSG > 0 && sg.merged) {
-        if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), kEcc>, grid, kBlock, kCellSmem, stream, true, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
-        return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), -1>, grid, kBlock, kCellSmem, stream, true, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+        static int coop = -1;                 // experiments: ODIS_B200_COOP=0 launches the merged kernel without the cooperative attribute
+        if (coop < 0) { const char* e = std::getenv("ODIS_B200_COOP"); coop = (e && std::atoi(e) == 0) ? 0 : 1; }
+        if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), kEcc>, grid, kBlock, kCellSmem, stream, coop != 0, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+        return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), -1>, grid, kBlock, kCellSmem, stream, coop != 0, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
     }
     if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, kEcc>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
     return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, -1>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);

@@ -17,8 +17,9 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--quiet")) opt.echo = 0;
         else if (!std::strcmp(argv[i], "--self-gravity")) opt.self_gravity = 1;   // pressureGradientSH, off at reference HEAD
         else if (!std::strcmp(argv[i], "--overlap-output")) opt.overlap_output = 1;  // dumps written while the next interval is computed
+        else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) opt.n_gpus = std::atoi(argv[++i]);   // grid partitioned over N GPUs
         else if (!std::strcmp(argv[i], "--dir") && i + 1 < argc) dir = argv[++i];
-        else { std::fprintf(stderr, "usage: ODIS [--dir RUN_DIR] [--device N] [--max-steps K] [--quiet] [--self-gravity] [--overlap-output]\n"); return 2; }
+        else { std::fprintf(stderr, "usage: ODIS [--dir RUN_DIR] [--device N] [--gpus N] [--max-steps K] [--quiet] [--self-gravity] [--overlap-output]\n"); return 2; }
     }
     odis_run_result res{};
     const int rc = odis_run(dir, &opt, &res);

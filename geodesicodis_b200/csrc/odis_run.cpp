@@ -255,19 +255,64 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     p.shell_thickness = cfg.get_double("shell thickness"); p.semimajor_axis = cfg.get_double("semimajor axis");
     p.potential = cfg.tide_type; p.friction = cfg.fric_type; p.surface = cfg.surface_type;
     p.init_load = cfg.initial_condition == odis::INIT_LOAD; p.reorder = opt.reorder;
-    odis_solver* s = nullptr;
-    int rc = odis_create(&mv, &p, opt.device, &s);
+    // n_gpus > 1: the grid is cut into that many space-filling-curve parts, one solver per GPU (devices device .. device + n_gpus - 1) in
+    // this one process, halos exchanged by the step kernels through peer memory (main.cpp:46-64 knows one process; so does this)
+    const int world = opt.n_gpus > 1 ? opt.n_gpus : 1;
+    std::vector<odis_solver*> ranks((size_t)world, nullptr);
+    struct SolverGuard {                      // every return below releases the device memory and the streams
+        std::vector<odis_solver*>& h;
+        ~SolverGuard() { for (auto& x : h) if (x) { odis_destroy(x); x = nullptr; } }
+    } solver_guard{ranks};
+    int rc = ODIS_OK;
+    for (int r = 0; r < world && rc == ODIS_OK; r++)
+        rc = world == 1 ? odis_create(&mv, &p, opt.device, &ranks[(size_t)r])
+                        : odis_create_partitioned(&mv, &p, opt.device + r, r, world, &ranks[(size_t)r]);
     if (rc != ODIS_OK) return terminate(rc, odis_last_error());
-    struct SolverGuard {                      // every return below releases the device memory and the stream
-        odis_solver*& h;
-        ~SolverGuard() { if (h) { odis_destroy(h); h = nullptr; } }
-    } solver_guard{s};
+    if (world > 1) {
+        const size_t bs = (size_t)odis_halo_blob_size();
+        std::vector<unsigned char> blobs(bs * (size_t)world);
+        for (int r = 0; r < world && rc == ODIS_OK; r++) rc = odis_halo_export(ranks[(size_t)r], blobs.data() + bs * (size_t)r);
+        for (int r = 0; r < world && rc == ODIS_OK; r++) rc = odis_halo_connect(ranks[(size_t)r], blobs.data());
+        if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+        log.out("grid partitioned over " + std::to_string(world) + " GPUs");
+    }
+    odis_solver* const s = ranks[0];          // unpartitioned calls below (advection, output snapshots) go to the one solver
+    auto on_all = [&](auto&& call) {          // the same call on every rank, in rank order; first failure wins
+        int r2 = ODIS_OK;
+        for (int r = 0; r < world && r2 == ODIS_OK; r++) r2 = call(ranks[(size_t)r]);
+        return r2;
+    };
+    // a field of the whole grid: every rank fills its own entries and leaves zeros elsewhere, so the sum is the field
+    std::vector<double> part_buf;
+    auto get_field_all = [&](int32_t field, std::vector<double>& out) {
+        int r2 = odis_get_field(ranks[0], field, out.data());
+        for (int r = 1; r < world && r2 == ODIS_OK; r++) {
+            part_buf.resize(out.size());
+            r2 = odis_get_field(ranks[(size_t)r], field, part_buf.data());
+            if (r2 == ODIS_OK)
+                for (size_t i = 0; i < out.size(); i++) out[i] += part_buf[i];
+        }
+        return r2;
+    };
+    auto dissipation_all = [&](double* out) {         // sum of the ranks' shares of sum(eps_e A_e) / (4 pi r^2)
+        double tot = 0.0;
+        int r2 = ODIS_OK;
+        for (int r = 0; r < world && r2 == ODIS_OK; r++) {
+            double x = 0.0;
+            r2 = odis_get_dissipation_avg(ranks[(size_t)r], &x);
+            tot += x;
+        }
+        *out = tot;
+        return r2;
+    };
     // tables of the nonlinear branch: the step needs them with `advection; true` (updateMomentum.cpp:37, updateEta.cpp:32), the
     // Cartesian velocity output needs operatorRBFinterp either way (timeIntegrator.cpp:173,290)
     odis::NonlinearTables nlt;
     if (cfg.get_bool("advection") || ds_ux >= 0) {
         if (odis::build_nonlinear_tables(mesh, mesh.radius, cfg.get_double("rbf epsilon"), nlt, err) != 0) return terminate(ODIS_ERR_GRID, err);
     }
+    if (cfg.get_bool("advection") && world > 1)
+        return terminate(ODIS_ERR_UNSUPPORTED, "advection; true runs on one GPU (the nonlinear branch is not partitioned)");
     if (cfg.get_bool("advection")) {
         auto csr = [](const odis::Csr& A) {
             odis_csr_view v;
@@ -287,7 +332,7 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
                                             : (cfg.surface_type == odis::LID_LOVE || cfg.surface_type == odis::LID_MEMBR) ? &cfg.shell_factor_beta : nullptr;
         if (!factor || (int)factor->size() < l_max + 1)
             return terminate(ODIS_ERR_CONFIG, "self-gravity needs a FREE_LOADING or LID_* surface with its per-degree factors (boundaryConditions.cpp)");
-        rc = odis_enable_self_gravity(s, &mv, l_max, factor->data(), opt.self_gravity == 2 ? 1 : 0);
+        rc = on_all([&](odis_solver* h) { return odis_enable_self_gravity(h, &mv, l_max, factor->data(), opt.self_gravity == 2 ? 1 : 0); });
         if (rc != ODIS_OK) return terminate(rc, odis_last_error());
         log.out("self-gravity / shell pressure term: spherical harmonics to degree " + std::to_string(l_max));
     }
@@ -303,12 +348,12 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fv);
         if (lp == 0) log.out("\nFound initial conditions file: " + fp);
         else log.err("WARNING: NO INITIAL CONDITION FILE FOUND " + fp);
-        rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
+        rc = on_all([&](odis_solver* h) { return odis_set_state(h, v.data(), eta.data(), dv.data(), de.data(), 0); });
         if (rc != ODIS_OK) return terminate(rc, odis_last_error());
     }
     if (cfg.initial_condition == odis::INIT_ANALYTICAL) {                     // initialConditions.cpp:311-313
         rc = odis_analytical_state(&mv, &p, v.data(), dv.data(), eta.data(), de.data());
-        if (rc == ODIS_OK) rc = odis_set_state(s, v.data(), eta.data(), dv.data(), de.data(), 0);
+        if (rc == ODIS_OK) rc = on_all([&](odis_solver* h) { return odis_set_state(h, v.data(), eta.data(), dv.data(), de.data(), 0); });
         if (rc != ODIS_OK) return terminate(rc, odis_last_error());
     }
     log.out("Defining arrays for Adams-Bashforth time integration...");       // timeIntegrator.cpp:140
@@ -322,19 +367,19 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     int64_t iter = 0;
     double e_diss = 0.0;
     auto dump = [&](double current_time) -> int {                             // timeIntegrator.cpp:190-196,296-302 + DumpData
-        int rc2 = odis_get_dissipation_avg(s, &e_diss);
+        int rc2 = dissipation_all(&e_diss);
         if (rc2) return rc2;
         log.out(fmt("DUMPING DATA AT %f AVG DISS: %e GW%d", current_time / period, e_diss * 4 * odis::kPi * r * r / 1e9, out_count));
         const uint64_t row = (uint64_t)(out_count - 1);
         if (row < T) {                                                         // beyond the extent HDF5 refuses the selection
             if (ds_u >= 0) {
-                if ((rc2 = odis_get_field(s, ODIS_FIELD_VELOCITY_EN, ven.data()))) return rc2;
+                if ((rc2 = get_field_all(ODIS_FIELD_VELOCITY_EN, ven))) return rc2;
                 for (int i = 0; i < F; i++) { fa[i] = (float)ven[(size_t)i * 2]; fb[i] = (float)ven[(size_t)i * 2 + 1]; }   // outFiles.cpp:546-553
                 wr(h5.write_rows(ds_u, row, 1, fa.data(), err));
                 wr(h5.write_rows(ds_v, row, 1, fb.data(), err));
             }
             if (ds_ux >= 0) {                                                  // interpolateVelocityCartRBF, interpolation.cpp:116; outFiles.cpp:567-590
-                if ((rc2 = odis_get_field(s, ODIS_FIELD_VELOCITY, vcur.data()))) return rc2;
+                if ((rc2 = get_field_all(ODIS_FIELD_VELOCITY, vcur))) return rc2;
                 const odis::Csr& A = nlt.rbf_interp;
                 for (int c = 0; c < 3; c++) {
                     for (int i = 0; i < N; i++) {
@@ -346,12 +391,12 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
                 }
             }
             if (ds_eta >= 0) {
-                if ((rc2 = odis_get_field(s, ODIS_FIELD_ETA, eta.data()))) return rc2;
+                if ((rc2 = get_field_all(ODIS_FIELD_ETA, eta))) return rc2;
                 for (int i = 0; i < N; i++) fa[i] = (float)eta[i];
                 wr(h5.write_rows(ds_eta, row, 1, fa.data(), err));
             }
             if (ds_diss >= 0) {
-                if ((rc2 = odis_get_field(s, ODIS_FIELD_DISSIPATION, ediss.data()))) return rc2;
+                if ((rc2 = get_field_all(ODIS_FIELD_DISSIPATION, ediss))) return rc2;
                 for (int i = 0; i < F; i++) fa[i] = (float)ediss[i];
                 wr(h5.write_rows(ds_diss, row, 1, fa.data(), err));
             }
@@ -367,7 +412,7 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     // Overlapped output (options.overlap_output): a dump is split into begin (the copy-out is enqueued behind the steps taken so far,
     // odis_snapshot_begin) and finish (wait for the copy, log line, float conversion, data.h5 rows). The next interval's steps are
     // enqueued between the two, so the GPU computes them while the host writes. Same files as the synchronous path.
-    const bool overlap = opt.overlap_output != 0;
+    const bool overlap = opt.overlap_output != 0 && world == 1;        // output snapshots need the unpartitioned solver
     uint32_t snap_fields = 0;
     if (ds_u >= 0) snap_fields |= ODIS_SNAP_VELOCITY_EN;
     if (ds_ux >= 0) snap_fields |= ODIS_SNAP_VELOCITY;
@@ -439,16 +484,16 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
         if (n > left) n = left;
         if (opt.max_steps > 0 && iter + n > opt.max_steps) n = opt.max_steps - iter;
         if (n <= 0) break;
-        if (stepping) rc = odis_step(s, (int32_t)n);                           // asynchronous: enqueued behind a pending snapshot
+        if (stepping) rc = on_all([&](odis_solver* h) { return odis_step(h, (int32_t)n); });   // asynchronous: enqueued behind a pending snapshot
         if (rc != ODIS_OK) break;
         if (overlap && (rc = finish_dump()) != ODIS_OK) break;                 // the previous dump is written while these steps run
         iter += n;
         if (iter % out_freq == 0) rc = overlap ? begin_dump(dt * (double)iter) : dump(dt * (double)iter);   // timeIntegrator.cpp:280-304
-        else rc = odis_synchronize(s);
+        else rc = on_all([&](odis_solver* h) { return odis_synchronize(h); });
         if (rc == ODIS_OK && io_rc != ODIS_OK) break;                          // stop at the first failed write
         // the run reads only the newest entry of the per-step dissipation series: forget the older ones, so that a 150-orbit run
         // (7 million steps) keeps a few KB of series instead of growing it by 56 B per step
-        if (rc == ODIS_OK) rc = odis_trim_dissipation_series(s);
+        if (rc == ODIS_OK) rc = on_all([&](odis_solver* h) { return odis_trim_dissipation_series(h); });
         if (g_sigint) {                                                        // :307-312
             if (overlap && rc == ODIS_OK) rc = finish_dump();
             log.out("Terminate signal caught...");
@@ -462,15 +507,18 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
 
     // restart files (writeInitialConditions, initialConditions.cpp:209-276)
     ::mkdir((dir + "/InitialConditions").c_str(), 0770);
-    if (odis_get_field(s, ODIS_FIELD_VELOCITY, v.data()) == ODIS_OK && odis_get_field(s, ODIS_FIELD_DVDT, dv.data()) == ODIS_OK &&
-        odis_get_field(s, ODIS_FIELD_ETA, eta.data()) == ODIS_OK && odis_get_field(s, ODIS_FIELD_DETADT, de.data()) == ODIS_OK) {
+    if (get_field_all(ODIS_FIELD_VELOCITY, v) == ODIS_OK && get_field_all(ODIS_FIELD_DVDT, dv) == ODIS_OK &&
+        get_field_all(ODIS_FIELD_ETA, eta) == ODIS_OK && get_field_all(ODIS_FIELD_DETADT, de) == ODIS_OK) {
         write_restart(dir + "/InitialConditions/vel_init.txt", (size_t)F, v, dv);
         write_restart(dir + "/InitialConditions/pres_init.txt", (size_t)N, eta, de);
     }
     int64_t launches = 0;
-    odis_get_launch_count(s, &launches);
-    odis_destroy(s);
-    s = nullptr;                                                               // (the guard holds a reference to this pointer)
+    for (int r = 0; r < world; r++) {
+        int64_t l = 0;
+        odis_get_launch_count(ranks[(size_t)r], &l);
+        launches += l;
+    }
+    for (auto& h : ranks) { odis_destroy(h); h = nullptr; }
     if (h5.close(err) != 0) return terminate(ODIS_ERR_IO, "closing DATA/data.h5 failed: " + err);
     res->steps = iter;
     res->n_cells = N; res->n_edges = F;

@@ -416,8 +416,8 @@ __global__ void __launch_bounds__(kShThreads) sh_bsolve_synthesis_mf_kernel(ShTa
         }
         __syncthreads();
         for (int k = threadIdx.x; k < t.rows; k += kShThreads) {
-            double a = 0.0;
-            for (int r = 0; r < x.world; r++) a = a + ld_relaxed_sys(x_pub(x.block[r], (int)(epoch & 1)) + k);
+            double a = 0.0;                                  // every rank pushed its sums into this rank's own block: [parity][rank][kShXSlot]
+            for (int r = 0; r < x.world; r++) a = a + ld_relaxed_sys(x_pub(x.block[x.rank], (int)(epoch & 1)) + (size_t)r * kShXSlot + k);
             bsh[k] = a;
             if (blockIdx.x == 0) w.b[k] = a;
         }

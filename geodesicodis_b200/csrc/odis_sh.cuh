@@ -55,6 +55,10 @@ cudaError_t sh_configure();           // dynamic shared-memory opt-in of the mat
 // A rank cannot be more than one epoch ahead of any other (the next allsolve needs everyone's publish), hence two buffers.
 constexpr int kShMaxWorld = 8;
 constexpr int kShXRows = 1024;
+// The folded analysis of the staged cell update (degrees <= 4: at most 25 sums) PUSHES instead: a rank writes its sums into slot
+// [parity][rank][kShXSlot] of EVERY rank's block before it raises its flags, so that the readers sum from their own memory.
+constexpr int kShXSlot = 32;
+static_assert(kShMaxWorld * kShXSlot <= kShXRows, "push layout fits one parity buffer");
 constexpr size_t kShXBytes = kShMaxWorld * sizeof(unsigned long long) + 2 * (size_t)kShXRows * sizeof(double);
 struct ShExchange {
     int world, rank;

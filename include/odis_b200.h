@@ -401,7 +401,10 @@ typedef struct odis_run_options {
     int64_t max_steps;    /* > 0: stop after this many steps even if the loop bound is larger */
     int32_t overlap_output; /* 1: dumps go through odis_snapshot_begin/_wait: the next output interval is computed while the previous
                              * dump is copied out and written to data.h5 (same datasets, log lines and restart files). 0: synchronous dumps */
-    int32_t reserved;
+    int32_t n_gpus;       /* 0 or 1: one GPU. N > 1: the grid is cut into N space-filling-curve parts, one partitioned solver per GPU
+                           * (devices device .. device + N - 1) driven from this one process; halos and harmonic sums are exchanged by the
+                           * step kernels through peer memory. Same files as the one-GPU run (bit-identical without the self-gravity
+                           * term). Not with `advection; true` or overlap_output. */
 } odis_run_options;
 
 typedef struct odis_run_result {

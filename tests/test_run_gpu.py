@@ -119,3 +119,33 @@ def test_cli_binary(odis, tmp_path):
     assert dumping_lines(out) == dumping_lines(str(case["output_txt"]))
     r = subprocess.run([exe, "--quiet", "--dir", os.path.join(d, "nowhere")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "ODIS HAS FOUND AN ERROR" in r.stdout          # the reference exits 0 from TerminateODIS
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_whole_run_writes_the_same_files(odis, tmp_path, world):
+    """`ODIS --gpus N` (odis_run with n_gpus: one partitioned solver per GPU, driven from the one process): the same run directory gives the
+    same data.h5, progress lines and restart files as on one GPU — bit for bit, the halo exchange changes where a value lives, never its
+    arithmetic (the energy sum associates per rank: float32 round-off at most). Reference: src/main.cpp:46-64 -> solveODIS -> ab3Explicit."""
+    from test_multigpu import _device_count
+    if _device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    case = load_case("l4_ecc_enceladus")
+    d1 = make_run_dir(tmp_path / "one", case)
+    dn = make_run_dir(tmp_path / "many", case)
+    r1 = odis.run(d1)
+    rn = odis.run(dn, n_gpus=world)
+    assert rn["steps"] == r1["steps"] == int(case["nsteps"]) and rn["dumps"] == r1["dumps"] and rn["dt"] == r1["dt"]
+    h1, hn = read_h5(os.path.join(d1, "DATA", "data.h5")), read_h5(os.path.join(dn, "DATA", "data.h5"))
+    assert sorted(h1) == sorted(hn)
+    for name in h1:
+        if name in ("dissipation avg output",):
+            assert np.abs(hn[name] - h1[name]).max() <= 2e-7 * np.abs(h1[name]).max(), name
+        else:
+            assert np.array_equal(hn[name], h1[name]), name
+    out1, outn = open(os.path.join(d1, "DATA", "OUTPUT.txt")).read(), open(os.path.join(dn, "DATA", "OUTPUT.txt")).read()
+    assert dumping_lines(outn) == dumping_lines(out1) and "grid partitioned over %d GPUs" % world in outn
+    for f in ("vel_init.txt", "pres_init.txt"):
+        assert open(os.path.join(dn, "InitialConditions", f)).read() == open(os.path.join(d1, "InitialConditions", f)).read()
+    # against the reference's own float32 rows too
+    ref = {k[3:]: case[k] for k in case if k.startswith("h5_")}
+    assert np.array_equal(hn["displacement"], ref["displacement"])
