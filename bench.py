@@ -408,6 +408,11 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
+        # the device is drained BEFORE the collective: a partitioned step in flight waits in-kernel for the neighbours' flags, and the
+        # merged cell kernel is a cooperative launch (all CTAs resident together) — an NCCL kernel squeezed in beside it would wait for a
+        # peer whose own NCCL kernel cannot start behind ITS in-flight steps: a cycle. (include/odis_b200.h, odis_step: synchronize
+        # partitioned solvers before any other operation that waits on another GPU.)
+        torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -667,7 +672,7 @@ def synthetic_l10_partitioned(odis, dist, torch, rank, local_rank, world, reduce
             solver.halo_connect(blobs)
         stage(connect)
         out["setup_s"] = round(time.time() - t0, 1)
-        stage(lambda: solver.step(24))
+        stage(lambda: (solver.step(24), solver.synchronize()))      # drained before the next collective (see barrier())
         barrier()
         ms = stage(lambda: solver.step_timed(200))
         torch.cuda.synchronize()

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -759,6 +760,14 @@ int odis_get_partition(odis_solver* s, int32_t* rank, int32_t* world, int32_t* o
 
 static int finish_set_state(odis_solver* s, int64_t iter, bool sync);
 
+// host threads for packing / spreading a partitioned solver's entries: the launcher of multi-process runs (torchrun) sets
+// OMP_NUM_THREADS=1, which would leave these memory-bound loops on one core; every rank takes its share of the cores instead
+static int pack_threads(const odis_solver* s) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int share = (int)(hw ? hw : 8u) / (s->world > 0 ? s->world : 1);
+    return std::max(1, std::min(16, share));
+}
+
 // page-locked staging of a partitioned solver (at least `doubles` entries); waits for copies still reading the previous content
 static int ensure_pack(odis_solver* s, size_t doubles) {
     if (s->pack_pending) {
@@ -782,20 +791,21 @@ static int set_state_partitioned(odis_solver* s, const double* v, const double* 
     if (rc) return rc;
     double* hv = s->h_pack; double* hdv = hv + F; double* he = hdv + 3 * Fo; double* hde = he + N;
     const int* ep = s->edge_perm.data(); const int* cp = s->cell_perm.data();
+    const int nt = pack_threads(s);
     if (v) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)F; i++) hv[i] = v[ep[i]];
     }
     if (dvdt) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)Fo; i++) { const size_t o = (size_t)ep[i] * 3; hdv[3 * i] = dvdt[o]; hdv[3 * i + 1] = dvdt[o + 1]; hdv[3 * i + 2] = dvdt[o + 2]; }
     }
     if (eta) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)N; i++) he[i] = eta[cp[i]];
     }
     if (detadt) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)N; i++) { const size_t o = (size_t)cp[i] * 3; hde[3 * i] = detadt[o]; hde[3 * i + 1] = detadt[o + 1]; hde[3 * i + 2] = detadt[o + 2]; }
     }
     // d_stage holds max(3 Fg, F + 3 Fo + 4 N) doubles (create_impl): the four packed arrays side by side
@@ -1417,11 +1427,12 @@ int odis_get_field(odis_solver* s, int32_t field, double* out) {
     std::memset(out, 0, count * sizeof(double));
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     const double* h = s->h_pack;
+    const int nt = pack_threads(s);
     if (comps == 1) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)own; i++) out[hperm[i]] = h[i];
     } else {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)own; i++)
             for (size_t c = 0; c < comps; c++) out[(size_t)hperm[i] * comps + c] = h[(size_t)i * comps + c];
     }

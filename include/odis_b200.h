@@ -211,7 +211,11 @@ int odis_analytical_state(const odis_mesh_view* mesh, const odis_params* params,
  * steps already taken (current_time = dt*iter, src/timeIntegrator.cpp:187,277). */
 int odis_set_state(odis_solver* s, const double* v, const double* eta, const double* dvdt /*[F][3]*/,
                    const double* detadt /*[N][3]*/, int64_t iter);
-/* Advance nsteps time steps (asynchronous on the solver's stream; odis_get_* synchronise). */
+/* Advance nsteps time steps (asynchronous on the solver's stream; odis_get_* synchronise).
+ * Partitioned solvers: the steps in flight wait INSIDE the kernels for the neighbours' flags (bounded: ~10 s, ODIS_B200_WAIT_TIMEOUT_S),
+ * so every rank must take the same steps, and the stream must be drained (odis_synchronize) before the caller runs anything ELSE
+ * that waits on another GPU on the same device — e.g. an NCCL collective: its kernel, resident beside a step that waits for a peer
+ * whose own collective is queued behind ITS steps, closes a cycle that only the time limit ends (reported as ODIS_ERR_STATE). */
 int odis_step(odis_solver* s, int32_t nsteps);
 /* As odis_step, bracketed by CUDA events on the solver's stream; returns elapsed device ms. */
 int odis_step_timed(odis_solver* s, int32_t nsteps, float* elapsed_ms_out);
