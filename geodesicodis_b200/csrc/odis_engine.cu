@@ -991,7 +991,10 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
         ODIS_CUDA(cudaMemsetAsync(s->d_sg_cta, 0, (size_t)rows * s->sg_cta_stride * sizeof(double), s->stream));
         ODIS_CUDA(cudaMemsetAsync(s->d_sg_ticket, 0, 32 * sizeof(unsigned int), s->stream));
         s->sh_fused = true;
-        s->sh_merged = odis::cell_pipe_merged();
+        // merged solve + synthesis (grid-wide barrier, cooperative launch) on unpartitioned solvers; partitioned ones keep the separate
+        // launch: measured faster there (655,362 cells on 8 GPUs: 48.9 vs 52.0 us per step), and no kernel of theirs then needs all of
+        // its CTAs resident at once, so a collective of the caller's running beside the steps cannot close a wait cycle
+        s->sh_merged = odis::cell_pipe_merged() && s->world == 1;
     }
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);     // captured without the extra launches

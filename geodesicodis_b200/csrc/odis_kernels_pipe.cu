@@ -194,7 +194,12 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
                 EdgeStage* d = stages + st;
                 const size_t e0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kTile;
                 const bool narrow = kIds16 && wide_s[i] == 0;
-                mbar_expect_tx(full + st, narrow ? kEdgeStageBytes - (uint32_t)sizeof(d->sid) + kNarrowIdBytes : kEdgeStageBytes);
+                // {v,l} of the tile's own edges only: behind the last own edge the array holds ghost slots, which the neighbours write
+                // while this kernel runs (the lanes beyond n_edges are idle anyway)
+                const int own_n = min(kTile, t.n_edges - (int)e0);
+                const uint32_t own_bytes = (uint32_t)own_n * (uint32_t)sizeof(double2);
+                mbar_expect_tx(full + st, (narrow ? kEdgeStageBytes - (uint32_t)sizeof(d->sid) + kNarrowIdBytes : kEdgeStageBytes) -
+                                              (uint32_t)sizeof(d->own) + own_bytes);
                 if (narrow) bulk_g2s(d->sid, sid16 + (e0 / kTile) * (size_t)(kStencil * kTile), kNarrowIdBytes, full + st, pol);
                 else {
 #pragma unroll
@@ -206,7 +211,7 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
                 bulk_g2s(d->grad, t.grad + e0, kTile * 16, full + st, pol);
                 bulk_g2s(d->dist, t.dist + e0, kTile * 8, full + st, pol);
                 bulk_g2s(d->fcor, t.fcor + e0, kTile * 8, full + st, pol);
-                bulk_g2s(d->own, s.vl_in + e0, kTile * 16, full + st, pol);
+                bulk_g2s(d->own, s.vl_in + e0, own_bytes, full + st, pol);
                 bulk_g2s(d->h1, s.h1 + e0, kTile * 8, full + st, pol);
                 bulk_g2s(d->h2, s.h2 + e0, kTile * 8, full + st, pol);
             }
@@ -225,6 +230,12 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
         const bool bnd_tile = (e - tl) < halo.n_bnd;
         mbar_wait(full + st, (i / kStages) & 1);
         double e_area = 0.0;
+        // boundary edges: where the new value goes (CSR over the boundary edges), requested now so that the look-up overlaps the gathers
+        int k0 = 0, k1 = 0, peer0 = 0, slot0 = 0;
+        if (e < halo.n_bnd) {
+            k0 = halo.send_first[e]; k1 = halo.send_first[e + 1];
+            if (k1 > k0) { peer0 = halo.send_peer[k0]; slot0 = halo.send_remote[k0]; }
+        }
         if (e < t.n_edges) {
             // gathers first (their addresses come from shared memory), arithmetic after
             double2 nb[kStencil];
@@ -264,9 +275,9 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
             s.vl_out[e] = make_double2(v, own.y);
             if (mode == AB3_SECOND) s.h1[e] = f0;
             else s.h2[e] = f0;
-            if (e < halo.n_bnd) {                          // into the neighbours' ghost slots (direct stores over NVLink)
-                const int k1 = halo.send_first[e + 1];
-                for (int k = halo.send_first[e]; k < k1; k++) halo.remote.data[halo.send_peer[k]][halo.send_remote[k]] = make_double2(v, own.y);
+            if (k1 > k0) {                                 // into the neighbours' ghost slots (direct stores over NVLink)
+                halo.remote.data[peer0][slot0] = make_double2(v, own.y);
+                for (int k = k0 + 1; k < k1; k++) halo.remote.data[halo.send_peer[k]][halo.send_remote[k]] = make_double2(v, own.y);
             }
         }
         __syncwarp();
@@ -436,6 +447,22 @@ __device__ __forceinline__ void halo_wait_all(const HaloWait& w, StepCtl* ctl) {
     }
     if (late) ctl->pad = 1ull;      // a neighbour never arrived: reported by the host (ODIS_ERR_STATE), no hang
 }
+// the same by a whole warp: lane k polls neighbour k (the waits overlap instead of adding up), then the warp joins
+__device__ __forceinline__ void halo_wait_warp(const HaloWait& w, StepCtl* ctl) {
+    const int lane = threadIdx.x & 31;
+    if (lane < w.n_peers) {
+        const unsigned long long ev = ((volatile unsigned long long*)ctl->epoch)[0];
+        const long long limit = ctl->spin_cycles > 0 ? ctl->spin_cycles : kHaloSpinCycles;
+        const long long t0 = clock64();
+        unsigned long long seen;
+        const unsigned long long* fv = w.flag[lane];
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fv) : "memory");
+        } while (seen < ev && clock64() - t0 < limit);
+        if (seen < ev) ctl->pad = 1ull;
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ unsigned long long* cx_flags(unsigned char* block) { return reinterpret_cast<unsigned long long*>(block); }
 __device__ __forceinline__ double* cx_pub(unsigned char* block, int parity) {
     return reinterpret_cast<double*>(block + kShMaxWorld * sizeof(unsigned long long)) + (size_t)parity * kShXRows;
@@ -561,6 +588,7 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     double acc[kRows];
 #pragma unroll
     for (int k = 0; k < kRows; k++) acc[k] = 0.0;
+    bool halo_seen = false;
     for (int i = g; i < my_tiles; i += kG) {
         const int st = i % kS;
         const CellStage* d = stages + st;
@@ -572,9 +600,9 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         int packed[kCellEdges];
 #pragma unroll
         for (int j = 0; j < kCellEdges; j++) packed[j] = d->eid[j][tl];
-        if (bnd_tile) {
-            if (lane == 0) halo_wait_all(halo.wait_v, halo.ctl);
-            __syncwarp();
+        if (bnd_tile && !halo_seen) {                    // flags only grow: one wait per warp and launch
+            halo_wait_warp(halo.wait_v, halo.ctl);
+            halo_seen = true;
         }
         // the six {v,l} gathers go out first; the rest of the stage is read (and the stage released) while they are in flight. A cell's
         // edges fill the slots from 0 (ascending reference id), so only slot 5 can be empty (the 12 pentagons); padded cells gather nothing.
