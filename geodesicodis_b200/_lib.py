@@ -96,6 +96,7 @@ SIGNATURES = {
     "odis_halo_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "odis_halo_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "odis_get_partition": (C.c_int, [C.c_void_p] + [P(c_i32)] * 7),
+    "odis_get_partition_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "odis_partition_plan": (C.c_int, [P(MeshView), c_i32, c_i32, c_i32, P(PartitionPlan)]),
     "odis_partition_plan_free": (None, [P(PartitionPlan)]),
     "odis_analytical_state": (C.c_int, [P(MeshView), P(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

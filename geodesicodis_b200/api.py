@@ -362,6 +362,14 @@ class Solver:
         check(_lib.load().odis_get_partition(self._h, *[C.byref(x) for x in v]))
         return dict(zip(("rank", "world", "own_cells", "own_edges", "ghost_cells", "ghost_edges", "n_peers"), (x.value for x in v)))
 
+    def partition_map(self) -> tuple[np.ndarray, np.ndarray]:
+        """(reference ids of the own cells, of the own edges) in the order of the solver's device arrays = the order of a partitioned
+        solver's compact snapshot arrays."""
+        p = self.partition()
+        c, e = np.empty(p["own_cells"], dtype=np.int32), np.empty(p["own_edges"], dtype=np.int32)
+        check(_lib.load().odis_get_partition_map(self._h, c.ctypes.data, e.ctypes.data))
+        return c, e
+
     @property
     def steps_since_state(self) -> int:
         return self.iter - self._iter0
@@ -484,8 +492,11 @@ class Solver:
         view = _lib.SnapshotView()
         check(_lib.load().odis_snapshot_wait(self._h, slot, C.byref(view)))
         out = {"dissipation_avg": view.dissipation_avg, "iter": view.iter}
-        for name, n, shape in (("eta", self.N, (self.N,)), ("velocity_en", 2 * self.F, (self.F, 2)), ("dissipation", self.F, (self.F,)),
-                               ("velocity", self.F, (self.F,))):
+        N, F = self.N, self.F
+        if self.world > 1:                       # the rank's own entries, compact, in partition_map() order
+            p = self.partition()
+            N, F = p["own_cells"], p["own_edges"]
+        for name, n, shape in (("eta", N, (N,)), ("velocity_en", 2 * F, (F, 2)), ("dissipation", F, (F,)), ("velocity", F, (F,))):
             ptr = getattr(view, name)
             if ptr:
                 a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)

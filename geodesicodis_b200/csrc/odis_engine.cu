@@ -173,6 +173,7 @@ struct odis_solver {
     cudaEvent_t staged = nullptr, consumed = nullptr;
     bool stage_pending = false, stage_used = false;
     unsigned stage_mask = 0;                 // bit k: array k of the staged state was given (others are zero)
+    double* h_stage_pack = nullptr;          // partitioned: page-locked copy of this rank's share of the staged state (pack_partitioned)
 
     // partitioned solvers move only the entries they hold across PCIe: page-locked host buffer for the packed state / fields
     double* h_pack = nullptr;
@@ -681,6 +682,14 @@ int odis_create_partitioned(const odis_mesh_view* mv, const odis_params* prm, in
     return create_impl(mv, prm, device, rank, world, out);
 }
 
+// reference ids of the entries a (partitioned) solver owns, in device order: the order of its compact snapshots
+int odis_get_partition_map(odis_solver* s, int32_t* own_cell_ref_out, int32_t* own_edge_ref_out) {
+    if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
+    if (own_cell_ref_out) std::memcpy(own_cell_ref_out, s->cell_perm.data(), (size_t)s->No * sizeof(int32_t));
+    if (own_edge_ref_out) std::memcpy(own_edge_ref_out, s->edge_perm.data(), (size_t)s->Fo * sizeof(int32_t));
+    return ODIS_OK;
+}
+
 int odis_halo_blob_size(void) { return (int)sizeof(HaloBlob); }
 
 int odis_halo_export(odis_solver* s, void* blob_out) {
@@ -783,13 +792,11 @@ static int ensure_pack(odis_solver* s, size_t doubles) {
     return ODIS_OK;
 }
 
-// odis_set_state of a partitioned solver: the rank packs the entries it holds (own + halo) out of the caller's global arrays into
-// page-locked memory, in device order, and uploads only those — 1/world of the state instead of all of it per rank
-static int set_state_partitioned(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt) {
+// A partitioned solver's share of the caller's GLOBAL (reference-ordered) state arrays, packed in device order into page-locked
+// memory: [v F | dvdt 3 Fo | eta N | detadt 3 N] (own + halo entries; the velocity history of the own edges only)
+static void pack_partitioned(const odis_solver* s, double* dst, const double* v, const double* eta, const double* dvdt, const double* detadt) {
     const size_t N = (size_t)s->N, F = (size_t)s->F, Fo = (size_t)s->Fo;
-    int rc = ensure_pack(s, F + 3 * Fo + 4 * N);
-    if (rc) return rc;
-    double* hv = s->h_pack; double* hdv = hv + F; double* he = hdv + 3 * Fo; double* hde = he + N;
+    double* hv = dst; double* hdv = hv + F; double* he = hdv + 3 * Fo; double* hde = he + N;
     const int* ep = s->edge_perm.data(); const int* cp = s->cell_perm.data();
     const int nt = pack_threads(s);
     if (v) {
@@ -808,20 +815,42 @@ static int set_state_partitioned(odis_solver* s, const double* v, const double* 
 #pragma omp parallel for schedule(static) num_threads(nt)
         for (long long i = 0; i < (long long)N; i++) { const size_t o = (size_t)cp[i] * 3; hde[3 * i] = detadt[o]; hde[3 * i + 1] = detadt[o + 1]; hde[3 * i + 2] = detadt[o + 2]; }
     }
+}
+
+// the four packed arrays, host -> device side by side at `d` (layout of pack_partitioned); mask bit k: array k was given
+static int upload_partitioned(odis_solver* s, double* d, const double* h, unsigned mask, cudaStream_t stream) {
+    const size_t N = (size_t)s->N, F = (size_t)s->F, Fo = (size_t)s->Fo;
+    const size_t off[4] = {0, F, F + 3 * Fo, F + 3 * Fo + N}, cnt[4] = {F, 3 * Fo, N, 3 * N};
+    for (int k = 0; k < 4; k++)
+        if (mask & (1u << k)) ODIS_CUDA(cudaMemcpyAsync(d + off[k], h + off[k], cnt[k] * sizeof(double), cudaMemcpyHostToDevice, stream));
+    return ODIS_OK;
+}
+
+// ... and from there into the state (already in device order: no permutation)
+static void scatter_partitioned(odis_solver* s, const double* d, unsigned mask) {
+    const size_t N = (size_t)s->N, F = (size_t)s->F, Fo = (size_t)s->Fo;
+    const double* dv = d; const double* ddv = dv + F; const double* de = ddv + 3 * Fo; const double* dde = de + N;
+    odis::launch_scatter_x(s->F, nullptr, (mask & 1u) ? dv : nullptr, s->d_vl[s->cur], 0, s->stream);
+    s->hv1 = 0;
+    odis::launch_scatter_history(s->Fo, nullptr, (mask & 2u) ? ddv : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
+    odis::launch_scatter_x(s->N, nullptr, (mask & 4u) ? de : nullptr, s->d_eu[s->ecur], 1, s->stream);
+    s->he1 = 0; s->he2 = 1; s->hefree = 2;
+    odis::launch_scatter_history(s->N, nullptr, (mask & 8u) ? dde : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+}
+
+// odis_set_state of a partitioned solver: the rank packs the entries it holds (own + halo) out of the caller's global arrays into
+// page-locked memory, in device order, and uploads only those — 1/world of the state instead of all of it per rank
+static int set_state_partitioned(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt) {
+    const size_t N = (size_t)s->N, F = (size_t)s->F, Fo = (size_t)s->Fo;
+    int rc = ensure_pack(s, F + 3 * Fo + 4 * N);
+    if (rc) return rc;
+    pack_partitioned(s, s->h_pack, v, eta, dvdt, detadt);
+    const unsigned mask = (v ? 1u : 0u) | (dvdt ? 2u : 0u) | (eta ? 4u : 0u) | (detadt ? 8u : 0u);
     // d_stage holds max(3 Fg, F + 3 Fo + 4 N) doubles (create_impl): the four packed arrays side by side
-    double* dv = s->d_stage; double* ddv = dv + F; double* de = ddv + 3 * Fo; double* dde = de + N;
-    if (v) ODIS_CUDA(cudaMemcpyAsync(dv, hv, F * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    if (dvdt) ODIS_CUDA(cudaMemcpyAsync(ddv, hdv, 3 * Fo * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    if (eta) ODIS_CUDA(cudaMemcpyAsync(de, he, N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    if (detadt) ODIS_CUDA(cudaMemcpyAsync(dde, hde, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if ((rc = upload_partitioned(s, s->d_stage, s->h_pack, mask, s->stream))) return rc;
     ODIS_CUDA(cudaEventRecord(s->pack_done, s->stream));
     s->pack_pending = true;
-    odis::launch_scatter_x(s->F, nullptr, v ? dv : nullptr, s->d_vl[s->cur], 0, s->stream);
-    s->hv1 = 0;
-    odis::launch_scatter_history(s->Fo, nullptr, dvdt ? ddv : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
-    odis::launch_scatter_x(s->N, nullptr, eta ? de : nullptr, s->d_eu[s->ecur], 1, s->stream);
-    s->he1 = 0; s->he2 = 1; s->hefree = 2;
-    odis::launch_scatter_history(s->N, nullptr, detadt ? dde : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    scatter_partitioned(s, s->d_stage, mask);
     return ODIS_OK;
 }
 
@@ -895,28 +924,39 @@ static int finish_set_state(odis_solver* s, int64_t iter, bool sync) {
 // odis_stage_state waits (on the device) until the commit has consumed the staging area.
 int odis_stage_state(odis_solver* s, const double* v, const double* eta, const double* dvdt, const double* detadt) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
-    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "staged state needs an unpartitioned solver");
     if (s->stage_pending) return fail(ODIS_ERR_STATE, "a staged state is waiting for odis_commit_state");
     ODIS_CUDA(cudaSetDevice(s->device));
-    const size_t F = (size_t)s->Fg, N = (size_t)s->Ng;
+    const bool part = s->world > 1;
+    // unpartitioned: the reference-ordered arrays as they are; partitioned: this rank's share, packed in device order
+    const size_t F = part ? (size_t)s->F : (size_t)s->Fg, N = part ? (size_t)s->N : (size_t)s->Ng, Fh = part ? (size_t)s->Fo : F;
+    const size_t total = F + 3 * Fh + 4 * N;
     if (!s->copy_stream) ODIS_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     if (!s->d_stage_next) {
-        int rc = dev_alloc(s, &s->d_stage_next, 4 * F + 4 * N);
+        int rc = dev_alloc(s, &s->d_stage_next, total);
         if (rc) return rc;
         ODIS_CUDA(cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming));
         ODIS_CUDA(cudaEventCreateWithFlags(&s->consumed, cudaEventDisableTiming));
     }
+    if (part) {
+        // the caller's global arrays are read HERE (packed on the host while the device steps), so they are free again on return;
+        // the previous staged copy has left the page-locked buffer before it is overwritten
+        if (!s->h_stage_pack) ODIS_CUDA(cudaHostAlloc((void**)&s->h_stage_pack, total * sizeof(double), cudaHostAllocDefault));
+        if (s->stage_used) ODIS_CUDA(cudaEventSynchronize(s->staged));
+        pack_partitioned(s, s->h_stage_pack, v, eta, dvdt, detadt);
+    }
     if (s->stage_used) ODIS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->consumed, 0));     // the previous commit's scatter launches have read it
-    double* d = s->d_stage_next;
-    const double* host[4] = {v, dvdt, eta, detadt};
-    const size_t count[4] = {F, 3 * F, N, 3 * N};
-    s->stage_mask = 0;
-    for (int k = 0; k < 4; k++) {
-        if (host[k]) {
-            ODIS_CUDA(cudaMemcpyAsync(d, host[k], count[k] * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));
-            s->stage_mask |= 1u << k;
+    s->stage_mask = (v ? 1u : 0u) | (dvdt ? 2u : 0u) | (eta ? 4u : 0u) | (detadt ? 8u : 0u);
+    if (part) {
+        int rc = upload_partitioned(s, s->d_stage_next, s->h_stage_pack, s->stage_mask, s->copy_stream);
+        if (rc) return rc;
+    } else {
+        double* d = s->d_stage_next;
+        const double* host[4] = {v, dvdt, eta, detadt};
+        const size_t count[4] = {F, 3 * F, N, 3 * N};
+        for (int k = 0; k < 4; k++) {
+            if (host[k]) ODIS_CUDA(cudaMemcpyAsync(d, host[k], count[k] * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));
+            d += count[k];
         }
-        d += count[k];
     }
     ODIS_CUDA(cudaEventRecord(s->staged, s->copy_stream));
     s->stage_pending = true;
@@ -928,16 +968,23 @@ int odis_commit_state(odis_solver* s, int64_t iter) {
     if (iter < 0) return fail(ODIS_ERR_ARG, "iter must be >= 0");
     if (!s->stage_pending) return fail(ODIS_ERR_STATE, "odis_stage_state has not been called");
     ODIS_CUDA(cudaSetDevice(s->device));
-    const size_t F = (size_t)s->Fg, N = (size_t)s->Ng;
-    const double* d_v = s->d_stage_next; const double* d_dv = d_v + F; const double* d_eta = d_dv + 3 * F; const double* d_de = d_eta + N;
     const unsigned m = s->stage_mask;
+    if (s->world > 1) {
+        int rcp = halo_drain(s);            // (a launch, no host wait) the neighbours' last pushes have landed before the state is overwritten
+        if (rcp) return rcp;
+    }
     ODIS_CUDA(cudaStreamWaitEvent(s->stream, s->staged, 0));
-    odis::launch_scatter_x(s->F, s->d_edge_perm, (m & 1u) ? d_v : nullptr, s->d_vl[s->cur], 0, s->stream);
-    s->hv1 = 0;
-    odis::launch_scatter_history(s->Fo, s->d_edge_perm, (m & 2u) ? d_dv : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
-    odis::launch_scatter_x(s->N, s->d_cell_perm, (m & 4u) ? d_eta : nullptr, s->d_eu[s->ecur], 1, s->stream);
-    s->he1 = 0; s->he2 = 1; s->hefree = 2;
-    odis::launch_scatter_history(s->N, s->d_cell_perm, (m & 8u) ? d_de : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    if (s->world > 1) scatter_partitioned(s, s->d_stage_next, m);
+    else {
+        const size_t F = (size_t)s->Fg, N = (size_t)s->Ng;
+        const double* d_v = s->d_stage_next; const double* d_dv = d_v + F; const double* d_eta = d_dv + 3 * F; const double* d_de = d_eta + N;
+        odis::launch_scatter_x(s->F, s->d_edge_perm, (m & 1u) ? d_v : nullptr, s->d_vl[s->cur], 0, s->stream);
+        s->hv1 = 0;
+        odis::launch_scatter_history(s->Fo, s->d_edge_perm, (m & 2u) ? d_dv : nullptr, s->d_lvl0_v, s->d_hv[0], s->d_hv[1], s->stream);
+        odis::launch_scatter_x(s->N, s->d_cell_perm, (m & 4u) ? d_eta : nullptr, s->d_eu[s->ecur], 1, s->stream);
+        s->he1 = 0; s->he2 = 1; s->hefree = 2;
+        odis::launch_scatter_history(s->N, s->d_cell_perm, (m & 8u) ? d_de : nullptr, s->d_lvl0_e, s->d_he[0], s->d_he[1], s->stream);
+    }
     ODIS_CUDA(cudaEventRecord(s->consumed, s->stream));
     s->stage_pending = false;
     s->stage_used = true;
@@ -1618,9 +1665,12 @@ int odis_snapshot_begin(odis_solver* s, int32_t slot, uint32_t fields) {
     if (!s) return fail(ODIS_ERR_ARG, "NULL solver");
     if (slot < 0 || slot > 1) return fail(ODIS_ERR_ARG, "snapshot slot must be 0 or 1");
     if (!s->have_state) return fail(ODIS_ERR_STATE, "no state");
-    if (s->world > 1) return fail(ODIS_ERR_UNSUPPORTED, "snapshots need an unpartitioned solver");
     ODIS_CUDA(cudaSetDevice(s->device));
-    const size_t N = (size_t)s->Ng, F = (size_t)s->Fg, total = N + 4 * F + 1;
+    // partitioned: the rank's OWN entries, compact, in device order (odis_get_partition_map gives their reference ids)
+    const bool part = s->world > 1;
+    const size_t N = part ? (size_t)s->No : (size_t)s->Ng, F = part ? (size_t)s->Fo : (size_t)s->Fg, total = N + 4 * F + 1;
+    const int* cperm = part ? nullptr : s->d_cell_perm;
+    const int* eperm = part ? nullptr : s->d_edge_perm;
     odis_solver::SnapshotSlot& sl = s->snap[slot];
     if (!s->copy_stream) ODIS_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     if (!sl.d_buf) {
@@ -1635,10 +1685,10 @@ int odis_snapshot_begin(odis_solver* s, int32_t slot, uint32_t fields) {
     const bool want_diag_fields = (fields & (ODIS_SNAP_VELOCITY_EN | ODIS_SNAP_DISSIPATION)) != 0;
     if ((rc = run_diagnostics(s, want_diag_fields))) return rc;
     double* d_eta = sl.d_buf; double* d_ven = d_eta + N; double* d_diss = d_ven + 2 * F; double* d_v = d_diss + F; double* d_sum = d_v + F;
-    if (fields & ODIS_SNAP_ETA) { odis::launch_gather_component(s->No, s->d_cell_perm, s->d_eu[s->ecur], 0, d_eta, s->stream); s->launches++; }
-    if (fields & ODIS_SNAP_VELOCITY_EN) { odis::launch_gather_pair(s->Fo, s->d_edge_perm, s->d_vavg, d_ven, s->stream); s->launches++; }
-    if (fields & ODIS_SNAP_DISSIPATION) { odis::launch_gather_scalar(s->Fo, s->d_edge_perm, s->d_ediss, d_diss, s->stream); s->launches++; }
-    if (fields & ODIS_SNAP_VELOCITY) { odis::launch_gather_component(s->Fo, s->d_edge_perm, s->d_vl[s->cur], 0, d_v, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_ETA) { odis::launch_gather_component(s->No, cperm, s->d_eu[s->ecur], 0, d_eta, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_VELOCITY_EN) { odis::launch_gather_pair(s->Fo, eperm, s->d_vavg, d_ven, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_DISSIPATION) { odis::launch_gather_scalar(s->Fo, eperm, s->d_ediss, d_diss, s->stream); s->launches++; }
+    if (fields & ODIS_SNAP_VELOCITY) { odis::launch_gather_component(s->Fo, eperm, s->d_vl[s->cur], 0, d_v, s->stream); s->launches++; }
     ODIS_CUDA(cudaGetLastError());
     ODIS_CUDA(cudaMemcpyAsync(d_sum, s->d_series + (s->iter - s->iter0), sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
     ODIS_CUDA(cudaEventRecord(sl.ready, s->stream));
@@ -1663,7 +1713,8 @@ int odis_snapshot_wait(odis_solver* s, int32_t slot, odis_snapshot_view* out) {
     if (!sl.pending) return fail(ODIS_ERR_STATE, "no snapshot was begun on this slot");
     ODIS_CUDA(cudaSetDevice(s->device));
     ODIS_CUDA(cudaEventSynchronize(sl.done));
-    const size_t N = (size_t)s->Ng, F = (size_t)s->Fg;
+    const bool part = s->world > 1;
+    const size_t N = part ? (size_t)s->No : (size_t)s->Ng, F = part ? (size_t)s->Fo : (size_t)s->Fg;
     const double* h = sl.h_buf;
     out->eta = (sl.fields & ODIS_SNAP_ETA) ? h : nullptr;
     out->velocity_en = (sl.fields & ODIS_SNAP_VELOCITY_EN) ? h + N : nullptr;
@@ -1749,6 +1800,7 @@ void odis_destroy(odis_solver* s) {
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (s->h_pack) cudaFreeHost(s->h_pack);
+    if (s->h_stage_pack) cudaFreeHost(s->h_stage_pack);
     if (s->pack_done) cudaEventDestroy(s->pack_done);
     if (s->d_stage_next) cudaFree(s->d_stage_next);
     if (s->staged) cudaEventDestroy(s->staged);

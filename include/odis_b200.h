@@ -181,6 +181,9 @@ int odis_halo_export(odis_solver* s, void* blob_out);
 int odis_halo_connect(odis_solver* s, const void* all_blobs);
 int odis_get_partition(odis_solver* s, int32_t* rank, int32_t* world, int32_t* own_cells, int32_t* own_edges,
                        int32_t* ghost_cells, int32_t* ghost_edges, int32_t* n_peers);
+/* Reference ids of the cells [own_cells] / edges [own_edges] this solver owns, in the order of its device arrays — the order in
+ * which a partitioned solver's snapshots (odis_snapshot_wait) hand out their compact arrays. Either pointer may be NULL. */
+int odis_get_partition_map(odis_solver* s, int32_t* own_cell_ref_out, int32_t* own_edge_ref_out);
 /* The decomposition odis_create_partitioned would use, computed on the host only (no GPU needed): which
  * cells/edges (reference ids) rank `rank` holds — own first, then halo —, its neighbours, and for every
  * neighbour what it sends (reference id + the slot in the neighbour's local numbering). Arrays are
@@ -312,7 +315,9 @@ int odis_op_update_energy(odis_solver* s, const double* v_avg, const double* are
  * requested fields (ODIS_SNAP_* bits; the dissipation average always) into page-locked memory owned by the library, on a second
  * stream, and returns; the caller enqueues the next interval with odis_step and then calls odis_snapshot_wait, which blocks only until
  * that copy has landed and hands out pointers valid until the slot's next odis_snapshot_begin. Two slots (0, 1) for double buffering.
- * Unpartitioned solvers. */
+ * Partitioned solvers: every array holds the rank's OWN entries only ([own_cells], [own_edges][2], ...), compact, in the order of
+ * odis_get_partition_map (only those bytes cross PCIe); dissipation_avg is the rank's partial sum over the sphere's area, as from
+ * odis_get_dissipation_avg. */
 #define ODIS_SNAP_ETA 1u          /* p_t0        [N]    */
 #define ODIS_SNAP_VELOCITY_EN 2u  /* v_avg       [F][2] */
 #define ODIS_SNAP_DISSIPATION 4u  /* energy_diss [F]    */
@@ -332,7 +337,9 @@ int odis_snapshot_wait(odis_solver* s, int32_t slot, odis_snapshot_view* out);
  * device on the second stream while the current interval is still stepping. odis_stage_state returns at once; the host arrays must stay
  * unchanged until odis_commit_state (page-locked memory makes the copies asynchronous). odis_commit_state makes the staged arrays the
  * solver's state behind the steps enqueued so far (same renumbering launches and first potential as odis_set_state) without waiting on
- * the host. One staged state at a time; unpartitioned solvers. */
+ * the host. One staged state at a time. Partitioned solvers take the GLOBAL arrays (as odis_set_state does), pack their own share on
+ * the host inside odis_stage_state — while the device steps; the arrays are free again when the call returns — and upload only that
+ * share; every rank calls both functions (collective, like odis_set_state). */
 int odis_stage_state(odis_solver* s, const double* v, const double* eta, const double* dvdt /*[F][3]*/, const double* detadt /*[N][3]*/);
 int odis_commit_state(odis_solver* s, int64_t iter);
 int odis_get_iter(odis_solver* s, int64_t* iter_out);
