@@ -38,6 +38,7 @@ using odis::fail;
     } while (0)
 
 constexpr int kMaxPeers = 8;
+constexpr double kL2KeepDefaultMB = 0.0;     // default threshold of odis_solver::l2_keep (MB streamed per step); 0 = off until measured
 
 struct odis_solver {
     int device = 0;
@@ -112,6 +113,8 @@ struct odis_solver {
     // nonlinear branch (odis_enable_advection)
     bool nl_on = false;
     bool nl_fused = true;            // the 4-launch nonlinear step (measured +11 %); the baseline selection (bit 0) keeps the 6-launch one
+    bool nl_folded = true;           // ... with the energy diagnostic and the next potential folded into its launches (ODIS_B200_NL_FOLDED=0: the
+                                     // two passes of their own, for A/B timing)
     int nl_launches() const { return nl_fused ? odis::kNlLaunchesFused : odis::kNlLaunches; }
     odis::NlTables nl{};
     double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
@@ -182,6 +185,7 @@ struct odis_solver {
     bool pack_pending = false;
 
     long long wait_cycles = 0;               // ODIS_B200_WAIT_TIMEOUT_S in clock64 ticks (0: the kernels' default)
+    bool l2_keep = false;                    // the bytes a step streams (tables + state) fit the L2: no evict-first hint on the table rows
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
     int last_mode = -1;
@@ -191,11 +195,13 @@ struct odis_solver {
     odis::EdgeTables edge_tables() const {
         odis::EdgeTables t;
         t.n_edges = Fo; t.stride = Fp; t.cells = d_cells; t.grad = d_grad; t.fcor = d_fcor; t.dist = d_dist; t.sid = d_sid; t.sw = d_sw;
+        t.l2_keep = l2_keep ? 1 : 0;
         return t;
     }
     odis::CellTables cell_tables(int n_active) const {
         odis::CellTables t;
         t.n_cells = Np; t.n_active = n_active; t.eid = d_eid; t.area = d_area; t.trig = d_trig; t.trig_sq = d_trig_sq;
+        t.l2_keep = l2_keep ? 1 : 0;
         return t;
     }
 };
@@ -400,6 +406,7 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     s->pipe_cell = s->pipe_edge && !(std::getenv("ODIS_B200_DIRECT_CELL") && std::atoi(std::getenv("ODIS_B200_DIRECT_CELL")) != 0);
     s->use_graph = (prm->reserved[0] & 8) == 0;
     s->nl_fused = s->pipe_edge;
+    { const char* e = std::getenv("ODIS_B200_NL_FOLDED"); s->nl_folded = !(e && std::atoi(e) == 0); }
     s->edge_ids16 = (prm->reserved[0] & 128) == 0 && s->pipe_edge;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
@@ -545,6 +552,15 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         s->wait_cycles = sec > 0.0 ? (long long)(sec * 2.0e9) : 0ll;
         if (s->wait_cycles > 0)
             cudaMemcpyAsync(&s->d_ctl->spin_cycles, &s->wait_cycles, sizeof(long long), cudaMemcpyHostToDevice, s->stream);
+    }
+    {   // L2 policy of the staged kernels' table rows: evict-first when a step streams more than the L2 holds beside the gathered state
+        // (the 655,362-cell grid on one GPU), none when everything a step touches fits — small grids and the ranks of a partitioned run
+        // then run out of the L2 from step to step. Threshold in MB of streamed bytes per step (216 B per edge + 160 B per cell held);
+        // ODIS_B200_L2_KEEP_MB overrides it (0: always evict-first).
+        const char* e = std::getenv("ODIS_B200_L2_KEEP_MB");
+        const double keep_mb = e ? std::atof(e) : kL2KeepDefaultMB;
+        const double step_mb = (216.0 * (double)F + 160.0 * (double)N) / 1.0e6;
+        s->l2_keep = step_mb <= keep_mb;
     }
     if (cudaSuccess != odis::pipe_configure()) return bail(fail(ODIS_ERR_CUDA, "cudaFuncSetAttribute(shared memory size) failed"));
     cudaMemsetAsync(s->d_eu[0], 0, (size_t)Np * sizeof(double2), s->stream);
@@ -1236,11 +1252,16 @@ static void rotate_cell_history(odis_solver* s, int mode) {
 constexpr int kGraphSteps = 12;      // steps per captured graph: a multiple of the rotation period (2 x 2 x 3 -> 6)
 
 // Launches of one time step on the solver's stream (also under stream capture) and the rotation of the buffers.
-// One step of the nonlinear branch: diagnostics of v^n (the linear edge kernel produces them on the fly), the six launches of
+// One step of the nonlinear branch. Default (folded): the 4 launches of launch_step_nonlinear_folded — energy diagnostic of v^n inside the
+// edge update, next potential inside the cell update. Otherwise: diagnostics of v^n (the linear edge kernel produces them on the fly), the launches of
 // odis_kernels_nl.cu, the potential pass for the next step.
 static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEvent_t>* marks, int k) {
-    odis::launch_edge_diagnostics(s->edge_tables(), s->phys, s->d_vl[s->cur], s->d_normal, nullptr, nullptr, s->d_block_partial, s->d_ticket,
-                                  s->d_series + (s->iter - s->iter0), s->prm.block_threads, s->stream);
+    const bool folded = s->nl_fused && s->nl_folded;
+    // forcing for the next step (current_time = dt*(iter+1), evaluated at current_time + dt)
+    const odis::StepScalars next = step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt);
+    if (!folded)
+        odis::launch_edge_diagnostics(s->edge_tables(), s->phys, s->d_vl[s->cur], s->d_normal, nullptr, nullptr, s->d_block_partial, s->d_ticket,
+                                      s->d_series + (s->iter - s->iter0), s->prm.block_threads, s->stream);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4], s->stream);
     odis::NlState ns;
     ns.vl_in = s->d_vl[s->cur]; ns.vl_out = s->d_vl[1 - s->cur];
@@ -1248,24 +1269,26 @@ static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEven
     ns.h1 = s->d_hv[s->hv1]; ns.h2 = s->d_hv[1 - s->hv1];
     ns.ch1 = s->d_he[s->he1]; ns.ch2 = s->d_he[s->he2]; ns.chw = s->d_he[s->hefree];
     ns.qv = s->d_nl_qv; ns.fq = s->d_nl_fq; ns.ekin = s->d_nl_ekin; ns.flux = s->d_nl_flux;
-    if (s->nl_fused) odis::launch_step_nonlinear_fused(s->nl, s->phys, ns, mode, s->stream);
+    ns.block_partial = s->d_block_partial; ns.ticket = s->d_ticket; ns.energy_out = s->d_series + (s->iter - s->iter0);
+    if (folded) odis::launch_step_nonlinear_folded(s->nl, s->phys, ns, mode, s->cell_tables(s->N), next, s->stream);
+    else if (s->nl_fused) odis::launch_step_nonlinear_fused(s->nl, s->phys, ns, mode, s->stream);
     else odis::launch_step_nonlinear(s->nl, s->phys, ns, mode, s->stream);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 1], s->stream);
     if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;
     rotate_cell_history(s, mode);
     s->ecur = 1 - s->ecur;
-    // forcing for the next step (current_time = dt*(iter+1), evaluated at current_time + dt), in place on the new {eta,U}
-    odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
-    odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt),
-                           odis::CELL_UPDATE_U, s->prm.block_threads, nullptr, s->stream);
-    enqueue_planet(s, s->d_eu[s->ecur], s->N, step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt), nullptr);
+    if (!folded) {      // the potential in place on the new {eta,U}, in a pass of its own
+        odis::CellState cs{s->d_vl[1 - s->cur], s->d_eu[s->ecur], s->d_eu[s->ecur], s->d_he[0], s->d_he[1], s->d_he[2], nullptr, 0, nullptr, nullptr};
+        odis::launch_cell_step(s->cell_tables(s->N), s->phys, cs, odis::AB3_FULL, next, odis::CELL_UPDATE_U, s->prm.block_threads, nullptr, s->stream);
+    }
+    enqueue_planet(s, s->d_eu[s->ecur], s->N, next, nullptr);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 2], s->stream);
     { int rc2 = enqueue_self_gravity(s, s->d_eu[s->ecur]); if (rc2) return rc2; }
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 3], s->stream);
     s->cur = 1 - s->cur;
     s->iter++;
     s->last_mode = mode;
-    s->launches += 2 + s->nl_launches() + planet_launches(s) + s->sh_launches();
+    s->launches += (folded ? 0 : 2) + s->nl_launches() + planet_launches(s) + s->sh_launches();
     return ODIS_OK;
 }
 

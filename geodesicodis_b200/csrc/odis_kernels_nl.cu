@@ -1,5 +1,6 @@
 // Kernels of the nonlinear branch: see odis_kernels_nl.cuh.
 #include "odis_kernels_nl.cuh"
+#include "odis_potential.cuh"
 
 namespace odis {
 namespace {
@@ -184,8 +185,11 @@ __global__ void __launch_bounds__(kNlThreads) nl_flux_kernel(NlTables t, Physics
     s.flux[e] = vel * 0.5 * (htot(c.x) + htot(c.y)) - dx2 * (d2_outer + d2_inner) * vel + dx2 * beta * fabs(vel) * (d2_outer - d2_inner);
 }
 
-// updateEta.cpp:33 (d eta/dt = Div flux) + integrateAB3scalar; the potential of the next step is left to the potential pass
-__global__ void __launch_bounds__(kNlThreads) nl_cell_step_kernel(NlTables t, Physics p, NlState s, int mode) {
+// updateEta.cpp:33 (d eta/dt = Div flux) + integrateAB3scalar. kPot = false: the potential of the next step is left to the potential
+// pass (a launch of cell_step_kernel); kPot = true: evaluated here from the same table rows with the same expression (tidal_potential,
+// odis_potential.cuh), which saves that launch and a second pass over {eta,U}
+template <bool kPot>
+__global__ void __launch_bounds__(kNlThreads) nl_cell_step_kernel(NlTables t, Physics p, NlState s, int mode, CellTables ct, StepScalars next) {
     const int i = blockIdx.x * kNlThreads + threadIdx.x;
     if (i >= t.n_cells) return;
     double2 st = s.eu_in[i];
@@ -195,6 +199,31 @@ __global__ void __launch_bounds__(kNlThreads) nl_cell_step_kernel(NlTables t, Ph
     double le[kCellEdges], fl[kCellEdges];
 #pragma unroll
     for (int j = 0; j < kCellEdges; j++) packed[j] = ldt(t.eid + (size_t)j * t.cstride + i);
+    TrigValues tv = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (kPot) {                                                                   // the rows the potential reads (as load_trig, odis_kernels.cu)
+        const size_t N = (size_t)ct.n_cells;
+        const double* T = ct.trig;
+        switch (p.potential) {
+            case P_ECC:
+                tv.cosSq = ldt(ct.trig_sq + i); tv.sinSq = ldt(ct.trig_sq + N + i); tv.cos2Lon = ldt(T + 6 * N + i); tv.sin2Lon = ldt(T + 7 * N + i);
+                break;
+            case P_OBLIQ:
+                tv.sin2Lat = ldt(T + 5 * N + i); tv.cosLon = ldt(T + 2 * N + i);
+                break;
+            case P_OBLIQ_WEST:
+                tv.cosLat = ldt(T + i); tv.sinLat = ldt(T + N + i); tv.cosLon = ldt(T + 2 * N + i); tv.sinLon = ldt(T + 3 * N + i);
+                break;
+            case P_FULL:
+                tv.cosSq = ldt(ct.trig_sq + i); tv.sinSq = ldt(ct.trig_sq + N + i); tv.cos2Lon = ldt(T + 6 * N + i); tv.sin2Lon = ldt(T + 7 * N + i);
+                tv.sin2Lat = ldt(T + 5 * N + i); tv.cosLon = ldt(T + 2 * N + i);
+                break;
+            case P_FULL2:
+                tv.cosLat = ldt(T + i); tv.sinLat = ldt(T + N + i); tv.cosLon = ldt(T + 2 * N + i); tv.sinLon = ldt(T + 3 * N + i);
+                tv.cos2Lat = ldt(T + 4 * N + i); tv.cos2Lon = ldt(T + 6 * N + i); tv.sin2Lon = ldt(T + 7 * N + i); tv.cosSq = ldt(ct.trig_sq + i);
+                break;
+            default: break;
+        }
+    }
     int all_and = packed[0], all_or = packed[0];
 #pragma unroll
     for (int j = 1; j < kCellEdges; j++) { all_and &= packed[j]; all_or |= packed[j]; }
@@ -215,6 +244,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_cell_step_kernel(NlTables t, Ph
     }
     st.x += ab3_increment(div, s.ch1[i], s.ch2[i], p.dt, mode);
     s.chw[i] = div;
+    if (kPot && p.potential != P_NONE) st.y = tidal_potential(p, next, tv);        // forcing(current_time + dt) of the NEXT step, tidalPotentials.cpp:80-172
     s.eu_out[i] = st;
 }
 
@@ -249,56 +279,108 @@ __global__ void __launch_bounds__(kNlThreads) nl_vertex_ekin_kernel(NlTables t, 
     }
 }
 
+// kEnergy: the dissipated energy of v^n (interpolation.cpp:31-59 + energy.cpp:32-60) is summed on the way — the tangential velocity of
+// an edge is the sum over the SAME ten neighbours this kernel gathers {F, q} from, with the weights w l_e' / d_e it already holds
+// (ncoef), so only v_e' itself is gathered on top — instead of in a pass of its own over the TRiSK tables (edge_diag_kernel: 150 B per
+// edge). Order and association of that sum differ from the diagnostic kernel's (reference slot order instead of ascending ids, the
+// division by d_e folded into the weight): ~1e-16 relative on a quantity whose bar is 1e-12 (a parallel sum either way).
+template <bool kEnergy>
 __global__ void __launch_bounds__(kNlThreads) nl_edge_step_flux_kernel(NlTables t, Physics p, NlState s, int mode) {
     const int e = blockIdx.x * kNlThreads + threadIdx.x;
-    if (e >= t.n_edges) return;
-    const int2 c = t.cells[e];
-    const double2 G = t.grad[e];
-    const double2 own = s.vl_in[e];
-    const double2 in = s.eu_in[c.x], out = s.eu_in[c.y];
-    double dv = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;
-    const double q_e = s.fq[e].y;
-    double F_tang_q = 0.0;
-    int nf[kStencil];
-    double nc[kStencil];
-    double2 no[kStencil];
+    double e_area = 0.0;
+    if (e < t.n_edges) {
+        const int2 c = t.cells[e];
+        const double2 G = t.grad[e];
+        const double2 own = s.vl_in[e];
+        const double2 in = s.eu_in[c.x], out = s.eu_in[c.y];
+        double dv = (-p.g * G.x) * in.x + (-p.g * G.y) * out.x;
+        const double q_e = s.fq[e].y;
+        double F_tang_q = 0.0;
+        int nf[kStencil];
+        double nc[kStencil];
+        double2 no[kStencil];
+        double nv[kEnergy ? kStencil : 1];
 #pragma unroll
-    for (int j = 0; j < kStencil; j++) {                                           // table values, then gathers, then the sum in slot order
-        nf[j] = ldt(t.nid + (size_t)j * t.estride + e);
-        nc[j] = ldt(t.ncoef + (size_t)j * t.estride + e);
+        for (int j = 0; j < kStencil; j++) {                                           // table values, then gathers, then the sum in slot order
+            nf[j] = ldt(t.nid + (size_t)j * t.estride + e);
+            nc[j] = ldt(t.ncoef + (size_t)j * t.estride + e);
+        }
+        // every gather address depends on every table value (z is 0: ids are >= -1 and never all 0x80000001 ... but only at run time), so
+        // the table loads have to be issued, all of them, before the first gather -- ptxas otherwise interleaves slot by slot
+        int all_ids = nf[0], all_hi = __double2hiint(nc[0]);
+#pragma unroll
+        for (int j = 1; j < kStencil; j++) { all_ids &= nf[j]; all_hi &= __double2hiint(nc[j]); }
+        const int z = (int)(all_ids == (int)0x80000001) & (int)(all_hi == (int)0x80000001);
+#pragma unroll
+        for (int j = 0; j < kStencil; j++) no[j] = ldo(s.fq + ((nf[j] >= 0 ? nf[j] : e) + z));   // {F_e', q_e'}
+        if (kEnergy) {
+#pragma unroll
+            for (int j = 0; j < kStencil; j++) nv[j] = ldo_x(s.vl_in + ((nf[j] >= 0 ? nf[j] : e) + z));
+        }
+        double vt = 0.0;
+#pragma unroll
+        for (int j = 0; j < kStencil; j++) {
+            if (nf[j] >= 0) {
+                const double2 o = no[j];
+                F_tang_q += nc[j] * o.x * (q_e + o.y) * 0.5;
+                if (kEnergy) vt += nc[j] * nv[j];
+            }
+        }
+        const double dx = t.dist[e];
+        if (kEnergy) {                                                                 // the stencil values are dead from here on
+            const double sq = own.x * own.x + vt * vt;
+            const double eps = p.friction == 0 ? p.alpha * 1000.0 * p.h * sq : p.alpha / p.h * sqrt(sq) * sq;      // energy.cpp:34 / :48-49
+            e_area = eps * (dx * own.y);
+        }
+        dv -= -F_tang_q;
+        dv += (-G.x) * s.ekin[c.x] + (-G.y) * s.ekin[c.y];
+        const double f0 = dv;
+        const double drag = (-p.alpha) * own.x + (G.x * in.y + G.y * out.y);
+        double v = own.x + ab3_increment(f0, s.h1[e], s.h2[e], p.dt, mode);
+        v += p.dt * drag;
+        s.vl_out[e] = make_double2(v, own.y);
+        if (mode == AB3_SECOND) s.h1[e] = f0;
+        else s.h2[e] = f0;
+        // interpolateLSQFlux (interpolation.cpp:311-364) for this edge, with the velocity just computed
+        auto htot = [&](int i) { return p.h + ldo_x(s.eu_in + i); };
+        const double d2_inner = ell_row(t.d2[0], e, htot), d2_outer = ell_row(t.d2[1], e, htot);
+        const double fact = 1. / 12.0, beta = 1.0;
+        const double dx2 = dx * dx * fact;
+        const double vel = v;
+        s.flux[e] = vel * 0.5 * (htot(c.x) + htot(c.y)) - dx2 * (d2_outer + d2_inner) * vel + dx2 * beta * fabs(vel) * (d2_outer - d2_inner);
     }
-    // every gather address depends on every table value (z is 0: ids are >= -1 and never all 0x80000001 ... but only at run time), so
-    // the table loads have to be issued, all of them, before the first gather -- ptxas otherwise interleaves slot by slot
-    int all_ids = nf[0], all_hi = __double2hiint(nc[0]);
-#pragma unroll
-    for (int j = 1; j < kStencil; j++) { all_ids &= nf[j]; all_hi &= __double2hiint(nc[j]); }
-    const int z = (int)(all_ids == (int)0x80000001) & (int)(all_hi == (int)0x80000001);
-#pragma unroll
-    for (int j = 0; j < kStencil; j++) no[j] = ldo(s.fq + ((nf[j] >= 0 ? nf[j] : e) + z));   // {F_e', q_e'}
-#pragma unroll
-    for (int j = 0; j < kStencil; j++) {
-        if (nf[j] >= 0) {
-            const double2 o = no[j];
-            F_tang_q += nc[j] * o.x * (q_e + o.y) * 0.5;
+    if (!kEnergy) return;
+    // deterministic grid-wide sum (as block_sum_and_publish, odis_kernels.cu): warp -> block -> the last block adds the partials in order
+    __shared__ double warp_sums[kNlThreads / 32];
+    __shared__ bool is_last;
+    for (int o = 16; o > 0; o >>= 1) e_area += __shfl_down_sync(0xffffffffu, e_area, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_sums[warp] = e_area;
+    __syncthreads();
+    if (warp == 0) {
+        double y = (lane < kNlThreads / 32) ? warp_sums[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) y += __shfl_down_sync(0xffffffffu, y, o);
+        if (lane == 0) {
+            s.block_partial[blockIdx.x] = y;
+            __threadfence();
+            is_last = (atomicAdd(s.ticket, 1u) == gridDim.x - 1);
         }
     }
-    dv -= -F_tang_q;
-    dv += (-G.x) * s.ekin[c.x] + (-G.y) * s.ekin[c.y];
-    const double f0 = dv;
-    const double drag = (-p.alpha) * own.x + (G.x * in.y + G.y * out.y);
-    double v = own.x + ab3_increment(f0, s.h1[e], s.h2[e], p.dt, mode);
-    v += p.dt * drag;
-    s.vl_out[e] = make_double2(v, own.y);
-    if (mode == AB3_SECOND) s.h1[e] = f0;
-    else s.h2[e] = f0;
-    // interpolateLSQFlux (interpolation.cpp:311-364) for this edge, with the velocity just computed
-    auto htot = [&](int i) { return p.h + ldo_x(s.eu_in + i); };
-    const double d2_inner = ell_row(t.d2[0], e, htot), d2_outer = ell_row(t.d2[1], e, htot);
-    const double fact = 1. / 12.0, beta = 1.0;
-    const double dx = t.dist[e];
-    const double dx2 = dx * dx * fact;
-    const double vel = v;
-    s.flux[e] = vel * 0.5 * (htot(c.x) + htot(c.y)) - dx2 * (d2_outer + d2_inner) * vel + dx2 * beta * fabs(vel) * (d2_outer - d2_inner);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += kNlThreads) acc += ((volatile double*)s.block_partial)[i];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) warp_sums[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < kNlThreads / 32; w++) tot += warp_sums[w];
+            *s.energy_out = tot;
+            *s.ticket = 0u;
+        }
+    }
 }
 
 }  // namespace
@@ -310,7 +392,7 @@ void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s
     nl_cell_ekin_kernel<<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, s);
     nl_edge_step_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
     nl_flux_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s);
-    nl_cell_step_kernel<<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode);
+    nl_cell_step_kernel<false><<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode, CellTables{}, StepScalars{});
 }
 
 void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream) {
@@ -318,8 +400,18 @@ void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlSt
     const unsigned vb = grid(t.n_vertices);
     nl_vertex_ekin_kernel<<<vb + grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, (int)vb);
     nl_edge_prep_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s);
-    nl_edge_step_flux_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
-    nl_cell_step_kernel<<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode);
+    nl_edge_step_flux_kernel<false><<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
+    nl_cell_step_kernel<false><<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode, CellTables{}, StepScalars{});
+}
+
+void launch_step_nonlinear_folded(const NlTables& t, const Physics& p, const NlState& s, int mode, const CellTables& ct, const StepScalars& next,
+                                  cudaStream_t stream) {
+    auto grid = [](int n) { return (unsigned)((n + kNlThreads - 1) / kNlThreads); };
+    const unsigned vb = grid(t.n_vertices);
+    nl_vertex_ekin_kernel<<<vb + grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, (int)vb);
+    nl_edge_prep_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s);
+    nl_edge_step_flux_kernel<true><<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
+    nl_cell_step_kernel<true><<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode, ct, next);
 }
 
 }  // namespace odis

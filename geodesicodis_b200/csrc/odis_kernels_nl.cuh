@@ -62,6 +62,10 @@ struct NlState {
     double2* fq;               // [F] scratch: {h_e v_e, q_e}
     double* ekin;              // [N] scratch
     double* flux;              // [F] scratch
+    // folded step only: the dissipated-energy sum of v^n leaves the edge update (per-block partials, last-block ticket, result)
+    double* block_partial;     // [>= ceil(F / 128)]
+    unsigned int* ticket;      // zero before the launch, left zero
+    double* energy_out;
 };
 
 // launches of one nonlinear step (before the potential pass and the diagnostics): vertex PV, edge {F_e, q_e}, cell Ekin,
@@ -72,5 +76,11 @@ void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s
 // cell update. Bit-identical fields.
 constexpr int kNlLaunchesFused = 4;
 void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream);
+// Default: the same 4 launches with the two passes AROUND them folded in — the dissipated energy of v^n is summed inside the edge update
+// (instead of edge_diag_kernel before the step) and the cell update evaluates the next step's tidal potential itself (instead of a
+// cell_step_kernel pass after it): 4 launches per step instead of 6. Fields bit-identical; the energy sum within ~1e-15 (bar 1e-12).
+// ct: the trig rows of the potential; next: its time factors (forcing(current_time + dt) of the next step).
+void launch_step_nonlinear_folded(const NlTables& t, const Physics& p, const NlState& s, int mode, const CellTables& ct, const StepScalars& next,
+                                  cudaStream_t stream);
 
 }  // namespace odis

@@ -84,6 +84,11 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ uint64_t l2_evict_normal_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
@@ -187,7 +192,7 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
-            const uint64_t pol = l2_evict_first_policy();
+            const uint64_t pol = t.l2_keep ? l2_evict_normal_policy() : l2_evict_first_policy();
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kStages;
                 if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
@@ -554,7 +559,7 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
-            const uint64_t pol = l2_evict_first_policy();
+            const uint64_t pol = t.l2_keep ? l2_evict_normal_policy() : l2_evict_first_policy();
             const uint32_t stage_bytes = kCellFixedBytes + (uint32_t)rows.n * kTile * 8;
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kS;
