@@ -1,4 +1,6 @@
-"""Per-step time of the nonlinear branch vs the linear one: python scripts/nonlinear_timing.py [level]"""
+"""Per-step time of the nonlinear branch vs the linear one: python scripts/nonlinear_timing.py [level]
+Variants: linear; nonlinear with the 6-launch baseline kernels (+ diagnostics + potential pass = 8 launches per step); the 4-launch
+kernels with the two passes of their own (ODIS_B200_NL_FOLDED=0, 6 launches per step: round 2's first default); the default (4 launches)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,17 +14,30 @@ t0 = time.time()
 nl = odis.nonlinear_tables(mesh, 0.5)
 t_tab = time.time() - t0
 dmin = float(mesh.tables["face_node_dist"].min())
-prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.2 * dmin / np.sqrt(9.80616 * 8e3), radius=r, omega=7.292e-5, love_reduct=1.0, ecc=0.01,
+prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.1 * dmin / np.sqrt(9.80616 * 8e3), radius=r, omega=7.292e-5, love_reduct=1.0, ecc=0.01,
            obl=np.deg2rad(-2.0), shell_thickness=0.0, semimajor_axis=0.0, potential=1, friction=0, surface=0, init_load=0, reorder=1)
-out = []
-for adv in (False, True, "4-launch variant (kernel_select=32)"):
-    s = odis.Solver(mesh, dict(prm, kernel_select=32) if isinstance(adv, str) else prm)
+out, fields = {}, {}
+for name, adv, sel, env in (("linear", False, 0, None), ("nonlinear 6-launch baseline kernels", True, 1, None),
+                            ("nonlinear 4-launch kernels + diagnostics + potential pass", True, 0, "0"), ("nonlinear default (folded, 4 launches)", True, 0, "1")):
+    if env is None:
+        os.environ.pop("ODIS_B200_NL_FOLDED", None)
+    else:
+        os.environ["ODIS_B200_NL_FOLDED"] = env
+    s = odis.Solver(mesh, dict(prm, kernel_select=sel))
     if adv:
         s.enable_advection(nl)
-    s.step(50)
-    ms = s.step_timed(400) / 400
-    out.append(ms)
+    l0 = s.launches
+    s.step(40)
+    per_step = (s.launches - l0) / 40
+    ms = min(s.step_timed(100) for _ in range(3)) / 100
+    out[name] = ms
     eta = s.field(odis.FIELD_ETA)
-    print(f"level {level} ({mesh.n_cells} cells) advection={adv}: {ms * 1e3:.1f} us/step, max|eta| {np.abs(eta).max():.4e}, finite {bool(np.isfinite(eta).all())}", flush=True)
+    fields[name] = (eta, s.field(odis.FIELD_VELOCITY), s.dissipation_series())
+    print(f"level {level} ({mesh.n_cells} cells) {name}: {ms * 1e3:.1f} us/step, {per_step:.0f} launches/step, max|eta| {np.abs(eta).max():.4e}, "
+          f"finite {bool(np.isfinite(eta).all())}", flush=True)
     s.close()
-print(f"nonlinear tables built on the host in {t_tab:.2f} s; nonlinear / linear step time = {out[1] / out[0]:.2f} (4-launch variant: {out[2] / out[0]:.2f})")
+names = [n for n in out if n.startswith("nonlinear")]
+same = all(np.array_equal(fields[n][0], fields[names[0]][0]) and np.array_equal(fields[n][1], fields[names[0]][1]) for n in names[1:])
+ser = max(float(np.abs(fields[n][2] - fields[names[0]][2]).max() / max(np.abs(fields[names[0]][2]).max(), 1e-300)) for n in names[1:])
+print(f"nonlinear variants: fields bit-identical {same}; dissipation series max rel diff {ser:.2e}")
+print(f"nonlinear tables built on the host in {t_tab:.2f} s; nonlinear default / linear step time = {out[names[-1]] / out['linear']:.2f}")
