@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import geodesicodis_b200 as odis
 
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+only = sys.argv[2] if len(sys.argv) > 2 else ""          # substring of a variant's name: run only those (profiling)
 pos, fr, cen = odis.generate_grid(level)
 r = 6.37122e6
 mesh = odis.Mesh.from_arrays(pos, fr, cen, r)
@@ -19,6 +20,8 @@ prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.1 * dmin / np.sqrt(9.80616 * 8e3),
 out, fields = {}, {}
 for name, adv, sel, env in (("linear", False, 0, None), ("nonlinear 6-launch baseline kernels", True, 1, None),
                             ("nonlinear 4-launch kernels + diagnostics + potential pass", True, 0, "0"), ("nonlinear default (folded, 4 launches)", True, 0, "1")):
+    if only and only not in name:
+        continue
     if env is None:
         os.environ.pop("ODIS_B200_NL_FOLDED", None)
     else:
@@ -37,6 +40,8 @@ for name, adv, sel, env in (("linear", False, 0, None), ("nonlinear 6-launch bas
           f"finite {bool(np.isfinite(eta).all())}", flush=True)
     s.close()
 names = [n for n in out if n.startswith("nonlinear")]
+if len(names) < 2 or "linear" not in out:
+    sys.exit(0)
 same = all(np.array_equal(fields[n][0], fields[names[0]][0]) and np.array_equal(fields[n][1], fields[names[0]][1]) for n in names[1:])
 ser = max(float(np.abs(fields[n][2] - fields[names[0]][2]).max() / max(np.abs(fields[names[0]][2]).max(), 1e-300)) for n in names[1:])
 print(f"nonlinear variants: fields bit-identical {same}; dissipation series max rel diff {ser:.2e}")

@@ -31,6 +31,6 @@ ODIS_B200_L2_KEEP_MB=100000 run 200 l2keep_l9_sg2 python scripts/step_cfg_timing
 run 200 l9_sg2 python scripts/step_cfg_timing.py 9 2 0
 export TAILN=3
 run 300 bench_short python bench.py --steps 10 --warmup 3 --no-variants --no-cpu
-run 300 ncu_nl ncu --set full --clock-control none --import-source on -k "regex:nl_" -s 200 -c 4 -o $OUT/nl_kernels_r02h -f python scripts/nonlinear_timing.py 8
-run 200 ncu_nl_launches ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:nl_|edge_diag|cell_step_kernel" -s 400 -c 60 --csv --log-file $OUT/launches_nl_r02h.csv python scripts/nonlinear_timing.py 8
+run 300 ncu_nl ncu --set full --clock-control none --import-source on -k "regex:nl_" -s 200 -c 4 -o $OUT/nl_kernels_r02h -f python scripts/nonlinear_timing.py 8 folded
+run 200 ncu_nl_launches ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 48 --csv --log-file $OUT/launches_nl_r02h.csv python scripts/nonlinear_timing.py 8 folded
 log done
