@@ -1748,6 +1748,14 @@ int odis_snapshot_wait(odis_solver* s, int32_t slot, odis_snapshot_view* out) {
     return ODIS_OK;
 }
 
+#ifdef ODIS_TRACE
+// variant library only (scripts/halo_trace.py): device buffer of [2 kernels][slots][ctas][8 events][2] 64-bit time stamps on the current device
+int odis_debug_trace_enable(void* device_buffer, int32_t slots, int32_t ctas) {
+    ODIS_CUDA(odis::trace_enable(static_cast<unsigned long long*>(device_buffer), (unsigned int)slots, (unsigned int)ctas));
+    return ODIS_OK;
+}
+#endif
+
 int odis_get_iter(odis_solver* s, int64_t* iter_out) {
     if (!s || !iter_out) return fail(ODIS_ERR_ARG, "NULL argument");
     *iter_out = s->iter;

@@ -132,6 +132,9 @@ void launch_edge_diagnostics(const EdgeTables& t, const Physics& p, const double
                              double* energy_out, int block_threads, cudaStream_t stream);
 int edge_grid_blocks(int n_edges, int block_threads);
 
+#ifdef ODIS_TRACE
+cudaError_t trace_enable(unsigned long long* buf, unsigned int slots, unsigned int ctas);   // tuning aid, odis_kernels_pipe.cu
+#endif
 // Pipelined variants (odis_kernels_pipe.cu): persistent CTAs, tables staged through shared memory by
 // cp.async.bulk + mbarrier, 128-entity tiles. Same results bit for bit. All arrays a tile touches must
 // be allocated up to the next multiple of pipe_tile().

@@ -142,6 +142,38 @@ __device__ __forceinline__ double dissipation_flux(const Physics& p, double vn, 
     return p.alpha / p.h * sqrt(sq) * sq;                         // energy.cpp:48-49
 }
 
+#ifdef ODIS_TRACE
+// Tuning aid (variant library only, build_variant("trace", ["ODIS_TRACE"])): per-CTA time stamps of the two staged kernels, written to a
+// buffer handed over with odis_debug_trace_enable: [kernel 0 = edge, 1 = cell][launch % slots][CTA][8 events][2: globaltimer ns, clock64].
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned int g_trace_slots = 0, g_trace_ctas = 0;
+__device__ unsigned int g_trace_arrivals[2] = {0u, 0u};
+struct Trace {
+    unsigned long long* row;      // this CTA's 8 x 2 entries of this launch, or nullptr
+    __device__ __forceinline__ void begin(int kernel) {     // one thread per CTA
+        row = nullptr;
+        unsigned long long* base = g_trace;
+        if (base == nullptr || blockIdx.x >= g_trace_ctas) return;
+        const unsigned int launch = atomicAdd(&g_trace_arrivals[kernel], 1u) / gridDim.x;
+        row = base + ((((size_t)kernel * g_trace_slots + launch % g_trace_slots) * g_trace_ctas + blockIdx.x) * 8) * 2;
+    }
+    __device__ __forceinline__ void mark(int ev) const {
+        if (row == nullptr) return;
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        row[2 * ev] = g;
+        row[2 * ev + 1] = (unsigned long long)clock64();
+    }
+};
+#define ODIS_TRACE_DECL __shared__ Trace trace_s;
+#define ODIS_TRACE_BEGIN(k) do { if (threadIdx.x == 0) { trace_s.begin(k); trace_s.mark(0); } } while (0)
+#define ODIS_TRACE_MARK(cond, ev) do { if (cond) trace_s.mark(ev); } while (0)
+#else
+#define ODIS_TRACE_DECL
+#define ODIS_TRACE_BEGIN(k) do { } while (0)
+#define ODIS_TRACE_MARK(cond, ev) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- edge step ----
 struct __align__(16) EdgeStage {
     int sid[kStencil][kTile];        //  5120 B
@@ -175,6 +207,8 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
     uint64_t* empty = full + kStages;
     unsigned char* wide_s = smem_raw + kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t);     // [my_tiles], kIds16 only
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ODIS_TRACE_DECL
+    ODIS_TRACE_BEGIN(0);
     if (kIds16) {
         const int mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         for (int i = threadIdx.x; i < mine; i += kPipeThreads) wide_s[i] = tile_wide[(size_t)blockIdx.x + (size_t)i * gridDim.x];
@@ -234,6 +268,7 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
         // partitioned runs: the first tiles hold the boundary edges (they feed the neighbours)
         const bool bnd_tile = (e - tl) < halo.n_bnd;
         mbar_wait(full + st, (i / kStages) & 1);
+        ODIS_TRACE_MARK(i == 0 && tl == 0, 1);                      // first tile: its rows have arrived
         double e_area = 0.0;
         // boundary edges: where the new value goes (CSR over the boundary edges), requested now so that the look-up overlaps the gathers
         int k0 = 0, k1 = 0, peer0 = 0, slot0 = 0;
@@ -287,10 +322,12 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);          // this warp no longer reads the stage
+        ODIS_TRACE_MARK(i == 0 && tl == 0, 2);                      // first tile: updated and stored
         if (bnd_tile) {
             asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kTile) : "memory");   // the group's peer stores are issued
             if (tl == 0) halo_tile_done(halo, (unsigned int)((halo.n_bnd + kTile - 1) / kTile));
         }
+        ODIS_TRACE_MARK(i == 0 && tl == 0, 3);                      // ... and counted done (boundary tile: fence + flag)
         for (int o = 16; o > 0; o >>= 1) e_area += __shfl_down_sync(0xffffffffu, e_area, o);
         warp_energy += e_area;
     }
@@ -300,6 +337,8 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
     __shared__ double warp_sums[kConsumerWarps];
     __shared__ bool is_last;
     if (lane == 0) warp_sums[warp - 1] = warp_energy;
+    ODIS_TRACE_MARK(tl == 0 && g == 0, 4);                          // group 0 through its tiles
+    ODIS_TRACE_MARK(tl == 0 && g == 1, 5);                          // group 1 through its tiles
     asm volatile("bar.sync 1, %0;" ::"n"(kGroups * kTile) : "memory");      // consumers only (the producer warp has left)
     if (threadIdx.x == 32) {
         double tot = 0.0;
@@ -309,6 +348,7 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
         is_last = (atomicAdd(s.ticket, 1u) == gridDim.x - 1);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kGroups * kTile) : "memory");
+    ODIS_TRACE_MARK(threadIdx.x == 32, 6);                          // CTA done (but for the last CTA's sum)
     if (is_last && warp == 1) {
         __threadfence();
         double acc = 0.0;
@@ -542,6 +582,8 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     __shared__ double ginv_s[kMerged ? kRows * kRows : 1];
     __shared__ double fac_s[kMerged ? kRows : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ODIS_TRACE_DECL
+    ODIS_TRACE_BEGIN(1);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kS; i++) {
             mbar_init(full + i, 1);
@@ -602,11 +644,14 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         // partitioned runs: the last tiles hold the cells that read ghost edges (own boundary cells, then the ghost cells)
         const bool bnd_tile = kPart && (c0 + kTile > halo.wait_from);
         mbar_wait(full + st, (i / kS) & 1);
+        ODIS_TRACE_MARK(i == 0 && tl == 0, 1);                      // first tile: its rows have arrived
         int packed[kCellEdges];
 #pragma unroll
         for (int j = 0; j < kCellEdges; j++) packed[j] = d->eid[j][tl];
         if (bnd_tile && !halo_seen) {                    // flags only grow: one wait per warp and launch
+            ODIS_TRACE_MARK(tl == 0, 2 + 2 * g);                    // group g: before / after the wait for the neighbours' flags
             halo_wait_warp(halo.wait_v, halo.ctl);
+            ODIS_TRACE_MARK(tl == 0, 3 + 2 * g);
             halo_seen = true;
         }
         // the six {v,l} gathers go out first; the rest of the stage is read (and the stage released) while they are in flight. A cell's
@@ -693,6 +738,8 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
             }
         }
     }
+    ODIS_TRACE_MARK(tl == 0 && g == 0, 6);                          // group 0 through its tiles
+    ODIS_TRACE_MARK(tl == 0 && g == 1, 7);
     if (LSG == 0) return;
     // ---- the CTA's harmonic sums: once per CTA ----
     __shared__ double red[kRows * kConsumerWarps];
@@ -992,6 +1039,17 @@ static cudaError_t launch_cell_cfg(const CellTables& t, const Physics& p, const 
     if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, kEcc>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
     return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, -1>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
 }
+
+#ifdef ODIS_TRACE
+cudaError_t trace_enable(unsigned long long* buf, unsigned int slots, unsigned int ctas) {
+    cudaError_t e;
+    const unsigned int zero[2] = {0u, 0u};
+    if ((e = cudaMemcpyToSymbol(g_trace_slots, &slots, sizeof slots)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(g_trace_ctas, &ctas, sizeof ctas)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(g_trace_arrivals, zero, sizeof zero)) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(g_trace, &buf, sizeof buf);
+}
+#endif
 
 cudaError_t launch_cell_step_pipe(const CellTables& t, const Physics& p, const CellState& s, int mode, const StepScalars& next,
                                   const HaloInline* halo, const CellSgAccum* sg, const ShExchange* x, cudaStream_t stream) {
