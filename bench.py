@@ -296,15 +296,26 @@ def variant_probe(args) -> None:
         prm = dict(g=9.80616, h=8e3, alpha=1e-7, dt=0.2 * dmin / math.sqrt(9.80616 * 8e3), radius=r, omega=7.292e-5, love_reduct=1.0, ecc=0.01,
                    obl=math.radians(-2.0), shell_thickness=0.0, semimajor_axis=0.0, potential=1, friction=0, surface=0, init_load=0, reorder=1)
         res = {}
-        for key, sel in (("4_launch_default", 0), ("6_launch_baseline", 1)):
+        # default: 4 launches per step (energy diagnostic and next potential folded into the edge / cell update); baseline selection: the
+        # six gather kernels + diagnostics + potential pass = 8 launches. Every timed chunk restarts from the zero state: at this resolution
+        # the reference's nonlinear scheme goes unstable after a few hundred steps, and a timing over NaN fields would prove little.
+        for key, sel in (("4_launch_default", 0), ("8_launch_baseline", 1)):
             sv = odis.Solver(mesh, dict(prm, kernel_select=sel))
             sv.enable_advection(nl)
             sv.step(60)
             res[key] = sv.field(odis.FIELD_ETA)
-            out[key + "_timesteps_per_s"] = round(400 / (sv.step_timed(400) * 1e-3), 1)
+            best = None
+            for _ in range(3):
+                sv.set_state()
+                sv.step(20)
+                ms = sv.step_timed(100) / 100
+                best = ms if best is None else min(best, ms)
+            out[key + "_timesteps_per_s"] = round(1.0 / (best * 1e-3), 1)
+            out[key + "_us_per_step"] = round(best * 1e3, 2)
+            out[key + "_finite"] = bool(math.isfinite(sv.dissipation_avg()))
             sv.close()
         out["cells"] = mesh.n_cells
-        out["fields_identical"] = bool(np.array_equal(res["4_launch_default"], res["6_launch_baseline"]))
+        out["fields_identical"] = bool(np.array_equal(res["4_launch_default"], res["8_launch_baseline"]))
     elif name == "synthetic_l10_1gpu":
         # BASELINE config 4's grid on ONE GPU (the N = 1 point of the 10,485,762-cell scaling curve): free-surface LTE, ECC, linear drag
         t0 = time.time()
@@ -595,10 +606,10 @@ def run_ours(args) -> None:
             solver.stage_state(h_v2, h_eta2, h_dv2, h_de2)
             for k in range(n):
                 solver.commit_state(iter=it0 + k * S)
+                solver.step(S)                                  # enqueued first: the device steps while the host packs the next state
+                solver.snapshot_begin(k & 1, snap_fields)
                 if k + 1 < n:
                     solver.stage_state(h_v2, h_eta2, h_dv2, h_de2)
-                solver.step(S)
-                solver.snapshot_begin(k & 1, snap_fields)
                 if k > 0:
                     solver.snapshot_wait((k - 1) & 1, copy=False)
             last = solver.snapshot_wait((n - 1) & 1, copy=False)

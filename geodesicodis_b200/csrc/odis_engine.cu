@@ -38,7 +38,6 @@ using odis::fail;
     } while (0)
 
 constexpr int kMaxPeers = 8;
-constexpr double kL2KeepDefaultMB = 0.0;     // default threshold of odis_solver::l2_keep (MB streamed per step); 0 = off until measured
 
 struct odis_solver {
     int device = 0;
@@ -185,7 +184,6 @@ struct odis_solver {
     bool pack_pending = false;
 
     long long wait_cycles = 0;               // ODIS_B200_WAIT_TIMEOUT_S in clock64 ticks (0: the kernels' default)
-    bool l2_keep = false;                    // the bytes a step streams (tables + state) fit the L2: no evict-first hint on the table rows
     int64_t iter = 0, iter0 = 0;
     bool have_state = false, diag_current = false;
     int last_mode = -1;
@@ -195,13 +193,11 @@ struct odis_solver {
     odis::EdgeTables edge_tables() const {
         odis::EdgeTables t;
         t.n_edges = Fo; t.stride = Fp; t.cells = d_cells; t.grad = d_grad; t.fcor = d_fcor; t.dist = d_dist; t.sid = d_sid; t.sw = d_sw;
-        t.l2_keep = l2_keep ? 1 : 0;
         return t;
     }
     odis::CellTables cell_tables(int n_active) const {
         odis::CellTables t;
         t.n_cells = Np; t.n_active = n_active; t.eid = d_eid; t.area = d_area; t.trig = d_trig; t.trig_sq = d_trig_sq;
-        t.l2_keep = l2_keep ? 1 : 0;
         return t;
     }
 };
@@ -552,15 +548,6 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
         s->wait_cycles = sec > 0.0 ? (long long)(sec * 2.0e9) : 0ll;
         if (s->wait_cycles > 0)
             cudaMemcpyAsync(&s->d_ctl->spin_cycles, &s->wait_cycles, sizeof(long long), cudaMemcpyHostToDevice, s->stream);
-    }
-    {   // L2 policy of the staged kernels' table rows: evict-first when a step streams more than the L2 holds beside the gathered state
-        // (the 655,362-cell grid on one GPU), none when everything a step touches fits — small grids and the ranks of a partitioned run
-        // then run out of the L2 from step to step. Threshold in MB of streamed bytes per step (216 B per edge + 160 B per cell held);
-        // ODIS_B200_L2_KEEP_MB overrides it (0: always evict-first).
-        const char* e = std::getenv("ODIS_B200_L2_KEEP_MB");
-        const double keep_mb = e ? std::atof(e) : kL2KeepDefaultMB;
-        const double step_mb = (216.0 * (double)F + 160.0 * (double)N) / 1.0e6;
-        s->l2_keep = step_mb <= keep_mb;
     }
     if (cudaSuccess != odis::pipe_configure()) return bail(fail(ODIS_ERR_CUDA, "cudaFuncSetAttribute(shared memory size) failed"));
     cudaMemsetAsync(s->d_eu[0], 0, (size_t)Np * sizeof(double2), s->stream);

@@ -62,9 +62,6 @@ struct EdgeTables {
     const double* dist;       // [F] d_e = face_node_dist
     const int* sid;           // [10][stride] stencil edge ids, slot order = ascending reference id, -1 pad
     const double* sw;         // [10][stride] TRiSK weights w_ee' in the same slot order
-    int l2_keep;              // staged kernels: 0 = table rows are streamed evict-first (they do not fit the L2 beside the state), 1 = this
-                              // solver's tables + state fit the L2 as a whole (small grids, ranks of a partitioned run): no eviction hint,
-                              // the rows stay resident from step to step
 };
 
 struct CellTables {
@@ -74,7 +71,6 @@ struct CellTables {
     const double* area;       // [N] control_volume_surf_area_map
     const double* trig;       // [8][N] cosLat sinLat cosLon sinLon cos2Lat sin2Lat cos2Lon sin2Lon   (mesh.cpp:2132-2142)
     const double* trig_sq;    // [2][N] cos^2 lat, sin^2 lat                                           (mesh.cpp:2144-2145)
-    int l2_keep;              // as EdgeTables::l2_keep
 };
 
 struct Physics {

@@ -78,15 +78,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // global -> shared bulk copy (TMA, 1-D), completion bytes counted on `bar`
 // read-once table rows are tagged evict-first in L2 so that they do not push the gathered state ({v,l}, {eta,U}),
-// which the next kernel re-reads, out of the 126 MB L2
+// which the next kernel re-reads, out of the 126 MB L2. (Measured on a B200, round 2: without the hint on grids whose tables fit the L2
+// as a whole — 40,962 and 163,842 cells — the step is no faster, 13.16 vs 13.21 us, resp. slower, 27.8 vs 26.1 us: those sizes are
+// latency-bound, not DRAM-bound, so the hint stays unconditional.)
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_evict_normal_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
@@ -111,11 +108,15 @@ __device__ __forceinline__ double2 ld_gather(const double2* p) {
 __device__ __forceinline__ void halo_tile_done(const HaloInline& h, unsigned int n_units) {
     __threadfence_system();
     if (atomicAdd(h.done, 1u) == n_units - 1u) {
+        // ONE system-scope fence (cumulative over every tile's stores: each was fenced before its count), then the flags as relaxed
+        // system-scope stores issued back to back. (A release store per neighbour, as until round 2, is a fence each: the second one
+        // waits for the first flag's NVLink round trip, and so on — about 3 us per neighbour, serial, measured as +6 / +11 / +18 us
+        // per step with 1 / 3 / 5 neighbours.)
         __threadfence_system();
         const unsigned long long epoch = ((volatile unsigned long long*)h.ctl->epoch)[0] + 1ull;
         for (int k = 0; k < h.n_peers; k++) {
             unsigned long long* f = h.remote.flags[k] + h.flag_slot;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
         }
         *h.done = 0u;
     }
@@ -226,7 +227,7 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
-            const uint64_t pol = t.l2_keep ? l2_evict_normal_policy() : l2_evict_first_policy();
+            const uint64_t pol = l2_evict_first_policy();
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kStages;
                 if (i >= kStages) mbar_wait(empty + st, ((i / kStages) - 1) & 1);
@@ -601,7 +602,7 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (warp == 0) {
         if (lane == 0) {
-            const uint64_t pol = t.l2_keep ? l2_evict_normal_policy() : l2_evict_first_policy();
+            const uint64_t pol = l2_evict_first_policy();
             const uint32_t stage_bytes = kCellFixedBytes + (uint32_t)rows.n * kTile * 8;
             for (int i = 0; i < my_tiles; i++) {
                 const int st = i % kS;
@@ -795,10 +796,9 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
                 const int r = q / kRows, k = q - r * kRows;
                 if (r != x.rank) cx_pub(x.block[r], (int)(epoch & 1ull))[(size_t)x.rank * kShXSlot + k] = __ldcg(bdst + k);
             }
-            __threadfence_system();
+            __threadfence_system();                              // every thread: its own pushes have landed (the waits overlap)
             asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
-            __threadfence_system();
-            if (ct < x.world) {
+            if (ct < x.world) {                                  // one lane per rank; the release store is the (cumulative) fence
                 unsigned long long* f = cx_flags(x.block[ct]) + x.rank;
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
             }

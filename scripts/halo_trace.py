@@ -7,11 +7,11 @@ import ctypes, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from geodesicodis_b200.build import build_variant
 lib_path = os.path.join(ROOT, "geodesicodis_b200", "libodis_b200_trace.so")
+os.environ["ODIS_B200_LIB"] = lib_path          # before the package is imported: geodesicodis_b200._lib reads it at import
+from geodesicodis_b200.build import build_variant
 if not os.path.exists(lib_path):
     build_variant("trace", ["ODIS_TRACE"])
-os.environ["ODIS_B200_LIB"] = lib_path
 import torch
 import geodesicodis_b200 as odis
 
@@ -47,6 +47,8 @@ torch.cuda.synchronize()
 if dist is not None:
     dist.barrier()
     torch.cuda.synchronize()
+from geodesicodis_b200 import _lib as odis_lib
+assert os.path.samefile(odis_lib.LIB_PATH, lib_path), odis_lib.LIB_PATH
 lib = ctypes.CDLL(lib_path)
 lib.odis_debug_trace_enable.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
 assert lib.odis_debug_trace_enable(buf.data_ptr(), SLOTS, CTAS) == 0

@@ -32,7 +32,14 @@ for name, adv, sel, env in (("linear", False, 0, None), ("nonlinear 6-launch bas
     l0 = s.launches
     s.step(40)
     per_step = (s.launches - l0) / 40
-    ms = min(s.step_timed(100) for _ in range(3)) / 100
+    # every timed chunk starts from the zero state again: at this resolution the reference's nonlinear scheme (no viscosity) goes
+    # unstable after a few hundred steps with any physics, and a timing over NaN fields would prove little
+    times = []
+    for _ in range(3):
+        s.set_state()
+        s.step(20)
+        times.append(s.step_timed(80) / 80)
+    ms = min(times)
     out[name] = ms
     eta = s.field(odis.FIELD_ETA)
     fields[name] = (eta, s.field(odis.FIELD_VELOCITY), s.dissipation_series())
@@ -42,7 +49,7 @@ for name, adv, sel, env in (("linear", False, 0, None), ("nonlinear 6-launch bas
 names = [n for n in out if n.startswith("nonlinear")]
 if len(names) < 2 or "linear" not in out:
     sys.exit(0)
-same = all(np.array_equal(fields[n][0], fields[names[0]][0]) and np.array_equal(fields[n][1], fields[names[0]][1]) for n in names[1:])
-ser = max(float(np.abs(fields[n][2] - fields[names[0]][2]).max() / max(np.abs(fields[names[0]][2]).max(), 1e-300)) for n in names[1:])
+same = all(np.array_equal(fields[n][0], fields[names[0]][0], equal_nan=True) and np.array_equal(fields[n][1], fields[names[0]][1], equal_nan=True) for n in names[1:])
+ser = max(float(np.nanmax(np.abs(fields[n][2] - fields[names[0]][2])) / max(np.nanmax(np.abs(fields[names[0]][2])), 1e-300)) for n in names[1:])
 print(f"nonlinear variants: fields bit-identical {same}; dissipation series max rel diff {ser:.2e}")
 print(f"nonlinear tables built on the host in {t_tab:.2f} s; nonlinear default / linear step time = {out[names[-1]] / out['linear']:.2f}")

@@ -150,7 +150,7 @@ def rewrite_asm(s: str) -> tuple[str, int]:
         ptx = "".join(re.findall(r'"((?:[^"\\]|\\.)*)"', sections[0]))
         outs = _operands(sections[1]) if len(sections) > 1 else []
         ins = _operands(sections[2]) if len(sections) > 2 else []
-        if ptx.startswith("createpolicy"):
+        if ptx.startswith("createpolicy") or "%globaltimer" in ptx:      # (the latter: tracing aid of the variant library, compiled out here)
             rep = f"{outs[0]} = 0;"
         elif ptx.startswith("ld.") and "{%0, %1}" in ptx:
             rep = f"{{ const auto* simt_p_ = ({ins[0]}); {outs[0]} = simt_p_->x; {outs[1]} = simt_p_->y; }}"
@@ -162,7 +162,7 @@ def rewrite_asm(s: str) -> tuple[str, int]:
             rep = f"{outs[0]} = *(const volatile decltype({outs[0]})*)({ins[0]});"
         elif ptx.startswith("ld."):
             rep = f"{outs[0]} = *({ins[0]});"
-        elif ptx.startswith("st.release"):
+        elif ptx.startswith("st.release") or ptx.startswith("st.relaxed.sys"):     # (a relaxed flag store behind a fence: modelled as a release store)
             rep = f"__atomic_store_n({ins[0]}, (unsigned long long)({ins[1]}), __ATOMIC_RELEASE);"
         elif ptx.startswith("st."):
             rep = f"*({ins[0]}) = ({ins[1]});"
