@@ -1044,7 +1044,9 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
         // merged solve + synthesis (grid-wide barrier, cooperative launch) on unpartitioned solvers; partitioned ones keep the separate
         // launch: measured faster there (655,362 cells on 8 GPUs: 48.9 vs 52.0 us per step), and no kernel of theirs then needs all of
         // its CTAs resident at once, so a collective of the caller's running beside the steps cannot close a wait cycle
-        s->sh_merged = odis::cell_pipe_merged() && s->world == 1;
+        // (ODIS_B200_MERGED_PART=1 selects the merged kernel on partitioned solvers too: A/B timing)
+        const char* mp = std::getenv("ODIS_B200_MERGED_PART");
+        s->sh_merged = odis::cell_pipe_merged() && (s->world == 1 || (mp && std::atoi(mp) != 0));
     }
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);     // captured without the extra launches

@@ -29,6 +29,12 @@ constexpr int kTile = 128;            // edges (cells) per tile = one consumer g
 constexpr int kGroups = 2;            // consumer groups per CTA
 constexpr int kStages = 4;            // tiles in flight per CTA
 constexpr int kPipeThreads = 32 + kGroups * kTile;
+// Partitioned launches of the edge kernel carry one more warp, the halo warp: it meets a consumer group at a named barrier when the
+// group has issued the peer stores of a boundary tile and then does the system-scope fence + count (+ flags) of that tile, so that the
+// group moves on to its next tile instead of sitting through the fence (measured on 2 and 4 B200s, round 2: up to 8 us per boundary
+// tile, which ended the boundary CTAs 4-5 us after all others, every step).
+constexpr int kHaloWarp = 1 + kGroups * kTile / 32;          // warp index of the halo warp
+constexpr int kPipeThreadsHalo = kPipeThreads + 32;
 
 // Launch of a per-step kernel. cooperative: the grid carries a grid-wide barrier, so all of its CTAs must be resident together — the
 // cooperative attribute makes the driver schedule the grid as a whole (two such grids of different streams never interleave
@@ -212,7 +218,7 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
     ODIS_TRACE_BEGIN(0);
     if (kIds16) {
         const int mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        for (int i = threadIdx.x; i < mine; i += kPipeThreads) wide_s[i] = tile_wide[(size_t)blockIdx.x + (size_t)i * gridDim.x];
+        for (int i = threadIdx.x; i < mine; i += (int)blockDim.x) wide_s[i] = tile_wide[(size_t)blockIdx.x + (size_t)i * gridDim.x];
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; i++) {
@@ -255,6 +261,17 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
                 bulk_g2s(d->h1, s.h1 + e0, kTile * 8, full + st, pol);
                 bulk_g2s(d->h2, s.h2 + e0, kTile * 8, full + st, pol);
             }
+        }
+        return;
+    }
+    const bool halo_warp_on = blockDim.x > kPipeThreads;    // partitioned launch
+    if (warp == kHaloWarp) {
+        // ---- halo warp: the boundary tiles are the first tiles; tile i of this CTA belongs to group i % kGroups ----
+        const int n_bnd_tiles = (halo.n_bnd + kTile - 1) / kTile;
+        for (int i = 0; i < my_tiles && (int)blockIdx.x + i * (int)gridDim.x < n_bnd_tiles; i++) {
+            asm volatile("bar.sync %0, %1;" ::"r"(4 + i % kGroups), "r"(kTile + 32) : "memory");   // the group's peer stores are issued
+            if (lane == 0) halo_tile_done(halo, (unsigned int)n_bnd_tiles);
+            __syncwarp();
         }
         return;
     }
@@ -325,8 +342,12 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
         if (lane == 0) mbar_arrive(empty + st);          // this warp no longer reads the stage
         ODIS_TRACE_MARK(i == 0 && tl == 0, 2);                      // first tile: updated and stored
         if (bnd_tile) {
-            asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kTile) : "memory");   // the group's peer stores are issued
-            if (tl == 0) halo_tile_done(halo, (unsigned int)((halo.n_bnd + kTile - 1) / kTile));
+            if (halo_warp_on) {                           // hand the tile to the halo warp (it is waiting there) and move on
+                asm volatile("bar.sync %0, %1;" ::"r"(4 + g), "r"(kTile + 32) : "memory");
+            } else {
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "r"(kTile) : "memory");   // the group's peer stores are issued
+                if (tl == 0) halo_tile_done(halo, (unsigned int)((halo.n_bnd + kTile - 1) / kTile));
+            }
         }
         ODIS_TRACE_MARK(i == 0 && tl == 0, 3);                      // ... and counted done (boundary tile: fence + flag)
         for (int o = 16; o > 0; o >>= 1) e_area += __shfl_down_sync(0xffffffffu, e_area, o);
@@ -370,11 +391,11 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
     }
 }
 
-__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
+__global__ void __launch_bounds__(kPipeThreadsHalo, 2) edge_step_pipe_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
                                                                           HaloInline halo) {
     edge_step_pipe_body<false>(t, p, s, mode, n_tiles, halo, nullptr, nullptr);
 }
-__global__ void __launch_bounds__(kPipeThreads, 2) edge_step_pipe16_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
+__global__ void __launch_bounds__(kPipeThreadsHalo, 2) edge_step_pipe16_kernel(EdgeTables t, Physics p, EdgeState s, int mode, int n_tiles,
                                                                             HaloInline halo, const short* sid16, const unsigned char* tile_wide) {
     edge_step_pipe_body<true>(t, p, s, mode, n_tiles, halo, sid16, tile_wide);
 }
@@ -509,11 +530,6 @@ __device__ __forceinline__ void halo_wait_warp(const HaloWait& w, StepCtl* ctl) 
     }
     __syncwarp();
 }
-__device__ __forceinline__ unsigned long long* cx_flags(unsigned char* block) { return reinterpret_cast<unsigned long long*>(block); }
-__device__ __forceinline__ double* cx_pub(unsigned char* block, int parity) {
-    return reinterpret_cast<double*>(block + kShMaxWorld * sizeof(unsigned long long)) + (size_t)parity * kShXRows;
-}
-
 // the synthesis of one cell: sum over degrees 2..LT of s_k Y_k (recurrences of sh_synthesis_mf_kernel, odis_sh.cu)
 template <int LT>
 __device__ __forceinline__ double cell_synthesis(const double* ssh, double u, double z, double c1, double s1) {
@@ -771,8 +787,9 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     if (is_last) {
         // the last CTA to arrive adds the CTAs' partials in CTA order: all of a lane's loads in flight together, then the butterfly
         __threadfence();
-        // partitioned: this rank's sums go into ITS slot of its own exchange block first ([parity][rank][kShXSlot]) ...
-        double* bdst = kPart ? cx_pub(x.block[x.rank], (int)(epoch & 1ull)) + (size_t)x.rank * kShXSlot : sg.b_out;
+        // partitioned: this rank's sums are collected in shared memory and PUSHED as LL lines (odis_sh.cuh) into slot [parity][rank] of
+        // every rank's exchange block, its own included — peer stores, no flag, no fence: the readers poll the lines in their own memory
+        double* bdst = kPart ? bsh : sg.b_out;
         constexpr int kMaxPerLane = 10;                               // grid <= 2 x 148 CTAs (cell_pipe_grid)
         for (int k = warp - 1; k < kRows; k += kConsumerWarps) {
             const double* row = sg.cta_partial + (size_t)k * sg.cta_stride;
@@ -788,19 +805,10 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         }
         if (!kMerged && ct == 0) *sg.ticket = 0u;
         if (kPart) {
-            // ... and are then PUSHED into the same slot of every other rank's block (peer stores), followed by the epoch flag
-            // (system-scope release): the readers find all ranks' sums in their own memory, no remote load on the critical path
-            __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
             for (int q = ct; q < x.world * kRows; q += kG * kTile) {
                 const int r = q / kRows, k = q - r * kRows;
-                if (r != x.rank) cx_pub(x.block[r], (int)(epoch & 1ull))[(size_t)x.rank * kShXSlot + k] = __ldcg(bdst + k);
-            }
-            __threadfence_system();                              // every thread: its own pushes have landed (the waits overlap)
-            asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
-            if (ct < x.world) {                                  // one lane per rank; the release store is the (cumulative) fence
-                unsigned long long* f = cx_flags(x.block[ct]) + x.rank;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+                sh_ll_store(sh_ll_lines(x.block[r], (int)(epoch & 1ull)) + (size_t)x.rank * kShXSlot + k, bsh[k], (unsigned int)epoch);
             }
             if (ct == 0) x.ctl[0] = epoch;
         }
@@ -814,23 +822,13 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
     // ---- merged: every CTA is past the grid barrier, this rank's sums are complete. b (all ranks), solve, synthesis of the own tiles ----
     if (kPart) {
         if (!is_last) epoch = ((volatile unsigned long long*)x.ctl)[0];         // written by the last CTA before the release
-        if (ct < x.world) {
-            const unsigned long long* f = cx_flags(x.block[x.rank]) + ct;
-            const long long t0 = clock64(), limit = (long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kHaloSpinCycles;
-            unsigned long long seen;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
-            } while (seen < epoch && clock64() - t0 < limit);
-            if (seen < epoch) x.ctl[2] = 1ull;
-        }
+        __shared__ double xs[kShMaxWorld * kShXSlot];
+        asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");             // (the last CTA: its own stores out of bsh are issued)
+        sh_ll_collect(x, epoch, kRows, xs, ct, kG * kTile, (long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kHaloSpinCycles);
         asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
         if (ct < kRows) {
             double a = 0.0;
-            for (int r = 0; r < x.world; r++) {               // rank order: the same bits on every rank and in every CTA
-                double v;                                    // (pushed into this rank's own block by rank r)
-                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(cx_pub(x.block[x.rank], (int)(epoch & 1ull)) + (size_t)r * kShXSlot + ct) : "memory");
-                a = a + v;
-            }
+            for (int r = 0; r < x.world; r++) a = a + xs[r * kShXSlot + ct];      // rank order: the same bits on every rank and in every CTA
             bsh[ct] = a;
             if (blockIdx.x == 0) sg.b_out[ct] = a;
         }
@@ -942,7 +940,7 @@ cudaError_t launch_edge_step_pipe(const EdgeTables& t, const Physics& p, const E
     const int grid = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
     HaloInline none;
     none.n_bnd = 0;
-    return launch_step_kernel(edge_step_pipe_kernel, grid, kPipeThreads, smem, stream, false, t, p, s, mode, n_tiles, halo ? *halo : none);
+    return launch_step_kernel(edge_step_pipe_kernel, grid, halo ? kPipeThreadsHalo : kPipeThreads, smem, stream, false, t, p, s, mode, n_tiles, halo ? *halo : none);
 }
 
 bool edge_ids16_fits(int n_edges) {
@@ -970,7 +968,7 @@ cudaError_t launch_edge_step_pipe16(const EdgeTables& t, const Physics& p, const
     const size_t smem = kStages * sizeof(EdgeStage) + 2 * kStages * sizeof(uint64_t) + (size_t)((per_cta + 15) / 16 * 16);
     HaloInline none;
     none.n_bnd = 0;
-    return launch_step_kernel(edge_step_pipe16_kernel, grid, kPipeThreads, smem, stream, false, t, p, s, mode, n_tiles, halo ? *halo : none, sid16, tile_wide);
+    return launch_step_kernel(edge_step_pipe16_kernel, grid, halo ? kPipeThreadsHalo : kPipeThreads, smem, stream, false, t, p, s, mode, n_tiles, halo ? *halo : none, sid16, tile_wide);
 }
 
 CellRows cell_rows_for(int potential, bool with_basis) {

@@ -405,19 +405,14 @@ __global__ void __launch_bounds__(kShThreads) sh_bsolve_synthesis_mf_kernel(ShTa
     __shared__ double ssh[kShInlineRows];
     const int warp = threadIdx.x >> 5;
     if (x.world > 1) {
+        // every rank pushed its sums as LL lines into this rank's own block ([parity][rank][kShXSlot], odis_sh.cuh): poll them there
+        __shared__ double xs[kShMaxWorld * kShXSlot];
         const unsigned long long epoch = x.ctl[0];
-        if ((int)threadIdx.x < x.world) {
-            const unsigned long long* f = x_flags(x.block[x.rank]) + threadIdx.x;
-            const long long t0 = clock64();
-            while (ld_acquire_sys(f) < epoch) {
-                if (clock64() - t0 > ((long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kShSpinCycles)) { x.ctl[2] = 1ull; break; }
-                __nanosleep(64);
-            }
-        }
+        sh_ll_collect(x, epoch, t.rows, xs, (int)threadIdx.x, kShThreads, (long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kShSpinCycles);
         __syncthreads();
         for (int k = threadIdx.x; k < t.rows; k += kShThreads) {
-            double a = 0.0;                                  // every rank pushed its sums into this rank's own block: [parity][rank][kShXSlot]
-            for (int r = 0; r < x.world; r++) a = a + ld_relaxed_sys(x_pub(x.block[x.rank], (int)(epoch & 1)) + (size_t)r * kShXSlot + k);
+            double a = 0.0;
+            for (int r = 0; r < x.world; r++) a = a + xs[r * kShXSlot + k];      // rank order: the same bits on every rank and in every CTA
             bsh[k] = a;
             if (blockIdx.x == 0) w.b[k] = a;
         }

@@ -60,11 +60,47 @@ constexpr int kShXRows = 1024;
 constexpr int kShXSlot = 32;
 static_assert(kShMaxWorld * kShXSlot <= kShXRows, "push layout fits one parity buffer");
 constexpr size_t kShXBytes = kShMaxWorld * sizeof(unsigned long long) + 2 * (size_t)kShXRows * sizeof(double);
+// ... as "LL" lines (the low-latency protocol of collective libraries): every double travels as ONE 16-byte store {low word, tag, high
+// word, tag}, tag = low 32 bits of the epoch. A reader polls the line in its own memory until both tags show the epoch it waits for —
+// each 8-byte half {data, tag} arrives atomically, so a matching tag proves its data — and needs neither a flag nor a fence: the
+// all-reduce costs ONE NVLink crossing instead of three (data + system fence, release flag, the reader's acquire). Lines live in the
+// data region of the block: [2 parities][kShMaxWorld ranks][kShXSlot] x 16 B = 8 KB of its 16 KB.
 struct ShExchange {
     int world, rank;
     unsigned long long* ctl;                 // local: [0] epoch, [1] ticket, [2] set to 1 when a wait gave up, [3] wait limit in clock64 ticks (0: default)
     unsigned char* block[kShMaxWorld];       // every rank's exchange block, own included
 };
+
+__device__ __forceinline__ uint4* sh_ll_lines(unsigned char* block, int parity) {
+    return reinterpret_cast<uint4*>(block + kShMaxWorld * sizeof(unsigned long long)) + (size_t)parity * (kShMaxWorld * kShXSlot);
+}
+__device__ __forceinline__ void sh_ll_store(uint4* line, double v, unsigned int tag) {
+    const unsigned int lo = (unsigned int)__double2loint(v), hi = (unsigned int)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+// one look at a line: true (and the value) when both halves carry `tag`
+__device__ __forceinline__ bool sh_ll_load(const uint4* line, unsigned int tag, double* v) {
+    unsigned int lo, t0, hi, t1;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(line) : "memory");
+    *v = __hiloint2double((int)hi, (int)lo);
+    return t0 == tag && t1 == tag;
+}
+// every rank's sums of `epoch` out of this rank's own block into xs[rank * kShXSlot + row] (shared memory), `nthreads` threads with
+// index `tid` polling one line each; bounded by `limit` clock64 ticks, a give-up is recorded in ctl[2]
+__device__ __forceinline__ void sh_ll_collect(const ShExchange& x, unsigned long long epoch, int rows, double* xs, int tid, int nthreads,
+                                              long long limit) {
+    const uint4* lines = sh_ll_lines(x.block[x.rank], (int)(epoch & 1ull));
+    const unsigned int tag = (unsigned int)epoch;
+    for (int q = tid; q < x.world * rows; q += nthreads) {
+        const int r = q / rows, k = q - r * rows;
+        const long long t0 = clock64();
+        double v = 0.0;
+        bool ok = sh_ll_load(lines + (size_t)r * kShXSlot + k, tag, &v);
+        while (!ok && clock64() - t0 < limit) ok = sh_ll_load(lines + (size_t)r * kShXSlot + k, tag, &v);
+        if (!ok) x.ctl[2] = 1ull;
+        xs[r * kShXSlot + k] = v;
+    }
+}
 
 constexpr int kShInlineRows = 128;    // up to here one launch both sums the per-CTA partials and applies the solve
 // launches per call of launch_sh_analysis (analysis + reduce/solve)

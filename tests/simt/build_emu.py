@@ -152,6 +152,14 @@ def rewrite_asm(s: str) -> tuple[str, int]:
         ins = _operands(sections[2]) if len(sections) > 2 else []
         if ptx.startswith("createpolicy") or "%globaltimer" in ptx:      # (the latter: tracing aid of the variant library, compiled out here)
             rep = f"{outs[0]} = 0;"
+        elif ptx.startswith("st.volatile.global.v4.u32"):        # LL line: each 8-byte half {data, tag} lands atomically
+            rep = (f"{{ unsigned long long* simt_p_ = (unsigned long long*)({ins[0]}); "
+                   f"__atomic_store_n(simt_p_, (unsigned long long)({ins[1]}) | ((unsigned long long)({ins[2]}) << 32), __ATOMIC_RELEASE); "
+                   f"__atomic_store_n(simt_p_ + 1, (unsigned long long)({ins[3]}) | ((unsigned long long)({ins[4]}) << 32), __ATOMIC_RELEASE); }}")
+        elif ptx.startswith("ld.volatile.global.v4.u32"):
+            rep = (f"{{ const unsigned long long* simt_p_ = (const unsigned long long*)({ins[0]}); std::this_thread::yield(); "
+                   f"const unsigned long long simt_a_ = __atomic_load_n(simt_p_, __ATOMIC_ACQUIRE), simt_b_ = __atomic_load_n(simt_p_ + 1, __ATOMIC_ACQUIRE); "
+                   f"{outs[0]} = (unsigned int)simt_a_; {outs[1]} = (unsigned int)(simt_a_ >> 32); {outs[2]} = (unsigned int)simt_b_; {outs[3]} = (unsigned int)(simt_b_ >> 32); }}")
         elif ptx.startswith("ld.") and "{%0, %1}" in ptx:
             rep = f"{{ const auto* simt_p_ = ({ins[0]}); {outs[0]} = simt_p_->x; {outs[1]} = simt_p_->y; }}"
         elif ptx.startswith("cp.async.bulk.prefetch"):          # no data moves; touching both ends lets the address sanitizer check the range
@@ -224,6 +232,12 @@ def build(force: bool = False, verbose: bool = False, asan: bool = False, tsan: 
         san = ["-g", "-fsanitize=thread", "--param=tsan-instrument-func-entry-exit=0"]
     flags = ["-O1", *san, "-mtls-dialect=gnu2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC]
     jobs = []
+    for name in sorted(os.listdir(CSRC)):                       # device headers with inline PTX get the same rewrite: the transformed
+        if name.endswith(".cuh"):                               # copy sits beside the transformed sources, where #include "..." looks first
+            with open(os.path.join(CSRC, name)) as f:
+                text = transform(name, f.read())
+            with open(os.path.join(src_dir, name), "w") as f:
+                f.write(text)
     for name in CUDA_SOURCES:
         with open(os.path.join(CSRC, name)) as f:
             text = transform(name, f.read())

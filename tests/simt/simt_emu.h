@@ -48,6 +48,7 @@ using std::min;
 
 struct double2 { double x, y; };
 struct int2 { int x, y; };
+struct alignas(16) uint4 { unsigned int x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
     unsigned x, y, z;
@@ -269,6 +270,11 @@ inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t st) {
 
 // ---- device intrinsics ----
 inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, sizeof b); return (int)(b >> 32); }
+inline int __double2loint(double x) { long long b; std::memcpy(&b, &x, sizeof b); return (int)(b & 0xffffffffll); }
+inline double __hiloint2double(int hi, int lo) {
+    const unsigned long long b = ((unsigned long long)(unsigned int)hi << 32) | (unsigned long long)(unsigned int)lo;
+    double x; std::memcpy(&x, &b, sizeof x); return x;
+}
 inline double __drcp_rn(double x) { return 1.0 / x; }                   // rcp.rn.f64 is correctly rounded, as IEEE division
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
