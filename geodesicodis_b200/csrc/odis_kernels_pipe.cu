@@ -124,6 +124,10 @@ __device__ __forceinline__ void halo_tile_done(const HaloInline& h, unsigned int
             unsigned long long* f = h.remote.flags[k] + h.flag_slot;
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
         }
+        // the publisher — one thread per launch — also records the epoch for the cell kernel that follows (which waits for the
+        // neighbours' flags to reach it). Not the CTA that happens to finish last: the halo warp publishes while the consumers carry on,
+        // and on a small grid every CTA can be through its tiles before the fence above returns.
+        ((volatile unsigned long long*)h.ctl->epoch)[0] = epoch;
         *h.done = 0u;
     }
 }
@@ -382,7 +386,6 @@ __device__ __forceinline__ void edge_step_pipe_body(const EdgeTables& t, const P
                 s.series[k] = acc;
                 s.ctl->cur = s.scal[k];
                 s.ctl->count = k + 1ull;
-                if (halo.n_bnd > 0) s.ctl->epoch[0] += 1ull;    // every CTA is past its boundary tiles: the v exchange is published
             } else {
                 *s.energy_out = acc;
             }

@@ -77,7 +77,7 @@ def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
     tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py", "tests/test_variant_ids16_gpu.py::test_narrow_ids_on_a_partitioned_grid",
                                                               "tests/test_self_gravity_step_gpu.py::test_three_launch_step_on_a_partitioned_grid"],
                                           extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="", workers=3)
-    assert int(tail.split(" passed")[0].split()[-1]) == 14 and "skipped" not in tail, tail
+    assert int(tail.split(" passed")[0].split()[-1]) == 18 and "skipped" not in tail, tail
 
 
 def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
