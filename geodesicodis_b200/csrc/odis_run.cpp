@@ -412,7 +412,21 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     // Overlapped output (options.overlap_output): a dump is split into begin (the copy-out is enqueued behind the steps taken so far,
     // odis_snapshot_begin) and finish (wait for the copy, log line, float conversion, data.h5 rows). The next interval's steps are
     // enqueued between the two, so the GPU computes them while the host writes. Same files as the synchronous path.
-    const bool overlap = opt.overlap_output != 0 && world == 1;        // output snapshots need the unpartitioned solver
+    // Partitioned runs: every rank's snapshot holds its OWN entries, compact; they are placed by the rank's partition map.
+    const bool overlap = opt.overlap_output != 0;
+    std::vector<std::vector<int32_t>> own_cells((size_t)world), own_edges((size_t)world);
+    std::vector<double> g_eta, g_ven, g_diss, g_v;
+    if (overlap && world > 1) {
+        for (int k = 0; k < world && rc == ODIS_OK; k++) {
+            int32_t nc = 0, ne = 0;
+            rc = odis_get_partition(ranks[(size_t)k], nullptr, nullptr, &nc, &ne, nullptr, nullptr, nullptr);
+            if (rc != ODIS_OK) break;
+            own_cells[(size_t)k].resize((size_t)nc); own_edges[(size_t)k].resize((size_t)ne);
+            rc = odis_get_partition_map(ranks[(size_t)k], own_cells[(size_t)k].data(), own_edges[(size_t)k].data());
+        }
+        if (rc != ODIS_OK) return terminate(rc, odis_last_error());
+        g_eta.assign((size_t)N, 0.0); g_ven.assign((size_t)F * 2, 0.0); g_diss.assign((size_t)F, 0.0); g_v.assign((size_t)F, 0.0);
+    }
     uint32_t snap_fields = 0;
     if (ds_u >= 0) snap_fields |= ODIS_SNAP_VELOCITY_EN;
     if (ds_ux >= 0) snap_fields |= ODIS_SNAP_VELOCITY;
@@ -421,7 +435,7 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     int snap_slot = 0, pending_slot = -1;
     double pending_time = 0.0;
     auto begin_dump = [&](double current_time) -> int {
-        const int rc2 = odis_snapshot_begin(s, snap_slot, snap_fields);
+        const int rc2 = on_all([&](odis_solver* h) { return odis_snapshot_begin(h, snap_slot, snap_fields); });
         if (rc2) return rc2;
         pending_slot = snap_slot;
         pending_time = current_time;
@@ -431,7 +445,29 @@ int odis_run(const char* run_dir_c, const odis_run_options* opt_in, odis_run_res
     auto finish_dump = [&]() -> int {
         if (pending_slot < 0) return ODIS_OK;
         odis_snapshot_view view{};
-        const int rc2 = odis_snapshot_wait(s, pending_slot, &view);
+        int rc2 = odis_snapshot_wait(s, pending_slot, &view);
+        if (rc2 == ODIS_OK && world > 1) {
+            // the ranks' own entries -> reference-ordered arrays of the whole grid; the dissipation sum is the sum of the ranks' shares
+            double tot = 0.0;
+            for (int k = 0; k < world && rc2 == ODIS_OK; k++) {
+                odis_snapshot_view vk{};
+                if (k > 0) rc2 = odis_snapshot_wait(ranks[(size_t)k], pending_slot, &vk);
+                else vk = view;
+                if (rc2 != ODIS_OK) break;
+                tot += vk.dissipation_avg;
+                const std::vector<int32_t>& cm = own_cells[(size_t)k];
+                const std::vector<int32_t>& em = own_edges[(size_t)k];
+                if (vk.eta) for (size_t i = 0; i < cm.size(); i++) g_eta[(size_t)cm[i]] = vk.eta[i];
+                if (vk.velocity_en) for (size_t i = 0; i < em.size(); i++) { g_ven[(size_t)em[i] * 2] = vk.velocity_en[2 * i]; g_ven[(size_t)em[i] * 2 + 1] = vk.velocity_en[2 * i + 1]; }
+                if (vk.dissipation) for (size_t i = 0; i < em.size(); i++) g_diss[(size_t)em[i]] = vk.dissipation[i];
+                if (vk.velocity) for (size_t i = 0; i < em.size(); i++) g_v[(size_t)em[i]] = vk.velocity[i];
+            }
+            view.dissipation_avg = tot;
+            if (view.eta) view.eta = g_eta.data();
+            if (view.velocity_en) view.velocity_en = g_ven.data();
+            if (view.dissipation) view.dissipation = g_diss.data();
+            if (view.velocity) view.velocity = g_v.data();
+        }
         pending_slot = -1;
         if (rc2) return rc2;
         e_diss = view.dissipation_avg;

@@ -415,7 +415,8 @@ typedef struct odis_run_options {
     int32_t n_gpus;       /* 0 or 1: one GPU. N > 1: the grid is cut into N space-filling-curve parts, one partitioned solver per GPU
                            * (devices device .. device + N - 1) driven from this one process; halos and harmonic sums are exchanged by the
                            * step kernels through peer memory. Same files as the one-GPU run (bit-identical without the self-gravity
-                           * term). Not with `advection; true` or overlap_output. */
+                           * term), also with overlap_output (every rank's own entries come back compact and are placed by its partition
+                           * map). Not with `advection; true`. */
 } odis_run_options;
 
 typedef struct odis_run_result {

@@ -149,3 +149,14 @@ def test_partitioned_whole_run_writes_the_same_files(odis, tmp_path, world):
     # against the reference's own float32 rows too
     ref = {k[3:]: case[k] for k in case if k.startswith("h5_")}
     assert np.array_equal(hn["displacement"], ref["displacement"])
+    # ... and with the dumps overlapped with stepping (`ODIS --gpus N --overlap-output`): every rank's own entries come back compact
+    # through its snapshot slots and are placed by its partition map — byte for byte the files of the synchronous partitioned run
+    do = make_run_dir(tmp_path / "many_overlapped", case)
+    ro = odis.run(do, n_gpus=world, overlap_output=True)
+    assert ro["steps"] == rn["steps"] and ro["dumps"] == rn["dumps"]
+    ho = read_h5(os.path.join(do, "DATA", "data.h5"))
+    for name in hn:
+        assert np.array_equal(ho[name], hn[name]), name
+    assert dumping_lines(open(os.path.join(do, "DATA", "OUTPUT.txt")).read()) == dumping_lines(outn)
+    for f in ("vel_init.txt", "pres_init.txt"):
+        assert open(os.path.join(do, "InitialConditions", f)).read() == open(os.path.join(dn, "InitialConditions", f)).read()
