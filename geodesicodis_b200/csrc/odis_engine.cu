@@ -111,10 +111,10 @@ struct odis_solver {
 
     // nonlinear branch (odis_enable_advection)
     bool nl_on = false;
-    bool nl_fused = true;            // the 4-launch nonlinear step (measured +11 %); the baseline selection (bit 0) keeps the 6-launch one
-    bool nl_folded = true;           // ... with the energy diagnostic and the next potential folded into its launches (ODIS_B200_NL_FOLDED=0: the
-                                     // two passes of their own, for A/B timing)
-    int nl_launches() const { return nl_fused ? odis::kNlLaunchesFused : odis::kNlLaunches; }
+    bool nl_folded = true;           // the 4-launch nonlinear step (vertex PV + cell Ekin in one grid, thickness flux / energy diagnostic inside the
+                                     // edge update, next potential inside the cell update); the baseline selection (bit 0) keeps the six gather
+                                     // launches + diagnostics + potential pass
+    int nl_launches() const { return nl_folded ? odis::kNlLaunchesFolded : odis::kNlLaunches; }
     odis::NlTables nl{};
     double *d_nl_qv = nullptr, *d_nl_ekin = nullptr, *d_nl_flux = nullptr;
     double2* d_nl_fq = nullptr;
@@ -399,10 +399,9 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
     // self-gravity launches, 6-launch nonlinear step); bit 3 = no CUDA-graph replay; bit 7 = 32-bit stencil ids only (default: 16-bit
     // offsets where they fit); bit 8 = test hook of the narrow ids (+-1023 range)
     s->pipe_edge = (prm->reserved[0] & 1) == 0;
-    s->pipe_cell = s->pipe_edge && !(std::getenv("ODIS_B200_DIRECT_CELL") && std::atoi(std::getenv("ODIS_B200_DIRECT_CELL")) != 0);
+    s->pipe_cell = s->pipe_edge;
     s->use_graph = (prm->reserved[0] & 8) == 0;
-    s->nl_fused = s->pipe_edge;
-    { const char* e = std::getenv("ODIS_B200_NL_FOLDED"); s->nl_folded = !(e && std::atoi(e) == 0); }
+    s->nl_folded = s->pipe_edge;
     s->edge_ids16 = (prm->reserved[0] & 128) == 0 && s->pipe_edge;
     const int N = s->N, F = s->F, No = s->No, Fo = s->Fo, Np = s->Np, Fp = s->Fp;
     const int Fvl = (F + tile - 1) / tile * tile;       // {v,l} arrays: every local edge, padded to whole tiles
@@ -474,7 +473,6 @@ int create_impl(const odis_mesh_view* mv, const odis_params* prm, int32_t device
                 n_wide += w;
             }
             s->wide_tiles = n_wide;
-            if (std::getenv("ODIS_B200_TRACE_IDS16")) std::fprintf(stderr, "ids16: %d of %d tiles wide (rank %d of %d)\n", n_wide, n_tiles, s->rank, s->world);
             if (!odis::edge_ids16_fits(Fo)) s->edge_ids16 = false;      // more tiles per CTA than the flag buffer holds: stays on the int rows
             else if ((rc = upload(s, &s->d_sid16, sid16)) || (rc = upload(s, &s->d_tile_wide, wide))) return bail(rc);
         }
@@ -1044,9 +1042,8 @@ int odis_enable_self_gravity(odis_solver* s, const odis_mesh_view* mv, int32_t l
         // merged solve + synthesis (grid-wide barrier, cooperative launch) on unpartitioned solvers; partitioned ones keep the separate
         // launch: measured faster there (655,362 cells on 8 GPUs: 48.9 vs 52.0 us per step), and no kernel of theirs then needs all of
         // its CTAs resident at once, so a collective of the caller's running beside the steps cannot close a wait cycle
-        // (ODIS_B200_MERGED_PART=1 selects the merged kernel on partitioned solvers too: A/B timing)
-        const char* mp = std::getenv("ODIS_B200_MERGED_PART");
-        s->sh_merged = odis::cell_pipe_merged() && (s->world == 1 || (mp && std::atoi(mp) != 0));
+        // (measured again after the all-reduce became LL lines, 2 and 4 GPUs: merged 59.3 / 39.8 us per step, separate 59.5 / 39.7)
+        s->sh_merged = odis::cell_pipe_merged() && s->world == 1;
     }
     ODIS_CUDA(cudaStreamSynchronize(s->stream));
     for (auto& g : s->graphs) cudaGraphExecDestroy(g.second);     // captured without the extra launches
@@ -1245,7 +1242,7 @@ constexpr int kGraphSteps = 12;      // steps per captured graph: a multiple of 
 // edge update, next potential inside the cell update. Otherwise: diagnostics of v^n (the linear edge kernel produces them on the fly), the launches of
 // odis_kernels_nl.cu, the potential pass for the next step.
 static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEvent_t>* marks, int k) {
-    const bool folded = s->nl_fused && s->nl_folded;
+    const bool folded = s->nl_folded;
     // forcing for the next step (current_time = dt*(iter+1), evaluated at current_time + dt)
     const odis::StepScalars next = step_scalars(s, s->prm.dt * (double)(s->iter + 1) + s->prm.dt);
     if (!folded)
@@ -1260,7 +1257,6 @@ static int enqueue_step_nonlinear(odis_solver* s, int mode, std::vector<cudaEven
     ns.qv = s->d_nl_qv; ns.fq = s->d_nl_fq; ns.ekin = s->d_nl_ekin; ns.flux = s->d_nl_flux;
     ns.block_partial = s->d_block_partial; ns.ticket = s->d_ticket; ns.energy_out = s->d_series + (s->iter - s->iter0);
     if (folded) odis::launch_step_nonlinear_folded(s->nl, s->phys, ns, mode, s->cell_tables(s->N), next, s->stream);
-    else if (s->nl_fused) odis::launch_step_nonlinear_fused(s->nl, s->phys, ns, mode, s->stream);
     else odis::launch_step_nonlinear(s->nl, s->phys, ns, mode, s->stream);
     if (marks) cudaEventRecord((*marks)[(size_t)k * 4 + 1], s->stream);
     if (mode == odis::AB3_FULL) s->hv1 = 1 - s->hv1;

@@ -395,15 +395,6 @@ void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s
     nl_cell_step_kernel<false><<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode, CellTables{}, StepScalars{});
 }
 
-void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream) {
-    auto grid = [](int n) { return (unsigned)((n + kNlThreads - 1) / kNlThreads); };
-    const unsigned vb = grid(t.n_vertices);
-    nl_vertex_ekin_kernel<<<vb + grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, (int)vb);
-    nl_edge_prep_kernel<<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s);
-    nl_edge_step_flux_kernel<false><<<grid(t.n_edges), kNlThreads, 0, stream>>>(t, p, s, mode);
-    nl_cell_step_kernel<false><<<grid(t.n_cells), kNlThreads, 0, stream>>>(t, p, s, mode, CellTables{}, StepScalars{});
-}
-
 void launch_step_nonlinear_folded(const NlTables& t, const Physics& p, const NlState& s, int mode, const CellTables& ct, const StepScalars& next,
                                   cudaStream_t stream) {
     auto grid = [](int n) { return (unsigned)((n + kNlThreads - 1) / kNlThreads); };

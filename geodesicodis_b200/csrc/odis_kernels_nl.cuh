@@ -72,14 +72,12 @@ struct NlState {
 // edge update, flux, cell update
 constexpr int kNlLaunches = 6;
 void launch_step_nonlinear(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream);
-// Opt-in variant, same arithmetic in 4 launches: vertex PV + cell Ekin in one grid; edge {F_e, q_e}; edge update + thickness flux;
-// cell update. Bit-identical fields.
-constexpr int kNlLaunchesFused = 4;
-void launch_step_nonlinear_fused(const NlTables& t, const Physics& p, const NlState& s, int mode, cudaStream_t stream);
-// Default: the same 4 launches with the two passes AROUND them folded in — the dissipated energy of v^n is summed inside the edge update
+// Default: the same arithmetic in 4 launches — vertex PV + cell Ekin in one grid; edge {F_e, q_e}; edge update + thickness flux; cell
+// update — with the two passes AROUND the step folded in: the dissipated energy of v^n is summed inside the edge update
 // (instead of edge_diag_kernel before the step) and the cell update evaluates the next step's tidal potential itself (instead of a
 // cell_step_kernel pass after it): 4 launches per step instead of 6. Fields bit-identical; the energy sum within ~1e-15 (bar 1e-12).
 // ct: the trig rows of the potential; next: its time factors (forcing(current_time + dt) of the next step).
+constexpr int kNlLaunchesFolded = 4;
 void launch_step_nonlinear_folded(const NlTables& t, const Physics& p, const NlState& s, int mode, const CellTables& ct, const StepScalars& next,
                                   cudaStream_t stream);
 

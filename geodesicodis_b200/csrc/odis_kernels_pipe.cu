@@ -591,6 +591,7 @@ template <int kG, int kS, int LSG, bool kPart, bool kMerged, int kPot>
 __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const Physics& p, const CellState& s, int mode, StepScalars next,
                                                     int n_tiles, const CellRows& rows, const HaloInline& halo, const CellSgAccum& sg,
                                                     const ShExchange& x) {
+    static_assert(!(kMerged && kPart), "partitioned solvers keep solve + synthesis in a launch of their own (sh_bsolve_synthesis_mf_kernel)");
     constexpr int kThreads = 32 + kG * kTile;
     constexpr int kConsumerWarps = kG * kTile / 32;
     constexpr int kRows = LSG > 0 ? (LSG + 1) * (LSG + 1) : 1;
@@ -822,20 +823,8 @@ __device__ __forceinline__ void cell_step_pipe_body(const CellTables& t, const P
         }
     }
     if (!kMerged) return;
-    // ---- merged: every CTA is past the grid barrier, this rank's sums are complete. b (all ranks), solve, synthesis of the own tiles ----
-    if (kPart) {
-        if (!is_last) epoch = ((volatile unsigned long long*)x.ctl)[0];         // written by the last CTA before the release
-        __shared__ double xs[kShMaxWorld * kShXSlot];
-        asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");             // (the last CTA: its own stores out of bsh are issued)
-        sh_ll_collect(x, epoch, kRows, xs, ct, kG * kTile, (long long)x.ctl[3] > 0 ? (long long)x.ctl[3] : kHaloSpinCycles);
-        asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
-        if (ct < kRows) {
-            double a = 0.0;
-            for (int r = 0; r < x.world; r++) a = a + xs[r * kShXSlot + ct];      // rank order: the same bits on every rank and in every CTA
-            bsh[ct] = a;
-            if (blockIdx.x == 0) sg.b_out[ct] = a;
-        }
-    } else if (ct < kRows) bsh[ct] = __ldcg(sg.b_out + ct);
+    // ---- merged (unpartitioned solvers): every CTA is past the grid barrier, the sums are complete. Solve, synthesis of the own tiles ----
+    if (ct < kRows) bsh[ct] = __ldcg(sg.b_out + ct);
     asm volatile("bar.sync 1, %0;" ::"n"(kG * kTile) : "memory");
     for (int j = warp - 1; j < kRows; j += kConsumerWarps) {   // s_j = (g factor_j) sum_k Ginv[j][k] b_k, order of solve_rows (odis_sh.cu)
         const double f = fac_s[j];
@@ -897,8 +886,11 @@ static cudaError_t cell_pipe_attrs() {
     else {
         if (e != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, false, (int)P_ECC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, true, (int)P_ECC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem)) != cudaSuccess) return e;
-        return cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, kPart, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
+        if constexpr (kPart) return e;
+        else {
+            if ((e = cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, false, true, (int)P_ECC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem)) != cudaSuccess) return e;
+            return cudaFuncSetAttribute(cell_step_pipe_kernel<LSG, false, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem);
+        }
     }
 }
 
@@ -1031,11 +1023,11 @@ static cudaError_t launch_cell_cfg(const CellTables& t, const Physics& p, const 
     constexpr int kBlock = 32 + kCellGroups * kTile;
     constexpr int kEcc = LSG > 0 ? (int)P_ECC : -1;          // the one-potential build exists for the self-gravity variants (register pressure)
     const bool ecc = LSG > 0 && p.potential == P_ECC;
-    if (LSG > 0 && sg.merged) {
-        static int coop = -1;                 // experiments: ODIS_B200_COOP=0 launches the merged kernel without the cooperative attribute
-        if (coop < 0) { const char* e = std::getenv("ODIS_B200_COOP"); coop = (e && std::atoi(e) == 0) ? 0 : 1; }
-        if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), kEcc>, grid, kBlock, kCellSmem, stream, coop != 0, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
-        return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, (LSG > 0), -1>, grid, kBlock, kCellSmem, stream, coop != 0, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+    if constexpr (LSG > 0 && !kPart) {        // merged solve + synthesis: unpartitioned solvers only (cooperative launch: all CTAs resident)
+        if (sg.merged) {
+            if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, false, true, kEcc>, grid, kBlock, kCellSmem, stream, true, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+            return launch_step_kernel(cell_step_pipe_kernel<LSG, false, true, -1>, grid, kBlock, kCellSmem, stream, true, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
+        }
     }
     if (ecc) return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, kEcc>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);
     return launch_step_kernel(cell_step_pipe_kernel<LSG, kPart, false, -1>, grid, kBlock, kCellSmem, stream, false, t, p, s, mode, next, n_tiles, rows, halo, sg, x);

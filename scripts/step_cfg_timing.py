@@ -1,6 +1,6 @@
 """One configuration of the headline step per process (the experiment switches are environment variables read once per process):
 
-    [ODIS_B200_CELL_CFG=0..3] [ODIS_B200_DIRECT_CELL=1] [ODIS_B200_PDL=1] python scripts/step_cfg_timing.py [level] [l_max] [kernel_select]
+    [ODIS_B200_MERGED_SYNTH=0] python scripts/step_cfg_timing.py [level] [l_max] [kernel_select]
 
 Prints one line: device time per step under graph replay (CUDA events), launches per step, the per-launch split from
 odis_step_profiled_sh (events between launches, no graph) and the difference of eta to the baseline selection after 120 steps.
