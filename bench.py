@@ -33,6 +33,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun gives every rank ONE OpenMP thread unless the caller says otherwise; the host-side set-up (grid generator, mesh tables,
+# renumbering, the ranks' table builds) would then crawl on one core each. Every rank takes its share of the cores instead
+# (before libgomp is loaded; nothing here is timed: the device times come from CUDA events).
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
+
 import numpy as np  # noqa: E402
 
 METRIC = "LTE timesteps/sec at grid L8 (FP64), 1-8 B200; achieved HBM GB/s vs peak"
@@ -710,9 +716,19 @@ def synthetic_l10_partitioned(odis, dist, torch, rank, local_rank, world, reduce
     solver = None
     try:
         def make_mesh():
-            if local_rank == 0:
+            if local_rank == 0:                                  # one rank builds, all cores (the others wait at the stage's all-reduce)
+                cores = os.cpu_count() or 8
+                gomp = None
+                try:
+                    import ctypes
+                    gomp = ctypes.CDLL("libgomp.so.1")
+                    gomp.omp_set_num_threads(cores)
+                except OSError:
+                    pass
                 pos, fr, cen = odis.generate_grid(11)
-                odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"]).save(shared)
+                odis.Mesh.from_arrays(pos, fr, cen, ENCELADUS["radius"], threads=cores).save(shared)
+                if gomp is not None:
+                    gomp.omp_set_num_threads(max(1, cores // world))
         stage(make_mesh)
         mesh = stage(lambda: odis.Mesh.load(shared))
         prm = dict(workload_params(mesh), surface=0, shell_thickness=0.0, love_reduct=1.0)
