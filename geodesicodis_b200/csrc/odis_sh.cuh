@@ -64,7 +64,10 @@ constexpr size_t kShXBytes = kShMaxWorld * sizeof(unsigned long long) + 2 * (siz
 // word, tag}, tag = low 32 bits of the epoch. A reader polls the line in its own memory until both tags show the epoch it waits for —
 // each 8-byte half {data, tag} arrives atomically, so a matching tag proves its data — and needs neither a flag nor a fence: the
 // all-reduce costs ONE NVLink crossing instead of three (data + system fence, release flag, the reader's acquire). Lines live in the
-// data region of the block: [2 parities][kShMaxWorld ranks][kShXSlot] x 16 B = 8 KB of its 16 KB.
+// data region of the block: [2 parities][kShMaxWorld ranks][kShXSlot] x 16 B = 8 KB of its 16 KB. The same solver also runs the
+// flag-based pair above once per odis_set_state (the term of the state as set), on the same epoch counter and the same region: its
+// doubles (<= 25 rows = the first 200 B of a parity's 8 KB) can only overwrite lines of an epoch two back, which every rank has
+// consumed (a rank is never more than one epoch ahead), and a line counts only with BOTH tags equal to the awaited epoch.
 struct ShExchange {
     int world, rank;
     unsigned long long* ctl;                 // local: [0] epoch, [1] ticket, [2] set to 1 when a wait gave up, [3] wait limit in clock64 ticks (0: default)
