@@ -174,6 +174,9 @@ def test_partitioned_pipelined_io_matches_synchronous_calls(odis, with_sg):
         assert got[k]["dissipation_avg"] == want[k]["dissipation_avg"], k
     assert sorted(np.concatenate([m[0] for m in maps]).tolist()) == list(range(N))         # the own cells / edges partition the grid
     assert sorted(np.concatenate([m[1] for m in maps]).tolist()) == list(range(F))
+    for k, (cm, em) in enumerate(maps):                                                     # ... exactly as the host-only plan says
+        plan = odis.partition_plan(mesh, k, world)
+        assert np.array_equal(cm, plan["local_cell_ref"][:plan["own_cells"]]) and np.array_equal(em, plan["local_edge_ref"][:plan["own_edges"]])
     if not with_sg:
         ref = odis.Solver(mesh, prm, device=0)
         ref.set_state(*states[-1], iter=5 * (len(states) - 1))
