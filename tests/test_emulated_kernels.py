@@ -103,7 +103,7 @@ def test_racecheck_of_partitioned_runs_under_thread_sanitizer(emulated_library):
     ordered after another rank's (or the host's) write by an epoch flag (system-scope release / acquire = __atomic), an event or a stream
     synchronisation is reported as a data race. Covers the in-kernel halo push / wait (read-after-write on the ghost slots and
     write-after-read on the slots a neighbour may still be reading), the harmonic all-reduce through peer memory, and the engine's host-side
-    waits. (Removing the flag wait from the cell kernel makes this test report the races -- checked by hand.) 2 ranks here; the 4-rank
+    waits, and the pipelined host I/O of partitioned solvers (second stream, page-locked pack buffer, the harmonic sums as LL lines). (Removing the flag wait from the cell kernel makes this test report the races -- checked by hand.) 2 ranks here; the 4-rank
     cases, the 16-bit-id kernel and the overlapped output pipeline were run the same way once, clean."""
     import build_emu
     tsan_rt = subprocess.run(["gcc", "-print-file-name=libtsan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
@@ -115,11 +115,12 @@ def test_racecheck_of_partitioned_runs_under_thread_sanitizer(emulated_library):
         if f.startswith("tsan_report"):
             os.remove(os.path.join(os.path.dirname(lib), f))
     files = ["tests/test_multigpu.py::test_partitioned_run_matches_single_gpu[2]",
-             "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]"]
+             "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]",
+             "tests/test_multigpu.py::test_partitioned_pipelined_io_matches_synchronous_calls"]      # copy stream / page-locked staging vs the steps
     tail = run_gpu_tests_on_the_emulation(lib, emulated_library[1], files, select="", workers=2,
                                           extra_env={"LD_PRELOAD": tsan_rt, "OMP_NUM_THREADS": "1", "ODIS_B200_EMULATED_DEVICES": "2",
                                                      "TSAN_OPTIONS": f"halt_on_error=0:report_signal_unsafe=0:exitcode=0:log_path={report}"})
-    assert int(tail.split(" passed")[0].split()[-1]) == 2, tail
+    assert int(tail.split(" passed")[0].split()[-1]) == 4, tail
     reports = [f for f in os.listdir(os.path.dirname(lib)) if f.startswith("tsan_report")]
     text = "".join(open(os.path.join(os.path.dirname(lib), f)).read() for f in reports)
     assert "WARNING: ThreadSanitizer" not in text, text[:6000]
