@@ -70,14 +70,14 @@ def test_code_written_after_the_last_gpu_run(emulated_library):
 
 
 def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
-    """tests/test_multigpu.py (2 and 4 ranks: halo exchange bit-identical to one device, self-gravity all-reduce through peer memory) with
+    """tests/test_multigpu.py (2, 4 and 8 ranks: halo exchange bit-identical to one device, self-gravity all-reduce through peer memory) with
     every rank's stream running as a thread of its own: the in-kernel flag waits really wait for the neighbour, a missing host-side
     synchronisation or a call that blocks on another rank's progress shows as a time-out or a mismatch. (The same tests run on
     2 and 4 B200s with `-m gpu`.)"""
     tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py", "tests/test_variant_ids16_gpu.py::test_narrow_ids_on_a_partitioned_grid",
                                                               "tests/test_self_gravity_step_gpu.py::test_three_launch_step_on_a_partitioned_grid"],
-                                          extra_env={"ODIS_B200_EMULATED_DEVICES": "4"}, select="", workers=3)
-    assert int(tail.split(" passed")[0].split()[-1]) == 18 and "skipped" not in tail, tail
+                                          extra_env={"ODIS_B200_EMULATED_DEVICES": "8"}, select="", workers=3)
+    assert int(tail.split(" passed")[0].split()[-1]) == 21 and "skipped" not in tail, tail
 
 
 def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):

@@ -15,7 +15,7 @@ def _device_count():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_run_matches_single_gpu(odis, world):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -48,7 +48,7 @@ def test_partitioned_run_matches_single_gpu(odis, world):
 
 
 @pytest.mark.parametrize("stored", [False, True])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_self_gravity_matches_single_gpu(odis, world, stored):
     """Self-gravity term on a partitioned grid: the harmonic sums are all-reduced through peer memory inside the kernels.
     The sums group differently than on one GPU, so fields agree to rounding (1e-10 asserted, BASELINE.json's bar), and every
