@@ -17,6 +17,7 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -282,7 +283,10 @@ template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+namespace simt { inline void slow_fence(); }
+// ODIS_EMU_SLOW_FENCE=R: a system-scope fence takes R scheduler rounds, during which the other threads of the CTA run on (on the
+// hardware it is an NVLink round trip, several microseconds: long enough for the rest of a small kernel to finish)
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); simt::slow_fence(); }
 inline long long clock64() { return (long long)(simt::now_ms() * 1.0e6); }          // "cycles" = nanoseconds: the kernels' spin bounds stay seconds
 
 namespace simt {
@@ -339,6 +343,14 @@ inline void yield(State why) {
     Fiber& f = c.fibers[(size_t)c.current];
     f.state = why;
     simt_switch(&f.sp, c.scheduler_sp);
+}
+inline void slow_fence() {
+    static const int rounds = [] { const char* e = std::getenv("ODIS_EMU_SLOW_FENCE"); return e ? std::atoi(e) : 0; }();
+    if (rounds <= 0 || self_ == nullptr || self_->cta_.current < 0 || self_->cta_.body == nullptr) return;     // host code, or not inside a kernel
+    for (int r = 0; r < rounds; r++) {
+        yield(RUNNABLE);
+        std::this_thread::yield();                  // ... and the CTAs on the other threads (ODIS_EMU_CTA_THREADS)
+    }
 }
 // a fresh context that simt_switch can resume: six callee-saved register slots, the entry address its `ret` jumps to, and a
 // null return address so that the entry function starts with the ABI's stack alignment
@@ -428,6 +440,8 @@ inline void run_cta(const dim3& block, const Closure& body) {
             std::abort();
         }
     }
+    c.current = -1;
+    c.body = nullptr;
 }
 
 inline void run_grid(dim3 grid, dim3 block, const Closure& body) {
@@ -435,6 +449,40 @@ inline void run_grid(dim3 grid, dim3 block, const Closure& body) {
     ThreadState* const me = self_;
     me->gdim = grid;
     me->bdim = block;
+    // ODIS_EMU_CTA_THREADS=K (K > 1): the CTAs of a launch run on K OS threads at once instead of one after another, so that the
+    // thread sanitizer also sees accesses of DIFFERENT CTAs that no ticket / fence / atomic orders (the epoch the last CTA counted
+    // while another CTA's halo warp still read it, round 2, would have been reported). CTAs are claimed in index order from an atomic
+    // counter; a kernel that needs all its CTAs resident at once (grid barrier) still cannot run here with K < grid.
+    static const int cta_threads = [] { const char* e = std::getenv("ODIS_EMU_CTA_THREADS"); return e ? std::atoi(e) : 0; }();
+    const unsigned total = grid.x * grid.y * grid.z;
+    if (cta_threads > 1 && total > 1) {
+        std::atomic<unsigned> next{0};
+        const int dev = current_device;
+        auto worker = [&]() {
+            current_device = dev;
+            ensure_thread_state();
+            ThreadState* const w = self_;
+            w->gdim = grid;
+            w->bdim = block;
+            for (unsigned i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
+                w->bid = uint3{i % grid.x, (i / grid.x) % grid.y, i / (grid.x * grid.y)};
+                run_cta(block, body);
+            }
+            if (w != me) {                                   // a helper thread of this launch: its fiber stacks go with it
+                for (Fiber& f : w->cta_.fibers) std::free(f.stack);
+                std::free(w->dyn);
+                delete w;
+                self_ = nullptr;
+            }
+        };
+        std::vector<std::thread> pool;
+        const int n = std::min<int>(cta_threads, (int)total);
+        for (int k = 1; k < n; k++) pool.emplace_back(worker);
+        worker();
+        for (auto& t : pool) t.join();
+        __atomic_fetch_add(&kernels_run, 1, __ATOMIC_RELAXED);
+        return;
+    }
     for (unsigned z = 0; z < grid.z; z++)
         for (unsigned y = 0; y < grid.y; y++)
             for (unsigned x = 0; x < grid.x; x++) {

@@ -80,6 +80,20 @@ def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
     assert int(tail.split(" passed")[0].split()[-1]) == 21 and "skipped" not in tail, tail
 
 
+def test_partitioned_runs_with_slow_fences_and_concurrent_ctas(emulated_library):
+    """What the plain emulation cannot show — its CTAs run one after another and a fence costs nothing — and the first hardware run of
+    round 2's halo warp did: on a grid whose kernels are shorter than a system-scope fence, the CTA that finished last counted the step
+    before another CTA's halo warp had published, an epoch one too high. ODIS_EMU_CTA_THREADS runs the CTAs of a launch on several OS
+    threads at once, ODIS_EMU_SLOW_FENCE makes __threadfence_system() last that many scheduler rounds (the other threads of the CTA run
+    on meanwhile). With that bug put back, test_partitioned_small_grids_stay_in_step[4-2] fails here (checked by hand); the fixed protocol
+    (the publisher records the epoch) must pass, together with the LL-line all-reduce and the pipelined host I/O."""
+    files = ["tests/test_multigpu.py::test_partitioned_small_grids_stay_in_step", "tests/test_multigpu.py::test_partitioned_pipelined_io_matches_synchronous_calls",
+             "tests/test_multigpu.py::test_partitioned_self_gravity_matches_single_gpu[2-False]", "tests/test_multigpu.py::test_partitioned_run_matches_single_gpu[4]"]
+    tail = run_gpu_tests_on_the_emulation(*emulated_library, files, select="", workers=4,
+                                          extra_env={"ODIS_B200_EMULATED_DEVICES": "4", "ODIS_EMU_CTA_THREADS": "4", "ODIS_EMU_SLOW_FENCE": "40"})
+    assert int(tail.split(" passed")[0].split()[-1]) == 8 and "skipped" not in tail, tail
+
+
 def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
     """The emulation built with -fsanitize=address: device arrays are host heap blocks, so any out-of-range load or store of a
     kernel (padding rows, the last partial block, per-CTA partial buffers with 256 / 512-thread blocks) aborts the run."""
