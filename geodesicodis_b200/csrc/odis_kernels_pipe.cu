@@ -1001,8 +1001,8 @@ int cell_pipe_grid(int n_cells) {
     return n_tiles < cap ? (n_tiles > 0 ? n_tiles : 1) : cap;
 }
 
-// The merged kernel (cell update + grid barrier + solve + synthesis) needs every CTA resident: cooperative launch. Off in host
-// emulation builds (CTAs run one after another there) and with ODIS_B200_MERGED_SYNTH=0 (A/B timing).
+// The merged kernel (cell update + grid barrier + solve + synthesis) needs every CTA resident: cooperative launch. Off with
+// ODIS_B200_MERGED_SYNTH=0 (A/B timing) and in host emulation builds unless the emulation runs all CTAs of a launch at once.
 bool cell_pipe_merged() {
 #ifdef __CUDACC__
     static int v = -1;
@@ -1012,7 +1012,9 @@ bool cell_pipe_merged() {
     }
     return v != 0;
 #else
-    return false;
+    // host emulation: only when it runs every CTA of a launch at once (tests/simt: ODIS_EMU_CTA_THREADS >= the grid) and says so
+    const char* e = std::getenv("ODIS_EMU_MERGED");
+    return e && std::atoi(e) != 0;
 #endif
 }
 

@@ -452,7 +452,7 @@ inline void run_grid(dim3 grid, dim3 block, const Closure& body) {
     // ODIS_EMU_CTA_THREADS=K (K > 1): the CTAs of a launch run on K OS threads at once instead of one after another, so that the
     // thread sanitizer also sees accesses of DIFFERENT CTAs that no ticket / fence / atomic orders (the epoch the last CTA counted
     // while another CTA's halo warp still read it, round 2, would have been reported). CTAs are claimed in index order from an atomic
-    // counter; a kernel that needs all its CTAs resident at once (grid barrier) still cannot run here with K < grid.
+    // counter; a kernel that needs all its CTAs resident at once (grid barrier) can run here when K >= its grid.
     static const int cta_threads = [] { const char* e = std::getenv("ODIS_EMU_CTA_THREADS"); return e ? std::atoi(e) : 0; }();
     const unsigned total = grid.x * grid.y * grid.z;
     if (cta_threads > 1 && total > 1) {
@@ -464,7 +464,8 @@ inline void run_grid(dim3 grid, dim3 block, const Closure& body) {
             ThreadState* const w = self_;
             w->gdim = grid;
             w->bdim = block;
-            for (unsigned i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
+            // (with a thread per CTA every CTA is live at once, claimed one each: what a grid-wide barrier needs)
+            for (unsigned i = next.fetch_add(1); i < total; i = (unsigned)cta_threads >= total ? total : next.fetch_add(1)) {
                 w->bid = uint3{i % grid.x, (i / grid.x) % grid.y, i / (grid.x * grid.y)};
                 run_cta(block, body);
             }

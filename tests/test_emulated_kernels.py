@@ -94,6 +94,18 @@ def test_partitioned_runs_with_slow_fences_and_concurrent_ctas(emulated_library)
     assert int(tail.split(" passed")[0].split()[-1]) == 8 and "skipped" not in tail, tail
 
 
+def test_merged_grid_barrier_kernel_with_a_thread_per_cta(emulated_library):
+    """The default single-GPU self-gravity step is ONE cell launch with a grid-wide barrier inside (cell update + harmonic analysis |
+    barrier | solve + synthesis), which needs every CTA live at once: the emulation runs it when it gives every CTA of a launch an OS
+    thread of its own (ODIS_EMU_CTA_THREADS >= the grid; ODIS_EMU_MERGED=1 tells the library so). Same assertions as on the GPU, plus:
+    2 launches per step, i.e. the merged kernel really ran. Run once by hand under the address sanitizer (clean) and the thread
+    sanitizer (one report: padded lanes of the synthesis loop read eu_out[0] as a dummy while CTA 0 writes it; the value is discarded)."""
+    tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_self_gravity_step_gpu.py::test_three_launch_step_matches_oracle_and_baseline_kernels"],
+                                          select="4-2 or 5-2 or 5-3", workers=3,
+                                          extra_env={"ODIS_EMU_MERGED": "1", "ODIS_EMU_CTA_THREADS": "128", "ODIS_TEST_EXPECT_MERGED": "1"})
+    assert int(tail.split(" passed")[0].split()[-1]) == 3, tail
+
+
 def test_memcheck_of_the_kernels_under_address_sanitizer(emulated_library):
     """The emulation built with -fsanitize=address: device arrays are host heap blocks, so any out-of-range load or store of a
     kernel (padding rows, the last partial block, per-CTA partial buffers with 256 / 512-thread blocks) aborts the run."""
