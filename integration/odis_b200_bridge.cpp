@@ -4,7 +4,9 @@
 #include "gridConstants.h"
 #include "outFiles.h"
 
+#include <cstdlib>
 #include <sstream>
+#include <vector>
 
 namespace odis_bridge {
 
@@ -12,6 +14,8 @@ namespace {
 odis_solver* g_solver = nullptr;
 Globals* g_globals = nullptr;
 Mesh* g_grid = nullptr;
+Group g_group;                       // world > 1: the partitioned solvers (g_solver stays null)
+std::vector<double> g_part;          // one rank's share of a field while the whole is summed
 }  // namespace
 
 void check(Globals* globals, int rc, const char* what) {
@@ -98,9 +102,71 @@ odis_solver* solver(Globals* globals, Mesh* grid) {
 
 void release() {
     if (g_solver) odis_destroy(g_solver);
+    for (int r = 0; r < g_group.world; r++)
+        if (g_group.rank[r] && g_group.rank[r] != g_solver) odis_destroy(g_group.rank[r]);
+    g_group = Group{};
     g_solver = nullptr;
     g_globals = nullptr;
     g_grid = nullptr;
+}
+
+const Group& group(Globals* globals, Mesh* grid) {
+    if (g_group.rank[0] && g_globals == globals && (grid == nullptr || g_grid == grid)) return g_group;
+    const char* e = std::getenv("ODIS_B200_GPUS");
+    const int world = e ? std::atoi(e) : 1;
+    if (world <= 1) {                                   // one GPU: the solver of solver()
+        odis_solver* s = solver(globals, grid);
+        g_group = Group{};
+        g_group.rank[0] = s;
+        return g_group;
+    }
+    if (world > 8) check(globals, ODIS_ERR_ARG, "ODIS_B200_GPUS: at most 8 GPUs");
+    if (globals->advection.Value()) check(globals, ODIS_ERR_UNSUPPORTED, "ODIS_B200_GPUS > 1 with `advection; true` (the nonlinear branch runs on one GPU)");
+    if (grid == nullptr) check(globals, ODIS_ERR_STATE, "looking up the device solvers (no Mesh seen yet)");
+    release();
+    const odis_mesh_view mv = mesh_view(globals, grid);
+    const odis_params p = params(globals);
+    Group g;
+    g.world = world;
+    for (int r = 0; r < world; r++) check(globals, odis_create_partitioned(&mv, &p, /*device*/ r, r, world, &g.rank[r]), "odis_create_partitioned");
+    const size_t bs = (size_t)odis_halo_blob_size();
+    std::vector<unsigned char> blobs(bs * (size_t)world);
+    for (int r = 0; r < world; r++) check(globals, odis_halo_export(g.rank[r], blobs.data() + bs * (size_t)r), "odis_halo_export");
+    for (int r = 0; r < world; r++) check(globals, odis_halo_connect(g.rank[r], blobs.data()), "odis_halo_connect");
+    g_group = g;
+    g_globals = globals;
+    g_grid = grid;
+    return g_group;
+}
+
+void set_state_all(Globals* globals, const Group& g, const double* v, const double* eta, const double* dvdt, const double* detadt, int64_t iter) {
+    for (int r = 0; r < g.world; r++) check(globals, odis_set_state(g.rank[r], v, eta, dvdt, detadt, iter), "odis_set_state");
+}
+
+void step_all(Globals* globals, const Group& g, int32_t nsteps) {
+    // every rank's steps are enqueued before any rank is waited for: the steps in flight wait inside the kernels for their neighbours
+    for (int r = 0; r < g.world; r++) check(globals, odis_step(g.rank[r], nsteps), "odis_step");
+    for (int r = 0; r < g.world; r++) check(globals, odis_synchronize(g.rank[r]), "odis_synchronize");
+}
+
+void get_field_all(Globals* globals, const Group& g, int32_t field, double* out, size_t count) {
+    check(globals, odis_get_field(g.rank[0], field, out), "odis_get_field");
+    if (g.world == 1) return;
+    g_part.resize(count);
+    for (int r = 1; r < g.world; r++) {
+        check(globals, odis_get_field(g.rank[r], field, g_part.data()), "odis_get_field");
+        for (size_t i = 0; i < count; i++) out[i] += g_part[i];       // own entries of rank r, zeros elsewhere
+    }
+}
+
+double dissipation_avg_all(Globals* globals, const Group& g) {
+    double tot = 0.0;
+    for (int r = 0; r < g.world; r++) {
+        double x = 0.0;
+        check(globals, odis_get_dissipation_avg(g.rank[r], &x), "odis_get_dissipation_avg");
+        tot += x;
+    }
+    return tot;
 }
 
 }  // namespace odis_bridge

@@ -18,6 +18,9 @@
 
 #include "odis_b200.h"
 
+#include <cstddef>
+#include <cstdint>
+
 namespace odis_bridge {
 
 // Borrowed view of the reference's Mesh tables (Array2D is row-major, &a(0,0) is the flat pointer).
@@ -32,5 +35,20 @@ odis_solver* solver(Globals* globals, Mesh* grid);
 // rc != ODIS_OK: report `what` + odis_last_error() through the reference's error channel and terminate.
 void check(Globals* globals, int rc, const char* what);
 void release();
+
+// Several GPUs from the reference's one process (the reference has no such notion; the environment variable ODIS_B200_GPUS=N is the
+// switch, input.in stays the reference's): the grid is cut into N parts, one partitioned solver per GPU (devices 0..N-1), halos
+// exchanged by the step kernels through peer memory. `group()` creates them on first use (N = 1: the one solver() above); the
+// helpers below issue a call on every rank and assemble whole-grid results — the ranks fill their own entries of a field and leave
+// zeros elsewhere, the dissipation is the sum of the ranks' shares. Linear branch only (`advection; false`) when N > 1.
+struct Group {
+    int world = 1;
+    odis_solver* rank[8] = {nullptr};
+};
+const Group& group(Globals* globals, Mesh* grid);
+void set_state_all(Globals* globals, const Group& g, const double* v, const double* eta, const double* dvdt, const double* detadt, int64_t iter);
+void step_all(Globals* globals, const Group& g, int32_t nsteps);              // enqueued on every rank, then every rank synchronised
+void get_field_all(Globals* globals, const Group& g, int32_t field, double* out, size_t count);
+double dissipation_avg_all(Globals* globals, const Group& g);
 
 }  // namespace odis_bridge

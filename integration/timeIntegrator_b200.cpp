@@ -67,20 +67,25 @@ int ab3Explicit(Globals* globals, Mesh* grid) {
 
     getInitialConditions(globals, grid, v_t0, dv_dt, p_t0, dp_dt);       // zeros, restart files or the analytical solution
 
-    odis_solver* s = odis_bridge::solver(globals, grid);
-    check(globals, odis_set_state(s, &v_t0(0), &p_t0(0), &dv_dt(0, 0), &dp_dt(0, 0), /*iter*/ 0), "odis_set_state");
+    // one solver, or ODIS_B200_GPUS=N partitioned ones driven from this process (odis_b200_bridge.h)
+    const odis_bridge::Group& dev = odis_bridge::group(globals, grid);
+    odis_bridge::set_state_all(globals, dev, &v_t0(0), &p_t0(0), &dv_dt(0, 0), &dp_dt(0, 0), /*iter*/ 0);
+    if (dev.world > 1) {
+        outstring << "grid partitioned over " << dev.world << " GPUs" << std::endl;
+        Output->Write(OUT_MESSAGE, &outstring);
+    }
 
     // device -> the arrays DumpData reads (what interpolateVelocity / updateEnergy leave behind every step in the
     // reference, src/timeIntegrator.cpp:261-263; here only when somebody looks)
     auto refresh_outputs = [&]() {
-        check(globals, odis_get_field(s, ODIS_FIELD_ETA, &p_t0(0)), "odis_get_field(eta)");
-        if (want_velocity) check(globals, odis_get_field(s, ODIS_FIELD_VELOCITY_EN, &v_avg(0, 0)), "odis_get_field(velocity)");
-        if (want_diss_field) check(globals, odis_get_field(s, ODIS_FIELD_DISSIPATION, &energy_diss(0)), "odis_get_field(dissipation)");
+        odis_bridge::get_field_all(globals, dev, ODIS_FIELD_ETA, &p_t0(0), NODE_NUM);
+        if (want_velocity) odis_bridge::get_field_all(globals, dev, ODIS_FIELD_VELOCITY_EN, &v_avg(0, 0), (size_t)FACE_NUM * 2);
+        if (want_diss_field) odis_bridge::get_field_all(globals, dev, ODIS_FIELD_DISSIPATION, &energy_diss(0), FACE_NUM);
         if (want_cartesian) {       // output-cadence only: the reference's own RBF reconstruction on the host copy of v
-            check(globals, odis_get_field(s, ODIS_FIELD_VELOCITY, &v_t0(0)), "odis_get_field(v)");
+            odis_bridge::get_field_all(globals, dev, ODIS_FIELD_VELOCITY, &v_t0(0), FACE_NUM);
             interpolateVelocityCartRBF(globals, grid, v_xyz, v_t0);
         }
-        check(globals, odis_get_dissipation_avg(s, &total_diss), "odis_get_dissipation_avg");
+        total_diss = odis_bridge::dissipation_avg_all(globals, dev);
     };
     int out_count = 1;
     auto log_and_dump = [&]() {
@@ -102,8 +107,7 @@ int ab3Explicit(Globals* globals, Mesh* grid) {
     while ((double)iter < bound) {
         long n = std::min<long>(out_freq - iter % out_freq, last - iter);
         n = std::min<long>(std::max<long>(n, 1), kChunk);
-        check(globals, odis_step(s, (int32_t)n), "odis_step");
-        check(globals, odis_synchronize(s), "odis_synchronize");
+        odis_bridge::step_all(globals, dev, (int32_t)n);
         iter += n;
         current_time = dt * iter;
         if (iter % out_freq == 0) {
@@ -118,10 +122,10 @@ int ab3Explicit(Globals* globals, Mesh* grid) {
     }
 
     // full state back for the restart files (src/timeIntegrator.cpp:316)
-    check(globals, odis_get_field(s, ODIS_FIELD_VELOCITY, &v_t0(0)), "odis_get_field(v)");
-    check(globals, odis_get_field(s, ODIS_FIELD_ETA, &p_t0(0)), "odis_get_field(eta)");
-    check(globals, odis_get_field(s, ODIS_FIELD_DVDT, &dv_dt(0, 0)), "odis_get_field(dvdt)");
-    check(globals, odis_get_field(s, ODIS_FIELD_DETADT, &dp_dt(0, 0)), "odis_get_field(detadt)");
+    odis_bridge::get_field_all(globals, dev, ODIS_FIELD_VELOCITY, &v_t0(0), FACE_NUM);
+    odis_bridge::get_field_all(globals, dev, ODIS_FIELD_ETA, &p_t0(0), NODE_NUM);
+    odis_bridge::get_field_all(globals, dev, ODIS_FIELD_DVDT, &dv_dt(0, 0), (size_t)FACE_NUM * 3);
+    odis_bridge::get_field_all(globals, dev, ODIS_FIELD_DETADT, &dp_dt(0, 0), (size_t)NODE_NUM * 3);
     writeInitialConditions(globals, grid, v_t0, dv_dt, p_t0, dp_dt);
     Output->Write(OUT_MESSAGE, &outstring);
     odis_bridge::release();

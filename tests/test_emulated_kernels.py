@@ -75,9 +75,10 @@ def test_partitioned_runs_on_concurrent_emulated_devices(emulated_library):
     synchronisation or a call that blocks on another rank's progress shows as a time-out or a mismatch. (The same tests run on
     2 and 4 B200s with `-m gpu`.)"""
     tail = run_gpu_tests_on_the_emulation(*emulated_library, ["tests/test_multigpu.py", "tests/test_variant_ids16_gpu.py::test_narrow_ids_on_a_partitioned_grid",
-                                                              "tests/test_self_gravity_step_gpu.py::test_three_launch_step_on_a_partitioned_grid"],
+                                                              "tests/test_self_gravity_step_gpu.py::test_three_launch_step_on_a_partitioned_grid",
+                                                              "tests/test_surface_hybrid_gpu.py::test_reference_program_with_the_device_time_loop_on_several_gpus"],
                                           extra_env={"ODIS_B200_EMULATED_DEVICES": "8"}, select="", workers=3)
-    assert int(tail.split(" passed")[0].split()[-1]) == 21 and "skipped" not in tail, tail
+    assert int(tail.split(" passed")[0].split()[-1]) == 25 and "skipped" not in tail, tail
 
 
 def test_partitioned_runs_with_slow_fences_and_concurrent_ctas(emulated_library):

@@ -22,12 +22,13 @@ from oracle.refio import read_h5shim, read_records
 pytestmark = pytest.mark.gpu
 
 
-def run_binary(tmp_path, case, exe):
+def run_binary(tmp_path, case, exe, env=None):
     path = os.path.join(ROOT, "oracle", "_ref", f"{exe}_l{int(case['level'])}")
     if not os.path.exists(path):
         pytest.skip(f"{path} not built (needs the reference tree at build time)")
     d = make_run_dir(tmp_path, case)
-    r = subprocess.run([path, "--quiet-restart"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run([path, "--quiet-restart"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, **(env or {})))
     err = open(os.path.join(d, "DATA", "ERROR.txt")).read() if os.path.exists(os.path.join(d, "DATA", "ERROR.txt")) else ""
     assert "TERMINATING" not in err, err[-2000:]
     assert r.returncode == 0, r.stdout[-2000:]
@@ -66,6 +67,22 @@ def test_reference_program_with_the_device_time_loop(tmp_path, name):
         h5 = read_h5shim(data)
         assert np.array_equal(h5["displacement"], case["h5_displacement"])
         assert np.allclose(h5["east velocity"], case["h5_east velocity"], rtol=1e-6, atol=1e-30)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("name", ["l4_ecc_enceladus", "l3_obliq_quadratic"])
+def test_reference_program_with_the_device_time_loop_on_several_gpus(tmp_path, name, world):
+    """The same unmodified reference program with ODIS_B200_GPUS=N: integration/odis_b200_bridge.cpp cuts the reference's own Mesh into N
+    parts and drives N partitioned solvers from the reference's one process (what src/main.cpp:46-64 can reach). Same bars as on one GPU:
+    state and restart arrays bit for bit, dissipation to 1e-12."""
+    from test_multigpu import _device_count
+    if _device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    case = load_case(name)
+    fin, dumps, data = run_binary(tmp_path, case, "odis_hybrid", env={"ODIS_B200_GPUS": str(world)})
+    check_against_case(case, fin, dumps, 1e-13)
+    log = open(os.path.join(data, "OUTPUT.txt")).read()
+    assert log.count("DUMPING DATA AT") == len(case["dump_slices"]) and f"grid partitioned over {world} GPUs" in log
 
 
 @pytest.mark.parametrize("name", ["l3_obliq_quadratic", "l4_full2_lidlove", "l3_ecc_lidmembr"])
